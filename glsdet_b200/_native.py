@@ -1,0 +1,116 @@
+"""ctypes binding of libglsdet_b200.so (the C ABI declared in include/glsdet_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libglsdet_b200.so"
+
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX = range(6)
+OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
+NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU = range(4)
+SE_SLABS = 32
+
+ACT_BY_NAME = {"none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "lrelu": ACT_LRELU}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    """Mirror of struct glsdet_conv_desc."""
+
+    _fields_ = [
+        ("src0", C.c_void_p), ("src0_c", C.c_int32), ("src0_ld", C.c_int32),
+        ("src1", C.c_void_p), ("src1_c", C.c_int32), ("src1_ld", C.c_int32),
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("weight", C.c_void_p), ("out_channels", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32),
+        ("pre_res", C.c_void_p), ("pre_shift", C.c_int32), ("pre_ld", C.c_int32),
+        ("post_res", C.c_void_p), ("post_shift", C.c_int32), ("post_ld", C.c_int32),
+        ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
+        ("out_batch_stride", C.c_int64),
+        ("dec_stride", C.c_float), ("dec_in_w", C.c_float), ("dec_in_h", C.c_float),
+    ]
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/glsdet_b200.h declares
+SIGNATURES = {
+    "glsdet_abi_version": (C.c_int, []),
+    "glsdet_last_error": (C.c_char_p, []),
+    "glsdet_launch_count": (C.c_int64, []),
+    "glsdet_conv_weight_shape": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32)]),
+    "glsdet_conv_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
+    "glsdet_conv_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "glsdet_conv_destroy": (None, [C.c_void_p]),
+    "glsdet_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glsdet_scale_pixel_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_decode_outputs": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glsdet_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "glsdet_nms_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                    C.POINTER(C.c_void_p)]),
+    "glsdet_nms_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "glsdet_nms_destroy": (None, [C.c_void_p]),
+    "glsdet_batched_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glsdet_batched_nms_workspace_bytes": (C.c_int64, [C.c_int32]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once) and declare all prototypes. Raises NativeError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise NativeError(
+            f"{_LIB_PATH} is missing: build it with `python -m glsdet_b200._build` (or __graft_entry__.build()). "
+            "glsdet_b200 has no CPU or PyTorch fallback path.")
+    lib = C.CDLL(os.fspath(_LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.glsdet_abi_version() != 1:
+        raise NativeError("libglsdet_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().glsdet_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what or 'glsdet call'} failed (rc={rc}): {msg}")
+
+
+def stream_ptr(stream=None) -> C.c_void_p:
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return C.c_void_p(0 if t is None else t.data_ptr())

@@ -1,0 +1,545 @@
+// Implicit-GEMM convolution for sm_100a: TMA-fed, tcgen05.mma with the accumulator in TMEM,
+// fused bias / residual / activation / decode epilogue.
+//
+//   out[pixel, n] = epilogue( sum_{src, tap, c} A_src[pixel + tap, c] * W[n, (src, tap, c)] )
+//
+// GEMM view: M = output pixels (a CTA tile is a tile_h x tile_w rectangle of 128 pixels of one image),
+// N = output channels, K = taps * input channels.  Activations are NHWC bf16, so for one tap the A tile
+// is a dense box of the input tensor shifted by (ky-1, kx-1): a single 5-D TMA box load whose
+// out-of-bounds elements are zero-filled by the hardware (that IS the conv padding).  Stride-2 3x3 convs
+// view the input as [B, H/2, 2, W/2, (2), C] so that each tap is again a dense box.  A second source
+// tensor gives torch.cat((a, b), 1) in front of the conv for free (its K range simply follows).
+//
+// Warp roles (256 threads, persistent CTAs, static round-robin tile schedule):
+//   warp 0 lane 0 : TMA producer   (A box + weight box per 64-wide K chunk -> smem ring, mbarrier tx)
+//   warp 1 lane 0 : MMA issuer     (4 x tcgen05.mma M128 x N x K16 per chunk; commit frees the smem slot)
+//   warp 2        : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
+//   warps 4..7    : epilogue       (tcgen05.ld 32 lanes x 16 columns -> registers -> global)
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <new>
+
+#include "../../include/glsdet_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace glsdet {
+
+constexpr int kBlockM = 128;
+constexpr int kChunkK = 64;                 // bf16 elements per K chunk = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * kChunkK * 2;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 256;
+constexpr int kSmemLimit = 232448;          // 227 KB opt-in limit per CTA
+
+struct alignas(64) ConvKParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB;
+  int32_t B, Ho, Wo;
+  int32_t tile_w_log2, tile_h;
+  int32_t tiles_x, tiles_y, n_blocks, total_tiles;
+  int32_t block_n, N;
+  int32_t taps, stride;
+  int32_t chunks0, chunks1;
+  int32_t stages;
+  int32_t tmem_cols;
+  const float* bias;
+  int32_t act;
+  const float* pre_res;
+  int32_t pre_shift, pre_ld;
+  const __nv_bfloat16* post_res;
+  int32_t post_shift, post_ld;
+  void* out;
+  int32_t out_mode, out_ld, out_coff;
+  int64_t out_bs;
+  float dec_stride, dec_in_w, dec_in_h;
+};
+
+struct TileCoord {
+  int b, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile) {
+  TileCoord t;
+  int nb = tile % p.n_blocks;
+  int m = tile / p.n_blocks;
+  int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  int ty = m % p.tiles_y;
+  t.b = m / p.tiles_y;
+  t.x0 = tx << p.tile_w_log2;
+  t.y0 = ty * p.tile_h;
+  t.n0 = nb * p.block_n;
+  return t;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case GLSDET_ACT_SILU: return silu_f(v);
+    case GLSDET_ACT_RELU: return fmaxf(v, 0.0f);
+    case GLSDET_ACT_LRELU: return v > 0.0f ? v : 0.1f * v;
+    case GLSDET_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+// Epilogue for 16 consecutive output channels [n_g, n_g+16) of one output pixel.
+__device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uint32_t (&raw)[16], int b, int oy,
+                                                 int ox, int n_g) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+  const bool full = (n_g + 16 <= p.N);
+
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (full || n_g + j < p.N) v[j] += __ldg(p.bias + n_g + j);
+  }
+  if (p.pre_res != nullptr) {
+    const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
+    const float* r =
+        p.pre_res + ((static_cast<int64_t>(b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + n_g;
+    if (full && (p.pre_ld & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(r + j));
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_g + j < p.N) v[j] += __ldg(r + j);
+    }
+  }
+
+  if (p.act == GLSDET_ACT_YOLOX_BOX) {
+    // models/core/utils_bbox.py:270-305: sigmoid on obj, (xy + grid) * stride, exp(wh) * stride, normalise
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = n_g + j;
+      if (n == 0) v[j] = ((v[j] + static_cast<float>(ox)) * p.dec_stride) / p.dec_in_w;
+      else if (n == 1) v[j] = ((v[j] + static_cast<float>(oy)) * p.dec_stride) / p.dec_in_h;
+      else if (n == 2) v[j] = (expf(v[j]) * p.dec_stride) / p.dec_in_w;
+      else if (n == 3) v[j] = (expf(v[j]) * p.dec_stride) / p.dec_in_h;
+      else v[j] = 1.0f / (1.0f + expf(-v[j]));
+    }
+  } else if (p.act != GLSDET_ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
+  }
+
+  if (p.post_res != nullptr) {
+    const int hs = p.Ho >> p.post_shift, ws = p.Wo >> p.post_shift;
+    const __nv_bfloat16* r = p.post_res +
+        ((static_cast<int64_t>(b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + n_g;
+    if (full && (p.post_ld & 7) == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + h);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[h * 8 + q * 2] += __uint_as_float(w[q] << 16);
+          v[h * 8 + q * 2 + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_g + j < p.N) v[j] += __bfloat162float(r[j]);
+    }
+  }
+
+  if (p.out_mode == GLSDET_OUT_NHWC_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+                       (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + n_g;
+    if (full && ((p.out_ld | p.out_coff) & 7) == 0) {
+      uint4 a, c;
+      a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
+      a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
+      c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
+      c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+      reinterpret_cast<uint4*>(o)[0] = a;
+      reinterpret_cast<uint4*>(o)[1] = c;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_g + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else if (p.out_mode == GLSDET_OUT_NHWC_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+               (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + n_g;
+    if (full && ((p.out_ld | p.out_coff) & 3) == 0 && (p.out_bs & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n_g + j < p.N) o[j] = v[j];
+    }
+  } else {  // NCHW fp32: consecutive lanes are consecutive x -> coalesced per channel
+    const int64_t plane = static_cast<int64_t>(p.Ho) * p.Wo;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+               (static_cast<int64_t>(p.out_coff) + n_g) * plane + static_cast<int64_t>(oy) * p.Wo + ox;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n_g + j < p.N) o[j * plane] = v[j];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int b_bytes = p.block_n * (kChunkK * 2);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + p.stages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k_iters = p.taps * (p.chunks0 + p.chunks1);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA[0]);
+    if (p.chunks1 > 0 || p.stride == 2) tma_prefetch_desc(&p.tmA[1]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(kABytes + b_bytes);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      int kcol = 0;
+      if (p.stride == 1) {
+        for (int src = 0; src < 2; ++src) {
+          const int nch = src ? p.chunks1 : p.chunks0;
+          for (int tap = 0; tap < (nch ? p.taps : 0); ++tap) {
+            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+            for (int ch = 0; ch < nch; ++ch) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+              tma_load_5d(smem_a + s * kABytes, &p.tmA[src], &full_bar[s], ch * kChunkK, t.x0 + dx, 0, t.y0 + dy,
+                          t.b);
+              tma_load_2d(smem_b + s * b_bytes, &p.tmB, &full_bar[s], kcol * kChunkK, t.n0);
+              ++kcol;
+              if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+          }
+        }
+      } else {
+        // stride 2: input row 2*oy + ky - 1 -> (half row, parity); tmA[0] holds even columns, tmA[1] odd ones
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap % 3;
+          const int map = (kx == 1) ? 0 : 1;
+          const int xh = t.x0 + (kx == 0 ? -1 : 0);
+          const int py = (ky == 1) ? 0 : 1;
+          const int yh = t.y0 + (ky == 0 ? -1 : 0);
+          for (int ch = 0; ch < p.chunks0; ++ch) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_5d(smem_a + s * kABytes, &p.tmA[map], &full_bar[s], ch * kChunkK, xh, py, yh, t.b);
+            tma_load_2d(smem_b + s * b_bytes, &p.tmB, &full_bar[s], kcol * kChunkK, t.n0);
+            ++kcol;
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
+    int s = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      mbar_wait(&tempty_bar[as], aph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+      for (int k = 0; k < k_iters; ++k) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + s * kABytes));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + s * b_bytes));
+#pragma unroll
+        for (int kk = 0; kk < kChunkK / 16; ++kk) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
+          umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                    (k > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+      }
+      umma_commit(&tfull_bar[as]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;
+    const int py = r >> p.tile_w_log2;
+    const int px = r & ((1 << p.tile_w_log2) - 1);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int as = it & 1;
+      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
+      const int oy = t.y0 + py, ox = t.x0 + px;
+      const bool valid = (oy < p.Ho) && (ox < p.Wo);
+      for (int c = 0; c < p.block_n; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + static_cast<uint32_t>(c), v);
+        tmem_ld_wait();
+        if (valid && t.n0 + c < p.N) epilogue_store16(p, v, t.b, oy, ox, t.n0 + c);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+}
+
+}  // namespace glsdet
+
+// ===================================================================================== host side
+using namespace glsdet;
+
+struct glsdet_conv {
+  ConvKParams kp;
+  int grid;
+  int smem_bytes;
+};
+
+namespace {
+
+struct ConvGeom {
+  int taps, chunks0, chunks1, n_blocks, block_n, n_pad, k_pad, Ho, Wo;
+};
+
+int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
+  GLSDET_REQUIRE(d != nullptr, "conv: null descriptor");
+  GLSDET_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
+  GLSDET_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
+  GLSDET_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, "conv: bad input size");
+  GLSDET_REQUIRE(d->src0_c > 0 && d->src0_ld >= d->src0_c, "conv: bad src0 channels/pitch");
+  GLSDET_REQUIRE((d->src0_ld % 8) == 0, "conv: src0 pitch must be a multiple of 8 elements (TMA 16-byte strides)");
+  GLSDET_REQUIRE(d->out_channels > 0, "conv: out_channels must be positive");
+  if (d->stride == 2) {
+    GLSDET_REQUIRE(d->ksize == 3 && d->src1 == nullptr, "conv: stride 2 needs ksize 3 and a single source");
+    GLSDET_REQUIRE((d->height % 2) == 0 && (d->width % 2) == 0, "conv: stride 2 needs even height/width");
+  }
+  if (d->src1 != nullptr) {
+    GLSDET_REQUIRE(d->src1_c > 0 && d->src1_ld >= d->src1_c && (d->src1_ld % 8) == 0, "conv: bad src1 channels/pitch");
+  }
+  g->taps = d->ksize * d->ksize;
+  g->chunks0 = (d->src0_c + kChunkK - 1) / kChunkK;
+  g->chunks1 = d->src1 ? (d->src1_c + kChunkK - 1) / kChunkK : 0;
+  g->n_blocks = (d->out_channels + 255) / 256;
+  int per = (d->out_channels + g->n_blocks - 1) / g->n_blocks;
+  g->block_n = (per + 15) / 16 * 16;
+  g->n_pad = g->n_blocks * g->block_n;
+  g->k_pad = g->taps * (g->chunks0 + g->chunks1) * kChunkK;
+  g->Ho = d->height / d->stride;
+  g->Wo = d->width / d->stride;
+  return 0;
+}
+
+int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B, int H, int W, int stride,
+                   int tile_w, int tile_h) {
+  EncodeTiledFn enc = get_encode_tiled();
+  GLSDET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv: source pointer must be 16-byte aligned");
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  const cuuint64_t e = 2;  // bf16
+  if (stride == 1) {
+    dims[0] = c_view; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    strides[0] = static_cast<cuuint64_t>(ld) * e;
+    strides[1] = static_cast<cuuint64_t>(W) * ld * e;
+    strides[2] = static_cast<cuuint64_t>(W) * ld * e;
+    strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
+  } else {
+    dims[0] = c_view; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = static_cast<cuuint64_t>(2) * ld * e;
+    strides[1] = static_cast<cuuint64_t>(W) * ld * e;
+    strides[2] = static_cast<cuuint64_t>(2) * W * ld * e;
+    strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
+  }
+  cuuint32_t box[5] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(tile_w), 1,
+                       static_cast<cuuint32_t>(tile_h), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GLSDET_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int glsdet_conv_weight_shape(const glsdet_conv_desc* desc, int32_t* n_pad, int32_t* k_pad,
+                                        int32_t* block_n) {
+  ConvGeom g;
+  if (int rc = conv_geometry(desc, &g)) return rc;
+  if (n_pad) *n_pad = g.n_pad;
+  if (k_pad) *k_pad = g.k_pad;
+  if (block_n) *block_n = g.block_n;
+  return 0;
+}
+
+extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out_op) {
+  GLSDET_REQUIRE(out_op != nullptr, "conv_create: null output handle");
+  *out_op = nullptr;
+  ConvGeom g;
+  if (int rc = conv_geometry(d, &g)) return rc;
+  GLSDET_REQUIRE(d->src0 && d->weight && d->out, "conv_create: null src0/weight/out pointer");
+  GLSDET_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "conv_create: bad out_mode %d", d->out_mode);
+  GLSDET_REQUIRE(d->act >= 0 && d->act <= GLSDET_ACT_YOLOX_BOX, "conv_create: bad act %d", d->act);
+
+  void* mem = nullptr;
+  if (posix_memalign(&mem, 64, sizeof(glsdet_conv)) != 0 || mem == nullptr) {
+    set_error("conv_create: out of host memory");
+    return 3;
+  }
+  glsdet_conv* op = new (mem) glsdet_conv();
+  ConvKParams& k = op->kp;
+  k.B = d->batch; k.Ho = g.Ho; k.Wo = g.Wo;
+
+  // tile rectangle: 128 pixels, minimise padded area, prefer the squarest (best halo reuse for 3x3)
+  int best_w = 16, best_cost = INT32_MAX;
+  const int cand[5] = {16, 8, 32, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    int tw = cand[i], th = kBlockM / tw;
+    int cost = ((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
+    if (cost < best_cost) { best_cost = cost; best_w = tw; }
+  }
+  int tw_log2 = 0;
+  while ((1 << tw_log2) < best_w) ++tw_log2;
+  k.tile_w_log2 = tw_log2;
+  k.tile_h = kBlockM / best_w;
+  k.tiles_x = (g.Wo + best_w - 1) / best_w;
+  k.tiles_y = (g.Ho + k.tile_h - 1) / k.tile_h;
+  k.n_blocks = g.n_blocks;
+  k.block_n = g.block_n;
+  k.N = d->out_channels;
+  const int64_t total = static_cast<int64_t>(k.tiles_x) * k.tiles_y * k.B * k.n_blocks;
+  if (total > INT32_MAX) { free(mem); set_error("conv_create: too many tiles"); return 2; }
+  k.total_tiles = static_cast<int32_t>(total);
+  k.taps = g.taps; k.stride = d->stride;
+  k.chunks0 = g.chunks0; k.chunks1 = g.chunks1;
+
+  const int stage_bytes = kABytes + g.block_n * kChunkK * 2;
+  int stages = (kSmemLimit - 2048) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  const int k_iters = g.taps * (g.chunks0 + g.chunks1);
+  if (stages > k_iters * 2) stages = k_iters * 2 > 2 ? k_iters * 2 : 2;
+  k.stages = stages;
+  op->smem_bytes = stages * stage_bytes + 1024 + 256;
+  int cols = 32;
+  while (cols < 2 * g.block_n) cols <<= 1;
+  k.tmem_cols = cols;
+
+  k.bias = d->bias; k.act = d->act;
+  k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
+  k.post_res = reinterpret_cast<const __nv_bfloat16*>(d->post_res); k.post_shift = d->post_shift; k.post_ld = d->post_ld;
+  k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
+  k.dec_stride = d->dec_stride; k.dec_in_w = d->dec_in_w; k.dec_in_h = d->dec_in_h;
+
+  int rc = 0;
+  if (d->stride == 1) {
+    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 1, best_w, k.tile_h);
+    if (!rc && d->src1)
+      rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, k.tile_h);
+    else if (!rc) k.tmA[1] = k.tmA[0];
+  } else {
+    const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(d->src0);
+    rc = encode_act_map(&k.tmA[0], s, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w, k.tile_h);
+    if (!rc)
+      rc = encode_act_map(&k.tmA[1], s + d->src0_ld, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w,
+                          k.tile_h);
+  }
+  if (!rc) {
+    EncodeTiledFn enc = get_encode_tiled();
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.k_pad) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(g.block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(weight) failed with CUresult %d", (int)r);
+      rc = 2;
+    }
+  }
+  if (rc) { free(mem); return rc; }
+
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) {
+      free(mem);
+      set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    attr_set[dev] = true;
+  }
+  const int sms = device_sm_count();
+  op->grid = k.total_tiles < sms ? k.total_tiles : sms;
+  *out_op = op;
+  return 0;
+}
+
+extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
+  GLSDET_REQUIRE(op != nullptr, "conv_launch: null op");
+  conv_gemm_kernel<<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
+  return count_launch("conv_gemm_kernel");
+}
+
+extern "C" void glsdet_conv_destroy(glsdet_conv_t* op) {
+  if (op) free(op);
+}

@@ -1,0 +1,134 @@
+"""Python handles for the native operators (thin: build a descriptor, keep tensors alive, launch)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+
+CHUNK_K = 64
+
+
+def fold_bn(conv_weight: torch.Tensor, bn_weight, bn_bias, bn_mean, bn_var, eps: float):
+    """Fold eval-mode BatchNorm into the conv (reference: BaseConv.forward, models/base/baseConv.py:15-16,
+    BatchNorm2d(eps=1e-3) at :12):  y = (conv(x) - mean) / sqrt(var + eps) * gamma + beta."""
+    scale = bn_weight.double() / torch.sqrt(bn_var.double() + eps)
+    w = conv_weight.double() * scale.view(-1, 1, 1, 1)
+    b = bn_bias.double() - bn_mean.double() * scale
+    return w.float(), b.float()
+
+
+def pack_conv_weight(weight: torch.Tensor, splits: Sequence[int], n_pad: int, k_pad: int) -> torch.Tensor:
+    """[N, Cin, kh, kw] fp32 -> bf16 [n_pad, k_pad] in the K order the kernel streams:
+    (source, tap = ky*kw + kx, channel) with every (source, tap) segment zero-padded to 64 channels."""
+    n, cin, kh, kw = weight.shape
+    assert sum(splits) == cin, (splits, cin)
+    segs = []
+    a = 0
+    for c in splits:
+        seg = weight[:, a:a + c].permute(0, 2, 3, 1)  # [N, kh, kw, c]
+        cpad = (c + CHUNK_K - 1) // CHUNK_K * CHUNK_K
+        if cpad != c:
+            seg = torch.nn.functional.pad(seg, (0, cpad - c))
+        segs.append(seg.reshape(n, kh * kw * cpad))
+        a += c
+    packed = torch.cat(segs, dim=1)
+    assert packed.shape[1] == k_pad, (packed.shape, k_pad)
+    out = torch.zeros((n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
+    out[:n] = packed.to(torch.bfloat16)
+    return out.contiguous()
+
+
+class View:
+    """A channel window of an NHWC buffer: tensor [B, H, W, ld] (bf16 or fp32), channels [coff, coff + c)."""
+
+    __slots__ = ("t", "coff", "c")
+
+    def __init__(self, t: torch.Tensor, coff: int = 0, c: Optional[int] = None):
+        assert t.dim() == 4 and t.is_contiguous()
+        self.t, self.coff = t, coff
+        self.c = t.shape[3] - coff if c is None else c
+        assert 0 <= coff and coff + self.c <= t.shape[3]
+
+    @property
+    def ld(self) -> int:
+        return self.t.shape[3]
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.coff * self.t.element_size()
+
+    @property
+    def bhw(self):
+        return tuple(self.t.shape[:3])
+
+
+class ConvOp:
+    """conv(+cat)(+bias)(+residual) -> act (+residual) -> store; see glsdet_conv_desc in include/glsdet_b200.h."""
+
+    def __init__(self, srcs: Sequence[View], weight: torch.Tensor, bias: Optional[torch.Tensor], *, ksize: int,
+                 stride: int = 1, act: int = N.ACT_NONE, out, out_mode: int = N.OUT_NHWC_BF16, out_ld: int = 0,
+                 out_coff: int = 0, out_batch_stride: int = 0, pre_res: Optional[View] = None, pre_shift: int = 0,
+                 post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0)):
+        lib = N.load()
+        assert 1 <= len(srcs) <= 2
+        b, h, w = srcs[0].bhw
+        for s in srcs:
+            assert s.bhw == (b, h, w) and s.t.dtype == torch.bfloat16
+        n_out = weight.shape[0]
+        d = N.ConvDesc()
+        d.src0, d.src0_c, d.src0_ld = srcs[0].ptr, srcs[0].c, srcs[0].ld
+        if len(srcs) == 2:
+            d.src1, d.src1_c, d.src1_ld = srcs[1].ptr, srcs[1].c, srcs[1].ld
+        d.batch, d.height, d.width = b, h, w
+        d.ksize, d.stride = ksize, stride
+        d.out_channels = n_out
+        d.act = act
+        n_pad, k_pad, block_n = C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(lib.glsdet_conv_weight_shape(C.byref(d), C.byref(n_pad), C.byref(k_pad), C.byref(block_n)),
+                "glsdet_conv_weight_shape")
+        self.block_n = block_n.value
+        self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value)
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        d.weight = self.packed.data_ptr()
+        d.bias = 0 if self.bias is None else self.bias.data_ptr()
+        ho, wo = h // stride, w // stride
+        if pre_res is not None:
+            assert pre_res.t.dtype == torch.float32
+            assert pre_res.bhw == (b, ho >> pre_shift, wo >> pre_shift), (pre_res.bhw, b, ho, wo, pre_shift)
+            d.pre_res, d.pre_shift, d.pre_ld = pre_res.ptr, pre_shift, pre_res.ld
+        if post_res is not None:
+            assert post_res.t.dtype == torch.bfloat16
+            assert post_res.bhw == (b, ho >> post_shift, wo >> post_shift)
+            d.post_res, d.post_shift, d.post_ld = post_res.ptr, post_shift, post_res.ld
+        if isinstance(out, View):
+            assert out.bhw == (b, ho, wo) and out.c >= n_out
+            d.out, d.out_ld, d.out_coff = out.t.data_ptr(), out.ld, out.coff
+            d.out_batch_stride = ho * wo * out.ld
+            d.out_mode = N.OUT_NHWC_BF16 if out.t.dtype == torch.bfloat16 else N.OUT_NHWC_F32
+            self._out_t = out.t
+        else:  # raw tensor with explicit addressing (NCHW fp32 logits / [B, A, C] decoded rows)
+            d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
+            d.out_batch_stride = out_batch_stride
+            d.out_mode = out_mode
+            self._out_t = out
+        d.dec_stride, d.dec_in_w, d.dec_in_h = dec
+        self._keep = (srcs, pre_res, post_res)
+        self.desc = d
+        self.handle = C.c_void_p()
+        N.check(lib.glsdet_conv_create(C.byref(d), C.byref(self.handle)), "glsdet_conv_create")
+        self._lib = lib
+        self.flops = 2.0 * b * ho * wo * n_out * sum(s.c for s in srcs) * ksize * ksize
+
+    def launch(self, stream=None):
+        N.check(self._lib.glsdet_conv_launch(self.handle, N.stream_ptr(stream)), "glsdet_conv_launch")
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self._lib.glsdet_conv_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

@@ -1,0 +1,179 @@
+/*
+ * glsdet_b200 — C ABI of the B200-native GLSDet inference hot path
+ * (PAFPN neck + FFA fusion + decoupled head + decode + score filter + class-aware NMS).
+ *
+ * The reference (WUTCM-Lab/GLSDet) is pure Python/PyTorch and has no FFI of its own; the
+ * "plugin boundary" it offers is Python-level (yolox-drone/yolo.py:99-111 imports a module path
+ * and calls YoloBody(num_classes, phi); mmdet builds NECKS/HEADS from the registry,
+ * yolox-ufp/mmdet/models/builder.py:7-45).  This library is what the Python mirrors of those
+ * modules (glsdet_b200/*.py) bind through ctypes.  Each entry point below names the reference
+ * call it replaces.
+ *
+ * Conventions
+ *   - plain C types only: raw device pointers, sizes, a cudaStream_t passed as void*.
+ *   - every function returns 0 on success, non-zero on error; glsdet_last_error() gives the
+ *     message of the last failing call of the calling thread.  No exceptions cross the ABI.
+ *   - all launches are asynchronous on the caller's stream; no internal device synchronisation.
+ *   - the library never allocates or frees caller tensors; op handles own only their descriptors.
+ *   - activations inside the path are NHWC bf16 (channels contiguous), accumulation is fp32.
+ */
+#ifndef GLSDET_B200_H_
+#define GLSDET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLSDET_ABI_VERSION 1
+
+/* activation applied in the conv epilogue (reference: models/base/activation.py:9-17, plus the
+ * decode of models/core/utils_bbox.py:266-305 when the conv is a prediction conv) */
+enum {
+  GLSDET_ACT_NONE = 0,
+  GLSDET_ACT_SILU = 1,       /* x * sigmoid(x)               activation.py:4-7 */
+  GLSDET_ACT_RELU = 2,
+  GLSDET_ACT_LRELU = 3,      /* leaky relu 0.1               activation.py:13 */
+  GLSDET_ACT_SIGMOID = 4,    /* cls logits -> probabilities  utils_bbox.py:270 */
+  GLSDET_ACT_YOLOX_BOX = 5   /* ch0..3 -> (cx,cy,w,h) normalised, ch4 -> sigmoid(obj); utils_bbox.py:270-305 */
+};
+
+/* output layouts of the conv epilogue */
+enum {
+  GLSDET_OUT_NHWC_BF16 = 0,  /* out[b*bs + (y*W+x)*ld + coff + n]  bf16 */
+  GLSDET_OUT_NHWC_F32 = 1,   /* same addressing, fp32 */
+  GLSDET_OUT_NCHW_F32 = 2    /* out[b*bs + (coff+n)*H*W + y*W + x] fp32 (reference tensor layout) */
+};
+
+typedef struct glsdet_conv glsdet_conv_t;
+
+/*
+ * One fused  conv(k x k, stride s, pad (k-1)/2) [+ bias] [+ residual] -> activation [+ residual] -> store.
+ * Replaces BaseConv.forward (yolox-drone/models/base/baseConv.py:15-16) with the BatchNorm folded into
+ * weight/bias, plain nn.Conv2d prediction convs (models/ffa/yolox_ffa.py:43-56), torch.cat of two
+ * inputs in front of a conv (yolox_ffa.py:211,228,241,254; ffa.py:79), the residual adds of
+ * yolox_ffa.py:73 and ffa.py:83, and - for prediction convs - decode_outputs (utils_bbox.py:254-306).
+ */
+typedef struct glsdet_conv_desc {
+  /* input: up to two NHWC bf16 sources of identical B,H,W concatenated along channels */
+  const void* src0;      /* device pointer to channel 0 of the view */
+  int32_t src0_c;        /* channels used from src0 */
+  int32_t src0_ld;       /* pixel pitch of src0 in elements (>= src0_c) */
+  const void* src1;      /* NULL when there is a single source */
+  int32_t src1_c;
+  int32_t src1_ld;
+  int32_t batch, height, width; /* input spatial size */
+  int32_t ksize;         /* 1 or 3 */
+  int32_t stride;        /* 1 or 2 (2 only with ksize 3, one source, even height/width) */
+  /* weights: bf16 [n_pad][k_pad] row-major; K order = (source, tap=ky*3+kx, channel) with every
+   * (source, tap) segment zero-padded to a multiple of 64 channels; see glsdet_conv_weight_shape() */
+  const void* weight;
+  int32_t out_channels;  /* N */
+  const float* bias;     /* [N] fp32 or NULL */
+  int32_t act;           /* GLSDET_ACT_* */
+  /* optional fp32 NHWC tensor added BEFORE the activation, read at (y>>shift, x>>shift): used to add the
+   * low-resolution half of a conv over cat(upsample(a), b) (1x1 convs commute with nearest upsampling) */
+  const float* pre_res;
+  int32_t pre_shift;
+  int32_t pre_ld;
+  /* optional bf16 NHWC tensor added AFTER the activation, read at (y>>shift, x>>shift) */
+  const void* post_res;
+  int32_t post_shift;
+  int32_t post_ld;
+  /* output */
+  void* out;
+  int32_t out_mode;      /* GLSDET_OUT_* */
+  int32_t out_ld;        /* pixel pitch (NHWC modes) or total channel count (NCHW mode) */
+  int32_t out_coff;      /* first output channel inside the destination */
+  int64_t out_batch_stride; /* elements between images in the destination */
+  /* GLSDET_ACT_YOLOX_BOX only: stride of this level and network input size (utils_bbox.py:285,303-304) */
+  float dec_stride, dec_in_w, dec_in_h;
+} glsdet_conv_desc;
+
+/* library / device */
+int glsdet_abi_version(void);
+const char* glsdet_last_error(void);
+/* number of kernels launched by this library since load (all threads); bench.py reports it */
+int64_t glsdet_launch_count(void);
+
+/* rows/cols (n_pad, k_pad) of the packed weight matrix a descriptor needs, and the N tile used */
+int glsdet_conv_weight_shape(const glsdet_conv_desc* desc, int32_t* n_pad, int32_t* k_pad, int32_t* block_n);
+int glsdet_conv_create(const glsdet_conv_desc* desc, glsdet_conv_t** op);
+int glsdet_conv_launch(glsdet_conv_t* op, void* stream);
+void glsdet_conv_destroy(glsdet_conv_t* op);
+
+/* layout converters at the module boundary (reference tensors are NCHW fp32 everywhere) */
+int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                                 int32_t width, int32_t dst_ld, int32_t dst_coff, void* stream);
+int glsdet_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels, int32_t height,
+                                 int32_t width, int32_t src_ld, int32_t src_coff, void* stream);
+
+/*
+ * SE gate of FFA (yolox-drone/models/ffa/ffa.py:5-20,77): partial[b][p][c] = sum over a slab of pixels of
+ * x[b,:,c]; gate[b][c] = 1 + sigmoid(W2 relu(W1 mean)).  Deterministic two-stage reduction.
+ *   x: NHWC bf16 [B, HW, C]; w1: fp32 [C/r][C]; w2: fp32 [C][C/r]; gate: fp32 [B][C];
+ *   scratch: fp32 [B][GLSDET_SE_SLABS][C]
+ */
+#define GLSDET_SE_SLABS 32
+int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld, const float* w1,
+                   const float* w2, int32_t hidden, float* scratch, float* gate, void* stream);
+/*
+ * t = PixelShuffle(2)(x * gate)  (ffa.py:77-78) on NHWC bf16 with x's channels pre-permuted to
+ * (i, j, c) order (done once when the producing conv's weights are packed):
+ *   dst[b, 2y+i, 2x+j, coff + c] = x[b, y, x, (2i+j)*C + c] * gate[b, (2i+j)*C + c]
+ */
+int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
+                               int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
+                               void* stream);
+
+/*
+ * decode_outputs (yolox-drone/models/core/utils_bbox.py:254-306) for callers that hold raw NCHW logits:
+ * levels[l] = fp32 [B, 5+nc, h_l, w_l]; pred = fp32 [B, A, 5+nc] contiguous.
+ */
+int glsdet_decode_outputs(const float* const* levels, const int32_t* heights, const int32_t* widths,
+                          int32_t num_levels, int32_t batch, int32_t num_classes, int32_t in_h, int32_t in_w,
+                          float* pred, void* stream);
+
+/*
+ * Post-processing: non_max_suppression (utils_bbox.py:375-484) without the per-image Python loop or host
+ * synchronisation.  Works on decoded predictions pred[B][A][5+nc] (cx,cy,w,h,obj,cls...).
+ *
+ *   strategy: how class awareness is realised, mirroring torchvision.ops.boxes.batched_nms
+ *     (third-party, torchvision 0.26.0; call site utils_bbox.py:414-419):
+ *       GLSDET_NMS_COORD_TRICK  boxes + label*(max_coord+1) then class-agnostic NMS (_batched_nms_coordinate_trick)
+ *       GLSDET_NMS_PER_CLASS    NMS inside each class on the raw boxes (_batched_nms_vanilla)
+ *       GLSDET_NMS_AUTO_CUDA    trick iff 4*K <= 100000  (torchvision's dispatch for CUDA tensors)
+ *       GLSDET_NMS_AUTO_CPU     trick iff 4*K <= 4000    (torchvision's dispatch for CPU tensors)
+ *   Results are bit-identical to the chosen torchvision strategy when fed identical predictions.
+ *
+ *   det: fp32 [B][max_det][7] rows (x1,y1,x2,y2,obj_conf,class_conf,class_pred) sorted by score desc;
+ *   det_count: int32 [B] number of valid rows per image (rows beyond max_det are dropped, count is clamped);
+ *   keep_index: optional int32 [B][max_det] anchor index of every kept row (NULL to skip).
+ */
+enum {
+  GLSDET_NMS_COORD_TRICK = 0,
+  GLSDET_NMS_PER_CLASS = 1,
+  GLSDET_NMS_AUTO_CUDA = 2,
+  GLSDET_NMS_AUTO_CPU = 3
+};
+typedef struct glsdet_nms glsdet_nms_t;
+/* bytes of device workspace needed for the given problem size */
+int64_t glsdet_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t num_classes);
+int glsdet_nms_create(int32_t batch, int32_t anchors, int32_t num_classes, int32_t max_det, void* workspace,
+                      int64_t workspace_bytes, glsdet_nms_t** op);
+int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf_thres, float nms_thres, int32_t strategy,
+                      float* det, int32_t* det_count, int32_t* keep_index, void* stream);
+void glsdet_nms_destroy(glsdet_nms_t* op);
+
+/* class-aware NMS on caller-supplied boxes (the exact contract of torchvision batched_nms on one image):
+ * boxes fp32 [K][4] xyxy, scores fp32 [K], labels fp32 [K]; keep int32 [K] (first *keep_count valid, score desc) */
+int glsdet_batched_nms(const float* boxes, const float* scores, const float* labels, int32_t k, float nms_thres,
+                       int32_t strategy, void* workspace, int64_t workspace_bytes, int32_t* keep,
+                       int32_t* keep_count, void* stream);
+int64_t glsdet_batched_nms_workspace_bytes(int32_t k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLSDET_B200_H_ */

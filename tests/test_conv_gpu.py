@@ -1,0 +1,171 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv against a plain fp32 PyTorch conv of the same op.
+
+Inputs and weights are rounded to bf16 first so that both sides see identical operands; the remaining
+difference is accumulation order (fp32) and the bf16 rounding of the stored output.
+Tolerances: bf16 outputs 1e-2 relative to the tensor's max magnitude (bf16 has 8 mantissa bits -> 4e-3
+per element), fp32 outputs 1e-4.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _nhwc(t):  # NCHW fp32 -> NHWC bf16 contiguous
+    return t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _act(x, name):
+    if name == "silu":
+        return x * torch.sigmoid(x)
+    if name == "relu":
+        return torch.relu(x)
+    return x
+
+
+CASES = [
+    # name, B, H, W, cins, N, k, stride, act
+    ("1x1_c64_n128", 2, 32, 32, [64], 128, 1, 1, "silu"),
+    ("1x1_c512_n256", 1, 32, 32, [512], 256, 1, 1, "silu"),
+    ("3x3_c128_n128_ragged", 2, 40, 40, [128], 128, 3, 1, "silu"),
+    ("3x3_c64_n64", 1, 64, 64, [64], 64, 3, 1, "silu"),
+    ("3x3s2_c128_n128", 2, 64, 64, [128], 128, 3, 2, "silu"),
+    ("3x3s2_c256_n256_ragged", 1, 40, 40, [256], 256, 3, 2, "silu"),
+    ("cat_1x1_128+128_n256", 2, 32, 32, [128, 128], 256, 1, 1, "relu"),
+    ("1x1_c512_n512", 1, 32, 32, [512], 512, 1, 1, "relu"),
+    ("1x1_c96_n192", 1, 24, 24, [96], 192, 1, 1, "none"),
+    ("3x3_c128_n256", 1, 20, 20, [128], 256, 3, 1, "silu"),
+    ("3x3_c128_n128_big", 2, 256, 256, [128], 128, 3, 1, "silu"),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_conv_matches_torch(case, native_lib, cuda_device):
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    name, B, H, W, cins, n_out, k, stride, act = case
+    g = torch.Generator(device="cpu").manual_seed(hash(name) % (2 ** 31))
+    dev = cuda_device
+    xs = [_bf16r(torch.randn(B, c, H, W, generator=g)).to(dev) for c in cins]
+    cin = sum(cins)
+    w = _bf16r(torch.randn(n_out, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+    bias = torch.randn(n_out, generator=g).to(dev)
+    ref = F.conv2d(torch.cat(xs, 1), w, bias, stride=stride, padding=(k - 1) // 2)
+    ref = _act(ref, act)
+
+    srcs = [View(_nhwc(x)) for x in xs]
+    Ho, Wo = H // stride, W // stride
+    out = torch.full((B, Ho, Wo, n_out), float("nan"), device=dev, dtype=torch.bfloat16)
+    op = ConvOp(srcs, w, bias, ksize=k, stride=stride, act=N.ACT_BY_NAME[act], out=View(out))
+    op.launch()
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all(), "unwritten or non-finite outputs"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 1e-2 * scale, f"{name}: max abs err {err} vs scale {scale}"
+
+
+def test_conv_residuals_and_fp32_out(native_lib, cuda_device):
+    """pre-activation fp32 low-res residual (upsampled), post-activation bf16 residual, fp32 NHWC output."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7)
+    B, H, W, Cin, Nout = 2, 32, 32, 128, 128
+    x = _bf16r(torch.randn(B, Cin, H, W, generator=g)).to(dev)
+    w = _bf16r(torch.randn(Nout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev)
+    bias = torch.randn(Nout, generator=g).to(dev)
+    pre = torch.randn(B, H // 2, W // 2, Nout, generator=g).to(dev)          # NHWC fp32, half resolution
+    post = _bf16r(torch.randn(B, H, W, Nout, generator=g)).to(dev)            # NHWC bf16 values
+    pre_up = F.interpolate(pre.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(x, w, bias) + pre_up
+    ref = ref * torch.sigmoid(ref) + post.permute(0, 3, 1, 2)
+
+    out = torch.full((B, H, W, Nout), float("nan"), device=dev, dtype=torch.float32)
+    op = ConvOp([View(_nhwc(x))], w, bias, ksize=1, act=N.ACT_SILU, out=View(out),
+                pre_res=View(pre.contiguous()), pre_shift=1, post_res=View(post.to(torch.bfloat16).contiguous()),
+                post_shift=0)
+    op.launch()
+    torch.cuda.synchronize()
+    got = out.permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+
+
+def test_conv_channel_windows(native_lib, cuda_device):
+    """Read channels [64,128) of a 192-wide buffer, write channels [32,96) of a 128-wide buffer."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 1, 16, 48
+    buf = _bf16r(torch.randn(B, H, W, 192, generator=g)).to(dev).to(torch.bfloat16)
+    w = _bf16r(torch.randn(64, 64, 3, 3, generator=g) / 24.0).to(dev)
+    out = torch.zeros((B, H, W, 128), device=dev, dtype=torch.bfloat16)
+    op = ConvOp([View(buf, 64, 64)], w, None, ksize=3, act=N.ACT_RELU, out=View(out, 32, 64))
+    op.launch()
+    torch.cuda.synchronize()
+    x = buf[..., 64:128].float().permute(0, 3, 1, 2)
+    ref = torch.relu(F.conv2d(x, w, None, padding=1))
+    got = out[..., 32:96].float().permute(0, 3, 1, 2)
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    assert out[..., :32].abs().max().item() == 0 and out[..., 96:].abs().max().item() == 0
+
+
+def test_pred_conv_nchw_and_decode(native_lib, cuda_device):
+    """Prediction convs: N=10 -> NCHW fp32 logits; N=5 with the fused YOLOX box decode into [B, A, 15] rows."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Cin, nc = 2, 24, 40, 128, 10
+    x = _bf16r(torch.randn(B, Cin, H, W, generator=g)).to(dev)
+    wc = _bf16r(torch.randn(nc, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev)
+    bc = torch.randn(nc, generator=g).to(dev)
+    wr = _bf16r(torch.randn(5, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev)
+    br = torch.randn(5, generator=g).to(dev)
+    xin = View(_nhwc(x))
+
+    logits = torch.full((B, 5 + nc, H, W), float("nan"), device=dev)
+    op = ConvOp([xin], wc, bc, ksize=1, act=N.ACT_NONE, out=logits, out_mode=N.OUT_NCHW_F32, out_ld=5 + nc,
+                out_coff=5, out_batch_stride=(5 + nc) * H * W)
+    op.launch()
+    torch.cuda.synchronize()
+    ref_c = F.conv2d(x, wc, bc)
+    assert (logits[:, 5:] - ref_c).abs().max().item() <= 1e-4 * ref_c.abs().max().item()
+    assert torch.isnan(logits[:, :5]).all()
+
+    A = H * W + 7  # rows of this level sit at offset 3 inside a longer anchor list
+    pred = torch.full((B, A, 5 + nc), float("nan"), device=dev)
+    stride, in_h, in_w = 8.0, H * 8.0, W * 8.0
+    base = pred[:, 3:, :]
+    op2 = ConvOp([xin], wr, br, ksize=1, act=N.ACT_YOLOX_BOX, out=pred, out_mode=N.OUT_NHWC_F32, out_ld=5 + nc,
+                 out_coff=3 * (5 + nc), out_batch_stride=A * (5 + nc), dec=(stride, in_w, in_h))
+    op2.launch()
+    op3 = ConvOp([xin], wc, bc, ksize=1, act=N.ACT_SIGMOID, out=pred, out_mode=N.OUT_NHWC_F32, out_ld=5 + nc,
+                 out_coff=3 * (5 + nc) + 5, out_batch_stride=A * (5 + nc))
+    op3.launch()
+    torch.cuda.synchronize()
+    r = F.conv2d(x, wr, br)  # [B,5,H,W]
+    gy, gx = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    cx = (r[:, 0] + gx) * stride / in_w
+    cy = (r[:, 1] + gy) * stride / in_h
+    bw = torch.exp(r[:, 2]) * stride / in_w
+    bh = torch.exp(r[:, 3]) * stride / in_h
+    ob = torch.sigmoid(r[:, 4])
+    ref_rows = torch.stack([cx, cy, bw, bh, ob], dim=-1).reshape(B, H * W, 5)
+    got_rows = base[:, :H * W, :5]
+    assert torch.allclose(got_rows, ref_rows, rtol=2e-4, atol=2e-5)
+    ref_cls = torch.sigmoid(ref_c).permute(0, 2, 3, 1).reshape(B, H * W, nc)
+    assert torch.allclose(base[:, :H * W, 5:], ref_cls, rtol=2e-4, atol=2e-5)
+    assert torch.isnan(pred[:, :3]).all() and torch.isnan(pred[:, 3 + H * W:]).all()

@@ -1,0 +1,58 @@
+"""Micro-benchmark of single conv ops (CUDA-event timing, L2 flushed between timed launches)."""
+import argparse
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from glsdet_b200 import _native as N  # noqa: E402
+from glsdet_b200.ops import ConvOp, View  # noqa: E402
+
+CASES = {
+    # name: (B, H, W, cins, N, k, stride)
+    "head3x3_s4_n128": (16, 256, 256, [128], 128, 3, 1),
+    "head3x3_s4_n256": (16, 256, 256, [128], 256, 3, 1),
+    "head3x3_s8_n256": (16, 128, 128, [128], 256, 3, 1),
+    "csp1x1_c64_n128": (16, 256, 256, [64], 128, 1, 1),
+    "csp3x3_c64_n64": (16, 256, 256, [64], 64, 3, 1),
+    "ffa1x1_c512_n512": (16, 64, 64, [512], 512, 1, 1),
+    "pred_n10": (16, 256, 256, [128], 10, 1, 1),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--iters", type=int, default=5)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for name in args.cases.split(","):
+        B, H, W, cins, n, k, s = CASES[name]
+        srcs = [View(torch.randn(B, H, W, c, device=dev).to(torch.bfloat16)) for c in cins]
+        w = torch.randn(n, sum(cins), k, k, device=dev) * 0.05
+        bias = torch.randn(n, device=dev)
+        out = torch.empty(B, H // s, W // s, n, device=dev, dtype=torch.bfloat16)
+        op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_SILU, out=View(out))
+        for _ in range(3):
+            op.launch()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(args.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            op.launch()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        t = sorted(ts)[len(ts) // 2]
+        in_bytes = sum(B * H * W * c * 2 for c in cins)
+        out_bytes = out.numel() * 2
+        print(f"{name:22s} {t*1e3:9.1f} us  {op.flops/t/1e9:8.1f} TFLOP/s  "
+              f"{(in_bytes+out_bytes)/t/1e6:8.1f} GB/s (algorithmic)  block_n={op.block_n}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
