@@ -88,10 +88,17 @@ def load():
             f"{_LIB_PATH} is missing: build it with `python -m glsdet_b200._build` (or __graft_entry__.build()). "
             "glsdet_b200 has no CPU or PyTorch fallback path.")
     lib = C.CDLL(os.fspath(_LIB_PATH))
+    missing = []
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
         fn.restype = res
         fn.argtypes = args
+    if missing and not os.environ.get("GLSDET_ALLOW_PARTIAL_LIB"):
+        raise NativeError(f"libglsdet_b200.so lacks symbols declared in include/glsdet_b200.h: {missing}")
     if lib.glsdet_abi_version() != 1:
         raise NativeError("libglsdet_b200.so ABI version mismatch; rebuild")
     _lib = lib

@@ -10,11 +10,13 @@
 // view the input as [B, H/2, 2, W/2, (2), C] so that each tap is again a dense box.  A second source
 // tensor gives torch.cat((a, b), 1) in front of the conv for free (its K range simply follows).
 //
-// Warp roles (256 threads, persistent CTAs, static round-robin tile schedule):
+// Warp roles (384 threads, persistent CTAs, static round-robin tile schedule):
 //   warp 0 lane 0 : TMA producer   (A box + weight box per 64-wide K chunk -> smem ring, mbarrier tx)
 //   warp 1 lane 0 : MMA issuer     (4 x tcgen05.mma M128 x N x K16 per chunk; commit frees the smem slot)
 //   warp 2        : TMEM allocator (2 accumulator stages so the epilogue of tile i overlaps tile i+1)
-//   warps 4..7    : epilogue       (tcgen05.ld 32 lanes x 16 columns -> registers -> global)
+//   warps 4..11   : epilogue       (tcgen05.ld 32 lanes x 16 columns -> registers -> global); a warp may only
+//                                   read TMEM lanes 32*(warp%4)..+31, so two warps share each lane quarter and
+//                                   split the accumulator columns
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -31,7 +33,8 @@ constexpr int kBlockM = 128;
 constexpr int kChunkK = 64;                 // bf16 elements per K chunk = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * kChunkK * 2;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;            // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 constexpr int kSmemLimit = 232448;          // 227 KB opt-in limit per CTA
 
 struct alignas(64) ConvKParams {
@@ -77,7 +80,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case GLSDET_ACT_SILU: return silu_f(v);
+    case GLSDET_ACT_SILU: return silu_f(v);  // MUFU.EX2 + MUFU.RCP, ~1e-6 relative
     case GLSDET_ACT_RELU: return fmaxf(v, 0.0f);
     case GLSDET_ACT_LRELU: return v > 0.0f ? v : 0.1f * v;
     case GLSDET_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
@@ -86,17 +89,18 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 // Epilogue for 16 consecutive output channels [n_g, n_g+16) of one output pixel.
-__device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uint32_t (&raw)[16], int b, int oy,
-                                                 int ox, int n_g) {
+// s_bias: shared-memory copy of the (zero-padded) bias, already offset to channel n_g.
+__device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uint32_t (&raw)[16],
+                                                 const float* s_bias, int b, int oy, int ox, int n_g) {
   float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
   const bool full = (n_g + 16 <= p.N);
-
-  if (p.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (full || n_g + j < p.N) v[j] += __ldg(p.bias + n_g + j);
+  for (int j = 0; j < 16; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(s_bias + j);  // warp-uniform address: smem broadcast
+    v[j] = __uint_as_float(raw[j]) + bv.x;
+    v[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+    v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
+    v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
   }
   if (p.pre_res != nullptr) {
     const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
@@ -191,6 +195,34 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
   }
 }
 
+// Fast path (the bulk of the network): bias + SiLU/ReLU -> bf16 NHWC, 16 channels = two 16-byte stores.
+__device__ __forceinline__ void epilogue_fast16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+                                                __nv_bfloat16* o) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(s_bias + j);
+    v[j] = __uint_as_float(raw[j]) + bv.x;
+    v[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+    v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
+    v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+  }
+  if (silu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  uint4 a, c;
+  a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
+  c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
+  c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+  reinterpret_cast<uint4*>(o)[0] = a;
+  reinterpret_cast<uint4*>(o)[1] = c;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -205,6 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tfull_bar = bars + 2 * kMaxStages;
   uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [n_blocks * block_n], zero padded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -230,6 +263,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
+    s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -309,10 +344,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int e = warp - 4;
+    const int q = e & 3;      // TMEM lane quarter this warp may read (== warp % 4)
+    const int half = e >> 2;  // which half of the accumulator columns
     const int r = q * 32 + lane;
     const int py = r >> p.tile_w_log2;
     const int px = r & ((1 << p.tile_w_log2) - 1);
+    const int n_chunks = p.block_n >> 4;
+    const int c_begin = half ? ((n_chunks + 1) >> 1) : 0;
+    const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
+    const bool fast = (p.out_mode == GLSDET_OUT_NHWC_BF16) && (p.pre_res == nullptr) && (p.post_res == nullptr) &&
+                      (p.act == GLSDET_ACT_SILU || p.act == GLSDET_ACT_RELU) && ((p.N & 15) == 0) &&
+                      (((p.out_ld | p.out_coff) & 7) == 0);
+    const bool silu = (p.act == GLSDET_ACT_SILU);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile);
@@ -323,11 +367,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
       const int oy = t.y0 + py, ox = t.x0 + px;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
-      for (int c = 0; c < p.block_n; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + static_cast<uint32_t>(c), v);
-        tmem_ld_wait();
-        if (valid && t.n0 + c < p.N) epilogue_store16(p, v, t.b, oy, ox, t.n0 + c);
+      if (fast) {
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                              (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
+        int c = c_begin;
+        for (; c + 2 <= c_end; c += 2) {  // two loads in flight per wait
+          uint32_t v0[16], v1[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
+          tmem_ld16(taddr + static_cast<uint32_t>(c * 16 + 16), v1);
+          tmem_ld_wait();
+          if (valid) {
+            if (t.n0 + c * 16 < p.N) epilogue_fast16(v0, s_bias + t.n0 + c * 16, silu, orow + c * 16);
+            if (t.n0 + c * 16 + 16 < p.N) epilogue_fast16(v1, s_bias + t.n0 + c * 16 + 16, silu, orow + c * 16 + 16);
+          }
+        }
+        if (c < c_end) {
+          uint32_t v0[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
+          tmem_ld_wait();
+          if (valid && t.n0 + c * 16 < p.N) epilogue_fast16(v0, s_bias + t.n0 + c * 16, silu, orow + c * 16);
+        }
+      } else {
+        for (int c = c_begin; c < c_end; ++c) {
+          uint32_t v[16];
+          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+          tmem_ld_wait();
+          if (valid && t.n0 + c * 16 < p.N)
+            epilogue_store16(p, v, s_bias + t.n0 + c * 16, t.b, oy, ox, t.n0 + c * 16);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -471,12 +538,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.chunks0 = g.chunks0; k.chunks1 = g.chunks1;
 
   const int stage_bytes = kABytes + g.block_n * kChunkK * 2;
-  int stages = (kSmemLimit - 2048) / stage_bytes;
+  int stages = (kSmemLimit - 2048 - g.n_pad * 4) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   const int k_iters = g.taps * (g.chunks0 + g.chunks1);
   if (stages > k_iters * 2) stages = k_iters * 2 > 2 ? k_iters * 2 : 2;
   k.stages = stages;
-  op->smem_bytes = stages * stage_bytes + 1024 + 256;
+  op->smem_bytes = stages * stage_bytes + 1024 + 256 + g.n_pad * 4;
   int cols = 32;
   while (cols < 2 * g.block_n) cols <<= 1;
   k.tmem_cols = cols;

@@ -1,0 +1,349 @@
+"""ORACLE (test infrastructure only) - CPU fp32 restatement of the reference's GLSDet hot path.
+
+This file restates, in plain functional PyTorch on the CPU, what WUTCM-Lab/GLSDet computes on the path
+neck -> FFA -> decoupled head -> decode -> score filter -> class-aware NMS, driven by nothing but a
+state_dict with the reference's keys.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import it; the product (glsdet_b200/) never does.
+
+Pinning: tests/golden/make_golden.py imports the REAL reference from /root/reference (with the two
+import-time shims of SURVEY.md section 0.2) in the build container, runs it on seeded inputs and commits the
+input/output vectors under tests/golden/; tests/test_oracle_cpu.py checks this restatement against those
+vectors.  The reference's own test-suite has no golden vectors for this path.
+
+Every function cites the reference lines it follows (paths relative to /root/reference/yolox-drone/).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import nms_oracle
+
+StateDict = Dict[str, torch.Tensor]
+BN_EPS = 1e-3  # models/base/baseConv.py:12
+
+
+def _act(x: torch.Tensor, act: str) -> torch.Tensor:
+    # models/base/activation.py:4-17
+    if act == "silu":
+        return x * torch.sigmoid(x)
+    if act == "relu":
+        return torch.relu(x)
+    if act == "lrelu":
+        return F.leaky_relu(x, 0.1)
+    raise AttributeError(f"Unsupported act type: {act}")
+
+
+def base_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int = 1, act: str = "silu") -> torch.Tensor:
+    """act(bn(conv(x))): models/base/baseConv.py:6-16 (pad=(k-1)//2, conv bias=False, BN eps 1e-3, eval mode)."""
+    w = sd[p + ".conv.weight"]
+    k = w.shape[-1]
+    y = F.conv2d(x, w, None, stride=stride, padding=(k - 1) // 2)
+    y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],
+                     sd[p + ".bn.bias"], training=False, eps=BN_EPS)
+    return _act(y, act)
+
+
+def _count_blocks(sd: StateDict, p: str) -> int:
+    n = 0
+    while f"{p}.m.{n}.conv1.conv.weight" in sd:
+        n += 1
+    return n
+
+
+def csp_layer(sd: StateDict, p: str, x: torch.Tensor, shortcut: bool = False, act: str = "silu") -> torch.Tensor:
+    """models/ffa/darknet.py:66-112 (CSPLayer) with Bottleneck :43-63 (expansion 1.0 inside CSP, :87)."""
+    x1 = base_conv(sd, p + ".conv1", x, act=act)
+    x2 = base_conv(sd, p + ".conv2", x, act=act)
+    for j in range(_count_blocks(sd, p)):
+        y = base_conv(sd, f"{p}.m.{j}.conv2", base_conv(sd, f"{p}.m.{j}.conv1", x1, act=act), act=act)
+        x1 = y + x1 if shortcut else y  # use_add = shortcut and cin == cout (:57); cin == cout inside CSP
+    return base_conv(sd, p + ".conv3", torch.cat((x1, x2), dim=1), act=act)
+
+
+def _up2(x: torch.Tensor) -> torch.Tensor:
+    return F.interpolate(x, scale_factor=2, mode="nearest")
+
+
+def pafpn_neck(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "backbone") -> List[torch.Tensor]:
+    """models/ffa/yolox_ffa.py:196-261 after the backbone call (:197-198): feats = (dark2, dark3, dark4, dark5)."""
+    feat0, feat1, feat2, feat3 = feats
+    P5 = base_conv(sd, f"{p}.lateral_conv0", feat3)                          # :203
+    x = csp_layer(sd, f"{p}.C3_p4", torch.cat([_up2(P5), feat2], 1))         # :207-215
+    P4 = base_conv(sd, f"{p}.reduce_conv1", x)                               # :220
+    P3_out = csp_layer(sd, f"{p}.C3_p3", torch.cat([_up2(P4), feat1], 1))    # :224-232
+    d = base_conv(sd, f"{p}.bu_conv2", P3_out, stride=2)                     # :237
+    P4_out = csp_layer(sd, f"{p}.C3_n3", torch.cat([d, P4], 1))              # :241-245
+    d = base_conv(sd, f"{p}.bu_conv1", P4_out, stride=2)                     # :250
+    P5_out = csp_layer(sd, f"{p}.C3_n4", torch.cat([d, P5], 1))              # :254-258
+    return [feat0, P3_out, P4_out, P5_out]                                   # :261
+
+
+def se_block(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+    """models/ffa/ffa.py:5-20: x * sigmoid(W2 relu(W1 avgpool(x))), Linear layers without bias."""
+    b, c = x.shape[:2]
+    y = x.mean(dim=(2, 3))
+    y = torch.sigmoid(F.linear(torch.relu(F.linear(y, sd[p + ".fc.0.weight"])), sd[p + ".fc.2.weight"]))
+    return x * y.view(b, c, 1, 1)
+
+
+def ffa(sd: StateDict, p: str, bottom: torch.Tensor, top: torch.Tensor) -> torch.Tensor:
+    """models/ffa/ffa.py:74-85 (all five BaseConvs use ReLU, :27-66)."""
+    t = base_conv(sd, p + ".scale", top, act="relu")
+    t = base_conv(sd, p + ".create_content_extractor.0", t, act="relu")
+    t = base_conv(sd, p + ".create_content_extractor.1", t, act="relu")
+    t = t + se_block(sd, p + ".se1", t)
+    t = F.pixel_shuffle(t, 2)
+    b = torch.cat((bottom, t), 1)
+    b = base_conv(sd, p + ".create_text_extractor.0", b, act="relu")
+    b = base_conv(sd, p + ".conv3", b, act="relu")
+    return t + b
+
+
+def yolox_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -> List[torch.Tensor]:
+    """models/ffa/yolox_ffa.py:58-118: FFA on (P3_out, P4_out), csp on dark2 (+ upsampled FFA output), stems on
+    the other three; level 0 uses tower index 3, level k>0 uses k-1 (:84-87); output cat([reg, obj, cls], 1)."""
+    zz = ffa(sd, f"{p}.ftt", inputs[1], inputs[2])                           # :66
+    proc = []
+    for k, x in enumerate(inputs):
+        if k == 0:
+            proc.append(csp_layer(sd, f"{p}.csp", x))                        # :70
+        else:
+            proc.append(base_conv(sd, f"{p}.stems.{k - 1}", x))              # :72
+    proc[0] = proc[0] + _up2(zz)                                             # :73
+    outs = []
+    for k, x in enumerate(proc):
+        i = 3 if k == 0 else k - 1
+        cf = base_conv(sd, f"{p}.cls_convs.{i}.1", base_conv(sd, f"{p}.cls_convs.{i}.0", x))
+        cls_out = F.conv2d(cf, sd[f"{p}.cls_preds.{i}.weight"], sd[f"{p}.cls_preds.{i}.bias"])
+        rf = base_conv(sd, f"{p}.reg_convs.{i}.1", base_conv(sd, f"{p}.reg_convs.{i}.0", x))
+        reg_out = F.conv2d(rf, sd[f"{p}.reg_preds.{i}.weight"], sd[f"{p}.reg_preds.{i}.bias"])
+        obj_out = F.conv2d(rf, sd[f"{p}.obj_preds.{i}.weight"], sd[f"{p}.obj_preds.{i}.bias"])
+        outs.append(torch.cat([reg_out, obj_out, cls_out], 1))               # :116
+    return outs
+
+
+def neck_head(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """YoloBody.forward minus the CSPDarknet call (yolox_ffa.py:275-284)."""
+    with torch.no_grad():
+        return yolox_head(sd, pafpn_neck(sd, feats))
+
+
+# ------------------------------------------------------------------------------------------ backbone (upstream)
+def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
+    """models/ffa/darknet.py:10-37,115-195.  Upstream of the measured path; restated only so that synthetic
+    feature maps with the right statistics can be produced where /root/reference is absent."""
+    with torch.no_grad():
+        x = torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), dim=1)
+        x = base_conv(sd, f"{p}.stem.conv", x)
+        outs = []
+        for name in ("dark2", "dark3", "dark4", "dark5"):
+            x = base_conv(sd, f"{p}.{name}.0", x, stride=2)
+            if name == "dark5":
+                x = base_conv(sd, f"{p}.{name}.1.conv1", x)
+                x = torch.cat([x] + [F.max_pool2d(x, ks, 1, ks // 2) for ks in (5, 9, 13)], dim=1)
+                x = base_conv(sd, f"{p}.{name}.1.conv2", x)
+                x = csp_layer(sd, f"{p}.{name}.2", x, shortcut=False)
+            else:
+                x = csp_layer(sd, f"{p}.{name}.1", x, shortcut=True)
+            outs.append(x)
+        return outs
+
+
+# ------------------------------------------------------------------------------------------ decode
+def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """models/core/utils_bbox.py:254-306.  Returns a contiguous [B, A, 5+nc] tensor (the reference returns the
+    same values as a permuted view)."""
+    hw = [o.shape[-2:] for o in outputs]
+    out = torch.cat([o.flatten(start_dim=2) for o in outputs], dim=2).permute(0, 2, 1).contiguous()
+    out[:, :, 4:] = torch.sigmoid(out[:, :, 4:])
+    grids, strides = [], []
+    for h, w in hw:
+        gy, gx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        grids.append(torch.stack((gx, gy), 2).view(1, -1, 2))
+        strides.append(torch.full((1, h * w, 1), input_shape[0] / h))       # :285 (H-stride for both axes)
+    grids = torch.cat(grids, dim=1).to(out.dtype)
+    strides = torch.cat(strides, dim=1).to(out.dtype)
+    out[..., :2] = (out[..., :2] + grids) * strides
+    out[..., 2:4] = torch.exp(out[..., 2:4]) * strides
+    out[..., [0, 2]] = out[..., [0, 2]] / input_shape[1]
+    out[..., [1, 3]] = out[..., [1, 3]] / input_shape[0]
+    return out
+
+
+# ------------------------------------------------------------------------------------------ post-processing
+def yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image):
+    """models/core/utils_bbox.py:8-33 (numpy, float64 intermediates exactly as numpy promotes them)."""
+    box_yx = box_xy[..., ::-1]
+    box_hw = box_wh[..., ::-1]
+    input_shape = np.array(input_shape)
+    image_shape = np.array(image_shape)
+    if letterbox_image:
+        new_shape = np.round(image_shape * np.min(input_shape / image_shape))
+        offset = (input_shape - new_shape) / 2.0 / input_shape
+        scale = input_shape / new_shape
+        box_yx = (box_yx - offset) * scale
+        box_hw = box_hw * scale
+    box_mins = box_yx - (box_hw / 2.0)
+    box_maxes = box_yx + (box_hw / 2.0)
+    boxes = np.concatenate([box_mins[..., 0:1], box_mins[..., 1:2], box_maxes[..., 0:1], box_maxes[..., 1:2]], axis=-1)
+    boxes = boxes * np.concatenate([image_shape, image_shape], axis=-1)
+    return boxes
+
+
+def filter_candidates(prediction: torch.Tensor, num_classes: int, conf_thres: float):
+    """utils_bbox.py:381-412 for the whole batch: cxcywh -> xyxy, class max, score threshold, compaction.
+    Returns per image (det [K,7] float32 numpy, anchor_index [K] int64)."""
+    pred = prediction.clone()
+    corner = pred.new_empty(pred.shape)
+    corner[:, :, 0] = pred[:, :, 0] - pred[:, :, 2] / 2
+    corner[:, :, 1] = pred[:, :, 1] - pred[:, :, 3] / 2
+    corner[:, :, 2] = pred[:, :, 0] + pred[:, :, 2] / 2
+    corner[:, :, 3] = pred[:, :, 1] + pred[:, :, 3] / 2
+    pred[:, :, :4] = corner[:, :, :4]
+    res = []
+    for image_pred in pred:
+        class_conf, class_pred = torch.max(image_pred[:, 5:5 + num_classes], 1, keepdim=True)
+        mask = (image_pred[:, 4] * class_conf[:, 0] >= conf_thres)
+        det = torch.cat((image_pred[:, :5], class_conf, class_pred.float()), 1)[mask]
+        res.append((det.numpy().astype(np.float32), torch.nonzero(mask)[:, 0].numpy()))
+    return res
+
+
+def non_max_suppression(prediction: torch.Tensor, num_classes: int, input_shape, image_shape, letterbox_image,
+                        conf_thres: float = 0.5, nms_thres: float = 0.4, strategy: str = "auto_cpu",
+                        correct_boxes: bool = True, return_index: bool = False):
+    """utils_bbox.py:375-484.  `strategy` names which torchvision batched_nms branch is restated (see
+    nms_oracle.batched_nms).  With correct_boxes=False rows stay (x1,y1,x2,y2,obj,cls_conf,cls) in network
+    coordinates (what the device produces before the host-side yolo_correct_boxes)."""
+    output = []
+    index = []
+    for det, anchor_idx in filter_candidates(prediction, num_classes, conf_thres):
+        keep = nms_oracle.batched_nms(det[:, :4], det[:, 4] * det[:, 5], det[:, 6], nms_thres, strategy)
+        out = det[keep]
+        index.append(anchor_idx[keep])
+        if correct_boxes:
+            box_xy, box_wh = (out[:, 0:2] + out[:, 2:4]) / 2, out[:, 2:4] - out[:, 0:2]
+            out[:, :4] = yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+        output.append(out)
+    return (output, index) if return_index else output
+
+
+# ------------------------------------------------------------------------------------------ synthetic weights
+def p0_state_dict_shapes(num_classes: int, phi: str) -> Dict[str, tuple]:
+    """Shapes of every state_dict entry of models/ffa/yolox_ffa.py YoloBody(num_classes, phi)."""
+    depth = {"tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
+    width = {"tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
+    shapes: Dict[str, tuple] = {}
+
+    def bc(p, cin, cout, k):
+        shapes[p + ".conv.weight"] = (cout, cin, k, k)
+        for n in ("weight", "bias", "running_mean", "running_var"):
+            shapes[f"{p}.bn.{n}"] = (cout,)
+        shapes[p + ".bn.num_batches_tracked"] = ()
+
+    def csp(p, cin, cout, n):
+        hid = int(cout * 0.5)
+        bc(p + ".conv1", cin, hid, 1)
+        bc(p + ".conv2", cin, hid, 1)
+        bc(p + ".conv3", 2 * hid, cout, 1)
+        for j in range(n):
+            bc(f"{p}.m.{j}.conv1", hid, hid, 1)
+            bc(f"{p}.m.{j}.conv2", hid, hid, 3)
+
+    base = int(width * 64)
+    bdep = max(round(depth * 3), 1)
+    bb = "backbone.backbone"
+    bc(f"{bb}.stem.conv", 12, base, 3)
+    for name, cin, cout, n in (("dark2", base, base * 2, bdep), ("dark3", base * 2, base * 4, bdep * 3),
+                               ("dark4", base * 4, base * 8, bdep * 3)):
+        bc(f"{bb}.{name}.0", cin, cout, 3)
+        csp(f"{bb}.{name}.1", cout, cout, n)
+    bc(f"{bb}.dark5.0", base * 8, base * 16, 3)
+    bc(f"{bb}.dark5.1.conv1", base * 16, base * 8, 1)
+    bc(f"{bb}.dark5.1.conv2", base * 32, base * 16, 1)
+    csp(f"{bb}.dark5.2", base * 16, base * 16, bdep)
+
+    c0, c1, c2 = int(256 * width), int(512 * width), int(1024 * width)
+    n = round(3 * depth)
+    bc("backbone.lateral_conv0", c2, c1, 1)
+    csp("backbone.C3_p4", 2 * c1, c1, n)
+    bc("backbone.reduce_conv1", c1, c0, 1)
+    csp("backbone.C3_p3", 2 * c0, c0, n)
+    bc("backbone.bu_conv2", c0, c0, 3)
+    csp("backbone.C3_n3", 2 * c0, c1, n)
+    bc("backbone.bu_conv1", c1, c1, 3)
+    csp("backbone.C3_n4", 2 * c1, c2, n)
+
+    hc = int(256 * width)
+    csp("head.csp", int(0.5 * 256 * width), hc, round(3 * 0.75))
+    f = "head.ftt"
+    bc(f + ".scale", 2 * hc, 4 * hc, 1)
+    bc(f + ".create_content_extractor.0", 4 * hc, 4 * hc, 1)
+    bc(f + ".create_content_extractor.1", 4 * hc, 4 * hc, 1)
+    bc(f + ".create_text_extractor.0", 2 * hc, 2 * hc, 1)
+    bc(f + ".conv3", 2 * hc, hc, 1)
+    shapes[f + ".se1.fc.0.weight"] = (4 * hc // 16, 4 * hc)
+    shapes[f + ".se1.fc.2.weight"] = (4 * hc, 4 * hc // 16)
+    for i, cin in enumerate((c0, c1, c2)):
+        bc(f"head.stems.{i}", cin, hc, 1)
+    for i in range(4):
+        for br in ("cls_convs", "reg_convs"):
+            bc(f"head.{br}.{i}.0", hc, hc, 3)
+            bc(f"head.{br}.{i}.1", hc, hc, 3)
+        for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
+            shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
+            shapes[f"head.{name}.{i}.bias"] = (co,)
+    return shapes
+
+
+def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str = "kaiming") -> StateDict:
+    """Random-init weights for the P0 architecture.
+
+    flavour "reference": what train.py does - default PyTorch init then weights_init(normal, 0.02)
+        (models/ffa/yolox_losses.py:402-421): conv weights N(0, 0.02), BN gamma N(1, 0.02), beta 0, stats (0, 1).
+        Activations collapse towards zero through the depth (gain < 1 per layer), so it exercises the kernels
+        poorly and every anchor scores ~0.25.
+    flavour "kaiming": variance-preserving conv init, randomised BN statistics, prediction biases at the YOLOX
+        prior (-log((1-p)/p), p = 0.01) and wider prediction weights, so that feature maps stay O(1) at every
+        depth and scores/boxes have a realistic spread.  Used for parity at full depth and for the benchmark.
+    """
+    g = torch.Generator().manual_seed(seed)
+    sd: StateDict = {}
+    for k, shp in p0_state_dict_shapes(num_classes, phi).items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith(".conv.weight"):
+            fan_in = shp[1] * shp[2] * shp[3]
+            std = 0.02 if flavour == "reference" else math.sqrt(2.0 / fan_in)
+            sd[k] = torch.randn(shp, generator=g) * std
+        elif ".bn." in k:
+            if flavour == "reference":
+                sd[k] = {"weight": 1.0 + 0.02 * torch.randn(shp, generator=g), "bias": torch.zeros(shp),
+                         "running_mean": torch.zeros(shp), "running_var": torch.ones(shp)}[k.rsplit(".", 1)[1]]
+            else:
+                sd[k] = {"weight": 1.0 + 0.1 * torch.randn(shp, generator=g),
+                         "bias": 0.1 * torch.randn(shp, generator=g),
+                         "running_mean": 0.1 * torch.randn(shp, generator=g),
+                         "running_var": 0.5 + torch.rand(shp, generator=g)}[k.rsplit(".", 1)[1]]
+        elif ".fc." in k:
+            sd[k] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
+        elif k.endswith("_preds.0.weight") or "_preds." in k and k.endswith(".weight"):
+            fan_in = shp[1]
+            std = 0.02 if flavour == "reference" else 2.0 * math.sqrt(1.0 / fan_in)
+            sd[k] = torch.randn(shp, generator=g) * std
+        elif "_preds." in k and k.endswith(".bias"):
+            if flavour == "reference":
+                bound = 1.0 / math.sqrt(1.0)
+                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * 0.05 * bound
+            elif "reg_preds" in k:
+                sd[k] = 0.5 * torch.randn(shp, generator=g)
+            else:
+                sd[k] = torch.full(shp, -math.log((1 - 0.01) / 0.01)) + 0.2 * torch.randn(shp, generator=g)
+        else:
+            raise KeyError(k)
+    return sd
