@@ -1,0 +1,298 @@
+// Bandwidth-bound pieces of the path: layout converters at the module boundary, the SE gate of FFA,
+// gate * PixelShuffle, and the stand-alone decode of raw NCHW logits.  All 128-bit vectorised on the
+// NHWC side, coalesced on the NCHW side (shared-memory transpose).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/glsdet_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace glsdet {
+
+constexpr int kTC = 64;  // channels per transpose tile (64 bf16 = 128 bytes on the NHWC side)
+constexpr int kTP = 32;  // pixels per transpose tile   (32 fp32 = 128 bytes on the NCHW side)
+
+// [B, C, HW] fp32 -> [B, HW, ld] bf16 (channels coff..coff+C)
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                           int C, int HW, int ld, int coff) {
+  __shared__ float tile[kTC][kTP + 1];
+  const int p0 = blockIdx.x * kTP, c0 = blockIdx.y * kTC, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* s = src + static_cast<int64_t>(b) * C * HW;
+#pragma unroll
+  for (int i = 0; i < kTC / 8; ++i) {
+    const int c = c0 + warp * (kTC / 8) + i;
+    const int p = p0 + lane;
+    tile[warp * (kTC / 8) + i][lane] = (c < C && p < HW) ? __ldg(s + static_cast<int64_t>(c) * HW + p) : 0.0f;
+  }
+  __syncthreads();
+  const int pl = threadIdx.x >> 3, cv = threadIdx.x & 7;  // 32 pixels x 8 vectors of 8 channels
+  const int p = p0 + pl, c = c0 + cv * 8;
+  if (p < HW && c < C) {
+    __nv_bfloat16* o = dst + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
+    if (c + 8 <= C && ((ld | coff) & 7) == 0) {
+      uint4 v;
+      v.x = pack_bf16x2(tile[cv * 8 + 0][pl], tile[cv * 8 + 1][pl]);
+      v.y = pack_bf16x2(tile[cv * 8 + 2][pl], tile[cv * 8 + 3][pl]);
+      v.z = pack_bf16x2(tile[cv * 8 + 4][pl], tile[cv * 8 + 5][pl]);
+      v.w = pack_bf16x2(tile[cv * 8 + 6][pl], tile[cv * 8 + 7][pl]);
+      *reinterpret_cast<uint4*>(o) = v;
+    } else {
+      for (int j = 0; j < 8 && c + j < C; ++j) o[j] = __float2bfloat16_rn(tile[cv * 8 + j][pl]);
+    }
+  }
+}
+
+// [B, HW, ld] bf16 (channels coff..coff+C) -> [B, C, HW] fp32
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                           int C, int HW, int ld, int coff) {
+  __shared__ float tile[kTC][kTP + 1];
+  const int p0 = blockIdx.x * kTP, c0 = blockIdx.y * kTC, b = blockIdx.z;
+  const int pl = threadIdx.x >> 3, cv = threadIdx.x & 7;
+  const int p = p0 + pl, c = c0 + cv * 8;
+  if (p < HW && c < C) {
+    const __nv_bfloat16* s = src + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
+    if (c + 8 <= C && ((ld | coff) & 7) == 0) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(s));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        tile[cv * 8 + 2 * q][pl] = __uint_as_float(w[q] << 16);
+        tile[cv * 8 + 2 * q + 1][pl] = __uint_as_float(w[q] & 0xFFFF0000u);
+      }
+    } else {
+      for (int j = 0; j < 8; ++j) tile[cv * 8 + j][pl] = (c + j < C) ? __bfloat162float(s[j]) : 0.0f;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* d = dst + static_cast<int64_t>(b) * C * HW;
+#pragma unroll
+  for (int i = 0; i < kTC / 8; ++i) {
+    const int cc = c0 + warp * (kTC / 8) + i;
+    const int pp = p0 + lane;
+    if (cc < C && pp < HW) d[static_cast<int64_t>(cc) * HW + pp] = tile[warp * (kTC / 8) + i][lane];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- SE gate
+// stage 1: per (image, slab of pixels) channel sums, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ scratch,
+                                                         int HW, int C, int ld) {
+  extern __shared__ float red[];  // [rows_par][C]
+  const int slab = blockIdx.x, b = blockIdx.y;
+  const int per = (HW + GLSDET_SE_SLABS - 1) / GLSDET_SE_SLABS;
+  const int p_begin = slab * per;
+  const int p_end = min(HW, p_begin + per);
+  const int nvec = C >> 3;
+  const int lanes = min(nvec, 256);
+  const int rows_par = 256 / lanes;
+  const int row = threadIdx.x / lanes;
+  const int vl = threadIdx.x % lanes;
+  if (row < rows_par) {
+    for (int vec = vl; vec < nvec; vec += lanes) {
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = p_begin + row; p < p_end; p += rows_par) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * HW + p) * ld) + vec);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc[2 * q] += __uint_as_float(w[q] << 16);
+          acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[row * C + vec * 8 + j] = acc[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.0f;
+    for (int r = 0; r < rows_par; ++r) s += red[r * C + c];
+    scratch[(static_cast<int64_t>(b) * GLSDET_SE_SLABS + slab) * C + c] = s;
+  }
+}
+
+// stage 2: mean -> FC -> ReLU -> FC -> sigmoid; gate = 1 + y  (x + x*y == x*(1+y), ffa.py:77)
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ scratch, const float* __restrict__ w1,
+                                                    const float* __restrict__ w2, float* __restrict__ gate, int HW,
+                                                    int C, int hidden) {
+  extern __shared__ float sm[];  // mean[C] | hid[hidden]
+  float* mean = sm;
+  float* hid = sm + C;
+  const int b = blockIdx.x;
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.0f;
+    for (int k = 0; k < GLSDET_SE_SLABS; ++k) s += scratch[(static_cast<int64_t>(b) * GLSDET_SE_SLABS + k) * C + c];
+    mean[c] = s * inv;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int h = warp; h < hidden; h += 8) {
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) s += __ldg(w1 + static_cast<int64_t>(h) * C + c) * mean[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) hid[h] = fmaxf(s, 0.0f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float s = 0.0f;
+    for (int h = 0; h < hidden; ++h) s += __ldg(w2 + static_cast<int64_t>(c) * hidden + h) * hid[h];
+    gate[static_cast<int64_t>(b) * C + c] = 1.0f + 1.0f / (1.0f + expf(-s));
+  }
+}
+
+// dst[b, 2y+i, 2x+j, coff + c] = x[b, y, x, (2i+j)*Cout + c] * gate[b, (2i+j)*Cout + c]
+__global__ void __launch_bounds__(256) scale_shuffle_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gate,
+                                                            __nv_bfloat16* __restrict__ dst, int B, int H, int W,
+                                                            int Cout, int ld, int coff) {
+  const int vec_per_pix = (4 * Cout) >> 3;
+  const int64_t total = static_cast<int64_t>(B) * H * W * vec_per_pix;
+  const int cvn = Cout >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(i % vec_per_pix);
+    int64_t pix = i / vec_per_pix;
+    const int xx = static_cast<int>(pix % W);
+    pix /= W;
+    const int yy = static_cast<int>(pix % H);
+    const int b = static_cast<int>(pix / H);
+    const int ij = vec / cvn, cv = vec % cvn;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<int64_t>(b) * 4 * Cout + vec * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<int64_t>(b) * 4 * Cout + vec * 8) + 1);
+    uint4 o;
+    o.x = pack_bf16x2(__uint_as_float(v.x << 16) * g0.x, __uint_as_float(v.x & 0xFFFF0000u) * g0.y);
+    o.y = pack_bf16x2(__uint_as_float(v.y << 16) * g0.z, __uint_as_float(v.y & 0xFFFF0000u) * g0.w);
+    o.z = pack_bf16x2(__uint_as_float(v.z << 16) * g1.x, __uint_as_float(v.z & 0xFFFF0000u) * g1.y);
+    o.w = pack_bf16x2(__uint_as_float(v.w << 16) * g1.z, __uint_as_float(v.w & 0xFFFF0000u) * g1.w);
+    const int oy = 2 * yy + (ij >> 1), ox = 2 * xx + (ij & 1);
+    __nv_bfloat16* d = dst + ((static_cast<int64_t>(b) * 2 * H + oy) * (2 * W) + ox) * ld + coff + cv * 8;
+    *reinterpret_cast<uint4*>(d) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- decode
+struct DecodeLevels {
+  const float* ptr[8];
+  int h[8], w[8], a_off[8];
+  int num;
+};
+
+// models/core/utils_bbox.py:254-306 - one thread per (image, anchor)
+__global__ void __launch_bounds__(256) decode_kernel(DecodeLevels lv, int B, int A, int nch, float in_h, float in_w,
+                                                     float* __restrict__ pred) {
+  const int64_t total = static_cast<int64_t>(B) * A;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i % A);
+    const int b = static_cast<int>(i / A);
+    int l = 0;
+    while (l + 1 < lv.num && a >= lv.a_off[l + 1]) ++l;
+    const int hw = lv.h[l] * lv.w[l];
+    const int cell = a - lv.a_off[l];
+    const int gy = cell / lv.w[l], gx = cell % lv.w[l];
+    const float stride = in_h / static_cast<float>(lv.h[l]);  // utils_bbox.py:285 (H-stride on both axes)
+    const float* s = lv.ptr[l] + static_cast<int64_t>(b) * nch * hw + cell;
+    float* o = pred + i * nch;
+    o[0] = ((__ldg(s) + static_cast<float>(gx)) * stride) / in_w;
+    o[1] = ((__ldg(s + hw) + static_cast<float>(gy)) * stride) / in_h;
+    o[2] = (expf(__ldg(s + 2 * static_cast<int64_t>(hw))) * stride) / in_w;
+    o[3] = (expf(__ldg(s + 3 * static_cast<int64_t>(hw))) * stride) / in_h;
+    for (int c = 4; c < nch; ++c) o[c] = 1.0f / (1.0f + expf(-__ldg(s + c * static_cast<int64_t>(hw))));
+  }
+}
+
+}  // namespace glsdet
+
+using namespace glsdet;
+
+extern "C" int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int32_t channels,
+                                            int32_t height, int32_t width, int32_t dst_ld, int32_t dst_coff,
+                                            void* stream) {
+  GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0 && height > 0 && width > 0, "nchw_to_nhwc: bad arguments");
+  GLSDET_REQUIRE(dst_coff >= 0 && dst_coff + channels <= dst_ld, "nchw_to_nhwc: channel window exceeds pitch");
+  const int HW = height * width;
+  dim3 grid((HW + kTP - 1) / kTP, (channels + kTC - 1) / kTC, batch);
+  GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nchw_to_nhwc: grid too large");
+  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), channels, HW, dst_ld, dst_coff);
+  return count_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int glsdet_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels,
+                                            int32_t height, int32_t width, int32_t src_ld, int32_t src_coff,
+                                            void* stream) {
+  GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0 && height > 0 && width > 0, "nhwc_to_nchw: bad arguments");
+  GLSDET_REQUIRE(src_coff >= 0 && src_coff + channels <= src_ld, "nhwc_to_nchw: channel window exceeds pitch");
+  const int HW = height * width;
+  dim3 grid((HW + kTP - 1) / kTP, (channels + kTC - 1) / kTC, batch);
+  GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nhwc_to_nchw: grid too large");
+  nhwc_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, channels, HW, src_ld, src_coff);
+  return count_launch("nhwc_to_nchw_kernel");
+}
+
+extern "C" int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld,
+                              const float* w1, const float* w2, int32_t hidden, float* scratch, float* gate,
+                              void* stream) {
+  GLSDET_REQUIRE(x && w1 && w2 && scratch && gate, "se_gate: null pointer");
+  GLSDET_REQUIRE(batch > 0 && hw > 0 && channels > 0 && hidden > 0, "se_gate: bad sizes");
+  GLSDET_REQUIRE((channels % 8) == 0 && (x_ld % 8) == 0 && x_ld >= channels, "se_gate: channels/pitch must be multiples of 8");
+  const int nvec = channels / 8;
+  const int lanes = nvec < 256 ? nvec : 256;
+  const int rows_par = 256 / lanes;
+  const size_t smem1 = static_cast<size_t>(rows_par) * channels * sizeof(float);
+  GLSDET_REQUIRE(smem1 <= 48 * 1024, "se_gate: too many channels (%d)", channels);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  se_partial_kernel<<<dim3(GLSDET_SE_SLABS, batch), 256, smem1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scratch,
+                                                                     hw, channels, x_ld);
+  if (int rc = count_launch("se_partial_kernel")) return rc;
+  const size_t smem2 = static_cast<size_t>(channels + hidden) * sizeof(float);
+  se_fc_kernel<<<batch, 256, smem2, st>>>(scratch, w1, w2, gate, hw, channels, hidden);
+  return count_launch("se_fc_kernel");
+}
+
+extern "C" int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
+                                          int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
+                                          void* stream) {
+  GLSDET_REQUIRE(x && gate && dst, "scale_pixel_shuffle: null pointer");
+  GLSDET_REQUIRE(batch > 0 && height > 0 && width > 0 && out_channels > 0, "scale_pixel_shuffle: bad sizes");
+  GLSDET_REQUIRE((out_channels % 8) == 0 && (dst_ld % 8) == 0 && (dst_coff % 8) == 0 && dst_coff + out_channels <= dst_ld,
+                 "scale_pixel_shuffle: channels/pitch/offset must be multiples of 8");
+  const int64_t total = static_cast<int64_t>(batch) * height * width * (4 * out_channels / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  scale_shuffle_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), gate, reinterpret_cast<__nv_bfloat16*>(dst), batch, height, width,
+      out_channels, dst_ld, dst_coff);
+  return count_launch("scale_shuffle_kernel");
+}
+
+extern "C" int glsdet_decode_outputs(const float* const* levels, const int32_t* heights, const int32_t* widths,
+                                     int32_t num_levels, int32_t batch, int32_t num_classes, int32_t in_h,
+                                     int32_t in_w, float* pred, void* stream) {
+  GLSDET_REQUIRE(levels && heights && widths && pred, "decode_outputs: null pointer");
+  GLSDET_REQUIRE(num_levels > 0 && num_levels <= 8, "decode_outputs: 1..8 levels supported (got %d)", num_levels);
+  GLSDET_REQUIRE(batch > 0 && num_classes > 0 && in_h > 0 && in_w > 0, "decode_outputs: bad sizes");
+  DecodeLevels lv;
+  int a = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    GLSDET_REQUIRE(levels[l] && heights[l] > 0 && widths[l] > 0, "decode_outputs: bad level %d", l);
+    lv.ptr[l] = levels[l]; lv.h[l] = heights[l]; lv.w[l] = widths[l]; lv.a_off[l] = a;
+    a += heights[l] * widths[l];
+  }
+  lv.num = num_levels;
+  const int64_t total = static_cast<int64_t>(batch) * a;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lv, batch, a, 5 + num_classes, static_cast<float>(in_h), static_cast<float>(in_w), pred);
+  return count_launch("decode_kernel");
+}

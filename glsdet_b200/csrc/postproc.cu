@@ -1,0 +1,636 @@
+// Post-processing of the GLSDet path on the device, without host synchronisation:
+//   score filter (obj * max cls >= conf)  ->  warp-ballot compaction  ->  per-image bitonic sort of
+//   (class, score desc, anchor) keys  ->  per-(image, class) greedy NMS with 64-wide IoU bitmasks  ->
+//   rank of every kept box among all kept boxes of its image (binary searches)  ->  [K,7] rows, score desc.
+//
+// Replaces non_max_suppression (yolox-drone/models/core/utils_bbox.py:375-484) and the torchvision
+// batched_nms it calls (:414-419).  Bit-exactness contract (see include/glsdet_b200.h): same keep set and
+// order as the chosen torchvision strategy, all box arithmetic in IEEE binary32 without FMA contraction.
+//
+// Greedy NMS decomposes exactly by class when boxes of different classes cannot overlap:
+//   - per-class strategy: by definition;
+//   - coordinate trick: boxes are shifted by label * (max_coord + 1); classes are disjoint whenever the
+//     smallest coordinate is >= -0.5 (far inside the guard band of max_coord + 1).  Otherwise the image
+//     falls back to one class-agnostic segment on the shifted boxes, which is the literal algorithm.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <new>
+
+#include "../../include/glsdet_b200.h"
+#include "common.h"
+
+namespace glsdet {
+
+constexpr int kSortChunk = 4096;    // keys sorted per CTA in shared memory
+constexpr int kSortThreads = 512;
+constexpr int kNmsThreads = 256;
+constexpr int kKeptSmem = 1536;     // kept boxes cached in shared memory per segment
+constexpr int kMaxClasses = 256;    // 8 label bits in the sort key
+constexpr uint64_t kPadKey = ~0ull;
+
+// key = [63:56] label (0 when the image runs class-agnostic) | [55:24] ~score bits | [23:0] anchor index
+__device__ __forceinline__ uint64_t make_key(uint32_t label, float score, uint32_t idx) {
+  return (static_cast<uint64_t>(label) << 56) | (static_cast<uint64_t>(~__float_as_uint(score)) << 24) | idx;
+}
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return static_cast<uint32_t>(k & 0xFFFFFFu); }
+__device__ __forceinline__ float key_score(uint64_t k) { return __uint_as_float(~static_cast<uint32_t>(k >> 24)); }
+
+__device__ __forceinline__ uint32_t float_order_bits(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float order_bits_float(uint32_t e) {
+  return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
+}
+
+struct Source {
+  // decoded predictions [B][A][nch] (cx, cy, w, h, obj, cls...), or caller-supplied boxes/scores/labels
+  const float* pred;
+  int A, nch, nc;
+  const float* boxes;
+  const float* scores;
+  const float* labels;
+};
+
+struct Cand {
+  float4 box;   // x1 y1 x2 y2 in network coordinates
+  float obj, cls_conf, label_f;
+  int label;
+};
+
+template <bool kFromPred>
+__device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
+  Cand c;
+  if (kFromPred) {
+    const float* r = s.pred + (static_cast<int64_t>(b) * s.A + idx) * s.nch;
+    const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
+    // utils_bbox.py:381-386: corner = centre -/+ size / 2
+    c.box.x = __fsub_rn(cx, __fdiv_rn(w, 2.0f));
+    c.box.y = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
+    c.box.z = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
+    c.box.w = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+    c.obj = __ldg(r + 4);
+    float best = __ldg(r + 5);
+    int arg = 0;
+    for (int k = 1; k < s.nc; ++k) {  // utils_bbox.py:398 torch.max: first maximal index
+      const float v = __ldg(r + 5 + k);
+      if (v > best) { best = v; arg = k; }
+    }
+    c.cls_conf = best;
+    c.label = arg;
+    c.label_f = static_cast<float>(arg);
+  } else {
+    c.box = __ldg(reinterpret_cast<const float4*>(s.boxes) + idx);
+    c.obj = __ldg(s.scores + idx);
+    c.cls_conf = 1.0f;
+    c.label_f = __ldg(s.labels + idx);
+    c.label = static_cast<int>(c.label_f);
+  }
+  return c;
+}
+
+struct Work {
+  int B, cap, P, nc;
+  int32_t* cand_count;   // [B]
+  uint32_t* max_bits;    // [B]
+  uint32_t* min_bits;    // [B]
+  int32_t* seg_start;    // [B][nc+1]
+  int32_t* seg_kept;     // [B][nc]
+  float* cand_score;     // [B][cap]
+  int32_t* cand_idx;     // [B][cap]
+  uint8_t* cand_label;   // [B][cap]
+  uint64_t* keys;        // [B][P]
+  uint64_t* kept_key;    // [B][cap]
+  float4* kept_box;      // [B][cap]   spill of the kept list beyond shared memory
+};
+
+struct ImageMode {
+  bool use_offsets;   // coordinate trick
+  bool per_class;     // class-segmented NMS
+  float offset_scale; // max_coord + 1
+};
+
+__device__ __forceinline__ ImageMode image_mode(const Work& w, int b, int strategy) {
+  ImageMode m;
+  const int n = w.cand_count[b];
+  bool trick;
+  if (strategy == GLSDET_NMS_COORD_TRICK) trick = true;
+  else if (strategy == GLSDET_NMS_PER_CLASS) trick = false;
+  else if (strategy == GLSDET_NMS_AUTO_CUDA) trick = (4ll * n <= 100000);
+  else trick = (4ll * n <= 4000);
+  m.use_offsets = trick;
+  const float maxc = order_bits_float(w.max_bits[b]);
+  const float minc = order_bits_float(w.min_bits[b]);
+  m.offset_scale = __fadd_rn(maxc, 1.0f);
+  // class separation needs a positive gap after rounding: min >= -0.5 leaves 0.5, and offsets below 2^21 keep
+  // every rounding error under 0.125
+  m.per_class = !trick || (n > 0 && minc >= -0.5f && static_cast<float>(w.nc) * m.offset_scale < 2097152.0f);
+  return m;
+}
+
+__global__ void reset_kernel(Work w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w.B) {
+    w.cand_count[i] = 0;
+    w.max_bits[i] = 0u;
+    w.min_bits[i] = 0xFFFFFFFFu;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- filter
+template <bool kFromPred>
+__global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float conf_thres) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < s.A; base += gridDim.x * blockDim.x) {
+    const int a = base + threadIdx.x;
+    bool pass = false;
+    Cand c;
+    float score = 0.0f;
+    if (a < s.A) {
+      c = load_cand<kFromPred>(s, b, a);
+      score = kFromPred ? __fmul_rn(c.obj, c.cls_conf) : c.obj;
+      pass = kFromPred ? (score >= conf_thres) : true;  // utils_bbox.py:403 (>=)
+    }
+    const uint32_t mask = __ballot_sync(0xffffffffu, pass);
+    if (mask == 0u) continue;
+    int slot0 = 0;
+    if (lane == 0) slot0 = atomicAdd(&w.cand_count[b], __popc(mask));
+    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+    float hi = -INFINITY, lo = INFINITY;
+    if (pass) {
+      const int slot = slot0 + __popc(mask & ((1u << lane) - 1u));
+      const int64_t o = static_cast<int64_t>(b) * w.cap + slot;
+      w.cand_score[o] = score;
+      w.cand_idx[o] = a;
+      w.cand_label[o] = static_cast<uint8_t>(c.label);
+      hi = fmaxf(fmaxf(c.box.x, c.box.y), fmaxf(c.box.z, c.box.w));
+      lo = fminf(fminf(c.box.x, c.box.y), fminf(c.box.z, c.box.w));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if (lane == 0) {
+      atomicMax(&w.max_bits[b], float_order_bits(hi));
+      atomicMin(&w.min_bits[b], float_order_bits(lo));
+    }
+  }
+}
+
+__device__ __forceinline__ int sort_extent(int n) {
+  int p = kSortChunk;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
+  const int b = blockIdx.y;
+  const int n = w.cand_count[b];
+  const int pb = sort_extent(n);
+  const ImageMode m = image_mode(w, b, strategy);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pb; i += gridDim.x * blockDim.x) {
+    uint64_t k = kPadKey;
+    if (i < n) {
+      const int64_t o = static_cast<int64_t>(b) * w.cap + i;
+      k = make_key(m.per_class ? w.cand_label[o] : 0u, w.cand_score[o], static_cast<uint32_t>(w.cand_idx[o]));
+    }
+    w.keys[static_cast<int64_t>(b) * w.P + i] = k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bitonic sort
+__device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
+  if ((a > b) == asc) { const uint64_t t = a; a = b; b = t; }
+}
+
+// sorts every kSortChunk-sized chunk (all levels k <= kSortChunk), direction alternating by global index
+__global__ void __launch_bounds__(kSortThreads) bitonic_local_sort_kernel(Work w) {
+  __shared__ uint64_t sk[kSortChunk];
+  const int b = blockIdx.y;
+  const int pb = sort_extent(w.cand_count[b]);
+  const int base = blockIdx.x * kSortChunk;
+  if (base >= pb) return;
+  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P + base;
+  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = g[i];
+  __syncthreads();
+  for (int k = 2; k <= kSortChunk; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kSortChunk / 2; t += kSortThreads) {
+        const int i = 2 * j * (t / j) + (t % j);
+        const bool asc = (((base + i) & k) == 0);
+        cmp_swap(sk[i], sk[i + j], asc);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) g[i] = sk[i];
+}
+
+// one compare-exchange step (level k, distance j >= kSortChunk) over the whole padded array
+__global__ void __launch_bounds__(256) bitonic_global_step_kernel(Work w, int k, int j) {
+  const int b = blockIdx.y;
+  const int pb = sort_extent(w.cand_count[b]);
+  if (k > pb) return;
+  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < pb / 2; t += gridDim.x * blockDim.x) {
+    const int i = 2 * j * (t / j) + (t % j);
+    const bool asc = ((i & k) == 0);
+    uint64_t a = g[i], c = g[i + j];
+    if ((a > c) == asc) { g[i] = c; g[i + j] = a; }
+  }
+}
+
+// finishes level k inside each chunk (distances kSortChunk/2 .. 1)
+__global__ void __launch_bounds__(kSortThreads) bitonic_local_merge_kernel(Work w, int k) {
+  __shared__ uint64_t sk[kSortChunk];
+  const int b = blockIdx.y;
+  const int pb = sort_extent(w.cand_count[b]);
+  const int base = blockIdx.x * kSortChunk;
+  if (k > pb || base >= pb) return;
+  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P + base;
+  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = g[i];
+  __syncthreads();
+  for (int j = kSortChunk >> 1; j > 0; j >>= 1) {
+    for (int t = threadIdx.x; t < kSortChunk / 2; t += kSortThreads) {
+      const int i = 2 * j * (t / j) + (t % j);
+      const bool asc = (((base + i) & k) == 0);
+      cmp_swap(sk[i], sk[i + j], asc);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) g[i] = sk[i];
+}
+
+// ---------------------------------------------------------------------------------------------- segments
+__global__ void segment_bounds_kernel(Work w, int strategy) {
+  const int b = blockIdx.x;
+  const int n = w.cand_count[b];
+  const ImageMode m = image_mode(w, b, strategy);
+  const uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
+  for (int c = threadIdx.x; c <= w.nc; c += blockDim.x) {
+    int pos;
+    if (!m.per_class) {
+      pos = (c == 0) ? 0 : n;
+    } else {
+      const uint64_t target = static_cast<uint64_t>(c) << 56;  // first key with label >= c
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (g[mid] < target) lo = mid + 1; else hi = mid;
+      }
+      pos = (c == w.nc) ? n : lo;
+    }
+    w.seg_start[b * (w.nc + 1) + c] = pos;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- NMS
+// torchvision nms_kernel_impl: ovr = inter / (area_i + area_j - inter); suppress iff ovr > thr
+__device__ __forceinline__ bool iou_exceeds(const float4& a, float aarea, const float4& b, float barea, float thr,
+                                            bool thr_nonneg) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float ww = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+  const float hh = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(ww, hh);
+  if (inter <= 0.0f && thr_nonneg) return false;  // 0/x = 0 or NaN: never > thr when thr >= 0
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
+  return ovr > thr;
+}
+
+template <bool kFromPred>
+__global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work w, float thr, int strategy) {
+  __shared__ float4 kbox[kKeptSmem];
+  __shared__ float karea[kKeptSmem];
+  __shared__ float4 cbox[64];
+  __shared__ float carea[64];
+  __shared__ uint64_t ckey[64];
+  __shared__ unsigned long long cmask[64];
+  __shared__ unsigned long long sup_prev;
+  __shared__ unsigned long long kept_bits;
+  __shared__ int kept_n;
+
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const int s0 = w.seg_start[b * (w.nc + 1) + seg];
+  const int s1 = w.seg_start[b * (w.nc + 1) + seg + 1];
+  const int n = s1 - s0;
+  const int tid = threadIdx.x;
+  if (n <= 0) {
+    if (tid == 0) w.seg_kept[b * w.nc + seg] = 0;
+    return;
+  }
+  const ImageMode m = image_mode(w, b, strategy);
+  const bool thr_nonneg = (thr >= 0.0f);
+  const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
+  float4* gk_box = w.kept_box + static_cast<int64_t>(b) * w.cap + s0;
+  uint64_t* gk_key = w.kept_key + static_cast<int64_t>(b) * w.cap + s0;
+  if (tid == 0) kept_n = 0;
+  __syncthreads();
+
+  for (int c0 = 0; c0 < n; c0 += 64) {
+    const int mcnt = min(64, n - c0);
+    if (tid < 64) {
+      cmask[tid] = 0ull;
+      if (tid < mcnt) {
+        const uint64_t key = keys[c0 + tid];
+        const Cand c = load_cand<kFromPred>(s, b, static_cast<int>(key_idx(key)));
+        float4 bx = c.box;
+        if (m.use_offsets) {
+          // boxes.py _batched_nms_coordinate_trick: offsets = idxs * (max_coordinate + 1); boxes + offsets
+          const float off = __fmul_rn(c.label_f, m.offset_scale);
+          bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
+          bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+        }
+        cbox[tid] = bx;
+        carea[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+        ckey[tid] = key;
+      }
+    }
+    if (tid == 0) sup_prev = 0ull;
+    __syncthreads();
+
+    // phase 1: which candidates of this chunk are suppressed by an already kept box
+    {
+      const int kn = kept_n;
+      unsigned long long sup = 0ull;
+      for (int k = tid; k < kn; k += kNmsThreads) {
+        float4 kb;
+        float ka;
+        if (k < kKeptSmem) { kb = kbox[k]; ka = karea[k]; }
+        else {
+          kb = gk_box[k];
+          ka = __fmul_rn(__fsub_rn(kb.z, kb.x), __fsub_rn(kb.w, kb.y));
+        }
+        for (int j = 0; j < mcnt; ++j)
+          if (iou_exceeds(kb, ka, cbox[j], carea[j], thr, thr_nonneg)) sup |= (1ull << j);
+      }
+      uint32_t lo = static_cast<uint32_t>(sup), hi = static_cast<uint32_t>(sup >> 32);
+      lo = __reduce_or_sync(0xffffffffu, lo);
+      hi = __reduce_or_sync(0xffffffffu, hi);
+      if ((tid & 31) == 0 && (lo | hi)) atomicOr(&sup_prev, (static_cast<unsigned long long>(hi) << 32) | lo);
+    }
+    // phase 2: pairwise masks inside the chunk (row i suppresses later column j)
+    {
+      const int i = tid & 63, part = tid >> 6;  // 4 parts x 16 columns
+      if (i < mcnt) {
+        unsigned long long bits = 0ull;
+        const float4 bi = cbox[i];
+        const float ai = carea[i];
+        for (int j = max(i + 1, part * 16); j < min(mcnt, part * 16 + 16); ++j)
+          if (iou_exceeds(bi, ai, cbox[j], carea[j], thr, thr_nonneg)) bits |= (1ull << j);
+        if (bits) atomicOr(&cmask[i], bits);
+      }
+    }
+    __syncthreads();
+    // phase 3: serial greedy resolution of the 64 candidates
+    if (tid == 0) {
+      unsigned long long alive = ~sup_prev;
+      if (mcnt < 64) alive &= ((1ull << mcnt) - 1ull);
+      unsigned long long kept = 0ull;
+      for (int i = 0; i < mcnt; ++i) {
+        if ((alive >> i) & 1ull) {
+          kept |= (1ull << i);
+          alive &= ~cmask[i];
+        }
+      }
+      kept_bits = kept;
+    }
+    __syncthreads();
+    // phase 4: append the survivors to the kept list (order preserved)
+    {
+      const unsigned long long kept = kept_bits;
+      const int kn = kept_n;
+      if (tid < mcnt && ((kept >> tid) & 1ull)) {
+        const int pos = kn + __popcll(kept & ((1ull << tid) - 1ull));
+        if (pos < kKeptSmem) { kbox[pos] = cbox[tid]; karea[pos] = carea[tid]; }
+        else gk_box[pos] = cbox[tid];
+        gk_key[pos] = ckey[tid] & 0x00FFFFFFFFFFFFFFull;  // (~score, anchor): order across classes
+      }
+      __syncthreads();
+      if (tid == 0) kept_n = kn + __popcll(kept);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) w.seg_kept[b * w.nc + seg] = kept_n;
+}
+
+// ---------------------------------------------------------------------------------------------- output
+template <bool kFromPred>
+__global__ void __launch_bounds__(256) rank_gather_kernel(Source s, Work w, int max_det, float* det,
+                                                          int32_t* det_count, int32_t* keep_index) {
+  __shared__ int sstart[kMaxClasses + 1];
+  __shared__ int skept[kMaxClasses];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c <= w.nc; c += blockDim.x) {
+    sstart[c] = w.seg_start[b * (w.nc + 1) + c];
+    if (c < w.nc) skept[c] = w.seg_kept[b * w.nc + c];
+  }
+  __syncthreads();
+  const int n = sstart[w.nc];
+  const uint64_t* kk = w.kept_key + static_cast<int64_t>(b) * w.cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int total = 0;
+    for (int c = 0; c < w.nc; ++c) total += skept[c];
+    det_count[b] = total < max_det ? total : max_det;
+  }
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    int c = 0;
+    while (c + 1 < w.nc && p >= sstart[c + 1]) ++c;
+    if (p - sstart[c] >= skept[c]) continue;  // not a kept slot
+    const uint64_t key = kk[p];
+    int rank = 0;
+    for (int c2 = 0; c2 < w.nc; ++c2) {
+      const uint64_t* base = kk + sstart[c2];
+      int lo = 0, hi = skept[c2];
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (base[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank >= max_det) continue;
+    const int idx = static_cast<int>(key_idx(key));
+    if (keep_index) keep_index[static_cast<int64_t>(b) * max_det + rank] = idx;
+    if (kFromPred && det) {
+      const Cand cd = load_cand<true>(s, b, idx);
+      float* o = det + (static_cast<int64_t>(b) * max_det + rank) * 7;
+      o[0] = cd.box.x; o[1] = cd.box.y; o[2] = cd.box.z; o[3] = cd.box.w;
+      o[4] = cd.obj; o[5] = cd.cls_conf; o[6] = cd.label_f;  // utils_bbox.py:411 row layout
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+inline int pow2_ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Layout {
+  int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
+      off_keptkey, off_keptbox, total;
+};
+
+Layout make_layout(int B, int cap, int P, int nc) {
+  Layout l;
+  int64_t o = 0;
+  l.off_count = o; o = align_up(o + 4ll * B, 256);
+  l.off_max = o; o = align_up(o + 4ll * B, 256);
+  l.off_min = o; o = align_up(o + 4ll * B, 256);
+  l.off_segstart = o; o = align_up(o + 4ll * B * (nc + 1), 256);
+  l.off_segkept = o; o = align_up(o + 4ll * B * nc, 256);
+  l.off_score = o; o = align_up(o + 4ll * B * cap, 256);
+  l.off_idx = o; o = align_up(o + 4ll * B * cap, 256);
+  l.off_label = o; o = align_up(o + 1ll * B * cap, 256);
+  l.off_keys = o; o = align_up(o + 8ll * B * P, 256);
+  l.off_keptkey = o; o = align_up(o + 8ll * B * cap, 256);
+  l.off_keptbox = o; o = align_up(o + 16ll * B * cap, 256);
+  l.total = o;
+  return l;
+}
+
+Work make_work(void* ws, int B, int cap, int nc) {
+  const int P = pow2_ceil(cap < kSortChunk ? kSortChunk : cap);
+  const Layout l = make_layout(B, cap, P, nc);
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  Work w;
+  w.B = B; w.cap = cap; w.P = P; w.nc = nc;
+  w.cand_count = reinterpret_cast<int32_t*>(p + l.off_count);
+  w.max_bits = reinterpret_cast<uint32_t*>(p + l.off_max);
+  w.min_bits = reinterpret_cast<uint32_t*>(p + l.off_min);
+  w.seg_start = reinterpret_cast<int32_t*>(p + l.off_segstart);
+  w.seg_kept = reinterpret_cast<int32_t*>(p + l.off_segkept);
+  w.cand_score = reinterpret_cast<float*>(p + l.off_score);
+  w.cand_idx = reinterpret_cast<int32_t*>(p + l.off_idx);
+  w.cand_label = p + l.off_label;
+  w.keys = reinterpret_cast<uint64_t*>(p + l.off_keys);
+  w.kept_key = reinterpret_cast<uint64_t*>(p + l.off_keptkey);
+  w.kept_box = reinterpret_cast<float4*>(p + l.off_keptbox);
+  return w;
+}
+
+int64_t workspace_bytes(int B, int cap, int nc) {
+  const int P = pow2_ceil(cap < kSortChunk ? kSortChunk : cap);
+  return make_layout(B, cap, P, nc).total;
+}
+
+template <bool kFromPred>
+int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thres, int strategy, int max_det,
+                 float* det, int32_t* det_count, int32_t* keep_index, cudaStream_t st) {
+  const int B = w.B;
+  reset_kernel<<<(B + 255) / 256, 256, 0, st>>>(w);
+  if (int rc = count_launch("reset_kernel")) return rc;
+  {
+    int gx = (s.A + 255) / 256;
+    if (gx > 4096) gx = 4096;
+    filter_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, conf_thres);
+    if (int rc = count_launch("filter_kernel")) return rc;
+  }
+  {
+    int gx = w.P / 256;
+    if (gx > 1024) gx = 1024;
+    build_keys_kernel<<<dim3(gx, B), 256, 0, st>>>(w, strategy);
+    if (int rc = count_launch("build_keys_kernel")) return rc;
+  }
+  const int chunks = w.P / kSortChunk;
+  bitonic_local_sort_kernel<<<dim3(chunks, B), kSortThreads, 0, st>>>(w);
+  if (int rc = count_launch("bitonic_local_sort_kernel")) return rc;
+  for (int k = 2 * kSortChunk; k <= w.P; k <<= 1) {
+    for (int j = k >> 1; j >= kSortChunk; j >>= 1) {
+      int gx = w.P / 2 / 256;
+      if (gx > 2048) gx = 2048;
+      bitonic_global_step_kernel<<<dim3(gx, B), 256, 0, st>>>(w, k, j);
+      if (int rc = count_launch("bitonic_global_step_kernel")) return rc;
+    }
+    bitonic_local_merge_kernel<<<dim3(chunks, B), kSortThreads, 0, st>>>(w, k);
+    if (int rc = count_launch("bitonic_local_merge_kernel")) return rc;
+  }
+  segment_bounds_kernel<<<B, 256, 0, st>>>(w, strategy);
+  if (int rc = count_launch("segment_bounds_kernel")) return rc;
+  nms_segment_kernel<kFromPred><<<dim3(w.nc, B), kNmsThreads, 0, st>>>(s, w, nms_thres, strategy);
+  if (int rc = count_launch("nms_segment_kernel")) return rc;
+  {
+    int gx = (w.cap + 255) / 256;
+    if (gx > 256) gx = 256;
+    rank_gather_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, max_det, det, det_count, keep_index);
+    if (int rc = count_launch("rank_gather_kernel")) return rc;
+  }
+  return 0;
+}
+
+}  // namespace glsdet
+
+using namespace glsdet;
+
+struct glsdet_nms {
+  int B, A, nc, max_det;
+  Work w;
+};
+
+extern "C" int64_t glsdet_nms_workspace_bytes(int32_t batch, int32_t anchors, int32_t num_classes) {
+  if (batch <= 0 || anchors <= 0 || num_classes <= 0) return -1;
+  return workspace_bytes(batch, anchors, num_classes);
+}
+
+extern "C" int glsdet_nms_create(int32_t batch, int32_t anchors, int32_t num_classes, int32_t max_det,
+                                 void* workspace, int64_t workspace_bytes_given, glsdet_nms_t** op) {
+  GLSDET_REQUIRE(op != nullptr, "nms_create: null output handle");
+  *op = nullptr;
+  GLSDET_REQUIRE(batch > 0 && anchors > 0 && max_det > 0, "nms_create: bad sizes");
+  GLSDET_REQUIRE(num_classes > 0 && num_classes <= kMaxClasses, "nms_create: 1..%d classes supported", kMaxClasses);
+  GLSDET_REQUIRE(anchors < (1 << 24), "nms_create: at most 2^24-1 anchors per image");
+  GLSDET_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                 "nms_create: workspace must be 256-byte aligned");
+  GLSDET_REQUIRE(workspace_bytes_given >= workspace_bytes(batch, anchors, num_classes), "nms_create: workspace too small");
+  glsdet_nms* h = new (std::nothrow) glsdet_nms();
+  GLSDET_REQUIRE(h != nullptr, "nms_create: out of host memory");
+  h->B = batch; h->A = anchors; h->nc = num_classes; h->max_det = max_det;
+  h->w = make_work(workspace, batch, anchors, num_classes);
+  *op = h;
+  return 0;
+}
+
+extern "C" int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf_thres, float nms_thres,
+                                 int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index, void* stream) {
+  GLSDET_REQUIRE(op && pred && det && det_count, "nms_launch: null pointer");
+  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_AUTO_CPU, "nms_launch: bad strategy %d", strategy);
+  Source s{};
+  s.pred = pred; s.A = op->A; s.nch = 5 + op->nc; s.nc = op->nc;
+  return run_pipeline<true>(s, op->w, conf_thres, nms_thres, strategy, op->max_det, det, det_count, keep_index,
+                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" void glsdet_nms_destroy(glsdet_nms_t* op) { delete op; }
+
+extern "C" int64_t glsdet_batched_nms_workspace_bytes(int32_t k) {
+  if (k <= 0) return 256;
+  return workspace_bytes(1, k, kMaxClasses);
+}
+
+extern "C" int glsdet_batched_nms(const float* boxes, const float* scores, const float* labels, int32_t k,
+                                  float nms_thres, int32_t strategy, void* workspace, int64_t workspace_bytes_given,
+                                  int32_t* keep, int32_t* keep_count, void* stream) {
+  GLSDET_REQUIRE(keep_count != nullptr, "batched_nms: null keep_count");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (k <= 0) {
+    GLSDET_CHECK_CUDA(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), st));
+    return 0;
+  }
+  GLSDET_REQUIRE(boxes && scores && labels && keep, "batched_nms: null pointer");
+  GLSDET_REQUIRE(k < (1 << 24), "batched_nms: at most 2^24-1 boxes");
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "batched_nms: boxes must be 16-byte aligned");
+  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_AUTO_CPU, "batched_nms: bad strategy %d", strategy);
+  GLSDET_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                 "batched_nms: workspace must be 256-byte aligned");
+  GLSDET_REQUIRE(workspace_bytes_given >= workspace_bytes(1, k, kMaxClasses), "batched_nms: workspace too small");
+  const Work w = make_work(workspace, 1, k, kMaxClasses);
+  Source s{};
+  s.A = k; s.nch = 0; s.nc = kMaxClasses;
+  s.boxes = boxes; s.scores = scores; s.labels = labels;
+  return run_pipeline<false>(s, w, 0.0f, nms_thres, strategy, k, nullptr, keep_count, keep, st);
+}

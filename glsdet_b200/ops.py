@@ -132,3 +132,71 @@ class ConvOp:
                 self.handle = C.c_void_p()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------------------------- other operators
+def nchw_to_nhwc(src: torch.Tensor, dst: View, stream=None) -> None:
+    """NCHW fp32 (reference layout) -> channel window of an NHWC bf16 buffer."""
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.is_cuda
+    b, c, h, w = src.shape
+    assert dst.bhw == (b, h, w) and dst.c == c and dst.t.dtype == torch.bfloat16
+    lib = N.load()
+    N.check(lib.glsdet_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff,
+                                             N.stream_ptr(stream)), "glsdet_nchw_f32_to_nhwc_bf16")
+
+
+def nhwc_to_nchw(src: View, dst: torch.Tensor, stream=None) -> None:
+    assert dst.dtype == torch.float32 and dst.is_contiguous() and src.t.dtype == torch.bfloat16
+    b, h, w = src.bhw
+    assert tuple(dst.shape) == (b, src.c, h, w)
+    lib = N.load()
+    N.check(lib.glsdet_nhwc_bf16_to_nchw_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff,
+                                             N.stream_ptr(stream)), "glsdet_nhwc_bf16_to_nchw_f32")
+
+
+class SeGateOp:
+    """gate[b, c] = 1 + sigmoid(W2 relu(W1 mean_hw(x)))  (models/ffa/ffa.py:16-20 and :77)."""
+
+    def __init__(self, x: View, w1: torch.Tensor, w2: torch.Tensor):
+        assert x.coff == 0 and x.t.dtype == torch.bfloat16
+        b, h, w = x.bhw
+        self.x, self.b, self.hw, self.c = x, b, h * w, x.c
+        self.w1 = w1.detach().float().contiguous()
+        self.w2 = w2.detach().float().contiguous()
+        self.hidden = self.w1.shape[0]
+        assert tuple(self.w1.shape) == (self.hidden, self.c) and tuple(self.w2.shape) == (self.c, self.hidden)
+        self.scratch = torch.empty((b, N.SE_SLABS, self.c), dtype=torch.float32, device=x.t.device)
+        self.gate = torch.empty((b, self.c), dtype=torch.float32, device=x.t.device)
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        N.check(self._lib.glsdet_se_gate(self.x.ptr, self.b, self.hw, self.c, self.x.ld, self.w1.data_ptr(),
+                                         self.w2.data_ptr(), self.hidden, self.scratch.data_ptr(),
+                                         self.gate.data_ptr(), N.stream_ptr(stream)), "glsdet_se_gate")
+
+
+class ScaleShuffleOp:
+    """dst = PixelShuffle(2)(x * gate) with x's channels in (i, j, c) order (ffa.py:77-78)."""
+
+    def __init__(self, x: View, gate: torch.Tensor, dst: View):
+        b, h, w = x.bhw
+        assert x.coff == 0 and x.c == x.ld and x.c % 4 == 0
+        self.cout = x.c // 4
+        assert dst.bhw == (b, 2 * h, 2 * w) and dst.c == self.cout
+        self.x, self.gate, self.dst, self.b, self.h, self.w = x, gate, dst, b, h, w
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        N.check(self._lib.glsdet_scale_pixel_shuffle(self.x.ptr, self.gate.data_ptr(), self.dst.t.data_ptr(), self.b,
+                                                     self.h, self.w, self.cout, self.dst.ld, self.dst.coff,
+                                                     N.stream_ptr(stream)), "glsdet_scale_pixel_shuffle")
+
+
+class _Call:
+    """Deferred plain function call so that converters can sit in an op list next to the op objects."""
+
+    def __init__(self, fn, *args):
+        self.fn, self.args = fn, args
+
+    def launch(self, stream=None):
+        self.fn(*self.args, stream=stream)

@@ -1,0 +1,159 @@
+"""Drop-in for yolox-drone/models/core/utils_bbox.py (decode_outputs :254-306, non_max_suppression :375-484,
+yolo_correct_boxes :8-33) running on the native sm_100a kernels.  Same names, arguments and return types;
+differences a caller can observe:
+
+  * `prediction` is not overwritten in place (the reference converts it to corner form in place, :386);
+  * decode_outputs returns a contiguous [B, A, 5+nc] tensor (the reference returns a permuted view);
+  * non_max_suppression has one extra keyword, `strategy`, naming which torchvision batched_nms branch to
+    reproduce bit-exactly (default: torchvision's own dispatch for CUDA tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+STRATEGIES = {"trick": N.NMS_COORD_TRICK, "per_class": N.NMS_PER_CLASS, "auto_cuda": N.NMS_AUTO_CUDA,
+              "auto_cpu": N.NMS_AUTO_CPU}
+
+
+def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """utils_bbox.py:254-306: list of raw [B, 5+nc, h, w] maps -> [B, sum(h*w), 5+nc] with normalised
+    (cx, cy, w, h), sigmoid(obj), sigmoid(cls)."""
+    lib = N.load()
+    outs = [o.float().contiguous() for o in outputs]
+    if not outs or not outs[0].is_cuda:
+        raise N.NativeError("decode_outputs needs CUDA tensors (glsdet_b200 has no CPU path)")
+    b, nch = outs[0].shape[:2]
+    n = len(outs)
+    ptrs = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+    hs = (C.c_int32 * n)(*[o.shape[2] for o in outs])
+    ws = (C.c_int32 * n)(*[o.shape[3] for o in outs])
+    a = sum(o.shape[2] * o.shape[3] for o in outs)
+    pred = torch.empty((b, a, nch), dtype=torch.float32, device=outs[0].device)
+    N.check(lib.glsdet_decode_outputs(ptrs, hs, ws, n, b, nch - 5, int(input_shape[0]), int(input_shape[1]),
+                                      pred.data_ptr(), N.stream_ptr()), "glsdet_decode_outputs")
+    return pred
+
+
+def yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image):
+    """utils_bbox.py:8-33: undo the letterbox and scale to the original image; returns (y1, x1, y2, x2).
+    Host-side numpy exactly like the reference (it runs after the device->host copy there too, :481-483)."""
+    yx = np.asarray(box_xy)[..., ::-1]
+    hw = np.asarray(box_wh)[..., ::-1]
+    inp = np.array(input_shape)
+    img = np.array(image_shape)
+    if letterbox_image:
+        new_shape = np.round(img * np.min(inp / img))
+        offset = (inp - new_shape) / 2.0 / inp
+        scale = inp / new_shape
+        yx = (yx - offset) * scale
+        hw = (hw * scale).astype(hw.dtype)  # in-place `*=` in the reference keeps the input dtype (:25)
+    mins = yx - hw / 2.0
+    maxes = yx + hw / 2.0
+    out = np.concatenate([mins[..., 0:1], mins[..., 1:2], maxes[..., 0:1], maxes[..., 1:2]], axis=-1)
+    return out * np.concatenate([img, img], axis=-1)
+
+
+class DeviceNMS:
+    """Score filter + class-aware NMS for a fixed (batch, anchors, classes); no host synchronisation.
+    det: [B, max_det, 7] rows (x1, y1, x2, y2, obj_conf, class_conf, class_pred) sorted by score,
+    count: [B] int32, keep_index: [B, max_det] int32 anchor indices."""
+
+    def __init__(self, batch: int, anchors: int, num_classes: int, max_det: Optional[int] = None, device=None):
+        self._lib = N.load()
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.batch, self.anchors, self.nc = batch, anchors, num_classes
+        self.max_det = anchors if max_det is None else int(max_det)
+        nbytes = self._lib.glsdet_nms_workspace_bytes(batch, anchors, num_classes)
+        if nbytes <= 0:
+            raise N.NativeError("glsdet_nms_workspace_bytes rejected the problem size")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.det = torch.zeros((batch, self.max_det, 7), dtype=torch.float32, device=dev)
+        self.count = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self.keep_index = torch.zeros((batch, self.max_det), dtype=torch.int32, device=dev)
+        self.handle = C.c_void_p()
+        N.check(self._lib.glsdet_nms_create(batch, anchors, num_classes, self.max_det, self.workspace.data_ptr(),
+                                            nbytes, C.byref(self.handle)), "glsdet_nms_create")
+
+    def launch(self, pred: torch.Tensor, conf_thres: float, nms_thres: float, strategy: str = "auto_cuda",
+               stream=None):
+        assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.is_cuda
+        assert tuple(pred.shape) == (self.batch, self.anchors, 5 + self.nc), (pred.shape, self.batch, self.anchors)
+        N.check(self._lib.glsdet_nms_launch(self.handle, pred.data_ptr(), float(conf_thres), float(nms_thres),
+                                            STRATEGIES[strategy], self.det.data_ptr(), self.count.data_ptr(),
+                                            self.keep_index.data_ptr(), N.stream_ptr(stream)), "glsdet_nms_launch")
+        return self.det, self.count
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None) and self.handle.value:
+                self._lib.glsdet_nms_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+_nms_cache = {}
+
+
+def _device_nms(batch, anchors, nc, device) -> DeviceNMS:
+    key = (batch, anchors, nc, str(device))
+    if key not in _nms_cache:
+        if len(_nms_cache) > 8:
+            _nms_cache.clear()
+        _nms_cache[key] = DeviceNMS(batch, anchors, nc, device=device)
+    return _nms_cache[key]
+
+
+def non_max_suppression(prediction: torch.Tensor, num_classes: int, input_shape, image_shape, letterbox_image,
+                        conf_thres: float = 0.5, nms_thres: float = 0.4, strategy: str = "auto_cuda",
+                        ) -> List[Optional[np.ndarray]]:
+    """utils_bbox.py:375-484.  Returns, per image, a float32 ndarray [K, 7] with rows
+    (y1, x1, y2, x2 in original-image pixels, obj_conf, class_conf, class_pred) sorted by score, or None for
+    an input without anchors (:405-406)."""
+    b, a = prediction.shape[:2]
+    if a == 0:
+        return [None for _ in range(b)]
+    if not prediction.is_cuda:
+        raise N.NativeError("non_max_suppression needs a CUDA tensor (glsdet_b200 has no CPU path)")
+    pred = prediction[..., :5 + num_classes].float().contiguous()
+    op = _device_nms(b, a, num_classes, pred.device)
+    det, count = op.launch(pred, conf_thres, nms_thres, strategy)
+    counts = count.cpu().numpy()                 # the one device->host sync of the reference (:481)
+    kmax = int(counts.max()) if b else 0
+    rows = det[:, :kmax].cpu().numpy()
+    output: List[Optional[np.ndarray]] = []
+    for i in range(b):
+        out = rows[i, :counts[i]].copy()
+        box_xy, box_wh = (out[:, 0:2] + out[:, 2:4]) / 2, out[:, 2:4] - out[:, 0:2]
+        out[:, :4] = yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image)
+        output.append(out)
+    return output
+
+
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                strategy: str = "auto_cuda") -> torch.Tensor:
+    """Same contract as torchvision.ops.boxes.batched_nms (the call at utils_bbox.py:414-419): int64 indices of
+    the kept boxes, sorted by decreasing score."""
+    lib = N.load()
+    k = boxes.shape[0]
+    if k == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    if not boxes.is_cuda:
+        raise N.NativeError("batched_nms needs CUDA tensors (glsdet_b200 has no CPU path)")
+    bx = boxes.float().contiguous()
+    sc = scores.float().contiguous()
+    lb = idxs.float().contiguous()
+    nbytes = lib.glsdet_batched_nms_workspace_bytes(k)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
+    keep = torch.empty((k,), dtype=torch.int32, device=boxes.device)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
+    N.check(lib.glsdet_batched_nms(bx.data_ptr(), sc.data_ptr(), lb.data_ptr(), k, float(iou_threshold),
+                                   STRATEGIES[strategy], ws.data_ptr(), nbytes, keep.data_ptr(), cnt.data_ptr(),
+                                   N.stream_ptr()), "glsdet_batched_nms")
+    return keep[:int(cnt.item())].long()

@@ -1,0 +1,352 @@
+"""Drop-in for yolox-drone/models/ffa/yolox_ffa.py: `YoloBody(num_classes, phi)`, `YOLOPAFPN`, `YOLOXHead`, `FFA`.
+
+Same constructor signatures, forward signatures, tensor layouts (NCHW fp32 in and out) and state_dict keys as
+the reference, so `yolox-drone/yolo.py` can load it by module path
+(`importlib.import_module(config_path).YoloBody(num_classes, phi)`, yolo.py:100-102) and
+`load_state_dict(torch.load(path))` strictly (yolo.py:105).
+
+The modules below only HOLD parameters with the reference's names.  The math of the neck, the FFA block, the
+head, the decode and the NMS runs in the native plan (glsdet_b200/engine.py -> libglsdet_b200.so); there is no
+PyTorch fallback for it.  The CSPDarknet backbone is upstream of this path and is the one
+piece executed by PyTorch.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .engine import FFAPathPlan
+from .utils_bbox import DeviceNMS
+
+_DEPTH = {"nano": 0.33, "tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.00, "x": 1.33}
+_WIDTH = {"nano": 0.25, "tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.00, "x": 1.25}
+
+
+def _activation(x: torch.Tensor, name: str) -> torch.Tensor:
+    if name == "silu":
+        return x * torch.sigmoid(x)
+    if name == "relu":
+        return torch.relu(x)
+    if name == "lrelu":
+        return F.leaky_relu(x, 0.1)
+    raise AttributeError(f"Unsupported act type: {name}")
+
+
+class BaseConv(nn.Module):
+    """Parameter holder for conv(bias=False) + BatchNorm2d(eps=1e-3, momentum=0.03) + activation
+    (reference: models/base/baseConv.py:6-16).  `upstream=True` marks backbone layers, the only ones whose
+    forward is evaluated by PyTorch."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="silu", upstream=False):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2, groups=groups, bias=bias)
+        self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0.03)
+        self.act_name = act
+        self.upstream = upstream
+
+    def forward(self, x):
+        if not self.upstream:
+            raise RuntimeError("this layer belongs to the native GLSDet path and is executed by libglsdet_b200.so "
+                               "through its parent module (YOLOPAFPN / YOLOXHead / YoloBody); it has no PyTorch forward")
+        return _activation(self.bn(self.conv(x)), self.act_name)
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, cout, shortcut=True, expansion=0.5, act="silu", upstream=False):
+        super().__init__()
+        hidden = int(cout * expansion)
+        self.conv1 = BaseConv(cin, hidden, 1, 1, act=act, upstream=upstream)
+        self.conv2 = BaseConv(hidden, cout, 3, 1, act=act, upstream=upstream)
+        self.use_add = shortcut and cin == cout
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x))
+        return y + x if self.use_add else y
+
+
+class CSPLayer(nn.Module):
+    """models/ffa/darknet.py:66-112 layout: conv1, conv2, conv3, m.<j>.conv{1,2}."""
+
+    def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu",
+                 upstream=False):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise (phi='nano') blocks are not part of the native path")
+        hidden = int(out_channels * expansion)
+        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act, upstream=upstream)
+        self.conv2 = BaseConv(in_channels, hidden, 1, 1, act=act, upstream=upstream)
+        self.conv3 = BaseConv(2 * hidden, out_channels, 1, 1, act=act, upstream=upstream)
+        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, act=act, upstream=upstream)
+                                 for _ in range(n)])
+
+    def forward(self, x):
+        return self.conv3(torch.cat((self.m(self.conv1(x)), self.conv2(x)), dim=1))
+
+
+class Focus(nn.Module):
+    def __init__(self, in_channels, out_channels, ksize=1, stride=1, act="silu"):
+        super().__init__()
+        self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act, upstream=True)
+
+    def forward(self, x):
+        return self.conv(torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1))
+
+
+class SPPBottleneck(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_sizes=(5, 9, 13), activation="silu"):
+        super().__init__()
+        hidden = in_channels // 2
+        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=activation, upstream=True)
+        self.m = nn.ModuleList([nn.MaxPool2d(ks, 1, ks // 2) for ks in kernel_sizes])
+        self.conv2 = BaseConv(hidden * (len(kernel_sizes) + 1), out_channels, 1, 1, act=activation, upstream=True)
+
+    def forward(self, x):
+        x = self.conv1(x)
+        return self.conv2(torch.cat([x] + [m(x) for m in self.m], dim=1))
+
+
+class CSPDarknet(nn.Module):
+    """Backbone (models/ffa/darknet.py:115-195).  Upstream of the native path: plain PyTorch."""
+
+    def __init__(self, dep_mul, wid_mul, out_features=("dark2", "dark3", "dark4", "dark5"), depthwise=False,
+                 act="silu"):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise (phi='nano') is not supported")
+        self.out_features = out_features
+        c = int(wid_mul * 64)
+        d = max(round(dep_mul * 3), 1)
+        self.stem = Focus(3, c, ksize=3, act=act)
+
+        def stage(cin, cout, n, shortcut=True, spp=False):
+            layers = [BaseConv(cin, cout, 3, 2, act=act, upstream=True)]
+            if spp:
+                layers.append(SPPBottleneck(cout, cout, activation=act))
+            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act, upstream=True))
+            return nn.Sequential(*layers)
+
+        self.dark2 = stage(c, c * 2, d)
+        self.dark3 = stage(c * 2, c * 4, d * 3)
+        self.dark4 = stage(c * 4, c * 8, d * 3)
+        self.dark5 = stage(c * 8, c * 16, d, shortcut=False, spp=True)
+
+    def forward(self, x):
+        outs = {}
+        x = self.stem(x)
+        outs["stem"] = x
+        for name in ("dark2", "dark3", "dark4", "dark5"):
+            x = getattr(self, name)(x)
+            outs[name] = x
+        return {k: v for k, v in outs.items() if k in self.out_features}
+
+
+class SE(nn.Module):
+    """models/ffa/ffa.py:5-20 parameter layout (fc.0.weight, fc.2.weight)."""
+
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.fc = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(),
+                                nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+
+class FFA(nn.Module):
+    """models/ffa/ffa.py:22-85 parameter layout; evaluated inside the head's native plan."""
+
+    def __init__(self, num_channels):
+        super().__init__()
+        c = num_channels
+        self.scale = BaseConv(c * 2, c * 4, 1, 1, act="relu")
+        self.create_content_extractor = nn.Sequential(BaseConv(c * 4, c * 4, 1, 1, act="relu"),
+                                                      BaseConv(c * 4, c * 4, 1, 1, act="relu"))
+        self.create_text_extractor = nn.Sequential(BaseConv(c * 2, c * 2, 1, 1, act="relu"))
+        self.conv3 = BaseConv(c * 2, c, 1, 1, act="relu")
+        self.se1 = SE(c * 4)
+
+
+FTT = FFA  # the reference constructs `FTT(...)` (yolox_ffa.py:31) while only FFA exists
+
+
+class _PlanOwner(nn.Module):
+    """Caches native plans per (batch, input size, device) and drops them when the weights change."""
+
+    _neck_prefix = ""
+    _head_prefix = ""
+    _parts: Tuple[str, ...] = ()
+
+    def __init__(self):
+        super().__init__()
+        self._plans: Dict[tuple, FFAPathPlan] = {}
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_plans())
+
+    def invalidate_plans(self):
+        self._plans.clear()
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_plans()
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise RuntimeError("glsdet_b200 modules are inference-only (BatchNorm is folded into the convs)")
+        return super().train(False)
+
+    def _num_classes(self) -> int:
+        raise NotImplementedError
+
+    def _plan(self, batch: int, input_hw: Sequence[int], device) -> FFAPathPlan:
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device))
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 4:
+                self._plans.clear()
+            plan = FFAPathPlan(self.state_dict(), batch, input_hw, self._num_classes(), device=device,
+                               neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts)
+            self._plans[key] = plan
+        return plan
+
+
+class YOLOXHead(_PlanOwner):
+    """models/ffa/yolox_ffa.py:12-118.  forward(inputs) takes the tuple YOLOPAFPN.forward returns
+    (feat0, P3_out, P4_out, P5_out; NCHW fp32) and returns the list of raw [B, 5+nc, h, w] maps."""
+
+    _parts = ("head",)
+
+    def __init__(self, num_classes, width=1.0, in_channels=[256, 512, 1024, 256], act="silu", depthwise=False):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
+        self.num_classes = num_classes
+        hc = int(256 * width)
+        self.cls_convs, self.reg_convs = nn.ModuleList(), nn.ModuleList()
+        self.cls_preds, self.reg_preds, self.obj_preds = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        self.stems = nn.ModuleList()
+        self.csp = CSPLayer(int(0.5 * in_channels[0] * width), int(in_channels[0] * width), round(3 * 0.75), False,
+                            act=act)
+        self.ftt = FTT(int(width * in_channels[0]))
+        for i, cin in enumerate(in_channels):
+            if i != 3:
+                self.stems.append(BaseConv(int(cin * width), hc, 1, 1, act=act))
+            self.cls_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 1, act=act)))
+            self.reg_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 1, act=act)))
+            self.cls_preds.append(nn.Conv2d(hc, num_classes, 1, 1, 0))
+            self.reg_preds.append(nn.Conv2d(hc, 4, 1, 1, 0))
+            self.obj_preds.append(nn.Conv2d(hc, 1, 1, 1, 0))
+        super().train(False)
+
+    def _num_classes(self):
+        return self.num_classes
+
+    @torch.no_grad()
+    def forward(self, inputs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        p3 = inputs[1]
+        plan = self._plan(p3.shape[0], (p3.shape[2] * 8, p3.shape[3] * 8), p3.device)
+        plan.load_head_inputs([t.float() for t in inputs])
+        plan.run_head(decoded=False)
+        return [t.clone() for t in plan.logits]
+
+
+class YOLOPAFPN(_PlanOwner):
+    """models/ffa/yolox_ffa.py:121-261.  forward(image batch) -> (feat0, P3_out, P4_out, P5_out), NCHW fp32."""
+
+    _parts = ("neck",)
+
+    def __init__(self, depth=1.0, width=1.0, in_features=("dark2", "dark3", "dark4", "dark5"),
+                 in_channels=[256, 512, 1024], depthwise=False, act="silu"):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
+        self.backbone = CSPDarknet(depth, width, depthwise=depthwise, act=act)
+        self.in_features = in_features
+        c0, c1, c2 = (int(c * width) for c in in_channels)
+        n = round(3 * depth)
+        self.lateral_conv0 = BaseConv(c2, c1, 1, 1, act=act)
+        self.C3_p4 = CSPLayer(2 * c1, c1, n, False, act=act)
+        self.reduce_conv1 = BaseConv(c1, c0, 1, 1, act=act)
+        self.C3_p3 = CSPLayer(2 * c0, c0, n, False, act=act)
+        self.bu_conv2 = BaseConv(c0, c0, 3, 2, act=act)
+        self.C3_n3 = CSPLayer(2 * c0, c1, n, False, act=act)
+        self.bu_conv1 = BaseConv(c1, c1, 3, 2, act=act)
+        self.C3_n4 = CSPLayer(2 * c1, c2, n, False, act=act)
+        super().train(False)
+
+    def _num_classes(self):
+        return 1  # unused by the neck-only plan
+
+    @torch.no_grad()
+    def features(self, x: torch.Tensor) -> List[torch.Tensor]:
+        out = self.backbone(x)
+        return [out[f] for f in self.in_features]
+
+    @torch.no_grad()
+    def forward_features(self, feats: Sequence[torch.Tensor]) -> Tuple[torch.Tensor, ...]:
+        """Neck only, from (dark2, dark3, dark4, dark5) NCHW fp32."""
+        f0 = feats[0]
+        plan = self._plan(f0.shape[0], (f0.shape[2] * 4, f0.shape[3] * 4), f0.device)
+        plan.load_features([t.float() for t in feats])
+        plan.run_neck()
+        outs = plan.neck_outputs_nchw()
+        return (feats[0], outs[1], outs[2], outs[3])
+
+    def forward(self, input: torch.Tensor):
+        return self.forward_features(self.features(input))
+
+
+class YoloBody(_PlanOwner):
+    """models/ffa/yolox_ffa.py:264-284.  forward(x) returns the raw per-level maps exactly like the reference;
+    `detect` is the fused neck -> head -> decode -> filter -> NMS path."""
+
+    _neck_prefix = "backbone."
+    _head_prefix = "head."
+    _parts = ("neck", "head")
+
+    def __init__(self, num_classes, phi):
+        super().__init__()
+        depth, width = _DEPTH[phi], _WIDTH[phi]
+        depthwise = phi == "nano"
+        self.num_classes = num_classes
+        self.backbone = YOLOPAFPN(depth, width, depthwise=depthwise)
+        self.head = YOLOXHead(num_classes, width, depthwise=depthwise)
+        self._nms: Dict[tuple, DeviceNMS] = {}
+        super().train(False)
+
+    def _num_classes(self):
+        return self.num_classes
+
+    def plan_for(self, feats: Sequence[torch.Tensor]) -> FFAPathPlan:
+        f0 = feats[0]
+        return self._plan(f0.shape[0], (f0.shape[2] * 4, f0.shape[3] * 4), f0.device)
+
+    @torch.no_grad()
+    def forward_features(self, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """Neck + head from backbone features (dark2..dark5, NCHW fp32): list of raw [B, 5+nc, h, w]."""
+        return [t.clone() for t in self.plan_for(feats).forward_logits(feats)]
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        return self.forward_features(self.backbone.features(x))
+
+    @torch.no_grad()
+    def decode_features(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
+        """decode_outputs(forward(...)) fused: [B, A, 5+nc] (cx, cy, w, h normalised, obj, cls)."""
+        return self.plan_for(feats).forward_decoded(feats)
+
+    @torch.no_grad()
+    def detect_features(self, feats: Sequence[torch.Tensor], conf_thres: float = 0.5, nms_thres: float = 0.4,
+                        strategy: str = "auto_cuda", max_det: Optional[int] = None):
+        """Whole hot path on the device.  Returns (det [B, max_det, 7], count [B]) device tensors; rows are
+        (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score."""
+        plan = self.plan_for(feats)
+        pred = plan.forward_decoded(feats)
+        key = (plan.B, plan.num_anchors, self.num_classes, max_det, str(plan.device))
+        nms = self._nms.get(key)
+        if nms is None:
+            nms = DeviceNMS(plan.B, plan.num_anchors, self.num_classes, max_det=max_det, device=plan.device)
+            self._nms = {key: nms}
+        return nms.launch(pred, conf_thres, nms_thres, strategy)
+
+    @torch.no_grad()
+    def detect(self, x: torch.Tensor, **kw):
+        return self.detect_features(self.backbone.features(x), **kw)

@@ -187,7 +187,7 @@ def yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image
         offset = (input_shape - new_shape) / 2.0 / input_shape
         scale = input_shape / new_shape
         box_yx = (box_yx - offset) * scale
-        box_hw = box_hw * scale
+        box_hw = (box_hw * scale).astype(box_hw.dtype)  # the reference multiplies in place (:25): stays float32
     box_mins = box_yx - (box_hw / 2.0)
     box_maxes = box_yx + (box_hw / 2.0)
     boxes = np.concatenate([box_mins[..., 0:1], box_mins[..., 1:2], box_maxes[..., 0:1], box_maxes[..., 1:2]], axis=-1)

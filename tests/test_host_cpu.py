@@ -1,0 +1,118 @@
+"""CPU tests of the host side: C-ABI library surface, module/state_dict contract, weight packing, BN folding."""
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = ROOT / "tests" / "golden"
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from glsdet_b200 import _native
+
+    header = (ROOT / "include" / "glsdet_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(glsdet_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found in the header"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(native_lib, name), f"{name} is declared in include/glsdet_b200.h but not exported"
+    assert native_lib.glsdet_abi_version() == 1
+
+
+def test_no_compute_without_gpu_but_errors_are_reported(native_lib):
+    from glsdet_b200 import _native as N
+
+    assert native_lib.glsdet_nms_workspace_bytes(2, 1000, 10) > 0
+    assert native_lib.glsdet_nms_workspace_bytes(0, 1000, 10) < 0
+    rc = native_lib.glsdet_conv_launch(None, None)
+    assert rc != 0 and b"null op" in native_lib.glsdet_last_error()
+    d = N.ConvDesc()
+    d.ksize, d.stride, d.batch, d.height, d.width = 5, 1, 1, 8, 8
+    assert native_lib.glsdet_conv_weight_shape(d, None, None, None) != 0
+    assert b"ksize" in native_lib.glsdet_last_error()
+
+
+def test_state_dict_keys_match_reference():
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    ref = json.loads((GOLD / "state_dict_keys_p0_s.json").read_text())
+    net = YoloBody(10, "s")
+    mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert list(mine.keys()) == list(ref.keys())
+    assert mine == ref
+    assert not net.training and not net.backbone.backbone.stem.conv.bn.training
+
+
+def test_strict_load_of_reference_style_checkpoint_and_no_torch_forward():
+    from glsdet_b200.yolox_ffa import YoloBody
+    from oracle import ref_path
+
+    sd = ref_path.synthetic_state_dict(3, "tiny", seed=5)
+    net = YoloBody(3, "tiny")
+    net.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError, match="native GLSDet path"):
+        net.head.stems[0](torch.zeros(1, 96, 4, 4))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net.train()
+    # backbone is plain PyTorch and must agree with the oracle's restatement of CSPDarknet
+    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        mine = net.backbone.features(x)
+    ref = ref_path.csp_darknet(sd, x)
+    for a, b in zip(mine, ref):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
+def test_fold_bn_and_pack_order():
+    from glsdet_b200.ops import fold_bn, pack_conv_weight
+
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(24, 40, 3, 3, generator=g)
+    gamma, beta = torch.randn(24, generator=g), torch.randn(24, generator=g)
+    mean, var = torch.randn(24, generator=g), torch.rand(24, generator=g) + 0.5
+    x = torch.randn(2, 40, 9, 9, generator=g)
+    ref = F.batch_norm(F.conv2d(x, w, padding=1), mean, var, gamma, beta, False, 0.0, 1e-3)
+    wf, bf = fold_bn(w, gamma, beta, mean, var, 1e-3)
+    assert torch.allclose(F.conv2d(x, wf, bf, padding=1), ref, rtol=1e-4, atol=1e-4)
+
+    # K order: (source, tap, channel) with 64-channel zero padding per (source, tap)
+    packed = pack_conv_weight(w, [24, 16], 32, 9 * 128).float()
+    assert packed.shape == (32, 1152) and packed[24:].abs().max() == 0
+    wb = w.to(torch.bfloat16).float()
+    for tap in (0, 4, 8):
+        ky, kx = divmod(tap, 3)
+        seg0 = packed[:24, tap * 64: tap * 64 + 64]
+        assert torch.equal(seg0[:, :24], wb[:, :24, ky, kx]) and seg0[:, 24:].abs().max() == 0
+        seg1 = packed[:24, 9 * 64 + tap * 64: 9 * 64 + tap * 64 + 64]
+        assert torch.equal(seg1[:, :16], wb[:, 24:, ky, kx]) and seg1[:, 16:].abs().max() == 0
+
+
+def test_yolo_correct_boxes_matches_oracle():
+    from glsdet_b200.utils_bbox import yolo_correct_boxes
+    from oracle import ref_path
+
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(0, 1, (50, 2)).astype(np.float32)
+    wh = rng.uniform(0, 0.4, (50, 2)).astype(np.float32)
+    for lb in (True, False):
+        a = yolo_correct_boxes(xy, wh, [640, 1024], np.array([540, 1024]), lb)
+        b = ref_path.yolo_correct_boxes(xy, wh, [640, 1024], np.array([540, 1024]), lb)
+        np.testing.assert_array_equal(a, b)
+
+
+def test_cpu_tensors_are_rejected_loudly(native_lib):
+    from glsdet_b200 import _native as N
+    from glsdet_b200.utils_bbox import batched_nms, decode_outputs, non_max_suppression
+
+    with pytest.raises(N.NativeError):
+        decode_outputs([torch.zeros(1, 15, 4, 4)], [32, 32])
+    with pytest.raises(N.NativeError):
+        non_max_suppression(torch.zeros(1, 16, 15), 10, [32, 32], np.array([32, 32]), False)
+    with pytest.raises(N.NativeError):
+        batched_nms(torch.zeros(3, 4), torch.zeros(3), torch.zeros(3), 0.5)

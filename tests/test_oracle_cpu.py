@@ -1,0 +1,105 @@
+"""CPU tests: the oracle restatement against the golden vectors produced by the real reference
+(tests/golden/make_golden.py), and the NMS oracle against torchvision's recorded outputs."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nms_oracle, ref_path
+
+GOLD = Path(__file__).resolve().parent / "golden"
+META = json.loads((GOLD / "meta.json").read_text())
+
+
+def _checksum(sd):
+    return sum(float(v.double().abs().sum()) for k, v in sorted(sd.items()) if v.dtype.is_floating_point)
+
+
+@pytest.mark.parametrize("meta", META["models"], ids=[m["name"] for m in META["models"]])
+def test_oracle_model_matches_reference_golden(meta):
+    z = np.load(GOLD / f"{meta['name']}.npz")
+    sd = ref_path.synthetic_state_dict(meta["nc"], meta["phi"], seed=meta["seed"], flavour=meta["flavour"])
+    assert len(sd) == meta["n_keys"]
+    assert _checksum(sd) == pytest.approx(meta["weight_checksum"], rel=1e-9), "seeded weights differ from the golden run"
+    feats = [torch.from_numpy(z[f"feat{i}"]) for i in range(4)]
+    with torch.no_grad():
+        neck = ref_path.pafpn_neck(sd, feats)
+        logits = ref_path.yolox_head(sd, neck)
+    for i in range(4):
+        np.testing.assert_allclose(neck[i].numpy(), z[f"neck{i}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(logits[i].numpy(), z[f"logits{i}"], rtol=1e-4, atol=2e-5)
+    pred = ref_path.decode_outputs([torch.from_numpy(z[f"logits{i}"]) for i in range(4)], [meta["in_h"], meta["in_w"]])
+    np.testing.assert_allclose(pred.numpy(), z["pred"], rtol=1e-6, atol=1e-7)
+    res = ref_path.non_max_suppression(torch.from_numpy(z["pred"]), meta["nc"], [meta["in_h"], meta["in_w"]],
+                                       np.array(meta["image_shape"]), meta["letterbox"], meta["conf"], meta["nms_thr"],
+                                       strategy="auto_cpu")
+    for b in range(meta["batch"]):
+        assert res[b].shape == z[f"nms{b}"].shape
+        np.testing.assert_array_equal(res[b], z[f"nms{b}"])
+
+
+def test_oracle_postproc_matches_reference_golden():
+    m = META["postproc"]
+    z = np.load(GOLD / "postproc_reference.npz")
+    pred = ref_path.decode_outputs([torch.from_numpy(z[f"logits{i}"]) for i in range(4)], [m["in_h"], m["in_w"]])
+    pred[2, :, 4] = 0.0
+    np.testing.assert_allclose(pred.numpy(), z["pred"], rtol=1e-6, atol=1e-7)
+    res = ref_path.non_max_suppression(torch.from_numpy(z["pred"]), m["nc"], [m["in_h"], m["in_w"]],
+                                       np.array(m["image_shape"]), m["letterbox"], m["conf"], m["nms_thr"], "auto_cpu")
+    assert [len(r) for r in res] == m["kept"]
+    assert res[2].shape == (0, 7)
+    for b in range(m["batch"]):
+        np.testing.assert_array_equal(res[b], z[f"nms{b}"])
+
+
+@pytest.mark.parametrize("case", META["nms"]["cases"], ids=[c["name"] for c in META["nms"]["cases"]])
+def test_nms_oracle_matches_torchvision_golden(case):
+    z = np.load(GOLD / "nms_torchvision.npz")
+    n = case["name"]
+    b, s, l = z[f"{n}_boxes"], z[f"{n}_scores"], z[f"{n}_labels"]
+    for thr in (0.45, 0.65):
+        got_t = nms_oracle.batched_nms(b, s, l, thr, "trick")
+        np.testing.assert_array_equal(got_t, z[f"{n}_keep_trick_{thr}"])
+        got_v = nms_oracle.batched_nms(b, s, l, thr, "per_class")
+        ref_v = z[f"{n}_keep_vanilla_{thr}"]
+        if case["ties"]:  # torch.sort(descending) in the vanilla branch is not stable: tied scores may permute
+            assert sorted(got_v.tolist()) == sorted(ref_v.tolist())
+            np.testing.assert_array_equal(s[got_v], s[ref_v])
+        else:
+            np.testing.assert_array_equal(got_v, ref_v)
+        got_a = nms_oracle.batched_nms(b, s, l, thr, "auto_cpu")
+        if not (case["ties"] and 4 * case["k"] > 4000):
+            np.testing.assert_array_equal(got_a, z[f"{n}_keep_auto_{thr}"])
+
+
+def test_nms_oracle_c_build_matches_scalar_python():
+    rng = np.random.default_rng(5)
+    c = rng.uniform(0, 1, (200, 2))
+    wh = rng.uniform(0.02, 0.3, (200, 2))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    scores = rng.uniform(0, 1, 200).astype(np.float32)
+    for thr in (0.3, 0.5, 0.7):
+        np.testing.assert_array_equal(nms_oracle.nms(boxes, scores, thr), nms_oracle.nms_python(boxes, scores, thr))
+
+
+def test_nms_oracle_live_torchvision():
+    """Same check against the installed torchvision binary, when importable (it is on both boxes)."""
+    tv = pytest.importorskip("torchvision")
+    rng = np.random.default_rng(11)
+    for k in (0, 1, 37, 999, 1001, 2500):
+        c = rng.uniform(0, 1, (k, 2))
+        wh = np.exp(rng.normal(-3, 0.5, (k, 2)))
+        boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        scores = ((rng.permutation(k) + 1) / (k + 1.0)).astype(np.float32)
+        labels = rng.integers(0, 10, k).astype(np.float32)
+        ref = tv.ops.batched_nms(torch.from_numpy(boxes), torch.from_numpy(scores), torch.from_numpy(labels), 0.5)
+        got = nms_oracle.batched_nms(boxes, scores, labels, 0.5, "auto_cpu")
+        np.testing.assert_array_equal(got, ref.numpy())
+
+
+def test_oracle_backbone_runs():
+    sd = ref_path.synthetic_state_dict(3, "tiny", seed=0)
+    feats = ref_path.csp_darknet(sd, torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(0)))
+    assert [tuple(f.shape) for f in feats] == [(1, 48, 16, 16), (1, 96, 8, 8), (1, 192, 4, 4), (1, 384, 2, 2)]

@@ -1,0 +1,275 @@
+"""GPU parity of the whole hot path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): bf16 path - feature maps and logits within 2e-2 relative
+(max |diff| <= 2e-2 * max |ref| and ||diff|| <= 2e-2 * ||ref||); decode within 1e-5; NMS keep sets bit-exact when
+fed identical predictions.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nms_oracle, ref_path
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+META = json.loads((GOLD / "meta.json").read_text())
+TOL = 2e-2
+
+
+def assert_close_rel(got: torch.Tensor, ref: torch.Tensor, tol=TOL, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    d = (got - ref)
+    assert d.abs().max().item() <= tol * ref.abs().max().item(), \
+        f"{what}: max abs diff {d.abs().max().item():.4g} vs {tol} * {ref.abs().max().item():.4g}"
+    assert d.norm().item() <= tol * ref.norm().item(), f"{what}: rel l2 {d.norm().item() / ref.norm().item():.4g}"
+
+
+# ---------------------------------------------------------------------------------------------- small kernels
+def test_layout_converters_roundtrip(native_lib, cuda_device):
+    from glsdet_b200.ops import View, nchw_to_nhwc, nhwc_to_nchw
+
+    g = torch.Generator().manual_seed(0)
+    for (b, c, h, w) in [(2, 64, 16, 24), (1, 48, 7, 9), (3, 200, 5, 33)]:
+        x = torch.randn(b, c, h, w, generator=g).to(cuda_device)
+        buf = torch.zeros(b, h, w, c + 16, device=cuda_device, dtype=torch.bfloat16)
+        nchw_to_nhwc(x, View(buf, 8, c))
+        ref = x.to(torch.bfloat16)
+        assert torch.equal(buf[..., 8:8 + c].permute(0, 3, 1, 2), ref)
+        assert buf[..., :8].abs().max() == 0 and buf[..., 8 + c:].abs().max() == 0
+        back = torch.empty(b, c, h, w, device=cuda_device)
+        nhwc_to_nchw(View(buf, 8, c), back)
+        assert torch.equal(back, ref.float())
+
+
+def test_se_gate_and_pixel_shuffle(native_lib, cuda_device):
+    from glsdet_b200.ops import ScaleShuffleOp, SeGateOp, View
+
+    g = torch.Generator().manual_seed(1)
+    B, H, W, C = 2, 12, 20, 64     # 4C = 256 channels before the shuffle
+    x = torch.randn(B, 4 * C, H, W, generator=g).abs().to(cuda_device)
+    w1 = (torch.randn(16, 4 * C, generator=g) / 16).to(cuda_device)
+    w2 = (torch.randn(4 * C, 16, generator=g) / 4).to(cuda_device)
+    xb = x.to(torch.bfloat16).float()
+    y = torch.sigmoid(F.linear(torch.relu(F.linear(xb.mean((2, 3)), w1)), w2))
+    ref = F.pixel_shuffle(xb + xb * y.view(B, 4 * C, 1, 1), 2)          # ffa.py:77-78
+    perm = torch.arange(4 * C, device=cuda_device).view(C, 4).t().reshape(-1)
+    xin = xb[:, perm].permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)  # channels in (i, j, c) order
+    se = SeGateOp(View(xin), w1[:, perm], w2[perm])
+    se.launch()
+    dst = torch.zeros(B, 2 * H, 2 * W, 2 * C, device=cuda_device, dtype=torch.bfloat16)
+    ScaleShuffleOp(View(xin), se.gate, View(dst, C, C)).launch()
+    torch.cuda.synchronize()
+    assert torch.allclose(se.gate, (1 + y)[:, perm], rtol=1e-5, atol=1e-6)
+    got = dst[..., C:].float().permute(0, 3, 1, 2)
+    assert_close_rel(got, ref, 1e-2, "scale+shuffle")
+    assert dst[..., :C].abs().max() == 0
+
+
+def test_decode_outputs_matches_reference_golden(native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import decode_outputs
+
+    m = META["postproc"]
+    z = np.load(GOLD / "postproc_reference.npz")
+    logits = [torch.from_numpy(z[f"logits{i}"]).to(cuda_device) for i in range(4)]
+    keep = [t.clone() for t in logits]
+    pred = decode_outputs(logits, [m["in_h"], m["in_w"]]).cpu()
+    ref = torch.from_numpy(z["pred"]).clone()
+    pred[2, :, 4] = 0.0
+    assert torch.allclose(pred, ref, rtol=1e-5, atol=1e-6)
+    for a, b in zip(logits, keep):
+        assert torch.equal(a, b), "decode_outputs must not modify its inputs (utils_bbox.py:266 works on a copy)"
+
+
+# ---------------------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("case", META["nms"]["cases"], ids=[c["name"] for c in META["nms"]["cases"]])
+def test_batched_nms_bit_exact_vs_torchvision_golden(case, native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import batched_nms
+
+    z = np.load(GOLD / "nms_torchvision.npz")
+    n = case["name"]
+    b, s, l = (torch.from_numpy(z[f"{n}_{k}"]).to(cuda_device) for k in ("boxes", "scores", "labels"))
+    for thr in (0.45, 0.65):
+        got = batched_nms(b, s, l, thr, "trick").cpu().numpy()
+        np.testing.assert_array_equal(got, z[f"{n}_keep_trick_{thr}"])
+        got = batched_nms(b, s, l, thr, "per_class").cpu().numpy()
+        ref = z[f"{n}_keep_vanilla_{thr}"]
+        if case["ties"]:   # the reference's final sort is unstable for tied scores; ours breaks ties by index
+            np.testing.assert_array_equal(got, nms_oracle.batched_nms(z[f"{n}_boxes"], z[f"{n}_scores"],
+                                                                      z[f"{n}_labels"], thr, "per_class"))
+            assert sorted(got.tolist()) == sorted(ref.tolist())
+        else:
+            np.testing.assert_array_equal(got, ref)
+        got = batched_nms(b, s, l, thr, "auto_cpu").cpu().numpy()
+        if not case["ties"]:
+            np.testing.assert_array_equal(got, z[f"{n}_keep_auto_{thr}"])
+
+
+def _clustered(rng, k, nc, spread=0.004, lo=0.05):
+    g = max(4, k // 12)
+    cen = rng.uniform(lo, 0.95, (g, 2))
+    which = rng.integers(0, g, k)
+    c = cen[which] + rng.normal(0, spread, (k, 2))
+    wh = np.exp(rng.normal(-3.2, 0.4, (g, 2)))[which] * np.exp(rng.normal(0, 0.15, (k, 2)))
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    scores = ((rng.permutation(k) + 1) / (k + 1.0)).astype(np.float32)
+    labels = rng.integers(0, nc, k).astype(np.float32)
+    return boxes, scores, labels
+
+
+@pytest.mark.parametrize("k,nc", [(2, 1), (63, 3), (64, 3), (65, 10), (4095, 10), (4096, 10), (4097, 10), (9000, 10),
+                                  (20000, 4), (40000, 80)])
+def test_batched_nms_random_vs_oracle(k, nc, native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import batched_nms
+
+    rng = np.random.default_rng(k * 131 + nc)
+    boxes, scores, labels = _clustered(rng, k, nc)
+    tb, ts, tl = (torch.from_numpy(a).to(cuda_device) for a in (boxes, scores, labels))
+    for strat in ("trick", "per_class"):
+        got = batched_nms(tb, ts, tl, 0.6, strat).cpu().numpy()
+        ref = nms_oracle.batched_nms(boxes, scores, labels, 0.6, strat)
+        np.testing.assert_array_equal(got, ref)
+        assert 0 < len(got) < k or k < 64
+
+
+def test_batched_nms_edge_cases(native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import batched_nms
+
+    dev = cuda_device
+    e = batched_nms(torch.zeros(0, 4, device=dev), torch.zeros(0, device=dev), torch.zeros(0, device=dev), 0.5)
+    assert e.shape == (0,) and e.dtype == torch.int64
+    # identical boxes, tied scores: the first index wins (stable sort), everything else is suppressed
+    b = torch.tensor([[0.1, 0.1, 0.5, 0.5]] * 5, device=dev)
+    s = torch.full((5,), 0.7, device=dev)
+    l = torch.zeros(5, device=dev)
+    assert batched_nms(b, s, l, 0.5, "trick").tolist() == [0]
+    # different classes never suppress each other
+    l2 = torch.arange(5, device=dev, dtype=torch.float32)
+    assert batched_nms(b, s, l2, 0.5, "trick").tolist() == [0, 1, 2, 3, 4]
+    assert batched_nms(b, s, l2, 0.5, "per_class").tolist() == [0, 1, 2, 3, 4]
+    # zero-area boxes: IoU is 0/0 = NaN and never suppresses (torchvision semantics)
+    z = torch.tensor([[0.3, 0.3, 0.3, 0.3]] * 3, device=dev)
+    assert batched_nms(z, torch.tensor([0.9, 0.8, 0.7], device=dev), torch.zeros(3, device=dev), 0.5).tolist() == [0, 1, 2]
+    # boxes far outside the image (min coordinate < -0.5) force the literal class-agnostic coordinate trick
+    rng = np.random.default_rng(3)
+    boxes, scores, labels = _clustered(rng, 700, 6)
+    boxes -= 2.0
+    got = batched_nms(*(torch.from_numpy(a).to(dev) for a in (boxes, scores, labels)), 0.5, "trick").cpu().numpy()
+    np.testing.assert_array_equal(got, nms_oracle.batched_nms(boxes, scores, labels, 0.5, "trick"))
+
+
+def test_non_max_suppression_matches_reference_golden(native_lib, cuda_device):
+    """Reference decode + NMS outputs recorded on the CPU (torchvision auto dispatch for CPU tensors)."""
+    from glsdet_b200.utils_bbox import non_max_suppression
+
+    m = META["postproc"]
+    z = np.load(GOLD / "postproc_reference.npz")
+    pred = torch.from_numpy(z["pred"]).to(cuda_device)
+    before = pred.clone()
+    res = non_max_suppression(pred, m["nc"], [m["in_h"], m["in_w"]], np.array(m["image_shape"]), m["letterbox"],
+                              conf_thres=m["conf"], nms_thres=m["nms_thr"], strategy="auto_cpu")
+    assert torch.equal(pred, before)
+    assert [len(r) for r in res] == m["kept"] and res[2].shape == (0, 7) and res[0].dtype == np.float32
+    for b in range(m["batch"]):
+        np.testing.assert_array_equal(res[b], z[f"nms{b}"])
+    assert non_max_suppression(torch.zeros(2, 0, 15, device=cuda_device), 10, [32, 32], np.array([32, 32]), False) == [None, None]
+
+
+def test_device_nms_full_anchor_count_properties(native_lib, cuda_device):
+    """BASELINE config 2 anchor count (87 040 per image): size-independent properties + oracle on one image."""
+    from glsdet_b200.utils_bbox import DeviceNMS
+
+    B, A, nc = 4, 87040, 10
+    g = torch.Generator().manual_seed(5)
+    pred = torch.rand(B, A, 5 + nc, generator=g)
+    pred[..., 0:2] = torch.rand(B, A, 2, generator=g)
+    pred[..., 2:4] = torch.rand(B, A, 2, generator=g) * 0.08 + 0.01
+    pred[..., 4] = torch.rand(B, A, generator=g) ** 4
+    pred[3, :, 4] = 0.0
+    dpred = pred.to(cuda_device)
+    op = DeviceNMS(B, A, nc)
+    det, cnt = op.launch(dpred, 0.3, 0.5, "auto_cuda")
+    torch.cuda.synchronize()
+    cnt = cnt.cpu().numpy()
+    assert cnt[3] == 0 and (cnt[:3] > 0).all()
+    det_h = det.cpu().numpy()
+    ref = ref_path.non_max_suppression(pred[:1], nc, [1024, 1024], None, False, 0.3, 0.5, strategy="auto_cuda",
+                                       correct_boxes=False)
+    np.testing.assert_array_equal(det_h[0, :cnt[0]], ref[0])
+    for b in range(3):
+        rows = det_h[b, :cnt[b]]
+        sc = rows[:, 4] * rows[:, 5]
+        assert (np.diff(sc) <= 0).all(), "rows must be sorted by score"
+        assert (sc >= 0.3).all()
+        # idempotence: NMS of the survivors keeps all of them
+        again = nms_oracle.batched_nms(rows[:, :4], sc, rows[:, 6], 0.5, "auto_cuda")
+        assert len(again) == len(rows)
+
+
+# ---------------------------------------------------------------------------------------------- whole model
+@pytest.mark.parametrize("meta", META["models"], ids=[m["name"] for m in META["models"]])
+def test_model_matches_reference_golden(meta, native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import decode_outputs, non_max_suppression
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    z = np.load(GOLD / f"{meta['name']}.npz")
+    sd = ref_path.synthetic_state_dict(meta["nc"], meta["phi"], seed=meta["seed"], flavour=meta["flavour"])
+    net = YoloBody(meta["nc"], meta["phi"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    feats = [torch.from_numpy(z[f"feat{i}"]).to(cuda_device) for i in range(4)]
+
+    neck = net.backbone.forward_features(feats)
+    for i in range(1, 4):
+        assert_close_rel(neck[i], torch.from_numpy(z[f"neck{i}"]), TOL, f"neck{i}")
+    logits = net.forward_features(feats)
+    for i in range(4):
+        assert_close_rel(logits[i], torch.from_numpy(z[f"logits{i}"]), TOL, f"logits{i}")
+    # stand-alone head module fed with the reference's own neck outputs
+    hl = net.head([torch.from_numpy(z[f"neck{i}"]).to(cuda_device) for i in range(4)])
+    for i in range(4):
+        assert_close_rel(hl[i], torch.from_numpy(z[f"logits{i}"]), TOL, f"head-only logits{i}")
+    # fused decode == decode_outputs(raw logits) on our own logits
+    pred_fused = net.decode_features(feats)
+    pred_sep = decode_outputs(logits, [meta["in_h"], meta["in_w"]])
+    assert torch.allclose(pred_fused, pred_sep, rtol=1e-5, atol=1e-6)
+    # post-processing fed with the reference's own predictions: bit-exact rows
+    res = non_max_suppression(torch.from_numpy(z["pred"]).to(cuda_device), meta["nc"], [meta["in_h"], meta["in_w"]],
+                              np.array(meta["image_shape"]), meta["letterbox"], meta["conf"], meta["nms_thr"], "auto_cpu")
+    for b in range(meta["batch"]):
+        np.testing.assert_array_equal(res[b], z[f"nms{b}"])
+
+
+def test_model_vs_oracle_1024_and_batch_invariance(native_lib, cuda_device):
+    """BASELINE config 2 shape (P0-s, 1024x1024): one image against the oracle, then batch-of-4 == 4 x batch-of-1."""
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    nc = 10
+    sd = ref_path.synthetic_state_dict(nc, "s", seed=11)
+    net = YoloBody(nc, "s")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    g = torch.Generator().manual_seed(12)
+    feats = [torch.randn(4, c, 1024 // s, 1024 // s, generator=g) for c, s in ((64, 4), (128, 8), (256, 16), (512, 32))]
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = ref_path.neck_head(sd, [f[:1] for f in feats])
+    dfeats = [f.to(cuda_device) for f in feats]
+    out4 = net.forward_features(dfeats)
+    for i in range(4):
+        assert_close_rel(out4[i][:1], ref[i], TOL, f"1024 logits{i}")
+    pred4 = net.decode_features(dfeats).clone()
+    ref_pred = ref_path.decode_outputs(ref, [1024, 1024])
+    assert pred4.shape == (4, 87040, 15)
+    assert (pred4[:1, :, :2].cpu() - ref_pred[..., :2]).abs().max() <= 0.25, "box centres far from the oracle"
+    assert (pred4[:1, :, 4:].cpu() - ref_pred[..., 4:]).abs().max() <= 0.05, "probabilities far from the oracle"
+    for b in range(4):
+        one = net.decode_features([f[b:b + 1].contiguous() for f in dfeats])
+        assert torch.equal(one[0], pred4[b]), "results must not depend on the batch an image is in"
+    det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65)
+    torch.cuda.synchronize()
+    assert (cnt.cpu() >= 0).all() and det.shape[0] == 4
