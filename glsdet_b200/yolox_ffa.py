@@ -333,6 +333,14 @@ class YoloBody(_PlanOwner):
         """decode_outputs(forward(...)) fused: [B, A, 5+nc] (cx, cy, w, h normalised, obj, cls)."""
         return self.plan_for(feats).forward_decoded(feats)
 
+    def nms_for(self, plan: FFAPathPlan, max_det: Optional[int] = None) -> DeviceNMS:
+        key = (plan.B, plan.num_anchors, self.num_classes, max_det, str(plan.device))
+        nms = self._nms.get(key)
+        if nms is None:
+            nms = DeviceNMS(plan.B, plan.num_anchors, self.num_classes, max_det=max_det, device=plan.device)
+            self._nms = {key: nms}
+        return nms
+
     @torch.no_grad()
     def detect_features(self, feats: Sequence[torch.Tensor], conf_thres: float = 0.5, nms_thres: float = 0.4,
                         strategy: str = "auto_cuda", max_det: Optional[int] = None):
@@ -340,12 +348,7 @@ class YoloBody(_PlanOwner):
         (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score."""
         plan = self.plan_for(feats)
         pred = plan.forward_decoded(feats)
-        key = (plan.B, plan.num_anchors, self.num_classes, max_det, str(plan.device))
-        nms = self._nms.get(key)
-        if nms is None:
-            nms = DeviceNMS(plan.B, plan.num_anchors, self.num_classes, max_det=max_det, device=plan.device)
-            self._nms = {key: nms}
-        return nms.launch(pred, conf_thres, nms_thres, strategy)
+        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy)
 
     @torch.no_grad()
     def detect(self, x: torch.Tensor, **kw):

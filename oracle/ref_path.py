@@ -234,116 +234,6 @@ def non_max_suppression(prediction: torch.Tensor, num_classes: int, input_shape,
 
 
 # ------------------------------------------------------------------------------------------ synthetic weights
-def p0_state_dict_shapes(num_classes: int, phi: str) -> Dict[str, tuple]:
-    """Shapes of every state_dict entry of models/ffa/yolox_ffa.py YoloBody(num_classes, phi)."""
-    depth = {"tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
-    width = {"tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
-    shapes: Dict[str, tuple] = {}
-
-    def bc(p, cin, cout, k):
-        shapes[p + ".conv.weight"] = (cout, cin, k, k)
-        for n in ("weight", "bias", "running_mean", "running_var"):
-            shapes[f"{p}.bn.{n}"] = (cout,)
-        shapes[p + ".bn.num_batches_tracked"] = ()
-
-    def csp(p, cin, cout, n):
-        hid = int(cout * 0.5)
-        bc(p + ".conv1", cin, hid, 1)
-        bc(p + ".conv2", cin, hid, 1)
-        bc(p + ".conv3", 2 * hid, cout, 1)
-        for j in range(n):
-            bc(f"{p}.m.{j}.conv1", hid, hid, 1)
-            bc(f"{p}.m.{j}.conv2", hid, hid, 3)
-
-    base = int(width * 64)
-    bdep = max(round(depth * 3), 1)
-    bb = "backbone.backbone"
-    bc(f"{bb}.stem.conv", 12, base, 3)
-    for name, cin, cout, n in (("dark2", base, base * 2, bdep), ("dark3", base * 2, base * 4, bdep * 3),
-                               ("dark4", base * 4, base * 8, bdep * 3)):
-        bc(f"{bb}.{name}.0", cin, cout, 3)
-        csp(f"{bb}.{name}.1", cout, cout, n)
-    bc(f"{bb}.dark5.0", base * 8, base * 16, 3)
-    bc(f"{bb}.dark5.1.conv1", base * 16, base * 8, 1)
-    bc(f"{bb}.dark5.1.conv2", base * 32, base * 16, 1)
-    csp(f"{bb}.dark5.2", base * 16, base * 16, bdep)
-
-    c0, c1, c2 = int(256 * width), int(512 * width), int(1024 * width)
-    n = round(3 * depth)
-    bc("backbone.lateral_conv0", c2, c1, 1)
-    csp("backbone.C3_p4", 2 * c1, c1, n)
-    bc("backbone.reduce_conv1", c1, c0, 1)
-    csp("backbone.C3_p3", 2 * c0, c0, n)
-    bc("backbone.bu_conv2", c0, c0, 3)
-    csp("backbone.C3_n3", 2 * c0, c1, n)
-    bc("backbone.bu_conv1", c1, c1, 3)
-    csp("backbone.C3_n4", 2 * c1, c2, n)
-
-    hc = int(256 * width)
-    csp("head.csp", int(0.5 * 256 * width), hc, round(3 * 0.75))
-    f = "head.ftt"
-    bc(f + ".scale", 2 * hc, 4 * hc, 1)
-    bc(f + ".create_content_extractor.0", 4 * hc, 4 * hc, 1)
-    bc(f + ".create_content_extractor.1", 4 * hc, 4 * hc, 1)
-    bc(f + ".create_text_extractor.0", 2 * hc, 2 * hc, 1)
-    bc(f + ".conv3", 2 * hc, hc, 1)
-    shapes[f + ".se1.fc.0.weight"] = (4 * hc // 16, 4 * hc)
-    shapes[f + ".se1.fc.2.weight"] = (4 * hc, 4 * hc // 16)
-    for i, cin in enumerate((c0, c1, c2)):
-        bc(f"head.stems.{i}", cin, hc, 1)
-    for i in range(4):
-        for br in ("cls_convs", "reg_convs"):
-            bc(f"head.{br}.{i}.0", hc, hc, 3)
-            bc(f"head.{br}.{i}.1", hc, hc, 3)
-        for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
-            shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
-            shapes[f"head.{name}.{i}.bias"] = (co,)
-    return shapes
-
-
-def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str = "kaiming") -> StateDict:
-    """Random-init weights for the P0 architecture.
-
-    flavour "reference": what train.py does - default PyTorch init then weights_init(normal, 0.02)
-        (models/ffa/yolox_losses.py:402-421): conv weights N(0, 0.02), BN gamma N(1, 0.02), beta 0, stats (0, 1).
-        Activations collapse towards zero through the depth (gain < 1 per layer), so it exercises the kernels
-        poorly and every anchor scores ~0.25.
-    flavour "kaiming": variance-preserving conv init, randomised BN statistics, prediction biases at the YOLOX
-        prior (-log((1-p)/p), p = 0.01) and wider prediction weights, so that feature maps stay O(1) at every
-        depth and scores/boxes have a realistic spread.  Used for parity at full depth and for the benchmark.
-    """
-    g = torch.Generator().manual_seed(seed)
-    sd: StateDict = {}
-    for k, shp in p0_state_dict_shapes(num_classes, phi).items():
-        if k.endswith("num_batches_tracked"):
-            sd[k] = torch.zeros((), dtype=torch.long)
-        elif k.endswith(".conv.weight"):
-            fan_in = shp[1] * shp[2] * shp[3]
-            std = 0.02 if flavour == "reference" else math.sqrt(2.0 / fan_in)
-            sd[k] = torch.randn(shp, generator=g) * std
-        elif ".bn." in k:
-            if flavour == "reference":
-                sd[k] = {"weight": 1.0 + 0.02 * torch.randn(shp, generator=g), "bias": torch.zeros(shp),
-                         "running_mean": torch.zeros(shp), "running_var": torch.ones(shp)}[k.rsplit(".", 1)[1]]
-            else:
-                sd[k] = {"weight": 1.0 + 0.1 * torch.randn(shp, generator=g),
-                         "bias": 0.1 * torch.randn(shp, generator=g),
-                         "running_mean": 0.1 * torch.randn(shp, generator=g),
-                         "running_var": 0.5 + torch.rand(shp, generator=g)}[k.rsplit(".", 1)[1]]
-        elif ".fc." in k:
-            sd[k] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
-        elif k.endswith("_preds.0.weight") or "_preds." in k and k.endswith(".weight"):
-            fan_in = shp[1]
-            std = 0.02 if flavour == "reference" else 2.0 * math.sqrt(1.0 / fan_in)
-            sd[k] = torch.randn(shp, generator=g) * std
-        elif "_preds." in k and k.endswith(".bias"):
-            if flavour == "reference":
-                bound = 1.0 / math.sqrt(1.0)
-                sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * 0.05 * bound
-            elif "reg_preds" in k:
-                sd[k] = 0.5 * torch.randn(shp, generator=g)
-            else:
-                sd[k] = torch.full(shp, -math.log((1 - 0.01) / 0.01)) + 0.2 * torch.randn(shp, generator=g)
-        else:
-            raise KeyError(k)
-    return sd
+# The seeded weight generator is plain data generation (no algorithm of the path); it lives in the package so that
+# bench.py's product arm can use it without touching oracle/.
+from glsdet_b200.synthetic import p0_state_dict_shapes, synthetic_state_dict  # noqa: E402,F401

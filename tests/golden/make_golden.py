@@ -164,9 +164,9 @@ def main():
     torch.set_num_threads(8)
     yf, ub = import_reference()
     metas = {}
-    m1, keys = run_model_case(yf, ub, "p0_s_kaiming", "s", 10, "kaiming", 1, 2, 64, 96, 0.02, 0.65)
+    m1, keys = run_model_case(yf, ub, "p0_s_calibrated", "s", 10, "calibrated", 1, 2, 64, 96, 0.01, 0.65)
     m2, _ = run_model_case(yf, ub, "p0_s_refinit", "s", 10, "reference", 2, 1, 64, 64, 0.01, 0.65)
-    m3, keys_t = run_model_case(yf, ub, "p0_tiny_kaiming", "tiny", 3, "kaiming", 3, 1, 96, 64, 0.02, 0.65)
+    m3, keys_t = run_model_case(yf, ub, "p0_tiny_calibrated", "tiny", 3, "calibrated", 3, 1, 96, 64, 0.01, 0.65)
     metas["models"] = [m1, m2, m3]
     metas["nms"] = nms_cases()
     metas["postproc"] = postproc_case(ub)

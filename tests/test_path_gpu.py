@@ -250,12 +250,13 @@ def test_model_vs_oracle_1024_and_batch_invariance(native_lib, cuda_device):
     from glsdet_b200.yolox_ffa import YoloBody
 
     nc = 10
-    sd = ref_path.synthetic_state_dict(nc, "s", seed=11)
+    sd = ref_path.synthetic_state_dict(nc, "s", seed=11, flavour="calibrated")
     net = YoloBody(nc, "s")
     net.load_state_dict(sd, strict=True)
     net = net.to(cuda_device).eval()
-    g = torch.Generator().manual_seed(12)
-    feats = [torch.randn(4, c, 1024 // s, 1024 // s, generator=g) for c, s in ((64, 4), (128, 8), (256, 16), (512, 32))]
+    from glsdet_b200.synthetic import synthetic_images
+
+    feats = ref_path.csp_darknet(sd, synthetic_images(4, 1024, 1024, seed=12))
     torch.set_num_threads(max(1, torch.get_num_threads()))
     ref = ref_path.neck_head(sd, [f[:1] for f in feats])
     dfeats = [f.to(cuda_device) for f in feats]

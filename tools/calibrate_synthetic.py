@@ -1,0 +1,85 @@
+"""Developer tool: make the seeded synthetic weights behave like a trained network.
+
+A random network without normalisation drifts (activations grow ~1.3x per layer), which gives absurd logits and
+a degenerate NMS load.  Real checkpoints have BatchNorm statistics that match their activations; this tool gives
+the synthetic ones the same property: it runs the CPU oracle once on seeded noise images, sets every BatchNorm's
+running_mean / running_var to the statistics of the conv output feeding it (exactly what BN training would have
+recorded), and rescales the prediction convs so that obj / cls logits have a standard deviation of 2.0 / 0.5 around the
+YOLOX prior and the box regressors 0.15.  Only those tensors are stored, as
+glsdet_b200/data/calib_p0_<phi>_nc<nc>_seed<seed>.npz; glsdet_b200.synthetic.synthetic_state_dict(flavour=
+"calibrated") overlays them on the seeded base weights.  (Uses oracle/, so it is a tool, not product code.)
+
+    python tools/calibrate_synthetic.py --phi s --nc 10 --seed 0
+"""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict  # noqa: E402
+from oracle import ref_path  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--phi", default="s")
+    ap.add_argument("--nc", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--obj-std", type=float, default=2.0)
+    ap.add_argument("--cls-std", type=float, default=0.5)
+    args = ap.parse_args()
+    torch.set_num_threads(8)
+    sd = synthetic_state_dict(args.nc, args.phi, seed=args.seed, flavour="kaiming")
+    changed = {}
+    orig = ref_path.base_conv
+
+    def calibrating_base_conv(sd_, p, x, stride=1, act="silu"):
+        w = sd_[p + ".conv.weight"]
+        y = F.conv2d(x, w, None, stride=stride, padding=(w.shape[-1] - 1) // 2)
+        sd_[p + ".bn.running_mean"] = y.mean(dim=(0, 2, 3))
+        sd_[p + ".bn.running_var"] = y.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-4)
+        changed[p + ".bn.running_mean"] = sd_[p + ".bn.running_mean"]
+        changed[p + ".bn.running_var"] = sd_[p + ".bn.running_var"]
+        return orig(sd_, p, x, stride, act)
+
+    ref_path.base_conv = calibrating_base_conv
+    x = synthetic_images(2, args.size, args.size, seed=args.seed + 4242)
+    with torch.no_grad():
+        feats = ref_path.csp_darknet(sd, x)
+        neck = ref_path.pafpn_neck(sd, feats)
+        # towers: rescale the prediction convs on the calibrated tower outputs
+        zz = ref_path.ffa(sd, "head.ftt", neck[1], neck[2])
+        proc = [ref_path.csp_layer(sd, "head.csp", neck[0]) + F.interpolate(zz, scale_factor=2, mode="nearest")]
+        proc += [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
+        for k, xk in enumerate(proc):
+            i = 3 if k == 0 else k - 1
+            cf = ref_path.base_conv(sd, f"head.cls_convs.{i}.1", ref_path.base_conv(sd, f"head.cls_convs.{i}.0", xk))
+            rf = ref_path.base_conv(sd, f"head.reg_convs.{i}.1", ref_path.base_conv(sd, f"head.reg_convs.{i}.0", xk))
+            for name, feat, target in (("cls_preds", cf, args.cls_std), ("obj_preds", rf, args.obj_std), ("reg_preds", rf, 0.15)):
+                key = f"head.{name}.{i}.weight"
+                y = F.conv2d(feat, sd[key])
+                std = y.std(dim=(0, 2, 3)).clamp_min(1e-6)
+                sd[key] = sd[key] * (target / std).view(-1, 1, 1, 1)
+                changed[key] = sd[key]
+    ref_path.base_conv = orig
+    out = ROOT / "glsdet_b200" / "data" / f"calib_p0_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
+    np.savez_compressed(out, **{k: v.numpy().astype(np.float32) for k, v in changed.items()})
+    # report
+    with torch.no_grad():
+        lg = ref_path.yolox_head(sd, neck)
+        pred = ref_path.decode_outputs(lg, [args.size, args.size])
+    sc = pred[:, :, 4] * pred[:, :, 5:].max(2)[0]
+    print(out.name, f"{out.stat().st_size/1e3:.0f} kB", "anchors", pred.shape[1], "cand@0.01", (sc >= 0.01).sum(1).tolist(),
+          "neck std", [round(float(t.std()), 2) for t in neck], "logit std", [round(float(l.std()), 2) for l in lg])
+    res = ref_path.non_max_suppression(pred, args.nc, [args.size, args.size], None, False, 0.01, 0.65, correct_boxes=False)
+    print("kept", [len(r) for r in res])
+
+
+if __name__ == "__main__":
+    main()
