@@ -1,7 +1,15 @@
 // Post-processing of the GLSDet path on the device, without host synchronisation:
 //   score filter (obj * max cls >= conf)  ->  warp-ballot compaction  ->  per-image bitonic sort of
-//   (class, score desc, anchor) keys  ->  per-(image, class) greedy NMS with 64-wide IoU bitmasks  ->
-//   rank of every kept box among all kept boxes of its image (binary searches)  ->  [K,7] rows, score desc.
+//   (class, score desc, anchor) keys  ->  per-(image, class) greedy NMS  ->  rank of every kept box among all
+//   kept boxes of its image (binary searches)  ->  [K,7] rows, score desc.
+//
+// NMS proper, per (image, class) segment of n score-sorted boxes:
+//   1. mask_tiles_kernel  - all 64x64 IoU tiles of the upper triangle, one 64-bit suppression word per (row,
+//      column tile), computed by the whole GPU (persistent CTAs pulling tiles from a device-side work list);
+//   2. scan_kernel        - one CTA per segment walks the 64-box chunks in order: the diagonal word resolves the
+//      chunk greedily, the kept rows' words are OR-ed into the 'removed' bitmap of the later chunks.
+//   Segments whose mask does not fit the workspace budget fall back to nms_segment_kernel (blocked greedy against
+//   the kept list, no mask memory).  Both are the same greedy algorithm and give identical keep sets.
 //
 // Replaces non_max_suppression (yolox-drone/models/core/utils_bbox.py:375-484) and the torchvision
 // batched_nms it calls (:414-419).  Bit-exactness contract (see include/glsdet_b200.h): same keep set and
@@ -14,6 +22,7 @@
 //     falls back to one class-agnostic segment on the shifted boxes, which is the literal algorithm.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -102,7 +111,14 @@ struct Work {
   uint8_t* cand_label;   // [B][cap]
   uint64_t* keys;        // [B][P]
   uint64_t* kept_key;    // [B][cap]
-  float4* kept_box;      // [B][cap]   spill of the kept list beyond shared memory
+  float4* kept_box;      // [B][cap]   spill of the kept list beyond shared memory (fallback kernel)
+  float4* nbox;          // [B][cap]   NMS-space box of every sorted candidate (offset applied for the trick)
+  int32_t* seg_tile_off; // [B*nc + 1] exclusive prefix of per-segment tile counts (mask path)
+  int64_t* seg_word_off; // [B*nc]     first mask word of the segment, or -1 when it runs on the fallback kernel
+  int32_t* tile_counter; // [1]        work-list cursor of mask_tiles_kernel
+  unsigned long long* mask;  // [mask_words]
+  int64_t mask_words;
+  int32_t max_scan_tiles;    // segments with more 64-box chunks than this use the fallback kernel
 };
 
 struct ImageMode {
@@ -301,6 +317,192 @@ __device__ __forceinline__ bool iou_exceeds(const float4& a, float aarea, const 
   return ovr > thr;
 }
 
+// NMS-space box of every sorted candidate: raw box, or box + label * (max_coord + 1) for the coordinate trick
+template <bool kFromPred>
+__global__ void __launch_bounds__(256) box_prep_kernel(Source s, Work w, int strategy) {
+  const int b = blockIdx.y;
+  const int n = w.cand_count[b];
+  const ImageMode m = image_mode(w, b, strategy);
+  const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const Cand c = load_cand<kFromPred>(s, b, static_cast<int>(key_idx(keys[i])));
+    float4 bx = c.box;
+    if (m.use_offsets) {
+      // boxes.py _batched_nms_coordinate_trick: offsets = idxs * (max_coordinate + 1); boxes + offsets[:, None]
+      const float off = __fmul_rn(c.label_f, m.offset_scale);
+      bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
+      bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
+    }
+    w.nbox[static_cast<int64_t>(b) * w.cap + i] = bx;
+  }
+}
+
+// word index of (row tile r, row-in-tile i, column tile c >= r) in the upper-triangular mask of a T-tile segment
+__device__ __forceinline__ int64_t tri_word(int T, int r, int i, int c) {
+  return 64ll * (static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2) +
+         static_cast<int64_t>(i) * (T - r) + (c - r);
+}
+
+__device__ __forceinline__ float box_area(const float4& b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+// One block: decide which segments get a bitmask (in segment order, until the word budget is spent) and build the
+// tile work list.  Segment ids are b * nc + c.
+__global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
+  __shared__ long long s_words[1024];
+  __shared__ int s_tiles[1024];
+  __shared__ long long carry_words;
+  __shared__ int carry_tiles;
+  const int total = w.B * w.nc;
+  if (threadIdx.x == 0) { carry_words = 0; carry_tiles = 0; *w.tile_counter = 0; }
+  __syncthreads();
+  for (int base = 0; base < total; base += 1024) {
+    const int sgm = base + threadIdx.x;
+    long long words = 0;
+    int tiles = 0, n = 0, T = 0;
+    if (sgm < total) {
+      const int b = sgm / w.nc, c = sgm % w.nc;
+      n = w.seg_start[b * (w.nc + 1) + c + 1] - w.seg_start[b * (w.nc + 1) + c];
+      T = (n + 63) >> 6;
+      if (T <= w.max_scan_tiles && T < 46000) {  // T*T must fit an int; larger segments go to the fallback
+        words = 32ll * T * (T + 1);  // upper triangle only: row tile r stores T - r words per row
+        tiles = T * T;
+      }
+    }
+    s_words[threadIdx.x] = words;
+    s_tiles[threadIdx.x] = tiles;
+    __syncthreads();
+    // serial prefix by thread 0 over <= 1024 entries: the budget cut-off is order dependent and tiny
+    if (threadIdx.x == 0) {
+      long long cw = carry_words;
+      int ct = carry_tiles;
+      for (int i = 0; i < 1024 && base + i < total; ++i) {
+        const long long wd = s_words[i];
+        const bool fits = wd > 0 && cw + wd <= w.mask_words && s_tiles[i] > 0 && ct + s_tiles[i] > ct;
+        w.seg_tile_off[base + i] = ct;
+        w.seg_word_off[base + i] = fits ? cw : -1;
+        if (fits) { cw += wd; ct += s_tiles[i]; }
+      }
+      carry_words = cw;
+      carry_tiles = ct;
+      if (base + 1024 >= total) w.seg_tile_off[total] = ct;
+    }
+    __syncthreads();
+  }
+}
+
+// Persistent CTAs of 64 threads: each pulls 64x64 tiles (row tile r, column tile c >= r) from the work list.
+__global__ void __launch_bounds__(64) mask_tiles_kernel(Work w, float thr) {
+  __shared__ float4 cbox[64];
+  __shared__ float carea[64];
+  __shared__ int s_tile;
+  const int total_seg = w.B * w.nc;
+  const int total_tiles = w.seg_tile_off[total_seg];
+  const bool thr_nonneg = (thr >= 0.0f);
+  const int tid = threadIdx.x;
+  while (true) {
+    if (tid == 0) s_tile = atomicAdd(w.tile_counter, 1);
+    __syncthreads();
+    const int t = s_tile;
+    if (t >= total_tiles) break;
+    // segment owning tile t: last entry with seg_tile_off <= t among mask-path segments
+    int lo = 0, hi = total_seg;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (w.seg_tile_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    // skip forward over zero-tile (empty / fallback) segments sharing the same offset
+    while (w.seg_tile_off[lo + 1] <= t) ++lo;
+    const int sgm = lo;
+    const int b = sgm / w.nc, c = sgm % w.nc;
+    const int s0 = w.seg_start[b * (w.nc + 1) + c];
+    const int n = w.seg_start[b * (w.nc + 1) + c + 1] - s0;
+    const int T = (n + 63) >> 6;
+    const int local = t - w.seg_tile_off[sgm];
+    const int r = local / T, cc = local % T;
+    if (cc >= r) {
+      const float4* bx = w.nbox + static_cast<int64_t>(b) * w.cap + s0;
+      const int cj = cc * 64 + tid;
+      if (cj < n) { cbox[tid] = bx[cj]; carea[tid] = box_area(cbox[tid]); }
+      __syncthreads();
+      const int ri = r * 64 + tid;
+      if (ri < n) {
+        const float4 rb = bx[ri];
+        const float ra = box_area(rb);
+        const int jn = min(64, n - cc * 64);
+        unsigned long long bits = 0ull;
+        for (int j = (cc == r) ? tid + 1 : 0; j < jn; ++j)
+          if (iou_exceeds(rb, ra, cbox[j], carea[j], thr, thr_nonneg)) bits |= (1ull << j);
+        w.mask[w.seg_word_off[sgm] + tri_word(T, r, tid, cc)] = bits;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// One CTA (32 warps) per mask-path segment: sequential over 64-box chunks, parallel inside.
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
+  extern __shared__ unsigned long long removed[];  // [T]
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long kept_bits_s;
+  __shared__ int kept_rows[64];
+  __shared__ int kept_n;
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const int sgm = b * w.nc + seg;
+  const int64_t woff = w.seg_word_off[sgm];
+  if (woff < 0) return;  // empty, or handled by nms_segment_kernel
+  const int s0 = w.seg_start[b * (w.nc + 1) + seg];
+  const int n = w.seg_start[b * (w.nc + 1) + seg + 1] - s0;
+  const int T = (n + 63) >> 6;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const unsigned long long* mask = w.mask + woff;
+  const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
+  uint64_t* gk_key = w.kept_key + static_cast<int64_t>(b) * w.cap + s0;
+  for (int i = tid; i < T; i += kScanThreads) removed[i] = 0ull;
+  if (tid == 0) kept_n = 0;
+  __syncthreads();
+  for (int r = 0; r < T; ++r) {
+    const int mcnt = min(64, n - r * 64);
+    if (tid < mcnt) diag[tid] = mask[tri_word(T, r, tid, r)];
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long alive = ~removed[r];
+      if (mcnt < 64) alive &= ((1ull << mcnt) - 1ull);
+      unsigned long long kept = 0ull;
+      int nk = 0;
+      for (int i = 0; i < mcnt; ++i) {
+        if ((alive >> i) & 1ull) { kept |= (1ull << i); alive &= ~diag[i]; kept_rows[nk++] = i; }
+      }
+      kept_bits_s = kept;
+    }
+    __syncthreads();
+    const unsigned long long kept = kept_bits_s;
+    const int nk = __popcll(kept);
+    const int kn = kept_n;
+    if (tid < mcnt && ((kept >> tid) & 1ull))
+      gk_key[kn + __popcll(kept & ((1ull << tid) - 1ull))] = keys[r * 64 + tid] & 0x00FFFFFFFFFFFFFFull;
+    // OR the kept rows into the bitmap of the later chunks: warps take kept rows, lanes take column words
+    // (coalesced, all loads independent), partial results merge through shared-memory atomics
+    const int ncol = T - r - 1;
+    if (ncol > 0 && nk > 0) {
+      const int64_t rowbase = 64ll * (static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2);
+      const int stride = T - r;
+      for (int c = lane; c < ncol; c += 32) {
+        unsigned long long acc = 0ull;
+        for (int k = warp; k < nk; k += kScanThreads / 32) acc |= mask[rowbase + static_cast<int64_t>(kept_rows[k]) * stride + 1 + c];
+        if (acc) atomicOr(&removed[r + 1 + c], acc);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) kept_n = kn + nk;
+  }
+  __syncthreads();
+  if (tid == 0) w.seg_kept[sgm] = kept_n;
+}
+
 template <bool kFromPred>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work w, float thr, int strategy) {
   __shared__ float4 kbox[kKeptSmem];
@@ -322,7 +524,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work
     if (tid == 0) w.seg_kept[b * w.nc + seg] = 0;
     return;
   }
-  const ImageMode m = image_mode(w, b, strategy);
+  if (w.seg_word_off[b * w.nc + seg] >= 0) return;  // this segment runs on the bitmask path
   const bool thr_nonneg = (thr >= 0.0f);
   const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
   float4* gk_box = w.kept_box + static_cast<int64_t>(b) * w.cap + s0;
@@ -335,18 +537,10 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work
     if (tid < 64) {
       cmask[tid] = 0ull;
       if (tid < mcnt) {
-        const uint64_t key = keys[c0 + tid];
-        const Cand c = load_cand<kFromPred>(s, b, static_cast<int>(key_idx(key)));
-        float4 bx = c.box;
-        if (m.use_offsets) {
-          // boxes.py _batched_nms_coordinate_trick: offsets = idxs * (max_coordinate + 1); boxes + offsets
-          const float off = __fmul_rn(c.label_f, m.offset_scale);
-          bx.x = __fadd_rn(bx.x, off); bx.y = __fadd_rn(bx.y, off);
-          bx.z = __fadd_rn(bx.z, off); bx.w = __fadd_rn(bx.w, off);
-        }
+        const float4 bx = w.nbox[static_cast<int64_t>(b) * w.cap + s0 + c0 + tid];
         cbox[tid] = bx;
-        carea[tid] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-        ckey[tid] = key;
+        carea[tid] = box_area(bx);
+        ckey[tid] = keys[c0 + tid];
       }
     }
     if (tid == 0) sup_prev = 0ull;
@@ -473,8 +667,17 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
-      off_keptkey, off_keptbox, total;
+      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_counter, off_mask, mask_words, total;
 };
+
+constexpr int kMaxScanTiles = 5120;  // 40 KB of shared memory for the 'removed' bitmap
+
+inline int64_t mask_budget_words(int B, int cap) {
+  int64_t bytes = static_cast<int64_t>(B) * cap * 768;
+  if (bytes < (32ll << 20)) bytes = 32ll << 20;
+  if (bytes > (3072ll << 20)) bytes = 3072ll << 20;
+  return bytes / 8;
+}
 
 Layout make_layout(int B, int cap, int P, int nc) {
   Layout l;
@@ -490,6 +693,12 @@ Layout make_layout(int B, int cap, int P, int nc) {
   l.off_keys = o; o = align_up(o + 8ll * B * P, 256);
   l.off_keptkey = o; o = align_up(o + 8ll * B * cap, 256);
   l.off_keptbox = o; o = align_up(o + 16ll * B * cap, 256);
+  l.off_nbox = o; o = align_up(o + 16ll * B * cap, 256);
+  l.off_tileoff = o; o = align_up(o + 4ll * (static_cast<int64_t>(B) * nc + 1), 256);
+  l.off_wordoff = o; o = align_up(o + 8ll * B * nc, 256);
+  l.off_counter = o; o = align_up(o + 4, 256);
+  l.mask_words = mask_budget_words(B, cap);
+  l.off_mask = o; o = align_up(o + 8ll * l.mask_words, 256);
   l.total = o;
   return l;
 }
@@ -511,6 +720,17 @@ Work make_work(void* ws, int B, int cap, int nc) {
   w.keys = reinterpret_cast<uint64_t*>(p + l.off_keys);
   w.kept_key = reinterpret_cast<uint64_t*>(p + l.off_keptkey);
   w.kept_box = reinterpret_cast<float4*>(p + l.off_keptbox);
+  w.nbox = reinterpret_cast<float4*>(p + l.off_nbox);
+  w.seg_tile_off = reinterpret_cast<int32_t*>(p + l.off_tileoff);
+  w.seg_word_off = reinterpret_cast<int64_t*>(p + l.off_wordoff);
+  w.tile_counter = reinterpret_cast<int32_t*>(p + l.off_counter);
+  w.mask = reinterpret_cast<unsigned long long*>(p + l.off_mask);
+  w.mask_words = l.mask_words;
+  if (const char* e = getenv("GLSDET_NMS_MASK_WORDS")) {  // tests: shrink the budget to force the fallback kernel
+    const long long v = atoll(e);
+    if (v >= 0 && v < w.mask_words) w.mask_words = v;
+  }
+  w.max_scan_tiles = kMaxScanTiles;
   return w;
 }
 
@@ -552,6 +772,22 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   }
   segment_bounds_kernel<<<B, 256, 0, st>>>(w, strategy);
   if (int rc = count_launch("segment_bounds_kernel")) return rc;
+  {
+    int gx = (w.cap + 255) / 256;
+    if (gx > 1024) gx = 1024;
+    box_prep_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, strategy);
+    if (int rc = count_launch("box_prep_kernel")) return rc;
+  }
+  seg_plan_kernel<<<1, 1024, 0, st>>>(w);
+  if (int rc = count_launch("seg_plan_kernel")) return rc;
+  mask_tiles_kernel<<<device_sm_count() * 16, 64, 0, st>>>(w, nms_thres);
+  if (int rc = count_launch("mask_tiles_kernel")) return rc;
+  {
+    int t = (w.cap + 63) / 64;
+    if (t > kMaxScanTiles) t = kMaxScanTiles;
+    scan_kernel<<<dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 8, st>>>(w);
+    if (int rc = count_launch("scan_kernel")) return rc;
+  }
   nms_segment_kernel<kFromPred><<<dim3(w.nc, B), kNmsThreads, 0, st>>>(s, w, nms_thres, strategy);
   if (int rc = count_launch("nms_segment_kernel")) return rc;
   {
