@@ -115,7 +115,7 @@ struct Work {
   float4* nbox;          // [B][cap]   NMS-space box of every sorted candidate (offset applied for the trick)
   int32_t* seg_tile_off; // [B*nc + 1] exclusive prefix of per-segment tile counts (mask path)
   int64_t* seg_word_off; // [B*nc]     first mask word of the segment, or -1 when it runs on the fallback kernel
-  int32_t* tile_counter; // [1]        work-list cursor of mask_tiles_kernel
+  unsigned long long* row_any;  // [B][P/64] bit i set: sorted candidate i suppresses at least one later box
   unsigned long long* mask;  // [mask_words]
   int64_t mask_words;
   int32_t max_scan_tiles;    // segments with more 64-box chunks than this use the fallback kernel
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
       k = make_key(m.per_class ? w.cand_label[o] : 0u, w.cand_score[o], static_cast<uint32_t>(w.cand_idx[o]));
     }
     w.keys[static_cast<int64_t>(b) * w.P + i] = k;
+    if ((i & 63) == 0) w.row_any[static_cast<int64_t>(b) * (w.P >> 6) + (i >> 6)] = 0ull;
   }
 }
 
@@ -337,11 +338,12 @@ __global__ void __launch_bounds__(256) box_prep_kernel(Source s, Work w, int str
   }
 }
 
-// word index of (row tile r, row-in-tile i, column tile c >= r) in the upper-triangular mask of a T-tile segment
-__device__ __forceinline__ int64_t tri_word(int T, int r, int i, int c) {
-  return 64ll * (static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2) +
-         static_cast<int64_t>(i) * (T - r) + (c - r);
+// Mask layout of a T-tile segment: upper-triangular list of 64x64 tiles, row-tile major; the 64 words of a tile
+// (one per row) are contiguous, so a tile is written with one coalesced 512-byte store.
+__device__ __forceinline__ int64_t tri_tile(int T, int r, int c) {
+  return static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2 + (c - r);
 }
+__device__ __forceinline__ int64_t tri_word(int T, int r, int i, int c) { return tri_tile(T, r, c) * 64 + i; }
 
 __device__ __forceinline__ float box_area(const float4& b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -355,7 +357,7 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
   __shared__ long long carry_words;
   __shared__ int carry_tiles;
   const int total = w.B * w.nc;
-  if (threadIdx.x == 0) { carry_words = 0; carry_tiles = 0; *w.tile_counter = 0; }
+  if (threadIdx.x == 0) { carry_words = 0; carry_tiles = 0; }
   __syncthreads();
   for (int base = 0; base < total; base += 1024) {
     const int sgm = base + threadIdx.x;
@@ -366,8 +368,8 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
       n = w.seg_start[b * (w.nc + 1) + c + 1] - w.seg_start[b * (w.nc + 1) + c];
       T = (n + 63) >> 6;
       if (T <= w.max_scan_tiles && T < 46000) {  // T*T must fit an int; larger segments go to the fallback
-        words = 32ll * T * (T + 1);  // upper triangle only: row tile r stores T - r words per row
-        tiles = T * T;
+        tiles = T * (T + 1) / 2;     // upper triangle only (column tile >= row tile)
+        words = 64ll * tiles;
       }
     }
     s_words[threadIdx.x] = words;
@@ -392,62 +394,90 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
   }
 }
 
-// Persistent CTAs of 64 threads: each pulls 64x64 tiles (row tile r, column tile c >= r) from the work list.
-__global__ void __launch_bounds__(64) mask_tiles_kernel(Work w, float thr) {
-  __shared__ float4 cbox[64];
-  __shared__ float carea[64];
-  __shared__ int s_tile;
+// Persistent CTAs of 4 x 64 threads; every 64-thread group owns one 64x64 tile at a time (row tile r, column tile
+// c >= r), statically strided over the work list.  Thread i of the group tests row box i against the 64 column
+// boxes staged in shared memory and emits one 64-bit word.
+constexpr int kMaskGroups = 4;
+__global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, float thr) {
+  __shared__ float4 cbox[kMaskGroups][64];
+  __shared__ float carea[kMaskGroups][64];
   const int total_seg = w.B * w.nc;
   const int total_tiles = w.seg_tile_off[total_seg];
   const bool thr_nonneg = (thr >= 0.0f);
-  const int tid = threadIdx.x;
-  while (true) {
-    if (tid == 0) s_tile = atomicAdd(w.tile_counter, 1);
-    __syncthreads();
-    const int t = s_tile;
-    if (t >= total_tiles) break;
-    // segment owning tile t: last entry with seg_tile_off <= t among mask-path segments
-    int lo = 0, hi = total_seg;
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (w.seg_tile_off[mid] <= t) lo = mid; else hi = mid;
-    }
-    // skip forward over zero-tile (empty / fallback) segments sharing the same offset
-    while (w.seg_tile_off[lo + 1] <= t) ++lo;
-    const int sgm = lo;
-    const int b = sgm / w.nc, c = sgm % w.nc;
-    const int s0 = w.seg_start[b * (w.nc + 1) + c];
-    const int n = w.seg_start[b * (w.nc + 1) + c + 1] - s0;
-    const int T = (n + 63) >> 6;
-    const int local = t - w.seg_tile_off[sgm];
-    const int r = local / T, cc = local % T;
-    if (cc >= r) {
-      const float4* bx = w.nbox + static_cast<int64_t>(b) * w.cap + s0;
-      const int cj = cc * 64 + tid;
-      if (cj < n) { cbox[tid] = bx[cj]; carea[tid] = box_area(cbox[tid]); }
-      __syncthreads();
-      const int ri = r * 64 + tid;
-      if (ri < n) {
-        const float4 rb = bx[ri];
-        const float ra = box_area(rb);
-        const int jn = min(64, n - cc * 64);
-        unsigned long long bits = 0ull;
-        for (int j = (cc == r) ? tid + 1 : 0; j < jn; ++j)
-          if (iou_exceeds(rb, ra, cbox[j], carea[j], thr, thr_nonneg)) bits |= (1ull << j);
-        w.mask[w.seg_word_off[sgm] + tri_word(T, r, tid, cc)] = bits;
+  const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
+  int cur_lo = 0, cur_hi = 0, sgm = 0, s0 = 0, n = 0, T = 0, b = 0;
+  for (int t = blockIdx.x * kMaskGroups + grp; t < total_tiles; t += gridDim.x * kMaskGroups) {
+    if (t >= cur_hi || t < cur_lo) {
+      int lo = 0, hi = total_seg;  // seg_tile_off[lo] <= t < seg_tile_off[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (w.seg_tile_off[mid] <= t) lo = mid; else hi = mid;
       }
+      sgm = lo;
+      cur_lo = w.seg_tile_off[sgm];
+      cur_hi = w.seg_tile_off[sgm + 1];
+      b = sgm / w.nc;
+      const int c = sgm % w.nc;
+      s0 = w.seg_start[b * (w.nc + 1) + c];
+      n = w.seg_start[b * (w.nc + 1) + c + 1] - s0;
+      T = (n + 63) >> 6;
     }
-    __syncthreads();
+    // invert local = r*T - r(r-1)/2 + (c - r)
+    const int local = t - cur_lo;
+    const float fT = static_cast<float>(2 * T + 1);
+    int r = static_cast<int>((fT - sqrtf(fmaxf(fT * fT - 8.0f * static_cast<float>(local), 0.0f))) * 0.5f);
+    r = max(0, min(r, T - 1));
+    while (r > 0 && static_cast<int>(tri_tile(T, r, r)) > local) --r;
+    while (r + 1 < T && static_cast<int>(tri_tile(T, r + 1, r + 1)) <= local) ++r;
+    const int cc = r + (local - static_cast<int>(tri_tile(T, r, r)));
+    const float4* bx = w.nbox + static_cast<int64_t>(b) * w.cap + s0;
+    const int cj = cc * 64 + tid;
+    if (cj < n) { cbox[grp][tid] = bx[cj]; carea[grp][tid] = box_area(cbox[grp][tid]); }
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
+    const int ri = r * 64 + tid;
+    unsigned long long bits = 0ull;
+    if (ri < n) {
+      const float4 rb = bx[ri];
+      const float ra = box_area(rb);
+      const int jn = min(64, n - cc * 64);
+      const int j0 = (cc == r) ? tid + 1 : 0;
+      if (thr_nonneg) {
+        // common case first: two subtractions decide "no overlap" (inter == 0 never exceeds thr >= 0); the exact
+        // IEEE division runs only for the few pairs that really intersect
+        uint32_t lo = 0u, hi = 0u;
+#pragma unroll 4
+        for (int j = j0; j < jn; ++j) {
+          const float4 cb = cbox[grp][j];
+          const float ww = __fsub_rn(fminf(rb.z, cb.z), fmaxf(rb.x, cb.x));
+          const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
+          if (fminf(ww, hh) > 0.0f) {
+            if (iou_exceeds(rb, ra, cb, carea[grp][j], thr, true)) {
+              if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
+            }
+          }
+        }
+        bits = (static_cast<unsigned long long>(hi) << 32) | lo;
+      } else {
+        for (int j = j0; j < jn; ++j)
+          if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, false)) bits |= (1ull << j);
+      }
+      if (bits) atomicOr(&w.row_any[static_cast<int64_t>(b) * (w.P >> 6) + ((s0 + ri) >> 6)], 1ull << ((s0 + ri) & 63));
+    }
+    w.mask[w.seg_word_off[sgm] + tri_word(T, r, tid, cc)] = bits;
+    asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
   }
 }
 
-// One CTA (32 warps) per mask-path segment: sequential over 64-box chunks, parallel inside.
-constexpr int kScanThreads = 1024;
+// One CTA per mask-path segment: sequential over 64-box chunks, parallel inside.  Suppression is sparse (most
+// boxes suppress nothing), so only rows flagged in row_any are ever read from the mask, and the serial part of a
+// chunk only walks the flagged rows.  The diagonal words of chunk r+1 are prefetched while chunk r is resolved.
+constexpr int kScanThreads = 512;
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
-  extern __shared__ unsigned long long removed[];  // [T]
-  __shared__ unsigned long long diag[64];
+  extern __shared__ unsigned long long scan_smem[];  // removed[T] | any[T]
+  __shared__ unsigned long long diag[2][64];
   __shared__ unsigned long long kept_bits_s;
-  __shared__ int kept_rows[64];
+  __shared__ int sup_rows[64];
+  __shared__ int sup_n;
   __shared__ int kept_n;
   const int seg = blockIdx.x, b = blockIdx.y;
   const int sgm = b * w.nc + seg;
@@ -456,50 +486,83 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
   const int s0 = w.seg_start[b * (w.nc + 1) + seg];
   const int n = w.seg_start[b * (w.nc + 1) + seg + 1] - s0;
   const int T = (n + 63) >> 6;
+  unsigned long long* removed = scan_smem;
+  unsigned long long* any_s = scan_smem + T;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const unsigned long long* mask = w.mask + woff;
+  const unsigned long long* any_words = w.row_any + static_cast<int64_t>(b) * (w.P >> 6);
   const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
   uint64_t* gk_key = w.kept_key + static_cast<int64_t>(b) * w.cap + s0;
-  for (int i = tid; i < T; i += kScanThreads) removed[i] = 0ull;
+  for (int r = tid; r < T; r += kScanThreads) {
+    removed[r] = 0ull;
+    // 64 'suppresses something' flags of chunk r (the segment need not start on a word boundary)
+    const int g0 = s0 + r * 64;
+    unsigned long long any = any_words[g0 >> 6] >> (g0 & 63);
+    if (g0 & 63) any |= any_words[(g0 >> 6) + 1] << (64 - (g0 & 63));
+    const int mc = min(64, n - r * 64);
+    if (mc < 64) any &= ((1ull << mc) - 1ull);
+    any_s[r] = any;
+  }
   if (tid == 0) kept_n = 0;
+  __syncthreads();
+  if (tid < 64) {
+    const unsigned long long a0 = any_s[0];
+    diag[0][tid] = ((a0 >> tid) & 1ull) ? mask[tri_word(T, 0, tid, 0)] : 0ull;
+  }
   __syncthreads();
   for (int r = 0; r < T; ++r) {
     const int mcnt = min(64, n - r * 64);
-    if (tid < mcnt) diag[tid] = mask[tri_word(T, r, tid, r)];
-    __syncthreads();
+    const int cur = r & 1;
+    const unsigned long long any = any_s[r];
+    // prefetch: keys of this chunk, diagonal words of the next one (both independent of the resolve below)
+    uint64_t my_key = 0;
+    if (tid < mcnt) my_key = keys[r * 64 + tid];
+    unsigned long long next_diag = 0ull;
+    if (tid >= 64 && tid < 128 && r + 1 < T) {
+      const int i = tid - 64;
+      if ((any_s[r + 1] >> i) & 1ull) next_diag = mask[tri_word(T, r + 1, i, r + 1)];
+    }
     if (tid == 0) {
       unsigned long long alive = ~removed[r];
       if (mcnt < 64) alive &= ((1ull << mcnt) - 1ull);
-      unsigned long long kept = 0ull;
-      int nk = 0;
-      for (int i = 0; i < mcnt; ++i) {
-        if ((alive >> i) & 1ull) { kept |= (1ull << i); alive &= ~diag[i]; kept_rows[nk++] = i; }
+      int ns = 0;
+      unsigned long long m = alive & any;   // only flagged rows can suppress; walk them in score order
+      while (m) {
+        const int i = __ffsll(static_cast<long long>(m)) - 1;
+        m &= m - 1ull;
+        if ((alive >> i) & 1ull) {
+          const unsigned long long d = diag[cur][i];
+          alive &= ~d;
+          m &= ~d;
+          sup_rows[ns++] = i;
+        }
       }
-      kept_bits_s = kept;
+      kept_bits_s = alive;
+      sup_n = ns;
     }
     __syncthreads();
     const unsigned long long kept = kept_bits_s;
-    const int nk = __popcll(kept);
+    const int ns = sup_n;
     const int kn = kept_n;
     if (tid < mcnt && ((kept >> tid) & 1ull))
-      gk_key[kn + __popcll(kept & ((1ull << tid) - 1ull))] = keys[r * 64 + tid] & 0x00FFFFFFFFFFFFFFull;
-    // OR the kept rows into the bitmap of the later chunks: warps take kept rows, lanes take column words
-    // (coalesced, all loads independent), partial results merge through shared-memory atomics
+      gk_key[kn + __popcll(kept & ((1ull << tid) - 1ull))] = my_key & 0x00FFFFFFFFFFFFFFull;
+    if (tid >= 64 && tid < 128) diag[cur ^ 1][tid - 64] = next_diag;
+    // OR the kept, suppressing rows into the bitmap of the later chunks: warps take rows, lanes take column tiles
     const int ncol = T - r - 1;
-    if (ncol > 0 && nk > 0) {
-      const int64_t rowbase = 64ll * (static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2);
-      const int stride = T - r;
-      for (int c = lane; c < ncol; c += 32) {
-        unsigned long long acc = 0ull;
-        for (int k = warp; k < nk; k += kScanThreads / 32) acc |= mask[rowbase + static_cast<int64_t>(kept_rows[k]) * stride + 1 + c];
-        if (acc) atomicOr(&removed[r + 1 + c], acc);
+    if (ncol > 0 && ns > 0) {
+      const int64_t tbase = tri_tile(T, r, r + 1) * 64;
+      for (int k = warp; k < ns; k += kScanThreads / 32) {
+        const int i = sup_rows[k];
+        for (int c = lane; c < ncol; c += 32) {
+          const unsigned long long mm = mask[tbase + static_cast<int64_t>(c) * 64 + i];
+          if (mm) atomicOr(&removed[r + 1 + c], mm);
+        }
       }
     }
     __syncthreads();
-    if (tid == 0) kept_n = kn + nk;
+    if (tid == 0) kept_n = kn + __popcll(kept);  // read again only after the next barrier
   }
-  __syncthreads();
   if (tid == 0) w.seg_kept[sgm] = kept_n;
 }
 
@@ -667,10 +730,10 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
-      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_counter, off_mask, mask_words, total;
+      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowany, off_mask, mask_words, total;
 };
 
-constexpr int kMaxScanTiles = 5120;  // 40 KB of shared memory for the 'removed' bitmap
+constexpr int kMaxScanTiles = 2816;  // 2 x 22 KB of shared memory for the 'removed' and 'any' bitmaps
 
 inline int64_t mask_budget_words(int B, int cap) {
   int64_t bytes = static_cast<int64_t>(B) * cap * 768;
@@ -696,7 +759,7 @@ Layout make_layout(int B, int cap, int P, int nc) {
   l.off_nbox = o; o = align_up(o + 16ll * B * cap, 256);
   l.off_tileoff = o; o = align_up(o + 4ll * (static_cast<int64_t>(B) * nc + 1), 256);
   l.off_wordoff = o; o = align_up(o + 8ll * B * nc, 256);
-  l.off_counter = o; o = align_up(o + 4, 256);
+  l.off_rowany = o; o = align_up(o + 8ll * B * (P / 64 + 2), 256);
   l.mask_words = mask_budget_words(B, cap);
   l.off_mask = o; o = align_up(o + 8ll * l.mask_words, 256);
   l.total = o;
@@ -723,7 +786,7 @@ Work make_work(void* ws, int B, int cap, int nc) {
   w.nbox = reinterpret_cast<float4*>(p + l.off_nbox);
   w.seg_tile_off = reinterpret_cast<int32_t*>(p + l.off_tileoff);
   w.seg_word_off = reinterpret_cast<int64_t*>(p + l.off_wordoff);
-  w.tile_counter = reinterpret_cast<int32_t*>(p + l.off_counter);
+  w.row_any = reinterpret_cast<unsigned long long*>(p + l.off_rowany);
   w.mask = reinterpret_cast<unsigned long long*>(p + l.off_mask);
   w.mask_words = l.mask_words;
   if (const char* e = getenv("GLSDET_NMS_MASK_WORDS")) {  // tests: shrink the budget to force the fallback kernel
@@ -780,12 +843,12 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   }
   seg_plan_kernel<<<1, 1024, 0, st>>>(w);
   if (int rc = count_launch("seg_plan_kernel")) return rc;
-  mask_tiles_kernel<<<device_sm_count() * 16, 64, 0, st>>>(w, nms_thres);
+  mask_tiles_kernel<<<device_sm_count() * 6, 64 * kMaskGroups, 0, st>>>(w, nms_thres);
   if (int rc = count_launch("mask_tiles_kernel")) return rc;
   {
     int t = (w.cap + 63) / 64;
     if (t > kMaxScanTiles) t = kMaxScanTiles;
-    scan_kernel<<<dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 8, st>>>(w);
+    scan_kernel<<<dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 16, st>>>(w);
     if (int rc = count_launch("scan_kernel")) return rc;
   }
   nms_segment_kernel<kFromPred><<<dim3(w.nc, B), kNmsThreads, 0, st>>>(s, w, nms_thres, strategy);

@@ -148,6 +148,17 @@ def neck_head(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor
         return yolox_head(sd, pafpn_neck(sd, feats))
 
 
+def neck_bf16(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """pafpn_neck with bf16 storage precision (see neck_head_bf16)."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = True
+    try:
+        with torch.no_grad():
+            return pafpn_neck(sd, [_q(f) for f in feats])
+    finally:
+        _EMULATE_BF16 = False
+
+
 def neck_head_bf16(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """The same graph evaluated with the STORAGE precision of the bf16 path (inputs, folded weights and every
     layer output rounded to bf16; fp32 accumulation).  Separates two error sources in the tests: the CUDA path must

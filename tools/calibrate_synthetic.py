@@ -5,7 +5,8 @@ a degenerate NMS load.  Real checkpoints have BatchNorm statistics that match th
 the synthetic ones the same property: it runs the CPU oracle once on seeded noise images, sets every BatchNorm's
 running_mean / running_var to the statistics of the conv output feeding it (exactly what BN training would have
 recorded), and rescales the prediction convs so that obj / cls logits have a standard deviation of 2.0 / 0.5 around the
-YOLOX prior and the box regressors 0.15.  Only those tensors are stored, as
+YOLOX prior and the box regressors 0.15, and the objectness biases are shifted by one common offset so that a
+target fraction of the anchors (default 4 %) passes conf 0.01.  Only those tensors are stored, as
 glsdet_b200/data/calib_p0_<phi>_nc<nc>_seed<seed>.npz; glsdet_b200.synthetic.synthetic_state_dict(flavour=
 "calibrated") overlays them on the seeded base weights.  (Uses oracle/, so it is a tool, not product code.)
 
@@ -32,6 +33,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--obj-std", type=float, default=2.0)
+    ap.add_argument("--target-pass", type=float, default=0.04, help="fraction of anchors with obj*cls >= 0.01")
     ap.add_argument("--cls-std", type=float, default=0.5)
     args = ap.parse_args()
     torch.set_num_threads(8)
@@ -68,6 +70,20 @@ def main():
                 sd[key] = sd[key] * (target / std).view(-1, 1, 1, 1)
                 changed[key] = sd[key]
     ref_path.base_conv = orig
+    # shift the objectness biases so that the wanted fraction of anchors passes conf 0.01 (bisection on one offset)
+    with torch.no_grad():
+        lg = ref_path.yolox_head(sd, neck)
+    obj = torch.cat([l[:, 4].flatten(1) for l in lg], 1)
+    cls = torch.cat([torch.sigmoid(l[:, 5:]).max(1)[0].flatten(1) for l in lg], 1)
+    lo, hi = -20.0, 20.0
+    for _ in range(50):
+        mid = 0.5 * (lo + hi)
+        frac = float(((torch.sigmoid(obj + mid) * cls) >= 0.01).float().mean())
+        lo, hi = (mid, hi) if frac < args.target_pass else (lo, mid)
+    for i in range(4):
+        key = f"head.obj_preds.{i}.bias"
+        sd[key] = sd[key] + 0.5 * (lo + hi)
+        changed[key] = sd[key]
     out = ROOT / "glsdet_b200" / "data" / f"calib_p0_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
     np.savez_compressed(out, **{k: v.numpy().astype(np.float32) for k, v in changed.items()})
     # report
