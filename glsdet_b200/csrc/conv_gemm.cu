@@ -21,6 +21,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include <new>
 
 #include "../../include/glsdet_b200.h"
@@ -58,7 +60,11 @@ struct alignas(64) ConvKParams {
   int32_t out_mode, out_ld, out_coff;
   int64_t out_bs;
   float dec_stride, dec_in_w, dec_in_h;
+  int32_t epi;   // EPI_* epilogue specialisation chosen at create time
 };
+
+enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
+       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7 };
 
 struct TileCoord {
   int b, y0, x0, n0;
@@ -195,9 +201,11 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
   }
 }
 
-// Fast path (the bulk of the network): bias + SiLU/ReLU -> bf16 NHWC, 16 channels = two 16-byte stores.
-__device__ __forceinline__ void epilogue_fast16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
-                                                __nv_bfloat16* o) {
+// Specialised epilogues (chosen per op at create time; everything warp-uniform is hoisted out of the element
+// loops).  bf16 NHWC output of 16 channels = two 16-byte stores.
+template <bool PRE, bool POST>
+__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+                                           const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
@@ -207,12 +215,31 @@ __device__ __forceinline__ void epilogue_fast16(const uint32_t (&raw)[16], const
     v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
     v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
   }
+  if (PRE) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(pre + j));
+      v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+    }
+  }
   if (silu) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (POST) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(post) + h);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[h * 8 + q * 2] += __uint_as_float(w[q] << 16);
+        v[h * 8 + q * 2 + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+      }
+    }
   }
   uint4 a, c;
   a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
@@ -221,6 +248,36 @@ __device__ __forceinline__ void epilogue_fast16(const uint32_t (&raw)[16], const
   c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
   reinterpret_cast<uint4*>(o)[0] = a;
   reinterpret_cast<uint4*>(o)[1] = c;
+}
+
+// bias only, fp32 NHWC, 16 channels = four 16-byte stores (low-resolution partial sums)
+__device__ __forceinline__ void epi16_f32_plain(const uint32_t (&raw)[16], const float* s_bias, float* o) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 bv = *reinterpret_cast<const float4*>(s_bias + j);
+    *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(raw[j]) + bv.x, __uint_as_float(raw[j + 1]) + bv.y,
+                                                    __uint_as_float(raw[j + 2]) + bv.z, __uint_as_float(raw[j + 3]) + bv.w);
+  }
+}
+
+// Walks the accumulator columns of one tile: two tcgen05.ld in flight per wait, then f(raw, chunk) on each.
+template <typename F>
+__device__ __forceinline__ void epi_walk(uint32_t taddr, int c_begin, int c_end, F&& f) {
+  int c = c_begin;
+  for (; c + 2 <= c_end; c += 2) {
+    uint32_t v0[16], v1[16];
+    tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
+    tmem_ld16(taddr + static_cast<uint32_t>(c * 16 + 16), v1);
+    tmem_ld_wait();
+    f(v0, c);
+    f(v1, c + 1);
+  }
+  if (c < c_end) {
+    uint32_t v0[16];
+    tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
+    tmem_ld_wait();
+    f(v0, c);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
@@ -353,9 +410,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int n_chunks = p.block_n >> 4;
     const int c_begin = half ? ((n_chunks + 1) >> 1) : 0;
     const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
-    const bool fast = (p.out_mode == GLSDET_OUT_NHWC_BF16) && (p.pre_res == nullptr) && (p.post_res == nullptr) &&
-                      (p.act == GLSDET_ACT_SILU || p.act == GLSDET_ACT_RELU) && ((p.N & 15) == 0) &&
-                      (((p.out_ld | p.out_coff) & 7) == 0);
     const bool silu = (p.act == GLSDET_ACT_SILU);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -367,33 +421,88 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
       const int oy = t.y0 + py, ox = t.x0 + px;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
-      if (fast) {
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
-                              (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
-        int c = c_begin;
-        for (; c + 2 <= c_end; c += 2) {  // two loads in flight per wait
-          uint32_t v0[16], v1[16];
-          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
-          tmem_ld16(taddr + static_cast<uint32_t>(c * 16 + 16), v1);
-          tmem_ld_wait();
-          if (valid) {
-            if (t.n0 + c * 16 < p.N) epilogue_fast16(v0, s_bias + t.n0 + c * 16, silu, orow + c * 16);
-            if (t.n0 + c * 16 + 16 < p.N) epilogue_fast16(v1, s_bias + t.n0 + c * 16 + 16, silu, orow + c * 16 + 16);
+      const float* sb = s_bias + t.n0;
+      // every lane of the warp must execute the TMEM loads; only valid pixels / channels below N are stored
+      switch (p.epi) {
+        case EPI_BF16:
+        case EPI_BF16_PRE:
+        case EPI_BF16_POST: {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                                (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
+          if (p.epi == EPI_BF16) {
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, silu, nullptr, nullptr, orow + c * 16);
+            });
+          } else if (p.epi == EPI_BF16_PRE) {
+            const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
+            const float* pre = p.pre_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + t.n0;
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, false>(raw, sb + c * 16, silu, pre + c * 16, nullptr, orow + c * 16);
+            });
+          } else {
+            const int hs = p.Ho >> p.post_shift, ws = p.Wo >> p.post_shift;
+            const __nv_bfloat16* post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, true>(raw, sb + c * 16, silu, nullptr, post + c * 16, orow + c * 16);
+            });
           }
+          break;
         }
-        if (c < c_end) {
-          uint32_t v0[16];
-          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v0);
-          tmem_ld_wait();
-          if (valid && t.n0 + c * 16 < p.N) epilogue_fast16(v0, s_bias + t.n0 + c * 16, silu, orow + c * 16);
+        case EPI_F32_PLAIN: {
+          float* orow = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                        (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
+          epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+            if (valid && t.n0 + c * 16 < p.N) epi16_f32_plain(raw, sb + c * 16, orow + c * 16);
+          });
+          break;
         }
-      } else {
-        for (int c = c_begin; c < c_end; ++c) {
-          uint32_t v[16];
-          tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
-          tmem_ld_wait();
-          if (valid && t.n0 + c * 16 < p.N)
-            epilogue_store16(p, v, s_bias + t.n0 + c * 16, t.b, oy, ox, t.n0 + c * 16);
+        case EPI_NCHW_RAW: {  // N <= 16: raw logits, reference layout; lanes are consecutive x -> coalesced per channel
+          const int64_t plane = static_cast<int64_t>(p.Ho) * p.Wo;
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                     static_cast<int64_t>(p.out_coff) * plane + static_cast<int64_t>(oy) * p.Wo + ox;
+          epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+            if (valid && c == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < p.N) o[j * plane] = __uint_as_float(raw[j]) + sb[j];
+            }
+          });
+          break;
+        }
+        case EPI_ROWS_BOX: {  // N == 5: utils_bbox.py:270-305 on (x, y, w, h, obj) -> decoded row prefix
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                     (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
+          epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+            if (valid && c == 0) {
+              o[0] = ((__uint_as_float(raw[0]) + sb[0] + static_cast<float>(ox)) * p.dec_stride) / p.dec_in_w;
+              o[1] = ((__uint_as_float(raw[1]) + sb[1] + static_cast<float>(oy)) * p.dec_stride) / p.dec_in_h;
+              o[2] = (expf(__uint_as_float(raw[2]) + sb[2]) * p.dec_stride) / p.dec_in_w;
+              o[3] = (expf(__uint_as_float(raw[3]) + sb[3]) * p.dec_stride) / p.dec_in_h;
+              o[4] = 1.0f / (1.0f + expf(-(__uint_as_float(raw[4]) + sb[4])));
+            }
+          });
+          break;
+        }
+        case EPI_ROWS_SIGMOID: {  // N <= 16 class probabilities of a decoded row
+          float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                     (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
+          epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+            if (valid && c == 0) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < p.N) o[j] = 1.0f / (1.0f + expf(-(__uint_as_float(raw[j]) + sb[j])));
+            }
+          });
+          break;
+        }
+        default: {
+          for (int c = c_begin; c < c_end; ++c) {
+            uint32_t v[16];
+            tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
+            tmem_ld_wait();
+            if (valid && t.n0 + c * 16 < p.N)
+              epilogue_store16(p, v, s_bias + t.n0 + c * 16, t.b, oy, ox, t.n0 + c * 16);
+          }
         }
       }
       tc_fence_before();
@@ -553,6 +662,31 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.post_res = reinterpret_cast<const __nv_bfloat16*>(d->post_res); k.post_shift = d->post_shift; k.post_ld = d->post_ld;
   k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
   k.dec_stride = d->dec_stride; k.dec_in_w = d->dec_in_w; k.dec_in_h = d->dec_in_h;
+  {
+    const bool n16 = (d->out_channels % 16) == 0;
+    const bool act_sr = (d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU);
+    const bool bf16_vec = d->out_mode == GLSDET_OUT_NHWC_BF16 && n16 && ((d->out_ld | d->out_coff) % 8) == 0 &&
+                          (d->out_batch_stride % 8) == 0;
+    const bool small_n = d->out_channels <= 16;
+    k.epi = EPI_GENERIC;
+    if (bf16_vec && act_sr && !d->pre_res && !d->post_res) k.epi = EPI_BF16;
+    else if (bf16_vec && act_sr && d->pre_res && !d->post_res && (d->pre_ld % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->pre_res) & 15) == 0) k.epi = EPI_BF16_PRE;
+    else if (bf16_vec && act_sr && !d->pre_res && d->post_res && (d->post_ld % 8) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->post_res) & 15) == 0) k.epi = EPI_BF16_POST;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_NONE && n16 && !d->pre_res && !d->post_res &&
+             ((d->out_ld | d->out_coff) % 4) == 0 && (d->out_batch_stride % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) k.epi = EPI_F32_PLAIN;
+    else if (d->out_mode == GLSDET_OUT_NCHW_F32 && d->act == GLSDET_ACT_NONE && small_n && !d->pre_res && !d->post_res)
+      k.epi = EPI_NCHW_RAW;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_YOLOX_BOX && d->out_channels == 5 &&
+             !d->pre_res && !d->post_res) k.epi = EPI_ROWS_BOX;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_SIGMOID && small_n && !d->pre_res &&
+             !d->post_res) k.epi = EPI_ROWS_SIGMOID;
+    if (const char* e = getenv("GLSDET_CONV_GENERIC_EPILOGUE")) {  // tests: force the generic epilogue
+      if (e[0] == '1') k.epi = EPI_GENERIC;
+    }
+  }
 
   int rc = 0;
   if (d->stride == 1) {

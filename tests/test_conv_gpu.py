@@ -169,3 +169,42 @@ def test_pred_conv_nchw_and_decode(native_lib, cuda_device):
     ref_cls = torch.sigmoid(ref_c).permute(0, 2, 3, 1).reshape(B, H * W, nc)
     assert torch.allclose(base[:, :H * W, 5:], ref_cls, rtol=2e-4, atol=2e-5)
     assert torch.isnan(pred[:, :3]).all() and torch.isnan(pred[:, 3 + H * W:]).all()
+
+
+def test_generic_epilogue_fallback(native_lib, cuda_device, monkeypatch):
+    """The runtime-dispatched generic epilogue (used for combinations without a specialisation) stays correct."""
+    monkeypatch.setenv("GLSDET_CONV_GENERIC_EPILOGUE", "1")
+    test_conv_residuals_and_fp32_out(native_lib, cuda_device)
+    test_pred_conv_nchw_and_decode(native_lib, cuda_device)
+    test_conv_matches_torch(CASES[2], native_lib, cuda_device)
+
+
+def test_bf16_residual_epilogues(native_lib, cuda_device):
+    """bf16 outputs with the pre-activation (fp32, half resolution) or post-activation (bf16, half resolution)
+    residual: the specialised epilogues used by the CSP blocks in front of an upsample+concat and by head.csp."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(21)
+    B, H, W, Cin, Nout = 2, 40, 24, 64, 128
+    x = _bf16r(torch.randn(B, Cin, H, W, generator=g)).to(dev)
+    w = _bf16r(torch.randn(Nout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev)
+    bias = torch.randn(Nout, generator=g).to(dev)
+    pre = torch.randn(B, H // 2, W // 2, Nout, generator=g).to(dev)
+    post = _bf16r(torch.randn(B, H // 2, W // 2, Nout, generator=g)).to(dev)
+    up = lambda t: F.interpolate(t.permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    conv = F.conv2d(x, w, bias)
+    out = torch.zeros((B, H, W, Nout), device=dev, dtype=torch.bfloat16)
+    ConvOp([View(_nhwc(x))], w, bias, ksize=1, act=N.ACT_SILU, out=View(out), pre_res=View(pre.contiguous()),
+           pre_shift=1).launch()
+    torch.cuda.synchronize()
+    ref = conv + up(pre)
+    ref = ref * torch.sigmoid(ref)
+    assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+    out.zero_()
+    ConvOp([View(_nhwc(x))], w, bias, ksize=1, act=N.ACT_RELU, out=View(out),
+           post_res=View(post.to(torch.bfloat16).contiguous()), post_shift=1).launch()
+    torch.cuda.synchronize()
+    ref = torch.relu(conv) + up(post)
+    assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
