@@ -10,6 +10,10 @@
 // view the input as [B, H/2, 2, W/2, (2), C] so that each tap is again a dense box.  A second source
 // tensor gives torch.cat((a, b), 1) in front of the conv for free (its K range simply follows).
 //
+// 3x3 stride-1 convs reuse A vertically: one TMA box of (tile_h + 2) x tile_w pixels per (kx, channel chunk) serves
+// the three ky taps - the MMA descriptor simply starts tile_w rows (a multiple of the 1024-byte swizzle atom)
+// further down - which cuts the A traffic from L2 2.5x.  A and B therefore live in separate smem rings.
+//
 // Warp roles (384 threads, persistent CTAs, static round-robin tile schedule):
 //   warp 0 lane 0 : TMA producer   (A box + weight box per 64-wide K chunk -> smem ring, mbarrier tx)
 //   warp 1 lane 0 : MMA issuer     (4 x tcgen05.mma M128 x N x K16 per chunk; commit frees the smem slot)
@@ -33,7 +37,7 @@ namespace glsdet {
 
 constexpr int kBlockM = 128;
 constexpr int kChunkK = 64;                 // bf16 elements per K chunk = one 128-byte swizzle row
-constexpr int kABytes = kBlockM * kChunkK * 2;
+constexpr int kRowBytes = kChunkK * 2;       // one pixel row of an A/B stage: 128 bytes
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 384;            // 4 control warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
@@ -42,13 +46,18 @@ constexpr int kSmemLimit = 232448;          // 227 KB opt-in limit per CTA
 struct alignas(64) ConvKParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
+  CUtensorMap tmB3[2];       // per source: 3-D view (k, n, ky) of the weights, one box = the three ky taps
   int32_t B, Ho, Wo;
   int32_t tile_w_log2, tile_h;
   int32_t tiles_x, tiles_y, n_blocks, total_tiles;
   int32_t block_n, N;
   int32_t taps, stride;
   int32_t chunks0, chunks1;
-  int32_t stages;
+  int32_t sa, sb;            // A / B ring depths
+  int32_t nsub;              // MMA sub-steps per A step: 3 (ky taps of a 3x3 stride-1 conv) or 1
+  int32_t bgroup;            // sub-steps served by one B stage: 3 (one 3-D box, N <= 128) or 1
+  int32_t a_steps;           // A steps per tile
+  int32_t a_bytes;           // bytes of one A stage
   int32_t tmem_cols;
   const float* bias;
   int32_t act;
@@ -285,30 +294,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int b_bytes = p.block_n * (kChunkK * 2);
+  const int b_tap_bytes = p.block_n * kRowBytes;
+  const int b_bytes = p.bgroup * b_tap_bytes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + p.stages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.stages * b_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + kMaxStages;
-  uint64_t* tfull_bar = bars + 2 * kMaxStages;
-  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [n_blocks * block_n], zero padded
+  uint8_t* smem_b = smem + p.sa * p.a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.sb * b_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + kMaxStages;
+  uint64_t* b_full = bars + 2 * kMaxStages;
+  uint64_t* b_empty = bars + 3 * kMaxStages;
+  uint64_t* tfull_bar = bars + 4 * kMaxStages;
+  uint64_t* tempty_bar = bars + 4 * kMaxStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 6);  // [n_blocks * block_n], zero padded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int k_iters = p.taps * (p.chunks0 + p.chunks1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
     if (p.chunks1 > 0 || p.stride == 2) tma_prefetch_desc(&p.tmA[1]);
     tma_prefetch_desc(&p.tmB);
+    if (p.bgroup == 3) { tma_prefetch_desc(&p.tmB3[0]); tma_prefetch_desc(&p.tmB3[1]); }
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.sa; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.sb; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -329,26 +345,49 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
-    int s = 0;
-    uint32_t ph = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(kABytes + b_bytes);
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
+    auto load_a = [&](const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4) {
+      mbar_wait(&a_empty[sa], pha ^ 1u);
+      mbar_arrive_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
+      tma_load_5d(smem_a + sa * p.a_bytes, tm, &a_full[sa], c0, c1, c2, c3, c4);
+      if (++sa == p.sa) { sa = 0; pha ^= 1u; }
+    };
+    auto load_b = [&](int kchunk, int n0) {
+      mbar_wait(&b_empty[sb], phb ^ 1u);
+      mbar_arrive_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
+      tma_load_2d(smem_b + sb * b_bytes, &p.tmB, &b_full[sb], kchunk * kChunkK, n0);
+      if (++sb == p.sb) { sb = 0; phb ^= 1u; }
+    };
+    auto load_b3 = [&](int src, int kchunk, int n0) {
+      mbar_wait(&b_empty[sb], phb ^ 1u);
+      mbar_arrive_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
+      tma_load_3d(smem_b + sb * b_bytes, &p.tmB3[src], &b_full[sb], kchunk * kChunkK, n0, 0);
+      if (++sb == p.sb) { sb = 0; phb ^= 1u; }
+    };
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      int kcol = 0;
       if (p.stride == 1) {
         for (int src = 0; src < 2; ++src) {
           const int nch = src ? p.chunks1 : p.chunks0;
-          for (int tap = 0; tap < (nch ? p.taps : 0); ++tap) {
-            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-            for (int ch = 0; ch < nch; ++ch) {
-              mbar_wait(&empty_bar[s], ph ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-              tma_load_5d(smem_a + s * kABytes, &p.tmA[src], &full_bar[s], ch * kChunkK, t.x0 + dx, 0, t.y0 + dy,
-                          t.b);
-              tma_load_2d(smem_b + s * b_bytes, &p.tmB, &full_bar[s], kcol * kChunkK, t.n0);
-              ++kcol;
-              if (++s == p.stages) { s = 0; ph ^= 1u; }
+          if (nch == 0) continue;
+          const int kbase = src ? p.taps * p.chunks0 : 0;  // weight K order: (source, tap, chunk)
+          if (p.nsub == 3) {
+            for (int kx = 0; kx < 3; ++kx) {
+              for (int ch = 0; ch < nch; ++ch) {
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, t.b);  // tile_h + 2 rows
+                if (p.bgroup == 3) load_b3(src, kbase + kx * nch + ch, t.n0);         // ky = 0,1,2 in one box
+                else for (int ky = 0; ky < 3; ++ky) load_b(kbase + (ky * 3 + kx) * nch + ch, t.n0);
+              }
+            }
+          } else {
+            for (int tap = 0; tap < p.taps; ++tap) {
+              const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+              const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+              for (int ch = 0; ch < nch; ++ch) {
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + dx, 0, t.y0 + dy, t.b);
+                load_b(kbase + tap * nch + ch, t.n0);
+              }
             }
           }
         }
@@ -361,12 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int py = (ky == 1) ? 0 : 1;
           const int yh = t.y0 + (ky == 0 ? -1 : 0);
           for (int ch = 0; ch < p.chunks0; ++ch) {
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_5d(smem_a + s * kABytes, &p.tmA[map], &full_bar[s], ch * kChunkK, xh, py, yh, t.b);
-            tma_load_2d(smem_b + s * b_bytes, &p.tmB, &full_bar[s], kcol * kChunkK, t.n0);
-            ++kcol;
-            if (++s == p.stages) { s = 0; ph ^= 1u; }
+            load_a(&p.tmA[map], ch * kChunkK, xh, py, yh, t.b);
+            load_b(tap * p.chunks0 + ch, t.n0);
           }
         }
       }
@@ -374,8 +409,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   } else if (warp == 1 && lane == 0) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
-    int s = 0;
-    uint32_t ph = 0;
+    const int a_sub_bytes = (kBlockM >> p.tile_w_log2 == p.tile_h) ? (kRowBytes << p.tile_w_log2) : 0;  // tile_w rows
+    int sa = 0, sb = 0;
+    uint32_t pha = 0, phb = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -383,19 +419,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_wait(&tempty_bar[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
-      for (int k = 0; k < k_iters; ++k) {
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + s * kABytes));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + s * b_bytes));
+      uint32_t acc = 0u;
+      for (int a = 0; a < p.a_steps; ++a) {
+        mbar_wait(&a_full[sa], pha);
+        const uint32_t a_addr = smem_u32(smem_a + sa * p.a_bytes);
+        for (int sub = 0; sub < p.nsub; ++sub) {
+          const int bsub = (p.bgroup == 3) ? sub : 0;
+          if (bsub == 0) mbar_wait(&b_full[sb], phb);
+          tc_fence_after();
+          // ky tap = sub: the 128 rows of the MMA start sub * tile_w rows into the (tile_h + 2)-row A stage
+          const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(sub * a_sub_bytes));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * b_bytes + bsub * b_tap_bytes));
 #pragma unroll
-        for (int kk = 0; kk < kChunkK / 16; ++kk) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
-          umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                    (k > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kChunkK / 16; ++kk) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
+            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, acc);
+            acc = 1u;
+          }
+          if (p.bgroup == 1 || sub == p.nsub - 1) {
+            umma_commit(&b_empty[sb]);
+            if (++sb == p.sb) { sb = 0; phb ^= 1u; }
+          }
         }
-        umma_commit(&empty_bar[s]);
-        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        umma_commit(&a_empty[sa]);
+        if (++sa == p.sa) { sa = 0; pha ^= 1u; }
       }
       umma_commit(&tfull_bar[as]);
     }
@@ -563,7 +610,7 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
 }
 
 int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B, int H, int W, int stride,
-                   int tile_w, int tile_h) {
+                   int tile_w, int box_rows) {
   EncodeTiledFn enc = get_encode_tiled();
   GLSDET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv: source pointer must be 16-byte aligned");
@@ -584,7 +631,7 @@ int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B,
     strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
   }
   cuuint32_t box[5] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(tile_w), 1,
-                       static_cast<cuuint32_t>(tile_h), 1};
+                       static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -646,13 +693,40 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.taps = g.taps; k.stride = d->stride;
   k.chunks0 = g.chunks0; k.chunks1 = g.chunks1;
 
-  const int stage_bytes = kABytes + g.block_n * kChunkK * 2;
-  int stages = (kSmemLimit - 2048 - g.n_pad * 4) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  const int k_iters = g.taps * (g.chunks0 + g.chunks1);
-  if (stages > k_iters * 2) stages = k_iters * 2 > 2 ? k_iters * 2 : 2;
-  k.stages = stages;
-  op->smem_bytes = stages * stage_bytes + 1024 + 256 + g.n_pad * 4;
+  // A/B rings.  3x3 stride-1: one (tile_h + 2)-row A stage feeds three B sub-steps (ky taps).
+  const bool vreuse = (d->ksize == 3 && d->stride == 1 && (k.tile_h + 2) <= 256 && getenv("GLSDET_CONV_NO_VREUSE") == nullptr);
+  k.nsub = vreuse ? 3 : 1;
+  const int box_rows = vreuse ? k.tile_h + 2 : k.tile_h;
+  k.a_bytes = box_rows * best_w * kRowBytes;
+  k.a_steps = (vreuse ? 3 : g.taps) * (g.chunks0 + g.chunks1);
+  k.bgroup = (vreuse && g.block_n <= 128 && getenv("GLSDET_CONV_NO_BGROUP") == nullptr) ? 3 : 1;
+  auto size_rings = [&]() -> bool {
+    const int b_bytes = k.bgroup * g.block_n * kRowBytes;
+    const int budget = kSmemLimit - 2048 - g.n_pad * 4;
+    if (vreuse && k.bgroup == 3) {
+      int stages = budget / (k.a_bytes + b_bytes);
+      if (stages > 6) stages = 6;
+      if (stages < 2) return false;
+      k.sa = k.sb = stages;
+    } else if (vreuse) {
+      k.sa = 3;
+      k.sb = (budget - k.sa * k.a_bytes) / b_bytes;
+      if (k.sb < 3) { k.sa = 2; k.sb = (budget - k.sa * k.a_bytes) / b_bytes; }
+      if (k.sb > kMaxStages) k.sb = kMaxStages;
+      if (k.sb < 2) return false;
+    } else {
+      int stages = budget / (k.a_bytes + b_bytes);
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages > k.a_steps * 2) stages = k.a_steps * 2 > 2 ? k.a_steps * 2 : 2;
+      k.sa = k.sb = stages;
+    }
+    op->smem_bytes = k.sa * k.a_bytes + k.sb * b_bytes + 1024 + 512 + g.n_pad * 4;
+    return true;
+  };
+  if (!size_rings()) {
+    k.bgroup = 1;
+    if (!size_rings()) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
+  }
   int cols = 32;
   while (cols < 2 * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
@@ -690,9 +764,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
 
   int rc = 0;
   if (d->stride == 1) {
-    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 1, best_w, k.tile_h);
+    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
     if (!rc && d->src1)
-      rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, k.tile_h);
+      rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
     else if (!rc) k.tmA[1] = k.tmA[0];
   } else {
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(d->src0);
@@ -713,6 +787,25 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(weight) failed with CUresult %d", (int)r);
       rc = 2;
+    }
+    k.tmB3[0] = k.tmB;
+    k.tmB3[1] = k.tmB;
+    for (int src = 0; src < 2 && rc == 0 && k.bgroup == 3; ++src) {
+      const int nch = src ? g.chunks1 : g.chunks0;
+      if (nch == 0) continue;
+      // (k, n, ky): ky advances three taps = 3 * nch chunks of 64 columns
+      cuuint64_t dims3[3] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad), 3};
+      cuuint64_t strides3[2] = {static_cast<cuuint64_t>(g.k_pad) * 2, static_cast<cuuint64_t>(3) * nch * kChunkK * 2};
+      cuuint32_t box3[3] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(g.block_n), 3};
+      cuuint32_t estr3[3] = {1, 1, 1};
+      r = enc(&k.tmB3[src], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims3, strides3, box3,
+              estr3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {  // not representable: fall back to one 2-D box per ky tap
+        k.bgroup = 1;
+        if (!size_rings()) { set_error("conv_create: tile does not fit shared memory"); rc = 2; }
+        break;
+      }
     }
   }
   if (rc) { free(mem); return rc; }

@@ -267,7 +267,7 @@ def test_model_matches_reference_golden(meta, native_lib, cuda_device):
     for i in range(4):
         ref_i = torch.from_numpy(z[f"logits{i}"])
         inherent = ((emu[i] - ref_i).norm() / ref_i.norm()).item()
-        assert_close_rel(logits[i], ref_i, max(TOL, 1.15 * inherent), f"logits{i}")
+        assert_close_rel(logits[i], ref_i, max(TOL, 1.15 * inherent), f"logits{i}", frac=2e-2)
         assert_close_rel(logits[i], emu[i], 1.5e-2, f"logits{i} vs bf16-storage emulation", max_factor=4.0, frac=5e-2)
     # stand-alone head module fed with the reference's own neck outputs
     hl = net.head([torch.from_numpy(z[f"neck{i}"]).to(cuda_device) for i in range(4)])

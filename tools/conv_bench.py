@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", default=",".join(CASES))
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--act", default="silu")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -34,7 +35,7 @@ def main():
         w = torch.randn(n, sum(cins), k, k, device=dev) * 0.05
         bias = torch.randn(n, device=dev)
         out = torch.empty(B, H // s, W // s, n, device=dev, dtype=torch.bfloat16)
-        op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_SILU, out=View(out))
+        op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=View(out))
         for _ in range(3):
             op.launch()
         torch.cuda.synchronize()
