@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
         ("out_batch_stride", C.c_int64),
         ("dec_stride", C.c_float), ("dec_in_w", C.c_float), ("dec_in_h", C.c_float),
+        ("pred_weight", C.c_void_p), ("pred_bias", C.c_void_p), ("pred_channels", C.c_int32), ("pred_act", C.c_int32),
     ]
 
 

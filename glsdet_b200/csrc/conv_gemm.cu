@@ -70,10 +70,13 @@ struct alignas(64) ConvKParams {
   int64_t out_bs;
   float dec_stride, dec_in_w, dec_in_h;
   int32_t epi;   // EPI_* epilogue specialisation chosen at create time
+  const float* pred_w;   // fused prediction conv: fp32 [pred_n][N]
+  const float* pred_b;
+  int32_t pred_n, pred_act;
 };
 
 enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
-       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7 };
+       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8 };
 
 struct TileCoord {
   int b, y0, x0, n0;
@@ -269,6 +272,58 @@ __device__ __forceinline__ void epi16_f32_plain(const uint32_t (&raw)[16], const
   }
 }
 
+// Fused prediction conv: acc[0..4*NV) += act(v[j]) * Wp[k = k0 + j][0..4*NV) for the 16 channels of one chunk.
+// s_pw is [N][16] (prediction channel fastest), so the float4 weight loads are warp-uniform broadcasts.
+template <int NV>
+__device__ __forceinline__ void pred_accumulate16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+                                                  const float* s_pw, float (&acc)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = __uint_as_float(raw[j]) + s_bias[j];
+    v = silu ? silu_f(v) : fmaxf(v, 0.0f);
+    const float4* w = reinterpret_cast<const float4*>(s_pw + j * 16);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      const float4 ww = w[q];
+      acc[4 * q] = fmaf(v, ww.x, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(v, ww.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(v, ww.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(v, ww.w, acc[4 * q + 3]);
+    }
+  }
+}
+
+// Output of the fused prediction conv for one pixel: raw logits (NCHW planes or NHWC rows), sigmoid rows, or the
+// YOLOX box decode (utils_bbox.py:270-305).
+__device__ __forceinline__ void store_pred(const ConvKParams& p, const float (&y)[16], int b, int oy, int ox) {
+  if (p.out_mode == GLSDET_OUT_NCHW_F32) {
+    const int64_t plane = static_cast<int64_t>(p.Ho) * p.Wo;
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+               static_cast<int64_t>(p.out_coff) * plane + static_cast<int64_t>(oy) * p.Wo + ox;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < p.pred_n) o[j * plane] = y[j];
+    return;
+  }
+  float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+             (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
+  if (p.pred_act == GLSDET_ACT_YOLOX_BOX) {
+    o[0] = ((y[0] + static_cast<float>(ox)) * p.dec_stride) / p.dec_in_w;
+    o[1] = ((y[1] + static_cast<float>(oy)) * p.dec_stride) / p.dec_in_h;
+    o[2] = (expf(y[2]) * p.dec_stride) / p.dec_in_w;
+    o[3] = (expf(y[3]) * p.dec_stride) / p.dec_in_h;
+    o[4] = 1.0f / (1.0f + expf(-y[4]));
+  } else if (p.pred_act == GLSDET_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < p.pred_n) o[j] = 1.0f / (1.0f + expf(-y[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < p.pred_n) o[j] = y[j];
+  }
+}
+
 // Walks the accumulator columns of one tile: two tcgen05.ld in flight per wait, then f(raw, chunk) on each.
 template <typename F>
 __device__ __forceinline__ void epi_walk(uint32_t taddr, int c_begin, int c_end, F&& f) {
@@ -307,6 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint64_t* tempty_bar = bars + 4 * kMaxStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 4);
   float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 6);  // [n_blocks * block_n], zero padded
+  float* s_pw = s_bias + p.n_blocks * p.block_n;                         // fused prediction weights [N][16]
+  float* s_red = s_pw + p.block_n * 16;                                  // [2][128][16] partial sums of the upper column half
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -338,6 +395,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
     s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
+  if (p.epi == EPI_TOWER_PRED) {
+    for (int i = threadIdx.x; i < p.block_n * 16; i += kThreads) {
+      const int kk = i >> 4, j = i & 15;
+      s_pw[i] = (kk < p.N && j < p.pred_n) ? __ldg(p.pred_w + static_cast<int64_t>(j) * p.N + kk) : 0.0f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -542,6 +605,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           });
           break;
         }
+        case EPI_TOWER_PRED: {
+          // second tower conv + prediction conv: the activated tile never leaves the SM.  Each thread reduces its
+          // row over its half of the channels; the two warps of a lane quarter meet at a 64-thread named barrier.
+          float acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+          if (p.pred_n <= 8) {
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              pred_accumulate16<2>(raw, sb + c * 16, silu, s_pw + c * 256, acc);
+            });
+          } else if (p.pred_n <= 12) {
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              pred_accumulate16<3>(raw, sb + c * 16, silu, s_pw + c * 256, acc);
+            });
+          } else {
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              pred_accumulate16<4>(raw, sb + c * 16, silu, s_pw + c * 256, acc);
+            });
+          }
+          float* red = s_red + (as * kBlockM + r) * 16;
+          if (half == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(red + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+          if (half == 0 && valid) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 o4 = *reinterpret_cast<const float4*>(red + j);
+              acc[j] += o4.x; acc[j + 1] += o4.y; acc[j + 2] += o4.z; acc[j + 3] += o4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < p.pred_n) acc[j] += __ldg(p.pred_b + j);
+            store_pred(p, acc, t.b, oy, ox);
+          }
+          break;
+        }
         default: {
           for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[16];
@@ -660,6 +762,19 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   GLSDET_REQUIRE(d->src0 && d->weight && d->out, "conv_create: null src0/weight/out pointer");
   GLSDET_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "conv_create: bad out_mode %d", d->out_mode);
   GLSDET_REQUIRE(d->act >= 0 && d->act <= GLSDET_ACT_YOLOX_BOX, "conv_create: bad act %d", d->act);
+  if (d->pred_weight != nullptr) {
+    GLSDET_REQUIRE(d->pred_bias != nullptr && d->pred_channels >= 1 && d->pred_channels <= 16,
+                   "conv_create: fused prediction conv needs a bias and 1..16 channels");
+    GLSDET_REQUIRE(d->out_channels <= 256 && (d->out_channels % 16) == 0,
+                   "conv_create: fused prediction conv needs out_channels <= 256 and a multiple of 16");
+    GLSDET_REQUIRE(d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU,
+                   "conv_create: fused prediction conv supports SiLU/ReLU towers");
+    GLSDET_REQUIRE(d->out_mode == GLSDET_OUT_NHWC_F32 || d->out_mode == GLSDET_OUT_NCHW_F32,
+                   "conv_create: fused prediction conv writes fp32 rows or planes");
+    GLSDET_REQUIRE(d->pred_act == GLSDET_ACT_NONE || d->pred_act == GLSDET_ACT_SIGMOID ||
+                   (d->pred_act == GLSDET_ACT_YOLOX_BOX && d->pred_channels == 5), "conv_create: bad pred_act");
+    GLSDET_REQUIRE(d->pre_res == nullptr && d->post_res == nullptr, "conv_create: fused prediction conv takes no residual");
+  }
 
   void* mem = nullptr;
   if (posix_memalign(&mem, 64, sizeof(glsdet_conv)) != 0 || mem == nullptr) {
@@ -699,10 +814,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   const int box_rows = vreuse ? k.tile_h + 2 : k.tile_h;
   k.a_bytes = box_rows * best_w * kRowBytes;
   k.a_steps = (vreuse ? 3 : g.taps) * (g.chunks0 + g.chunks1);
+  const bool fused_pred = d->pred_weight != nullptr;
+  const int pred_smem = fused_pred ? (g.block_n * 16 + 2 * kBlockM * 16) * 4 : 0;
   k.bgroup = (vreuse && g.block_n <= 128 && getenv("GLSDET_CONV_NO_BGROUP") == nullptr) ? 3 : 1;
   auto size_rings = [&]() -> bool {
     const int b_bytes = k.bgroup * g.block_n * kRowBytes;
-    const int budget = kSmemLimit - 2048 - g.n_pad * 4;
+    const int budget = kSmemLimit - 2048 - g.n_pad * 4 - pred_smem;
     if (vreuse && k.bgroup == 3) {
       int stages = budget / (k.a_bytes + b_bytes);
       if (stages > 6) stages = 6;
@@ -720,7 +837,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
       if (stages > k.a_steps * 2) stages = k.a_steps * 2 > 2 ? k.a_steps * 2 : 2;
       k.sa = k.sb = stages;
     }
-    op->smem_bytes = k.sa * k.a_bytes + k.sb * b_bytes + 1024 + 512 + g.n_pad * 4;
+    op->smem_bytes = k.sa * k.a_bytes + k.sb * b_bytes + 1024 + 512 + g.n_pad * 4 + pred_smem;
     return true;
   };
   if (!size_rings()) {
@@ -760,6 +877,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (const char* e = getenv("GLSDET_CONV_GENERIC_EPILOGUE")) {  // tests: force the generic epilogue
       if (e[0] == '1') k.epi = EPI_GENERIC;
     }
+    k.pred_w = d->pred_weight; k.pred_b = d->pred_bias; k.pred_n = d->pred_channels; k.pred_act = d->pred_act;
+    if (fused_pred) k.epi = EPI_TOWER_PRED;
   }
 
   int rc = 0;

@@ -10,7 +10,8 @@ forward pass becomes a flat list of native launches (no PyTorch math on the path
   * CSP conv1/conv2 share their input -> one GEMM with stacked output channels; the same for the first conv of
     the cls/reg towers; reg_preds/obj_preds are one N=5 GEMM;
   * PixelShuffle is a pure re-addressing because the producing conv's output channels are permuted at pack time;
-  * in `decoded` mode the prediction convs apply sigmoid/exp/grid/stride and write [B, A, 5+nc] rows directly.
+  * the 1x1 prediction convs are fused into the epilogue of the second tower conv (its activated tile never leaves
+    the SM); in `decoded` mode that epilogue also applies sigmoid/exp/grid/stride and writes [B, A, 5+nc] rows.
 """
 from __future__ import annotations
 
@@ -201,29 +202,32 @@ class FFAPathPlan:
             wc0, bc0 = self._folded(f"head.cls_convs.{i}.0")
             wr0, br0 = self._folded(f"head.reg_convs.{i}.0")
             F = self._buf(f"tower{k}", k, 2 * hc)
-            cf = self._buf(f"cls_feat{k}", k, hc)
-            rf = self._buf(f"reg_feat{k}", k, hc)
             self._conv(hd, torch.cat([wc0, wr0], 0), torch.cat([bc0, br0], 0), [View(p[k])], View(F), 3)
-            self._base_conv(hd, f"head.cls_convs.{i}.1", [View(F, 0, hc)], View(cf))
-            self._base_conv(hd, f"head.reg_convs.{i}.1", [View(F, hc, hc)], View(rf))
+            wc1, bc1 = self._folded(f"head.cls_convs.{i}.1")
+            wr1, br1 = self._folded(f"head.reg_convs.{i}.1")
             sd = self.sd
             w_ro = torch.cat([sd[f"head.reg_preds.{i}.weight"], sd[f"head.obj_preds.{i}.weight"]], 0).float()
             b_ro = torch.cat([sd[f"head.reg_preds.{i}.bias"], sd[f"head.obj_preds.{i}.bias"]], 0).float()
             w_cl, b_cl = sd[f"head.cls_preds.{i}.weight"].float(), sd[f"head.cls_preds.{i}.bias"].float()
-            # raw logits, reference layout cat([reg, obj, cls], 1) (yolox_ffa.py:116)
+            cls_in, reg_in = [View(F, 0, hc)], [View(F, hc, hc)]
+            # The second tower conv and the 1x1 prediction conv run as one kernel (the activated tile stays on the
+            # SM).  Raw variant: reference layout cat([reg, obj, cls], 1) (yolox_ffa.py:116).
             kw = dict(out_mode=N.OUT_NCHW_F32, out_ld=nch, out_batch_stride=nch * h * w)
-            self._conv(self.pred_raw_ops, w_ro, b_ro, [View(rf)], self.logits[k], 1, act=N.ACT_NONE, out_coff=0, **kw)
-            self._conv(self.pred_raw_ops, w_cl, b_cl, [View(cf)], self.logits[k], 1, act=N.ACT_NONE, out_coff=5, **kw)
-            # decoded rows (utils_bbox.py:254-306 fused into the epilogue)
+            self._conv(self.pred_raw_ops, wr1, br1, reg_in, self.logits[k], 3, out_coff=0, pred_weight=w_ro,
+                       pred_bias=b_ro, pred_act=N.ACT_NONE, **kw)
+            self._conv(self.pred_raw_ops, wc1, bc1, cls_in, self.logits[k], 3, out_coff=5, pred_weight=w_cl,
+                       pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
+            # Decoded variant: utils_bbox.py:254-306 applied in the same epilogue, rows of [B, A, 5+nc].
             stride = float(self.in_h / h)
             kw = dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch)
-            self._conv(self.pred_dec_ops, w_ro, b_ro, [View(rf)], self.pred, 1, act=N.ACT_YOLOX_BOX,
-                       out_coff=a_off * nch, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
-            self._conv(self.pred_dec_ops, w_cl, b_cl, [View(cf)], self.pred, 1, act=N.ACT_SIGMOID,
-                       out_coff=a_off * nch + 5, **kw)
+            self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred, 3, out_coff=a_off * nch, pred_weight=w_ro,
+                       pred_bias=b_ro, pred_act=N.ACT_YOLOX_BOX, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
+            self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred, 3, out_coff=a_off * nch + 5, pred_weight=w_cl,
+                       pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             a_off += h * w
-        # prediction convs were counted twice (raw + decoded variants)
+        # the second tower convs exist twice (raw + decoded variants); count them once, plus the prediction convs
         self.flops -= sum(op.flops for op in self.pred_dec_ops)
+        self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
 
     # ------------------------------------------------------------------ execution
     def load_features(self, feats: Sequence[torch.Tensor], stream=None) -> None:

@@ -71,7 +71,9 @@ class ConvOp:
     def __init__(self, srcs: Sequence[View], weight: torch.Tensor, bias: Optional[torch.Tensor], *, ksize: int,
                  stride: int = 1, act: int = N.ACT_NONE, out, out_mode: int = N.OUT_NHWC_BF16, out_ld: int = 0,
                  out_coff: int = 0, out_batch_stride: int = 0, pre_res: Optional[View] = None, pre_shift: int = 0,
-                 post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0)):
+                 post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0),
+                 pred_weight: Optional[torch.Tensor] = None, pred_bias: Optional[torch.Tensor] = None,
+                 pred_act: int = N.ACT_NONE):
         lib = N.load()
         assert 1 <= len(srcs) <= 2
         b, h, w = srcs[0].bhw
@@ -104,7 +106,7 @@ class ConvOp:
             assert post_res.bhw == (b, ho >> post_shift, wo >> post_shift)
             d.post_res, d.post_shift, d.post_ld = post_res.ptr, post_shift, post_res.ld
         if isinstance(out, View):
-            assert out.bhw == (b, ho, wo) and out.c >= n_out
+            assert out.bhw == (b, ho, wo) and (out.c >= n_out or pred_weight is not None)
             d.out, d.out_ld, d.out_coff = out.t.data_ptr(), out.ld, out.coff
             d.out_batch_stride = ho * wo * out.ld
             d.out_mode = N.OUT_NHWC_BF16 if out.t.dtype == torch.bfloat16 else N.OUT_NHWC_F32
@@ -115,6 +117,13 @@ class ConvOp:
             d.out_mode = out_mode
             self._out_t = out
         d.dec_stride, d.dec_in_w, d.dec_in_h = dec
+        self.pred_weight = self.pred_bias = None
+        if pred_weight is not None:   # fused prediction conv on the activated tile (never stored)
+            self.pred_weight = pred_weight.detach().float().reshape(pred_weight.shape[0], -1).contiguous()
+            assert self.pred_weight.shape[1] == n_out and self.pred_weight.shape[0] <= 16
+            self.pred_bias = pred_bias.detach().float().contiguous()
+            d.pred_weight, d.pred_bias = self.pred_weight.data_ptr(), self.pred_bias.data_ptr()
+            d.pred_channels, d.pred_act = self.pred_weight.shape[0], pred_act
         self._keep = (srcs, pre_res, post_res)
         self.desc = d
         self.handle = C.c_void_p()

@@ -89,6 +89,17 @@ typedef struct glsdet_conv_desc {
   int64_t out_batch_stride; /* elements between images in the destination */
   /* GLSDET_ACT_YOLOX_BOX only: stride of this level and network input size (utils_bbox.py:285,303-304) */
   float dec_stride, dec_in_w, dec_in_h;
+  /*
+   * Optional fused prediction conv (yolox_ffa.py:88,100,109: cls_preds / reg_preds / obj_preds applied to the
+   * output of the second tower conv).  When pred_weight != NULL the activated tile of THIS conv is not stored;
+   * instead  y[j] = pred_bias[j] + sum_k act(conv)[k] * pred_weight[j][k]  (j < pred_channels <= 16) is computed in
+   * the epilogue, `pred_act` (NONE, SIGMOID or YOLOX_BOX) is applied and y is written through out / out_mode /
+   * out_ld / out_coff / out_batch_stride (NHWC_F32 rows or NCHW_F32 planes).  Requires out_channels <= 256.
+   */
+  const float* pred_weight;  /* fp32 [pred_channels][out_channels] */
+  const float* pred_bias;    /* fp32 [pred_channels] */
+  int32_t pred_channels;
+  int32_t pred_act;
 } glsdet_conv_desc;
 
 /* library / device */

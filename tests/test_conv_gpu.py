@@ -208,3 +208,53 @@ def test_bf16_residual_epilogues(native_lib, cuda_device):
     torch.cuda.synchronize()
     ref = torch.relu(conv) + up(post)
     assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("n_tower,n_pred,pred_act", [(128, 10, "sigmoid"), (128, 5, "box"), (128, 10, "none_nchw"),
+                                                     (256, 3, "sigmoid"), (64, 5, "none_nchw"), (96, 16, "none_rows")])
+def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_device):
+    """3x3 tower conv + SiLU + 1x1 prediction conv (+ decode) in one kernel vs the two-step PyTorch evaluation."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n_tower * 31 + n_pred)
+    B, H, W, Cin = 2, 24, 40, 128
+    x = _bf16r(torch.randn(B, Cin, H, W, generator=g)).to(dev)
+    w = _bf16r(torch.randn(n_tower, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+    bias = torch.randn(n_tower, generator=g).to(dev)
+    wp = (torch.randn(n_pred, n_tower, 1, 1, generator=g) / n_tower ** 0.5).to(dev)
+    bp = torch.randn(n_pred, generator=g).to(dev)
+    t = F.conv2d(x, w, bias, padding=1)
+    t = t * torch.sigmoid(t)
+    y = F.conv2d(t, wp, bp)                                     # [B, n_pred, H, W]
+    rows = y.permute(0, 2, 3, 1).reshape(B, H * W, n_pred)
+    nch = n_pred + 3
+    if pred_act == "none_nchw":
+        out = torch.full((B, nch, H, W), float("nan"), device=dev)
+        ConvOp([View(_nhwc(x))], w, bias, ksize=3, act=N.ACT_SILU, out=out, out_mode=N.OUT_NCHW_F32, out_ld=nch,
+               out_coff=2, out_batch_stride=nch * H * W, pred_weight=wp, pred_bias=bp, pred_act=N.ACT_NONE).launch()
+        torch.cuda.synchronize()
+        assert torch.allclose(out[:, 2:2 + n_pred], y, rtol=2e-3, atol=2e-3)
+        assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + n_pred:]).all()
+        return
+    out = torch.full((B, H * W, nch), float("nan"), device=dev)
+    act = {"sigmoid": N.ACT_SIGMOID, "box": N.ACT_YOLOX_BOX, "none_rows": N.ACT_NONE}[pred_act]
+    stride, in_h, in_w = 8.0, H * 8.0, W * 8.0
+    ConvOp([View(_nhwc(x))], w, bias, ksize=3, act=N.ACT_SILU, out=out, out_mode=N.OUT_NHWC_F32, out_ld=nch,
+           out_coff=1, out_batch_stride=H * W * nch, pred_weight=wp, pred_bias=bp, pred_act=act,
+           dec=(stride, in_w, in_h)).launch()
+    torch.cuda.synchronize()
+    got = out[:, :, 1:1 + n_pred]
+    if pred_act == "sigmoid":
+        ref = torch.sigmoid(rows)
+    elif pred_act == "none_rows":
+        ref = rows
+    else:
+        gy, gx = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+        gx, gy = gx.reshape(1, -1).float(), gy.reshape(1, -1).float()
+        ref = torch.stack([(rows[..., 0] + gx) * stride / in_w, (rows[..., 1] + gy) * stride / in_h,
+                           torch.exp(rows[..., 2]) * stride / in_w, torch.exp(rows[..., 3]) * stride / in_h,
+                           torch.sigmoid(rows[..., 4])], dim=-1)
+    assert torch.allclose(got, ref, rtol=3e-3, atol=3e-3), (got - ref).abs().max()
+    assert torch.isnan(out[:, :, 0]).all() and torch.isnan(out[:, :, 1 + n_pred:]).all()
