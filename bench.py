@@ -40,12 +40,13 @@ WEIGHT_SEED = 0
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--max-det", type=int, default=1000, help="detections per image copied out / gathered")
-    ap.add_argument("--cpu-images", type=int, default=4, help="images of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=16, help="images per pass of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample: repeat passes for about this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -57,6 +58,16 @@ def peaks():
         return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def conv_traffic(batch):
+    """DRAM bytes (read + write) of the conv segment of one step, from the committed ncu capture (same batch only)."""
+    f = ROOT / "profiles" / "r1_conv_traffic.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        if d.get("batch") == batch:
+            return d["total_bytes_per_step"]
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -96,7 +107,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -335,20 +346,24 @@ def run_native_arm(args):
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                             "frac": achieved_tf / pk["tf_sustained"], "traffic": None,
+                             "frac": achieved_tf / pk["tf_sustained"], "traffic": conv_traffic(B),
                              "kernel": "conv_gemm_kernel (all conv launches of a step, neck+FFA+head segment)",
                              "algorithmic_gflop_per_image": ALGO_GFLOP_PER_IMAGE, "segment_ms": conv_ms,
                              "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"},
                 "launches_per_step": int(launches) // args.steps}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = args.cpu_images
+            n = min(args.cpu_images, B)
             feats_cpu = [t[:n].clone() for t in host_feats]
             cpu_reference_run(sd, feats_cpu, 1, threads)  # warm-up
-            dt, ccand, ckept = cpu_reference_run(sd, feats_cpu, n, threads)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "images/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n} of the batch's images, one at a time (yolo.py per-image loop), fp32, "
-                                              f"torch CPU {threads} threads, {dt:.1f} s",
+            total_dt, images, ccand, ckept = 0.0, 0, None, None
+            while total_dt < args.cpu_seconds and images < 64 * n:
+                dt, ccand, ckept = cpu_reference_run(sd, feats_cpu, n, threads)
+                total_dt += dt
+                images += n
+            line["cpu_baseline"] = {"value": images / total_dt, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": f"{images} images ({n} of the batch's images, repeated), one at a time "
+                                              f"(yolo.py per-image loop), fp32, torch CPU {threads} threads, {total_dt:.1f} s",
                                     "candidates_per_image": ccand, "kept_per_image": ckept}
         print(json.dumps(line), flush=True)
     if world > 1:
