@@ -50,6 +50,7 @@ struct alignas(64) ConvKParams {
   int32_t B, Ho, Wo;
   int32_t tile_w_log2, tile_h;
   int32_t tiles_x, tiles_y, n_blocks, total_tiles;
+  int32_t m_tiles, total_pairs;   // 2-CTA mode: a CTA pair takes M tiles (2i, 2i+1) of one N block
   int32_t block_n, N;
   int32_t taps, stride;
   int32_t chunks0, chunks1;
@@ -93,6 +94,26 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   t.x0 = tx << p.tile_w_log2;
   t.y0 = ty * p.tile_h;
   t.n0 = nb * p.block_n;
+  return t;
+}
+
+// 2-CTA mode: work item = (pair of adjacent M tiles, N block); CTA `rank` of the pair owns M tile 2*pm + rank.
+// An odd tile count leaves one dummy tile: it sits below the image, so TMA zero-fills it and no row is stored.
+__device__ __forceinline__ TileCoord decode_pair(const ConvKParams& p, int work, int rank) {
+  TileCoord t;
+  const int nb = work % p.n_blocks;
+  int m = 2 * (work / p.n_blocks) + rank;
+  t.n0 = nb * p.block_n;
+  if (m >= p.m_tiles) {
+    t.b = 0; t.x0 = 0; t.y0 = p.tiles_y * p.tile_h;
+    return t;
+  }
+  const int tx = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int ty = m % p.tiles_y;
+  t.b = m / p.tiles_y;
+  t.x0 = tx << p.tile_w_log2;
+  t.y0 = ty * p.tile_h;
   return t;
 }
 
@@ -344,13 +365,15 @@ __device__ __forceinline__ void epi_walk(uint32_t taddr, int c_begin, int c_end,
   }
 }
 
+template <bool k2>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int b_tap_bytes = p.block_n * kRowBytes;
-  const int b_bytes = p.bgroup * b_tap_bytes;
+  // 2-CTA mode: every CTA stages half of the B rows, and one stage always carries all nsub taps (single ring)
+  const int b_tap_bytes = (k2 ? (p.block_n >> 1) : p.block_n) * kRowBytes;
+  const int b_bytes = (k2 ? p.nsub : p.bgroup) * b_tap_bytes;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.sa * p.a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.sb * b_bytes);
@@ -367,6 +390,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = k2 ? cluster_ctarank() : 0u;
+  const int work0 = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int work_stride = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_work = k2 ? p.total_pairs : p.total_tiles;
+  auto decode = [&](int work) { return k2 ? decode_pair(p, work, static_cast<int>(cta_rank)) : decode_tile(p, work); };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA[0]);
@@ -376,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.sa; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], k2 ? 2 : 1);   // 2-CTA: both producers arrive on the leader's barrier
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < p.sb; ++s) {
@@ -385,13 +413,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], k2 ? 2 * kEpiWarps : kEpiWarps);  // 2-CTA: the peer's epilogue warps arrive too
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
-    tmem_relinquish();
+    if (k2) { tmem2_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols)); tmem2_relinquish(); }
+    else { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols)); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
     s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
@@ -403,10 +431,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (k2) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  if (k2 && warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer, 2-CTA mode (single ring)
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t pair_bytes = 2u * static_cast<uint32_t>(p.a_bytes + b_bytes);
+    const int n_half = p.block_n >> 1;
+    for (int work = work0; work < total_work; work += work_stride) {
+      const TileCoord t = decode(work);
+      const int nrow0 = t.n0 + static_cast<int>(cta_rank) * n_half;
+      for (int src = 0; src < 2; ++src) {
+        const int nch = src ? p.chunks1 : p.chunks0;
+        if (nch == 0) continue;
+        const int kbase = src ? p.taps * p.chunks0 : 0;
+        const int outer = (p.nsub == 3) ? 3 : p.taps;     // kx for 3x3 with vertical reuse, else the tap itself
+        for (int o = 0; o < outer; ++o) {
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait(&a_empty[s], ph ^ 1u);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[s], pair_bytes);
+            else mbar_arrive_cluster(&a_full[s], 0);
+            uint8_t* bdst = smem_b + s * b_bytes;
+            if (p.nsub == 3) {
+              tma2_load_5d(smem_a + s * p.a_bytes, &p.tmA[src], &a_full[s], ch * kChunkK, t.x0 + o - 1, 0, t.y0 - 1, t.b);
+              if (p.bgroup == 3) {
+                tma2_load_3d(bdst, &p.tmB3[src], &a_full[s], (kbase + o * nch + ch) * kChunkK, nrow0, 0);
+              } else {
+                for (int ky = 0; ky < 3; ++ky)
+                  tma2_load_2d(bdst + ky * b_tap_bytes, &p.tmB, &a_full[s], (kbase + (ky * 3 + o) * nch + ch) * kChunkK, nrow0);
+              }
+            } else {
+              const int dy = (p.taps == 9) ? o / 3 - 1 : 0;
+              const int dx = (p.taps == 9) ? o % 3 - 1 : 0;
+              tma2_load_5d(smem_a + s * p.a_bytes, &p.tmA[src], &a_full[s], ch * kChunkK, t.x0 + dx, 0, t.y0 + dy, t.b);
+              tma2_load_2d(bdst, &p.tmB, &a_full[s], (kbase + o * nch + ch) * kChunkK, nrow0);
+            }
+            if (++s == p.sa) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (k2 && warp == 1) {
+    // ------------------------------------------------------------ MMA issuer, 2-CTA mode (leader only)
+    // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
+    // issues.  A divergent single-lane loop costs a register->uniform-register move per operand of every MMA.
+    if (cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.block_n));
+      const int a_sub_bytes = kRowBytes << p.tile_w_log2;
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int work = work0; work < total_work; work += work_stride, ++it) {
+        const int as = it & 1;
+        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+        uint32_t acc = 0u;
+        for (int a = 0; a < p.a_steps; ++a) {
+          mbar_wait(&a_full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * p.a_bytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * b_bytes);
+          if (elect_one()) {
+            for (int sub = 0; sub < p.nsub; ++sub) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(sub * a_sub_bytes));
+              const uint64_t db = umma_desc_k_sw128(b_addr + static_cast<uint32_t>(sub * b_tap_bytes));
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                umma2_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                           (acc | static_cast<uint32_t>(sub | kk)) ? 1u : 0u);
+              }
+            }
+            umma2_commit_both(&a_empty[s]);   // frees this stage in both CTAs
+            if (a == p.a_steps - 1) umma2_commit_both(&tfull_bar[as]);  // both epilogues may read their half
+          }
+          __syncwarp();
+          acc = 1u;
+          if (++s == p.sa) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (!k2 && warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
@@ -428,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tma_load_3d(smem_b + sb * b_bytes, &p.tmB3[src], &b_full[sb], kchunk * kChunkK, n0, 0);
       if (++sb == p.sb) { sb = 0; phb ^= 1u; }
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = work0; tile < total_work; tile += work_stride) {
       const TileCoord t = decode_tile(p, tile);
       if (p.stride == 1) {
         for (int src = 0; src < 2; ++src) {
@@ -469,14 +578,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (!k2 && warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
-    const int a_sub_bytes = (kBlockM >> p.tile_w_log2 == p.tile_h) ? (kRowBytes << p.tile_w_log2) : 0;  // tile_w rows
+    const int a_sub_bytes = kRowBytes << p.tile_w_log2;  // tile_w rows
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
       const int as = it & 1;
       const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
       mbar_wait(&tempty_bar[as], aph ^ 1u);
@@ -490,24 +599,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int bsub = (p.bgroup == 3) ? sub : 0;
           if (bsub == 0) mbar_wait(&b_full[sb], phb);
           tc_fence_after();
-          // ky tap = sub: the 128 rows of the MMA start sub * tile_w rows into the (tile_h + 2)-row A stage
-          const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(sub * a_sub_bytes));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * b_bytes + bsub * b_tap_bytes));
+          const bool last_of_b = (p.bgroup == 1 || sub == p.nsub - 1);
+          if (elect_one()) {
+            // ky tap = sub: the 128 rows of the MMA start sub * tile_w rows into the (tile_h + 2)-row A stage
+            const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(sub * a_sub_bytes));
+            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * b_bytes + bsub * b_tap_bytes));
 #pragma unroll
-          for (int kk = 0; kk < kChunkK / 16; ++kk) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, acc);
-            acc = 1u;
+            for (int kk = 0; kk < kChunkK / 16; ++kk) {
+              // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
+              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                        (acc | static_cast<uint32_t>(kk)) ? 1u : 0u);
+            }
+            if (last_of_b) umma_commit(&b_empty[sb]);
+            if (sub == p.nsub - 1) {
+              umma_commit(&a_empty[sa]);
+              if (a == p.a_steps - 1) umma_commit(&tfull_bar[as]);
+            }
           }
-          if (p.bgroup == 1 || sub == p.nsub - 1) {
-            umma_commit(&b_empty[sb]);
+          __syncwarp();
+          acc = 1u;
+          if (last_of_b) {
             if (++sb == p.sb) { sb = 0; phb ^= 1u; }
           }
         }
-        umma_commit(&a_empty[sa]);
         if (++sa == p.sa) { sa = 0; pha ^= 1u; }
       }
-      umma_commit(&tfull_bar[as]);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -522,8 +638,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
     const bool silu = (p.act == GLSDET_ACT_SILU);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
+      const TileCoord t = decode(tile);
       const int as = it & 1;
       const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
       mbar_wait(&tfull_bar[as], aph);
@@ -656,14 +772,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (k2) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread waits for both epilogues
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (k2) cluster_sync_all();   // the peer may still be reading operands / signalling barriers of this CTA
   tc_fence_after();
-  if (warp == 2) tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  if (warp == 2) {
+    if (k2) tmem2_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
 }
 
 }  // namespace glsdet
@@ -675,6 +798,7 @@ struct glsdet_conv {
   ConvKParams kp;
   int grid;
   int smem_bytes;
+  int two_cta;   // launched as clusters of 2 CTAs issuing tcgen05.mma.cta_group::2
 };
 
 namespace {
@@ -814,12 +938,33 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   const int box_rows = vreuse ? k.tile_h + 2 : k.tile_h;
   k.a_bytes = box_rows * best_w * kRowBytes;
   k.a_steps = (vreuse ? 3 : g.taps) * (g.chunks0 + g.chunks1);
+  // 2-CTA mode (cta_group::2, M = 256 per CTA pair): halves the B operand traffic of every SM's shared memory,
+  // which is what bounds the 1-CTA kernel on dense 3x3 convs.  Used for stride-1 convs with enough tiles.
+  k.m_tiles = k.tiles_x * k.tiles_y * k.B;
+  k.total_pairs = ((k.m_tiles + 1) / 2) * k.n_blocks;
+  // Measured on B200 (profiles/README.md): correct, 40 % less L2->SM traffic, but 5-15 % slower than the 1-CTA
+  // kernel at these shapes (neither L2 nor shared memory is the limiter once the MMA issue loop is warp-uniform),
+  // so it is opt-in: GLSDET_CONV_2CTA=1.
+  bool two_cta = false;
+  if (const char* e = getenv("GLSDET_CONV_2CTA")) {
+    if (e[0] == '1') two_cta = d->stride == 1 && (g.block_n % 32) == 0;
+  }
+  op->two_cta = two_cta ? 1 : 0;
   const bool fused_pred = d->pred_weight != nullptr;
   const int pred_smem = fused_pred ? (g.block_n * 16 + 2 * kBlockM * 16) * 4 : 0;
-  k.bgroup = (vreuse && g.block_n <= 128 && getenv("GLSDET_CONV_NO_BGROUP") == nullptr) ? 3 : 1;
+  k.bgroup = (vreuse && (g.block_n <= 128 || two_cta) && getenv("GLSDET_CONV_NO_BGROUP") == nullptr) ? 3 : 1;
   auto size_rings = [&]() -> bool {
-    const int b_bytes = k.bgroup * g.block_n * kRowBytes;
     const int budget = kSmemLimit - 2048 - g.n_pad * 4 - pred_smem;
+    if (two_cta) {  // single ring; a stage = A box + all nsub taps of this CTA's half of B
+      const int b_bytes2 = k.nsub * (g.block_n / 2) * kRowBytes;
+      int stages = budget / (k.a_bytes + b_bytes2);
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages < 2) return false;
+      k.sa = k.sb = stages;
+      op->smem_bytes = stages * (k.a_bytes + b_bytes2) + 1024 + 512 + g.n_pad * 4 + pred_smem;
+      return true;
+    }
+    const int b_bytes = k.bgroup * g.block_n * kRowBytes;
     if (vreuse && k.bgroup == 3) {
       int stages = budget / (k.a_bytes + b_bytes);
       if (stages > 6) stages = 6;
@@ -898,7 +1043,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     EncodeTiledFn enc = get_encode_tiled();
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.k_pad) * 2};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(g.block_n)};
+    const cuuint32_t b_rows = static_cast<cuuint32_t>(op->two_cta ? g.block_n / 2 : g.block_n);
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), b_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight), dims, strides, box,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -915,7 +1061,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
       // (k, n, ky): ky advances three taps = 3 * nch chunks of 64 columns
       cuuint64_t dims3[3] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad), 3};
       cuuint64_t strides3[2] = {static_cast<cuuint64_t>(g.k_pad) * 2, static_cast<cuuint64_t>(3) * nch * kChunkK * 2};
-      cuuint32_t box3[3] = {static_cast<cuuint32_t>(kChunkK), static_cast<cuuint32_t>(g.block_n), 3};
+      cuuint32_t box3[3] = {static_cast<cuuint32_t>(kChunkK), b_rows, 3};
       cuuint32_t estr3[3] = {1, 1, 1};
       r = enc(&k.tmB3[src], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims3, strides3, box3,
               estr3, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -933,7 +1079,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) {
       free(mem);
       set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
@@ -942,14 +1090,39 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     attr_set[dev] = true;
   }
   const int sms = device_sm_count();
-  op->grid = k.total_tiles < sms ? k.total_tiles : sms;
+  if (op->two_cta) {
+    const int clusters = k.total_pairs < sms / 2 ? k.total_pairs : sms / 2;
+    op->grid = 2 * clusters;
+  } else {
+    op->grid = k.total_tiles < sms ? k.total_tiles : sms;
+  }
   *out_op = op;
   return 0;
 }
 
 extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
   GLSDET_REQUIRE(op != nullptr, "conv_launch: null op");
-  conv_gemm_kernel<<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
+  if (op->two_cta) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(op->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = op->smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, op->kp);
+    if (e != cudaSuccess) {
+      set_error("cudaLaunchKernelEx(conv_gemm_kernel<2cta>) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    return count_launch("conv_gemm_kernel<2cta>");
+  }
+  conv_gemm_kernel<false><<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
   return count_launch("conv_gemm_kernel");
 }
 

@@ -258,3 +258,12 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
                            torch.sigmoid(rows[..., 4])], dim=-1)
     assert torch.allclose(got, ref, rtol=3e-3, atol=3e-3), (got - ref).abs().max()
     assert torch.isnan(out[:, :, 0]).all() and torch.isnan(out[:, :, 1 + n_pred:]).all()
+
+
+def test_two_cta_mode(native_lib, cuda_device, monkeypatch):
+    """cta_group::2 variant (CTA pairs, M = 256 per tcgen05.mma, operands split over two SMs): opt-in, same results."""
+    monkeypatch.setenv("GLSDET_CONV_2CTA", "1")
+    for case in (CASES[2], CASES[3], CASES[6], CASES[9], CASES[10]):
+        test_conv_matches_torch(case, native_lib, cuda_device)
+    test_fused_tower_pred_conv(128, 10, "sigmoid", native_lib, cuda_device)
+    test_bf16_residual_epilogues(native_lib, cuda_device)
