@@ -318,3 +318,35 @@ def test_model_vs_oracle_1024_and_batch_invariance(native_lib, cuda_device):
     det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65)
     torch.cuda.synchronize()
     assert (cnt.cpu() >= 0).all() and det.shape[0] == 4
+
+
+def test_config4_yolox_l_544x1024(native_lib, cuda_device):
+    """BASELINE config 4: P0 YOLOX-l, UAVDT-shaped 544x1024 input, nc=3, detections capped at 1000 per
+    image.  Odd level sizes (17x32 at stride 32) exercise ragged tiles; one image is checked against the oracle."""
+    from glsdet_b200.synthetic import synthetic_images
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    nc, in_h, in_w = 3, 544, 1024
+    sd = ref_path.synthetic_state_dict(nc, "l", seed=4, flavour="calibrated")
+    net = YoloBody(nc, "l")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    feats = ref_path.csp_darknet(sd, synthetic_images(2, in_h, in_w, seed=5))
+    assert [tuple(f.shape[1:]) for f in feats] == [(128, 136, 256), (256, 68, 128), (512, 34, 64), (1024, 17, 32)]
+    ref = ref_path.neck_head(sd, [f[:1] for f in feats])
+    emu = ref_path.neck_head_bf16(sd, [f[:1] for f in feats])
+    dfeats = [f.to(cuda_device) for f in feats]
+    logits = net.forward_features(dfeats)
+    for i in range(4):
+        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
+        assert_close_rel(logits[i][:1], ref[i], max(TOL, 1.15 * inherent), f"l-544 logits{i}", frac=2e-2)
+    det, cnt = net.detect_features(dfeats, conf_thres=0.01, nms_thres=0.65, max_det=1000)
+    torch.cuda.synchronize()
+    assert det.shape == (2, 1000, 7) and (cnt.cpu() <= 1000).all() and (cnt.cpu() > 0).all()
+    # top-1000 by score of the uncapped result (mmdet max_per_img semantics, base_dense_head.py:297)
+    full, full_cnt = net.detect_features(dfeats, conf_thres=0.01, nms_thres=0.65, max_det=None)
+    torch.cuda.synchronize()
+    for b in range(2):
+        n = int(cnt[b])
+        assert n == min(1000, int(full_cnt[b]))
+        assert torch.equal(det[b, :n], full[b, :n])
