@@ -10,9 +10,9 @@ from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libglsdet_b200.so"
 
-ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX = range(6)
+ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX, ACT_MMDET_BOX = range(7)
 OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
-NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU = range(4)
+NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
 SE_SLABS = 32
 
 ACT_BY_NAME = {"none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "lrelu": ACT_LRELU}
@@ -68,7 +68,13 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p)]),
     "glsdet_nms_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "glsdet_nms_launch_scaled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_nms_destroy": (None, [C.c_void_p]),
+    "glsdet_decode_mmdet": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms_workspace_bytes": (C.c_int64, [C.c_int32]),

@@ -334,6 +334,14 @@ __device__ __forceinline__ void store_pred(const ConvKParams& p, const float (&y
     o[2] = (expf(y[2]) * p.dec_stride) / p.dec_in_w;
     o[3] = (expf(y[3]) * p.dec_stride) / p.dec_in_h;
     o[4] = 1.0f / (1.0f + expf(-y[4]));
+  } else if (p.pred_act == GLSDET_ACT_MMDET_BOX) {
+    // mmdet yolox_head.py:298-301: xy = pred * stride + prior (prior = cell index * stride), wh = exp(pred) * stride;
+    // explicit roundings: no FMA contraction, like the PyTorch reference
+    o[0] = __fadd_rn(__fmul_rn(y[0], p.dec_stride), static_cast<float>(ox) * p.dec_stride);
+    o[1] = __fadd_rn(__fmul_rn(y[1], p.dec_stride), static_cast<float>(oy) * p.dec_stride);
+    o[2] = __fmul_rn(expf(y[2]), p.dec_stride);
+    o[3] = __fmul_rn(expf(y[3]), p.dec_stride);
+    o[4] = 1.0f / (1.0f + expf(-y[4]));
   } else if (p.pred_act == GLSDET_ACT_SIGMOID) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -885,7 +893,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   if (int rc = conv_geometry(d, &g)) return rc;
   GLSDET_REQUIRE(d->src0 && d->weight && d->out, "conv_create: null src0/weight/out pointer");
   GLSDET_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "conv_create: bad out_mode %d", d->out_mode);
-  GLSDET_REQUIRE(d->act >= 0 && d->act <= GLSDET_ACT_YOLOX_BOX, "conv_create: bad act %d", d->act);
+  GLSDET_REQUIRE(d->act >= 0 && d->act <= GLSDET_ACT_YOLOX_BOX, "conv_create: bad act %d", d->act);  // MMDET_BOX: fused preds only
   if (d->pred_weight != nullptr) {
     GLSDET_REQUIRE(d->pred_bias != nullptr && d->pred_channels >= 1 && d->pred_channels <= 16,
                    "conv_create: fused prediction conv needs a bias and 1..16 channels");
@@ -896,7 +904,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     GLSDET_REQUIRE(d->out_mode == GLSDET_OUT_NHWC_F32 || d->out_mode == GLSDET_OUT_NCHW_F32,
                    "conv_create: fused prediction conv writes fp32 rows or planes");
     GLSDET_REQUIRE(d->pred_act == GLSDET_ACT_NONE || d->pred_act == GLSDET_ACT_SIGMOID ||
-                   (d->pred_act == GLSDET_ACT_YOLOX_BOX && d->pred_channels == 5), "conv_create: bad pred_act");
+                   ((d->pred_act == GLSDET_ACT_YOLOX_BOX || d->pred_act == GLSDET_ACT_MMDET_BOX) && d->pred_channels == 5),
+                   "conv_create: bad pred_act");
     GLSDET_REQUIRE(d->pre_res == nullptr && d->post_res == nullptr, "conv_create: fused prediction conv takes no residual");
   }
 

@@ -207,6 +207,42 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeLevels lv, int B, int
   }
 }
 
+struct MmdetLevels {
+  const float* cls[8];
+  const float* box[8];
+  const float* obj[8];
+  long long cls_bs[8], box_bs[8], obj_bs[8];
+  int h[8], w[8], a_off[8];
+  float stride[8];
+  int num;
+};
+
+// yolox-ufp/mmdet/models/dense_heads/yolox_head.py:262-281,298-301 - one thread per (image, anchor)
+__global__ void __launch_bounds__(256) decode_mmdet_kernel(MmdetLevels lv, int B, int A, int nc, float* __restrict__ pred) {
+  const int64_t total = static_cast<int64_t>(B) * A;
+  const int nch = 5 + nc;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i % A);
+    const int b = static_cast<int>(i / A);
+    int l = 0;
+    while (l + 1 < lv.num && a >= lv.a_off[l + 1]) ++l;
+    const int64_t hw = static_cast<int64_t>(lv.h[l]) * lv.w[l];
+    const int cell = a - lv.a_off[l];
+    const int gy = cell / lv.w[l], gx = cell % lv.w[l];
+    const float st = lv.stride[l];
+    const float* bx = lv.box[l] + b * lv.box_bs[l] + cell;
+    float* o = pred + i * nch;
+    o[0] = __fadd_rn(__fmul_rn(__ldg(bx), st), static_cast<float>(gx) * st);
+    o[1] = __fadd_rn(__fmul_rn(__ldg(bx + hw), st), static_cast<float>(gy) * st);
+    o[2] = __fmul_rn(expf(__ldg(bx + 2 * hw)), st);
+    o[3] = __fmul_rn(expf(__ldg(bx + 3 * hw)), st);
+    o[4] = 1.0f / (1.0f + expf(-__ldg(lv.obj[l] + b * lv.obj_bs[l] + cell)));
+    const float* cl = lv.cls[l] + b * lv.cls_bs[l] + cell;
+    for (int c = 0; c < nc; ++c) o[5 + c] = 1.0f / (1.0f + expf(-__ldg(cl + c * hw)));
+  }
+}
+
 }  // namespace glsdet
 
 using namespace glsdet;
@@ -295,4 +331,32 @@ extern "C" int glsdet_decode_outputs(const float* const* levels, const int32_t* 
   decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       lv, batch, a, 5 + num_classes, static_cast<float>(in_h), static_cast<float>(in_w), pred);
   return count_launch("decode_kernel");
+}
+
+extern "C" int glsdet_decode_mmdet(const float* const* cls, const float* const* box, const float* const* obj,
+                                   const int64_t* cls_bs, const int64_t* box_bs, const int64_t* obj_bs,
+                                   const int32_t* heights, const int32_t* widths, const int32_t* strides,
+                                   int32_t num_levels, int32_t batch, int32_t num_classes, float* pred, void* stream) {
+  GLSDET_REQUIRE(cls && box && obj && cls_bs && box_bs && obj_bs && heights && widths && strides && pred,
+                 "decode_mmdet: null pointer");
+  GLSDET_REQUIRE(num_levels > 0 && num_levels <= 8, "decode_mmdet: 1..8 levels supported (got %d)", num_levels);
+  GLSDET_REQUIRE(batch > 0 && num_classes > 0, "decode_mmdet: bad sizes");
+  MmdetLevels lv;
+  int a = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    GLSDET_REQUIRE(cls[l] && box[l] && obj[l] && heights[l] > 0 && widths[l] > 0 && strides[l] > 0,
+                   "decode_mmdet: bad level %d", l);
+    lv.cls[l] = cls[l]; lv.box[l] = box[l]; lv.obj[l] = obj[l];
+    lv.cls_bs[l] = cls_bs[l]; lv.box_bs[l] = box_bs[l]; lv.obj_bs[l] = obj_bs[l];
+    lv.h[l] = heights[l]; lv.w[l] = widths[l]; lv.a_off[l] = a; lv.stride[l] = static_cast<float>(strides[l]);
+    a += heights[l] * widths[l];
+  }
+  lv.num = num_levels;
+  const int64_t total = static_cast<int64_t>(batch) * a;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
+  if (blocks > cap) blocks = cap;
+  decode_mmdet_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(lv, batch, a,
+                                                                                                  num_classes, pred);
+  return count_launch("decode_mmdet_kernel");
 }

@@ -60,6 +60,7 @@ struct Source {
   const float* boxes;
   const float* scores;
   const float* labels;
+  const float* box_div;  // optional [B][4] divisors of the corner boxes (mmdet rescale), pred mode only
 };
 
 struct Cand {
@@ -79,6 +80,13 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
     c.box.y = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
     c.box.z = __fadd_rn(cx, __fdiv_rn(w, 2.0f));
     c.box.w = __fadd_rn(cy, __fdiv_rn(h, 2.0f));
+    if (s.box_div != nullptr) {  // yolox_head.py:283-285: flatten_bboxes[..., :4] /= scale_factors
+      const float* dv = s.box_div + 4 * b;
+      c.box.x = __fdiv_rn(c.box.x, __ldg(dv));
+      c.box.y = __fdiv_rn(c.box.y, __ldg(dv + 1));
+      c.box.z = __fdiv_rn(c.box.z, __ldg(dv + 2));
+      c.box.w = __fdiv_rn(c.box.w, __ldg(dv + 3));
+    }
     c.obj = __ldg(r + 4);
     float best = __ldg(r + 5);
     int arg = 0;
@@ -131,7 +139,7 @@ __device__ __forceinline__ ImageMode image_mode(const Work& w, int b, int strate
   ImageMode m;
   const int n = w.cand_count[b];
   bool trick;
-  if (strategy == GLSDET_NMS_COORD_TRICK) trick = true;
+  if (strategy == GLSDET_NMS_COORD_TRICK || strategy == GLSDET_NMS_MMCV) trick = true;
   else if (strategy == GLSDET_NMS_PER_CLASS) trick = false;
   else if (strategy == GLSDET_NMS_AUTO_CUDA) trick = (4ll * n <= 100000);
   else trick = (4ll * n <= 4000);
@@ -142,6 +150,8 @@ __device__ __forceinline__ ImageMode image_mode(const Work& w, int b, int strate
   // class separation needs a positive gap after rounding: min >= -0.5 leaves 0.5, and offsets below 2^21 keep
   // every rounding error under 0.125
   m.per_class = !trick || (n > 0 && minc >= -0.5f && static_cast<float>(w.nc) * m.offset_scale < 2097152.0f);
+  // mmcv: from split_thr = 10000 boxes on, NMS runs class by class (on the shifted boxes)
+  if (strategy == GLSDET_NMS_MMCV && n >= 10000) m.per_class = true;
   return m;
 }
 
@@ -896,10 +906,16 @@ extern "C" int glsdet_nms_create(int32_t batch, int32_t anchors, int32_t num_cla
 
 extern "C" int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf_thres, float nms_thres,
                                  int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index, void* stream) {
+  return glsdet_nms_launch_scaled(op, pred, nullptr, conf_thres, nms_thres, strategy, det, det_count, keep_index, stream);
+}
+
+extern "C" int glsdet_nms_launch_scaled(glsdet_nms_t* op, const float* pred, const float* box_div, float conf_thres,
+                                        float nms_thres, int32_t strategy, float* det, int32_t* det_count,
+                                        int32_t* keep_index, void* stream) {
   GLSDET_REQUIRE(op && pred && det && det_count, "nms_launch: null pointer");
-  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_AUTO_CPU, "nms_launch: bad strategy %d", strategy);
+  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_MMCV, "nms_launch: bad strategy %d", strategy);
   Source s{};
-  s.pred = pred; s.A = op->A; s.nch = 5 + op->nc; s.nc = op->nc;
+  s.pred = pred; s.A = op->A; s.nch = 5 + op->nc; s.nc = op->nc; s.box_div = box_div;
   return run_pipeline<true>(s, op->w, conf_thres, nms_thres, strategy, op->max_det, det, det_count, keep_index,
                             static_cast<cudaStream_t>(stream));
 }
@@ -923,7 +939,7 @@ extern "C" int glsdet_batched_nms(const float* boxes, const float* scores, const
   GLSDET_REQUIRE(boxes && scores && labels && keep, "batched_nms: null pointer");
   GLSDET_REQUIRE(k < (1 << 24), "batched_nms: at most 2^24-1 boxes");
   GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "batched_nms: boxes must be 16-byte aligned");
-  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_AUTO_CPU, "batched_nms: bad strategy %d", strategy);
+  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_MMCV, "batched_nms: bad strategy %d", strategy);
   GLSDET_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                  "batched_nms: workspace must be 256-byte aligned");
   GLSDET_REQUIRE(workspace_bytes_given >= workspace_bytes(1, k, kMaxClasses), "batched_nms: workspace too small");

@@ -1,8 +1,14 @@
-"""Execution plan of the P0 hot path (models/ffa/yolox_ffa.py: PAFPN neck -> FFA -> decoupled head -> decode).
+"""Execution plans of the YOLOX-drone hot path: PAFPN neck -> (FFA) -> decoupled head -> decode.
+
+Two topologies share one builder:
+  * variant "ffa"   - models/ffa/yolox_ffa.py (GLSDet P0): four levels (strides 4..32), FFA fusion on (P3_out,
+                      P4_out), CSP block on dark2, level 0 uses tower index 3;
+  * variant "stock" - models/base/yolox.py and, with renamed keys, the mmdet pair YOLOXPAFPN + YOLOXHead
+                      (yolox-ufp/mmdet/models/necks/yolox_pafpn.py, dense_heads/yolox_head.py): three levels.
 
 A plan is built once per (weights, batch, input size): BatchNorm is folded into the conv weights, weights are
-re-laid out for the tcgen05 kernel, every intermediate lives in a preallocated NHWC bf16 buffer, and the
-forward pass becomes a flat list of native launches (no PyTorch math on the path):
+re-laid out for the tcgen05 kernel, every intermediate lives in a preallocated NHWC bf16 buffer, and the forward
+pass becomes a flat list of native launches (no PyTorch math on the path):
 
   * torch.cat is never materialised: producers write straight into channel windows of the concat buffer;
   * upsample + cat in front of a CSP block uses  conv1x1(cat(up(a), b)) = up(conv1x1_a(a)) + conv1x1_b(b):
@@ -11,7 +17,11 @@ forward pass becomes a flat list of native launches (no PyTorch math on the path
     the cls/reg towers; reg_preds/obj_preds are one N=5 GEMM;
   * PixelShuffle is a pure re-addressing because the producing conv's output channels are permuted at pack time;
   * the 1x1 prediction convs are fused into the epilogue of the second tower conv (its activated tile never leaves
-    the SM); in `decoded` mode that epilogue also applies sigmoid/exp/grid/stride and writes [B, A, 5+nc] rows.
+    the SM); in `decoded` mode that epilogue also applies sigmoid/exp/grid/stride and writes [B, A, 5+nc] rows
+    (yolox-drone: normalised centre boxes, utils_bbox.py:254-306; mmdet: pixel centre boxes, yolox_head.py:298-301).
+
+Op lists:  neck_ops -> stem_ops (everything that produces the per-level head inputs p_k) -> tower_ops (first tower
+conv) -> pred_raw_ops | pred_dec_ops (second tower conv + fused prediction conv).
 """
 from __future__ import annotations
 
@@ -20,30 +30,38 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import ConvOp, ScaleShuffleOp, SeGateOp, View, _Call, fold_bn, nchw_to_nhwc, nhwc_to_nchw
+from .ops import ConvOp, ScaleShuffleOp, SeGateOp, View, fold_bn, nchw_to_nhwc, nhwc_to_nchw
 
 BN_EPS = 1e-3
 
 
 class FFAPathPlan:
-    """Neck + head of YoloBody (yolox_ffa.py:264-284) for fixed weights / batch / input size."""
+    """Neck + head for fixed weights / batch / input size.  State-dict keys follow yolox-drone ("backbone.*" for the
+    neck, "head.*" for the head) after `neck_prefix` / `head_prefix` have been stripped."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], num_classes: int,
                  device=None, act: str = "silu", neck_prefix: str = "backbone.", head_prefix: str = "head.",
-                 parts: Sequence[str] = ("neck", "head")):
-        """state_dict uses the reference's keys; `neck_prefix`/`head_prefix` locate the YOLOPAFPN and YOLOXHead
-        entries (YoloBody: "backbone." / "head."; a stand-alone module: "").  `parts` selects which op lists are
-        built - a stand-alone neck or head module only owns its own weights."""
+                 parts: Sequence[str] = ("neck", "head"), variant: str = "ffa", decode: str = "drone"):
+        """`parts` selects which op lists are built - "neck", "stems" (everything producing the per-level head
+        inputs), "towers" (tower + prediction convs), "head" = stems + towers - because a stand-alone neck or head
+        module only owns its own weights; `decode` picks the decoded-row flavour: "drone" (normalised) or "mmdet"
+        (input pixels)."""
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
-        self.parts = tuple(parts)
+        parts = set(parts)
+        if "head" in parts:
+            parts |= {"stems", "towers"}
+        self.parts = parts
+        self.variant = variant
+        self.decode = decode
+        assert variant in ("ffa", "stock") and decode in ("drone", "mmdet")
         sd = {}
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked"):
                 continue
             if "neck" in self.parts and k.startswith(neck_prefix) and not k.startswith(neck_prefix + "backbone."):
                 sd["backbone." + k[len(neck_prefix):]] = v.detach().to(dev)   # CSPDarknet entries are skipped
-            elif "head" in self.parts and k.startswith(head_prefix):
+            elif ({"stems", "towers"} & self.parts) and k.startswith(head_prefix):
                 sd["head." + k[len(head_prefix):]] = v.detach().to(dev)
         self.sd = sd
         self.B = batch
@@ -52,34 +70,43 @@ class FFAPathPlan:
             raise ValueError("input size must be a multiple of 32 (yolox-drone/yolo.py:34-36)")
         self.nc = num_classes
         self.act = N.ACT_BY_NAME[act]
-        sd = self.sd
         if "neck" in self.parts:
             self.c0 = sd["backbone.reduce_conv1.conv.weight"].shape[0]   # int(256 * width)
             self.c1 = sd["backbone.lateral_conv0.conv.weight"].shape[0]  # int(512 * width)
             self.c2 = sd["backbone.lateral_conv0.conv.weight"].shape[1]  # int(1024 * width)
-        else:
+        elif "stems" in self.parts:
             self.c0, self.c1, self.c2 = (sd[f"head.stems.{i}.conv.weight"].shape[1] for i in range(3))
-        if "head" in self.parts:
-            self.cd2 = sd["head.csp.conv1.conv.weight"].shape[1]         # dark2 channels
+        else:   # towers only: the neck-side buffers are never touched, any consistent sizes do
+            self.c0 = sd["head.cls_convs.0.0.conv.weight"].shape[1]
+            self.c1, self.c2 = 2 * self.c0, 4 * self.c0
+        if "stems" in self.parts:
             self.hc = sd["head.stems.0.conv.weight"].shape[0]            # head width int(256 * width)
+        elif "towers" in self.parts:
+            self.hc = sd["head.cls_convs.0.0.conv.weight"].shape[1]
         else:
-            self.cd2, self.hc = self.c0 // 2, self.c0
+            self.hc = self.c0
+        self.cd2 = sd["head.csp.conv1.conv.weight"].shape[1] if (variant == "ffa" and "stems" in self.parts) else self.c0 // 2
         for c in (self.c0, self.c1, self.c2, self.cd2, self.hc):
             if c % 16:
                 raise NotImplementedError(f"channel count {c} is not a multiple of 16 (depthwise/nano is not supported)")
-        self.level_hw = [(self.in_h // s, self.in_w // s) for s in (4, 8, 16, 32)]
+        self.strides = (4, 8, 16, 32) if variant == "ffa" else (8, 16, 32)
+        self.stride_hw = {s: (self.in_h // s, self.in_w // s) for s in (4, 8, 16, 32)}
+        self.level_hw = [self.stride_hw[s] for s in self.strides]
         self.num_anchors = sum(h * w for h, w in self.level_hw)
         self._bufs: Dict[str, torch.Tensor] = {}
         self.neck_ops: List = []
-        self.head_ops: List = []
+        self.stem_ops: List = []
+        self.tower_ops: List = []
         self.pred_raw_ops: List = []
         self.pred_dec_ops: List = []
+        self.logits: List[torch.Tensor] = []
+        self.pred: Optional[torch.Tensor] = None
         self.flops = 0.0
         self._build()
 
     # ------------------------------------------------------------------ helpers
-    def _buf(self, name: str, level: int, channels: int, dtype=torch.bfloat16) -> torch.Tensor:
-        h, w = self.level_hw[level]
+    def _buf(self, name: str, stride: int, channels: int, dtype=torch.bfloat16) -> torch.Tensor:
+        h, w = self.stride_hw[stride]
         t = torch.empty((self.B, h, w, channels), dtype=dtype, device=self.device)
         self._bufs[name] = t
         return t
@@ -99,7 +126,7 @@ class FFAPathPlan:
         w, b = self._folded(p)
         return self._conv(ops, w, b, srcs, out, w.shape[-1], stride, act, **kw)
 
-    def _csp(self, ops, p: str, level: int, src: Optional[View], out, *, up_src: Optional[View] = None,
+    def _csp(self, ops, p: str, stride: int, src: Optional[View], out, *, up_src: Optional[View] = None,
              x_name: str, **out_kw):
         """CSPLayer (models/ffa/darknet.py:91-112), shortcut=False.  With `up_src` the block input is
         cat([upsample(up_src), src], 1) (yolox_ffa.py:207-211,224-228)."""
@@ -108,15 +135,15 @@ class FFAPathPlan:
         w2, b2 = self._folded(p + ".conv2")
         w12, b12 = torch.cat([w1, w2], 0), torch.cat([b1, b2], 0)
         hid = w1.shape[0]
-        X = self._buf(x_name, level, 2 * hid)
+        X = self._buf(x_name, stride, 2 * hid)
         if up_src is not None:
             ca = up_src.c
-            T = self._buf(x_name + "_T", level + 1, 2 * hid, torch.float32)
+            T = self._buf(x_name + "_T", stride * 2, 2 * hid, torch.float32)
             self._conv(ops, w12[:, :ca].contiguous(), None, [up_src], View(T), 1, act=N.ACT_NONE)
             self._conv(ops, w12[:, ca:].contiguous(), b12, [src], View(X), 1, pre_res=View(T), pre_shift=1)
         else:
             self._conv(ops, w12, b12, [src], View(X), 1)
-        bb = self._buf(x_name + "_b", level, hid)
+        bb = self._buf(x_name + "_b", stride, hid)
         j = 0
         while f"{p}.m.{j}.conv1.conv.weight" in sd:
             self._base_conv(ops, f"{p}.m.{j}.conv1", [View(X, 0, hid)], View(bb))
@@ -126,50 +153,60 @@ class FFAPathPlan:
 
     # ------------------------------------------------------------------ graph
     def _build(self):
-        c0, c1, c2, hc, nc = self.c0, self.c1, self.c2, self.hc, self.nc
-        nk, hd = self.neck_ops, self.head_ops
-        # inputs (NHWC bf16 copies of the backbone features)
-        d2 = self._buf("dark2", 0, self.cd2)
-        d3 = self._buf("dark3", 1, c0)
-        d4 = self._buf("dark4", 2, c1)
-        d5 = self._buf("dark5", 3, c2)
-        cat5 = self._buf("cat5", 3, 2 * c1)    # [bu_conv1(P4_out) | P5]
-        cat4 = self._buf("cat4", 2, 2 * c0)    # [bu_conv2(P3_out) | P4]
-        catf = self._buf("catf", 1, 2 * c0)    # [P3_out | FFA top after PixelShuffle]
-        p5up = self._buf("c3p4_out", 2, c1)
-        p4out = self._buf("P4_out", 2, c1)
-        p5out = self._buf("P5_out", 3, c2)
+        c0, c1, c2, hc = self.c0, self.c1, self.c2, self.hc
+        ffa = self.variant == "ffa"
+        d3 = self._buf("dark3", 8, c0)
+        d4 = self._buf("dark4", 16, c1)
+        d5 = self._buf("dark5", 32, c2)
+        cat5 = self._buf("cat5", 32, 2 * c1)              # [bu_conv1(P4_out) | P5]
+        cat4 = self._buf("cat4", 16, 2 * c0)              # [bu_conv2(P3_out) | P4]
+        catf = self._buf("catf", 8, 2 * c0 if ffa else c0)  # [P3_out | FFA top after PixelShuffle]
+        p5up = self._buf("c3p4_out", 16, c1)
+        p4out = self._buf("P4_out", 16, c1)
+        p5out = self._buf("P5_out", 32, c2)
         P5 = View(cat5, c1, c1)
         P4 = View(cat4, c0, c0)
         P3o = View(catf, 0, c0)
-
-        self.inputs = (d2, d3, d4, d5)
-        self.neck_out = (View(d2), P3o, View(p4out), View(p5out))
-        self.logits, self.pred = [], None
+        if ffa:
+            d2 = self._buf("dark2", 4, self.cd2)
+            self.inputs = (d2, d3, d4, d5)
+            self.neck_out = (View(d2), P3o, View(p4out), View(p5out))
+        else:
+            self.inputs = (d3, d4, d5)
+            self.neck_out = (P3o, View(p4out), View(p5out))
+        # per-level head inputs (what mmdet calls the neck outputs after out_convs)
+        self.p = [self._buf(f"p{k}", s, hc) for k, s in enumerate(self.strides)]
         if "neck" in self.parts:
-            self._build_neck(nk, d3, d4, d5, cat4, cat5, p5up, p4out, p5out, P5, P4, P3o)
-        if "head" in self.parts:
-            self._build_head(hd, d2, catf, p4out, p5out, P3o)
+            self._build_neck(self.neck_ops, d3, d4, d5, cat4, cat5, p5up, p4out, p5out, P5, P4, P3o)
+        if "stems" in self.parts:
+            if ffa:
+                self._build_ffa_stems(self.stem_ops, self._bufs["dark2"], catf, p4out, p5out, P3o)
+            else:
+                for k, src in enumerate((P3o, View(p4out), View(p5out))):
+                    self._base_conv(self.stem_ops, f"head.stems.{k}", [src], View(self.p[k]))
+        if "towers" in self.parts:
+            self._build_towers()
 
     def _build_neck(self, nk, d3, d4, d5, cat4, cat5, p5up, p4out, p5out, P5, P4, P3o):
         c0, c1 = self.c0, self.c1
-        # ---- neck: yolox_ffa.py:203-258
+        # yolox_ffa.py:203-258 == base/yolox.py YOLOPAFPN.forward == mmdet yolox_pafpn.py:117-150
         self._base_conv(nk, "backbone.lateral_conv0", [View(d5)], P5)
-        self._csp(nk, "backbone.C3_p4", 2, View(d4), View(p5up), up_src=P5, x_name="c3p4")
+        self._csp(nk, "backbone.C3_p4", 16, View(d4), View(p5up), up_src=P5, x_name="c3p4")
         self._base_conv(nk, "backbone.reduce_conv1", [View(p5up)], P4)
-        self._csp(nk, "backbone.C3_p3", 1, View(d3), P3o, up_src=P4, x_name="c3p3")
+        self._csp(nk, "backbone.C3_p3", 8, View(d3), P3o, up_src=P4, x_name="c3p3")
         self._base_conv(nk, "backbone.bu_conv2", [P3o], View(cat4, 0, c0), stride=2)
-        self._csp(nk, "backbone.C3_n3", 2, View(cat4), View(p4out), x_name="c3n3")
+        self._csp(nk, "backbone.C3_n3", 16, View(cat4), View(p4out), x_name="c3n3")
         self._base_conv(nk, "backbone.bu_conv1", [View(p4out)], View(cat5, 0, c1), stride=2)
-        self._csp(nk, "backbone.C3_n4", 3, View(cat5), View(p5out), x_name="c3n4")
+        self._csp(nk, "backbone.C3_n4", 32, View(cat5), View(p5out), x_name="c3n4")
 
-    def _build_head(self, hd, d2, catf, p4out, p5out, P3o):
-        c0, hc, nc = self.c0, self.hc, self.nc
+    def _build_ffa_stems(self, hd, d2, catf, p4out, p5out, P3o):
+        c0, hc = self.c0, self.hc
+        p = self.p
         # ---- FFA: ffa.py:74-85 (all ReLU)
         f = "head.ftt"
         relu = N.ACT_RELU
-        s_a = self._buf("ffa_a", 2, 4 * hc)
-        s_b = self._buf("ffa_b", 2, 4 * hc)
+        s_a = self._buf("ffa_a", 16, 4 * hc)
+        s_b = self._buf("ffa_b", 16, 4 * hc)
         self._base_conv(hd, f + ".scale", [View(p4out)], View(s_a), act=relu)
         self._base_conv(hd, f + ".create_content_extractor.0", [View(s_a)], View(s_b), act=relu)
         # PixelShuffle(2): out[c, 2y+i, 2x+j] = in[4c+2i+j, y, x]  ->  store channels in (i, j, c) order
@@ -179,33 +216,34 @@ class FFAPathPlan:
         se = SeGateOp(View(s_a), self.sd[f + ".se1.fc.0.weight"][:, perm], self.sd[f + ".se1.fc.2.weight"][perm])
         hd.append(se)
         hd.append(ScaleShuffleOp(View(s_a), se.gate, View(catf, c0, hc)))
-        tx = self._buf("ffa_text", 1, 2 * hc)
-        zz = self._buf("ffa_out", 1, hc)
+        tx = self._buf("ffa_text", 8, 2 * hc)
+        zz = self._buf("ffa_out", 8, hc)
         self._base_conv(hd, f + ".create_text_extractor.0", [View(catf)], View(tx), act=relu)
         self._base_conv(hd, f + ".conv3", [View(tx)], View(zz), act=relu, post_res=View(catf, c0, hc), post_shift=0)
-
         # ---- head inputs: yolox_ffa.py:66-73
-        p = [self._buf(f"p{k}", k, hc) for k in range(4)]
-        self._csp(hd, "head.csp", 0, View(d2), View(p[0]), x_name="hcsp", post_res=View(zz), post_shift=1)
+        self._csp(hd, "head.csp", 4, View(d2), View(p[0]), x_name="hcsp", post_res=View(zz), post_shift=1)
         self._base_conv(hd, "head.stems.0", [P3o], View(p[1]))
         self._base_conv(hd, "head.stems.1", [View(p4out)], View(p[2]))
         self._base_conv(hd, "head.stems.2", [View(p5out)], View(p[3]))
 
-        # ---- towers + predictions: yolox_ffa.py:76-117 (level 0 uses tower index 3)
+    def _build_towers(self):
+        """Towers + predictions: yolox_ffa.py:76-117 (level 0 uses tower index 3) / base/yolox.py / mmdet
+        yolox_head.py:184-195."""
+        hc, nc, sd = self.hc, self.nc, self.sd
         nch = 5 + nc
         self.logits = [torch.empty((self.B, nch, h, w), dtype=torch.float32, device=self.device)
                        for h, w in self.level_hw]
         self.pred = torch.empty((self.B, self.num_anchors, nch), dtype=torch.float32, device=self.device)
+        box_act = N.ACT_YOLOX_BOX if self.decode == "drone" else N.ACT_MMDET_BOX
         a_off = 0
         for k, (h, w) in enumerate(self.level_hw):
-            i = 3 if k == 0 else k - 1
+            i = k if self.variant == "stock" else (3 if k == 0 else k - 1)
             wc0, bc0 = self._folded(f"head.cls_convs.{i}.0")
             wr0, br0 = self._folded(f"head.reg_convs.{i}.0")
-            F = self._buf(f"tower{k}", k, 2 * hc)
-            self._conv(hd, torch.cat([wc0, wr0], 0), torch.cat([bc0, br0], 0), [View(p[k])], View(F), 3)
+            F = self._buf(f"tower{k}", self.strides[k], 2 * hc)
+            self._conv(self.tower_ops, torch.cat([wc0, wr0], 0), torch.cat([bc0, br0], 0), [View(self.p[k])], View(F), 3)
             wc1, bc1 = self._folded(f"head.cls_convs.{i}.1")
             wr1, br1 = self._folded(f"head.reg_convs.{i}.1")
-            sd = self.sd
             w_ro = torch.cat([sd[f"head.reg_preds.{i}.weight"], sd[f"head.obj_preds.{i}.weight"]], 0).float()
             b_ro = torch.cat([sd[f"head.reg_preds.{i}.bias"], sd[f"head.obj_preds.{i}.bias"]], 0).float()
             w_cl, b_cl = sd[f"head.cls_preds.{i}.weight"].float(), sd[f"head.cls_preds.{i}.bias"].float()
@@ -217,11 +255,12 @@ class FFAPathPlan:
                        pred_bias=b_ro, pred_act=N.ACT_NONE, **kw)
             self._conv(self.pred_raw_ops, wc1, bc1, cls_in, self.logits[k], 3, out_coff=5, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
-            # Decoded variant: utils_bbox.py:254-306 applied in the same epilogue, rows of [B, A, 5+nc].
+            # Decoded variant: the decode runs in the same epilogue, rows of [B, A, 5+nc].  Stride as the reference
+            # computes it: input_shape[0] / h (utils_bbox.py:285); equal to the integer mmdet stride.
             stride = float(self.in_h / h)
             kw = dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch)
             self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred, 3, out_coff=a_off * nch, pred_weight=w_ro,
-                       pred_bias=b_ro, pred_act=N.ACT_YOLOX_BOX, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
+                       pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
             self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred, 3, out_coff=a_off * nch + 5, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             a_off += h * w
@@ -231,33 +270,57 @@ class FFAPathPlan:
 
     # ------------------------------------------------------------------ execution
     def load_features(self, feats: Sequence[torch.Tensor], stream=None) -> None:
-        """(dark2, dark3, dark4, dark5) NCHW fp32 -> internal NHWC bf16 buffers."""
+        """Backbone features, NCHW fp32 -> internal NHWC bf16 buffers: (dark2, dark3, dark4, dark5) for the FFA
+        variant, (dark3, dark4, dark5) for the stock one."""
+        assert len(feats) == len(self.inputs), (len(feats), len(self.inputs))
         for src, dst in zip(feats, self.inputs):
             nchw_to_nhwc(src.contiguous(), View(dst), stream)
 
     def load_head_inputs(self, inputs: Sequence[torch.Tensor], stream=None) -> None:
-        """(feat0, P3_out, P4_out, P5_out) NCHW fp32 (the tuple YOLOPAFPN.forward returns) -> internal buffers."""
+        """The tuple YOLOPAFPN.forward returns (NCHW fp32) -> internal buffers."""
+        assert len(inputs) == len(self.neck_out)
         for src, dst in zip(inputs, self.neck_out):
             nchw_to_nhwc(src.contiguous(), dst, stream)
 
-    def run_neck(self, stream=None) -> None:
-        for op in self.neck_ops:
+    def load_tower_inputs(self, feats: Sequence[torch.Tensor], stream=None) -> None:
+        """Per-level head inputs p_k (what mmdet's neck returns after out_convs), NCHW fp32 -> internal buffers."""
+        assert len(feats) == len(self.p)
+        for src, dst in zip(feats, self.p):
+            nchw_to_nhwc(src.contiguous(), View(dst), stream)
+
+    @staticmethod
+    def _run(ops, stream):
+        for op in ops:
             op.launch(stream)
+
+    def run_neck(self, stream=None) -> None:
+        self._run(self.neck_ops, stream)
+
+    def run_stems(self, stream=None) -> None:
+        self._run(self.stem_ops, stream)
+
+    def run_towers(self, decoded: bool, stream=None) -> None:
+        self._run(self.tower_ops, stream)
+        self._run(self.pred_dec_ops if decoded else self.pred_raw_ops, stream)
 
     def run_head(self, decoded: bool, stream=None) -> None:
-        for op in self.head_ops:
-            op.launch(stream)
-        for op in (self.pred_dec_ops if decoded else self.pred_raw_ops):
-            op.launch(stream)
+        self.run_stems(stream)
+        self.run_towers(decoded, stream)
 
-    def neck_outputs_nchw(self, stream=None) -> List[torch.Tensor]:
+    def _to_nchw(self, views, stream=None) -> List[torch.Tensor]:
         outs = []
-        for v in self.neck_out:
+        for v in views:
             b, h, w = v.bhw
             t = torch.empty((b, v.c, h, w), dtype=torch.float32, device=self.device)
             nhwc_to_nchw(v, t, stream)
             outs.append(t)
         return outs
+
+    def neck_outputs_nchw(self, stream=None) -> List[torch.Tensor]:
+        return self._to_nchw(self.neck_out, stream)
+
+    def stem_outputs_nchw(self, stream=None) -> List[torch.Tensor]:
+        return self._to_nchw([View(t) for t in self.p], stream)
 
     def forward_logits(self, feats: Sequence[torch.Tensor], stream=None) -> List[torch.Tensor]:
         """Raw [B, 5+nc, h, w] logits per level, as YoloBody.forward returns them (yolox_ffa.py:116)."""
@@ -274,8 +337,9 @@ class FFAPathPlan:
         return self.pred
 
     def num_launches(self, decoded: bool) -> int:
-        se = sum(1 for op in self.head_ops if isinstance(op, SeGateOp))  # two kernels per SE gate
-        return 4 + len(self.neck_ops) + len(self.head_ops) + se + len(self.pred_dec_ops if decoded else self.pred_raw_ops)
+        se = sum(1 for op in self.stem_ops if isinstance(op, SeGateOp))  # two kernels per SE gate
+        return (len(self.inputs) + len(self.neck_ops) + len(self.stem_ops) + se + len(self.tower_ops) +
+                len(self.pred_dec_ops if decoded else self.pred_raw_ops))
 
     def buffer(self, name: str) -> torch.Tensor:
         return self._bufs[name]

@@ -12,7 +12,7 @@ import torch
 
 StateDict = Dict[str, torch.Tensor]
 
-def p0_state_dict_shapes(num_classes: int, phi: str) -> Dict[str, tuple]:
+def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Dict[str, tuple]:
     """Shapes of every state_dict entry of models/ffa/yolox_ffa.py YoloBody(num_classes, phi)."""
     depth = {"tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
     width = {"tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
@@ -58,6 +58,16 @@ def p0_state_dict_shapes(num_classes: int, phi: str) -> Dict[str, tuple]:
     csp("backbone.C3_n4", 2 * c1, c2, n)
 
     hc = int(256 * width)
+    if variant == "stock":   # models/base/yolox.py: three levels, stems on (P3_out, P4_out, P5_out), no FFA
+        for i, cin in enumerate((c0, c1, c2)):
+            bc(f"head.stems.{i}", cin, hc, 1)
+            for br in ("cls_convs", "reg_convs"):
+                bc(f"head.{br}.{i}.0", hc, hc, 3)
+                bc(f"head.{br}.{i}.1", hc, hc, 3)
+            for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
+                shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
+                shapes[f"head.{name}.{i}.bias"] = (co,)
+        return shapes
     csp("head.csp", int(0.5 * 256 * width), hc, round(3 * 0.75))
     f = "head.ftt"
     bc(f + ".scale", 2 * hc, 4 * hc, 1)
@@ -79,7 +89,8 @@ def p0_state_dict_shapes(num_classes: int, phi: str) -> Dict[str, tuple]:
     return shapes
 
 
-def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str = "kaiming") -> StateDict:
+def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str = "kaiming",
+                         variant: str = "ffa") -> StateDict:
     """Random-init weights for the P0 architecture.
 
     flavour "reference": what train.py does - default PyTorch init then weights_init(normal, 0.02)
@@ -102,10 +113,12 @@ def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str
         import numpy as np
         from pathlib import Path
 
-        f = Path(__file__).resolve().parent / "data" / f"calib_p0_{phi}_nc{num_classes}_seed{seed}.npz"
+        tag = "p0" if variant == "ffa" else variant
+        f = Path(__file__).resolve().parent / "data" / f"calib_{tag}_{phi}_nc{num_classes}_seed{seed}.npz"
         if not f.exists():
-            raise FileNotFoundError(f"{f} missing: run tools/calibrate_synthetic.py --phi {phi} --nc {num_classes} --seed {seed}")
-        sd = synthetic_state_dict(num_classes, phi, seed, "kaiming")
+            raise FileNotFoundError(f"{f} missing: run tools/calibrate_synthetic.py --phi {phi} --nc {num_classes} "
+                                    f"--seed {seed} --variant {variant}")
+        sd = synthetic_state_dict(num_classes, phi, seed, "kaiming", variant)
         with np.load(f) as z:
             for k in z.files:
                 assert tuple(z[k].shape) == tuple(sd[k].shape), k
@@ -114,7 +127,7 @@ def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str
     g = torch.Generator().manual_seed(seed)
     sd: StateDict = {}
     relu_layers = ("head.ftt.",)
-    for k, shp in p0_state_dict_shapes(num_classes, phi).items():
+    for k, shp in p0_state_dict_shapes(num_classes, phi, variant).items():
         part = k.rsplit(".", 1)[1]
         if k.endswith("num_batches_tracked"):
             sd[k] = torch.zeros((), dtype=torch.long)

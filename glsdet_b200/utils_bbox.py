@@ -18,7 +18,7 @@ import torch
 from . import _native as N
 
 STRATEGIES = {"trick": N.NMS_COORD_TRICK, "per_class": N.NMS_PER_CLASS, "auto_cuda": N.NMS_AUTO_CUDA,
-              "auto_cpu": N.NMS_AUTO_CPU}
+              "auto_cpu": N.NMS_AUTO_CPU, "mmcv": N.NMS_MMCV}
 
 
 def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:

@@ -175,6 +175,8 @@ class _PlanOwner(nn.Module):
     _neck_prefix = ""
     _head_prefix = ""
     _parts: Tuple[str, ...] = ()
+    _variant = "ffa"      # "ffa": models/ffa/yolox_ffa.py; "stock": models/base/yolox.py and the mmdet pair
+    _decode = "drone"     # decoded-row flavour of the fused path
 
     def __init__(self):
         super().__init__()
@@ -196,14 +198,19 @@ class _PlanOwner(nn.Module):
     def _num_classes(self) -> int:
         raise NotImplementedError
 
+    def _plan_state_dict(self):
+        """state_dict in yolox-drone naming (subclasses with other naming translate here)."""
+        return self.state_dict()
+
     def _plan(self, batch: int, input_hw: Sequence[int], device) -> FFAPathPlan:
         key = (batch, int(input_hw[0]), int(input_hw[1]), str(device))
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:
                 self._plans.clear()
-            plan = FFAPathPlan(self.state_dict(), batch, input_hw, self._num_classes(), device=device,
-                               neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts)
+            plan = FFAPathPlan(self._plan_state_dict(), batch, input_hw, self._num_classes(), device=device,
+                               neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts,
+                               variant=self._variant, decode=self._decode)
             self._plans[key] = plan
         return plan
 

@@ -36,7 +36,10 @@ enum {
   GLSDET_ACT_RELU = 2,
   GLSDET_ACT_LRELU = 3,      /* leaky relu 0.1               activation.py:13 */
   GLSDET_ACT_SIGMOID = 4,    /* cls logits -> probabilities  utils_bbox.py:270 */
-  GLSDET_ACT_YOLOX_BOX = 5   /* ch0..3 -> (cx,cy,w,h) normalised, ch4 -> sigmoid(obj); utils_bbox.py:270-305 */
+  GLSDET_ACT_YOLOX_BOX = 5,  /* ch0..3 -> (cx,cy,w,h) normalised, ch4 -> sigmoid(obj); utils_bbox.py:270-305 */
+  GLSDET_ACT_MMDET_BOX = 6   /* ch0..3 -> (cx,cy,w,h) in input pixels: xy*stride + prior, exp(wh)*stride; ch4 -> sigmoid
+                                (yolox-ufp/mmdet/models/dense_heads/yolox_head.py:298-301, priors of
+                                core/anchor/point_generator.py with offset 0) */
 };
 
 /* output layouts of the conv epilogue */
@@ -93,7 +96,7 @@ typedef struct glsdet_conv_desc {
    * Optional fused prediction conv (yolox_ffa.py:88,100,109: cls_preds / reg_preds / obj_preds applied to the
    * output of the second tower conv).  When pred_weight != NULL the activated tile of THIS conv is not stored;
    * instead  y[j] = pred_bias[j] + sum_k act(conv)[k] * pred_weight[j][k]  (j < pred_channels <= 16) is computed in
-   * the epilogue, `pred_act` (NONE, SIGMOID or YOLOX_BOX) is applied and y is written through out / out_mode /
+   * the epilogue, `pred_act` (NONE, SIGMOID, YOLOX_BOX or MMDET_BOX) is applied and y is written through out / out_mode /
    * out_ld / out_coff / out_batch_stride (NHWC_F32 rows or NCHW_F32 planes).  Requires out_channels <= 256.
    */
   const float* pred_weight;  /* fp32 [pred_channels][out_channels] */
@@ -147,6 +150,18 @@ int glsdet_decode_outputs(const float* const* levels, const int32_t* heights, co
                           float* pred, void* stream);
 
 /*
+ * mmdet flavour of the decode (yolox-ufp/mmdet/models/dense_heads/yolox_head.py:255-308 with the priors of
+ * core/anchor/point_generator.py:148-175, offset 0): three lists of raw NCHW fp32 maps (cls [B,nc,h,w],
+ * bbox [B,4,h,w], objectness [B,1,h,w]; pass the same base pointers with channel strides for views) ->
+ * pred fp32 [B, A, 5+nc] rows (cx, cy, w, h in input pixels, sigmoid(obj), sigmoid(cls)).
+ * cls_bs / box_bs / obj_bs: elements between images of each list entry (lets callers pass channel slices).
+ */
+int glsdet_decode_mmdet(const float* const* cls, const float* const* box, const float* const* obj,
+                        const int64_t* cls_bs, const int64_t* box_bs, const int64_t* obj_bs, const int32_t* heights,
+                        const int32_t* widths, const int32_t* strides, int32_t num_levels, int32_t batch,
+                        int32_t num_classes, float* pred, void* stream);
+
+/*
  * Post-processing: non_max_suppression (utils_bbox.py:375-484) without the per-image Python loop or host
  * synchronisation.  Works on decoded predictions pred[B][A][5+nc] (cx,cy,w,h,obj,cls...).
  *
@@ -166,7 +181,11 @@ enum {
   GLSDET_NMS_COORD_TRICK = 0,
   GLSDET_NMS_PER_CLASS = 1,
   GLSDET_NMS_AUTO_CUDA = 2,
-  GLSDET_NMS_AUTO_CPU = 3
+  GLSDET_NMS_AUTO_CPU = 3,
+  /* mmcv.ops.nms.batched_nms (mmcv-full 1.3.17 .. 1.5.0, the pin of yolox-ufp/requirements/mminstall.txt; call sites
+   * dense_heads/yolox_head.py:321, base_dense_head.py:295): boxes are always shifted by label * (max + 1); one NMS
+   * over all boxes when K < split_thr = 10000, otherwise one NMS per class on the shifted boxes */
+  GLSDET_NMS_MMCV = 4
 };
 typedef struct glsdet_nms glsdet_nms_t;
 /* bytes of device workspace needed for the given problem size */
@@ -175,6 +194,12 @@ int glsdet_nms_create(int32_t batch, int32_t anchors, int32_t num_classes, int32
                       int64_t workspace_bytes, glsdet_nms_t** op);
 int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf_thres, float nms_thres, int32_t strategy,
                       float* det, int32_t* det_count, int32_t* keep_index, void* stream);
+/* Same with per-image divisors box_div[B][4] applied to the corner boxes (x1/d0, y1/d1, x2/d2, y2/d3) before
+ * NMS and in the output rows: mmdet's `rescale` (dense_heads/yolox_head.py:283-285 divides the decoded corners by
+ * scale_factor before _bboxes_nms).  box_div == NULL is glsdet_nms_launch. */
+int glsdet_nms_launch_scaled(glsdet_nms_t* op, const float* pred, const float* box_div, float conf_thres,
+                             float nms_thres, int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index,
+                             void* stream);
 void glsdet_nms_destroy(glsdet_nms_t* op);
 
 /* class-aware NMS on caller-supplied boxes (the exact contract of torchvision batched_nms on one image):

@@ -142,6 +142,34 @@ def yolox_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -
     return outs
 
 
+def stock_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -> List[torch.Tensor]:
+    """models/base/yolox.py YOLOXHead.forward: stem -> two 3x3 towers -> 1x1 preds per level, cat([reg, obj, cls])."""
+    outs = []
+    for k, x in enumerate(inputs):
+        x = base_conv(sd, f"{p}.stems.{k}", x)
+        cf = base_conv(sd, f"{p}.cls_convs.{k}.1", base_conv(sd, f"{p}.cls_convs.{k}.0", x))
+        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"]), sd[f"{p}.cls_preds.{k}.bias"])
+        rf = base_conv(sd, f"{p}.reg_convs.{k}.1", base_conv(sd, f"{p}.reg_convs.{k}.0", x))
+        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"]), sd[f"{p}.reg_preds.{k}.bias"])
+        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"]), sd[f"{p}.obj_preds.{k}.bias"])
+        outs.append(torch.cat([reg_out, obj_out, cls_out], 1))
+    return outs
+
+
+def stock_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+    """models/base/yolox.py YoloBody.forward minus CSPDarknet: feats = (dark3, dark4, dark5).  The neck is the same
+    PAFPN as yolox_ffa.py (the FFA variant only adds dark2 as a pass-through fourth input)."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = bf16
+    try:
+        with torch.no_grad():
+            f = [_q(t) for t in feats]
+            neck = pafpn_neck(sd, [None] + list(f))
+            return stock_head(sd, neck[1:])
+    finally:
+        _EMULATE_BF16 = False
+
+
 def neck_head(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     """YoloBody.forward minus the CSPDarknet call (yolox_ffa.py:275-284)."""
     with torch.no_grad():

@@ -88,6 +88,45 @@ def run_model_case(yf, ub, name, phi, nc, flavour, seed, batch, in_h, in_w, conf
     return meta, key_shapes
 
 
+def run_stock_case(ub, name, phi, nc, seed, batch, in_h, in_w, conf, nms_thr):
+    """Stock 3-level YOLOX (models/base/yolox.py, imports as shipped): the math the mmdet YOLOXPAFPN / YOLOXHead
+    pair also computes (key map in SURVEY.md section 8c)."""
+    import models.base.yolox as yb
+    from oracle import ref_path
+
+    sd = ref_path.synthetic_state_dict(nc, phi, seed=seed, flavour="calibrated", variant="stock")
+    net = yb.YoloBody(nc, phi).eval()
+    net.load_state_dict(sd, strict=True)
+    key_shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    width = {"tiny": 0.375, "s": 0.5, "m": 0.75, "l": 1.0}[phi]
+    chans = [int(c * width) for c in (256, 512, 1024)]
+    g = torch.Generator().manual_seed(seed + 100)
+    feats = [torch.randn(batch, c, in_h // s, in_w // s, generator=g) for c, s in zip(chans, (8, 16, 32))]
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return dict(zip(("dark3", "dark4", "dark5"), feats))
+
+    net.backbone.backbone = Stub()
+    with torch.no_grad():
+        neck_out = net.backbone(torch.zeros(batch, 3, in_h, in_w))
+        logits = net.head(neck_out)
+        pred = ub.decode_outputs([o.clone() for o in logits], [in_h, in_w]).contiguous()
+        results = ub.non_max_suppression(pred.clone(), nc, [in_h, in_w], np.array([in_h, in_w]), False,
+                                         conf_thres=conf, nms_thres=nms_thr)
+    out = {f"feat{i}": f.numpy() for i, f in enumerate(feats)}
+    out.update({f"neck{i}": t.numpy() for i, t in enumerate(neck_out)})
+    out.update({f"logits{i}": t.numpy() for i, t in enumerate(logits)})
+    out["pred"] = pred.numpy()
+    for i, r in enumerate(results):
+        out[f"nms{i}"] = r if r is not None else np.zeros((0, 7), np.float32)
+    meta = dict(name=name, phi=phi, nc=nc, seed=seed, batch=batch, in_h=in_h, in_w=in_w, conf=conf, nms_thr=nms_thr,
+                weight_checksum=weight_checksum(sd), n_keys=len(sd), kept=[int(len(out[f"nms{i}"])) for i in range(batch)])
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, meta["kept"], meta["weight_checksum"])
+    return meta, key_shapes
+
+
 def clustered_boxes(rng, k, nc, normalised=True, ties=False):
     g = max(4, k // 12)
     cen = rng.uniform(0.05, 0.95, (g, 2))
@@ -168,6 +207,9 @@ def main():
     m2, _ = run_model_case(yf, ub, "p0_s_refinit", "s", 10, "reference", 2, 1, 64, 64, 0.01, 0.65)
     m3, keys_t = run_model_case(yf, ub, "p0_tiny_calibrated", "tiny", 3, "calibrated", 3, 1, 96, 64, 0.01, 0.65)
     metas["models"] = [m1, m2, m3]
+    ms, keys_stock = run_stock_case(ub, "stock_s_calibrated", "s", 10, 21, 2, 96, 64, 0.01, 0.65)
+    metas["stock"] = ms
+    (HERE / "state_dict_keys_stock_s.json").write_text(json.dumps(keys_stock, indent=0))
     metas["nms"] = nms_cases()
     metas["postproc"] = postproc_case(ub)
     metas["torch"] = torch.__version__

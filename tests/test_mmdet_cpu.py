@@ -1,0 +1,88 @@
+"""CPU tests of the mmdet registry face: oracle restatement vs the pinned stock-YOLOX golden, key contract, registry."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mmdet_ref, ref_path
+
+GOLD = Path(__file__).resolve().parent / "golden"
+META = json.loads((GOLD / "meta.json").read_text())["stock"]
+
+
+def _stock_sd():
+    return ref_path.synthetic_state_dict(META["nc"], META["phi"], seed=META["seed"], flavour="calibrated", variant="stock")
+
+
+def test_stock_oracle_matches_reference_golden():
+    z = np.load(GOLD / "stock_s_calibrated.npz")
+    sd = _stock_sd()
+    feats = [torch.from_numpy(z[f"feat{i}"]) for i in range(3)]
+    out = ref_path.stock_neck_head(sd, feats)
+    for i in range(3):
+        np.testing.assert_allclose(out[i].numpy(), z[f"logits{i}"], rtol=1e-4, atol=2e-5)
+    pred = ref_path.decode_outputs([torch.from_numpy(z[f"logits{i}"]) for i in range(3)], [META["in_h"], META["in_w"]])
+    np.testing.assert_allclose(pred.numpy(), z["pred"], rtol=1e-6, atol=1e-7)
+
+
+def test_mmdet_oracle_reproduces_stock_reference_outputs():
+    """SURVEY 8c cross-check: yolox-drone base/yolox.py weights renamed onto the restated mmdet modules give the
+    outputs of the real reference (golden)."""
+    z = np.load(GOLD / "stock_s_calibrated.npz")
+    neck_sd, head_sd = mmdet_ref.drone_to_mmdet_keys(_stock_sd())
+    feats = [torch.from_numpy(z[f"feat{i}"]) for i in range(3)]
+    p = mmdet_ref.yolox_pafpn(neck_sd, feats)
+    cls, box, obj = mmdet_ref.yolox_head_forward(head_sd, p)
+    for i in range(3):
+        got = torch.cat([box[i], obj[i], cls[i]], 1).numpy()
+        np.testing.assert_allclose(got, z[f"logits{i}"], rtol=1e-4, atol=2e-5)
+
+
+def test_mmdet_get_bboxes_oracle_consistent_with_drone_postproc():
+    """The mmdet decode (pixels) equals the yolox-drone decode (normalised) times the input size, and its NMS keeps
+    the same anchors when both use the coordinate trick."""
+    z = np.load(GOLD / "stock_s_calibrated.npz")
+    logits = [torch.from_numpy(z[f"logits{i}"]) for i in range(3)]
+    cls, box, obj = [l[:, 5:] for l in logits], [l[:, :4] for l in logits], [l[:, 4:5] for l in logits]
+    res = mmdet_ref.get_bboxes(cls, box, obj, [8, 16, 32], META["conf"], META["nms_thr"])
+    pred = torch.from_numpy(z["pred"])
+    for b in range(META["batch"]):
+        dets, labels = res[b]
+        assert dets.shape[1] == 5 and len(dets) == len(labels) > 0
+        assert (np.diff(dets[:, 4]) <= 0).all()
+        drone = ref_path.non_max_suppression(pred[b:b + 1], META["nc"], [META["in_h"], META["in_w"]], None, False,
+                                             META["conf"], META["nms_thr"], strategy="trick", correct_boxes=False)[0]
+        # same number of survivors up to boxes whose IoU sits within rounding of the threshold
+        assert abs(len(drone) - len(dets)) <= max(2, len(dets) // 50)
+        k = min(len(drone), len(dets), 5)
+        scale = np.array([META["in_w"], META["in_h"], META["in_w"], META["in_h"]], np.float32)
+        np.testing.assert_allclose(dets[:k, :4], drone[:k, :4] * scale, rtol=1e-4, atol=1e-3)
+
+
+def test_registry_and_state_dict_keys():
+    from glsdet_b200.mmdet_face import HEADS, NECKS, YOLOXHead, YOLOXPAFPN
+
+    neck = NECKS.build(dict(type="YOLOXPAFPN", in_channels=[128, 256, 512], out_channels=128, num_csp_blocks=1))
+    head = HEADS.build(dict(type="YOLOXHead", num_classes=80, in_channels=128, feat_channels=128,
+                            test_cfg=dict(score_thr=0.01, nms=dict(type="nms", iou_threshold=0.65))))
+    assert isinstance(neck, YOLOXPAFPN) and isinstance(head, YOLOXHead)
+    nk, hk = mmdet_ref.expected_keys([128, 256, 512], 128, 1, 80, 128)
+    assert list(neck.state_dict().keys()) == nk
+    assert list(head.state_dict().keys()) == hk
+    assert head.test_cfg.score_thr == 0.01 and head.test_cfg.nms.iou_threshold == 0.65
+    with pytest.raises(KeyError):
+        NECKS.build(dict(type="NoSuchNeck"))
+    # weights of the stock yolox-drone model load strictly after renaming (shapes agree)
+    nsd, hsd = mmdet_ref.drone_to_mmdet_keys(_stock_sd())
+    neck10 = YOLOXPAFPN([128, 256, 512], 128, num_csp_blocks=1)
+    head10 = YOLOXHead(10, 128, feat_channels=128)
+    neck10.load_state_dict(nsd, strict=True)
+    head10.load_state_dict(hsd, strict=True)
+    # and the module's own key translation inverts the oracle's
+    back = {**neck10._plan_state_dict(), **head10._plan_state_dict()}
+    want = {k: v for k, v in _stock_sd().items() if not k.startswith("backbone.backbone.")}
+    assert set(back) == set(want)
+    for k in want:
+        assert torch.equal(back[k], want[k]), k

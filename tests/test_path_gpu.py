@@ -18,25 +18,12 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+from _helpers import TOL, _clustered, assert_close_rel
 from oracle import nms_oracle, ref_path
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
 META = json.loads((GOLD / "meta.json").read_text())
-TOL = 2e-2
-
-
-def assert_close_rel(got: torch.Tensor, ref: torch.Tensor, tol=TOL, what="", max_factor=4.0, frac=1e-2):
-    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
-    assert got.shape == ref.shape, (what, got.shape, ref.shape)
-    assert torch.isfinite(got).all(), f"{what}: non-finite values"
-    d = (got - ref).abs()
-    scale = ref.abs().max().item()
-    rel_l2 = (got - ref).norm().item() / max(ref.norm().item(), 1e-30)
-    assert rel_l2 <= tol, f"{what}: relative l2 error {rel_l2:.4g} > {tol}"
-    frac_bad = (d > tol * scale).float().mean().item()
-    assert frac_bad <= frac, f"{what}: {frac_bad:.2%} of the elements differ by more than {tol} * max|ref|"
-    assert d.max().item() <= max_factor * tol * scale, f"{what}: max abs diff {d.max().item():.4g} vs scale {scale:.4g}"
 
 
 # ---------------------------------------------------------------------------------------------- small kernels
@@ -117,18 +104,6 @@ def test_batched_nms_bit_exact_vs_torchvision_golden(case, native_lib, cuda_devi
         got = batched_nms(b, s, l, thr, "auto_cpu").cpu().numpy()
         if not case["ties"]:
             np.testing.assert_array_equal(got, z[f"{n}_keep_auto_{thr}"])
-
-
-def _clustered(rng, k, nc, spread=0.004, lo=0.05):
-    g = max(4, k // 12)
-    cen = rng.uniform(lo, 0.95, (g, 2))
-    which = rng.integers(0, g, k)
-    c = cen[which] + rng.normal(0, spread, (k, 2))
-    wh = np.exp(rng.normal(-3.2, 0.4, (g, 2)))[which] * np.exp(rng.normal(0, 0.15, (k, 2)))
-    boxes = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
-    scores = ((rng.permutation(k) + 1) / (k + 1.0)).astype(np.float32)
-    labels = rng.integers(0, nc, k).astype(np.float32)
-    return boxes, scores, labels
 
 
 @pytest.mark.parametrize("k,nc", [(2, 1), (63, 3), (64, 3), (65, 10), (4095, 10), (4096, 10), (4097, 10), (9000, 10),

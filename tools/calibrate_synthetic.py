@@ -31,13 +31,14 @@ def main():
     ap.add_argument("--phi", default="s")
     ap.add_argument("--nc", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--variant", default="ffa", choices=["ffa", "stock"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--obj-std", type=float, default=2.0)
     ap.add_argument("--target-pass", type=float, default=0.04, help="fraction of anchors with obj*cls >= 0.01")
     ap.add_argument("--cls-std", type=float, default=0.5)
     args = ap.parse_args()
     torch.set_num_threads(8)
-    sd = synthetic_state_dict(args.nc, args.phi, seed=args.seed, flavour="kaiming")
+    sd = synthetic_state_dict(args.nc, args.phi, seed=args.seed, flavour="kaiming", variant=args.variant)
     changed = {}
     orig = ref_path.base_conv
 
@@ -56,11 +57,14 @@ def main():
         feats = ref_path.csp_darknet(sd, x)
         neck = ref_path.pafpn_neck(sd, feats)
         # towers: rescale the prediction convs on the calibrated tower outputs
-        zz = ref_path.ffa(sd, "head.ftt", neck[1], neck[2])
-        proc = [ref_path.csp_layer(sd, "head.csp", neck[0]) + F.interpolate(zz, scale_factor=2, mode="nearest")]
-        proc += [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
+        if args.variant == "stock":
+            proc = [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
+        else:
+            zz = ref_path.ffa(sd, "head.ftt", neck[1], neck[2])
+            proc = [ref_path.csp_layer(sd, "head.csp", neck[0]) + F.interpolate(zz, scale_factor=2, mode="nearest")]
+            proc += [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
         for k, xk in enumerate(proc):
-            i = 3 if k == 0 else k - 1
+            i = k if args.variant == "stock" else (3 if k == 0 else k - 1)
             cf = ref_path.base_conv(sd, f"head.cls_convs.{i}.1", ref_path.base_conv(sd, f"head.cls_convs.{i}.0", xk))
             rf = ref_path.base_conv(sd, f"head.reg_convs.{i}.1", ref_path.base_conv(sd, f"head.reg_convs.{i}.0", xk))
             for name, feat, target in (("cls_preds", cf, args.cls_std), ("obj_preds", rf, args.obj_std), ("reg_preds", rf, 0.15)):
@@ -71,8 +75,9 @@ def main():
                 changed[key] = sd[key]
     ref_path.base_conv = orig
     # shift the objectness biases so that the wanted fraction of anchors passes conf 0.01 (bisection on one offset)
+    head_fn = (lambda n: ref_path.stock_head(sd, n[1:])) if args.variant == "stock" else (lambda n: ref_path.yolox_head(sd, n))
     with torch.no_grad():
-        lg = ref_path.yolox_head(sd, neck)
+        lg = head_fn(neck)
     obj = torch.cat([l[:, 4].flatten(1) for l in lg], 1)
     cls = torch.cat([torch.sigmoid(l[:, 5:]).max(1)[0].flatten(1) for l in lg], 1)
     lo, hi = -20.0, 20.0
@@ -80,15 +85,16 @@ def main():
         mid = 0.5 * (lo + hi)
         frac = float(((torch.sigmoid(obj + mid) * cls) >= 0.01).float().mean())
         lo, hi = (mid, hi) if frac < args.target_pass else (lo, mid)
-    for i in range(4):
+    for i in range(len(lg)):
         key = f"head.obj_preds.{i}.bias"
         sd[key] = sd[key] + 0.5 * (lo + hi)
         changed[key] = sd[key]
-    out = ROOT / "glsdet_b200" / "data" / f"calib_p0_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
+    tag = "p0" if args.variant == "ffa" else args.variant
+    out = ROOT / "glsdet_b200" / "data" / f"calib_{tag}_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
     np.savez_compressed(out, **{k: v.numpy().astype(np.float32) for k, v in changed.items()})
     # report
     with torch.no_grad():
-        lg = ref_path.yolox_head(sd, neck)
+        lg = head_fn(neck)
         pred = ref_path.decode_outputs(lg, [args.size, args.size])
     sc = pred[:, :, 4] * pred[:, :, 5:].max(2)[0]
     print(out.name, f"{out.stat().st_size/1e3:.0f} kB", "anchors", pred.shape[1], "cand@0.01", (sc >= 0.01).sum(1).tolist(),
