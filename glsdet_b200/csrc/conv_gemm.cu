@@ -60,6 +60,11 @@ struct alignas(64) ConvKParams {
   int32_t a_steps;           // A steps per tile
   int32_t a_bytes;           // bytes of one A stage
   int32_t tmem_cols;
+  int32_t mt;                // M tiles (vertically adjacent, one A box) per work item: every B stage feeds mt MMAs
+  int32_t nacc;              // accumulator ring depth in work items (2, or 1 when 2 * mt * block_n > 512 columns)
+  int32_t bres;              // all weight chunks stay resident in shared memory (loaded once per CTA)
+  int32_t b_chunks;          // number of 64-wide K chunks of the weight matrix
+  int32_t pdl;               // launched with programmatic stream serialisation
   const float* bias;
   int32_t act;
   const float* pre_res;
@@ -77,7 +82,10 @@ struct alignas(64) ConvKParams {
 };
 
 enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
-       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8 };
+       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8, EPI_TOWER_PRED_MMA = 9 };
+
+constexpr int kStageTileBytes = kBlockM * kRowBytes;   // one 128-row x 64-channel K-major SW128 operand tile
+constexpr int kPredTileBytes = 16 * kRowBytes;         // prediction weights: 16 rows x 64 channels
 
 struct TileCoord {
   int b, y0, x0, n0;
@@ -92,7 +100,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int tile)
   int ty = m % p.tiles_y;
   t.b = m / p.tiles_y;
   t.x0 = tx << p.tile_w_log2;
-  t.y0 = ty * p.tile_h;
+  t.y0 = ty * p.tile_h * p.mt;
   t.n0 = nb * p.block_n;
   return t;
 }
@@ -257,7 +265,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   }
   if (silu) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+    for (int j = 0; j < 16; j += 4) silu4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -382,18 +390,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   // 2-CTA mode: every CTA stages half of the B rows, and one stage always carries all nsub taps (single ring)
   const int b_tap_bytes = (k2 ? (p.block_n >> 1) : p.block_n) * kRowBytes;
   const int b_bytes = (k2 ? p.nsub : p.bgroup) * b_tap_bytes;
+  const int b_region = p.bres ? p.b_chunks * b_tap_bytes : p.sb * b_bytes;
+  const bool pred_mma = (p.epi == EPI_TOWER_PRED_MMA);
+  const int k_tiles = p.block_n >> 6;   // 64-channel operand tiles of the activated tile (prediction MMA)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.sa * p.a_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + p.sb * b_bytes);
+  uint8_t* smem_stage = smem_b + b_region;                                          // [k_tiles][128 rows][128 B]
+  uint8_t* smem_pw = smem_stage + (pred_mma ? k_tiles * kStageTileBytes : 0);      // [k_tiles][16 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pw + (pred_mma ? k_tiles * kPredTileBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kMaxStages;
   uint64_t* b_full = bars + 2 * kMaxStages;
   uint64_t* b_empty = bars + 3 * kMaxStages;
   uint64_t* tfull_bar = bars + 4 * kMaxStages;
   uint64_t* tempty_bar = bars + 4 * kMaxStages + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 4);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 6);  // [n_blocks * block_n], zero padded
-  float* s_pw = s_bias + p.n_blocks * p.block_n;                         // fused prediction weights [N][16]
+  uint64_t* bres_full = bars + 4 * kMaxStages + 4;
+  uint64_t* pred_bar = bars + 4 * kMaxStages + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 6);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);  // [n_blocks * block_n], zero padded
+  float* s_pw = s_bias + p.n_blocks * p.block_n;                         // FMA prediction path: weights [N][16]
   float* s_red = s_pw + p.block_n * 16;                                  // [2][128][16] partial sums of the upper column half
 
   const int warp = threadIdx.x >> 5;
@@ -423,14 +438,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], k2 ? 2 * kEpiWarps : kEpiWarps);  // 2-CTA: the peer's epilogue warps arrive too
     }
+    mbar_init(bres_full, 1);
+    mbar_init(pred_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
     if (k2) { tmem2_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols)); tmem2_relinquish(); }
     else { tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols)); tmem_relinquish(); }
   }
+  // Programmatic dependent launch: everything above overlaps the tail of the previous kernel of the stream; global
+  // memory (inputs, and outputs a predecessor may still read) is only touched after this point.
+  if (p.pdl) {
+    griddep_wait();
+    griddep_launch_dependents();
+  }
   for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
     s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
+  if (pred_mma) {
+    // prediction weights fp32 [pred_n][N] -> bf16 B operand (16 rows, K-major, 128-byte swizzle) per 64-channel tile
+    for (int i = threadIdx.x; i < 16 * p.block_n; i += kThreads) {
+      const int n = i / p.block_n, k = i - n * p.block_n;
+      const float v = (n < p.pred_n && k < p.N) ? __ldg(p.pred_w + static_cast<int64_t>(n) * p.N + k) : 0.0f;
+      const int kc = k >> 6, kk = k & 63;
+      const int off = kc * kPredTileBytes + (n >> 3) * 1024 + (n & 7) * kRowBytes + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(smem_pw + off) = __float2bfloat16_rn(v);
+    }
+    fence_proxy_async_smem();
+  }
   if (p.epi == EPI_TOWER_PRED) {
     for (int i = threadIdx.x; i < p.block_n * 16; i += kThreads) {
       const int kk = i >> 4, j = i & 15;
@@ -534,6 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       if (++sa == p.sa) { sa = 0; pha ^= 1u; }
     };
     auto load_b = [&](int kchunk, int n0) {
+      if (p.bres) return;
       mbar_wait(&b_empty[sb], phb ^ 1u);
       mbar_arrive_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
       tma_load_2d(smem_b + sb * b_bytes, &p.tmB, &b_full[sb], kchunk * kChunkK, n0);
@@ -545,6 +580,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tma_load_3d(smem_b + sb * b_bytes, &p.tmB3[src], &b_full[sb], kchunk * kChunkK, n0, 0);
       if (++sb == p.sb) { sb = 0; phb ^= 1u; }
     };
+    if (p.bres && work0 < total_work) {
+      // resident weights (one N block): every K chunk once, at its K position
+      mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(p.b_chunks * b_tap_bytes));
+      for (int c = 0; c < p.b_chunks; ++c)
+        tma_load_2d(smem_b + c * b_tap_bytes, &p.tmB, bres_full, c * kChunkK, 0);
+    }
     for (int tile = work0; tile < total_work; tile += work_stride) {
       const TileCoord t = decode_tile(p, tile);
       if (p.stride == 1) {
@@ -555,7 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (p.nsub == 3) {
             for (int kx = 0; kx < 3; ++kx) {
               for (int ch = 0; ch < nch; ++ch) {
-                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, t.b);  // tile_h + 2 rows
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, t.b);  // mt * tile_h + 2 rows
+                if (p.bres) continue;
                 if (p.bgroup == 3) load_b3(src, kbase + kx * nch + ch, t.n0);         // ky = 0,1,2 in one box
                 else for (int ky = 0; ky < 3; ++ky) load_b(kbase + (ky * 3 + kx) * nch + ch, t.n0);
               }
@@ -590,33 +632,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
     const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
     const int a_sub_bytes = kRowBytes << p.tile_w_log2;  // tile_w rows
+    const int a_m_bytes = p.tile_h * a_sub_bytes;         // distance between the M tiles of a work item
     int sa = 0, sb = 0;
     uint32_t pha = 0, phb = 0;
     int it = 0;
+    if (p.bres && work0 < total_work) mbar_wait(bres_full, 0);
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
-      const int as = it & 1;
-      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      const int as = (p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t aph = static_cast<uint32_t>(p.nacc == 2 ? (it >> 1) : it) & 1u;
       mbar_wait(&tempty_bar[as], aph ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.mt * p.block_n);
       uint32_t acc = 0u;
+      int src = 0, o = 0, ch = 0;   // position of this A step in the producer's (source, kx | tap, chunk) order
       for (int a = 0; a < p.a_steps; ++a) {
         mbar_wait(&a_full[sa], pha);
         const uint32_t a_addr = smem_u32(smem_a + sa * p.a_bytes);
+        const int nch = src ? p.chunks1 : p.chunks0;
         for (int sub = 0; sub < p.nsub; ++sub) {
           const int bsub = (p.bgroup == 3) ? sub : 0;
-          if (bsub == 0) mbar_wait(&b_full[sb], phb);
+          uint32_t b_addr;
+          bool last_of_b = false;
+          if (p.bres) {
+            const int kchunk = (p.nsub == 3) ? (src ? p.taps * p.chunks0 : 0) + (sub * 3 + o) * nch + ch : a;
+            b_addr = smem_u32(smem_b + kchunk * b_tap_bytes);
+          } else {
+            if (bsub == 0) mbar_wait(&b_full[sb], phb);
+            b_addr = smem_u32(smem_b + sb * b_bytes + bsub * b_tap_bytes);
+            last_of_b = (p.bgroup == 1 || sub == p.nsub - 1);
+          }
           tc_fence_after();
-          const bool last_of_b = (p.bgroup == 1 || sub == p.nsub - 1);
           if (elect_one()) {
-            // ky tap = sub: the 128 rows of the MMA start sub * tile_w rows into the (tile_h + 2)-row A stage
-            const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(sub * a_sub_bytes));
-            const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + sb * b_bytes + bsub * b_tap_bytes));
+            // ky tap = sub: the 128 rows of the MMA start sub * tile_w rows into the (mt * tile_h + 2)-row A stage
+            const uint64_t db = umma_desc_k_sw128(b_addr);
+            for (int m = 0; m < p.mt; ++m) {
+              const uint64_t da = umma_desc_k_sw128(a_addr + static_cast<uint32_t>(m * a_m_bytes + sub * a_sub_bytes));
+              const uint32_t d_m = d_tmem + static_cast<uint32_t>(m * p.block_n);
 #pragma unroll
-            for (int kk = 0; kk < kChunkK / 16; ++kk) {
-              // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
-              umma_bf16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
-                        (acc | static_cast<uint32_t>(kk)) ? 1u : 0u);
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                // +32 bytes per K=16 step inside the 128-byte swizzle row (start-address field is in 16-byte units)
+                umma_bf16(d_m, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc,
+                          (acc | static_cast<uint32_t>(kk)) ? 1u : 0u);
+              }
             }
             if (last_of_b) umma_commit(&b_empty[sb]);
             if (sub == p.nsub - 1) {
@@ -631,6 +688,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
         if (++sa == p.sa) { sa = 0; pha ^= 1u; }
+        if (++ch == nch) {
+          ch = 0;
+          if (++o == 3) { o = 0; ++src; }
+        }
       }
     }
   } else if (warp >= 4) {
@@ -645,15 +706,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int c_begin = half ? ((n_chunks + 1) >> 1) : 0;
     const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
     const bool silu = (p.act == GLSDET_ACT_SILU);
+    const int mt = k2 ? 1 : p.mt;
     int it = 0;
+    uint32_t tcount = 0;   // tiles processed by this CTA (prediction-MMA barrier phase, FMA scratch slot)
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
       const TileCoord t = decode(tile);
-      const int as = it & 1;
-      const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+      const int as = (k2 || p.nacc == 2) ? (it & 1) : 0;
+      const uint32_t aph = static_cast<uint32_t>((k2 || p.nacc == 2) ? (it >> 1) : it) & 1u;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(as * p.block_n);
-      const int oy = t.y0 + py, ox = t.x0 + px;
+      for (int m = 0; m < mt; ++m, ++tcount) {
+      const uint32_t tcol = static_cast<uint32_t>((as * mt + m) * p.block_n);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tcol;
+      const int oy = t.y0 + m * p.tile_h + py, ox = t.x0 + px;
       const bool valid = (oy < p.Ho) && (ox < p.Wo);
       const float* sb = s_bias + t.n0;
       // every lane of the warp must execute the TMEM loads; only valid pixels / channels below N are stored
@@ -748,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               pred_accumulate16<4>(raw, sb + c * 16, silu, s_pw + c * 256, acc);
             });
           }
-          float* red = s_red + (as * kBlockM + r) * 16;
+          float* red = s_red + ((tcount & 1u) * kBlockM + r) * 16;
           if (half == 1) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -768,6 +833,72 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
           break;
         }
+        case EPI_TOWER_PRED_MMA: {
+          // second tower conv + prediction conv on the tensor core: the activated tile goes to shared memory as a
+          // bf16 K-major operand (row = pixel, 128-byte swizzle), one thread issues M128 x N16 x K(block_n) MMAs into
+          // the first 16 columns of this (already drained) accumulator, and the lower-half warps decode + store.
+          epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(sb + c * 16 + j);
+              v[j] = __uint_as_float(raw[j]) + bv.x;
+              v[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
+              v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
+              v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+            }
+            if (silu) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) silu4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
+            }
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(v[0], v[1]);  lo.y = pack_bf16x2(v[2], v[3]);
+            lo.z = pack_bf16x2(v[4], v[5]);  lo.w = pack_bf16x2(v[6], v[7]);
+            hi.x = pack_bf16x2(v[8], v[9]);  hi.y = pack_bf16x2(v[10], v[11]);
+            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            uint8_t* rowp = smem_stage + (c >> 2) * kStageTileBytes + (r >> 3) * 1024 + (r & 7) * kRowBytes;
+            const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte row
+            *reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)) = lo;
+            *reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)) = hi;
+          });
+          fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
+          tc_fence_before();
+          asm volatile("bar.sync 5, 256;" ::: "memory");
+          if (e == 0) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t idesc_p = umma_idesc_bf16(kBlockM, 16);
+              const uint32_t d_pred = tmem_base + tcol;
+              for (int kc = 0; kc < k_tiles; ++kc) {
+                const uint64_t da = umma_desc_k_sw128(smem_u32(smem_stage + kc * kStageTileBytes));
+                const uint64_t db = umma_desc_k_sw128(smem_u32(smem_pw + kc * kPredTileBytes));
+#pragma unroll
+                for (int kk = 0; kk < kChunkK / 16; ++kk)
+                  umma_bf16(d_pred, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc_p,
+                            (kc | kk) ? 1u : 0u);
+              }
+              umma_commit(pred_bar);
+            }
+            __syncwarp();
+          }
+          mbar_wait(pred_bar, tcount & 1u);
+          tc_fence_after();
+          if (half == 0) {
+            uint32_t yr[16];
+            tmem_ld16(taddr, yr);
+            tmem_ld_wait();
+            if (valid) {
+              float y[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(yr[j]) + ((j < p.pred_n) ? __ldg(p.pred_b + j) : 0.0f);
+              store_pred(p, y, t.b, oy, ox);
+            }
+          }
+          break;
+        }
         default: {
           for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[16];
@@ -778,6 +909,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           }
         }
       }
+      }  // M tiles of the work item
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -918,20 +1050,52 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   ConvKParams& k = op->kp;
   k.B = d->batch; k.Ho = g.Ho; k.Wo = g.Wo;
 
-  // tile rectangle: 128 pixels, minimise padded area, prefer the squarest (best halo reuse for 3x3)
-  int best_w = 16, best_cost = INT32_MAX;
-  const int cand[5] = {16, 8, 32, 64, 128};
-  for (int i = 0; i < 5; ++i) {
-    int tw = cand[i], th = kBlockM / tw;
-    int cost = ((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
-    if (cost < best_cost) { best_cost = cost; best_w = tw; }
+  // 2-CTA mode (cta_group::2, M = 256 per CTA pair).  Measured on B200 (profiles/README.md): correct, 40 % less
+  // L2->SM traffic, but 5-15 % slower than the 1-CTA kernel at these shapes, so it is opt-in: GLSDET_CONV_2CTA=1.
+  bool two_cta = false;
+  if (const char* e = getenv("GLSDET_CONV_2CTA")) {
+    if (e[0] == '1') two_cta = d->stride == 1 && (g.block_n % 32) == 0;
   }
+  op->two_cta = two_cta ? 1 : 0;
+  const int sms = device_sm_count();
+
+  // Tile rectangle: 128 pixels (tile_h x tile_w), minimise padded area, prefer the squarest (best halo reuse for 3x3).
+  // A work item is `mt` vertically adjacent tiles covered by ONE A box: every weight stage then feeds mt MMAs, which
+  // halves the weight traffic L2 -> SM (the 1-tile kernel re-reads all weights per 128 pixels and saturates L2).
+  auto pick_tile = [&](int mt, int* best_w_out) -> int64_t {
+    int best_w = 16;
+    int64_t best_cost = INT64_MAX;
+    const int cand[5] = {16, 8, 32, 64, 128};
+    for (int i = 0; i < 5; ++i) {
+      const int tw = cand[i], th = (kBlockM / tw) * mt;
+      const int64_t cost = static_cast<int64_t>((g.Wo + tw - 1) / tw) * ((g.Ho + th - 1) / th);
+      if (cost < best_cost) { best_cost = cost; best_w = tw; }
+    }
+    *best_w_out = best_w;
+    return best_cost;   // work items per image and N block
+  };
+  int mt = 1, best_w = 16;
+  {
+    int mt_mode = 0;   // 0 auto, 1 never, 2 whenever legal
+    if (const char* e = getenv("GLSDET_CONV_MT")) mt_mode = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
+    // block_n = 256 would need 2 x 2 x 256 TMEM columns for double-buffered accumulators; single-buffered (exposed
+    // epilogue) it measured 15 % slower than one tile per item, so two-tile items stop at block_n = 128 by default
+    int mt_max_n = 128;
+    if (const char* e = getenv("GLSDET_CONV_MT_MAXN")) mt_max_n = atoi(e);
+    int w2 = 16;
+    const int64_t items2 = pick_tile(2, &w2) * d->batch * g.n_blocks;
+    const bool legal = !two_cta && mt_mode != 1 && g.block_n <= mt_max_n && 2 * g.block_n <= 512;
+    if (legal && (mt_mode == 2 || items2 >= 2 * static_cast<int64_t>(sms))) { mt = 2; best_w = w2; }
+    else pick_tile(1, &best_w);
+  }
+  k.mt = mt;
+  k.nacc = (2 * mt * g.block_n <= 512) ? 2 : 1;
   int tw_log2 = 0;
   while ((1 << tw_log2) < best_w) ++tw_log2;
   k.tile_w_log2 = tw_log2;
   k.tile_h = kBlockM / best_w;
   k.tiles_x = (g.Wo + best_w - 1) / best_w;
-  k.tiles_y = (g.Ho + k.tile_h - 1) / k.tile_h;
+  k.tiles_y = (g.Ho + k.tile_h * mt - 1) / (k.tile_h * mt);
   k.n_blocks = g.n_blocks;
   k.block_n = g.block_n;
   k.N = d->out_channels;
@@ -940,67 +1104,91 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.total_tiles = static_cast<int32_t>(total);
   k.taps = g.taps; k.stride = d->stride;
   k.chunks0 = g.chunks0; k.chunks1 = g.chunks1;
+  k.b_chunks = g.taps * (g.chunks0 + g.chunks1);
 
-  // A/B rings.  3x3 stride-1: one (tile_h + 2)-row A stage feeds three B sub-steps (ky taps).
-  const bool vreuse = (d->ksize == 3 && d->stride == 1 && (k.tile_h + 2) <= 256 && getenv("GLSDET_CONV_NO_VREUSE") == nullptr);
+  // A/B rings.  3x3 stride-1: one (mt * tile_h + 2)-row A stage feeds three B sub-steps (ky taps).
+  const int super_h = k.tile_h * mt;
+  const bool vreuse = (d->ksize == 3 && d->stride == 1 && (super_h + 2) <= 256 && getenv("GLSDET_CONV_NO_VREUSE") == nullptr);
   k.nsub = vreuse ? 3 : 1;
-  const int box_rows = vreuse ? k.tile_h + 2 : k.tile_h;
+  const int box_rows = vreuse ? super_h + 2 : super_h;
   k.a_bytes = box_rows * best_w * kRowBytes;
   k.a_steps = (vreuse ? 3 : g.taps) * (g.chunks0 + g.chunks1);
-  // 2-CTA mode (cta_group::2, M = 256 per CTA pair): halves the B operand traffic of every SM's shared memory,
-  // which is what bounds the 1-CTA kernel on dense 3x3 convs.  Used for stride-1 convs with enough tiles.
   k.m_tiles = k.tiles_x * k.tiles_y * k.B;
   k.total_pairs = ((k.m_tiles + 1) / 2) * k.n_blocks;
-  // Measured on B200 (profiles/README.md): correct, 40 % less L2->SM traffic, but 5-15 % slower than the 1-CTA
-  // kernel at these shapes (neither L2 nor shared memory is the limiter once the MMA issue loop is warp-uniform),
-  // so it is opt-in: GLSDET_CONV_2CTA=1.
-  bool two_cta = false;
-  if (const char* e = getenv("GLSDET_CONV_2CTA")) {
-    if (e[0] == '1') two_cta = d->stride == 1 && (g.block_n % 32) == 0;
-  }
-  op->two_cta = two_cta ? 1 : 0;
+
+  // Fused prediction conv: on the tensor core when the tower width is a multiple of 64 (activated tile staged in
+  // shared memory as a bf16 operand), else per-thread FMAs.
   const bool fused_pred = d->pred_weight != nullptr;
-  const int pred_smem = fused_pred ? (g.block_n * 16 + 2 * kBlockM * 16) * 4 : 0;
-  k.bgroup = (vreuse && (g.block_n <= 128 || two_cta) && getenv("GLSDET_CONV_NO_BGROUP") == nullptr) ? 3 : 1;
-  auto size_rings = [&]() -> bool {
-    const int budget = kSmemLimit - 2048 - g.n_pad * 4 - pred_smem;
+  bool pred_mma = fused_pred && !two_cta && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
+                  getenv("GLSDET_CONV_PRED_FMA") == nullptr;
+  const int b_tap_bytes = g.block_n * kRowBytes;
+  bool bres = false;
+  k.bgroup = 1;
+  auto size_rings = [&](bool want_bgroup3) -> bool {
+    const int pred_smem = !fused_pred ? 0
+                          : pred_mma ? (g.block_n / 64) * (kStageTileBytes + kPredTileBytes)
+                                     : (g.block_n * 16 + 2 * kBlockM * 16) * 4;
+    const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem;
+    const int budget = kSmemLimit - fixed;
+    bres = false;
+    k.bgroup = 1;
     if (two_cta) {  // single ring; a stage = A box + all nsub taps of this CTA's half of B
+      k.bgroup = want_bgroup3 && vreuse ? 3 : 1;
       const int b_bytes2 = k.nsub * (g.block_n / 2) * kRowBytes;
       int stages = budget / (k.a_bytes + b_bytes2);
       if (stages > kMaxStages) stages = kMaxStages;
       if (stages < 2) return false;
       k.sa = k.sb = stages;
-      op->smem_bytes = stages * (k.a_bytes + b_bytes2) + 1024 + 512 + g.n_pad * 4 + pred_smem;
+      op->smem_bytes = stages * (k.a_bytes + b_bytes2) + fixed;
       return true;
     }
-    const int b_bytes = k.bgroup * g.block_n * kRowBytes;
-    if (vreuse && k.bgroup == 3) {
-      int stages = budget / (k.a_bytes + b_bytes);
-      if (stages > 6) stages = 6;
-      if (stages < 2) return false;
-      k.sa = k.sb = stages;
-    } else if (vreuse) {
+    // resident weights: small K x N (one N block) - the weight traffic per tile disappears
+    const int b_total = k.b_chunks * b_tap_bytes;
+    if (g.n_blocks == 1 && b_total <= 96 * 1024 && getenv("GLSDET_CONV_NO_BRES") == nullptr) {
+      int stages = (budget - b_total) / k.a_bytes;
+      if (stages > kMaxStages) stages = kMaxStages;
+      if (stages >= 3) {
+        bres = true;
+        k.sa = stages; k.sb = 0;
+        op->smem_bytes = stages * k.a_bytes + b_total + fixed;
+        return true;
+      }
+    }
+    if (vreuse && want_bgroup3 && g.block_n <= 128) {
+      const int stages = budget / (k.a_bytes + 3 * b_tap_bytes);
+      if (stages >= 3) {
+        k.bgroup = 3;
+        k.sa = k.sb = stages > 6 ? 6 : stages;
+        op->smem_bytes = k.sa * (k.a_bytes + 3 * b_tap_bytes) + fixed;
+        return true;
+      }
+    }
+    if (vreuse) {
       k.sa = 3;
-      k.sb = (budget - k.sa * k.a_bytes) / b_bytes;
-      if (k.sb < 3) { k.sa = 2; k.sb = (budget - k.sa * k.a_bytes) / b_bytes; }
+      k.sb = (budget - k.sa * k.a_bytes) / b_tap_bytes;
+      if (k.sb < 3) { k.sa = 2; k.sb = (budget - k.sa * k.a_bytes) / b_tap_bytes; }
       if (k.sb > kMaxStages) k.sb = kMaxStages;
       if (k.sb < 2) return false;
     } else {
-      int stages = budget / (k.a_bytes + b_bytes);
+      int stages = budget / (k.a_bytes + b_tap_bytes);
       if (stages > kMaxStages) stages = kMaxStages;
       if (stages > k.a_steps * 2) stages = k.a_steps * 2 > 2 ? k.a_steps * 2 : 2;
+      if (stages < 2) return false;
       k.sa = k.sb = stages;
     }
-    op->smem_bytes = k.sa * k.a_bytes + k.sb * b_bytes + 1024 + 512 + g.n_pad * 4 + pred_smem;
+    op->smem_bytes = k.sa * k.a_bytes + k.sb * b_tap_bytes + fixed;
     return true;
   };
-  if (!size_rings()) {
-    k.bgroup = 1;
-    if (!size_rings()) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
+  const bool want_b3 = getenv("GLSDET_CONV_NO_BGROUP") == nullptr;
+  if (!size_rings(want_b3)) {
+    if (pred_mma) { pred_mma = false; }   // the staged operand does not fit next to the rings: FMA prediction path
+    if (!size_rings(want_b3)) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
   }
+  k.bres = bres ? 1 : 0;
   int cols = 32;
-  while (cols < 2 * g.block_n) cols <<= 1;
+  while (cols < k.nacc * mt * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
+  k.pdl = (!two_cta && getenv("GLSDET_CONV_NO_PDL") == nullptr) ? 1 : 0;
 
   k.bias = d->bias; k.act = d->act;
   k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
@@ -1032,7 +1220,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
       if (e[0] == '1') k.epi = EPI_GENERIC;
     }
     k.pred_w = d->pred_weight; k.pred_b = d->pred_bias; k.pred_n = d->pred_channels; k.pred_act = d->pred_act;
-    if (fused_pred) k.epi = EPI_TOWER_PRED;
+    if (fused_pred) k.epi = pred_mma ? EPI_TOWER_PRED_MMA : EPI_TOWER_PRED;
   }
 
   int rc = 0;
@@ -1043,10 +1231,10 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     else if (!rc) k.tmA[1] = k.tmA[0];
   } else {
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(d->src0);
-    rc = encode_act_map(&k.tmA[0], s, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w, k.tile_h);
+    rc = encode_act_map(&k.tmA[0], s, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w, box_rows);
     if (!rc)
       rc = encode_act_map(&k.tmA[1], s + d->src0_ld, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w,
-                          k.tile_h);
+                          box_rows);
   }
   if (!rc) {
     EncodeTiledFn enc = get_encode_tiled();
@@ -1077,7 +1265,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) {  // not representable: fall back to one 2-D box per ky tap
         k.bgroup = 1;
-        if (!size_rings()) { set_error("conv_create: tile does not fit shared memory"); rc = 2; }
+        if (!size_rings(false)) { set_error("conv_create: tile does not fit shared memory"); rc = 2; }
         break;
       }
     }
@@ -1098,7 +1286,6 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     }
     attr_set[dev] = true;
   }
-  const int sms = device_sm_count();
   if (op->two_cta) {
     const int clusters = k.total_pairs < sms / 2 ? k.total_pairs : sms / 2;
     op->grid = 2 * clusters;
@@ -1130,6 +1317,26 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
       return 1;
     }
     return count_launch("conv_gemm_kernel<2cta>");
+  }
+  if (op->kp.pdl) {
+    // programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+    // tail of the previous kernel of the stream; the kernel itself waits (griddepcontrol.wait) before touching memory
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(op->grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = op->smem_bytes;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, op->kp);
+    if (e != cudaSuccess) {
+      set_error("cudaLaunchKernelEx(conv_gemm_kernel, PDL) failed: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    return count_launch("conv_gemm_kernel");
   }
   conv_gemm_kernel<false><<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
   return count_launch("conv_gemm_kernel");

@@ -235,11 +235,45 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: blocks until every prerequisite grid of the stream has completed and its memory is visible.
+// launch_dependents: lets the next kernel of the stream (launched with programmatic stream serialisation) start
+// its own prologue on SMs as they free up.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// x * sigmoid(x) for four values with ONE reciprocal.  The epilogue of a small-K conv is bound by the MUFU pipe
+// (ex2 + rcp per element at 4 lanes/clk/SMSP take longer than the MMAs for K < 512): with q_i = 1 + e^-x_i,
+// r = 1 / (q0 q1 q2 q3) gives 1/q0 = r q1 (q2 q3) etc., i.e. 5 MUFU ops per 4 elements instead of 8.
+// x is clamped at -20 (silu(-20) = -4e-8) so that the product of four q_i stays below 2^128.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void silu4(float& a, float& b, float& c, float& d) {
+  const float kNegLog2e = -1.4426950408889634f;
+  a = fmaxf(a, -20.0f); b = fmaxf(b, -20.0f); c = fmaxf(c, -20.0f); d = fmaxf(d, -20.0f);
+  const float qa = 1.0f + ex2_approx(a * kNegLog2e);
+  const float qb = 1.0f + ex2_approx(b * kNegLog2e);
+  const float qc = 1.0f + ex2_approx(c * kNegLog2e);
+  const float qd = 1.0f + ex2_approx(d * kNegLog2e);
+  const float qab = qa * qb, qcd = qc * qd;
+  const float r = rcp_approx(qab * qcd);
+  const float rab = r * qcd, rcd = r * qab;   // 1 / (qa qb), 1 / (qc qd)
+  a *= rab * qb; b *= rab * qa; c *= rcd * qd; d *= rcd * qc;
+}
 
 }  // namespace glsdet

@@ -227,7 +227,12 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
     bp = torch.randn(n_pred, generator=g).to(dev)
     t = F.conv2d(x, w, bias, padding=1)
     t = t * torch.sigmoid(t)
-    y = F.conv2d(t, wp, bp)                                     # [B, n_pred, H, W]
+    import os
+    if n_tower % 64 == 0 and not os.environ.get("GLSDET_CONV_PRED_FMA"):
+        # tensor-core prediction path: the activated tile and the prediction weights are bf16 MMA operands
+        y = F.conv2d(_bf16r(t), _bf16r(wp), bp)
+    else:
+        y = F.conv2d(t, wp, bp)                                 # [B, n_pred, H, W]
     rows = y.permute(0, 2, 3, 1).reshape(B, H * W, n_pred)
     nch = n_pred + 3
     if pred_act == "none_nchw":
@@ -235,7 +240,8 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
         ConvOp([View(_nhwc(x))], w, bias, ksize=3, act=N.ACT_SILU, out=out, out_mode=N.OUT_NCHW_F32, out_ld=nch,
                out_coff=2, out_batch_stride=nch * H * W, pred_weight=wp, pred_bias=bp, pred_act=N.ACT_NONE).launch()
         torch.cuda.synchronize()
-        assert torch.allclose(out[:, 2:2 + n_pred], y, rtol=2e-3, atol=2e-3)
+        # 6e-3: one bf16 rounding flip of a large activation (|t| 4 * 2^-8) times a prediction weight
+        assert torch.allclose(out[:, 2:2 + n_pred], y, rtol=6e-3, atol=6e-3), (out[:, 2:2 + n_pred] - y).abs().max()
         assert torch.isnan(out[:, :2]).all() and torch.isnan(out[:, 2 + n_pred:]).all()
         return
     out = torch.full((B, H * W, nch), float("nan"), device=dev)
@@ -256,14 +262,40 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
         ref = torch.stack([(rows[..., 0] + gx) * stride / in_w, (rows[..., 1] + gy) * stride / in_h,
                            torch.exp(rows[..., 2]) * stride / in_w, torch.exp(rows[..., 3]) * stride / in_h,
                            torch.sigmoid(rows[..., 4])], dim=-1)
-    assert torch.allclose(got, ref, rtol=3e-3, atol=3e-3), (got - ref).abs().max()
+    assert torch.allclose(got, ref, rtol=6e-3, atol=6e-3), (got - ref).abs().max()
     assert torch.isnan(out[:, :, 0]).all() and torch.isnan(out[:, :, 1 + n_pred:]).all()
 
 
 def test_two_cta_mode(native_lib, cuda_device, monkeypatch):
     """cta_group::2 variant (CTA pairs, M = 256 per tcgen05.mma, operands split over two SMs): opt-in, same results."""
     monkeypatch.setenv("GLSDET_CONV_2CTA", "1")
+    monkeypatch.setenv("GLSDET_CONV_PRED_FMA", "1")   # the 2-CTA kernel keeps the FMA prediction path
     for case in (CASES[2], CASES[3], CASES[6], CASES[9], CASES[10]):
         test_conv_matches_torch(case, native_lib, cuda_device)
     test_fused_tower_pred_conv(128, 10, "sigmoid", native_lib, cuda_device)
     test_bf16_residual_epilogues(native_lib, cuda_device)
+
+
+def test_fused_pred_fma_path(native_lib, cuda_device, monkeypatch):
+    """Per-thread FMA prediction path (tower widths that are not a multiple of 64 use it; forced here)."""
+    monkeypatch.setenv("GLSDET_CONV_PRED_FMA", "1")
+    test_fused_tower_pred_conv(128, 10, "sigmoid", native_lib, cuda_device)
+    test_fused_tower_pred_conv(128, 5, "box", native_lib, cuda_device)
+    test_fused_tower_pred_conv(256, 3, "sigmoid", native_lib, cuda_device)
+
+
+@pytest.mark.parametrize("env", [{"GLSDET_CONV_MT": "2"}, {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BRES": "1"},
+                                 {"GLSDET_CONV_MT": "1", "GLSDET_CONV_NO_BRES": "1", "GLSDET_CONV_NO_PDL": "1"},
+                                 {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BGROUP": "1"}],
+                         ids=["mt2", "mt2_nobres", "mt1_nobres_nopdl", "mt2_nobgroup"])
+def test_conv_schedule_variants(env, native_lib, cuda_device, monkeypatch):
+    """Work-item shapes and weight staging are scheduling choices: two M tiles per weight stage (mt=2), resident
+    weights, grouped ky taps, programmatic dependent launch - every combination must give the same results."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for case in CASES:
+        test_conv_matches_torch(case, native_lib, cuda_device)
+    test_conv_residuals_and_fp32_out(native_lib, cuda_device)
+    test_bf16_residual_epilogues(native_lib, cuda_device)
+    for args in [(128, 10, "sigmoid"), (128, 5, "box"), (256, 3, "sigmoid"), (64, 5, "none_nchw"), (96, 16, "none_rows")]:
+        test_fused_tower_pred_conv(*args, native_lib, cuda_device)

@@ -18,6 +18,13 @@ CASES = {
     "csp3x3_c64_n64": (16, 256, 256, [64], 64, 3, 1),
     "ffa1x1_c512_n512": (16, 64, 64, [512], 512, 1, 1),
     "pred_n10": (16, 256, 256, [128], 10, 1, 1),
+    "csp1x1_c64_n64": (16, 256, 256, [64], 64, 1, 1),
+    "csp1x1_c128_n128": (16, 256, 256, [128], 128, 1, 1),
+    "neck1x1_c256_n128_s8": (16, 128, 128, [256], 128, 1, 1),
+    "neck3x3_c128_n128_s16": (16, 64, 64, [128], 128, 3, 1),
+    # second tower conv + fused prediction conv (10 classes, sigmoid rows)
+    "tower_pred_s4": (16, 256, 256, [128], 128, 3, 1, 10),
+    "tower_pred_s8": (16, 128, 128, [128], 128, 3, 1, 10),
 }
 
 
@@ -30,12 +37,21 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name in args.cases.split(","):
-        B, H, W, cins, n, k, s = CASES[name]
+        B, H, W, cins, n, k, s = CASES[name][:7]
+        n_pred = CASES[name][7] if len(CASES[name]) > 7 else 0
         srcs = [View(torch.randn(B, H, W, c, device=dev).to(torch.bfloat16)) for c in cins]
         w = torch.randn(n, sum(cins), k, k, device=dev) * 0.05
         bias = torch.randn(n, device=dev)
         out = torch.empty(B, H // s, W // s, n, device=dev, dtype=torch.bfloat16)
-        op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=View(out))
+        if n_pred:
+            rows = torch.empty(B, (H // s) * (W // s), n_pred + 5, device=dev)
+            wp = torch.randn(n_pred, n, 1, 1, device=dev) * 0.05
+            op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=rows,
+                        out_mode=N.OUT_NHWC_F32, out_ld=n_pred + 5, out_coff=5,
+                        out_batch_stride=rows.shape[1] * (n_pred + 5), pred_weight=wp,
+                        pred_bias=torch.zeros(n_pred, device=dev), pred_act=N.ACT_SIGMOID)
+        else:
+            op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=View(out))
         for _ in range(3):
             op.launch()
         torch.cuda.synchronize()
