@@ -47,6 +47,7 @@ struct alignas(64) ConvKParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
   CUtensorMap tmB3[2];       // per source: 3-D view (k, n, ky) of the weights, one box = the three ky taps
+  CUtensorMap tmO;           // TMA-store epilogue: the bf16 NHWC output window, box = one 128-pixel x 64-channel tile
   int32_t B, Ho, Wo;
   int32_t tile_w_log2, tile_h;
   int32_t tiles_x, tiles_y, n_blocks, total_tiles;
@@ -65,6 +66,7 @@ struct alignas(64) ConvKParams {
   int32_t bres;              // all weight chunks stay resident in shared memory (loaded once per CTA)
   int32_t b_chunks;          // number of 64-wide K chunks of the weight matrix
   int32_t pdl;               // launched with programmatic stream serialisation
+  int32_t ts;                // bf16 epilogues stage the tile in shared memory and TMA-store it
   const float* bias;
   int32_t act;
   const float* pre_res;
@@ -246,7 +248,7 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
 // loops).  bf16 NHWC output of 16 channels = two 16-byte stores.
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
-                                           const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o) {
+                                           const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
@@ -265,7 +267,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   }
   if (silu) {
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) silu4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -287,8 +289,13 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
   c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
   c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
-  reinterpret_cast<uint4*>(o)[0] = a;
-  reinterpret_cast<uint4*>(o)[1] = c;
+  *o0 = a;
+  *o1 = c;
+}
+template <bool PRE, bool POST>
+__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+                                           const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o) {
+  epi16_bf16<PRE, POST>(raw, s_bias, silu, pre, post, reinterpret_cast<uint4*>(o), reinterpret_cast<uint4*>(o) + 1);
 }
 
 // bias only, fp32 NHWC, 16 channels = four 16-byte stores (low-resolution partial sums)
@@ -309,7 +316,7 @@ __device__ __forceinline__ void pred_accumulate16(const uint32_t (&raw)[16], con
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float v = __uint_as_float(raw[j]) + s_bias[j];
-    v = silu ? silu_f(v) : fmaxf(v, 0.0f);
+    v = silu ? silu_fast(v) : fmaxf(v, 0.0f);
     const float4* w = reinterpret_cast<const float4*>(s_pw + j * 16);
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
@@ -381,6 +388,48 @@ __device__ __forceinline__ void epi_walk(uint32_t taddr, int c_begin, int c_end,
   }
 }
 
+// TMA-store epilogue of one 128-pixel tile (bf16 NHWC output).  Direct per-thread stores cost one L1 wavefront per
+// 16 bytes (every lane owns a different pixel row) - 16 * N cycles per tile, more than the MMAs of a K < 512 conv.
+// Here each thread writes its row into a 128-pixel x 64-channel staging tile (128-byte swizzle, conflict-free), and
+// one thread per warp group hands the tile to the TMA unit, which also clips ragged tiles at the tensor bounds.
+// Staging is double-buffered per group: the issuer waits until its earlier stores have finished reading shared
+// memory BEFORE the group barrier, so after barrier i every thread may overwrite the buffer of store i-1.
+struct TsCtx {
+  uint8_t* gbuf;      // this group's two staging tiles
+  int nthr, bar_id;   // group size / named barrier
+  bool issuer;
+  bool wide;          // block_n >= 128: each column half owns whole 64-channel tiles; else both halves share one
+};
+template <bool PRE, bool POST>
+__device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g, uint32_t taddr, int r, int half,
+                                            int k_tiles, bool valid, bool silu, const float* sb, const float* pre,
+                                            const __nv_bfloat16* post, const TileCoord& t, int y_tile,
+                                            uint32_t& sbuf) {
+  const int kc_begin = g.wide ? (half ? (k_tiles + 1) >> 1 : 0) : 0;
+  const int kc_end = g.wide ? (half ? k_tiles : (k_tiles + 1) >> 1) : 1;
+  for (int kc = kc_begin; kc < kc_end; ++kc, ++sbuf) {
+    uint8_t* buf = g.gbuf + (sbuf & 1u) * kStageTileBytes;
+    uint8_t* rowp = buf + (r >> 3) * 1024 + (r & 7) * kRowBytes;
+    const int cb = g.wide ? kc * 4 : half * 2;
+    const int ce = g.wide ? kc * 4 + 4 : half * 2 + 2;
+    epi_walk(taddr, cb, ce, [&](const uint32_t (&raw)[16], int c) {
+      if (valid) {
+        const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte staging row
+        epi16_bf16<PRE, POST>(raw, sb + c * 16, silu, PRE ? pre + c * 16 : nullptr, POST ? post + c * 16 : nullptr,
+                              reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)),
+                              reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)));
+      }
+    });
+    fence_proxy_async_smem();
+    if (g.issuer) tma_store_wait_read();
+    named_bar_sync(g.bar_id, g.nthr);
+    if (g.issuer) {
+      tma_store_5d(&p.tmO, buf, t.n0 + kc * kChunkK, t.x0, 0, y_tile, t.b);
+      tma_store_commit();
+    }
+  }
+}
+
 template <bool k2>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -396,7 +445,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.sa * p.a_bytes;
   uint8_t* smem_stage = smem_b + b_region;                                          // [k_tiles][128 rows][128 B]
-  uint8_t* smem_pw = smem_stage + (pred_mma ? k_tiles * kStageTileBytes : 0);      // [k_tiles][16 rows][128 B]
+  const int ts_groups = (p.block_n >= 128) ? 2 : 1;
+  uint8_t* smem_pw = smem_stage + (pred_mma ? k_tiles * kStageTileBytes               // [k_tiles][16 rows][128 B]
+                                            : p.ts ? ts_groups * 2 * kStageTileBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pw + (pred_mma ? k_tiles * kPredTileBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kMaxStages;
@@ -424,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (p.chunks1 > 0 || p.stride == 2) tma_prefetch_desc(&p.tmA[1]);
     tma_prefetch_desc(&p.tmB);
     if (p.bgroup == 3) { tma_prefetch_desc(&p.tmB3[0]); tma_prefetch_desc(&p.tmB3[1]); }
+    if (p.ts) tma_prefetch_desc(&p.tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.sa; ++s) {
@@ -707,6 +759,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
     const bool silu = (p.act == GLSDET_ACT_SILU);
     const int mt = k2 ? 1 : p.mt;
+    TsCtx tsg;
+    tsg.wide = p.block_n >= 128;
+    tsg.gbuf = smem_stage + (tsg.wide ? half : 0) * 2 * kStageTileBytes;
+    tsg.nthr = tsg.wide ? 128 : 256;
+    tsg.bar_id = 6 + (tsg.wide ? half : 0);
+    tsg.issuer = (lane == 0) && (tsg.wide ? (q == 0) : (e == 0));
+    uint32_t sbuf = 0;     // staging tiles written by this warp group (TMA-store epilogue)
     int it = 0;
     uint32_t tcount = 0;   // tiles processed by this CTA (prediction-MMA barrier phase, FMA scratch slot)
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
@@ -728,6 +787,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         case EPI_BF16_POST: {
           __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                                 (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
+          if (p.ts) {
+            const int y_tile = t.y0 + m * p.tile_h;
+            if (p.epi == EPI_BF16) {
+              epi_tile_ts<false, false>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, nullptr, nullptr, t, y_tile, sbuf);
+            } else if (p.epi == EPI_BF16_PRE) {
+              const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
+              const float* pre = p.pre_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + t.n0;
+              epi_tile_ts<true, false>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, pre, nullptr, t, y_tile, sbuf);
+            } else {
+              const int hs = p.Ho >> p.post_shift, ws = p.Wo >> p.post_shift;
+              const __nv_bfloat16* post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
+              epi_tile_ts<false, true>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, nullptr, post, t, y_tile, sbuf);
+            }
+            break;
+          }
           if (p.epi == EPI_BF16) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
               if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, silu, nullptr, nullptr, orow + c * 16);
@@ -849,7 +923,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             if (silu) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) silu4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -917,6 +991,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         else mbar_arrive(&tempty_bar[as]);
       }
     }
+    if (p.ts && tsg.issuer) tma_store_wait_all();   // shared memory must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -1116,9 +1191,40 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.m_tiles = k.tiles_x * k.tiles_y * k.B;
   k.total_pairs = ((k.m_tiles + 1) / 2) * k.n_blocks;
 
+  k.epi = EPI_GENERIC;
+  {
+    const bool n16 = (d->out_channels % 16) == 0;
+    const bool act_sr = (d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU);
+    const bool bf16_vec = d->out_mode == GLSDET_OUT_NHWC_BF16 && n16 && ((d->out_ld | d->out_coff) % 8) == 0 &&
+                          (d->out_batch_stride % 8) == 0;
+    const bool small_n = d->out_channels <= 16;
+    k.epi = EPI_GENERIC;
+    if (bf16_vec && act_sr && !d->pre_res && !d->post_res) k.epi = EPI_BF16;
+    else if (bf16_vec && act_sr && d->pre_res && !d->post_res && (d->pre_ld % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->pre_res) & 15) == 0) k.epi = EPI_BF16_PRE;
+    else if (bf16_vec && act_sr && !d->pre_res && d->post_res && (d->post_ld % 8) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->post_res) & 15) == 0) k.epi = EPI_BF16_POST;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_NONE && n16 && !d->pre_res && !d->post_res &&
+             ((d->out_ld | d->out_coff) % 4) == 0 && (d->out_batch_stride % 4) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) k.epi = EPI_F32_PLAIN;
+    else if (d->out_mode == GLSDET_OUT_NCHW_F32 && d->act == GLSDET_ACT_NONE && small_n && !d->pre_res && !d->post_res)
+      k.epi = EPI_NCHW_RAW;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_YOLOX_BOX && d->out_channels == 5 &&
+             !d->pre_res && !d->post_res) k.epi = EPI_ROWS_BOX;
+    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_SIGMOID && small_n && !d->pre_res &&
+             !d->post_res) k.epi = EPI_ROWS_SIGMOID;
+    if (const char* e = getenv("GLSDET_CONV_GENERIC_EPILOGUE")) {  // tests: force the generic epilogue
+      if (e[0] == '1') k.epi = EPI_GENERIC;
+    }
+  }
+  // TMA-store epilogue: small-K convs whose epilogue (not the MMAs) paces the kernel
+  const bool fused_pred = d->pred_weight != nullptr;
+  bool ts = !two_cta && !fused_pred && (k.epi == EPI_BF16 || k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST) &&
+            (d->out_channels % 64) == 0 && (g.block_n % 64) == 0 && g.k_pad <= 640 &&
+            d->out_batch_stride == static_cast<int64_t>(g.Ho) * g.Wo * d->out_ld &&
+            getenv("GLSDET_CONV_NO_TMA_STORE") == nullptr;
   // Fused prediction conv: on the tensor core when the tower width is a multiple of 64 (activated tile staged in
   // shared memory as a bf16 operand), else per-thread FMAs.
-  const bool fused_pred = d->pred_weight != nullptr;
   bool pred_mma = fused_pred && !two_cta && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
                   getenv("GLSDET_CONV_PRED_FMA") == nullptr;
   const int b_tap_bytes = g.block_n * kRowBytes;
@@ -1128,7 +1234,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     const int pred_smem = !fused_pred ? 0
                           : pred_mma ? (g.block_n / 64) * (kStageTileBytes + kPredTileBytes)
                                      : (g.block_n * 16 + 2 * kBlockM * 16) * 4;
-    const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem;
+    const int ts_smem = ts ? (g.block_n >= 128 ? 4 : 2) * kStageTileBytes : 0;
+    const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem + ts_smem;
     const int budget = kSmemLimit - fixed;
     bres = false;
     k.bgroup = 1;
@@ -1180,6 +1287,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     return true;
   };
   const bool want_b3 = getenv("GLSDET_CONV_NO_BGROUP") == nullptr;
+  if (ts && !size_rings(want_b3)) ts = false;   // no room for the staging tiles: direct stores
   if (!size_rings(want_b3)) {
     if (pred_mma) { pred_mma = false; }   // the staged operand does not fit next to the rings: FMA prediction path
     if (!size_rings(want_b3)) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
@@ -1189,6 +1297,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   while (cols < k.nacc * mt * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
   k.pdl = (!two_cta && getenv("GLSDET_CONV_NO_PDL") == nullptr) ? 1 : 0;
+  k.ts = ts ? 1 : 0;
 
   k.bias = d->bias; k.act = d->act;
   k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
@@ -1196,29 +1305,6 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
   k.dec_stride = d->dec_stride; k.dec_in_w = d->dec_in_w; k.dec_in_h = d->dec_in_h;
   {
-    const bool n16 = (d->out_channels % 16) == 0;
-    const bool act_sr = (d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU);
-    const bool bf16_vec = d->out_mode == GLSDET_OUT_NHWC_BF16 && n16 && ((d->out_ld | d->out_coff) % 8) == 0 &&
-                          (d->out_batch_stride % 8) == 0;
-    const bool small_n = d->out_channels <= 16;
-    k.epi = EPI_GENERIC;
-    if (bf16_vec && act_sr && !d->pre_res && !d->post_res) k.epi = EPI_BF16;
-    else if (bf16_vec && act_sr && d->pre_res && !d->post_res && (d->pre_ld % 4) == 0 &&
-             (reinterpret_cast<uintptr_t>(d->pre_res) & 15) == 0) k.epi = EPI_BF16_PRE;
-    else if (bf16_vec && act_sr && !d->pre_res && d->post_res && (d->post_ld % 8) == 0 &&
-             (reinterpret_cast<uintptr_t>(d->post_res) & 15) == 0) k.epi = EPI_BF16_POST;
-    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_NONE && n16 && !d->pre_res && !d->post_res &&
-             ((d->out_ld | d->out_coff) % 4) == 0 && (d->out_batch_stride % 4) == 0 &&
-             (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) k.epi = EPI_F32_PLAIN;
-    else if (d->out_mode == GLSDET_OUT_NCHW_F32 && d->act == GLSDET_ACT_NONE && small_n && !d->pre_res && !d->post_res)
-      k.epi = EPI_NCHW_RAW;
-    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_YOLOX_BOX && d->out_channels == 5 &&
-             !d->pre_res && !d->post_res) k.epi = EPI_ROWS_BOX;
-    else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_SIGMOID && small_n && !d->pre_res &&
-             !d->post_res) k.epi = EPI_ROWS_SIGMOID;
-    if (const char* e = getenv("GLSDET_CONV_GENERIC_EPILOGUE")) {  // tests: force the generic epilogue
-      if (e[0] == '1') k.epi = EPI_GENERIC;
-    }
     k.pred_w = d->pred_weight; k.pred_b = d->pred_bias; k.pred_n = d->pred_channels; k.pred_act = d->pred_act;
     if (fused_pred) k.epi = pred_mma ? EPI_TOWER_PRED_MMA : EPI_TOWER_PRED;
   }
@@ -1235,6 +1321,10 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (!rc)
       rc = encode_act_map(&k.tmA[1], s + d->src0_ld, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w,
                           box_rows);
+  }
+  if (!rc && k.ts) {
+    const __nv_bfloat16* obase = reinterpret_cast<const __nv_bfloat16*>(d->out) + d->out_coff;
+    rc = encode_act_map(&k.tmO, obase, d->out_channels, d->out_ld, d->batch, g.Ho, g.Wo, 1, best_w, k.tile_h);
   }
   if (!rc) {
     EncodeTiledFn enc = get_encode_tiled();

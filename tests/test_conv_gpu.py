@@ -41,6 +41,9 @@ CASES = [
     ("1x1_c96_n192", 1, 24, 24, [96], 192, 1, 1, "none"),
     ("3x3_c128_n256", 1, 20, 20, [128], 256, 3, 1, "silu"),
     ("3x3_c128_n128_big", 2, 256, 256, [128], 128, 3, 1, "silu"),
+    ("1x1_c64_n64_ragged", 2, 40, 36, [64], 64, 1, 1, "silu"),
+    ("1x1_c128_n192_ragged", 1, 20, 44, [128], 192, 1, 1, "relu"),
+    ("1x1_c64_n128_big", 2, 256, 256, [64], 128, 1, 1, "silu"),
 ]
 
 
@@ -286,8 +289,9 @@ def test_fused_pred_fma_path(native_lib, cuda_device, monkeypatch):
 
 @pytest.mark.parametrize("env", [{"GLSDET_CONV_MT": "2"}, {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BRES": "1"},
                                  {"GLSDET_CONV_MT": "1", "GLSDET_CONV_NO_BRES": "1", "GLSDET_CONV_NO_PDL": "1"},
-                                 {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BGROUP": "1"}],
-                         ids=["mt2", "mt2_nobres", "mt1_nobres_nopdl", "mt2_nobgroup"])
+                                 {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BGROUP": "1"},
+                                 {"GLSDET_CONV_NO_TMA_STORE": "1"}],
+                         ids=["mt2", "mt2_nobres", "mt1_nobres_nopdl", "mt2_nobgroup", "direct_stores"])
 def test_conv_schedule_variants(env, native_lib, cuda_device, monkeypatch):
     """Work-item shapes and weight staging are scheduling choices: two M tiles per weight stage (mt=2), resident
     weights, grouped ky taps, programmatic dependent launch - every combination must give the same results."""

@@ -1,0 +1,56 @@
+"""One profiled step of the bench workload, bracketed by cudaProfilerStart/Stop (run under
+`ncu --profile-from-start off ...`).  Also writes the op list of the step (shapes, FLOPs) so that the per-launch
+ncu table can be joined with layer shapes: gpurun_out/step_ops.json."""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+from glsdet_b200.ops import ConvOp  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    sd = bench.make_weights()
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    net = YoloBody(bench.NUM_CLASSES, bench.PHI)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    B = 16
+    feats = bench.make_features(net, B, 1000, dev)
+    plan = net.plan_for(feats)
+    nms = net.nms_for(plan, 1000)
+
+    def step():
+        plan.load_features(feats)
+        plan.run_neck()
+        plan.run_head(True)
+        nms.launch(plan.pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
+
+    ops = []
+    for group, lst in (("neck", plan.neck_ops), ("stems", plan.stem_ops), ("tower", plan.tower_ops), ("pred", plan.pred_dec_ops)):
+        for op in lst:
+            if isinstance(op, ConvOp):
+                d = op.desc
+                ops.append(dict(group=group, k=d.ksize, s=d.stride, cin=d.src0_c + d.src1_c, n=d.out_channels,
+                                h=d.height, w=d.width, gflop=op.flops / 1e9, pred=int(d.pred_channels)))
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "step_ops.json").write_text(json.dumps(ops))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStart()
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+
+
+if __name__ == "__main__":
+    main()
