@@ -38,6 +38,8 @@ class ConvDesc(C.Structure):
         ("out_batch_stride", C.c_int64),
         ("dec_stride", C.c_float), ("dec_in_w", C.c_float), ("dec_in_h", C.c_float),
         ("pred_weight", C.c_void_p), ("pred_bias", C.c_void_p), ("pred_channels", C.c_int32), ("pred_act", C.c_int32),
+        ("weight_batch_stride", C.c_int64), ("weight_ld", C.c_int32), ("src_shared", C.c_int32),
+        ("patch_mode", C.c_int32),
     ]
 
 
@@ -57,6 +59,12 @@ SIGNATURES = {
                                                C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_patch_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_void_p]),
+    "glsdet_gather_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int64, C.c_int32, C.c_void_p]),
+    "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_scale_pixel_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -67,8 +67,12 @@ struct alignas(64) ConvKParams {
   int32_t b_chunks;          // number of 64-wide K chunks of the weight matrix
   int32_t pdl;               // launched with programmatic stream serialisation
   int32_t ts;                // bf16 epilogues stage the tile in shared memory and TMA-store it
+  int32_t w_batched;         // one weight matrix per image (third coordinate of tmB)
+  int32_t a_shared;          // k > 0: image b reads activation image b % k (static matrices used as activations)
+  int32_t patch;             // src0 / post_res / out are 2x2 patch views (image b' = (b*2 + py)*2 + px)
   const float* bias;
   int32_t act;
+  int32_t act_epi;           // activation code of the fast bf16 epilogues (act, or kActSiluExact)
   const float* pre_res;
   int32_t pre_shift, pre_ld;
   const __nv_bfloat16* post_res;
@@ -84,8 +88,9 @@ struct alignas(64) ConvKParams {
 };
 
 enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
-       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8, EPI_TOWER_PRED_MMA = 9 };
+       EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8, EPI_TOWER_PRED_MMA = 9, EPI_BF16_PREPOST = 10 };
 
+constexpr int kActSiluExact = 100;   // diagnostic (GLSDET_CONV_EXACT_SILU=1): ex2 + rcp SiLU instead of tanh.approx
 constexpr int kStageTileBytes = kBlockM * kRowBytes;   // one 128-row x 64-channel K-major SW128 operand tile
 constexpr int kPredTileBytes = 16 * kRowBytes;         // prediction weights: 16 rows x 64 channels
 
@@ -247,7 +252,7 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
 // Specialised epilogues (chosen per op at create time; everything warp-uniform is hoisted out of the element
 // loops).  bf16 NHWC output of 16 channels = two 16-byte stores.
 template <bool PRE, bool POST>
-__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, int act,
                                            const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1) {
   float v[16];
 #pragma unroll
@@ -265,10 +270,13 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
       v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
     }
   }
-  if (silu) {
+  if (act == GLSDET_ACT_SILU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
-  } else {
+  } else if (act == kActSiluExact) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+  } else if (act == GLSDET_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
   }
@@ -293,9 +301,9 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   *o1 = c;
 }
 template <bool PRE, bool POST>
-__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, bool silu,
+__device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, int act,
                                            const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o) {
-  epi16_bf16<PRE, POST>(raw, s_bias, silu, pre, post, reinterpret_cast<uint4*>(o), reinterpret_cast<uint4*>(o) + 1);
+  epi16_bf16<PRE, POST>(raw, s_bias, act, pre, post, reinterpret_cast<uint4*>(o), reinterpret_cast<uint4*>(o) + 1);
 }
 
 // bias only, fp32 NHWC, 16 channels = four 16-byte stores (low-resolution partial sums)
@@ -402,9 +410,11 @@ struct TsCtx {
 };
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g, uint32_t taddr, int r, int half,
-                                            int k_tiles, bool valid, bool silu, const float* sb, const float* pre,
+                                            int k_tiles, bool valid, int act, const float* sb, const float* pre,
                                             const __nv_bfloat16* post, const TileCoord& t, int y_tile,
                                             uint32_t& sbuf) {
+  const int c2 = p.patch ? (t.b & 1) : 0;        // patch views: image b' = (b*2 + py)*2 + px
+  const int c4 = p.patch ? (t.b >> 1) : t.b;
   const int kc_begin = g.wide ? (half ? (k_tiles + 1) >> 1 : 0) : 0;
   const int kc_end = g.wide ? (half ? k_tiles : (k_tiles + 1) >> 1) : 1;
   for (int kc = kc_begin; kc < kc_end; ++kc, ++sbuf) {
@@ -415,7 +425,7 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
     epi_walk(taddr, cb, ce, [&](const uint32_t (&raw)[16], int c) {
       if (valid) {
         const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte staging row
-        epi16_bf16<PRE, POST>(raw, sb + c * 16, silu, PRE ? pre + c * 16 : nullptr, POST ? post + c * 16 : nullptr,
+        epi16_bf16<PRE, POST>(raw, sb + c * 16, act, PRE ? pre + c * 16 : nullptr, POST ? post + c * 16 : nullptr,
                               reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)),
                               reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)));
       }
@@ -424,7 +434,7 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
     if (g.issuer) tma_store_wait_read();
     named_bar_sync(g.bar_id, g.nthr);
     if (g.issuer) {
-      tma_store_5d(&p.tmO, buf, t.n0 + kc * kChunkK, t.x0, 0, y_tile, t.b);
+      tma_store_5d(&p.tmO, buf, t.n0 + kc * kChunkK, t.x0, c2, y_tile, c4);
       tma_store_commit();
     }
   }
@@ -619,11 +629,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       tma_load_5d(smem_a + sa * p.a_bytes, tm, &a_full[sa], c0, c1, c2, c3, c4);
       if (++sa == p.sa) { sa = 0; pha ^= 1u; }
     };
+    int wb = 0;   // image index of the weight matrix (per-image weights)
     auto load_b = [&](int kchunk, int n0) {
       if (p.bres) return;
       mbar_wait(&b_empty[sb], phb ^ 1u);
       mbar_arrive_expect_tx(&b_full[sb], static_cast<uint32_t>(b_bytes));
-      tma_load_2d(smem_b + sb * b_bytes, &p.tmB, &b_full[sb], kchunk * kChunkK, n0);
+      if (p.w_batched) tma_load_3d(smem_b + sb * b_bytes, &p.tmB, &b_full[sb], kchunk * kChunkK, n0, wb);
+      else tma_load_2d(smem_b + sb * b_bytes, &p.tmB, &b_full[sb], kchunk * kChunkK, n0);
       if (++sb == p.sb) { sb = 0; phb ^= 1u; }
     };
     auto load_b3 = [&](int src, int kchunk, int n0) {
@@ -640,6 +652,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int tile = work0; tile < total_work; tile += work_stride) {
       const TileCoord t = decode_tile(p, tile);
+      wb = t.b;
+      const int ac2 = p.patch ? (t.b & 1) : 0;                              // patch views: b' = (b*2 + py)*2 + px
+      const int ab = p.a_shared ? (t.b % p.a_shared) : (p.patch ? (t.b >> 1) : t.b);
       if (p.stride == 1) {
         for (int src = 0; src < 2; ++src) {
           const int nch = src ? p.chunks1 : p.chunks0;
@@ -648,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           if (p.nsub == 3) {
             for (int kx = 0; kx < 3; ++kx) {
               for (int ch = 0; ch < nch; ++ch) {
-                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, t.b);  // mt * tile_h + 2 rows
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, ab);  // mt * tile_h + 2 rows
                 if (p.bres) continue;
                 if (p.bgroup == 3) load_b3(src, kbase + kx * nch + ch, t.n0);         // ky = 0,1,2 in one box
                 else for (int ky = 0; ky < 3; ++ky) load_b(kbase + (ky * 3 + kx) * nch + ch, t.n0);
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
               const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
               for (int ch = 0; ch < nch; ++ch) {
-                load_a(&p.tmA[src], ch * kChunkK, t.x0 + dx, 0, t.y0 + dy, t.b);
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + dx, ac2, t.y0 + dy, ab);
                 load_b(kbase + tap * nch + ch, t.n0);
               }
             }
@@ -674,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
           const int py = (ky == 1) ? 0 : 1;
           const int yh = t.y0 + (ky == 0 ? -1 : 0);
           for (int ch = 0; ch < p.chunks0; ++ch) {
-            load_a(&p.tmA[map], ch * kChunkK, xh, py, yh, t.b);
+            load_a(&p.tmA[map], ch * kChunkK, xh, py, yh, ab);
             load_b(tap * p.chunks0 + ch, t.n0);
           }
         }
@@ -784,39 +799,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
       switch (p.epi) {
         case EPI_BF16:
         case EPI_BF16_PRE:
-        case EPI_BF16_POST: {
-          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
-                                (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
-          if (p.ts) {
-            const int y_tile = t.y0 + m * p.tile_h;
-            if (p.epi == EPI_BF16) {
-              epi_tile_ts<false, false>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, nullptr, nullptr, t, y_tile, sbuf);
-            } else if (p.epi == EPI_BF16_PRE) {
-              const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
-              const float* pre = p.pre_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + t.n0;
-              epi_tile_ts<true, false>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, pre, nullptr, t, y_tile, sbuf);
+        case EPI_BF16_POST:
+        case EPI_BF16_PREPOST: {
+          const bool has_pre = (p.epi == EPI_BF16_PRE || p.epi == EPI_BF16_PREPOST);
+          const bool has_post = (p.epi == EPI_BF16_POST || p.epi == EPI_BF16_PREPOST);
+          const float* pre = nullptr;
+          const __nv_bfloat16* post = nullptr;
+          if (has_pre) {   // a shift beyond the image size selects one row per image (per-image bias)
+            const int hs = max(p.Ho >> p.pre_shift, 1), ws = max(p.Wo >> p.pre_shift, 1);
+            pre = p.pre_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + t.n0;
+          }
+          if (has_post) {
+            if (p.patch) {   // residual read from the un-split tensor [B, 2 Ho, 2 Wo, ld]
+              const int pb = t.b >> 2, ppy = (t.b >> 1) & 1, ppx = t.b & 1;
+              post = p.post_res + ((static_cast<int64_t>(pb) * 2 * p.Ho + ppy * p.Ho + oy) * (2 * p.Wo) + ppx * p.Wo + ox) * p.post_ld + t.n0;
             } else {
               const int hs = p.Ho >> p.post_shift, ws = p.Wo >> p.post_shift;
-              const __nv_bfloat16* post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
-              epi_tile_ts<false, true>(p, tsg, taddr, r, half, k_tiles, valid, silu, sb, nullptr, post, t, y_tile, sbuf);
+              post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
             }
+          }
+          if (p.ts) {
+            const int y_tile = t.y0 + m * p.tile_h;
+            if (has_pre && has_post) epi_tile_ts<true, true>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_pre) epi_tile_ts<true, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_post) epi_tile_ts<false, true>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else epi_tile_ts<false, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
             break;
           }
-          if (p.epi == EPI_BF16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
+                                (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
+          if (has_pre && has_post) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, silu, nullptr, nullptr, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, true>(raw, sb + c * 16, p.act_epi, pre + c * 16, post + c * 16, orow + c * 16);
             });
-          } else if (p.epi == EPI_BF16_PRE) {
-            const int hs = p.Ho >> p.pre_shift, ws = p.Wo >> p.pre_shift;
-            const float* pre = p.pre_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.pre_shift)) * ws + (ox >> p.pre_shift)) * p.pre_ld + t.n0;
+          } else if (has_pre) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, false>(raw, sb + c * 16, silu, pre + c * 16, nullptr, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, false>(raw, sb + c * 16, p.act_epi, pre + c * 16, nullptr, orow + c * 16);
+            });
+          } else if (has_post) {
+            epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, true>(raw, sb + c * 16, p.act_epi, nullptr, post + c * 16, orow + c * 16);
             });
           } else {
-            const int hs = p.Ho >> p.post_shift, ws = p.Wo >> p.post_shift;
-            const __nv_bfloat16* post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, true>(raw, sb + c * 16, silu, nullptr, post + c * 16, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, p.act_epi, nullptr, nullptr, orow + c * 16);
             });
           }
           break;
@@ -921,7 +947,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
               v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
             }
-            if (silu) {
+            if (silu && p.act_epi == kActSiluExact) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+            } else if (silu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
             } else {
@@ -1037,6 +1066,17 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   if (d->src1 != nullptr) {
     GLSDET_REQUIRE(d->src1_c > 0 && d->src1_ld >= d->src1_c && (d->src1_ld % 8) == 0, "conv: bad src1 channels/pitch");
   }
+  if (d->patch_mode) {
+    GLSDET_REQUIRE(d->ksize == 1 && d->src1 == nullptr && (d->batch % 4) == 0,
+                   "conv: patch_mode needs a 1x1 conv, a single source and batch = 4 * images");
+    GLSDET_REQUIRE(d->out_mode == GLSDET_OUT_NHWC_BF16 && d->pre_shift >= 0 && d->post_shift == 0,
+                   "conv: patch_mode writes bf16 NHWC and reads its post residual at full resolution");
+  }
+  if (d->weight_batch_stride != 0) {
+    GLSDET_REQUIRE(d->ksize == 1, "conv: per-image weights are supported for 1x1 convs");
+    GLSDET_REQUIRE((d->weight_batch_stride % 8) == 0 && (d->weight_ld % 8) == 0,
+                   "conv: per-image weight strides must be multiples of 8 elements");
+  }
   g->taps = d->ksize * d->ksize;
   g->chunks0 = (d->src0_c + kChunkK - 1) / kChunkK;
   g->chunks1 = d->src1 ? (d->src1_c + kChunkK - 1) / kChunkK : 0;
@@ -1049,6 +1089,8 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   g->Wo = d->width / d->stride;
   return 0;
 }
+
+constexpr int kPatchView = 3;   // encode_act_map `stride` value selecting the 2x2 patch view
 
 int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B, int H, int W, int stride,
                    int tile_w, int box_rows) {
@@ -1064,6 +1106,13 @@ int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B,
     strides[1] = static_cast<cuuint64_t>(W) * ld * e;
     strides[2] = static_cast<cuuint64_t>(W) * ld * e;
     strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
+  } else if (stride == kPatchView) {
+    // 2x2 patch views of a [B/4, 2H, 2W, ld] tensor: coordinate 2 = px, coordinate 4 = image * 2 + py
+    dims[0] = c_view; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B / 2;
+    strides[0] = static_cast<cuuint64_t>(ld) * e;
+    strides[1] = static_cast<cuuint64_t>(W) * ld * e;
+    strides[2] = static_cast<cuuint64_t>(2) * W * ld * e;
+    strides[3] = static_cast<cuuint64_t>(H) * 2 * W * ld * e;
   } else {
     dims[0] = c_view; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
     strides[0] = static_cast<cuuint64_t>(2) * ld * e;
@@ -1194,7 +1243,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.epi = EPI_GENERIC;
   {
     const bool n16 = (d->out_channels % 16) == 0;
-    const bool act_sr = (d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU);
+    const bool act_sr = (d->act == GLSDET_ACT_SILU || d->act == GLSDET_ACT_RELU || d->act == GLSDET_ACT_NONE);
     const bool bf16_vec = d->out_mode == GLSDET_OUT_NHWC_BF16 && n16 && ((d->out_ld | d->out_coff) % 8) == 0 &&
                           (d->out_batch_stride % 8) == 0;
     const bool small_n = d->out_channels <= 16;
@@ -1204,6 +1253,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
              (reinterpret_cast<uintptr_t>(d->pre_res) & 15) == 0) k.epi = EPI_BF16_PRE;
     else if (bf16_vec && act_sr && !d->pre_res && d->post_res && (d->post_ld % 8) == 0 &&
              (reinterpret_cast<uintptr_t>(d->post_res) & 15) == 0) k.epi = EPI_BF16_POST;
+    else if (bf16_vec && act_sr && d->pre_res && d->post_res && (d->pre_ld % 4) == 0 && (d->post_ld % 8) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->pre_res) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(d->post_res) & 15) == 0) k.epi = EPI_BF16_PREPOST;
     else if (d->out_mode == GLSDET_OUT_NHWC_F32 && d->act == GLSDET_ACT_NONE && n16 && !d->pre_res && !d->post_res &&
              ((d->out_ld | d->out_coff) % 4) == 0 && (d->out_batch_stride % 4) == 0 &&
              (reinterpret_cast<uintptr_t>(d->out) & 15) == 0) k.epi = EPI_F32_PLAIN;
@@ -1219,10 +1271,23 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   }
   // TMA-store epilogue: small-K convs whose epilogue (not the MMAs) paces the kernel
   const bool fused_pred = d->pred_weight != nullptr;
-  bool ts = !two_cta && !fused_pred && (k.epi == EPI_BF16 || k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST) &&
-            (d->out_channels % 64) == 0 && (g.block_n % 64) == 0 && g.k_pad <= 640 &&
+  const bool patch = d->patch_mode != 0;
+  const bool w_batched = d->weight_batch_stride != 0;
+  bool ts = !two_cta && !fused_pred &&
+            (k.epi == EPI_BF16 || k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST || k.epi == EPI_BF16_PREPOST) &&
+            (d->out_channels % 64) == 0 && (g.block_n % 64) == 0 && (g.k_pad <= 640 || patch) &&
             d->out_batch_stride == static_cast<int64_t>(g.Ho) * g.Wo * d->out_ld &&
-            getenv("GLSDET_CONV_NO_TMA_STORE") == nullptr;
+            (getenv("GLSDET_CONV_NO_TMA_STORE") == nullptr || patch);
+  if (patch && !ts) {
+    free(mem);
+    set_error("conv_create: patch_mode needs the TMA-store epilogue (bf16 output, channels a multiple of 64)");
+    return 2;
+  }
+  if ((patch || w_batched) && two_cta) {
+    free(mem);
+    set_error("conv_create: patch_mode / per-image weights are not available in the 2-CTA kernel");
+    return 2;
+  }
   // Fused prediction conv: on the tensor core when the tower width is a multiple of 64 (activated tile staged in
   // shared memory as a bf16 operand), else per-thread FMAs.
   bool pred_mma = fused_pred && !two_cta && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
@@ -1251,7 +1316,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     }
     // resident weights: small K x N (one N block) - the weight traffic per tile disappears
     const int b_total = k.b_chunks * b_tap_bytes;
-    if (g.n_blocks == 1 && b_total <= 96 * 1024 && getenv("GLSDET_CONV_NO_BRES") == nullptr) {
+    if (g.n_blocks == 1 && !w_batched && b_total <= 96 * 1024 && getenv("GLSDET_CONV_NO_BRES") == nullptr) {
       int stages = (budget - b_total) / k.a_bytes;
       if (stages > kMaxStages) stages = kMaxStages;
       if (stages >= 3) {
@@ -1261,7 +1326,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
         return true;
       }
     }
-    if (vreuse && want_bgroup3 && g.block_n <= 128) {
+    if (vreuse && want_bgroup3 && g.block_n <= 128 && !w_batched) {
       const int stages = budget / (k.a_bytes + 3 * b_tap_bytes);
       if (stages >= 3) {
         k.bgroup = 3;
@@ -1287,7 +1352,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     return true;
   };
   const bool want_b3 = getenv("GLSDET_CONV_NO_BGROUP") == nullptr;
-  if (ts && !size_rings(want_b3)) ts = false;   // no room for the staging tiles: direct stores
+  if (ts && !patch && !size_rings(want_b3)) ts = false;   // no room for the staging tiles: direct stores
   if (!size_rings(want_b3)) {
     if (pred_mma) { pred_mma = false; }   // the staged operand does not fit next to the rings: FMA prediction path
     if (!size_rings(want_b3)) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
@@ -1298,8 +1363,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.tmem_cols = cols;
   k.pdl = (!two_cta && getenv("GLSDET_CONV_NO_PDL") == nullptr) ? 1 : 0;
   k.ts = ts ? 1 : 0;
+  k.w_batched = w_batched ? 1 : 0;
+  k.a_shared = d->src_shared > 0 ? d->src_shared : 0;
+  k.patch = patch ? 1 : 0;
 
   k.bias = d->bias; k.act = d->act;
+  k.act_epi = (d->act == GLSDET_ACT_SILU && getenv("GLSDET_CONV_EXACT_SILU") != nullptr) ? kActSiluExact : d->act;
   k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
   k.post_res = reinterpret_cast<const __nv_bfloat16*>(d->post_res); k.post_shift = d->post_shift; k.post_ld = d->post_ld;
   k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
@@ -1311,7 +1380,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
 
   int rc = 0;
   if (d->stride == 1) {
-    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
+    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width,
+                        patch ? kPatchView : 1, best_w, box_rows);
     if (!rc && d->src1)
       rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
     else if (!rc) k.tmA[1] = k.tmA[0];
@@ -1324,18 +1394,24 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   }
   if (!rc && k.ts) {
     const __nv_bfloat16* obase = reinterpret_cast<const __nv_bfloat16*>(d->out) + d->out_coff;
-    rc = encode_act_map(&k.tmO, obase, d->out_channels, d->out_ld, d->batch, g.Ho, g.Wo, 1, best_w, k.tile_h);
+    rc = encode_act_map(&k.tmO, obase, d->out_channels, d->out_ld, d->batch, g.Ho, g.Wo, patch ? kPatchView : 1, best_w,
+                        k.tile_h);
   }
   if (!rc) {
     EncodeTiledFn enc = get_encode_tiled();
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(g.k_pad) * 2};
+    const int w_ld = d->weight_ld > 0 ? d->weight_ld : g.k_pad;
+    if (w_ld < g.k_pad) { set_error("conv_create: weight_ld %d is smaller than the padded K %d", w_ld, g.k_pad); rc = 2; }
+    // shared weights: [n_pad][w_ld]; per-image weights: one more dimension (image), rows beyond N read as zero
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(w_batched ? d->out_channels : g.n_pad),
+                          static_cast<cuuint64_t>(d->batch)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(w_ld) * 2, static_cast<cuuint64_t>(d->weight_batch_stride) * 2};
     const cuuint32_t b_rows = static_cast<cuuint32_t>(op->two_cta ? g.block_n / 2 : g.block_n);
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(kChunkK), b_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->weight), dims, strides, box,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(kChunkK), b_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = rc ? CUDA_ERROR_INVALID_VALUE
+                    : enc(&k.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, w_batched ? 3 : 2, const_cast<void*>(d->weight), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error("cuTensorMapEncodeTiled(weight) failed with CUresult %d", (int)r);
       rc = 2;

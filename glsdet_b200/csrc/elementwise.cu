@@ -360,3 +360,119 @@ extern "C" int glsdet_decode_mmdet(const float* const* cls, const float* const* 
                                                                                                   num_classes, pred);
   return count_launch("decode_mmdet_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------- non-local helpers
+namespace glsdet {
+
+// [B, C, H, W] fp32 -> per-patch transposed bf16 [B*4, rows, t_ld]: row c of patch image b' = (b*2 + py)*2 + px holds
+// the pixels of patch (py, px) in row-major order (t = y' * w2 + x').  This is the K-major operand of the Gram
+// product X^T X (the contraction runs over pixels).  Rows >= C (ones row, zero padding) and columns >= h2*w2 are
+// written once at plan build time and never touched here.  PAIR: one thread per two pixels of a row (needs an even
+// patch width so that a pair never straddles two patches), else one thread per pixel.
+template <bool PAIR>
+__global__ void __launch_bounds__(256) patch_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                              int C, int H, int W, int rows, int t_ld) {
+  const int h2 = H >> 1, w2 = W >> 1;
+  const int b = blockIdx.y;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int per_row = PAIR ? (W >> 1) : W;
+  if (idx >= static_cast<int64_t>(C) * H * per_row) return;
+  const int xp = static_cast<int>(idx % per_row);
+  const int y = static_cast<int>((idx / per_row) % H);
+  const int c = static_cast<int>(idx / (static_cast<int64_t>(per_row) * H));
+  const int x = PAIR ? xp * 2 : xp;
+  const float* s = src + ((static_cast<int64_t>(b) * C + c) * H + y) * W + x;
+  const int py = y >= h2, px = x >= w2;
+  const int bp = (b * 2 + py) * 2 + px;
+  const int t = (y - py * h2) * w2 + (x - px * w2);
+  __nv_bfloat16* o = dst + (static_cast<int64_t>(bp) * rows + c) * t_ld + t;
+  if (PAIR) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(s));
+    *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v.x, v.y);
+  } else {
+    *o = __float2bfloat16_rn(__ldg(s));
+  }
+}
+
+// bias[b'][n] = base[n] + w[b'][n][col]  (the bias column of the per-patch effective weight matrix)
+__global__ void __launch_bounds__(256) gather_bias_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ base,
+                                                          float* __restrict__ bias, int n_rows, int ld, int col,
+                                                          int64_t batch_stride, int base_groups, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = i / n_rows, n = i - b * n_rows;
+  bias[i] = base[(b % base_groups) * n_rows + n] + __bfloat162float(w[static_cast<int64_t>(b) * batch_stride + static_cast<int64_t>(n) * ld + col]);
+}
+
+}  // namespace glsdet
+
+extern "C" int glsdet_patch_transpose(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                                      int32_t width, int32_t dst_rows, int32_t dst_ld, void* stream) {
+  GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0, "patch_transpose: bad arguments");
+  GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "patch_transpose: height and width must be even "
+                 "(equal 2x2 patches; odd splits of Non_local_family.py:230-233 are not supported)");
+  GLSDET_REQUIRE(dst_rows >= channels && dst_ld >= (height / 2) * (width / 2) && (dst_ld % 2) == 0,
+                 "patch_transpose: destination too small");
+  const bool pair = (width % 4) == 0;
+  const int64_t n = static_cast<int64_t>(channels) * height * (pair ? width / 2 : width);
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), batch);
+  if (pair)
+    glsdet::patch_transpose_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, reinterpret_cast<__nv_bfloat16*>(dst), channels, height, width, dst_rows, dst_ld);
+  else
+    glsdet::patch_transpose_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, reinterpret_cast<__nv_bfloat16*>(dst), channels, height, width, dst_rows, dst_ld);
+  return glsdet::count_launch("patch_transpose_kernel");
+}
+
+extern "C" int glsdet_gather_bias(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows,
+                                  int32_t ld, int32_t col, int64_t batch_stride, int32_t base_groups, void* stream) {
+  GLSDET_REQUIRE(w && base && bias && batch > 0 && n_rows > 0 && col >= 0 && col < ld && base_groups > 0,
+                 "gather_bias: bad arguments");
+  const int total = batch * n_rows;
+  glsdet::gather_bias_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w), base, bias, n_rows, ld, col, batch_stride, base_groups, total);
+  return glsdet::count_launch("gather_bias_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------- nearest upsample
+namespace glsdet {
+
+// dst[b, 2y+i, 2x+j, dcoff + c] = src[b, y, x, scoff + c]  (nn.Upsample(scale_factor=2, mode="nearest") into a
+// channel window of a concat buffer).  One thread per (source pixel, 8-channel vector): one 16-byte load, four stores.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         int H, int W, int C, int sld, int scoff, int dld, int dcoff,
+                                                         int64_t total) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int nvec = C >> 3;
+  const int v = static_cast<int>(idx % nvec);
+  int64_t pix = idx / nvec;
+  const int x = static_cast<int>(pix % W);
+  pix /= W;
+  const int y = static_cast<int>(pix % H);
+  const int b = static_cast<int>(pix / H);
+  const uint4 val = __ldg(reinterpret_cast<const uint4*>(src + ((static_cast<int64_t>(b) * H + y) * W + x) * sld + scoff) + v);
+  __nv_bfloat16* o = dst + ((static_cast<int64_t>(b) * 2 * H + 2 * y) * (2 * W) + 2 * x) * dld + dcoff + v * 8;
+  const int64_t row = static_cast<int64_t>(2) * W * dld;
+  *reinterpret_cast<uint4*>(o) = val;
+  *reinterpret_cast<uint4*>(o + dld) = val;
+  *reinterpret_cast<uint4*>(o + row) = val;
+  *reinterpret_cast<uint4*>(o + row + dld) = val;
+}
+
+}  // namespace glsdet
+
+extern "C" int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int32_t height, int32_t width,
+                                 int32_t channels, int32_t src_ld, int32_t src_coff, int32_t dst_ld, int32_t dst_coff,
+                                 void* stream) {
+  GLSDET_REQUIRE(src && dst && batch > 0 && height > 0 && width > 0 && channels > 0, "upsample2x: bad arguments");
+  GLSDET_REQUIRE((channels % 8) == 0 && (src_ld % 8) == 0 && (src_coff % 8) == 0 && (dst_ld % 8) == 0 && (dst_coff % 8) == 0,
+                 "upsample2x: channels, pitches and offsets must be multiples of 8");
+  GLSDET_REQUIRE(src_coff + channels <= src_ld && dst_coff + channels <= dst_ld, "upsample2x: window exceeds pitch");
+  const int64_t total = static_cast<int64_t>(batch) * height * width * (channels / 8);
+  glsdet::upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), height, width, channels, src_ld,
+      src_coff, dst_ld, dst_coff, total);
+  return glsdet::count_launch("upsample2x_kernel");
+}

@@ -1,6 +1,9 @@
 """Execution plans of the YOLOX-drone hot path: PAFPN neck -> (FFA) -> decoupled head -> decode.
 
-Two topologies share one builder:
+Three topologies share one builder:
+  * variant "p1"    - models/new/yolox10.py (GLSDet P1): patch non-local attention on dark3..dark5 in front of the
+                      PAFPN (Non_local_family.py:204-250, evaluated in reassociated form, see _build_nonlocal),
+                      three levels, CSP block on dark2, cross-level cls branch;
   * variant "ffa"   - models/ffa/yolox_ffa.py (GLSDet P0): four levels (strides 4..32), FFA fusion on (P3_out,
                       P4_out), CSP block on dark2, level 0 uses tower index 3;
   * variant "stock" - models/base/yolox.py and, with renamed keys, the mmdet pair YOLOXPAFPN + YOLOXHead
@@ -30,7 +33,8 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import ConvOp, ScaleShuffleOp, SeGateOp, View, fold_bn, nchw_to_nhwc, nhwc_to_nchw
+from .ops import (ConvOp, GatherBiasOp, PatchTransposeOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
+                  nchw_to_nhwc, nhwc_to_nchw)
 
 BN_EPS = 1e-3
 
@@ -54,7 +58,7 @@ class FFAPathPlan:
         self.parts = parts
         self.variant = variant
         self.decode = decode
-        assert variant in ("ffa", "stock") and decode in ("drone", "mmdet")
+        assert variant in ("ffa", "stock", "p1") and decode in ("drone", "mmdet")
         sd = {}
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked"):
@@ -85,11 +89,16 @@ class FFAPathPlan:
             self.hc = sd["head.cls_convs.0.0.conv.weight"].shape[1]
         else:
             self.hc = self.c0
-        self.cd2 = sd["head.csp.conv1.conv.weight"].shape[1] if (variant == "ffa" and "stems" in self.parts) else self.c0 // 2
+        if variant == "ffa" and "stems" in self.parts:
+            self.cd2 = sd["head.csp.conv1.conv.weight"].shape[1]
+        elif variant == "p1" and "stems" in self.parts:
+            self.cd2 = sd["head.csp_feat0.conv1.conv.weight"].shape[1]
+        else:
+            self.cd2 = self.c0 // 2
         for c in (self.c0, self.c1, self.c2, self.cd2, self.hc):
             if c % 16:
                 raise NotImplementedError(f"channel count {c} is not a multiple of 16 (depthwise/nano is not supported)")
-        self.strides = (4, 8, 16, 32) if variant == "ffa" else (8, 16, 32)
+        self.strides = (4, 8, 16, 32) if variant == "ffa" else (8, 16, 32)   # levels of the head outputs
         self.stride_hw = {s: (self.in_h // s, self.in_w // s) for s in (4, 8, 16, 32)}
         self.level_hw = [self.stride_hw[s] for s in self.strides]
         self.num_anchors = sum(h * w for h, w in self.level_hw)
@@ -119,7 +128,10 @@ class FFAPathPlan:
     def _conv(self, ops: List, w, b, srcs, out, k, stride=1, act=None, **kw) -> ConvOp:
         op = ConvOp(srcs, w, b, ksize=k, stride=stride, act=self.act if act is None else act, out=out, **kw)
         ops.append(op)
-        self.flops += op.flops
+        if w is not None:   # the batched products of the non-local block are not part of the reference's conv FLOPs
+            self.flops += op.flops
+        else:
+            self.attn_flops = getattr(self, "attn_flops", 0.0) + op.flops
         return op
 
     def _base_conv(self, ops, p, srcs, out, stride=1, act=None, **kw):
@@ -155,9 +167,15 @@ class FFAPathPlan:
     def _build(self):
         c0, c1, c2, hc = self.c0, self.c1, self.c2, self.hc
         ffa = self.variant == "ffa"
+        p1 = self.variant == "p1"
         d3 = self._buf("dark3", 8, c0)
         d4 = self._buf("dark4", 16, c1)
         d5 = self._buf("dark5", 32, c2)
+        self.pre_loads: List = []   # (input index, op): extra per-input conversions run by load_features
+        raw = (d3, d4, d5)
+        if p1 and "neck" in self.parts:
+            # feat_k + Patch_conv_feat_k(feat_k) replaces dark3..dark5 in front of the PAFPN (yolox10.py:262-266)
+            d3, d4, d5 = (self._buf(f"feat{i + 1}", s_, c_) for i, (s_, c_) in enumerate(((8, c0), (16, c1), (32, c2))))
         cat5 = self._buf("cat5", 32, 2 * c1)              # [bu_conv1(P4_out) | P5]
         cat4 = self._buf("cat4", 16, 2 * c0)              # [bu_conv2(P3_out) | P4]
         catf = self._buf("catf", 8, 2 * c0 if ffa else c0)  # [P3_out | FFA top after PixelShuffle]
@@ -167,17 +185,27 @@ class FFAPathPlan:
         P5 = View(cat5, c1, c1)
         P4 = View(cat4, c0, c0)
         P3o = View(catf, 0, c0)
-        if ffa:
+        if ffa or p1:
             d2 = self._buf("dark2", 4, self.cd2)
-            self.inputs = (d2, d3, d4, d5)
+            self.inputs = (d2,) + raw
             self.neck_out = (View(d2), P3o, View(p4out), View(p5out))
         else:
             self.inputs = (d3, d4, d5)
             self.neck_out = (P3o, View(p4out), View(p5out))
         # per-level head inputs (what mmdet calls the neck outputs after out_convs)
-        self.p = [self._buf(f"p{k}", s, hc) for k, s in enumerate(self.strides)]
+        if p1:   # head inputs x_k live in the first hc channels of the cls-branch concat buffers
+            self.p = []
+        else:
+            self.p = [self._buf(f"p{k}", s, hc) for k, s in enumerate(self.strides)]
         if "neck" in self.parts:
+            if p1:
+                for i, (x, f, s_) in enumerate(zip(raw, (d3, d4, d5), (8, 16, 32))):
+                    self._build_nonlocal(self.neck_ops, f"backbone.Patch_conv_feat{i + 1}", i + 1, x, f, s_)
             self._build_neck(self.neck_ops, d3, d4, d5, cat4, cat5, p5up, p4out, p5out, P5, P4, P3o)
+        if p1:
+            if "stems" in self.parts or "towers" in self.parts:
+                self._build_p1_head(self._bufs["dark2"], P3o, p4out, p5out)
+            return
         if "stems" in self.parts:
             if ffa:
                 self._build_ffa_stems(self.stem_ops, self._bufs["dark2"], catf, p4out, p5out, P3o)
@@ -225,6 +253,123 @@ class FFAPathPlan:
         self._base_conv(hd, "head.stems.0", [P3o], View(p[1]))
         self._base_conv(hd, "head.stems.1", [View(p4out)], View(p[2]))
         self._base_conv(hd, "head.stems.2", [View(p5out)], View(p[3]))
+
+    def _build_nonlocal(self, ops, p: str, in_idx: int, x: torch.Tensor, out: torch.Tensor, stride: int):
+        """out = x + channel_conv(retile(non_local(patch)))  -  Patch_Conv_NonLocal_new.forward
+        (models/new/Non_local_family.py:229-250) + the residual of yolox10.py:262-266, with each Non_local_Block (:32-48,
+        dot-product mode, no softmax) reassociated:  y = (theta^T phi / T) g = theta (phi^T g / T), hence
+            block(X) = X + X W_eff^T + 1 b_eff^T,   W_eff = (Wo G / T) S (Phi^T Wtheta),   b_eff = (Wo G / T) S Phi^T btheta + bo
+        with S = [X | 1]^T [X | 1] the Gram matrix of the patch (pixels x channels, plus a ones column that carries the
+        conv biases), G = [Wg | bg], Phi = [Wphi | bphi].  O(T C^2) instead of O(T^2 C), no [T, T] intermediate.
+        Everything is the tcgen05 conv kernel with per-image weight matrices:
+          S = Xt Xt^T (Xt = per-patch transposed copy of the input, ones row appended), Z^T = A2'^T S, W = A1 Z, then
+          a 1x1 conv over the patch with weights W[:, :C], bias column W[:, C] + bo, and the input as residual.
+        Patch images are ordered b' = (b*2 + py)*2 + px; position (py, px) = lt (0,0), rt (0,1), lb (1,0), rb (1,1)."""
+        sd, dev = self.sd, self.device
+        B, H, W_, C = x.shape
+        if H % 2 or W_ % 2:
+            raise NotImplementedError("non-local patches need an even height and width at every level, i.e. an input "
+                                      "size that is a multiple of 64 (unequal 2x2 splits, Non_local_family.py:230-233, "
+                                      "are not supported)")
+        T = (H // 2) * (W_ // 2)
+        Tp = (T + 63) // 64 * 64
+        Ca = C + 64
+        Bp = 4 * B
+        xt = torch.zeros((Bp, Ca, Tp), dtype=torch.bfloat16, device=dev)
+        xt[:, C, :T] = 1.0
+        self._bufs[p + ".xt"] = xt
+        self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
+        a1 = torch.zeros((4, C, Ca), dtype=torch.float64, device=dev)
+        a2t = torch.zeros((4, Ca, Ca), dtype=torch.float64, device=dev)
+        bo = torch.zeros((4, C), dtype=torch.float32, device=dev)
+        for i, pos in enumerate(("lt", "rt", "lb", "rb")):
+            q = f"{p}.feat_patchconv_{pos}_nonlocal."
+            wg, wt, wp, wo = (sd[q + n + ".weight"].double().flatten(1) for n in ("g", "theta", "phi", "conv_out"))
+            bg, bt, bp = (sd[q + n + ".bias"].double() for n in ("g", "theta", "phi"))
+            G = torch.cat([wg, bg[:, None]], 1)          # [Ci, C+1]
+            Phi = torch.cat([wp, bp[:, None]], 1)        # [Ci, C+1]
+            a1[i, :, :C + 1] = wo @ G / T                # [C, C+1]
+            a2 = Phi.t() @ torch.cat([wt, bt[:, None]], 1)   # [C+1, C+1]: columns 0..C-1 -> W_eff, column C -> b_eff - bo
+            a2t[i, :C + 1, :C + 1] = a2.t()
+            bo[i] = sd[q + "conv_out.bias"].float()
+        a1 = a1.to(torch.bfloat16).view(4, 1, C, Ca).contiguous()
+        a2t = a2t.to(torch.bfloat16).view(4, 1, Ca, Ca).contiguous()
+        S = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
+        Zt = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
+        Wm = torch.empty((Bp, 1, C, Ca), dtype=torch.bfloat16, device=dev)
+        bias = torch.empty((Bp, 1, 1, C), dtype=torch.float32, device=dev)
+        none = N.ACT_NONE
+        # S[c][c'] = sum_t Xt[c][t] Xt[c'][t]
+        self._conv(ops, None, None, [View(xt.view(Bp, 1, Ca, Tp))], View(S), 1, act=none, weight_raw=xt, n_out=Ca)
+        # Zt[k][i] = sum_j A2'[j][k] S[i][j]
+        self._conv(ops, None, None, [View(a2t)], View(Zt), 1, act=none, weight_raw=S.view(Bp, Ca, Ca), n_out=Ca,
+                   src_shared=4, batch=Bp)
+        # W[n][k] = sum_i A1[n][i] Z[i][k]
+        self._conv(ops, None, None, [View(a1)], View(Wm), 1, act=none, weight_raw=Zt.view(Bp, Ca, Ca), n_out=Ca,
+                   src_shared=4, batch=Bp)
+        gb = GatherBiasOp(Wm.view(Bp, C, Ca), bo, bias, C)
+        ops.append(gb)
+        nl = self._buf(p + ".nl", stride, C)
+        self._conv(ops, None, None, [View(x)], View(nl), 1, act=none, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
+                   patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
+        self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
+        self._keepalive = getattr(self, "_keepalive", []) + [a1, a2t, bo, S, Zt, Wm, bias]
+
+    def _build_p1_head(self, d2, P3o, p4out, p5out):
+        """models/new/yolox10.py:70-158.  Level k (strides 8/16/32): x_k = stems[k](P_k); cls branch input
+        cat([x_k, up_convs[k](level below), upsample(x_{k+1})]) (the top level has no upsampled part); reg branch
+        input x_k.  The concat buffers are written in place by the producers; the prediction convs are fused into the
+        second tower convs as in the other variants."""
+        hc, nc, sd = self.hc, self.nc, self.sd
+        nch = 5 + nc
+        st, tw = self.stem_ops, self.tower_ops
+        f0 = self._buf("p1_f0", 4, hc)
+        cat = [self._buf(f"p1_cat{k}", s_, (3 if k < 2 else 2) * hc) for k, s_ in enumerate((8, 16, 32))]
+        xs = [View(c, 0, hc) for c in cat]
+        self.p = cat
+        if "stems" in self.parts:
+            self._csp(st, "head.csp_feat0", 4, View(d2), View(f0), x_name="hcsp")
+            for k, src in enumerate((P3o, View(p4out), View(p5out))):
+                self._base_conv(st, f"head.stems.{k}", [src], xs[k])
+            for k, s_ in enumerate((8, 16, 32)):
+                lower = View(f0) if k == 0 else xs[k - 1]
+                tmp = self._buf(f"p1_up{k}", s_ // 2, hc)
+                self._base_conv(st, f"head.up_convs.{k}.0", [lower], View(tmp))
+                self._base_conv(st, f"head.up_convs.{k}.1", [View(tmp)], View(cat[k], hc, hc), stride=2)
+                if k < 2:
+                    st.append(Upsample2xOp(xs[k + 1], View(cat[k], 2 * hc, hc)))
+        if "towers" not in self.parts:
+            return
+        self.logits = [torch.empty((self.B, nch, h, w), dtype=torch.float32, device=self.device) for h, w in self.level_hw]
+        self.pred = torch.empty((self.B, self.num_anchors, nch), dtype=torch.float32, device=self.device)
+        box_act = N.ACT_YOLOX_BOX if self.decode == "drone" else N.ACT_MMDET_BOX
+        a_off = 0
+        for k, (h, w) in enumerate(self.level_hw):
+            s_ = self.strides[k]
+            m = 3 if k < 2 else 2
+            tc = self._buf(f"p1_tc{k}", s_, m * hc)
+            tr = self._buf(f"p1_tr{k}", s_, hc)
+            self._base_conv(tw, f"head.cls_convs.{k}.0", [View(cat[k])], View(tc))
+            self._base_conv(tw, f"head.reg_convs.{k}.0", [xs[k]], View(tr))
+            wc1, bc1 = self._folded(f"head.cls_convs.{k}.1")
+            wr1, br1 = self._folded(f"head.reg_convs.{k}.1")
+            w_ro = torch.cat([sd[f"head.reg_preds.{k}.weight"], sd[f"head.obj_preds.{k}.weight"]], 0).float()
+            b_ro = torch.cat([sd[f"head.reg_preds.{k}.bias"], sd[f"head.obj_preds.{k}.bias"]], 0).float()
+            w_cl, b_cl = sd[f"head.cls_preds.{k}.weight"].float(), sd[f"head.cls_preds.{k}.bias"].float()
+            kw = dict(out_mode=N.OUT_NCHW_F32, out_ld=nch, out_batch_stride=nch * h * w)
+            self._conv(self.pred_raw_ops, wr1, br1, [View(tr)], self.logits[k], 3, out_coff=0, pred_weight=w_ro,
+                       pred_bias=b_ro, pred_act=N.ACT_NONE, **kw)
+            self._conv(self.pred_raw_ops, wc1, bc1, [View(tc)], self.logits[k], 3, out_coff=5, pred_weight=w_cl,
+                       pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
+            stride = float(self.in_h / h)
+            kw = dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch)
+            self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred, 3, out_coff=a_off * nch, pred_weight=w_ro,
+                       pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
+            self._conv(self.pred_dec_ops, wc1, bc1, [View(tc)], self.pred, 3, out_coff=a_off * nch + 5, pred_weight=w_cl,
+                       pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
+            a_off += h * w
+        self.flops -= sum(op.flops for op in self.pred_dec_ops)
+        self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
 
     def _build_towers(self):
         """Towers + predictions: yolox_ffa.py:76-117 (level 0 uses tower index 3) / base/yolox.py / mmdet
@@ -275,6 +420,8 @@ class FFAPathPlan:
         assert len(feats) == len(self.inputs), (len(feats), len(self.inputs))
         for src, dst in zip(feats, self.inputs):
             nchw_to_nhwc(src.contiguous(), View(dst), stream)
+        for idx, op in self.pre_loads:
+            op.launch(feats[idx].contiguous(), stream)
 
     def load_head_inputs(self, inputs: Sequence[torch.Tensor], stream=None) -> None:
         """The tuple YOLOPAFPN.forward returns (NCHW fp32) -> internal buffers."""
@@ -338,8 +485,8 @@ class FFAPathPlan:
 
     def num_launches(self, decoded: bool) -> int:
         se = sum(1 for op in self.stem_ops if isinstance(op, SeGateOp))  # two kernels per SE gate
-        return (len(self.inputs) + len(self.neck_ops) + len(self.stem_ops) + se + len(self.tower_ops) +
-                len(self.pred_dec_ops if decoded else self.pred_raw_ops))
+        return (len(self.inputs) + len(self.pre_loads) + len(self.neck_ops) + len(self.stem_ops) + se +
+                len(self.tower_ops) + len(self.pred_dec_ops if decoded else self.pred_raw_ops))
 
     def buffer(self, name: str) -> torch.Tensor:
         return self._bufs[name]

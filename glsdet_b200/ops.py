@@ -73,13 +73,23 @@ class ConvOp:
                  out_coff: int = 0, out_batch_stride: int = 0, pre_res: Optional[View] = None, pre_shift: int = 0,
                  post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0),
                  pred_weight: Optional[torch.Tensor] = None, pred_bias: Optional[torch.Tensor] = None,
-                 pred_act: int = N.ACT_NONE):
+                 pred_act: int = N.ACT_NONE, weight_raw: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
+                 src_shared: int = 0, patch_mode: bool = False, batch: Optional[int] = None):
+        """`weight_raw`: a bf16 device matrix [N rows, pitch] (shared) or [batch, N rows, pitch] (one per image) used
+        as is (the batched products of the non-local block); `src_shared` = k > 0: srcs[0] holds k static matrices and image b reads matrix b mod k;
+        `patch_mode`: srcs[0] / post_res / out are [B, H, W, .] tensors processed as their 4*B 2x2 patches."""
         lib = N.load()
         assert 1 <= len(srcs) <= 2
         b, h, w = srcs[0].bhw
         for s in srcs:
             assert s.bhw == (b, h, w) and s.t.dtype == torch.bfloat16
-        n_out = weight.shape[0]
+        if patch_mode:
+            assert h % 2 == 0 and w % 2 == 0 and ksize == 1
+            b, h, w = 4 * b, h // 2, w // 2
+        if src_shared:
+            assert b == src_shared and batch is not None
+            b = batch
+        n_out = weight.shape[0] if weight_raw is None else n_out
         d = N.ConvDesc()
         d.src0, d.src0_c, d.src0_ld = srcs[0].ptr, srcs[0].c, srcs[0].ld
         if len(srcs) == 2:
@@ -92,21 +102,38 @@ class ConvOp:
         N.check(lib.glsdet_conv_weight_shape(C.byref(d), C.byref(n_pad), C.byref(k_pad), C.byref(block_n)),
                 "glsdet_conv_weight_shape")
         self.block_n = block_n.value
-        self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value)
+        if weight_raw is None:
+            self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value)
+        else:
+            assert weight_raw.dtype == torch.bfloat16 and weight_raw.is_contiguous() and ksize == 1
+            assert weight_raw.shape[-1] >= k_pad.value and weight_raw.shape[-2] >= n_out, (weight_raw.shape, k_pad.value)
+            self.packed = weight_raw
+            d.weight_ld = weight_raw.shape[-1]
+            if weight_raw.dim() == 3:
+                assert weight_raw.shape[0] == b, (weight_raw.shape, b)
+                d.weight_batch_stride = weight_raw.shape[1] * weight_raw.shape[2]
+        d.src_shared = int(src_shared)
+        d.patch_mode = 1 if patch_mode else 0
         self.bias = None if bias is None else bias.detach().float().contiguous()
         d.weight = self.packed.data_ptr()
         d.bias = 0 if self.bias is None else self.bias.data_ptr()
         ho, wo = h // stride, w // stride
         if pre_res is not None:
             assert pre_res.t.dtype == torch.float32
-            assert pre_res.bhw == (b, ho >> pre_shift, wo >> pre_shift), (pre_res.bhw, b, ho, wo, pre_shift)
+            assert pre_res.bhw == (b, max(ho >> pre_shift, 1), max(wo >> pre_shift, 1)), (pre_res.bhw, b, ho, wo, pre_shift)
             d.pre_res, d.pre_shift, d.pre_ld = pre_res.ptr, pre_shift, pre_res.ld
         if post_res is not None:
             assert post_res.t.dtype == torch.bfloat16
-            assert post_res.bhw == (b, ho >> post_shift, wo >> post_shift)
+            if patch_mode:
+                assert post_res.bhw == (b // 4, 2 * ho, 2 * wo) and post_shift == 0
+            else:
+                assert post_res.bhw == (b, ho >> post_shift, wo >> post_shift)
             d.post_res, d.post_shift, d.post_ld = post_res.ptr, post_shift, post_res.ld
         if isinstance(out, View):
-            assert out.bhw == (b, ho, wo) and (out.c >= n_out or pred_weight is not None)
+            if patch_mode:
+                assert out.bhw == (b // 4, 2 * ho, 2 * wo) and out.c >= n_out
+            else:
+                assert out.bhw == (b, ho, wo) and (out.c >= n_out or pred_weight is not None)
             d.out, d.out_ld, d.out_coff = out.t.data_ptr(), out.ld, out.coff
             d.out_batch_stride = ho * wo * out.ld
             d.out_mode = N.OUT_NHWC_BF16 if out.t.dtype == torch.bfloat16 else N.OUT_NHWC_F32
@@ -124,7 +151,7 @@ class ConvOp:
             self.pred_bias = pred_bias.detach().float().contiguous()
             d.pred_weight, d.pred_bias = self.pred_weight.data_ptr(), self.pred_bias.data_ptr()
             d.pred_channels, d.pred_act = self.pred_weight.shape[0], pred_act
-        self._keep = (srcs, pre_res, post_res)
+        self._keep = (srcs, pre_res, post_res, weight_raw)
         self.desc = d
         self.handle = C.c_void_p()
         N.check(lib.glsdet_conv_create(C.byref(d), C.byref(self.handle)), "glsdet_conv_create")
@@ -209,3 +236,55 @@ class _Call:
 
     def launch(self, stream=None):
         self.fn(*self.args, stream=stream)
+
+
+class PatchTransposeOp:
+    """NCHW fp32 map -> per-patch transposed bf16 matrices [4B, rows, t_ld] (Gram operand of the non-local block)."""
+
+    def __init__(self, dst: torch.Tensor, channels: int, height: int, width: int):
+        assert dst.dtype == torch.bfloat16 and dst.dim() == 3 and dst.is_contiguous()
+        self.dst, self.c, self.h, self.w = dst, channels, height, width
+        self._lib = N.load()
+
+    def launch(self, src: torch.Tensor, stream=None):
+        assert src.dtype == torch.float32 and src.is_contiguous() and src.is_cuda
+        b = src.shape[0]
+        assert tuple(src.shape) == (b, self.c, self.h, self.w) and self.dst.shape[0] == 4 * b
+        N.check(self._lib.glsdet_patch_transpose(src.data_ptr(), self.dst.data_ptr(), b, self.c, self.h, self.w,
+                                                 self.dst.shape[1], self.dst.shape[2], N.stream_ptr(stream)),
+                "glsdet_patch_transpose")
+
+
+class GatherBiasOp:
+    """bias[b][n] = base[b mod groups][n] + w[b][n][col]."""
+
+    def __init__(self, w: torch.Tensor, base: torch.Tensor, bias: torch.Tensor, col: int):
+        assert w.dtype == torch.bfloat16 and w.dim() == 3 and w.is_contiguous()
+        assert base.dtype == torch.float32 and bias.dtype == torch.float32 and base.is_contiguous()
+        self.w, self.base, self.bias, self.col = w, base, bias, col
+        self.groups = base.shape[0]
+        assert base.shape[1] == w.shape[1] and bias.numel() == w.shape[0] * w.shape[1]
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        w = self.w
+        N.check(self._lib.glsdet_gather_bias(w.data_ptr(), self.base.data_ptr(), self.bias.data_ptr(), w.shape[0],
+                                             w.shape[1], w.shape[2], self.col, w.shape[1] * w.shape[2], self.groups,
+                                             N.stream_ptr(stream)), "glsdet_gather_bias")
+
+
+class Upsample2xOp:
+    """dst window = nearest 2x upsampling of the src window (NHWC bf16)."""
+
+    def __init__(self, src: View, dst: View):
+        b, h, w = src.bhw
+        assert dst.bhw == (b, 2 * h, 2 * w) and dst.c == src.c
+        assert src.t.dtype == torch.bfloat16 and dst.t.dtype == torch.bfloat16
+        self.src, self.dst = src, dst
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        s, d = self.src, self.dst
+        b, h, w = s.bhw
+        N.check(self._lib.glsdet_upsample2x(s.t.data_ptr(), d.t.data_ptr(), b, h, w, s.c, s.ld, s.coff, d.ld, d.coff,
+                                            N.stream_ptr(stream)), "glsdet_upsample2x")

@@ -58,6 +58,28 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
     csp("backbone.C3_n4", 2 * c1, c2, n)
 
     hc = int(256 * width)
+    if variant == "p1":   # models/new/yolox10.py: patch non-local blocks in the neck, cross-level cls branch (App. C)
+        for i, c in ((1, c0), (2, c1), (3, c2)):
+            q = f"backbone.Patch_conv_feat{i}"
+            for pos in ("lt", "lb", "rt", "rb"):
+                for name in ("g", "theta", "phi", "conv_out"):
+                    shapes[f"{q}.feat_patchconv_{pos}_nonlocal.{name}.weight"] = (c, c, 1, 1)
+                    shapes[f"{q}.feat_patchconv_{pos}_nonlocal.{name}.bias"] = (c,)
+            bc(q + ".channel_conv", c, c, 3)
+        csp("head.csp_feat0", int(0.5 * 256 * width), hc, round(3 * 0.75))
+        for i, cin in enumerate((c0, c1, c2)):
+            bc(f"head.stems.{i}", cin, hc, 1)
+            bc(f"head.up_convs.{i}.0", hc, hc, 3)
+            bc(f"head.up_convs.{i}.1", hc, hc, 3)
+            m = 2 if i == 2 else 3
+            bc(f"head.cls_convs.{i}.0", m * hc, m * hc, 3)
+            bc(f"head.cls_convs.{i}.1", m * hc, hc, 3)
+            bc(f"head.reg_convs.{i}.0", hc, hc, 3)
+            bc(f"head.reg_convs.{i}.1", hc, hc, 3)
+            for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
+                shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
+                shapes[f"head.{name}.{i}.bias"] = (co,)
+        return shapes
     if variant == "stock":   # models/base/yolox.py: three levels, stems on (P3_out, P4_out, P5_out), no FFA
         for i, cin in enumerate((c0, c1, c2)):
             bc(f"head.stems.{i}", cin, hc, 1)
@@ -150,6 +172,11 @@ def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str
                          "running_var": 0.9 + 0.2 * torch.rand(shp, generator=g)}[part]
         elif ".fc." in k:
             sd[k] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
+        elif "_nonlocal." in k:   # plain nn.Conv2d 1x1 with bias (Non_local_family.py:15-18)
+            if part == "weight":
+                sd[k] = torch.randn(shp, generator=g) * (0.02 if flavour == "reference" else math.sqrt(1.0 / shp[1]))
+            else:
+                sd[k] = torch.randn(shp, generator=g) * (0.02 if flavour == "reference" else 0.1)
         elif "_preds." in k and part == "weight":
             if flavour == "reference":
                 sd[k] = torch.randn(shp, generator=g) * 0.02

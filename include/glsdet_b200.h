@@ -103,6 +103,19 @@ typedef struct glsdet_conv_desc {
   const float* pred_bias;    /* fp32 [pred_channels] */
   int32_t pred_channels;
   int32_t pred_act;
+  /*
+   * Batched-GEMM extensions.  They carry Non_local_Block (yolox-drone/models/new/Non_local_family.py:6-48) and
+   * Patch_Conv_NonLocal_new (:204-250) in the reassociated form  out = x + W_eff(b, patch) x + b_eff(b, patch)
+   * (DESIGN.md section 3.4): the Gram matrix of a patch, the two C x C products that turn it into W_eff and the
+   * final per-patch 1x1 conv are all this operator with a weight matrix PER IMAGE.
+   */
+  int64_t weight_batch_stride; /* elements between the weight matrices of consecutive images; 0 = one shared matrix */
+  int32_t weight_ld;           /* row pitch of the weight matrix in elements; 0 = k_pad */
+  int32_t src_shared;          /* k > 0: image b reads image (b mod k) of src0 (k static matrices used as activations,
+                                  e.g. one per patch position) */
+  int32_t patch_mode;          /* 1 (1x1 convs): src0, post_res and out are the 2x2 patch views of
+                                  [batch/4, 2*height, 2*width, ld] tensors; image b' = (b*2 + py)*2 + px is patch
+                                  (py, px) of image b (the split of Non_local_family.py:230-233) */
 } glsdet_conv_desc;
 
 /* library / device */
@@ -122,6 +135,29 @@ int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int
                                  int32_t width, int32_t dst_ld, int32_t dst_coff, void* stream);
 int glsdet_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels, int32_t height,
                                  int32_t width, int32_t src_ld, int32_t src_coff, void* stream);
+
+/*
+ * Non-local helpers (yolox-drone/models/new/Non_local_family.py:32-48, 229-250).
+ * glsdet_patch_transpose: the four 2x2 patches of an NCHW fp32 map (split of :230-233, equal halves only) as
+ *   per-patch transposed bf16 matrices dst[(b*2+py)*2+px][c][t], t = y'*(W/2) + x', row pitch dst_ld, dst_rows rows
+ *   per patch (rows >= channels - the ones row that yields the channel sums, zero padding - are the caller's).
+ *   This is the K-major operand of the Gram product X^T X that replaces theta^T phi / T followed by (.) g.
+ * glsdet_gather_bias: bias[b][n] = base[b mod base_groups][n] + w[b][n][col] for a bf16 matrix batch (row pitch
+ *   ld): the per-patch effective bias W_o M^T b_theta + b_o of conv_out(y) (:45-46); base holds b_o of the
+ *   base_groups (= 4) patch positions.
+ */
+int glsdet_patch_transpose(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                           int32_t width, int32_t dst_rows, int32_t dst_ld, void* stream);
+int glsdet_gather_bias(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows, int32_t ld,
+                       int32_t col, int64_t batch_stride, int32_t base_groups, void* stream);
+
+/*
+ * nn.Upsample(scale_factor=2, mode="nearest") of an NHWC bf16 channel window into a channel window of a concat
+ * buffer (yolox-drone/models/new/yolox10.py:95,97: the upsampled neighbour level inside the cls-branch concat, where a
+ * 3x3 conv follows, so the upsampling cannot be folded into the conv as it is for the 1x1 convs of the neck).
+ */
+int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int32_t height, int32_t width, int32_t channels,
+                      int32_t src_ld, int32_t src_coff, int32_t dst_ld, int32_t dst_coff, void* stream);
 
 /*
  * SE gate of FFA (yolox-drone/models/ffa/ffa.py:5-20,77): partial[b][p][c] = sum over a slab of pixels of

@@ -201,6 +201,76 @@ def neck_head_bf16(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.T
         _EMULATE_BF16 = False
 
 
+# ------------------------------------------------------------------------------------------ P1: models/new/yolox10.py
+def non_local_block(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+    """models/new/Non_local_family.py:32-48 (dot_product mode, :27-30): g / theta / phi / conv_out are 1x1 convs WITH
+    bias and no BN; pairwise = theta^T phi / T with T = H*W (the divisor is pairwise.shape[-1], :29); no softmax."""
+    n, _, h, w = x.shape
+    ci = sd[p + ".g.weight"].shape[0]
+    g_x = F.conv2d(_q(x), _q(sd[p + ".g.weight"]), sd[p + ".g.bias"]).view(n, ci, -1).permute(0, 2, 1)          # [N, T, Ci]
+    theta_x = F.conv2d(_q(x), _q(sd[p + ".theta.weight"]), sd[p + ".theta.bias"]).view(n, ci, -1).permute(0, 2, 1)
+    phi_x = F.conv2d(_q(x), _q(sd[p + ".phi.weight"]), sd[p + ".phi.bias"]).view(n, ci, -1)                     # [N, Ci, T]
+    pairwise = torch.matmul(theta_x, phi_x)
+    pairwise = pairwise / pairwise.shape[-1]                                                                    # :29
+    y = torch.matmul(pairwise, g_x).permute(0, 2, 1).reshape(n, ci, h, w)                                       # :44-45
+    return x + F.conv2d(y, _q(sd[p + ".conv_out.weight"]), sd[p + ".conv_out.bias"])                            # :46
+
+
+def patch_conv_nonlocal_new(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+    """models/new/Non_local_family.py:229-250: 2x2 patch split at int(H/2), int(W/2) (:230-233), one non-local block
+    per patch, re-tile (:240-247), then channel_conv = 3x3 BaseConv + SiLU (channel_cat='non_linear', :224-227)."""
+    h2, w2 = int(x.shape[2] / 2), int(x.shape[3] / 2)
+    lt = non_local_block(sd, p + ".feat_patchconv_lt_nonlocal", x[:, :, :h2, :w2])
+    lb = non_local_block(sd, p + ".feat_patchconv_lb_nonlocal", x[:, :, h2:, :w2])
+    rt = non_local_block(sd, p + ".feat_patchconv_rt_nonlocal", x[:, :, :h2, w2:])
+    rb = non_local_block(sd, p + ".feat_patchconv_rb_nonlocal", x[:, :, h2:, w2:])
+    y = torch.cat((torch.cat((lt, rt), dim=3), torch.cat((lb, rb), dim=3)), dim=2)
+    return base_conv(sd, p + ".channel_conv", _q(y))
+
+
+def p1_neck(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "backbone") -> List[torch.Tensor]:
+    """models/new/yolox10.py:259-335 after the backbone call: feat_k + Patch_conv_feat_k(feat_k) for dark3..dark5
+    (:262-266), then the same PAFPN as pafpn_neck; returns (feat0, P3_out, P4_out, P5_out) (:335)."""
+    feat0, feat1, feat2, feat3 = feats
+    feat1 = _q(feat1 + patch_conv_nonlocal_new(sd, f"{p}.Patch_conv_feat1", feat1))
+    feat2 = _q(feat2 + patch_conv_nonlocal_new(sd, f"{p}.Patch_conv_feat2", feat2))
+    feat3 = _q(feat3 + patch_conv_nonlocal_new(sd, f"{p}.Patch_conv_feat3", feat3))
+    return pafpn_neck(sd, [feat0, feat1, feat2, feat3], p)
+
+
+def p1_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -> List[torch.Tensor]:
+    """models/new/yolox10.py:70-158: csp_feat0 on dark2, stems on (P3_out, P4_out, P5_out); the cls branch of level k
+    sees cat([x_k, up_convs[k](level below), upsample(x_{k+1})]) (:93-99; the top level has no upsampled input); the
+    reg branch sees x_k alone (:139); output cat([reg, obj, cls], 1) (:156)."""
+    f0 = csp_layer(sd, f"{p}.csp_feat0", inputs[0])                                                    # :83
+    xs = [base_conv(sd, f"{p}.stems.{k}", inputs[k + 1]) for k in range(3)]                            # :86
+    outs = []
+    for k, x in enumerate(xs):
+        lower = f0 if k == 0 else xs[k - 1]
+        down = base_conv(sd, f"{p}.up_convs.{k}.1", base_conv(sd, f"{p}.up_convs.{k}.0", lower), stride=2)
+        parts = [x, down] + ([_up2(xs[k + 1])] if k < 2 else [])
+        cf = torch.cat(parts, 1)
+        cf = base_conv(sd, f"{p}.cls_convs.{k}.1", base_conv(sd, f"{p}.cls_convs.{k}.0", cf))
+        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"]), sd[f"{p}.cls_preds.{k}.bias"])
+        rf = base_conv(sd, f"{p}.reg_convs.{k}.1", base_conv(sd, f"{p}.reg_convs.{k}.0", x))
+        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"]), sd[f"{p}.reg_preds.{k}.bias"])
+        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"]), sd[f"{p}.obj_preds.{k}.bias"])
+        outs.append(torch.cat([reg_out, obj_out, cls_out], 1))
+    return outs
+
+
+def p1_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+    """models/new/yolox10.py YoloBody.forward (:339-345) minus the CSPDarknet call; `bf16` = storage-precision
+    emulation as in neck_head_bf16."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = bf16
+    try:
+        with torch.no_grad():
+            return p1_head(sd, p1_neck(sd, [_q(f) for f in feats]))
+    finally:
+        _EMULATE_BF16 = False
+
+
 # ------------------------------------------------------------------------------------------ backbone (upstream)
 def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
     """models/ffa/darknet.py:10-37,115-195.  Upstream of the measured path; restated only so that synthetic

@@ -127,6 +127,58 @@ def run_stock_case(ub, name, phi, nc, seed, batch, in_h, in_w, conf, nms_thr):
     return meta, key_shapes
 
 
+def run_p1_case(ub, name, phi, nc, seed, batch, in_h, in_w, conf, nms_thr):
+    """GLSDet P1 (models/new/yolox10.py: patch non-local neck + cross-level head).  Import shim D2 (SURVEY.md section
+    0.2): yolox10.py imports `models.decouple.darknet`, which does not exist; `models.new.darknet` is the identical
+    file (same bytes as models/ffa/darknet.py) and is aliased to that name."""
+    import types
+
+    import models.new.darknet as dk
+
+    sys.modules.setdefault("models.decouple", types.ModuleType("models.decouple"))
+    sys.modules["models.decouple.darknet"] = dk
+    import models.new.yolox10 as y10
+    from oracle import ref_path
+
+    sd = ref_path.synthetic_state_dict(nc, phi, seed=seed, flavour="calibrated", variant="p1")
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = y10.YoloBody(nc, phi).eval()
+    net.load_state_dict(sd, strict=True)
+    key_shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    width = {"tiny": 0.375, "s": 0.5, "m": 0.75, "l": 1.0}[phi]
+    chans = [int(c * width) for c in (128, 256, 512, 1024)]
+    feats = seeded_feats(seed + 100, batch, in_h, in_w, chans)
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return dict(zip(("dark2", "dark3", "dark4", "dark5"), feats))
+
+    net.backbone.backbone = Stub()
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        neck_out = net.backbone(torch.zeros(batch, 3, in_h, in_w))
+        logits = net.head(neck_out)
+        pred = ub.decode_outputs([o.clone() for o in logits], [in_h, in_w]).contiguous()
+        results = ub.non_max_suppression(pred.clone(), nc, [in_h, in_w], np.array([in_h, in_w]), False,
+                                         conf_thres=conf, nms_thres=nms_thr)
+        # one stand-alone non-local block and patch module, for the unit-level pins
+        pc = net.backbone.Patch_conv_feat2
+        nl_lt = pc.feat_patchconv_lt_nonlocal(feats[2][:, :, :feats[2].shape[2] // 2, :feats[2].shape[3] // 2])
+        pc_out = pc(feats[2])
+    out = {f"feat{i}": f.numpy() for i, f in enumerate(feats)}
+    out.update({f"neck{i}": t.numpy() for i, t in enumerate(neck_out)})
+    out.update({f"logits{i}": t.numpy() for i, t in enumerate(logits)})
+    out["pred"] = pred.numpy()
+    out["nonlocal_lt_feat2"] = nl_lt.numpy()
+    out["patchconv_feat2"] = pc_out.numpy()
+    for i, r in enumerate(results):
+        out[f"nms{i}"] = r if r is not None else np.zeros((0, 7), np.float32)
+    meta = dict(name=name, phi=phi, nc=nc, seed=seed, batch=batch, in_h=in_h, in_w=in_w, conf=conf, nms_thr=nms_thr,
+                weight_checksum=weight_checksum(sd), n_keys=len(sd), kept=[int(len(out[f"nms{i}"])) for i in range(batch)])
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, meta["kept"], meta["weight_checksum"])
+    return meta, key_shapes
+
+
 def clustered_boxes(rng, k, nc, normalised=True, ties=False):
     g = max(4, k // 12)
     cen = rng.uniform(0.05, 0.95, (g, 2))
@@ -202,6 +254,13 @@ def main():
     os.environ["PYTHONDONTWRITEBYTECODE"] = "1"
     torch.set_num_threads(8)
     yf, ub = import_reference()
+    if "--only-p1" in sys.argv:   # add / refresh the P1 vectors without touching the other files
+        metas = json.loads((HERE / "meta.json").read_text())
+        mp, keys_p1 = run_p1_case(ub, "p1_s_calibrated", "s", 10, 0, 1, 128, 192, 0.01, 0.65)
+        metas["p1"] = mp
+        (HERE / "state_dict_keys_p1_s.json").write_text(json.dumps(keys_p1, indent=0))
+        (HERE / "meta.json").write_text(json.dumps(metas, indent=1))
+        return
     metas = {}
     m1, keys = run_model_case(yf, ub, "p0_s_calibrated", "s", 10, "calibrated", 1, 2, 64, 96, 0.01, 0.65)
     m2, _ = run_model_case(yf, ub, "p0_s_refinit", "s", 10, "reference", 2, 1, 64, 64, 0.01, 0.65)
@@ -210,6 +269,9 @@ def main():
     ms, keys_stock = run_stock_case(ub, "stock_s_calibrated", "s", 10, 21, 2, 96, 64, 0.01, 0.65)
     metas["stock"] = ms
     (HERE / "state_dict_keys_stock_s.json").write_text(json.dumps(keys_stock, indent=0))
+    mp, keys_p1 = run_p1_case(ub, "p1_s_calibrated", "s", 10, 0, 1, 128, 192, 0.01, 0.65)
+    metas["p1"] = mp
+    (HERE / "state_dict_keys_p1_s.json").write_text(json.dumps(keys_p1, indent=0))
     metas["nms"] = nms_cases()
     metas["postproc"] = postproc_case(ub)
     metas["torch"] = torch.__version__

@@ -1,0 +1,226 @@
+"""GPU parity of the GLSDet P1 slice (models/new/yolox10.py: patch non-local attention in the neck, cross-level head)
+through the C ABI: the batched-GEMM / patch-view modes of the conv operator, the helper kernels, the non-local stage
+against the oracle, and the whole model against the reference's golden vectors and the oracle.
+
+Tolerances as in test_path_gpu.py (BASELINE.json: 2e-2 relative in bf16).  The non-local stage rounds three
+intermediate matrices (Gram matrix, two C x C products) to bf16; measured error of the stage alone: below 1e-2.
+"""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _helpers import TOL, assert_close_rel
+from oracle import ref_path
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+META = json.loads((GOLD / "meta.json").read_text())["p1"]
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def test_batched_gemm_modes(native_lib, cuda_device):
+    """out[b] = A[b mod k] @ W[b]^T with a weight matrix per image (and static activations shared by groups)."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(0)
+    for (B, M, K, Nn, groups) in ((8, 192, 320, 192, 0), (8, 128, 192, 320, 4), (12, 320, 576, 576, 4), (4, 192, 4096, 192, 0)):
+        nact = groups if groups else B
+        a = _bf(torch.randn(nact, M, K, generator=g) / K ** 0.5).to(dev)
+        w = _bf(torch.randn(B, Nn, K, generator=g)).to(dev)
+        ref = torch.stack([a[(b % groups) if groups else b] @ w[b].t() for b in range(B)])
+        out = torch.full((B, 1, M, Nn), float("nan"), device=dev, dtype=torch.bfloat16)
+        act = a.to(torch.bfloat16).view(nact, 1, M, K).contiguous()
+        op = ConvOp([View(act)], None, None, ksize=1, act=N.ACT_NONE, out=View(out), weight_raw=w.to(torch.bfloat16).contiguous(),
+                    n_out=Nn, src_shared=groups, batch=B if groups else None)
+        op.launch()
+        torch.cuda.synchronize()
+        got = out.float().view(B, M, Nn)
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), (B, M, K, Nn, groups)
+
+
+def test_patch_mode_conv(native_lib, cuda_device):
+    """1x1 conv over the four 2x2 patches of a map with one weight matrix and one bias per (image, patch), the input
+    as residual, written back in place of the patches (the 'apply' step of the non-local block)."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(1)
+    for (B, H, W, C) in ((2, 16, 24, 128), (1, 8, 12, 256), (3, 32, 32, 64), (1, 4, 6, 512)):
+        x = _bf(torch.randn(B, H, W, C, generator=g)).to(dev)
+        Ca = C + 64
+        wm = _bf(torch.randn(4 * B, C, Ca, generator=g) / C ** 0.5).to(dev)
+        bias = torch.randn(4 * B, 1, 1, C, generator=g).to(dev)
+        ref = torch.empty(B, H, W, C, device=dev)
+        h2, w2 = H // 2, W // 2
+        for b in range(B):
+            for py in range(2):
+                for px in range(2):
+                    bp = (b * 2 + py) * 2 + px
+                    xp = x[b, py * h2:(py + 1) * h2, px * w2:(px + 1) * w2]
+                    ref[b, py * h2:(py + 1) * h2, px * w2:(px + 1) * w2] = xp + xp @ wm[bp, :, :C].t() + bias[bp, 0, 0]
+        xin = x.to(torch.bfloat16).contiguous()
+        out = torch.full((B, H, W, C), float("nan"), device=dev, dtype=torch.bfloat16)
+        op = ConvOp([View(xin)], None, None, ksize=1, act=N.ACT_NONE, out=View(out), weight_raw=wm.to(torch.bfloat16).contiguous(),
+                    n_out=C, patch_mode=True, pre_res=View(bias.contiguous()), pre_shift=30, post_res=View(xin), post_shift=0)
+        op.launch()
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all(), (B, H, W, C)
+        assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item(), (B, H, W, C)
+
+
+def test_nonlocal_helper_kernels(native_lib, cuda_device):
+    from glsdet_b200.ops import GatherBiasOp, PatchTransposeOp, Upsample2xOp, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(2)
+    for (B, C, H, W) in ((2, 64, 8, 12), (1, 128, 4, 6), (2, 32, 16, 16)):
+        x = torch.randn(B, C, H, W, generator=g).to(dev)
+        h2, w2 = H // 2, W // 2
+        T = h2 * w2
+        Tp = (T + 63) // 64 * 64
+        dst = torch.zeros(4 * B, C + 64, Tp, device=dev, dtype=torch.bfloat16)
+        dst[:, C, :T] = 1.0
+        PatchTransposeOp(dst, C, H, W).launch(x)
+        torch.cuda.synchronize()
+        for b in range(B):
+            for py in range(2):
+                for px in range(2):
+                    patch = x[b, :, py * h2:(py + 1) * h2, px * w2:(px + 1) * w2].reshape(C, T).to(torch.bfloat16)
+                    assert torch.equal(dst[(b * 2 + py) * 2 + px, :C, :T], patch)
+        assert (dst[:, C, :T] == 1).all() and dst[:, C + 1:].abs().sum() == 0 and dst[:, :, T:].abs().sum() == 0
+    # gather_bias
+    w = torch.randn(8, 32, 96, generator=g).to(dev).to(torch.bfloat16)
+    base = torch.randn(4, 32, generator=g).to(dev)
+    bias = torch.empty(8, 1, 1, 32, device=dev)
+    GatherBiasOp(w, base, bias, 40).launch()
+    torch.cuda.synchronize()
+    ref = base[torch.arange(8, device=dev) % 4] + w[:, :, 40].float()
+    assert torch.equal(bias.view(8, 32), ref)
+    # nearest upsampling into a channel window
+    src = torch.randn(2, 5, 7, 48, generator=g).to(dev).to(torch.bfloat16)
+    dstu = torch.zeros(2, 10, 14, 64, device=dev, dtype=torch.bfloat16)
+    Upsample2xOp(View(src, 8, 32), View(dstu, 16, 32)).launch()
+    torch.cuda.synchronize()
+    ref = F.interpolate(src[..., 8:40].permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(dstu[..., 16:48].float(), ref)
+    assert dstu[..., :16].abs().max() == 0 and dstu[..., 48:].abs().max() == 0
+
+
+def _net(sd, dev, nc=10, phi="s"):
+    from glsdet_b200.yolox10 import YoloBody
+
+    net = YoloBody(nc, phi)
+    net.load_state_dict(sd, strict=True)
+    return net.to(dev).eval()
+
+
+def test_p1_model_matches_reference_golden(native_lib, cuda_device):
+    from glsdet_b200.utils_bbox import decode_outputs, non_max_suppression
+
+    z = np.load(GOLD / f"{META['name']}.npz")
+    sd = ref_path.synthetic_state_dict(META["nc"], META["phi"], seed=META["seed"], flavour="calibrated", variant="p1")
+    net = _net(sd, cuda_device)
+    feats = [torch.from_numpy(z[f"feat{i}"]).to(cuda_device) for i in range(4)]
+    cpu_feats = [f.cpu() for f in feats]
+    neck = net.backbone.forward_features(feats)
+    global_emu = ref_path._EMULATE_BF16
+    assert not global_emu
+    ref_path._EMULATE_BF16 = True
+    try:
+        with torch.no_grad():
+            neck_emu = ref_path.p1_neck(sd, [ref_path._q(f) for f in cpu_feats])
+    finally:
+        ref_path._EMULATE_BF16 = False
+    for i in range(1, 4):
+        ref_i = torch.from_numpy(z[f"neck{i}"])
+        inherent = ((neck_emu[i] - ref_i).norm() / ref_i.norm()).item()
+        assert_close_rel(neck[i], ref_i, max(TOL, 1.15 * inherent), f"p1 neck{i}")
+    logits = net.forward_features(feats)
+    emu = ref_path.p1_neck_head(sd, cpu_feats, bf16=True)
+    assert len(logits) == 3
+    for i in range(3):
+        ref_i = torch.from_numpy(z[f"logits{i}"])
+        inherent = ((emu[i] - ref_i).norm() / ref_i.norm()).item()
+        assert_close_rel(logits[i], ref_i, max(TOL, 1.15 * inherent), f"p1 logits{i}", frac=2e-2)
+        assert_close_rel(logits[i], emu[i], 1.5e-2, f"p1 logits{i} vs bf16-storage emulation", max_factor=4.0, frac=5e-2)
+    hl = net.head([torch.from_numpy(z[f"neck{i}"]).to(cuda_device) for i in range(4)])
+    for i in range(3):
+        assert_close_rel(hl[i], torch.from_numpy(z[f"logits{i}"]), TOL, f"p1 head-only logits{i}")
+    pred_fused = net.decode_features(feats)
+    pred_sep = decode_outputs(logits, [META["in_h"], META["in_w"]])
+    assert torch.allclose(pred_fused, pred_sep, rtol=1e-5, atol=1e-6)
+    res = non_max_suppression(torch.from_numpy(z["pred"]).to(cuda_device), META["nc"], [META["in_h"], META["in_w"]],
+                              np.array([META["in_h"], META["in_w"]]), False, META["conf"], META["nms_thr"], "auto_cpu")
+    for b in range(META["batch"]):
+        np.testing.assert_array_equal(res[b], z[f"nms{b}"])
+
+
+def test_p1_nonlocal_stage_vs_oracle(native_lib, cuda_device):
+    """feat + Patch_conv_feat(feat) alone (the attention rows a11/a12 of SURVEY.md section 8) on backbone-like features
+    at the sizes of a 512 x 768 input, against the fp32 oracle."""
+    from glsdet_b200.synthetic import synthetic_images
+
+    sd = ref_path.synthetic_state_dict(10, "s", seed=0, flavour="calibrated", variant="p1")
+    net = _net(sd, cuda_device)
+    feats = ref_path.csp_darknet(sd, synthetic_images(2, 512, 768, seed=3))
+    plan = net.plan_for([f.to(cuda_device) for f in feats])
+    plan.load_features([f.to(cuda_device) for f in feats])
+    plan.run_neck()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for i, name in ((1, "feat1"), (2, "feat2"), (3, "feat3")):
+            ref = feats[i] + ref_path.patch_conv_nonlocal_new(sd, f"backbone.Patch_conv_feat{i}", feats[i])
+            got = plan.buffer(name).float().permute(0, 3, 1, 2)
+            assert_close_rel(got, ref, 1.5e-2, f"non-local stage {name}")
+            nl_ref = torch.cat([torch.cat([ref_path.non_local_block(sd, f"backbone.Patch_conv_feat{i}.feat_patchconv_{a}_nonlocal", q)
+                                           for a, q in row], 3) for row in (
+                (("lt", feats[i][:, :, :feats[i].shape[2] // 2, :feats[i].shape[3] // 2]),
+                 ("rt", feats[i][:, :, :feats[i].shape[2] // 2, feats[i].shape[3] // 2:])),
+                (("lb", feats[i][:, :, feats[i].shape[2] // 2:, :feats[i].shape[3] // 2]),
+                 ("rb", feats[i][:, :, feats[i].shape[2] // 2:, feats[i].shape[3] // 2:])))], 2)
+            nl = plan.buffer(f"backbone.Patch_conv_feat{i}.nl").float().permute(0, 3, 1, 2)
+            assert_close_rel(nl, nl_ref, 1.5e-2, f"re-tiled non-local blocks of {name}")
+
+
+def test_p1_model_vs_oracle_1024(native_lib, cuda_device):
+    """P1-s at 1024 x 1024 (SURVEY.md section 8d row 2'): one image against the oracle, batch invariance, detections.
+
+    This graph is 35 layers deep on the cls branch and the calibrated synthetic weights make it ill-conditioned in
+    bf16: a plain fp32 evaluation with bf16-rounded weights / layer outputs (the emulation) is itself 2.7e-2 .. 3.5e-2
+    away from the fp32 oracle at the logits (1.3e-2 .. 2.3e-2 at the neck outputs, 0.4e-2 .. 0.5e-2 right after the
+    non-local stage).  Measured for the CUDA path (tools/p1_error_report.py): 3.3e-2 .. 4.2e-2 against the oracle,
+    3.4e-2 .. 4.4e-2 against the emulation, i.e. 1.2x the inherent error (two bf16 evaluations with different rounding
+    points differ from each other by about sqrt(2) x the error of one).  The bounds below are therefore relative to
+    the inherent error; the 2e-2 bar of BASELINE.json is met by the non-local stage and the small golden case."""
+    from glsdet_b200.synthetic import synthetic_images
+
+    sd = ref_path.synthetic_state_dict(10, "s", seed=0, flavour="calibrated", variant="p1")
+    net = _net(sd, cuda_device)
+    feats = ref_path.csp_darknet(sd, synthetic_images(2, 1024, 1024, seed=12))
+    ref = ref_path.p1_neck_head(sd, [f[:1] for f in feats])
+    emu = ref_path.p1_neck_head(sd, [f[:1] for f in feats], bf16=True)
+    dfeats = [f.to(cuda_device) for f in feats]
+    out = net.forward_features(dfeats)
+    for i in range(3):
+        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
+        assert_close_rel(out[i][:1], ref[i], max(TOL, 1.3 * inherent), f"p1 1024 logits{i}", frac=5e-2)
+        assert_close_rel(out[i][:1], emu[i], max(1.5e-2, 1.6 * inherent), f"p1 1024 logits{i} vs bf16-storage emulation",
+                         frac=8e-2)
+    pred2 = net.decode_features(dfeats).clone()
+    assert pred2.shape == (2, 128 * 128 + 64 * 64 + 32 * 32, 15)
+    one = net.decode_features([f[1:2].contiguous() for f in dfeats])
+    assert torch.equal(one[0], pred2[1]), "results must not depend on the batch an image is in"
+    det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65)
+    torch.cuda.synchronize()
+    assert (cnt.cpu() >= 0).all() and det.shape[0] == 2

@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--phi", default="s")
     ap.add_argument("--nc", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--variant", default="ffa", choices=["ffa", "stock"])
+    ap.add_argument("--variant", default="ffa", choices=["ffa", "stock", "p1"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--obj-std", type=float, default=2.0)
     ap.add_argument("--target-pass", type=float, default=0.04, help="fraction of anchors with obj*cls >= 0.01")
@@ -55,18 +55,35 @@ def main():
     x = synthetic_images(2, args.size, args.size, seed=args.seed + 4242)
     with torch.no_grad():
         feats = ref_path.csp_darknet(sd, x)
-        neck = ref_path.pafpn_neck(sd, feats)
+        neck = ref_path.p1_neck(sd, feats) if args.variant == "p1" else ref_path.pafpn_neck(sd, feats)
         # towers: rescale the prediction convs on the calibrated tower outputs
-        if args.variant == "stock":
+        towers = None
+        if args.variant == "p1":   # models/new/yolox10.py:83-139
+            f0 = ref_path.csp_layer(sd, "head.csp_feat0", neck[0])
+            xs = [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
+            towers = []
+            for k, xk in enumerate(xs):
+                lower = f0 if k == 0 else xs[k - 1]
+                down = ref_path.base_conv(sd, f"head.up_convs.{k}.1", ref_path.base_conv(sd, f"head.up_convs.{k}.0", lower), stride=2)
+                parts = [xk, down] + ([F.interpolate(xs[k + 1], scale_factor=2, mode="nearest")] if k < 2 else [])
+                cf = ref_path.base_conv(sd, f"head.cls_convs.{k}.1", ref_path.base_conv(sd, f"head.cls_convs.{k}.0", torch.cat(parts, 1)))
+                rf = ref_path.base_conv(sd, f"head.reg_convs.{k}.1", ref_path.base_conv(sd, f"head.reg_convs.{k}.0", xk))
+                towers.append((k, cf, rf))
+            proc = []
+        elif args.variant == "stock":
             proc = [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
         else:
             zz = ref_path.ffa(sd, "head.ftt", neck[1], neck[2])
             proc = [ref_path.csp_layer(sd, "head.csp", neck[0]) + F.interpolate(zz, scale_factor=2, mode="nearest")]
             proc += [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
-        for k, xk in enumerate(proc):
-            i = k if args.variant == "stock" else (3 if k == 0 else k - 1)
-            cf = ref_path.base_conv(sd, f"head.cls_convs.{i}.1", ref_path.base_conv(sd, f"head.cls_convs.{i}.0", xk))
-            rf = ref_path.base_conv(sd, f"head.reg_convs.{i}.1", ref_path.base_conv(sd, f"head.reg_convs.{i}.0", xk))
+        if towers is None:
+            towers = []
+            for k, xk in enumerate(proc):
+                i = k if args.variant == "stock" else (3 if k == 0 else k - 1)
+                cf = ref_path.base_conv(sd, f"head.cls_convs.{i}.1", ref_path.base_conv(sd, f"head.cls_convs.{i}.0", xk))
+                rf = ref_path.base_conv(sd, f"head.reg_convs.{i}.1", ref_path.base_conv(sd, f"head.reg_convs.{i}.0", xk))
+                towers.append((i, cf, rf))
+        for i, cf, rf in towers:
             for name, feat, target in (("cls_preds", cf, args.cls_std), ("obj_preds", rf, args.obj_std), ("reg_preds", rf, 0.15)):
                 key = f"head.{name}.{i}.weight"
                 y = F.conv2d(feat, sd[key])
@@ -75,7 +92,8 @@ def main():
                 changed[key] = sd[key]
     ref_path.base_conv = orig
     # shift the objectness biases so that the wanted fraction of anchors passes conf 0.01 (bisection on one offset)
-    head_fn = (lambda n: ref_path.stock_head(sd, n[1:])) if args.variant == "stock" else (lambda n: ref_path.yolox_head(sd, n))
+    head_fn = {"stock": lambda n: ref_path.stock_head(sd, n[1:]), "p1": lambda n: ref_path.p1_head(sd, n),
+               "ffa": lambda n: ref_path.yolox_head(sd, n)}[args.variant]
     with torch.no_grad():
         lg = head_fn(neck)
     obj = torch.cat([l[:, 4].flatten(1) for l in lg], 1)
