@@ -43,6 +43,23 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvF32Desc(C.Structure):
+    """Mirror of struct glsdet_conv_f32_desc."""
+
+    _fields_ = [
+        ("src0", C.c_void_p), ("src0_c", C.c_int32), ("src0_ld", C.c_int32),
+        ("src1", C.c_void_p), ("src1_c", C.c_int32), ("src1_ld", C.c_int32),
+        ("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+        ("weight", C.c_void_p), ("out_channels", C.c_int32),
+        ("bias", C.c_void_p), ("act", C.c_int32),
+        ("pre_res", C.c_void_p), ("pre_shift", C.c_int32), ("pre_ld", C.c_int32),
+        ("post_res", C.c_void_p), ("post_shift", C.c_int32), ("post_ld", C.c_int32),
+        ("out", C.c_void_p), ("out_mode", C.c_int32), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
+        ("out_batch_stride", C.c_int64),
+        ("dec_stride", C.c_float), ("dec_in_w", C.c_float), ("dec_in_h", C.c_float),
+    ]
+
+
 _lib = None
 
 # name -> (restype, argtypes); must list every symbol include/glsdet_b200.h declares
@@ -63,6 +80,14 @@ SIGNATURES = {
                                          C.c_int32, C.c_void_p]),
     "glsdet_gather_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int64, C.c_int32, C.c_void_p]),
+    "glsdet_conv_f32": (C.c_int, [C.POINTER(ConvF32Desc), C.c_void_p]),
+    "glsdet_nchw_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_se_partial_f32": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glsdet_se_fc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                               C.c_int32, C.c_void_p]),
+    "glsdet_scale_pixel_shuffle_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -293,6 +293,15 @@ extern "C" int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t 
   return count_launch("se_fc_kernel");
 }
 
+extern "C" int glsdet_se_fc(const float* scratch, const float* w1, const float* w2, int32_t hidden, float* gate,
+                            int32_t batch, int32_t hw, int32_t channels, void* stream) {
+  GLSDET_REQUIRE(scratch && w1 && w2 && gate && batch > 0 && hw > 0 && channels > 0 && hidden > 0, "se_fc: bad arguments");
+  const size_t smem2 = static_cast<size_t>(channels + hidden) * sizeof(float);
+  GLSDET_REQUIRE(smem2 <= 48 * 1024, "se_fc: too many channels (%d)", channels);
+  se_fc_kernel<<<batch, 256, smem2, static_cast<cudaStream_t>(stream)>>>(scratch, w1, w2, gate, hw, channels, hidden);
+  return count_launch("se_fc_kernel");
+}
+
 extern "C" int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
                                           int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
                                           void* stream) {

@@ -33,7 +33,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import (ConvOp, GatherBiasOp, PatchTransposeOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
+from .ops import (ConvOp, ConvOpF32, GatherBiasOp, PatchTransposeOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
                   nchw_to_nhwc, nhwc_to_nchw)
 
 BN_EPS = 1e-3
@@ -45,11 +45,18 @@ class FFAPathPlan:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], num_classes: int,
                  device=None, act: str = "silu", neck_prefix: str = "backbone.", head_prefix: str = "head.",
-                 parts: Sequence[str] = ("neck", "head"), variant: str = "ffa", decode: str = "drone"):
+                 parts: Sequence[str] = ("neck", "head"), variant: str = "ffa", decode: str = "drone",
+                 precision: str = "bf16"):
         """`parts` selects which op lists are built - "neck", "stems" (everything producing the per-level head
         inputs), "towers" (tower + prediction convs), "head" = stems + towers - because a stand-alone neck or head
         module only owns its own weights; `decode` picks the decoded-row flavour: "drone" (normalised) or "mmdet"
-        (input pixels)."""
+        (input pixels); `precision` "bf16" is the tensor-core path, "fp32" the accuracy mode of BASELINE.json configs[0]
+        (every tensor fp32, SIMT fp32 convs, csrc/fp32_path.cu; parity bar 1e-3 relative)."""
+        assert precision in ("bf16", "fp32")
+        self.fp32 = precision == "fp32"
+        self.dtype = torch.float32 if self.fp32 else torch.bfloat16
+        if self.fp32 and variant == "p1":
+            raise NotImplementedError("the fp32 accuracy mode covers the P0 and stock topologies")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         parts = set(parts)
@@ -114,9 +121,9 @@ class FFAPathPlan:
         self._build()
 
     # ------------------------------------------------------------------ helpers
-    def _buf(self, name: str, stride: int, channels: int, dtype=torch.bfloat16) -> torch.Tensor:
+    def _buf(self, name: str, stride: int, channels: int, dtype=None) -> torch.Tensor:
         h, w = self.stride_hw[stride]
-        t = torch.empty((self.B, h, w, channels), dtype=dtype, device=self.device)
+        t = torch.empty((self.B, h, w, channels), dtype=self.dtype if dtype is None else dtype, device=self.device)
         self._bufs[name] = t
         return t
 
@@ -126,6 +133,8 @@ class FFAPathPlan:
                        sd[p + ".bn.running_var"], BN_EPS)
 
     def _conv(self, ops: List, w, b, srcs, out, k, stride=1, act=None, **kw) -> ConvOp:
+        if self.fp32:
+            return self._conv_f32(ops, w, b, srcs, out, k, stride, self.act if act is None else act, **kw)
         op = ConvOp(srcs, w, b, ksize=k, stride=stride, act=self.act if act is None else act, out=out, **kw)
         ops.append(op)
         if w is not None:   # the batched products of the non-local block are not part of the reference's conv FLOPs
@@ -133,6 +142,23 @@ class FFAPathPlan:
         else:
             self.attn_flops = getattr(self, "attn_flops", 0.0) + op.flops
         return op
+
+    def _conv_f32(self, ops, w, b, srcs, out, k, stride, act, pred_weight=None, pred_bias=None, pred_act=N.ACT_NONE,
+                  dec=(0.0, 0.0, 0.0), **kw):
+        """fp32 accuracy mode: same graph on ConvOpF32; the fused prediction conv becomes a separate 1x1 conv."""
+        if pred_weight is None:
+            op = ConvOpF32(srcs, w, b, ksize=k, stride=stride, act=act, out=out, dec=dec, **kw)
+            ops.append(op)
+            self.flops += op.flops
+            return op
+        bb, hh, ww = srcs[0].bhw
+        tmp = torch.empty((bb, hh // stride, ww // stride, w.shape[0]), dtype=torch.float32, device=self.device)
+        op1 = ConvOpF32(srcs, w, b, ksize=k, stride=stride, act=act, out=View(tmp))
+        op2 = ConvOpF32([View(tmp)], pred_weight.reshape(pred_weight.shape[0], -1, 1, 1), pred_bias, ksize=1, act=pred_act,
+                        out=out, dec=dec, **kw)
+        ops.extend([op1, op2])
+        self.flops += op1.flops + op2.flops
+        return op2
 
     def _base_conv(self, ops, p, srcs, out, stride=1, act=None, **kw):
         w, b = self._folded(p)

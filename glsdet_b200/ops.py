@@ -175,17 +175,27 @@ def nchw_to_nhwc(src: torch.Tensor, dst: View, stream=None) -> None:
     """NCHW fp32 (reference layout) -> channel window of an NHWC bf16 buffer."""
     assert src.dtype == torch.float32 and src.is_contiguous() and src.is_cuda
     b, c, h, w = src.shape
-    assert dst.bhw == (b, h, w) and dst.c == c and dst.t.dtype == torch.bfloat16
     lib = N.load()
+    if dst.t.dtype == torch.float32:   # fp32 accuracy mode
+        assert dst.bhw == (b, h, w) and dst.c == c
+        N.check(lib.glsdet_nchw_nhwc_f32(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff, 1,
+                                         N.stream_ptr(stream)), "glsdet_nchw_nhwc_f32")
+        return
+    assert dst.bhw == (b, h, w) and dst.c == c and dst.t.dtype == torch.bfloat16
     N.check(lib.glsdet_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff,
                                              N.stream_ptr(stream)), "glsdet_nchw_f32_to_nhwc_bf16")
 
 
 def nhwc_to_nchw(src: View, dst: torch.Tensor, stream=None) -> None:
-    assert dst.dtype == torch.float32 and dst.is_contiguous() and src.t.dtype == torch.bfloat16
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
     b, h, w = src.bhw
     assert tuple(dst.shape) == (b, src.c, h, w)
     lib = N.load()
+    if src.t.dtype == torch.float32:
+        N.check(lib.glsdet_nchw_nhwc_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff, 0,
+                                         N.stream_ptr(stream)), "glsdet_nchw_nhwc_f32")
+        return
+    assert src.t.dtype == torch.bfloat16
     N.check(lib.glsdet_nhwc_bf16_to_nchw_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff,
                                              N.stream_ptr(stream)), "glsdet_nhwc_bf16_to_nchw_f32")
 
@@ -194,7 +204,7 @@ class SeGateOp:
     """gate[b, c] = 1 + sigmoid(W2 relu(W1 mean_hw(x)))  (models/ffa/ffa.py:16-20 and :77)."""
 
     def __init__(self, x: View, w1: torch.Tensor, w2: torch.Tensor):
-        assert x.coff == 0 and x.t.dtype == torch.bfloat16
+        assert x.coff == 0 and x.t.dtype in (torch.bfloat16, torch.float32)
         b, h, w = x.bhw
         self.x, self.b, self.hw, self.c = x, b, h * w, x.c
         self.w1 = w1.detach().float().contiguous()
@@ -206,6 +216,13 @@ class SeGateOp:
         self._lib = N.load()
 
     def launch(self, stream=None):
+        if self.x.t.dtype == torch.float32:
+            st = N.stream_ptr(stream)
+            N.check(self._lib.glsdet_se_partial_f32(self.x.ptr, self.b, self.hw, self.c, self.x.ld,
+                                                    self.scratch.data_ptr(), st), "glsdet_se_partial_f32")
+            N.check(self._lib.glsdet_se_fc(self.scratch.data_ptr(), self.w1.data_ptr(), self.w2.data_ptr(), self.hidden,
+                                           self.gate.data_ptr(), self.b, self.hw, self.c, st), "glsdet_se_fc")
+            return
         N.check(self._lib.glsdet_se_gate(self.x.ptr, self.b, self.hw, self.c, self.x.ld, self.w1.data_ptr(),
                                          self.w2.data_ptr(), self.hidden, self.scratch.data_ptr(),
                                          self.gate.data_ptr(), N.stream_ptr(stream)), "glsdet_se_gate")
@@ -223,6 +240,12 @@ class ScaleShuffleOp:
         self._lib = N.load()
 
     def launch(self, stream=None):
+        if self.x.t.dtype == torch.float32:
+            N.check(self._lib.glsdet_scale_pixel_shuffle_f32(self.x.ptr, self.gate.data_ptr(), self.dst.t.data_ptr(),
+                                                             self.b, self.h, self.w, self.cout, self.dst.ld,
+                                                             self.dst.coff, N.stream_ptr(stream)),
+                    "glsdet_scale_pixel_shuffle_f32")
+            return
         N.check(self._lib.glsdet_scale_pixel_shuffle(self.x.ptr, self.gate.data_ptr(), self.dst.t.data_ptr(), self.b,
                                                      self.h, self.w, self.cout, self.dst.ld, self.dst.coff,
                                                      N.stream_ptr(stream)), "glsdet_scale_pixel_shuffle")
@@ -288,3 +311,60 @@ class Upsample2xOp:
         b, h, w = s.bhw
         N.check(self._lib.glsdet_upsample2x(s.t.data_ptr(), d.t.data_ptr(), b, h, w, s.c, s.ld, s.coff, d.ld, d.coff,
                                             N.stream_ptr(stream)), "glsdet_upsample2x")
+
+
+class ConvOpF32:
+    """fp32 accuracy-mode twin of ConvOp (glsdet_conv_f32: SIMT fp32 implicit GEMM, every tensor fp32).  Same
+    arguments as ConvOp minus the tensor-core-only ones (fused prediction conv, batched / patch modes)."""
+
+    def __init__(self, srcs: Sequence[View], weight: torch.Tensor, bias: Optional[torch.Tensor], *, ksize: int,
+                 stride: int = 1, act: int = N.ACT_NONE, out, out_mode: int = N.OUT_NHWC_F32, out_ld: int = 0,
+                 out_coff: int = 0, out_batch_stride: int = 0, pre_res: Optional[View] = None, pre_shift: int = 0,
+                 post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0)):
+        self._lib = N.load()
+        assert 1 <= len(srcs) <= 2
+        b, h, w = srcs[0].bhw
+        for s in srcs:
+            assert s.bhw == (b, h, w) and s.t.dtype == torch.float32
+        n_out, cin = weight.shape[0], weight.shape[1]
+        assert cin == sum(s.c for s in srcs)
+        # K order (source, tap, channel)
+        segs, a = [], 0
+        for s in srcs:
+            segs.append(weight[:, a:a + s.c].permute(0, 2, 3, 1).reshape(n_out, -1))
+            a += s.c
+        self.packed = torch.cat(segs, 1).float().contiguous()
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        d = N.ConvF32Desc()
+        d.src0, d.src0_c, d.src0_ld = srcs[0].ptr, srcs[0].c, srcs[0].ld
+        if len(srcs) == 2:
+            d.src1, d.src1_c, d.src1_ld = srcs[1].ptr, srcs[1].c, srcs[1].ld
+        d.batch, d.height, d.width, d.ksize, d.stride = b, h, w, ksize, stride
+        d.weight, d.out_channels = self.packed.data_ptr(), n_out
+        d.bias = 0 if self.bias is None else self.bias.data_ptr()
+        d.act = act
+        ho, wo = h // stride, w // stride
+        if pre_res is not None:
+            assert pre_res.t.dtype == torch.float32 and pre_res.bhw == (b, max(ho >> pre_shift, 1), max(wo >> pre_shift, 1))
+            d.pre_res, d.pre_shift, d.pre_ld = pre_res.ptr, pre_shift, pre_res.ld
+        if post_res is not None:
+            assert post_res.t.dtype == torch.float32 and post_res.bhw == (b, ho >> post_shift, wo >> post_shift)
+            d.post_res, d.post_shift, d.post_ld = post_res.ptr, post_shift, post_res.ld
+        if isinstance(out, View):
+            assert out.bhw == (b, ho, wo) and out.c >= n_out and out.t.dtype == torch.float32
+            d.out, d.out_ld, d.out_coff = out.t.data_ptr(), out.ld, out.coff
+            d.out_batch_stride = ho * wo * out.ld
+            d.out_mode = N.OUT_NHWC_F32
+            self._out_t = out.t
+        else:
+            assert out.dtype == torch.float32
+            d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
+            d.out_batch_stride, d.out_mode = out_batch_stride, out_mode
+            self._out_t = out
+        d.dec_stride, d.dec_in_w, d.dec_in_h = dec
+        self.desc = d
+        self._keep = (srcs, pre_res, post_res)
+        self.flops = 2.0 * b * ho * wo * n_out * cin * ksize * ksize
+
+    def launch(self, stream=None):
+        N.check(self._lib.glsdet_conv_f32(C.byref(self.desc), N.stream_ptr(stream)), "glsdet_conv_f32")

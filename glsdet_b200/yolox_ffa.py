@@ -177,6 +177,16 @@ class _PlanOwner(nn.Module):
     _parts: Tuple[str, ...] = ()
     _variant = "ffa"      # "ffa": models/ffa/yolox_ffa.py; "stock": models/base/yolox.py and the mmdet pair
     _decode = "drone"     # decoded-row flavour of the fused path
+    precision = "bf16"    # "bf16": tcgen05 path; "fp32": accuracy mode (SIMT fp32 kernels, 1e-3 parity bar)
+
+    def set_precision(self, precision: str):
+        """Select the arithmetic of the native plan for this module and its native children."""
+        assert precision in ("bf16", "fp32")
+        for m in self.modules():
+            if isinstance(m, _PlanOwner):
+                m.precision = precision
+                m.invalidate_plans()
+        return self
 
     def __init__(self):
         super().__init__()
@@ -203,14 +213,14 @@ class _PlanOwner(nn.Module):
         return self.state_dict()
 
     def _plan(self, batch: int, input_hw: Sequence[int], device) -> FFAPathPlan:
-        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device))
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), self.precision)
         plan = self._plans.get(key)
         if plan is None:
             if len(self._plans) >= 4:
                 self._plans.clear()
             plan = FFAPathPlan(self._plan_state_dict(), batch, input_hw, self._num_classes(), device=device,
                                neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts,
-                               variant=self._variant, decode=self._decode)
+                               variant=self._variant, decode=self._decode, precision=self.precision)
             self._plans[key] = plan
         return plan
 

@@ -130,6 +130,35 @@ int glsdet_conv_create(const glsdet_conv_desc* desc, glsdet_conv_t** op);
 int glsdet_conv_launch(glsdet_conv_t* op, void* stream);
 void glsdet_conv_destroy(glsdet_conv_t* op);
 
+/*
+ * fp32 evaluation of the same operator (accuracy mode: BASELINE.json configs[0], parity bar 1e-3 relative in fp32).
+ * Same semantics as glsdet_conv_desc with every tensor fp32: src NHWC fp32 channel windows, weight fp32 [N][K] with
+ * K order (source, tap = ky*k + kx, channel) unpadded (BatchNorm folded in by the caller), fp32 residuals, output
+ * GLSDET_OUT_NHWC_F32 or GLSDET_OUT_NCHW_F32.  SIMT fp32 FMA implicit GEMM; no tensor cores, no bf16 anywhere.
+ */
+typedef struct glsdet_conv_f32_desc {
+  const float* src0; int32_t src0_c, src0_ld;
+  const float* src1; int32_t src1_c, src1_ld;      /* NULL when there is a single source */
+  int32_t batch, height, width, ksize, stride;     /* ksize 1/3/5/7, pad (k-1)/2, stride 1/2 */
+  const float* weight; int32_t out_channels;
+  const float* bias; int32_t act;                  /* GLSDET_ACT_* (exact expf-based SiLU / sigmoid) */
+  const float* pre_res; int32_t pre_shift, pre_ld;   /* added before the activation, read at (y>>shift, x>>shift) */
+  const float* post_res; int32_t post_shift, post_ld; /* added after the activation */
+  float* out; int32_t out_mode, out_ld, out_coff; int64_t out_batch_stride;
+  float dec_stride, dec_in_w, dec_in_h;
+} glsdet_conv_f32_desc;
+int glsdet_conv_f32(const glsdet_conv_f32_desc* desc, void* stream);
+/* NCHW fp32 <-> channel window of an NHWC fp32 buffer (to_nhwc = 1: src is NCHW; 0: src is the NHWC buffer) */
+int glsdet_nchw_nhwc_f32(const float* src, float* dst, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                         int32_t nhwc_ld, int32_t nhwc_coff, int32_t to_nhwc, void* stream);
+/* fp32 variants of the FFA helpers (SE stage 1 on fp32 NHWC; stage 2 = glsdet_se_fc; gate * PixelShuffle) */
+int glsdet_se_partial_f32(const float* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld, float* scratch,
+                          void* stream);
+int glsdet_se_fc(const float* scratch, const float* w1, const float* w2, int32_t hidden, float* gate, int32_t batch,
+                 int32_t hw, int32_t channels, void* stream);
+int glsdet_scale_pixel_shuffle_f32(const float* x, const float* gate, float* dst, int32_t batch, int32_t height,
+                                   int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff, void* stream);
+
 /* layout converters at the module boundary (reference tensors are NCHW fp32 everywhere) */
 int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
                                  int32_t width, int32_t dst_ld, int32_t dst_coff, void* stream);
