@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=16, help="images per pass of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample: repeat passes for about this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="p0", choices=["p0", "p1"],
+                    help="p0 = BASELINE configs[1] (models/ffa/yolox_ffa.py, the default and the judged metric); "
+                         "p1 = models/new/yolox10.py (patch non-local attention neck, SURVEY.md section 8d row 2')")
     return ap.parse_args()
 
 
@@ -117,10 +120,28 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ synthetic data
+VARIANT = "p0"
+
+
 def make_weights():
     from glsdet_b200.synthetic import synthetic_state_dict
 
-    return synthetic_state_dict(NUM_CLASSES, PHI, seed=WEIGHT_SEED, flavour="calibrated")
+    return synthetic_state_dict(NUM_CLASSES, PHI, seed=WEIGHT_SEED, flavour="calibrated",
+                                variant="ffa" if VARIANT == "p0" else "p1")
+
+
+def body_class():
+    if VARIANT == "p1":
+        from glsdet_b200.yolox10 import YoloBody
+    else:
+        from glsdet_b200.yolox_ffa import YoloBody
+    return YoloBody
+
+
+def ref_neck_head(sd, feats):
+    from oracle import ref_path
+
+    return ref_path.neck_head(sd, feats) if VARIANT == "p0" else ref_path.p1_neck_head(sd, feats)
 
 
 def make_features(net, batch, seed, device):
@@ -151,7 +172,7 @@ def cpu_reference_run(sd, feats_cpu, n_images, threads):
     t0 = time.perf_counter()
     for i in range(n_images):
         f = [t[i:i + 1] for t in feats_cpu]
-        logits = ref_path.neck_head(sd, f)
+        logits = ref_neck_head(sd, f)
         pred = ref_path.decode_outputs(logits, [IN_H, IN_W])
         res = ref_path.non_max_suppression(pred, NUM_CLASSES, [IN_H, IN_W], None, False, CONF_THRES, NMS_THRES,
                                            strategy="auto_cpu", correct_boxes=False)
@@ -169,9 +190,7 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sd = make_weights()
-    from glsdet_b200.yolox_ffa import YoloBody
-
-    net = YoloBody(NUM_CLASSES, PHI)
+    net = body_class()(NUM_CLASSES, PHI)
     net.load_state_dict(sd, strict=True)
     n = max(1, min(args.cpu_images, 2))
     feats = make_features(net, n, 1000, torch.device("cpu"))
@@ -204,7 +223,8 @@ def run_native_arm(args):
 
     from glsdet_b200 import _native as N
     from glsdet_b200.dist import gather_detections
-    from glsdet_b200.yolox_ffa import YoloBody
+
+    YoloBody = body_class()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -329,12 +349,15 @@ def run_native_arm(args):
 
     if rank == 0:
         pk = peaks()
-        achieved_tf = ALGO_GFLOP_PER_IMAGE * B / conv_ms  # GFLOP / ms = TFLOP/s
+        algo_gflop = ALGO_GFLOP_PER_IMAGE if VARIANT == "p0" else (plan.flops + getattr(plan, "attn_flops", 0.0)) / B / 1e9
+        achieved_tf = algo_gflop * B / conv_ms  # GFLOP / ms = TFLOP/s
         line = {"metric": "images/sec at 1024^2 (neck+head+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "GLSDet YOLOX-s (yolox_ffa YoloBody(10,'s')) neck+FFA+head+decode+filter+NMS, "
-                                       f"batch {B} of synthetic 1024x1024 images per GPU (BASELINE configs[1])",
+                "config": {"workload": ("GLSDet YOLOX-s (yolox_ffa YoloBody(10,'s')) neck+FFA+head+decode+filter+NMS, "
+                                        f"batch {B} of synthetic 1024x1024 images per GPU (BASELINE configs[1])") if VARIANT == "p0" else
+                                       ("GLSDet P1 YOLOX-s (yolox10 YoloBody(10,'s')) non-local neck+head+decode+filter+NMS, "
+                                        f"batch {B} of synthetic 1024x1024 images per GPU (SURVEY 8d row 2')"),
                            "images_per_gpu": B, "num_classes": NUM_CLASSES, "conf_thres": CONF_THRES,
                            "nms_thres": NMS_THRES, "nms_strategy": "torchvision auto dispatch for CUDA tensors",
                            "l2": "inputs (503 MB fp32 feature maps per batch) exceed the 126 MB L2; no explicit flush",
@@ -348,7 +371,7 @@ def run_native_arm(args):
                 "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                              "frac": achieved_tf / pk["tf_sustained"], "traffic": conv_traffic(B),
                              "kernel": "conv_gemm_kernel (all conv launches of a step, neck+FFA+head segment)",
-                             "algorithmic_gflop_per_image": ALGO_GFLOP_PER_IMAGE, "segment_ms": conv_ms,
+                             "algorithmic_gflop_per_image": algo_gflop, "segment_ms": conv_ms,
                              "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)"},
                 "launches_per_step": int(launches) // args.steps}
         if not args.no_cpu_baseline:
@@ -373,7 +396,9 @@ def run_native_arm(args):
 
 
 def main():
+    global VARIANT
     args = parse_args()
+    VARIANT = args.variant
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_native_arm(args)

@@ -127,6 +127,10 @@ struct Work {
   unsigned long long* mask;  // [mask_words]
   int64_t mask_words;
   int32_t max_scan_tiles;    // segments with more 64-box chunks than this use the fallback kernel
+  int32_t topk;              // > 0: only the `topk` best kept boxes per image are wanted (max_det) and the kept list of
+                             // a segment fits shared memory: every segment runs on the blocked-greedy kernel, which
+                             // stops once it has kept `topk` boxes (a later box of the segment cannot rank in the top
+                             // `topk` of its image); no suppression bitmask is built at all
 };
 
 struct ImageMode {
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
       const int b = sgm / w.nc, c = sgm % w.nc;
       n = w.seg_start[b * (w.nc + 1) + c + 1] - w.seg_start[b * (w.nc + 1) + c];
       T = (n + 63) >> 6;
-      if (T <= w.max_scan_tiles && T < 46000) {  // T*T must fit an int; larger segments go to the fallback
+      if (w.topk == 0 && T <= w.max_scan_tiles && T < 46000) {  // T*T must fit an int; larger segments go to the fallback
         tiles = T * (T + 1) / 2;     // upper triangle only (column tile >= row tile)
         words = 64ll * tiles;
       }
@@ -606,6 +610,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work
   __syncthreads();
 
   for (int c0 = 0; c0 < n; c0 += 64) {
+    if (w.topk > 0 && kept_n >= w.topk) break;   // uniform: kept_n was published before the last barrier
     const int mcnt = min(64, n - c0);
     if (tid < 64) {
       cmask[tid] = 0ull;
@@ -804,6 +809,7 @@ Work make_work(void* ws, int B, int cap, int nc) {
     if (v >= 0 && v < w.mask_words) w.mask_words = v;
   }
   w.max_scan_tiles = kMaxScanTiles;
+  w.topk = 0;
   return w;
 }
 
@@ -853,9 +859,11 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   }
   seg_plan_kernel<<<1, 1024, 0, st>>>(w);
   if (int rc = count_launch("seg_plan_kernel")) return rc;
-  mask_tiles_kernel<<<device_sm_count() * 6, 64 * kMaskGroups, 0, st>>>(w, nms_thres);
-  if (int rc = count_launch("mask_tiles_kernel")) return rc;
-  {
+  if (w.topk == 0) {
+    mask_tiles_kernel<<<device_sm_count() * 6, 64 * kMaskGroups, 0, st>>>(w, nms_thres);
+    if (int rc = count_launch("mask_tiles_kernel")) return rc;
+  }
+  if (w.topk == 0) {
     int t = (w.cap + 63) / 64;
     if (t > kMaxScanTiles) t = kMaxScanTiles;
     scan_kernel<<<dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 16, st>>>(w);
@@ -900,6 +908,7 @@ extern "C" int glsdet_nms_create(int32_t batch, int32_t anchors, int32_t num_cla
   GLSDET_REQUIRE(h != nullptr, "nms_create: out of host memory");
   h->B = batch; h->A = anchors; h->nc = num_classes; h->max_det = max_det;
   h->w = make_work(workspace, batch, anchors, num_classes);
+  if (max_det <= kKeptSmem && max_det < anchors && getenv("GLSDET_NMS_NO_TOPK") == nullptr) h->w.topk = max_det;
   *op = h;
   return 0;
 }

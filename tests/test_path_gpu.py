@@ -216,6 +216,46 @@ def test_device_nms_full_anchor_count_properties(native_lib, cuda_device):
         assert len(again) == len(rows)
 
 
+def test_device_nms_topk_mode_matches_full_nms(native_lib, cuda_device, monkeypatch):
+    """max_det <= 1536 switches to the bitmask-free blocked-greedy kernel with early exit per (image, class) segment:
+    its rows must be exactly the first max_det rows of the unlimited NMS (mask path), for every strategy."""
+    from glsdet_b200.utils_bbox import DeviceNMS
+
+    B, A, nc = 3, 20000, 4
+    rng = np.random.default_rng(11)
+    pred = np.zeros((B, A, 5 + nc), np.float32)
+    for b in range(B):
+        boxes, scores, labels = _clustered(rng, A, nc, spread=0.01)
+        labels[: A // 2] = 0                      # one dominant class: its segment is cut short by the early exit
+        cxcy = (boxes[:, :2] + boxes[:, 2:]) / 2
+        pred[b, :, 0:2], pred[b, :, 2:4] = cxcy, boxes[:, 2:] - boxes[:, :2]
+        pred[b, :, 4] = scores
+        pred[b, np.arange(A), 5 + labels.astype(int)] = 1.0
+    pred[2, :, 4] *= 0.2                          # an image with few candidates (no early exit)
+    dpred = torch.from_numpy(pred).to(cuda_device)
+    full = DeviceNMS(B, A, nc)
+    for strategy in ("auto_cuda", "per_class", "trick"):
+        det_f, cnt_f = (t.clone() for t in full.launch(dpred, 0.15, 0.5, strategy))
+        for max_det in (100, 1000, 1536):
+            lim = DeviceNMS(B, A, nc, max_det=max_det)
+            det_l, cnt_l = lim.launch(dpred, 0.15, 0.5, strategy)
+            torch.cuda.synchronize()
+            for b in range(B):
+                k = min(int(cnt_f[b]), max_det)
+                assert int(cnt_l[b]) == k, (strategy, max_det, b, int(cnt_l[b]), k)
+                assert torch.equal(det_l[b, :k], det_f[b, :k])
+                assert torch.equal(lim.keep_index[b, :k], full.keep_index[b, :k])
+    assert int(cnt_f[0]) > 1536, "the case must really truncate"
+    monkeypatch.setenv("GLSDET_NMS_NO_TOPK", "1")    # same limit on the bitmask path
+    lim = DeviceNMS(B, A, nc, max_det=1000)
+    det_l, cnt_l = lim.launch(dpred, 0.15, 0.5, "auto_cuda")
+    det_f, cnt_f = full.launch(dpred, 0.15, 0.5, "auto_cuda")
+    torch.cuda.synchronize()
+    for b in range(B):
+        k = min(int(cnt_f[b]), 1000)
+        assert int(cnt_l[b]) == k and torch.equal(det_l[b, :k], det_f[b, :k])
+
+
 # ---------------------------------------------------------------------------------------------- whole model
 @pytest.mark.parametrize("meta", META["models"], ids=[m["name"] for m in META["models"]])
 def test_model_matches_reference_golden(meta, native_lib, cuda_device):
