@@ -90,6 +90,10 @@ struct alignas(64) ConvKParams {
 enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
        EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8, EPI_TOWER_PRED_MMA = 9, EPI_BF16_PREPOST = 10 };
 
+// Epilogue classes: the kernel is instantiated once per class so that each binary only carries its own epilogue
+// (smaller instruction footprint - the all-in-one kernel lost 18 % of its epilogue issue slots to instruction-cache
+// misses - and registers sized for that epilogue).  EC_ALL keeps every path (2-CTA kernel, generic fallback).
+enum { EC_ALL = 0, EC_BF16 = 1, EC_BF16_TS = 2, EC_F32 = 3, EC_SMALL = 4, EC_PRED_FMA = 5, EC_PRED_MMA = 6, EC_COUNT = 7 };
 constexpr int kActSiluExact = 100;   // diagnostic (GLSDET_CONV_EXACT_SILU=1): ex2 + rcp SiLU instead of tanh.approx
 constexpr int kStageTileBytes = kBlockM * kRowBytes;   // one 128-row x 64-channel K-major SW128 operand tile
 constexpr int kPredTileBytes = 16 * kRowBytes;         // prediction weights: 16 rows x 64 channels
@@ -407,6 +411,7 @@ struct TsCtx {
   int nthr, bar_id;   // group size / named barrier
   bool issuer;
   bool wide;          // block_n >= 128: each column half owns whole 64-channel tiles; else both halves share one
+  int parts;          // column parts = epilogue warps / 4 (2, or 4 in the 16-warp variant: block_n 64 or 128 only)
 };
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g, uint32_t taddr, int r, int half,
@@ -415,13 +420,21 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
                                             uint32_t& sbuf) {
   const int c2 = p.patch ? (t.b & 1) : 0;        // patch views: image b' = (b*2 + py)*2 + px
   const int c4 = p.patch ? (t.b >> 1) : t.b;
-  const int kc_begin = g.wide ? (half ? (k_tiles + 1) >> 1 : 0) : 0;
-  const int kc_end = g.wide ? (half ? k_tiles : (k_tiles + 1) >> 1) : 1;
+  int kc_begin = g.wide ? (half ? (k_tiles + 1) >> 1 : 0) : 0;
+  int kc_end = g.wide ? (half ? k_tiles : (k_tiles + 1) >> 1) : 1;
+  if (g.parts == 4) {   // one 64-channel tile per group (block_n 64: tile 0 for everybody; 128: tile = half / 2)
+    kc_begin = g.wide ? (half >> 1) : 0;
+    kc_end = kc_begin + 1;
+  }
   for (int kc = kc_begin; kc < kc_end; ++kc, ++sbuf) {
     uint8_t* buf = g.gbuf + (sbuf & 1u) * kStageTileBytes;
     uint8_t* rowp = buf + (r >> 3) * 1024 + (r & 7) * kRowBytes;
-    const int cb = g.wide ? kc * 4 : half * 2;
-    const int ce = g.wide ? kc * 4 + 4 : half * 2 + 2;
+    int cb = g.wide ? kc * 4 : half * 2;
+    int ce = g.wide ? kc * 4 + 4 : half * 2 + 2;
+    if (g.parts == 4) {   // 32 columns per warp (block_n 128) or 16 (block_n 64)
+      cb = g.wide ? kc * 4 + (half & 1) * 2 : half;
+      ce = g.wide ? cb + 2 : half + 1;
+    }
     epi_walk(taddr, cb, ce, [&](const uint32_t (&raw)[16], int c) {
       if (valid) {
         const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte staging row
@@ -440,8 +453,11 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
   }
 }
 
-template <bool k2>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+// EW = epilogue warps (8, or 16 for the TMA-store class: its epilogue is a chain of short dependent instructions per
+// tile, so four warps per scheduler instead of two hide twice the latency; the register budget of that class allows it)
+template <bool k2, int EC, int EW = kEpiWarps>
+__global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __grid_constant__ ConvKParams p) {
+  constexpr int kThreads = (4 + EW) * 32;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -498,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], k2 ? 2 * kEpiWarps : kEpiWarps);  // 2-CTA: the peer's epilogue warps arrive too
+      mbar_init(&tempty_bar[s], k2 ? 2 * EW : EW);  // 2-CTA: the peer's epilogue warps arrive too
     }
     mbar_init(bres_full, 1);
     mbar_init(pred_bar, 1);
@@ -765,7 +781,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     // ------------------------------------------------------------ epilogue
     const int e = warp - 4;
     const int q = e & 3;      // TMEM lane quarter this warp may read (== warp % 4)
-    const int half = e >> 2;  // which half of the accumulator columns
+    const int half = e >> 2;  // which part of the accumulator columns (2 parts with 8 warps, 4 with 16)
     const int r = q * 32 + lane;
     const int py = r >> p.tile_w_log2;
     const int px = r & ((1 << p.tile_w_log2) - 1);
@@ -776,10 +792,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int mt = k2 ? 1 : p.mt;
     TsCtx tsg;
     tsg.wide = p.block_n >= 128;
-    tsg.gbuf = smem_stage + (tsg.wide ? half : 0) * 2 * kStageTileBytes;
-    tsg.nthr = tsg.wide ? 128 : 256;
-    tsg.bar_id = 6 + (tsg.wide ? half : 0);
-    tsg.issuer = (lane == 0) && (tsg.wide ? (q == 0) : (e == 0));
+    if (EW == 16) {
+      // four column parts: block_n = 64 -> all 16 warps share one 64-channel tile; block_n = 128 -> parts (0,1) own
+      // tile 0, parts (2,3) tile 1
+      const int grp = tsg.wide ? (half >> 1) : 0;
+      tsg.gbuf = smem_stage + grp * 2 * kStageTileBytes;
+      tsg.nthr = tsg.wide ? 256 : 512;
+      tsg.bar_id = 6 + grp;
+      tsg.issuer = (lane == 0) && (q == 0) && (tsg.wide ? ((half & 1) == 0) : (half == 0));
+    } else {
+      tsg.gbuf = smem_stage + (tsg.wide ? half : 0) * 2 * kStageTileBytes;
+      tsg.nthr = tsg.wide ? 128 : 256;
+      tsg.bar_id = 6 + (tsg.wide ? half : 0);
+      tsg.issuer = (lane == 0) && (tsg.wide ? (q == 0) : (e == 0));
+    }
+    tsg.parts = EW / 4;
     uint32_t sbuf = 0;     // staging tiles written by this warp group (TMA-store epilogue)
     int it = 0;
     uint32_t tcount = 0;   // tiles processed by this CTA (prediction-MMA barrier phase, FMA scratch slot)
@@ -800,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         case EPI_BF16:
         case EPI_BF16_PRE:
         case EPI_BF16_POST:
-        case EPI_BF16_PREPOST: {
+        case EPI_BF16_PREPOST: { if constexpr (EC == EC_ALL || EC == EC_BF16 || EC == EC_BF16_TS) {
           const bool has_pre = (p.epi == EPI_BF16_PRE || p.epi == EPI_BF16_PREPOST);
           const bool has_post = (p.epi == EPI_BF16_POST || p.epi == EPI_BF16_PREPOST);
           const float* pre = nullptr;
@@ -818,7 +845,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
             }
           }
-          if (p.ts) {
+          if constexpr (EC == EC_ALL || EC == EC_BF16_TS) if (p.ts) {
             const int y_tile = t.y0 + m * p.tile_h;
             if (has_pre && has_post) epi_tile_ts<true, true>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
             else if (has_pre) epi_tile_ts<true, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
@@ -826,6 +853,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             else epi_tile_ts<false, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
             break;
           }
+          if constexpr (EC == EC_ALL || EC == EC_BF16) {
           __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                                 (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
           if (has_pre && has_post) {
@@ -845,17 +873,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, p.act_epi, nullptr, nullptr, orow + c * 16);
             });
           }
+          }  // direct stores
+          }
           break;
         }
-        case EPI_F32_PLAIN: {
+        case EPI_F32_PLAIN: { if constexpr (EC == EC_ALL || EC == EC_F32) {
           float* orow = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                         (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
           epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
             if (valid && t.n0 + c * 16 < p.N) epi16_f32_plain(raw, sb + c * 16, orow + c * 16);
           });
+          }
           break;
         }
-        case EPI_NCHW_RAW: {  // N <= 16: raw logits, reference layout; lanes are consecutive x -> coalesced per channel
+        case EPI_NCHW_RAW: { if constexpr (EC == EC_ALL || EC == EC_SMALL) {  // N <= 16: raw logits, reference layout; lanes are consecutive x -> coalesced per channel
           const int64_t plane = static_cast<int64_t>(p.Ho) * p.Wo;
           float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                      static_cast<int64_t>(p.out_coff) * plane + static_cast<int64_t>(oy) * p.Wo + ox;
@@ -866,9 +897,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (j < p.N) o[j * plane] = __uint_as_float(raw[j]) + sb[j];
             }
           });
+          }
           break;
         }
-        case EPI_ROWS_BOX: {  // N == 5: utils_bbox.py:270-305 on (x, y, w, h, obj) -> decoded row prefix
+        case EPI_ROWS_BOX: { if constexpr (EC == EC_ALL || EC == EC_SMALL) {  // N == 5: utils_bbox.py:270-305 on (x, y, w, h, obj) -> decoded row prefix
           float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                      (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
           epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
@@ -880,9 +912,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               o[4] = 1.0f / (1.0f + expf(-(__uint_as_float(raw[4]) + sb[4])));
             }
           });
+          }
           break;
         }
-        case EPI_ROWS_SIGMOID: {  // N <= 16 class probabilities of a decoded row
+        case EPI_ROWS_SIGMOID: { if constexpr (EC == EC_ALL || EC == EC_SMALL) {  // N <= 16 class probabilities of a decoded row
           float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                      (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
           epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
@@ -892,9 +925,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (j < p.N) o[j] = 1.0f / (1.0f + expf(-(__uint_as_float(raw[j]) + sb[j])));
             }
           });
+          }
           break;
         }
-        case EPI_TOWER_PRED: {
+        case EPI_TOWER_PRED: { if constexpr (EC == EC_ALL || EC == EC_PRED_FMA) {
           // second tower conv + prediction conv: the activated tile never leaves the SM.  Each thread reduces its
           // row over its half of the channels; the two warps of a lane quarter meet at a 64-thread named barrier.
           float acc[16];
@@ -931,9 +965,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               if (j < p.pred_n) acc[j] += __ldg(p.pred_b + j);
             store_pred(p, acc, t.b, oy, ox);
           }
+          }
           break;
         }
-        case EPI_TOWER_PRED_MMA: {
+        case EPI_TOWER_PRED_MMA: { if constexpr (EC == EC_ALL || EC == EC_PRED_MMA) {
           // second tower conv + prediction conv on the tensor core: the activated tile goes to shared memory as a
           // bf16 K-major operand (row = pixel, 128-byte swizzle), one thread issues M128 x N16 x K(block_n) MMAs into
           // the first 16 columns of this (already drained) accumulator, and the lower-half warps decode + store.
@@ -1000,9 +1035,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
               store_pred(p, y, t.b, oy, ox);
             }
           }
+          }
           break;
         }
-        default: {
+        default: { if constexpr (EC == EC_ALL) {
           for (int c = c_begin; c < c_end; ++c) {
             uint32_t v[16];
             tmem_ld16(taddr + static_cast<uint32_t>(c * 16), v);
@@ -1010,7 +1046,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (valid && t.n0 + c * 16 < p.N)
               epilogue_store16(p, v, s_bias + t.n0 + c * 16, t.b, oy, ox, t.n0 + c * 16);
           }
-        }
+        } }
       }
       }  // M tiles of the work item
       tc_fence_before();
@@ -1043,7 +1079,26 @@ struct glsdet_conv {
   int grid;
   int smem_bytes;
   int two_cta;   // launched as clusters of 2 CTAs issuing tcgen05.mma.cta_group::2
+  int ec;        // epilogue class = kernel instantiation (EC_*)
+  int threads;   // CTA size of that instantiation
 };
+
+namespace {
+typedef void (*ConvKernelFn)(const ConvKParams);
+constexpr int EC_BF16_TS16 = EC_COUNT;   // TMA-store class with 16 epilogue warps (640 threads)
+ConvKernelFn conv_kernel_for(int ec) {
+  switch (ec) {
+    case EC_BF16_TS16: return conv_gemm_kernel<false, EC_BF16_TS, 16>;
+    case EC_BF16: return conv_gemm_kernel<false, EC_BF16>;
+    case EC_BF16_TS: return conv_gemm_kernel<false, EC_BF16_TS>;
+    case EC_F32: return conv_gemm_kernel<false, EC_F32>;
+    case EC_SMALL: return conv_gemm_kernel<false, EC_SMALL>;
+    case EC_PRED_FMA: return conv_gemm_kernel<false, EC_PRED_FMA>;
+    case EC_PRED_MMA: return conv_gemm_kernel<false, EC_PRED_MMA>;
+    default: return conv_gemm_kernel<false, EC_ALL>;
+  }
+}
+}  // namespace
 
 namespace {
 
@@ -1438,13 +1493,25 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   }
   if (rc) { free(mem); return rc; }
 
+  switch (k.epi) {
+    case EPI_BF16: case EPI_BF16_PRE: case EPI_BF16_POST: case EPI_BF16_PREPOST: op->ec = k.ts ? EC_BF16_TS : EC_BF16; break;
+    case EPI_F32_PLAIN: op->ec = EC_F32; break;
+    case EPI_NCHW_RAW: case EPI_ROWS_BOX: case EPI_ROWS_SIGMOID: op->ec = EC_SMALL; break;
+    case EPI_TOWER_PRED: op->ec = EC_PRED_FMA; break;
+    case EPI_TOWER_PRED_MMA: op->ec = EC_PRED_MMA; break;
+    default: op->ec = EC_ALL;
+  }
+  if (op->ec == EC_BF16_TS && (g.block_n == 64 || g.block_n == 128) && getenv("GLSDET_CONV_EPI8") == nullptr)
+    op->ec = EC_BF16_TS16;
+  if (op->two_cta || getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
+  op->threads = (op->ec == EC_BF16_TS16) ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<true, EC_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    for (int ec = 0; ec <= EC_COUNT && e == cudaSuccess; ++ec)
+      e = cudaFuncSetAttribute(conv_kernel_for(ec), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) {
       free(mem);
       set_error("cudaFuncSetAttribute(max dynamic smem) failed: %s", cudaGetErrorString(e));
@@ -1477,7 +1544,7 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, op->kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, EC_ALL>, op->kp);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(conv_gemm_kernel<2cta>) failed: %s", cudaGetErrorString(e));
       return 1;
@@ -1489,7 +1556,7 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
     // tail of the previous kernel of the stream; the kernel itself waits (griddepcontrol.wait) before touching memory
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(op->grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(op->threads);
     cfg.dynamicSmemBytes = op->smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[1];
@@ -1497,14 +1564,14 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<false>, op->kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(op->ec), op->kp);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(conv_gemm_kernel, PDL) failed: %s", cudaGetErrorString(e));
       return 1;
     }
     return count_launch("conv_gemm_kernel");
   }
-  conv_gemm_kernel<false><<<op->grid, kThreads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
+  conv_kernel_for(op->ec)<<<op->grid, op->threads, op->smem_bytes, static_cast<cudaStream_t>(stream)>>>(op->kp);
   return count_launch("conv_gemm_kernel");
 }
 

@@ -36,7 +36,7 @@ def main(path, out=None, ops_path=None):
                     f"{d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']:8.1f} "
                     f"{d['dram__bytes_read.sum']:10.1f} {d['dram__bytes_write.sum']:10.1f} {d['lts__t_bytes.sum']:9.1f}"
                     + (f"  {ops[i]['group']:5s} {ops[i]['k']}x{ops[i]['k']}/{ops[i]['s']} {ops[i]['cin']:4d}->{ops[i]['n']:3d}"
-                       f"{'+p' + str(ops[i]['pred']) if ops[i]['pred'] else '':4s} @{ops[i]['h']}x{ops[i]['w']} {ops[i]['gflop']:7.1f} GF "
+                       f"{'+p' + str(ops[i]['pred']) if ops[i]['pred'] else ('*W/img' if ops[i].get('batched') else ''):6s} @{ops[i]['h']}x{ops[i]['w']} {ops[i]['gflop']:7.1f} GF "
                        f"{ops[i]["gflop"] / d["gpu__time_duration.sum"] * 1e3:7.1f}" if ops and i < len(ops) else ""))
     text.append(f"total {tot:.1f} us over {len(per)} launches")
     s = "\n".join(text)

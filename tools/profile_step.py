@@ -16,8 +16,10 @@ from glsdet_b200.ops import ConvOp  # noqa: E402
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "p1":
+        bench.VARIANT = "p1"
     sd = bench.make_weights()
-    from glsdet_b200.yolox_ffa import YoloBody
+    YoloBody = bench.body_class()
 
     net = YoloBody(bench.NUM_CLASSES, bench.PHI)
     net.load_state_dict(sd, strict=True)
@@ -39,10 +41,11 @@ def main():
             if isinstance(op, ConvOp):
                 d = op.desc
                 ops.append(dict(group=group, k=d.ksize, s=d.stride, cin=d.src0_c + d.src1_c, n=d.out_channels,
-                                h=d.height, w=d.width, gflop=op.flops / 1e9, pred=int(d.pred_channels)))
+                                h=d.height, w=d.width, gflop=op.flops / 1e9, pred=int(d.pred_channels),
+                                batched=int(d.weight_batch_stride != 0), patch=int(d.patch_mode)))
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
-    (out / "step_ops.json").write_text(json.dumps(ops))
+    (out / f"step_ops_{bench.VARIANT}.json").write_text(json.dumps(ops))
     for _ in range(3):
         step()
     torch.cuda.synchronize()
