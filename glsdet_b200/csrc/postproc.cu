@@ -33,7 +33,7 @@ namespace glsdet {
 
 constexpr int kSortChunk = 4096;    // keys sorted per CTA in shared memory
 constexpr int kSortThreads = 512;
-constexpr int kNmsThreads = 256;
+constexpr int kNmsThreads = 1024;   // 8 warps per scheduler: the kept-list sweep of a chunk is latency-bound
 constexpr int kKeptSmem = 1536;     // kept boxes cached in shared memory per segment
 constexpr int kMaxClasses = 256;    // 8 label bits in the sort key
 constexpr uint64_t kPadKey = ~0ull;
@@ -646,12 +646,13 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work
     }
     // phase 2: pairwise masks inside the chunk (row i suppresses later column j)
     {
-      const int i = tid & 63, part = tid >> 6;  // 4 parts x 16 columns
+      constexpr int kParts = kNmsThreads / 64, kCols = 64 / kParts;
+      const int i = tid & 63, part = tid >> 6;  // kParts parts x kCols columns
       if (i < mcnt) {
         unsigned long long bits = 0ull;
         const float4 bi = cbox[i];
         const float ai = carea[i];
-        for (int j = max(i + 1, part * 16); j < min(mcnt, part * 16 + 16); ++j)
+        for (int j = max(i + 1, part * kCols); j < min(mcnt, part * kCols + kCols); ++j)
           if (iou_exceeds(bi, ai, cbox[j], carea[j], thr, thr_nonneg)) bits |= (1ull << j);
         if (bits) atomicOr(&cmask[i], bits);
       }
