@@ -234,7 +234,19 @@ def run_native_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout while the communicator is created; the contract is ONE JSON
+        # line on stdout, so route fd 1 to stderr for the duration of the (eager) communicator set-up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = N.load()
 
     sd = make_weights()
