@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=16, help="images per pass of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample: repeat passes for about this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", default="p0", choices=["p0", "p1"],
+    ap.add_argument("--variant", default="p0", choices=["p0", "p1", "p2"],
                     help="p0 = BASELINE configs[1] (models/ffa/yolox_ffa.py, the default and the judged metric); "
                          "p1 = models/new/yolox10.py (patch non-local attention neck, SURVEY.md section 8d row 2')")
     return ap.parse_args()
@@ -127,11 +127,13 @@ def make_weights():
     from glsdet_b200.synthetic import synthetic_state_dict
 
     return synthetic_state_dict(NUM_CLASSES, PHI, seed=WEIGHT_SEED, flavour="calibrated",
-                                variant="ffa" if VARIANT == "p0" else "p1")
+                                variant={"p0": "ffa", "p1": "p1", "p2": "p2"}[VARIANT])
 
 
 def body_class():
-    if VARIANT == "p1":
+    if VARIANT == "p2":
+        from glsdet_b200.yolo_patch_nonlocal_plus import YoloBody
+    elif VARIANT == "p1":
         from glsdet_b200.yolox10 import YoloBody
     else:
         from glsdet_b200.yolox_ffa import YoloBody
@@ -141,6 +143,8 @@ def body_class():
 def ref_neck_head(sd, feats):
     from oracle import ref_path
 
+    if VARIANT == "p2":
+        return ref_path.p2_neck_head(sd, feats)
     return ref_path.neck_head(sd, feats) if VARIANT == "p0" else ref_path.p1_neck_head(sd, feats)
 
 

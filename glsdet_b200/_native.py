@@ -39,8 +39,14 @@ class ConvDesc(C.Structure):
         ("dec_stride", C.c_float), ("dec_in_w", C.c_float), ("dec_in_h", C.c_float),
         ("pred_weight", C.c_void_p), ("pred_bias", C.c_void_p), ("pred_channels", C.c_int32), ("pred_act", C.c_int32),
         ("weight_batch_stride", C.c_int64), ("weight_ld", C.c_int32), ("src_shared", C.c_int32),
-        ("patch_mode", C.c_int32),
+        ("src_shared_div", C.c_int32), ("patch_mode", C.c_int32),
     ]
+
+
+class Rect(C.Structure):
+    """Mirror of struct glsdet_rect."""
+
+    _fields_ = [(n, C.c_int32) for n in ("sb", "sy", "sx", "db", "dy", "dx", "h", "w")]
 
 
 class ConvF32Desc(C.Structure):
@@ -88,6 +94,11 @@ SIGNATURES = {
                                C.c_int32, C.c_void_p]),
     "glsdet_scale_pixel_shuffle_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                                  C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_rect_copy": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                   C.c_void_p]),
+    "glsdet_nhwc_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -54,6 +54,7 @@ struct alignas(64) ConvKParams {
   int32_t m_tiles, total_pairs;   // 2-CTA mode: a CTA pair takes M tiles (2i, 2i+1) of one N block
   int32_t block_n, N;
   int32_t taps, stride;
+  int32_t ksz;               // kernel size (1, 3, 5, 7); taps = ksz * ksz
   int32_t chunks0, chunks1;
   int32_t sa, sb;            // A / B ring depths
   int32_t nsub;              // MMA sub-steps per A step: 3 (ky taps of a 3x3 stride-1 conv) or 1
@@ -69,6 +70,7 @@ struct alignas(64) ConvKParams {
   int32_t ts;                // bf16 epilogues stage the tile in shared memory and TMA-store it
   int32_t w_batched;         // one weight matrix per image (third coordinate of tmB)
   int32_t a_shared;          // k > 0: image b reads activation image b % k (static matrices used as activations)
+  int32_t a_div;             // with a_shared: image b reads activation image b / a_div instead of b % a_shared
   int32_t patch;             // src0 / post_res / out are 2x2 patch views (image b' = (b*2 + py)*2 + px)
   const float* bias;
   int32_t act;
@@ -670,25 +672,26 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       const TileCoord t = decode_tile(p, tile);
       wb = t.b;
       const int ac2 = p.patch ? (t.b & 1) : 0;                              // patch views: b' = (b*2 + py)*2 + px
-      const int ab = p.a_shared ? (t.b % p.a_shared) : (p.patch ? (t.b >> 1) : t.b);
+      const int ab = p.a_shared ? (p.a_div ? t.b / p.a_div : t.b % p.a_shared) : (p.patch ? (t.b >> 1) : t.b);
       if (p.stride == 1) {
         for (int src = 0; src < 2; ++src) {
           const int nch = src ? p.chunks1 : p.chunks0;
           if (nch == 0) continue;
           const int kbase = src ? p.taps * p.chunks0 : 0;  // weight K order: (source, tap, chunk)
-          if (p.nsub == 3) {
-            for (int kx = 0; kx < 3; ++kx) {
+          const int pad = p.ksz >> 1;
+          if (p.nsub > 1) {   // one A box of (rows + ksz - 1) rows per (kx, chunk) serves all ky taps
+            for (int kx = 0; kx < p.ksz; ++kx) {
               for (int ch = 0; ch < nch; ++ch) {
-                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - 1, 0, t.y0 - 1, ab);  // mt * tile_h + 2 rows
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - pad, 0, t.y0 - pad, ab);
                 if (p.bres) continue;
                 if (p.bgroup == 3) load_b3(src, kbase + kx * nch + ch, t.n0);         // ky = 0,1,2 in one box
-                else for (int ky = 0; ky < 3; ++ky) load_b(kbase + (ky * 3 + kx) * nch + ch, t.n0);
+                else for (int ky = 0; ky < p.ksz; ++ky) load_b(kbase + (ky * p.ksz + kx) * nch + ch, t.n0);
               }
             }
           } else {
             for (int tap = 0; tap < p.taps; ++tap) {
-              const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-              const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+              const int dy = tap / p.ksz - pad;
+              const int dx = tap % p.ksz - pad;
               for (int ch = 0; ch < nch; ++ch) {
                 load_a(&p.tmA[src], ch * kChunkK, t.x0 + dx, ac2, t.y0 + dy, ab);
                 load_b(kbase + tap * nch + ch, t.n0);
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           uint32_t b_addr;
           bool last_of_b = false;
           if (p.bres) {
-            const int kchunk = (p.nsub == 3) ? (src ? p.taps * p.chunks0 : 0) + (sub * 3 + o) * nch + ch : a;
+            const int kchunk = (p.nsub > 1) ? (src ? p.taps * p.chunks0 : 0) + (sub * p.ksz + o) * nch + ch : a;
             b_addr = smem_u32(smem_b + kchunk * b_tap_bytes);
           } else {
             if (bsub == 0) mbar_wait(&b_full[sb], phb);
@@ -773,7 +776,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
         if (++sa == p.sa) { sa = 0; pha ^= 1u; }
         if (++ch == nch) {
           ch = 0;
-          if (++o == 3) { o = 0; ++src; }
+          if (++o == p.ksz) { o = 0; ++src; }
         }
       }
     }
@@ -1108,7 +1111,9 @@ struct ConvGeom {
 
 int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   GLSDET_REQUIRE(d != nullptr, "conv: null descriptor");
-  GLSDET_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3 (got %d)", d->ksize);
+  GLSDET_REQUIRE(d->ksize == 1 || d->ksize == 3 || d->ksize == 5 || d->ksize == 7,
+                 "conv: ksize must be 1, 3, 5 or 7 (got %d)", d->ksize);
+  GLSDET_REQUIRE(d->ksize <= 3 || d->stride == 1, "conv: 5x5 / 7x7 convs are stride 1");
   GLSDET_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   GLSDET_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, "conv: bad input size");
   GLSDET_REQUIRE(d->src0_c > 0 && d->src0_ld >= d->src0_c, "conv: bad src0 channels/pitch");
@@ -1233,7 +1238,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // L2->SM traffic, but 5-15 % slower than the 1-CTA kernel at these shapes, so it is opt-in: GLSDET_CONV_2CTA=1.
   bool two_cta = false;
   if (const char* e = getenv("GLSDET_CONV_2CTA")) {
-    if (e[0] == '1') two_cta = d->stride == 1 && (g.block_n % 32) == 0;
+    if (e[0] == '1') two_cta = d->stride == 1 && d->ksize <= 3 && (g.block_n % 32) == 0;
   }
   op->two_cta = two_cta ? 1 : 0;
   const int sms = device_sm_count();
@@ -1287,11 +1292,13 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
 
   // A/B rings.  3x3 stride-1: one (mt * tile_h + 2)-row A stage feeds three B sub-steps (ky taps).
   const int super_h = k.tile_h * mt;
-  const bool vreuse = (d->ksize == 3 && d->stride == 1 && (super_h + 2) <= 256 && getenv("GLSDET_CONV_NO_VREUSE") == nullptr);
-  k.nsub = vreuse ? 3 : 1;
-  const int box_rows = vreuse ? super_h + 2 : super_h;
+  const bool vreuse = (d->ksize >= 3 && d->stride == 1 && (super_h + d->ksize - 1) <= 256 &&
+                       (getenv("GLSDET_CONV_NO_VREUSE") == nullptr || d->ksize > 3));
+  k.ksz = d->ksize;
+  k.nsub = vreuse ? d->ksize : 1;
+  const int box_rows = vreuse ? super_h + d->ksize - 1 : super_h;
   k.a_bytes = box_rows * best_w * kRowBytes;
-  k.a_steps = (vreuse ? 3 : g.taps) * (g.chunks0 + g.chunks1);
+  k.a_steps = (vreuse ? d->ksize : g.taps) * (g.chunks0 + g.chunks1);
   k.m_tiles = k.tiles_x * k.tiles_y * k.B;
   k.total_pairs = ((k.m_tiles + 1) / 2) * k.n_blocks;
 
@@ -1360,7 +1367,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     bres = false;
     k.bgroup = 1;
     if (two_cta) {  // single ring; a stage = A box + all nsub taps of this CTA's half of B
-      k.bgroup = want_bgroup3 && vreuse ? 3 : 1;
+      k.bgroup = want_bgroup3 && vreuse && d->ksize == 3 ? 3 : 1;
       const int b_bytes2 = k.nsub * (g.block_n / 2) * kRowBytes;
       int stages = budget / (k.a_bytes + b_bytes2);
       if (stages > kMaxStages) stages = kMaxStages;
@@ -1381,7 +1388,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
         return true;
       }
     }
-    if (vreuse && want_bgroup3 && g.block_n <= 128 && !w_batched) {
+    if (vreuse && d->ksize == 3 && want_bgroup3 && g.block_n <= 128 && !w_batched) {
       const int stages = budget / (k.a_bytes + 3 * b_tap_bytes);
       if (stages >= 3) {
         k.bgroup = 3;
@@ -1420,6 +1427,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.ts = ts ? 1 : 0;
   k.w_batched = w_batched ? 1 : 0;
   k.a_shared = d->src_shared > 0 ? d->src_shared : 0;
+  k.a_div = (d->src_shared > 0 && d->src_shared_div > 0) ? d->src_shared_div : 0;
   k.patch = patch ? 1 : 0;
 
   k.bias = d->bias; k.act = d->act;

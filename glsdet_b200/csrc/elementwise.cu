@@ -485,3 +485,89 @@ extern "C" int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int3
       src_coff, dst_ld, dst_coff, total);
   return glsdet::count_launch("upsample2x_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------- rectangle copies
+namespace glsdet {
+
+struct RectList {
+  glsdet_rect r[8];
+};
+
+// one thread per (rectangle pixel, 8-channel vector); blockIdx.y = rectangle
+__global__ void __launch_bounds__(256) rect_copy_kernel(const __nv_bfloat16* __restrict__ src, int sh, int sw, int sld, int scoff,
+                                                        __nv_bfloat16* __restrict__ dst, int dh, int dw, int dld, int dcoff,
+                                                        int B, int C, RectList rl) {
+  const glsdet_rect q = rl.r[blockIdx.y];
+  const int nvec = C >> 3;
+  const int64_t total = static_cast<int64_t>(B) * q.h * q.w * nvec;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    int64_t pix = i / nvec;
+    const int x = static_cast<int>(pix % q.w);
+    pix /= q.w;
+    const int y = static_cast<int>(pix % q.h);
+    const int b = static_cast<int>(pix / q.h);
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(
+        src + ((static_cast<int64_t>(q.sb + b) * sh + q.sy + y) * sw + q.sx + x) * sld + scoff) + v);
+    *(reinterpret_cast<uint4*>(dst + ((static_cast<int64_t>(q.db + b) * dh + q.dy + y) * dw + q.dx + x) * dld + dcoff) + v) = val;
+  }
+}
+
+// [B, T, ld] bf16 (channels coff..coff+C) -> [B, rows, t_ld] bf16 with dst[b][c][t] = src[b][t][c]; 32 x 32 smem tiles
+__global__ void __launch_bounds__(256) nhwc_transpose_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                             int T, int C, int sld, int scoff, int rows, int t_ld) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  for (int i = ly; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + lx;
+    tile[i][lx] = (t < T && c < C) ? src[(static_cast<int64_t>(b) * T + t) * sld + scoff + c] : __float2bfloat16_rn(0.0f);
+  }
+  __syncthreads();
+  for (int i = ly; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + lx;
+    if (c < C && t < T) dst[(static_cast<int64_t>(b) * rows + c) * t_ld + t] = tile[lx][i];
+  }
+}
+
+}  // namespace glsdet
+
+extern "C" int glsdet_rect_copy(const void* src, int32_t src_h, int32_t src_w, int32_t src_ld, int32_t src_coff, void* dst,
+                                int32_t dst_h, int32_t dst_w, int32_t dst_ld, int32_t dst_coff, int32_t batch,
+                                int32_t channels, const glsdet_rect* rects, int32_t num_rects, void* stream) {
+  GLSDET_REQUIRE(src && dst && rects && batch > 0 && channels > 0 && num_rects >= 1 && num_rects <= 8,
+                 "rect_copy: bad arguments (1..8 rectangles)");
+  GLSDET_REQUIRE(((channels | src_ld | src_coff | dst_ld | dst_coff) % 8) == 0, "rect_copy: channels, pitches and offsets "
+                 "must be multiples of 8");
+  GLSDET_REQUIRE(src_coff + channels <= src_ld && dst_coff + channels <= dst_ld, "rect_copy: window exceeds pitch");
+  glsdet::RectList rl;
+  int64_t biggest = 0;
+  for (int i = 0; i < num_rects; ++i) {
+    const glsdet_rect& q = rects[i];
+    GLSDET_REQUIRE(q.h > 0 && q.w > 0 && q.sy >= 0 && q.sx >= 0 && q.dy >= 0 && q.dx >= 0 && q.sb >= 0 && q.db >= 0 &&
+                   q.sy + q.h <= src_h && q.sx + q.w <= src_w && q.dy + q.h <= dst_h && q.dx + q.w <= dst_w,
+                   "rect_copy: rectangle %d leaves its tensor", i);
+    rl.r[i] = q;
+    const int64_t n = static_cast<int64_t>(batch) * q.h * q.w * (channels / 8);
+    if (n > biggest) biggest = n;
+  }
+  int64_t gx = (biggest + 255) / 256;
+  if (gx > 4096) gx = 4096;
+  glsdet::rect_copy_kernel<<<dim3(static_cast<unsigned>(gx), num_rects), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), src_h, src_w, src_ld, src_coff, reinterpret_cast<__nv_bfloat16*>(dst), dst_h,
+      dst_w, dst_ld, dst_coff, batch, channels, rl);
+  return glsdet::count_launch("rect_copy_kernel");
+}
+
+extern "C" int glsdet_nhwc_transpose(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels,
+                                     int32_t src_ld, int32_t src_coff, int32_t dst_rows, int32_t dst_ld, void* stream) {
+  GLSDET_REQUIRE(src && dst && batch > 0 && pixels > 0 && channels > 0, "nhwc_transpose: bad arguments");
+  GLSDET_REQUIRE(src_coff + channels <= src_ld && dst_rows >= channels && dst_ld >= pixels, "nhwc_transpose: sizes");
+  dim3 grid((pixels + 31) / 32, (channels + 31) / 32, batch);
+  GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nhwc_transpose: grid too large");
+  glsdet::nhwc_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), pixels, channels, src_ld, src_coff,
+      dst_rows, dst_ld);
+  return glsdet::count_launch("nhwc_transpose_kernel");
+}

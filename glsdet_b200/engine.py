@@ -6,6 +6,9 @@ Three topologies share one builder:
                       three levels, CSP block on dark2, cross-level cls branch;
   * variant "ffa"   - models/ffa/yolox_ffa.py (GLSDet P0): four levels (strides 4..32), FFA fusion on (P3_out,
                       P4_out), CSP block on dark2, level 0 uses tower index 3;
+  * variant "p2"    - models/block/non_local/yolo_patch_nonlocal_plus.py (GLSDet P2): Patch_Conv_NonLocal on dark3 and
+                      Patch_Conv on dark4 feeding C3_p4 / C3_n3 as third inputs, 7x7 / 5x5 / 3x3 identity convs behind
+                      the neck outputs, stock three-level head;
   * variant "stock" - models/base/yolox.py and, with renamed keys, the mmdet pair YOLOXPAFPN + YOLOXHead
                       (yolox-ufp/mmdet/models/necks/yolox_pafpn.py, dense_heads/yolox_head.py): three levels.
 
@@ -33,7 +36,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import (ConvOp, ConvOpF32, GatherBiasOp, PatchTransposeOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
+from .ops import (ConvOp, ConvOpF32, GatherBiasOp, NhwcTransposeOp, PatchTransposeOp, RectCopyOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
                   nchw_to_nhwc, nhwc_to_nchw)
 
 BN_EPS = 1e-3
@@ -55,7 +58,7 @@ class FFAPathPlan:
         assert precision in ("bf16", "fp32")
         self.fp32 = precision == "fp32"
         self.dtype = torch.float32 if self.fp32 else torch.bfloat16
-        if self.fp32 and variant == "p1":
+        if self.fp32 and variant in ("p1", "p2"):
             raise NotImplementedError("the fp32 accuracy mode covers the P0 and stock topologies")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
@@ -65,7 +68,7 @@ class FFAPathPlan:
         self.parts = parts
         self.variant = variant
         self.decode = decode
-        assert variant in ("ffa", "stock", "p1") and decode in ("drone", "mmdet")
+        assert variant in ("ffa", "stock", "p1", "p2") and decode in ("drone", "mmdet")
         sd = {}
         for k, v in state_dict.items():
             if k.endswith("num_batches_tracked"):
@@ -173,14 +176,15 @@ class FFAPathPlan:
         w2, b2 = self._folded(p + ".conv2")
         w12, b12 = torch.cat([w1, w2], 0), torch.cat([b1, b2], 0)
         hid = w1.shape[0]
+        srcs = list(src) if isinstance(src, (list, tuple)) else [src]
         X = self._buf(x_name, stride, 2 * hid)
         if up_src is not None:
             ca = up_src.c
             T = self._buf(x_name + "_T", stride * 2, 2 * hid, torch.float32)
             self._conv(ops, w12[:, :ca].contiguous(), None, [up_src], View(T), 1, act=N.ACT_NONE)
-            self._conv(ops, w12[:, ca:].contiguous(), b12, [src], View(X), 1, pre_res=View(T), pre_shift=1)
+            self._conv(ops, w12[:, ca:].contiguous(), b12, srcs, View(X), 1, pre_res=View(T), pre_shift=1)
         else:
-            self._conv(ops, w12, b12, [src], View(X), 1)
+            self._conv(ops, w12, b12, srcs, View(X), 1)
         bb = self._buf(x_name + "_b", stride, hid)
         j = 0
         while f"{p}.m.{j}.conv1.conv.weight" in sd:
@@ -190,7 +194,27 @@ class FFAPathPlan:
         self._base_conv(ops, p + ".conv3", [View(X)], out, **out_kw)
 
     # ------------------------------------------------------------------ graph
+    def _build_p2(self):
+        """GLSDet P2 (yolo_patch_nonlocal_plus.py): patch-conv neck of _build_neck_p2 + the stock three-level head."""
+        c0, c1, c2, hc = self.c0, self.c1, self.c2, self.hc
+        d3, d4, d5 = self._buf("dark3", 8, c0), self._buf("dark4", 16, c1), self._buf("dark5", 32, c2)
+        self.pre_loads = []
+        self.inputs = (d3, d4, d5)
+        if "neck" in self.parts:
+            self.neck_out = self._build_neck_p2(self.neck_ops, d3, d4, d5)
+        else:
+            self.neck_out = (View(self._buf("P3_out", 8, c0)), View(self._buf("P4_out", 16, c1)),
+                             View(self._buf("P5_out", 32, c2)))
+        self.p = [self._buf(f"p{k}", s, hc) for k, s in enumerate(self.strides)]
+        if "stems" in self.parts:
+            for k, src in enumerate(self.neck_out):
+                self._base_conv(self.stem_ops, f"head.stems.{k}", [src], View(self.p[k]))
+        if "towers" in self.parts:
+            self._build_towers()
+
     def _build(self):
+        if self.variant == "p2":
+            return self._build_p2()
         c0, c1, c2, hc = self.c0, self.c1, self.c2, self.hc
         ffa = self.variant == "ffa"
         p1 = self.variant == "p1"
@@ -298,13 +322,31 @@ class FFAPathPlan:
                                       "size that is a multiple of 64 (unequal 2x2 splits, Non_local_family.py:230-233, "
                                       "are not supported)")
         T = (H // 2) * (W_ // 2)
+        Bp = 4 * B
+        xt, Ca = self._nonlocal_operand(p, Bp, C, T)
+        self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
+        Wm, bias = self._nonlocal_gemms(ops, p, xt, C, T, Bp, dict(src_shared=4))
+        nl = self._buf(p + ".nl", stride, C)
+        self._conv(ops, None, None, [View(x)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
+                   patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
+        self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
+
+    def _nonlocal_operand(self, p: str, Bp: int, C: int, T: int):
+        """Per-patch transposed operand Xt[b'][c][t] with the ones row (channel sums / conv biases) preset."""
         Tp = (T + 63) // 64 * 64
         Ca = C + 64
-        Bp = 4 * B
-        xt = torch.zeros((Bp, Ca, Tp), dtype=torch.bfloat16, device=dev)
+        xt = torch.zeros((Bp, Ca, Tp), dtype=torch.bfloat16, device=self.device)
         xt[:, C, :T] = 1.0
         self._bufs[p + ".xt"] = xt
-        self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
+        return xt, Ca
+
+    def _nonlocal_gemms(self, ops, p: str, xt: torch.Tensor, C: int, T: int, Bp: int, shared_kw: dict):
+        """Gram matrix and the two C x C products of the reassociated non-local block for Bp patch images; returns
+        (W [Bp, 1, C, Ca] bf16: columns 0..C-1 = W_eff, column C = b_eff - b_o;  bias [Bp, 1, 1, C] fp32 = b_eff).
+        `shared_kw` tells the conv operator how a patch image selects its position's static matrices
+        (position order lt, rt, lb, rb = py * 2 + px)."""
+        sd, dev = self.sd, self.device
+        Ca, Tp = xt.shape[1], xt.shape[2]
         a1 = torch.zeros((4, C, Ca), dtype=torch.float64, device=dev)
         a2t = torch.zeros((4, Ca, Ca), dtype=torch.float64, device=dev)
         bo = torch.zeros((4, C), dtype=torch.float32, device=dev)
@@ -320,6 +362,9 @@ class FFAPathPlan:
             bo[i] = sd[q + "conv_out.bias"].float()
         a1 = a1.to(torch.bfloat16).view(4, 1, C, Ca).contiguous()
         a2t = a2t.to(torch.bfloat16).view(4, 1, Ca, Ca).contiguous()
+        div = shared_kw.get("src_shared_div", 0)
+        img_pos = (torch.arange(Bp, device=dev) // div) if div else (torch.arange(Bp, device=dev) % 4)
+        bo_full = bo[img_pos].contiguous()               # [Bp, C]: b_o of every patch image
         S = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
         Zt = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
         Wm = torch.empty((Bp, 1, C, Ca), dtype=torch.bfloat16, device=dev)
@@ -329,17 +374,93 @@ class FFAPathPlan:
         self._conv(ops, None, None, [View(xt.view(Bp, 1, Ca, Tp))], View(S), 1, act=none, weight_raw=xt, n_out=Ca)
         # Zt[k][i] = sum_j A2'[j][k] S[i][j]
         self._conv(ops, None, None, [View(a2t)], View(Zt), 1, act=none, weight_raw=S.view(Bp, Ca, Ca), n_out=Ca,
-                   src_shared=4, batch=Bp)
+                   batch=Bp, **shared_kw)
         # W[n][k] = sum_i A1[n][i] Z[i][k]
         self._conv(ops, None, None, [View(a1)], View(Wm), 1, act=none, weight_raw=Zt.view(Bp, Ca, Ca), n_out=Ca,
-                   src_shared=4, batch=Bp)
-        gb = GatherBiasOp(Wm.view(Bp, C, Ca), bo, bias, C)
-        ops.append(gb)
-        nl = self._buf(p + ".nl", stride, C)
-        self._conv(ops, None, None, [View(x)], View(nl), 1, act=none, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
-                   patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
-        self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
-        self._keepalive = getattr(self, "_keepalive", []) + [a1, a2t, bo, S, Zt, Wm, bias]
+                   batch=Bp, **shared_kw)
+        ops.append(GatherBiasOp(Wm.view(Bp, C, Ca), bo_full, bias, C))
+        self._keepalive = getattr(self, "_keepalive", []) + [a1, a2t, bo_full, S, Zt, Wm, bias]
+        return Wm, bias
+
+    def _build_patch_conv(self, ops, p: str, x: torch.Tensor, stride: int, nonlocal_: bool, out: View):
+        """Patch_Conv / Patch_Conv_NonLocal (models/block/non_local/Identity_Conv.py:292-318, 353-384): 2x2 split, one
+        3x3 BaseConv per patch position (own weights, zero padding at the patch borders), [the dot-product non-local
+        block per patch, reassociated as in _build_nonlocal], seam convs on the left / right / top / bottom halves,
+        re-tile, 1x1 channel conv with bias.  Patches live as dense images ordered by position
+        (b' = position * B + b, position = py * 2 + px), so every conv is a plain dense launch; the split, the halves
+        and the re-tiling are rectangle copies."""
+        sd, dev = self.sd, self.device
+        B, H, W_, Cin = x.shape
+        if H % (2 * stride) or W_ % (2 * stride):
+            raise NotImplementedError("patch convs need equal 2x2 patches (unequal splits are not supported)")
+        mid = sd[f"{p}.feat_patchconv_lt.conv.weight"].shape[0]
+        h2, w2 = H // 2, W_ // 2
+        hq, wq = h2 // stride, w2 // stride
+        pos_yx = ((0, 0), (0, 1), (1, 0), (1, 1))    # lt, rt, lb, rb
+        names = ("lt", "rt", "lb", "rb")
+        xp = torch.empty((4 * B, h2, w2, Cin), dtype=torch.bfloat16, device=dev)
+        ops.append(RectCopyOp(View(x), View(xp), B, [(0, py * h2, px * w2, i * B, 0, 0, h2, w2)
+                                                     for i, (py, px) in enumerate(pos_yx)]))
+        y = torch.empty((4 * B, hq, wq, mid), dtype=torch.bfloat16, device=dev)
+        for i, nm in enumerate(names):
+            self._base_conv(ops, f"{p}.feat_patchconv_{nm}", [View(xp[i * B:(i + 1) * B])], View(y[i * B:(i + 1) * B]),
+                            stride=stride)
+        if nonlocal_:
+            T = hq * wq
+            xt, Ca = self._nonlocal_operand(p, 4 * B, mid, T)
+            ops.append(NhwcTransposeOp(View(y), xt))
+            Wm, bias = self._nonlocal_gemms(ops, p, xt, mid, T, 4 * B, dict(src_shared=4, src_shared_div=B))
+            nl = torch.empty_like(y)
+            self._conv(ops, None, None, [View(y)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(4 * B, mid, Ca),
+                       n_out=mid, pre_res=View(bias), pre_shift=30, post_res=View(y), post_shift=0)
+        else:
+            nl = y
+        lr_in = torch.empty((2 * B, 2 * hq, wq, mid), dtype=torch.bfloat16, device=dev)   # L images, then R images
+        tb_in = torch.empty((2 * B, hq, 2 * wq, mid), dtype=torch.bfloat16, device=dev)   # T images, then B images
+        ops.append(RectCopyOp(View(nl), View(lr_in), B, [(i * B, 0, 0, px * B, py * hq, 0, hq, wq)
+                                                         for i, (py, px) in enumerate(pos_yx)]))
+        ops.append(RectCopyOp(View(nl), View(tb_in), B, [(i * B, 0, 0, py * B, 0, px * wq, hq, wq)
+                                                         for i, (py, px) in enumerate(pos_yx)]))
+        lr_o, tb_o = torch.empty_like(lr_in), torch.empty_like(tb_in)
+        self._base_conv(ops, f"{p}.feat_patchconv_l", [View(lr_in[:B])], View(lr_o[:B]))
+        self._base_conv(ops, f"{p}.feat_patchconv_r", [View(lr_in[B:])], View(lr_o[B:]))
+        self._base_conv(ops, f"{p}.feat_patchconv_t", [View(tb_in[:B])], View(tb_o[:B]))
+        self._base_conv(ops, f"{p}.feat_patchconv_b", [View(tb_in[B:])], View(tb_o[B:]))
+        cc = torch.empty((B, 2 * hq, 2 * wq, 2 * mid), dtype=torch.bfloat16, device=dev)   # [cat(l, r; W) | cat(t, b; H)]
+        ops.append(RectCopyOp(View(lr_o), View(cc, 0, mid), B, [(0, 0, 0, 0, 0, 0, 2 * hq, wq), (B, 0, 0, 0, 0, wq, 2 * hq, wq)]))
+        ops.append(RectCopyOp(View(tb_o), View(cc, mid, mid), B, [(0, 0, 0, 0, 0, 0, hq, 2 * wq), (B, 0, 0, 0, hq, 0, hq, 2 * wq)]))
+        self._conv(ops, sd[p + ".channel_conv.weight"].float(), sd[p + ".channel_conv.bias"].float(), [View(cc)], out, 1,
+                   act=N.ACT_NONE)
+        self._keepalive = getattr(self, "_keepalive", []) + [xp, y, nl, lr_in, tb_in, lr_o, tb_o, cc]
+
+    def _build_neck_p2(self, nk, d3, d4, d5):
+        """models/block/non_local/yolo_patch_nonlocal_plus.py:180-247: PAFPN with two extra inputs (the patch modules on
+        dark3 / dark4, concatenated into C3_p4 / C3_n3) and k x k identity convs (7 / 5 / 3) behind the three outputs."""
+        c0, c1, c2 = self.c0, self.c1, self.c2
+        sd = self.sd
+        f1p = self._buf("feat1_patch", 16, c1)
+        cat4 = self._buf("cat4", 16, 3 * c0)               # [bu_conv2(P3_out) | P4 | feat2_patch]
+        cat5 = self._buf("cat5", 32, 2 * c1)               # [bu_conv1(P4_out) | P5]
+        P5, P4 = View(cat5, c1, c1), View(cat4, c0, c0)
+        self._build_patch_conv(nk, "backbone.Patch_conv_feat1", d3, 2, True, View(f1p))
+        self._build_patch_conv(nk, "backbone.Patch_conv_feat2", d4, 1, False, View(cat4, 2 * c0, c0))
+        self._base_conv(nk, "backbone.lateral_conv0", [View(d5)], P5)
+        p5up = self._buf("c3p4_out", 16, c1)
+        self._csp(nk, "backbone.C3_p4", 16, [View(d4), View(f1p)], View(p5up), up_src=P5, x_name="c3p4")
+        self._base_conv(nk, "backbone.reduce_conv1", [View(p5up)], P4)
+        p3raw, p4raw, p5raw = self._buf("p3raw", 8, c0), self._buf("p4raw", 16, c1), self._buf("p5raw", 32, c2)
+        p3o, p4out, p5out = self._buf("P3_out", 8, c0), self._buf("P4_out", 16, c1), self._buf("P5_out", 32, c2)
+        self._csp(nk, "backbone.C3_p3", 8, View(d3), View(p3raw), up_src=P4, x_name="c3p3")
+        ident = lambda q, src, dst: self._conv(nk, sd[q + ".conv.weight"].float(), sd[q + ".conv.bias"].float(), [View(src)],
+                                               View(dst), sd[q + ".conv.weight"].shape[-1], act=N.ACT_NONE)
+        ident("backbone.P3_Identity", p3raw, p3o)
+        self._base_conv(nk, "backbone.bu_conv2", [View(p3o)], View(cat4, 0, c0), stride=2)
+        self._csp(nk, "backbone.C3_n3", 16, View(cat4), View(p4raw), x_name="c3n3")
+        ident("backbone.P4_Identity", p4raw, p4out)
+        self._base_conv(nk, "backbone.bu_conv1", [View(p4out)], View(cat5, 0, c1), stride=2)
+        self._csp(nk, "backbone.C3_n4", 32, View(cat5), View(p5raw), x_name="c3n4")
+        ident("backbone.P5_Identity", p5raw, p5out)
+        return View(p3o), View(p4out), View(p5out)
 
     def _build_p1_head(self, d2, P3o, p4out, p5out):
         """models/new/yolox10.py:70-158.  Level k (strides 8/16/32): x_k = stems[k](P_k); cls branch input
@@ -408,7 +529,7 @@ class FFAPathPlan:
         box_act = N.ACT_YOLOX_BOX if self.decode == "drone" else N.ACT_MMDET_BOX
         a_off = 0
         for k, (h, w) in enumerate(self.level_hw):
-            i = k if self.variant == "stock" else (3 if k == 0 else k - 1)
+            i = k if self.variant in ("stock", "p2") else (3 if k == 0 else k - 1)
             wc0, bc0 = self._folded(f"head.cls_convs.{i}.0")
             wr0, br0 = self._folded(f"head.reg_convs.{i}.0")
             F = self._buf(f"tower{k}", self.strides[k], 2 * hc)

@@ -74,7 +74,7 @@ class ConvOp:
                  post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0),
                  pred_weight: Optional[torch.Tensor] = None, pred_bias: Optional[torch.Tensor] = None,
                  pred_act: int = N.ACT_NONE, weight_raw: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
-                 src_shared: int = 0, patch_mode: bool = False, batch: Optional[int] = None):
+                 src_shared: int = 0, src_shared_div: int = 0, patch_mode: bool = False, batch: Optional[int] = None):
         """`weight_raw`: a bf16 device matrix [N rows, pitch] (shared) or [batch, N rows, pitch] (one per image) used
         as is (the batched products of the non-local block); `src_shared` = k > 0: srcs[0] holds k static matrices and image b reads matrix b mod k;
         `patch_mode`: srcs[0] / post_res / out are [B, H, W, .] tensors processed as their 4*B 2x2 patches."""
@@ -113,6 +113,7 @@ class ConvOp:
                 assert weight_raw.shape[0] == b, (weight_raw.shape, b)
                 d.weight_batch_stride = weight_raw.shape[1] * weight_raw.shape[2]
         d.src_shared = int(src_shared)
+        d.src_shared_div = int(src_shared_div)
         d.patch_mode = 1 if patch_mode else 0
         self.bias = None if bias is None else bias.detach().float().contiguous()
         d.weight = self.packed.data_ptr()
@@ -368,3 +369,41 @@ class ConvOpF32:
 
     def launch(self, stream=None):
         N.check(self._lib.glsdet_conv_f32(C.byref(self.desc), N.stream_ptr(stream)), "glsdet_conv_f32")
+
+
+class RectCopyOp:
+    """Up to 8 rectangle copies between two NHWC bf16 tensors in one launch (glsdet_rect_copy):
+    rects = [(src_image0, sy, sx, dst_image0, dy, dx, h, w), ...], each applied to `batch` consecutive images."""
+
+    def __init__(self, src: View, dst: View, batch: int, rects):
+        assert src.t.dtype == torch.bfloat16 and dst.t.dtype == torch.bfloat16 and src.c == dst.c
+        assert 1 <= len(rects) <= 8
+        self.src, self.dst, self.batch = src, dst, batch
+        self.rects = (N.Rect * len(rects))(*[N.Rect(*r) for r in rects])
+        for r in rects:
+            assert r[0] + batch <= src.t.shape[0] and r[3] + batch <= dst.t.shape[0], (r, src.t.shape, dst.t.shape)
+        self.n = len(rects)
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        s, d = self.src, self.dst
+        N.check(self._lib.glsdet_rect_copy(s.t.data_ptr(), s.t.shape[1], s.t.shape[2], s.ld, s.coff, d.t.data_ptr(),
+                                           d.t.shape[1], d.t.shape[2], d.ld, d.coff, self.batch, s.c, self.rects, self.n,
+                                           N.stream_ptr(stream)), "glsdet_rect_copy")
+
+
+class NhwcTransposeOp:
+    """NHWC bf16 [B', h, w, C] window -> per-image transposed matrices dst[b'][c][t] (Gram operand)."""
+
+    def __init__(self, src: View, dst: torch.Tensor):
+        assert src.t.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and dst.dim() == 3 and dst.is_contiguous()
+        b, h, w = src.bhw
+        assert dst.shape[0] == b and dst.shape[1] >= src.c and dst.shape[2] >= h * w
+        self.src, self.dst, self.b, self.t = src, dst, b, h * w
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        s = self.src
+        N.check(self._lib.glsdet_nhwc_transpose(s.t.data_ptr(), self.dst.data_ptr(), self.b, self.t, s.c, s.ld, s.coff,
+                                                self.dst.shape[1], self.dst.shape[2], N.stream_ptr(stream)),
+                "glsdet_nhwc_transpose")

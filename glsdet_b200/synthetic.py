@@ -48,15 +48,35 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
 
     c0, c1, c2 = int(256 * width), int(512 * width), int(1024 * width)
     n = round(3 * depth)
+    p2 = variant == "p2"   # models/block/non_local/yolo_patch_nonlocal_plus.py: C3_p4 / C3_n3 take a third input
     bc("backbone.lateral_conv0", c2, c1, 1)
-    csp("backbone.C3_p4", 2 * c1, c1, n)
+    csp("backbone.C3_p4", (3 if p2 else 2) * c1, c1, n)
     bc("backbone.reduce_conv1", c1, c0, 1)
     csp("backbone.C3_p3", 2 * c0, c0, n)
+    if p2:
+        shapes["backbone.P3_Identity.conv.weight"], shapes["backbone.P3_Identity.conv.bias"] = (c0, c0, 7, 7), (c0,)
     bc("backbone.bu_conv2", c0, c0, 3)
-    csp("backbone.C3_n3", 2 * c0, c1, n)
+    csp("backbone.C3_n3", (3 if p2 else 2) * c0, c1, n)
+    if p2:
+        shapes["backbone.P4_Identity.conv.weight"], shapes["backbone.P4_Identity.conv.bias"] = (c1, c1, 5, 5), (c1,)
     bc("backbone.bu_conv1", c1, c1, 3)
     csp("backbone.C3_n4", 2 * c1, c2, n)
 
+    if p2:
+        for name, cin, cout, nl in (("Patch_conv_feat1", c0, c1, True), ("Patch_conv_feat2", c1, c0, False)):
+            q, mid = f"backbone.{name}", cin // 2
+            for pos in ("lt", "lb", "rt", "rb"):
+                bc(f"{q}.feat_patchconv_{pos}", cin, mid, 3)
+            if nl:
+                for pos in ("lt", "lb", "rt", "rb"):
+                    for nm in ("g", "theta", "phi", "conv_out"):
+                        shapes[f"{q}.feat_patchconv_{pos}_nonlocal.{nm}.weight"] = (mid, mid, 1, 1)
+                        shapes[f"{q}.feat_patchconv_{pos}_nonlocal.{nm}.bias"] = (mid,)
+            for pos in ("r", "l", "t", "b"):
+                bc(f"{q}.feat_patchconv_{pos}", mid, mid, 3)
+            shapes[f"{q}.channel_conv.weight"], shapes[f"{q}.channel_conv.bias"] = (cout, 2 * mid, 1, 1), (cout,)
+        shapes["backbone.P5_Identity.conv.weight"], shapes["backbone.P5_Identity.conv.bias"] = (c2, c2, 3, 3), (c2,)
+        variant = "stock"   # the head is the stock three-level one
     hc = int(256 * width)
     if variant == "p1":   # models/new/yolox10.py: patch non-local blocks in the neck, cross-level cls branch (App. C)
         for i, c in ((1, c0), (2, c1), (3, c2)):
@@ -172,6 +192,17 @@ def synthetic_state_dict(num_classes: int, phi: str, seed: int = 0, flavour: str
                          "running_var": 0.9 + 0.2 * torch.rand(shp, generator=g)}[part]
         elif ".fc." in k:
             sd[k] = torch.randn(shp, generator=g) * math.sqrt(1.0 / shp[1])
+        elif ".channel_conv." in k and ".conv." not in k and ".bn." not in k or "_Identity.conv." in k:
+            # plain nn.Conv2d with bias (Identity_Conv.py:287-288 and :27-84); identity convs start near identity
+            if part == "weight":
+                fan_in = shp[1] * shp[2] * shp[3]
+                wgt = torch.randn(shp, generator=g) * (0.02 if flavour == "reference" else 0.5 * math.sqrt(1.0 / fan_in))
+                if "_Identity" in k:
+                    idx = torch.arange(shp[0])
+                    wgt[idx, idx, shp[2] // 2, shp[3] // 2] += 1.0
+                sd[k] = wgt
+            else:
+                sd[k] = torch.randn(shp, generator=g) * (0.02 if flavour == "reference" else 0.1)
         elif "_nonlocal." in k:   # plain nn.Conv2d 1x1 with bias (Non_local_family.py:15-18)
             if part == "weight":
                 sd[k] = torch.randn(shp, generator=g) * (0.02 if flavour == "reference" else math.sqrt(1.0 / shp[1]))

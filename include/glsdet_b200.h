@@ -113,6 +113,8 @@ typedef struct glsdet_conv_desc {
   int32_t weight_ld;           /* row pitch of the weight matrix in elements; 0 = k_pad */
   int32_t src_shared;          /* k > 0: image b reads image (b mod k) of src0 (k static matrices used as activations,
                                   e.g. one per patch position) */
+  int32_t src_shared_div;      /* with src_shared = k: d > 0 selects image (b / d) instead of (b mod k) (images grouped
+                                  by patch position: b = position * images + image) */
   int32_t patch_mode;          /* 1 (1x1 convs): src0, post_res and out are the 2x2 patch views of
                                   [batch/4, 2*height, 2*width, ld] tensors; image b' = (b*2 + py)*2 + px is patch
                                   (py, px) of image b (the split of Non_local_family.py:230-233) */
@@ -179,6 +181,26 @@ int glsdet_patch_transpose(const float* src, void* dst, int32_t batch, int32_t c
                            int32_t width, int32_t dst_rows, int32_t dst_ld, void* stream);
 int glsdet_gather_bias(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows, int32_t ld,
                        int32_t col, int64_t batch_stride, int32_t base_groups, void* stream);
+
+/*
+ * Rectangle copies between NHWC bf16 tensors (up to 8 per launch): the patch split, the seam halves and the re-tiling
+ * of Patch_Conv / Patch_Conv_NonLocal (yolox-drone/models/block/non_local/Identity_Conv.py:292-318, 353-384) as data
+ * movement:  dst[db + b, dy + y, dx + x, dcoff + c] = src[sb + b, sy + y, sx + x, scoff + c]  for b < batch, y < h,
+ * x < w, c < channels (channels, offsets and pitches multiples of 8).
+ */
+typedef struct glsdet_rect {
+  int32_t sb, sy, sx, db, dy, dx, h, w;
+} glsdet_rect;
+int glsdet_rect_copy(const void* src, int32_t src_h, int32_t src_w, int32_t src_ld, int32_t src_coff, void* dst,
+                     int32_t dst_h, int32_t dst_w, int32_t dst_ld, int32_t dst_coff, int32_t batch, int32_t channels,
+                     const glsdet_rect* rects, int32_t num_rects, void* stream);
+/*
+ * NHWC bf16 [B, T pixels, ld] channel window -> per-image transposed matrices dst[b][c][t] (row pitch dst_ld, dst_rows
+ * rows per image): the Gram operand of the non-local block when its input is already an NHWC activation
+ * (Patch_Conv_NonLocal, Identity_Conv.py:364-367).
+ */
+int glsdet_nhwc_transpose(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels, int32_t src_ld,
+                          int32_t src_coff, int32_t dst_rows, int32_t dst_ld, void* stream);
 
 /*
  * nn.Upsample(scale_factor=2, mode="nearest") of an NHWC bf16 channel window into a channel window of a concat

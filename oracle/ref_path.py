@@ -271,6 +271,73 @@ def p1_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = Fals
         _EMULATE_BF16 = False
 
 
+# ------------------------------------------------------------------------------------------ P2: yolo_patch_nonlocal_plus.py
+def _patch_seams(sd: StateDict, p: str, lt, lb, rt, rb) -> torch.Tensor:
+    """Seam convs + re-tiling shared by Patch_Conv and Patch_Conv_NonLocal
+    (models/block/non_local/Identity_Conv.py:303-316 / 369-382): 3x3 BaseConvs on the left / right halves
+    (cat along H) and the top / bottom halves (cat along W), lr = cat(l, r; W), tb = cat(t, b; H), channel cat,
+    channel_conv = plain 1x1 nn.Conv2d with bias (channel_cat='linear', :287-288)."""
+    l = base_conv(sd, p + ".feat_patchconv_l", torch.cat((lt, lb), dim=2))
+    r = base_conv(sd, p + ".feat_patchconv_r", torch.cat((rt, rb), dim=2))
+    t = base_conv(sd, p + ".feat_patchconv_t", torch.cat((lt, rt), dim=3))
+    b = base_conv(sd, p + ".feat_patchconv_b", torch.cat((lb, rb), dim=3))
+    y = torch.cat((torch.cat((l, r), dim=3), torch.cat((t, b), dim=2)), dim=1)
+    return _q(F.conv2d(y, _q(sd[p + ".channel_conv.weight"]), sd[p + ".channel_conv.bias"]))
+
+
+def patch_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int, nonlocal_: bool) -> torch.Tensor:
+    """Patch_Conv.forward (Identity_Conv.py:292-318) / Patch_Conv_NonLocal.forward (:353-384): 2x2 split at
+    int(H/2), int(W/2), one 3x3 BaseConv (stride `stride`) per patch, [one dot-product Non_local_Block per patch],
+    seam convs, re-tile, 1x1."""
+    h2, w2 = int(x.shape[2] / 2), int(x.shape[3] / 2)
+    parts = {"lt": x[:, :, :h2, :w2], "lb": x[:, :, h2:, :w2], "rt": x[:, :, :h2, w2:], "rb": x[:, :, h2:, w2:]}
+    out = {}
+    for k, v in parts.items():
+        y = base_conv(sd, f"{p}.feat_patchconv_{k}", v, stride=stride)
+        if nonlocal_:
+            y = _q(non_local_block(sd, f"{p}.feat_patchconv_{k}_nonlocal", y))
+        out[k] = y
+    return _patch_seams(sd, p, out["lt"], out["lb"], out["rt"], out["rb"])
+
+
+def identity_conv(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
+    """Identity_Conv_{three,five,seven}.forward (Identity_Conv.py:27-84): a plain k x k nn.Conv2d with bias and
+    padding k // 2 (the identity initialisation only matters for training from scratch)."""
+    w = sd[p + ".conv.weight"]
+    return _q(F.conv2d(_q(x), _q(w), sd[p + ".conv.bias"], padding=w.shape[-1] // 2))
+
+
+def p2_neck(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "backbone") -> List[torch.Tensor]:
+    """models/block/non_local/yolo_patch_nonlocal_plus.py:180-247 after the backbone call: feats = (dark3, dark4, dark5)."""
+    feat1, feat2, feat3 = feats
+    feat1_patch = patch_conv(sd, f"{p}.Patch_conv_feat1", feat1, stride=2, nonlocal_=True)     # :184
+    feat2_patch = patch_conv(sd, f"{p}.Patch_conv_feat2", feat2, stride=1, nonlocal_=False)    # :185
+    P5 = base_conv(sd, f"{p}.lateral_conv0", feat3)
+    x = csp_layer(sd, f"{p}.C3_p4", torch.cat([_up2(P5), feat2, feat1_patch], 1))             # :197-201
+    P4 = base_conv(sd, f"{p}.reduce_conv1", x)
+    P3_out = csp_layer(sd, f"{p}.C3_p3", torch.cat([_up2(P4), feat1], 1))
+    P3_out = identity_conv(sd, f"{p}.P3_Identity", P3_out)                                      # :219
+    d = base_conv(sd, f"{p}.bu_conv2", P3_out, stride=2)
+    P4_out = csp_layer(sd, f"{p}.C3_n3", torch.cat([d, P4, feat2_patch], 1))                   # :228-232
+    P4_out = identity_conv(sd, f"{p}.P4_Identity", P4_out)                                      # :233
+    d = base_conv(sd, f"{p}.bu_conv1", P4_out, stride=2)
+    P5_out = csp_layer(sd, f"{p}.C3_n4", torch.cat([d, P5], 1))
+    P5_out = identity_conv(sd, f"{p}.P5_Identity", P5_out)                                      # :246
+    return [P3_out, P4_out, P5_out]
+
+
+def p2_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+    """yolo_patch_nonlocal_plus.py YoloBody.forward minus the CSPDarknet call; the head (:6-147) is the stock
+    three-level decoupled head."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = bf16
+    try:
+        with torch.no_grad():
+            return stock_head(sd, p2_neck(sd, [_q(f) for f in feats]))
+    finally:
+        _EMULATE_BF16 = False
+
+
 # ------------------------------------------------------------------------------------------ backbone (upstream)
 def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
     """models/ffa/darknet.py:10-37,115-195.  Upstream of the measured path; restated only so that synthetic

@@ -179,6 +179,48 @@ def run_p1_case(ub, name, phi, nc, seed, batch, in_h, in_w, conf, nms_thr):
     return meta, key_shapes
 
 
+def run_p2_case(ub, name, phi, nc, seed, batch, in_h, in_w, conf, nms_thr):
+    """GLSDet P2 (models/block/non_local/yolo_patch_nonlocal_plus.py, imports as shipped)."""
+    import models.block.non_local.yolo_patch_nonlocal_plus as yp
+    from oracle import ref_path
+
+    sd = ref_path.synthetic_state_dict(nc, phi, seed=seed, flavour="calibrated", variant="p2")
+    with contextlib.redirect_stdout(io.StringIO()):
+        net = yp.YoloBody(nc, phi).eval()
+    net.load_state_dict(sd, strict=True)
+    key_shapes = {k: list(v.shape) for k, v in net.state_dict().items()}
+    width = {"tiny": 0.375, "s": 0.5, "m": 0.75, "l": 1.0}[phi]
+    chans = [int(c * width) for c in (256, 512, 1024)]
+    g = torch.Generator().manual_seed(seed + 100)
+    feats = [torch.randn(batch, c, in_h // s, in_w // s, generator=g) for c, s in zip(chans, (8, 16, 32))]
+
+    class Stub(torch.nn.Module):
+        def forward(self, x):
+            return dict(zip(("dark3", "dark4", "dark5"), feats))
+
+    net.backbone.backbone = Stub()
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        neck_out = net.backbone(torch.zeros(batch, 3, in_h, in_w))
+        logits = net.head(neck_out)
+        pred = ub.decode_outputs([o.clone() for o in logits], [in_h, in_w]).contiguous()
+        results = ub.non_max_suppression(pred.clone(), nc, [in_h, in_w], np.array([in_h, in_w]), False,
+                                         conf_thres=conf, nms_thres=nms_thr)
+        f1p = net.backbone.Patch_conv_feat1(feats[0])
+        f2p = net.backbone.Patch_conv_feat2(feats[1])
+    out = {f"feat{i}": f.numpy() for i, f in enumerate(feats)}
+    out.update({f"neck{i}": t.numpy() for i, t in enumerate(neck_out)})
+    out.update({f"logits{i}": t.numpy() for i, t in enumerate(logits)})
+    out["pred"] = pred.numpy()
+    out["feat1_patch"], out["feat2_patch"] = f1p.numpy(), f2p.numpy()
+    for i, r in enumerate(results):
+        out[f"nms{i}"] = r if r is not None else np.zeros((0, 7), np.float32)
+    meta = dict(name=name, phi=phi, nc=nc, seed=seed, batch=batch, in_h=in_h, in_w=in_w, conf=conf, nms_thr=nms_thr,
+                weight_checksum=weight_checksum(sd), n_keys=len(sd), kept=[int(len(out[f"nms{i}"])) for i in range(batch)])
+    np.savez_compressed(HERE / f"{name}.npz", **out)
+    print(name, meta["kept"], meta["weight_checksum"])
+    return meta, key_shapes
+
+
 def clustered_boxes(rng, k, nc, normalised=True, ties=False):
     g = max(4, k // 12)
     cen = rng.uniform(0.05, 0.95, (g, 2))
@@ -261,6 +303,13 @@ def main():
         (HERE / "state_dict_keys_p1_s.json").write_text(json.dumps(keys_p1, indent=0))
         (HERE / "meta.json").write_text(json.dumps(metas, indent=1))
         return
+    if "--only-p2" in sys.argv:
+        metas = json.loads((HERE / "meta.json").read_text())
+        mp, keys_p2 = run_p2_case(ub, "p2_s_calibrated", "s", 10, 0, 1, 128, 192, 0.01, 0.65)
+        metas["p2"] = mp
+        (HERE / "state_dict_keys_p2_s.json").write_text(json.dumps(keys_p2, indent=0))
+        (HERE / "meta.json").write_text(json.dumps(metas, indent=1))
+        return
     metas = {}
     m1, keys = run_model_case(yf, ub, "p0_s_calibrated", "s", 10, "calibrated", 1, 2, 64, 96, 0.01, 0.65)
     m2, _ = run_model_case(yf, ub, "p0_s_refinit", "s", 10, "reference", 2, 1, 64, 64, 0.01, 0.65)
@@ -272,6 +321,9 @@ def main():
     mp, keys_p1 = run_p1_case(ub, "p1_s_calibrated", "s", 10, 0, 1, 128, 192, 0.01, 0.65)
     metas["p1"] = mp
     (HERE / "state_dict_keys_p1_s.json").write_text(json.dumps(keys_p1, indent=0))
+    mp2, keys_p2 = run_p2_case(ub, "p2_s_calibrated", "s", 10, 0, 1, 128, 192, 0.01, 0.65)
+    metas["p2"] = mp2
+    (HERE / "state_dict_keys_p2_s.json").write_text(json.dumps(keys_p2, indent=0))
     metas["nms"] = nms_cases()
     metas["postproc"] = postproc_case(ub)
     metas["torch"] = torch.__version__

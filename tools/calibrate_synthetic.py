@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--phi", default="s")
     ap.add_argument("--nc", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--variant", default="ffa", choices=["ffa", "stock", "p1"])
+    ap.add_argument("--variant", default="ffa", choices=["ffa", "stock", "p1", "p2"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--obj-std", type=float, default=2.0)
     ap.add_argument("--target-pass", type=float, default=0.04, help="fraction of anchors with obj*cls >= 0.01")
@@ -55,7 +55,10 @@ def main():
     x = synthetic_images(2, args.size, args.size, seed=args.seed + 4242)
     with torch.no_grad():
         feats = ref_path.csp_darknet(sd, x)
-        neck = ref_path.p1_neck(sd, feats) if args.variant == "p1" else ref_path.pafpn_neck(sd, feats)
+        if args.variant == "p2":
+            neck = [None] + ref_path.p2_neck(sd, feats[1:])
+        else:
+            neck = ref_path.p1_neck(sd, feats) if args.variant == "p1" else ref_path.pafpn_neck(sd, feats)
         # towers: rescale the prediction convs on the calibrated tower outputs
         towers = None
         if args.variant == "p1":   # models/new/yolox10.py:83-139
@@ -70,7 +73,7 @@ def main():
                 rf = ref_path.base_conv(sd, f"head.reg_convs.{k}.1", ref_path.base_conv(sd, f"head.reg_convs.{k}.0", xk))
                 towers.append((k, cf, rf))
             proc = []
-        elif args.variant == "stock":
+        elif args.variant in ("stock", "p2"):
             proc = [ref_path.base_conv(sd, f"head.stems.{k}", neck[k + 1]) for k in range(3)]
         else:
             zz = ref_path.ffa(sd, "head.ftt", neck[1], neck[2])
@@ -79,7 +82,7 @@ def main():
         if towers is None:
             towers = []
             for k, xk in enumerate(proc):
-                i = k if args.variant == "stock" else (3 if k == 0 else k - 1)
+                i = k if args.variant in ("stock", "p2") else (3 if k == 0 else k - 1)
                 cf = ref_path.base_conv(sd, f"head.cls_convs.{i}.1", ref_path.base_conv(sd, f"head.cls_convs.{i}.0", xk))
                 rf = ref_path.base_conv(sd, f"head.reg_convs.{i}.1", ref_path.base_conv(sd, f"head.reg_convs.{i}.0", xk))
                 towers.append((i, cf, rf))
@@ -92,7 +95,7 @@ def main():
                 changed[key] = sd[key]
     ref_path.base_conv = orig
     # shift the objectness biases so that the wanted fraction of anchors passes conf 0.01 (bisection on one offset)
-    head_fn = {"stock": lambda n: ref_path.stock_head(sd, n[1:]), "p1": lambda n: ref_path.p1_head(sd, n),
+    head_fn = {"stock": lambda n: ref_path.stock_head(sd, n[1:]), "p2": lambda n: ref_path.stock_head(sd, n[1:]), "p1": lambda n: ref_path.p1_head(sd, n),
                "ffa": lambda n: ref_path.yolox_head(sd, n)}[args.variant]
     with torch.no_grad():
         lg = head_fn(neck)
@@ -116,7 +119,7 @@ def main():
         pred = ref_path.decode_outputs(lg, [args.size, args.size])
     sc = pred[:, :, 4] * pred[:, :, 5:].max(2)[0]
     print(out.name, f"{out.stat().st_size/1e3:.0f} kB", "anchors", pred.shape[1], "cand@0.01", (sc >= 0.01).sum(1).tolist(),
-          "neck std", [round(float(t.std()), 2) for t in neck], "logit std", [round(float(l.std()), 2) for l in lg])
+          "neck std", [round(float(t.std()), 2) for t in neck if t is not None], "logit std", [round(float(l.std()), 2) for l in lg])
     res = ref_path.non_max_suppression(pred, args.nc, [args.size, args.size], None, False, 0.01, 0.65, correct_boxes=False)
     print("kept", [len(r) for r in res])
 

@@ -16,8 +16,8 @@ from glsdet_b200.ops import ConvOp  # noqa: E402
 def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    if len(sys.argv) > 1 and sys.argv[1] == "p1":
-        bench.VARIANT = "p1"
+    if len(sys.argv) > 1 and sys.argv[1] in ("p0", "p1", "p2"):
+        bench.VARIANT = sys.argv[1]
     sd = bench.make_weights()
     YoloBody = bench.body_class()
 
