@@ -33,7 +33,7 @@ def test_no_compute_without_gpu_but_errors_are_reported(native_lib):
     rc = native_lib.glsdet_conv_launch(None, None)
     assert rc != 0 and b"null op" in native_lib.glsdet_last_error()
     d = N.ConvDesc()
-    d.ksize, d.stride, d.batch, d.height, d.width = 5, 1, 1, 8, 8
+    d.ksize, d.stride, d.batch, d.height, d.width = 4, 1, 1, 8, 8   # even kernel sizes are rejected
     assert native_lib.glsdet_conv_weight_shape(d, None, None, None) != 0
     assert b"ksize" in native_lib.glsdet_last_error()
 
