@@ -317,18 +317,31 @@ class FFAPathPlan:
         Patch images are ordered b' = (b*2 + py)*2 + px; position (py, px) = lt (0,0), rt (0,1), lb (1,0), rb (1,1)."""
         sd, dev = self.sd, self.device
         B, H, W_, C = x.shape
-        if H % 2 or W_ % 2:
-            raise NotImplementedError("non-local patches need an even height and width at every level, i.e. an input "
-                                      "size that is a multiple of 64 (unequal 2x2 splits, Non_local_family.py:230-233, "
-                                      "are not supported)")
-        T = (H // 2) * (W_ // 2)
-        Bp = 4 * B
-        xt, Ca = self._nonlocal_operand(p, Bp, C, T)
-        self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
-        Wm, bias = self._nonlocal_gemms(ops, p, xt, C, T, Bp, dict(src_shared=4))
         nl = self._buf(p + ".nl", stride, C)
-        self._conv(ops, None, None, [View(x)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
-                   patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
+        if H % 2 or W_ % 2:
+            # unequal 2x2 split (int(H/2), int(W/2): Non_local_family.py:230-233, e.g. 17 x 32 at 544 x 1024): every
+            # patch position is cut out as its own dense batch and runs its own chain of GEMMs
+            h2, w2 = H // 2, W_ // 2
+            for pos, (y0, x0, ph, pw) in (("lt", (0, 0, h2, w2)), ("rt", (0, w2, h2, W_ - w2)),
+                                          ("lb", (h2, 0, H - h2, w2)), ("rb", (h2, w2, H - h2, W_ - w2))):
+                xp = torch.empty((B, ph, pw, C), dtype=torch.bfloat16, device=dev)
+                ops.append(RectCopyOp(View(x), View(xp), B, [(0, y0, x0, 0, 0, 0, ph, pw)]))
+                xt, Ca = self._nonlocal_operand(f"{p}.{pos}", B, C, ph * pw)
+                ops.append(NhwcTransposeOp(View(xp), xt))
+                Wm, bias = self._nonlocal_gemms(ops, p, xt, C, ph * pw, B, dict(src_shared=1), positions=(pos,))
+                nlp = torch.empty_like(xp)
+                self._conv(ops, None, None, [View(xp)], View(nlp), 1, act=N.ACT_NONE, weight_raw=Wm.view(B, C, Ca),
+                           n_out=C, pre_res=View(bias), pre_shift=30, post_res=View(xp), post_shift=0)
+                ops.append(RectCopyOp(View(nlp), View(nl), B, [(0, 0, 0, 0, y0, x0, ph, pw)]))
+                self._keepalive = getattr(self, "_keepalive", []) + [xp, nlp]
+        else:
+            T = (H // 2) * (W_ // 2)
+            Bp = 4 * B
+            xt, Ca = self._nonlocal_operand(p, Bp, C, T)
+            self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
+            Wm, bias = self._nonlocal_gemms(ops, p, xt, C, T, Bp, dict(src_shared=4))
+            self._conv(ops, None, None, [View(x)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
+                       patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
         self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
 
     def _nonlocal_operand(self, p: str, Bp: int, C: int, T: int):
@@ -340,17 +353,19 @@ class FFAPathPlan:
         self._bufs[p + ".xt"] = xt
         return xt, Ca
 
-    def _nonlocal_gemms(self, ops, p: str, xt: torch.Tensor, C: int, T: int, Bp: int, shared_kw: dict):
+    def _nonlocal_gemms(self, ops, p: str, xt: torch.Tensor, C: int, T: int, Bp: int, shared_kw: dict,
+                        positions=("lt", "rt", "lb", "rb")):
         """Gram matrix and the two C x C products of the reassociated non-local block for Bp patch images; returns
         (W [Bp, 1, C, Ca] bf16: columns 0..C-1 = W_eff, column C = b_eff - b_o;  bias [Bp, 1, 1, C] fp32 = b_eff).
         `shared_kw` tells the conv operator how a patch image selects its position's static matrices
         (position order lt, rt, lb, rb = py * 2 + px)."""
         sd, dev = self.sd, self.device
         Ca, Tp = xt.shape[1], xt.shape[2]
-        a1 = torch.zeros((4, C, Ca), dtype=torch.float64, device=dev)
-        a2t = torch.zeros((4, Ca, Ca), dtype=torch.float64, device=dev)
-        bo = torch.zeros((4, C), dtype=torch.float32, device=dev)
-        for i, pos in enumerate(("lt", "rt", "lb", "rb")):
+        npos = len(positions)
+        a1 = torch.zeros((npos, C, Ca), dtype=torch.float64, device=dev)
+        a2t = torch.zeros((npos, Ca, Ca), dtype=torch.float64, device=dev)
+        bo = torch.zeros((npos, C), dtype=torch.float32, device=dev)
+        for i, pos in enumerate(positions):
             q = f"{p}.feat_patchconv_{pos}_nonlocal."
             wg, wt, wp, wo = (sd[q + n + ".weight"].double().flatten(1) for n in ("g", "theta", "phi", "conv_out"))
             bg, bt, bp = (sd[q + n + ".bias"].double() for n in ("g", "theta", "phi"))
@@ -360,10 +375,10 @@ class FFAPathPlan:
             a2 = Phi.t() @ torch.cat([wt, bt[:, None]], 1)   # [C+1, C+1]: columns 0..C-1 -> W_eff, column C -> b_eff - bo
             a2t[i, :C + 1, :C + 1] = a2.t()
             bo[i] = sd[q + "conv_out.bias"].float()
-        a1 = a1.to(torch.bfloat16).view(4, 1, C, Ca).contiguous()
-        a2t = a2t.to(torch.bfloat16).view(4, 1, Ca, Ca).contiguous()
+        a1 = a1.to(torch.bfloat16).view(npos, 1, C, Ca).contiguous()
+        a2t = a2t.to(torch.bfloat16).view(npos, 1, Ca, Ca).contiguous()
         div = shared_kw.get("src_shared_div", 0)
-        img_pos = (torch.arange(Bp, device=dev) // div) if div else (torch.arange(Bp, device=dev) % 4)
+        img_pos = (torch.arange(Bp, device=dev) // div) if div else (torch.arange(Bp, device=dev) % npos)
         bo_full = bo[img_pos].contiguous()               # [Bp, C]: b_o of every patch image
         S = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
         Zt = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)

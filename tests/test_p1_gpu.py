@@ -224,3 +224,38 @@ def test_p1_model_vs_oracle_1024(native_lib, cuda_device):
     det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65)
     torch.cuda.synchronize()
     assert (cnt.cpu() >= 0).all() and det.shape[0] == 2
+
+
+def test_p1_config4_yolox_l_544x1024_unequal_patches(native_lib, cuda_device):
+    """SURVEY.md section 8d row 4': P1 YOLOX-l, UAVDT-shaped 544 x 1024 input, nc = 3.  dark5 is 17 x 32, so the 2x2
+    split is unequal (8 / 9 rows, Non_local_family.py:230-233): that level runs one dense chain per patch position.
+    One image against the fp32 oracle: the non-local stages and the logits."""
+    from glsdet_b200.synthetic import synthetic_images
+    from glsdet_b200.yolox10 import YoloBody
+
+    nc = 3
+    sd = ref_path.synthetic_state_dict(nc, "l", seed=4, flavour="calibrated", variant="p1")
+    net = YoloBody(nc, "l")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    feats = ref_path.csp_darknet(sd, synthetic_images(1, 544, 1024, seed=21))
+    assert feats[3].shape[2:] == (17, 32)
+    dfeats = [f.to(cuda_device) for f in feats]
+    plan = net.plan_for(dfeats)
+    plan.load_features(dfeats)
+    plan.run_neck()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        for i in (1, 2, 3):
+            ref = feats[i] + ref_path.patch_conv_nonlocal_new(sd, f"backbone.Patch_conv_feat{i}", feats[i])
+            assert_close_rel(plan.buffer(f"feat{i}").float().permute(0, 3, 1, 2), ref, 1.5e-2, f"P1-l non-local stage feat{i}")
+    ref = ref_path.p1_neck_head(sd, feats)
+    emu = ref_path.p1_neck_head(sd, feats, bf16=True)
+    out = net.forward_features(dfeats)
+    assert [tuple(o.shape[2:]) for o in out] == [(68, 128), (34, 64), (17, 32)]
+    for i in range(3):
+        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
+        assert_close_rel(out[i], ref[i], max(TOL, 1.3 * inherent), f"P1-l 544x1024 logits{i}", frac=5e-2)
+    det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65, max_det=1000)
+    torch.cuda.synchronize()
+    assert det.shape == (1, 1000, 7) and 0 <= int(cnt[0]) <= 1000
