@@ -99,6 +99,16 @@ SIGNATURES = {
                                    C.c_void_p]),
     "glsdet_nhwc_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_group_norm_relu": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "glsdet_group_norm_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "glsdet_proxy_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "glsdet_gfl_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "glsdet_gfl_select": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

@@ -211,6 +211,35 @@ int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int32_t height,
                       int32_t src_ld, int32_t src_coff, int32_t dst_ld, int32_t dst_coff, void* stream);
 
 /*
+ * MP-Det head pieces (yolox-ufp/mmdet/models/dense_heads/mp_head.py, gfl_head.py; BASELINE configs[2]).
+ * glsdet_group_norm_relu: in place x = relu(GroupNorm(x)) on NHWC bf16 (the norm + activation of mmcv ConvModule in the
+ *   shared towers, mp_head.py:46-62); scratch = glsdet_group_norm_scratch_floats(batch, channels) floats.
+ * glsdet_proxy_scores: MPHead.forward_proxy (mp_head.py:105-121): feat fp32 NHWC [batch*hw, channels], centers = the
+ *   L2-normalised proxies fp32 [num_proxies, channels], cls_start[num_classes + 1] = first proxy of each class;
+ *   rows[b][row0 + pixel][class] = gamma * sum_j softmax(gamma * sim)_j * sim_j  (raw class scores).
+ * glsdet_gfl_decode: Integral (gfl_head.py:35-49) * stride + DistancePointBBoxCoder.decode on the cell points
+ *   (x * stride, y * stride) with clamping (core/bbox/transforms.py:136-165): reg fp32 NHWC [.., reg_ld] with
+ *   4 * bins logits per pixel (Scale folded into the conv) -> boxes[b][row0 + pixel][4] xyxy.
+ * glsdet_gfl_select: filter_scores_and_topk (core/utils/misc.py:143-165) for one level: (anchor, class) pairs with
+ *   sigmoid(score) > score_thr, best topk by score, appended to the image's candidate list (cand_count must be zeroed
+ *   by the caller before the first level); keys = scratch of 8 * keys_batch_stride bytes per image.
+ */
+int glsdet_group_norm_relu(void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld, int32_t groups,
+                           const float* gamma, const float* beta, float eps, float* scratch, void* stream);
+int64_t glsdet_group_norm_scratch_floats(int32_t batch, int32_t channels);
+int glsdet_proxy_scores(const float* feat, const float* centers, const int32_t* cls_start, int32_t num_classes,
+                        int32_t num_proxies, int32_t channels, int32_t batch, int32_t hw, float gamma, float* rows,
+                        int32_t rows_ld, int64_t rows_batch_stride, int32_t row0, void* stream);
+int glsdet_gfl_decode(const float* reg, int32_t reg_ld, int32_t bins, int32_t batch, int32_t height, int32_t width,
+                      float stride, float max_x, float max_y, float* boxes, int64_t boxes_batch_stride, int32_t row0,
+                      void* stream);
+int glsdet_gfl_select(const float* rows, int32_t rows_ld, int64_t rows_batch_stride, const float* boxes,
+                      int64_t boxes_batch_stride, int32_t row0, int32_t level_anchors, int32_t num_classes,
+                      float score_thr, int32_t topk, int32_t batch, void* keys, int64_t keys_batch_stride,
+                      int32_t* cand_count, float* cand_boxes, float* cand_scores, float* cand_labels,
+                      int32_t cand_capacity, void* stream);
+
+/*
  * SE gate of FFA (yolox-drone/models/ffa/ffa.py:5-20,77): partial[b][p][c] = sum over a slab of pixels of
  * x[b,:,c]; gate[b][c] = 1 + sigmoid(W2 relu(W1 mean)).  Deterministic two-stage reduction.
  *   x: NHWC bf16 [B, HW, C]; w1: fp32 [C/r][C]; w2: fp32 [C][C/r]; gate: fp32 [B][C];

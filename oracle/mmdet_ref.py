@@ -194,3 +194,164 @@ def expected_keys(in_channels, out_channels, num_csp_blocks, num_classes, feat_c
         for l in range(levels):
             head += [f"{name}.{l}.weight", f"{name}.{l}.bias"]
     return neck, head
+
+
+# ------------------------------------------------------------------------------------------ MP-Det (BASELINE configs[2])
+# FPN + MPHead inference path of yolox-ufp (necks/fpn.py, dense_heads/mp_head.py, dense_heads/gfl_head.py).  PARITY
+# UNPINNED like the rest of this file: mmcv is absent and the MP-Det config file is missing from the checkout (SURVEY.md
+# D6), so the configuration is the reconstruction of SURVEY.md section 8d row 3: FPN(in_channels=[256,512,1024,2048],
+# out_channels=256, start_level=1, add_extra_convs='on_output', num_outs=5), MPHead(num_classes=10, in_channels=256,
+# stacked_convs=4, feat_channels=256, reg_max=16, GN32, strides 8..128, proxies_list, gamma=10), AnchorGenerator with
+# center_offset 0 (cell (x, y) -> point (x*s, y*s)), test_cfg(score_thr=0.05, nms_pre=1000, nms iou 0.6, max_per_img=500).
+from . import ref_path as _rp
+
+MP_PROXIES = (2, 3, 2, 5, 4, 8, 8, 4, 3, 3)   # mp_head.py:31
+MP_STRIDES = (8, 16, 32, 64, 128)
+
+
+def fpn_forward(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "", start_level: int = 1, num_outs: int = 5):
+    """necks/fpn.py:152-203 with add_extra_convs='on_output', no norm, no activation (ConvModule = conv + bias)."""
+    q = _rp._q
+    n_lat = len(inputs) - start_level
+    lat = [q(F.conv2d(q(inputs[i + start_level]), q(sd[f"{p}lateral_convs.{i}.conv.weight"]),
+                      sd[f"{p}lateral_convs.{i}.conv.bias"])) for i in range(n_lat)]
+    for i in range(n_lat - 1, 0, -1):                                                   # :166-175
+        lat[i - 1] = q(lat[i - 1] + F.interpolate(lat[i], size=lat[i - 1].shape[2:], mode="nearest"))
+    outs = [q(F.conv2d(lat[i], q(sd[f"{p}fpn_convs.{i}.conv.weight"]), sd[f"{p}fpn_convs.{i}.conv.bias"], padding=1))
+            for i in range(n_lat)]                                                      # :179-181
+    for i in range(n_lat, num_outs):                                                    # :196-202 ('on_output')
+        outs.append(q(F.conv2d(outs[-1], q(sd[f"{p}fpn_convs.{i}.conv.weight"]), sd[f"{p}fpn_convs.{i}.conv.bias"],
+                               stride=2, padding=1)))
+    return outs
+
+
+def _conv_gn_relu(sd, p, x):
+    """mmcv ConvModule(conv without bias -> GroupNorm(32) -> ReLU), mp_head.py:46-62."""
+    q = _rp._q
+    y = q(F.conv2d(x, q(sd[p + ".conv.weight"]), None, padding=1))
+    return q(torch.relu(F.group_norm(y, 32, sd[p + ".gn.weight"], sd[p + ".gn.bias"], eps=1e-5)))
+
+
+def mp_forward_proxy(feat: torch.Tensor, proxies: torch.Tensor, proxies_list=MP_PROXIES, gamma: float = 10.0):
+    """mp_head.py:105-121: cosine similarity to the class proxies, softmax(gamma * sim)-weighted sum per class, * gamma."""
+    centers = F.normalize(proxies, p=2, dim=1)
+    feat = F.normalize(feat, p=2, dim=1)
+    sim = feat.matmul(centers.t())
+    out, pre = [], 0
+    for n in proxies_list:
+        sub = sim[:, pre:pre + n]
+        prob = F.softmax(sub * gamma, dim=1)
+        out.append(torch.sum(prob * sub, dim=1)[:, None])
+        pre += n
+    return torch.cat(out, dim=1) * gamma
+
+
+def mp_head_forward(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "", stacked_convs: int = 4,
+                    proxies_list=MP_PROXIES, gamma: float = 10.0):
+    """MPHead.forward_single per level (mp_head.py:123-154): shared towers, gfl_reg * Scale, proxy classification.
+    Returns (cls_scores [B, nc, H, W], bbox_preds [B, 4*(reg_max+1), H, W]) lists."""
+    q = _rp._q
+    cls_scores, bbox_preds = [], []
+    for l, x in enumerate(feats):
+        cf = rf = q(x)
+        for i in range(stacked_convs):
+            cf = _conv_gn_relu(sd, f"{p}cls_convs.{i}", cf)
+            rf = _conv_gn_relu(sd, f"{p}reg_convs.{i}", rf)
+        bbox = F.conv2d(rf, q(sd[p + "gfl_reg.weight"]), sd[p + "gfl_reg.bias"], padding=1) * sd[f"{p}scales.{l}.scale"]
+        f = F.conv2d(cf, q(sd[p + "gfl_cls_conv.weight"]), sd[p + "gfl_cls_conv.bias"], padding=1)
+        b, c, h, w = f.shape
+        s = mp_forward_proxy(f.permute(0, 2, 3, 1).reshape(-1, c), sd[p + "proxies"], proxies_list, gamma)
+        cls_scores.append(s.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous())
+        bbox_preds.append(bbox.float())
+    return cls_scores, bbox_preds
+
+
+def gfl_decode_level(bbox_pred: torch.Tensor, stride: int, img_shape, reg_max: int = 16) -> torch.Tensor:
+    """Integral (gfl_head.py:35-49) * stride and DistancePointBBoxCoder.decode on the cell points (x*s, y*s)
+    (gfl_head.py:437-438,456-457; core/bbox/transforms.py:136-165): [4*(reg_max+1), H, W] -> [H*W, 4] xyxy clamped."""
+    _, h, w = bbox_pred.shape
+    x = bbox_pred.permute(1, 2, 0).reshape(-1, reg_max + 1)
+    d = F.linear(F.softmax(x, dim=1), torch.linspace(0, reg_max, reg_max + 1)[None]).reshape(-1, 4) * stride
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    px, py = (xs.reshape(-1) * stride).float(), (ys.reshape(-1) * stride).float()
+    boxes = torch.stack([px - d[:, 0], py - d[:, 1], px + d[:, 2], py + d[:, 3]], -1)
+    boxes[:, 0::2] = boxes[:, 0::2].clamp(min=0, max=img_shape[1])
+    boxes[:, 1::2] = boxes[:, 1::2].clamp(min=0, max=img_shape[0])
+    return boxes
+
+
+def gfl_get_bboxes_single(cls_scores, bbox_preds, img_shape, score_thr=0.05, nms_pre=1000, iou_thr=0.6, max_per_img=500,
+                          strides=MP_STRIDES):
+    """_get_bboxes_single (gfl_head.py:426-471) + filter_scores_and_topk (core/utils/misc.py:143-165) +
+    _bbox_post_process (base_dense_head.py:276-301) for ONE image: per-level maps [nc, H, W] / [68, H, W].
+    Ties in the per-level sort are broken by (anchor, class) order (torch.sort is not stable; documented choice)."""
+    mb, ms, ml = [], [], []
+    for cs, bp, s in zip(cls_scores, bbox_preds, strides):
+        nc = cs.shape[0]
+        scores = cs.permute(1, 2, 0).reshape(-1, nc).sigmoid()
+        boxes = gfl_decode_level(bp, s, img_shape)
+        flat = scores.reshape(-1)
+        idx = torch.nonzero(flat > score_thr).reshape(-1)
+        order = torch.sort(flat[idx], descending=True, stable=True)[1][:nms_pre]
+        idx = idx[order]
+        ms.append(flat[idx]); ml.append(idx % nc); mb.append(boxes[idx // nc])
+    boxes, scores, labels = torch.cat(mb), torch.cat(ms), torch.cat(ml)
+    if boxes.numel() == 0:
+        return torch.zeros((0, 5)), labels
+    _, keep = mmcv_batched_nms(boxes.numpy(), scores.numpy(), labels.float().numpy(), iou_thr)
+    keep = torch.from_numpy(np.asarray(keep, dtype=np.int64))[:max_per_img]
+    return torch.cat([boxes[keep], scores[keep][:, None]], 1), labels[keep]
+
+
+def mpdet_state_dict_shapes(num_classes: int = 10, proxies_list=MP_PROXIES, reg_max: int = 16, feat: int = 256,
+                            in_channels=(256, 512, 1024, 2048), num_words: int = 200):
+    """Keys / shapes of FPN ('neck.') and MPHead ('bbox_head.') parameters and buffers (mp_head.py:42-98)."""
+    sh = {}
+    for i, c in enumerate(in_channels[1:]):
+        sh[f"neck.lateral_convs.{i}.conv.weight"], sh[f"neck.lateral_convs.{i}.conv.bias"] = (feat, c, 1, 1), (feat,)
+    for i in range(5):
+        sh[f"neck.fpn_convs.{i}.conv.weight"], sh[f"neck.fpn_convs.{i}.conv.bias"] = (feat, feat, 3, 3), (feat,)
+    for br in ("cls_convs", "reg_convs"):
+        for i in range(4):
+            sh[f"bbox_head.{br}.{i}.conv.weight"] = (feat, feat, 3, 3)
+            sh[f"bbox_head.{br}.{i}.gn.weight"], sh[f"bbox_head.{br}.{i}.gn.bias"] = (feat,), (feat,)
+    sh["bbox_head.gfl_cls_conv.weight"], sh["bbox_head.gfl_cls_conv.bias"] = (feat, feat, 3, 3), (feat,)
+    sh["bbox_head.gfl_reg.weight"], sh["bbox_head.gfl_reg.bias"] = (4 * (reg_max + 1), feat, 3, 3), (4 * (reg_max + 1),)
+    for l in range(5):
+        sh[f"bbox_head.scales.{l}.scale"] = ()
+    sh["bbox_head.proxies"] = (sum(proxies_list), feat)
+    sh["bbox_head._embedding"] = (num_classes + 1, num_words, feat)
+    sh["bbox_head._pos_embedding_ptr"] = (num_classes + 1,)
+    sh["bbox_head._proxies_prob"] = (sum(proxies_list),)
+    sh["bbox_head.integral.project"] = (reg_max + 1,)
+    return sh
+
+
+def mpdet_synthetic_state_dict(seed: int = 0, num_classes: int = 10):
+    """Seeded random weights with O(1) activations (variance-preserving convs, GN affine near identity, logit noise)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in mpdet_state_dict_shapes(num_classes).items():
+        if k.endswith("conv.weight") or k.endswith("gfl_cls_conv.weight") or k.endswith("gfl_reg.weight"):
+            fan = shp[1] * shp[2] * shp[3]
+            gain = 1.0 if k.startswith("neck.") else (2.0 if "_convs." in k else 1.0)
+            sd[k] = torch.randn(shp, generator=g) * (gain / fan) ** 0.5
+        elif k.endswith("gn.weight"):
+            sd[k] = 1.0 + 0.05 * torch.randn(shp, generator=g)
+        elif k.endswith(".bias"):
+            sd[k] = 0.1 * torch.randn(shp, generator=g)
+        elif k.endswith(".scale"):
+            sd[k] = torch.tensor(1.0 + 0.1 * float(torch.randn((), generator=g)))
+        elif k.endswith("proxies"):
+            sd[k] = torch.randn(shp, generator=g)
+        elif k.endswith("_embedding"):
+            sd[k] = torch.randn(shp, generator=g)
+        elif k.endswith("_pos_embedding_ptr"):
+            sd[k] = torch.zeros(shp, dtype=torch.long)
+        elif k.endswith("_proxies_prob"):
+            sd[k] = torch.cat([torch.full((n,), 1.0 / n) for n in MP_PROXIES])
+        elif k.endswith("integral.project"):
+            sd[k] = torch.linspace(0, 16, 17)
+        else:
+            raise KeyError(k)
+    return sd
