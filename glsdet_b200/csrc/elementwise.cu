@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __
   if (row < rows_par) {
     for (int vec = vl; vec < nvec; vec += lanes) {
       float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 4
       for (int p = p_begin + row; p < p_end; p += rows_par) {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<int64_t>(b) * HW + p) * ld) + vec);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};

@@ -1,0 +1,35 @@
+"""Warm time of the post-processing pipeline alone on the bench workload's predictions (CUDA events)."""
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda", 0)
+    sd = bench.make_weights()
+    net = bench.body_class()(bench.NUM_CLASSES, bench.PHI)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(dev).eval()
+    feats = bench.make_features(net, 16, 1000, dev)
+    plan = net.plan_for(feats)
+    pred = plan.forward_decoded(feats).clone()
+    nms = net.nms_for(plan, 1000)
+    for _ in range(5):
+        nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"post-processing: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per batch of 16")
+
+
+if __name__ == "__main__":
+    main()
