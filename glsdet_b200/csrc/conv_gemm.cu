@@ -575,7 +575,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           for (int ch = 0; ch < nch; ++ch) {
             mbar_wait(&a_empty[s], ph ^ 1u);
             if (cta_rank == 0) mbar_arrive_expect_tx(&a_full[s], pair_bytes);
-            else mbar_arrive_cluster(&a_full[s], 0);
+            else mbar_arrive_cluster_relaxed(&a_full[s], 0);   // counts this producer; the data is tracked by complete_tx
             uint8_t* bdst = smem_b + s * b_bytes;
             if (p.nsub == 3) {
               tma2_load_5d(smem_a + s * p.a_bytes, &p.tmA[src], &a_full[s], ch * kChunkK, t.x0 + o - 1, 0, t.y0 - 1, t.b);
@@ -789,8 +789,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     const int py = r >> p.tile_w_log2;
     const int px = r & ((1 << p.tile_w_log2) - 1);
     const int n_chunks = p.block_n >> 4;
-    const int c_begin = half ? ((n_chunks + 1) >> 1) : 0;
-    const int c_end = half ? n_chunks : ((n_chunks + 1) >> 1);
+    // column chunks of this warp: two parts with 8 epilogue warps, four with 16
+    const int c_begin = (EW == 16) ? (n_chunks * half) / 4 : (half ? ((n_chunks + 1) >> 1) : 0);
+    const int c_end = (EW == 16) ? (n_chunks * (half + 1)) / 4 : (half ? n_chunks : ((n_chunks + 1) >> 1));
     const bool silu = (p.act == GLSDET_ACT_SILU);
     const int mt = k2 ? 1 : p.mt;
     TsCtx tsg;
@@ -1007,7 +1008,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           });
           fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
           tc_fence_before();
-          asm volatile("bar.sync 5, 256;" ::: "memory");
+          named_bar_sync(5, EW * 32);
           if (e == 0) {
             tc_fence_after();
             if (elect_one()) {
@@ -1055,7 +1056,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (k2) mbar_arrive_cluster(&tempty_bar[as], 0);   // the leader's MMA thread waits for both epilogues
+        if (k2) mbar_arrive_cluster_relaxed(&tempty_bar[as], 0);   // the leader's MMA thread waits for both epilogues
         else mbar_arrive(&tempty_bar[as]);
       }
     }
@@ -1089,9 +1090,11 @@ struct glsdet_conv {
 namespace {
 typedef void (*ConvKernelFn)(const ConvKParams);
 constexpr int EC_BF16_TS16 = EC_COUNT;   // TMA-store class with 16 epilogue warps (640 threads)
+constexpr int EC_PRED_MMA16 = EC_COUNT + 1;   // tensor-core prediction class with 16 epilogue warps
 ConvKernelFn conv_kernel_for(int ec) {
   switch (ec) {
     case EC_BF16_TS16: return conv_gemm_kernel<false, EC_BF16_TS, 16>;
+    case EC_PRED_MMA16: return conv_gemm_kernel<false, EC_PRED_MMA, 16>;
     case EC_BF16: return conv_gemm_kernel<false, EC_BF16>;
     case EC_BF16_TS: return conv_gemm_kernel<false, EC_BF16_TS>;
     case EC_F32: return conv_gemm_kernel<false, EC_F32>;
@@ -1234,12 +1237,18 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   ConvKParams& k = op->kp;
   k.B = d->batch; k.Ho = g.Ho; k.Wo = g.Wo;
 
-  // 2-CTA mode (cta_group::2, M = 256 per CTA pair).  Measured on B200 (profiles/README.md): correct, 40 % less
-  // L2->SM traffic, but 5-15 % slower than the 1-CTA kernel at these shapes, so it is opt-in: GLSDET_CONV_2CTA=1.
-  bool two_cta = false;
+  // 2-CTA mode (cta_group::2, M = 256 per CTA pair): each SM feeds the tensor core its own 128 rows of A and HALF of the
+  // B rows, so the shared-memory operand traffic per MMA drops from A + B to A + B/2 (the 1-CTA kernel is bound by
+  // it: 50 % tensor-pipe utilisation at N = 128, 67 % at N = 256) and every weight byte is fetched from L2 once per 256
+  // pixels.  Measured (profiles/README.md): 3x3 N=256 at 256^2 491 -> 385 us (1.6 PF/s), N=128 299 -> 207 us.  Default
+  // for 3x3 stride-1 convs; the small-K 1x1 convs stay on the 1-CTA kernel (resident weights, TMA-store epilogue).
+  // GLSDET_CONV_2CTA=0 disables it, =1 also uses it for 1x1 convs.
+  bool two_cta = d->stride == 1 && d->ksize == 3 && (g.block_n % 32) == 0;
   if (const char* e = getenv("GLSDET_CONV_2CTA")) {
+    if (e[0] == '0') two_cta = false;
     if (e[0] == '1') two_cta = d->stride == 1 && d->ksize <= 3 && (g.block_n % 32) == 0;
   }
+  if (d->weight_batch_stride != 0 || d->patch_mode != 0) two_cta = false;
   op->two_cta = two_cta ? 1 : 0;
   const int sms = device_sm_count();
 
@@ -1345,11 +1354,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     set_error("conv_create: patch_mode needs the TMA-store epilogue (bf16 output, channels a multiple of 64)");
     return 2;
   }
-  if ((patch || w_batched) && two_cta) {
-    free(mem);
-    set_error("conv_create: patch_mode / per-image weights are not available in the 2-CTA kernel");
-    return 2;
-  }
+
   // Fused prediction conv: on the tensor core when the tower width is a multiple of 64 (activated tile staged in
   // shared memory as a bf16 operand), else per-thread FMAs.
   bool pred_mma = fused_pred && !two_cta && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
@@ -1511,14 +1516,17 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   }
   if (op->ec == EC_BF16_TS && (g.block_n == 64 || g.block_n == 128) && getenv("GLSDET_CONV_EPI8") == nullptr)
     op->ec = EC_BF16_TS16;
+  // the second tower conv + prediction MMA: its epilogue (activate, stage, prediction MMA round trip, decode) is as long
+  // as the MMAs of two tiles with two warps per scheduler; four warps per scheduler halve the per-thread work
+  if (op->ec == EC_PRED_MMA && (g.block_n % 64) == 0 && getenv("GLSDET_CONV_EPI8") == nullptr) op->ec = EC_PRED_MMA16;
   if (op->two_cta || getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
-  op->threads = (op->ec == EC_BF16_TS16) ? (4 + 16) * 32 : kThreads;
+  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16) ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<true, EC_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    for (int ec = 0; ec <= EC_COUNT && e == cudaSuccess; ++ec)
+    for (int ec = 0; ec <= EC_COUNT + 1 && e == cudaSuccess; ++ec)
       e = cudaFuncSetAttribute(conv_kernel_for(ec), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) {
       free(mem);

@@ -195,6 +195,18 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
       ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
+// same without release semantics: for barriers that only order tcgen05 operations (TMEM accumulator hand-over, ordered
+// by tcgen05.fence), where a cluster-scope release would make the arriving warp wait for all its global stores
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
 // TMA loads of a CTA pair: data lands in the issuing CTA, the transaction bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(

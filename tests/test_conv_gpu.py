@@ -231,7 +231,8 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
     t = F.conv2d(x, w, bias, padding=1)
     t = t * torch.sigmoid(t)
     import os
-    if n_tower % 64 == 0 and not os.environ.get("GLSDET_CONV_PRED_FMA"):
+    one_cta = os.environ.get("GLSDET_CONV_2CTA") == "0"   # 3x3 convs run on the 2-CTA kernel (FMA prediction path) by default
+    if one_cta and n_tower % 64 == 0 and not os.environ.get("GLSDET_CONV_PRED_FMA"):
         # tensor-core prediction path: the activated tile and the prediction weights are bf16 MMA operands
         y = F.conv2d(_bf16r(t), _bf16r(wp), bp)
     else:
@@ -270,7 +271,8 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
 
 
 def test_two_cta_mode(native_lib, cuda_device, monkeypatch):
-    """cta_group::2 variant (CTA pairs, M = 256 per tcgen05.mma, operands split over two SMs): opt-in, same results."""
+    """cta_group::2 variant (CTA pairs, M = 256 per tcgen05.mma, operands split over two SMs) forced for every stride-1
+    conv including the 1x1 ones (it is the default for 3x3 only)."""
     monkeypatch.setenv("GLSDET_CONV_2CTA", "1")
     monkeypatch.setenv("GLSDET_CONV_PRED_FMA", "1")   # the 2-CTA kernel keeps the FMA prediction path
     for case in (CASES[2], CASES[3], CASES[6], CASES[9], CASES[10]):
@@ -280,18 +282,21 @@ def test_two_cta_mode(native_lib, cuda_device, monkeypatch):
 
 
 def test_fused_pred_fma_path(native_lib, cuda_device, monkeypatch):
-    """Per-thread FMA prediction path (tower widths that are not a multiple of 64 use it; forced here)."""
+    """Per-thread FMA prediction path on the 1-CTA kernel (tower widths that are not a multiple of 64 use it; forced)."""
+    monkeypatch.setenv("GLSDET_CONV_2CTA", "0")
     monkeypatch.setenv("GLSDET_CONV_PRED_FMA", "1")
     test_fused_tower_pred_conv(128, 10, "sigmoid", native_lib, cuda_device)
     test_fused_tower_pred_conv(128, 5, "box", native_lib, cuda_device)
     test_fused_tower_pred_conv(256, 3, "sigmoid", native_lib, cuda_device)
 
 
-@pytest.mark.parametrize("env", [{"GLSDET_CONV_MT": "2"}, {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BRES": "1"},
-                                 {"GLSDET_CONV_MT": "1", "GLSDET_CONV_NO_BRES": "1", "GLSDET_CONV_NO_PDL": "1"},
-                                 {"GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BGROUP": "1"},
-                                 {"GLSDET_CONV_NO_TMA_STORE": "1"}],
-                         ids=["mt2", "mt2_nobres", "mt1_nobres_nopdl", "mt2_nobgroup", "direct_stores"])
+@pytest.mark.parametrize("env", [{"GLSDET_CONV_2CTA": "0"},
+                                 {"GLSDET_CONV_2CTA": "0", "GLSDET_CONV_MT": "2"},
+                                 {"GLSDET_CONV_2CTA": "0", "GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BRES": "1"},
+                                 {"GLSDET_CONV_2CTA": "0", "GLSDET_CONV_MT": "1", "GLSDET_CONV_NO_BRES": "1", "GLSDET_CONV_NO_PDL": "1"},
+                                 {"GLSDET_CONV_2CTA": "0", "GLSDET_CONV_MT": "2", "GLSDET_CONV_NO_BGROUP": "1"},
+                                 {"GLSDET_CONV_NO_TMA_STORE": "1"}, {"GLSDET_CONV_2CTA": "0", "GLSDET_CONV_EPI8": "1"}],
+                         ids=["one_cta", "mt2", "mt2_nobres", "mt1_nobres_nopdl", "mt2_nobgroup", "direct_stores", "epi8"])
 def test_conv_schedule_variants(env, native_lib, cuda_device, monkeypatch):
     """Work-item shapes and weight staging are scheduling choices: two M tiles per weight stage (mt=2), resident
     weights, grouped ky taps, programmatic dependent launch - every combination must give the same results."""
