@@ -485,6 +485,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint64_t* tempty_bar = bars + 4 * kMaxStages + 2;
   uint64_t* bres_full = bars + 4 * kMaxStages + 4;
   uint64_t* pred_bar = bars + 4 * kMaxStages + 5;
+  uint64_t* pstage_bar = bars + 4 * kMaxStages + 7;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 6);
   float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);  // [n_blocks * block_n], zero padded
   float* s_pw = s_bias + p.n_blocks * p.block_n;                         // FMA prediction path: weights [N][16]
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     }
     mbar_init(bres_full, 1);
     mbar_init(pred_bar, 1);
+    mbar_init(pstage_bar, 2);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -536,9 +538,12 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
   if (pred_mma) {
     // prediction weights fp32 [pred_n][N] -> bf16 B operand (16 rows, K-major, 128-byte swizzle) per 64-channel tile
-    for (int i = threadIdx.x; i < 16 * p.block_n; i += kThreads) {
+    // (2-CTA: the M256 x N16 prediction MMA takes 8 of the 16 rows from each CTA, at the same shared-memory offset)
+    const int prow = k2 ? 8 : 16, prow0 = k2 ? static_cast<int>(cta_rank) * 8 : 0;
+    for (int i = threadIdx.x; i < prow * p.block_n; i += kThreads) {
       const int n = i / p.block_n, k = i - n * p.block_n;
-      const float v = (n < p.pred_n && k < p.N) ? __ldg(p.pred_w + static_cast<int64_t>(n) * p.N + k) : 0.0f;
+      const int ng = prow0 + n;
+      const float v = (ng < p.pred_n && k < p.N) ? __ldg(p.pred_w + static_cast<int64_t>(ng) * p.N + k) : 0.0f;
       const int kc = k >> 6, kk = k & 63;
       const int off = kc * kPredTileBytes + (n >> 3) * 1024 + (n & 7) * kRowBytes + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
       *reinterpret_cast<__nv_bfloat16*>(smem_pw + off) = __float2bfloat16_rn(v);
@@ -1009,7 +1014,33 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core (async proxy)
           tc_fence_before();
           named_bar_sync(5, EW * 32);
-          if (e == 0) {
+          if (k2) {
+            // both CTAs of the pair stage their tile; the leader issues ONE M256 x N16 MMA chain over both halves and
+            // its commit arrives on pred_bar in both CTAs.  The staged data is consumed by each SM's own tensor core
+            // after the leader has seen both arrives, so the arrive itself needs no release fence.
+            if (e == 0) {
+              if (elect_one()) mbar_arrive_cluster_relaxed(pstage_bar, 0);
+              __syncwarp();
+              if (cta_rank == 0) {
+                mbar_wait(pstage_bar, tcount & 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                  const uint32_t idesc_p = umma_idesc_bf16(2 * kBlockM, 16);
+                  const uint32_t d_pred = tmem_base + tcol;
+                  for (int kc = 0; kc < k_tiles; ++kc) {
+                    const uint64_t da = umma_desc_k_sw128(smem_u32(smem_stage + kc * kStageTileBytes));
+                    const uint64_t db = umma_desc_k_sw128(smem_u32(smem_pw + kc * kPredTileBytes));
+#pragma unroll
+                    for (int kk = 0; kk < kChunkK / 16; ++kk)
+                      umma2_bf16(d_pred, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc_p,
+                                 (kc | kk) ? 1u : 0u);
+                  }
+                  umma2_commit_both(pred_bar);
+                }
+                __syncwarp();
+              }
+            }
+          } else if (e == 0) {
             tc_fence_after();
             if (elect_one()) {
               const uint32_t idesc_p = umma_idesc_bf16(kBlockM, 16);
@@ -1357,7 +1388,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
 
   // Fused prediction conv: on the tensor core when the tower width is a multiple of 64 (activated tile staged in
   // shared memory as a bf16 operand), else per-thread FMAs.
-  bool pred_mma = fused_pred && !two_cta && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
+  bool pred_mma = fused_pred && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
                   getenv("GLSDET_CONV_PRED_FMA") == nullptr;
   const int b_tap_bytes = g.block_n * kRowBytes;
   bool bres = false;
@@ -1428,7 +1459,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   int cols = 32;
   while (cols < k.nacc * mt * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
-  k.pdl = (!two_cta && getenv("GLSDET_CONV_NO_PDL") == nullptr) ? 1 : 0;
+  k.pdl = (getenv("GLSDET_CONV_NO_PDL") == nullptr) ? 1 : 0;
   k.ts = ts ? 1 : 0;
   k.w_batched = w_batched ? 1 : 0;
   k.a_shared = d->src_shared > 0 ? d->src_shared : 0;
@@ -1553,13 +1584,15 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = op->smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = op->kp.pdl ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, EC_ALL>, op->kp);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(conv_gemm_kernel<2cta>) failed: %s", cudaGetErrorString(e));

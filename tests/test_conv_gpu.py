@@ -231,8 +231,7 @@ def test_fused_tower_pred_conv(n_tower, n_pred, pred_act, native_lib, cuda_devic
     t = F.conv2d(x, w, bias, padding=1)
     t = t * torch.sigmoid(t)
     import os
-    one_cta = os.environ.get("GLSDET_CONV_2CTA") == "0"   # 3x3 convs run on the 2-CTA kernel (FMA prediction path) by default
-    if one_cta and n_tower % 64 == 0 and not os.environ.get("GLSDET_CONV_PRED_FMA"):
+    if n_tower % 64 == 0 and not os.environ.get("GLSDET_CONV_PRED_FMA"):
         # tensor-core prediction path: the activated tile and the prediction weights are bf16 MMA operands
         y = F.conv2d(_bf16r(t), _bf16r(wp), bp)
     else:
