@@ -1122,10 +1122,15 @@ namespace {
 typedef void (*ConvKernelFn)(const ConvKParams);
 constexpr int EC_BF16_TS16 = EC_COUNT;   // TMA-store class with 16 epilogue warps (640 threads)
 constexpr int EC_PRED_MMA16 = EC_COUNT + 1;   // tensor-core prediction class with 16 epilogue warps
+constexpr int EC2_ALL = EC_COUNT + 2;         // 2-CTA kernel, every epilogue
+constexpr int EC2_PRED_MMA16 = EC_COUNT + 3;  // 2-CTA kernel, tensor-core prediction class, 16 epilogue warps
+constexpr int EC_KERNELS = EC_COUNT + 4;
 ConvKernelFn conv_kernel_for(int ec) {
   switch (ec) {
     case EC_BF16_TS16: return conv_gemm_kernel<false, EC_BF16_TS, 16>;
     case EC_PRED_MMA16: return conv_gemm_kernel<false, EC_PRED_MMA, 16>;
+    case EC2_ALL: return conv_gemm_kernel<true, EC_ALL>;
+    case EC2_PRED_MMA16: return conv_gemm_kernel<true, EC_PRED_MMA, 16>;
     case EC_BF16: return conv_gemm_kernel<false, EC_BF16>;
     case EC_BF16_TS: return conv_gemm_kernel<false, EC_BF16_TS>;
     case EC_F32: return conv_gemm_kernel<false, EC_F32>;
@@ -1550,14 +1555,16 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // the second tower conv + prediction MMA: its epilogue (activate, stage, prediction MMA round trip, decode) is as long
   // as the MMAs of two tiles with two warps per scheduler; four warps per scheduler halve the per-thread work
   if (op->ec == EC_PRED_MMA && (g.block_n % 64) == 0 && getenv("GLSDET_CONV_EPI8") == nullptr) op->ec = EC_PRED_MMA16;
-  if (op->two_cta || getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
-  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16) ? (4 + 16) * 32 : kThreads;
+  if (getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
+  if (op->two_cta)   // the pair kernel: one all-epilogue binary, plus the prediction class with 16 epilogue warps
+    op->ec = (op->ec == EC_PRED_MMA16 && getenv("GLSDET_CONV_ONE_KERNEL") == nullptr) ? EC2_PRED_MMA16 : EC2_ALL;
+  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16) ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<true, EC_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    for (int ec = 0; ec <= EC_COUNT + 1 && e == cudaSuccess; ++ec)
+    cudaError_t e = cudaSuccess;
+    for (int ec = 0; ec < EC_KERNELS && e == cudaSuccess; ++ec)
       e = cudaFuncSetAttribute(conv_kernel_for(ec), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) {
       free(mem);
@@ -1581,7 +1588,7 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
   if (op->two_cta) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(op->grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(op->threads);
     cfg.dynamicSmemBytes = op->smem_bytes;
     cfg.stream = static_cast<cudaStream_t>(stream);
     cudaLaunchAttribute attr[2];
@@ -1593,7 +1600,7 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = op->kp.pdl ? 2 : 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true, EC_ALL>, op->kp);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(op->ec), op->kp);
     if (e != cudaSuccess) {
       set_error("cudaLaunchKernelEx(conv_gemm_kernel<2cta>) failed: %s", cudaGetErrorString(e));
       return 1;
