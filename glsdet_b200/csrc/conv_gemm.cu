@@ -1124,13 +1124,15 @@ constexpr int EC_BF16_TS16 = EC_COUNT;   // TMA-store class with 16 epilogue war
 constexpr int EC_PRED_MMA16 = EC_COUNT + 1;   // tensor-core prediction class with 16 epilogue warps
 constexpr int EC2_ALL = EC_COUNT + 2;         // 2-CTA kernel, every epilogue
 constexpr int EC2_PRED_MMA16 = EC_COUNT + 3;  // 2-CTA kernel, tensor-core prediction class, 16 epilogue warps
-constexpr int EC_KERNELS = EC_COUNT + 4;
+constexpr int EC2_BF16_TS16 = EC_COUNT + 4;   // 2-CTA kernel, TMA-store class, 16 epilogue warps
+constexpr int EC_KERNELS = EC_COUNT + 5;
 ConvKernelFn conv_kernel_for(int ec) {
   switch (ec) {
     case EC_BF16_TS16: return conv_gemm_kernel<false, EC_BF16_TS, 16>;
     case EC_PRED_MMA16: return conv_gemm_kernel<false, EC_PRED_MMA, 16>;
     case EC2_ALL: return conv_gemm_kernel<true, EC_ALL>;
     case EC2_PRED_MMA16: return conv_gemm_kernel<true, EC_PRED_MMA, 16>;
+    case EC2_BF16_TS16: return conv_gemm_kernel<true, EC_BF16_TS, 16>;
     case EC_BF16: return conv_gemm_kernel<false, EC_BF16>;
     case EC_BF16_TS: return conv_gemm_kernel<false, EC_BF16_TS>;
     case EC_F32: return conv_gemm_kernel<false, EC_F32>;
@@ -1380,7 +1382,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   const bool fused_pred = d->pred_weight != nullptr;
   const bool patch = d->patch_mode != 0;
   const bool w_batched = d->weight_batch_stride != 0;
-  bool ts = !two_cta && !fused_pred &&
+  bool ts = !fused_pred &&
             (k.epi == EPI_BF16 || k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST || k.epi == EPI_BF16_PREPOST) &&
             (d->out_channels % 64) == 0 && (g.block_n % 64) == 0 && (g.k_pad <= 640 || patch) &&
             d->out_batch_stride == static_cast<int64_t>(g.Ho) * g.Wo * d->out_ld &&
@@ -1557,8 +1559,10 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   if (op->ec == EC_PRED_MMA && (g.block_n % 64) == 0 && getenv("GLSDET_CONV_EPI8") == nullptr) op->ec = EC_PRED_MMA16;
   if (getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
   if (op->two_cta)   // the pair kernel: one all-epilogue binary, plus the prediction class with 16 epilogue warps
-    op->ec = (op->ec == EC_PRED_MMA16 && getenv("GLSDET_CONV_ONE_KERNEL") == nullptr) ? EC2_PRED_MMA16 : EC2_ALL;
-  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16) ? (4 + 16) * 32 : kThreads;
+    op->ec = getenv("GLSDET_CONV_ONE_KERNEL") != nullptr ? EC2_ALL
+             : op->ec == EC_PRED_MMA16 ? EC2_PRED_MMA16 : op->ec == EC_BF16_TS16 ? EC2_BF16_TS16 : EC2_ALL;
+  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16 || op->ec == EC2_BF16_TS16)
+                    ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
