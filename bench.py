@@ -12,7 +12,10 @@ what the reference's CSPDarknet hands to the neck) -> neck -> FFA -> head -> fus
 (conf 0.01, yolo.py:44) -> class-aware NMS (iou 0.65, yolo.py:48) -> [K,7] detections; for N > 1 ranks the
 per-step NCCL gather of the detections is part of the step.  Inputs are synthetic: random-init weights of the
 reference's exact shapes (glsdet_b200/synthetic.py) and feature maps produced once by the CSPDarknet backbone from
-seeded noise images; the backbone is upstream of the metric and is not timed.
+seeded noise images; the backbone is upstream of the metric and is not part of `value` or of the roofline segment.
+`e2e` goes through the public module API with host buffers: YoloBody.detect(pinned host image batch) -> detections on
+the host, i.e. it additionally runs the native CSPDarknet backbone (SURVEY.md section 8f row 1) in front of the path;
+`e2e.from_features` is the same with host feature maps (the metric's exact segment, PCIe-bound on 503 MB per step).
 """
 from __future__ import annotations
 
@@ -148,17 +151,24 @@ def ref_neck_head(sd, feats):
     return ref_path.neck_head(sd, feats) if VARIANT == "p0" else ref_path.p1_neck_head(sd, feats)
 
 
-def make_features(net, batch, seed, device):
-    """Backbone features of seeded synthetic images (unit variance, natural-image-like spectrum); not timed."""
+def make_images(batch, seed):
+    """Seeded synthetic images (unit variance, natural-image-like spectrum), [batch, 3, 1024, 1024] fp32 on the host."""
     import torch
 
     from glsdet_b200.synthetic import synthetic_images
 
+    return torch.cat([synthetic_images(min(4, batch - i), IN_H, IN_W, seed=seed * 64 + i) for i in range(0, batch, 4)])
+
+
+def make_features(net, batch, seed, device, images=None):
+    """Backbone features (NCHW fp32, what the reference's CSPDarknet hands to the neck) of the synthetic images."""
+    import torch
+
+    images = make_images(batch, seed) if images is None else images
     feats = None
     with torch.no_grad():
         for i in range(0, batch, 4):
-            x = synthetic_images(min(4, batch - i), IN_H, IN_W, seed=seed * 64 + i).to(device)
-            f = [t.float().contiguous() for t in net.backbone.features(x)]
+            f = [t.float().contiguous() for t in net.backbone.features(images[i:i + 4].to(device))]
             feats = f if feats is None else [torch.cat([a, b]) for a, b in zip(feats, f)]
     return feats
 
@@ -258,9 +268,9 @@ def run_native_arm(args):
     net.load_state_dict(sd, strict=True)
     net = net.to(dev).eval()
     B = args.batch
-    feats = make_features(net, B, 1000 + rank, dev)
+    host_images = make_images(B, 1000 + rank).pin_memory()
+    feats = make_features(net, B, 1000 + rank, dev, images=host_images)
     host_feats = [t.cpu().pin_memory() for t in feats]
-    h2d_bytes = sum(t.numel() * 4 for t in host_feats)
     plan = net.plan_for(feats)
     max_det = args.max_det
     nms = net.nms_for(plan, max_det)
@@ -311,57 +321,95 @@ def run_native_arm(args):
         elapsed_ms = float(t.item())
     value = world * B * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- end-to-end: pinned host features -> device -> path -> detections back on the host, every step.
-    # Two device input sets: the upload of step i+1 (copy stream) overlaps the compute of step i; the host waits
-    # for step i's detections (counts + rows) before it moves on.  Every step's H2D and D2H is inside the region.
-    dev_in = [[torch.empty_like(t, device=dev) for t in host_feats] for _ in range(2)]
+    # ---- end-to-end through the public module API with HOST buffers, every step: pinned host input -> device ->
+    # path -> detections (counts + rows) back on the host.  Two device input sets: the upload of step i+1 (copy
+    # stream) overlaps the compute of step i; the host waits for step i's detections before it moves on.
+    #   "images":   YoloBody.detect(image batch) - what a user of the reference calls (yolo.py:116-160 feeds images);
+    #               the CSPDarknet backbone (+27.9 GFLOP/image, NOT part of the metric's work and not
+    #               part of the reference arm's) runs natively in front of the path, 201 MB of H2D per step;
+    #   "features": YoloBody.detect_features(dark2..dark5 fp32 NCHW) - exactly the metric's segment, 503 MB of H2D per
+    #               step (PCIe-bound).
     host_cnt = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
     host_det = [torch.empty((B, max_det, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
-    uploaded = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
 
-    def upload(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])       # the previous user of this input set has finished
-            for d, h in zip(dev_in[slot], host_feats):
-                d.copy_(h, non_blocking=True)
-            uploaded[slot].record(copy_stream)
+    def e2e_measure(host_inputs, step_fn):
+        dev_in = [[torch.empty_like(t, device=dev) for t in host_inputs] for _ in range(2)]
+        uploaded = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_run(n_steps):
-        for ev_ in consumed:
-            ev_.record(stream)
-        upload(0)
-        for i in range(n_steps):
-            slot = i & 1
-            if i + 1 < n_steps:
-                upload(slot ^ 1)
-            stream.wait_event(uploaded[slot])
-            det, cnt = net.detect_features(dev_in[slot], conf_thres=CONF_THRES, nms_thres=NMS_THRES,
-                                           strategy="auto_cuda", max_det=max_det)
-            consumed[slot].record(stream)
-            if world > 1:
-                gather_detections(det, cnt, max_rows=max_det)
-            host_cnt[slot].copy_(cnt, non_blocking=True)
-            host_det[slot].copy_(det, non_blocking=True)
-            done[slot].record(stream)
-            done[slot].synchronize()                     # the caller reads this step's detections now
+        def upload(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])       # the previous user of this input set has finished
+                for d, h in zip(dev_in[slot], host_inputs):
+                    d.copy_(h, non_blocking=True)
+                uploaded[slot].record(copy_stream)
 
-    e2e_run(max(2, args.warmup // 2))
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    sync_all()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+        def run(n_steps):
+            for ev_ in consumed:
+                ev_.record(stream)
+            upload(0)
+            for i in range(n_steps):
+                slot = i & 1
+                if i + 1 < n_steps:
+                    upload(slot ^ 1)
+                stream.wait_event(uploaded[slot])
+                det, cnt = step_fn(dev_in[slot])
+                consumed[slot].record(stream)
+                if world > 1:
+                    gather_detections(det, cnt, max_rows=max_det)
+                host_cnt[slot].copy_(cnt, non_blocking=True)
+                host_det[slot].copy_(det, non_blocking=True)
+                done[slot].record(stream)
+                done[slot].synchronize()                     # the caller reads this step's detections now
+
+        run(max(2, args.warmup // 2))
+        sync_all()
+        t0 = time.perf_counter()
+        run(args.steps)
+        sync_all()
+        ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        del dev_in
+        return ms
+
+    kw = dict(conf_thres=CONF_THRES, nms_thres=NMS_THRES, strategy="auto_cuda", max_det=max_det)
+    if VARIANT == "p0":
+        image_step = lambda inp: net.detect(inp[0], **kw)
+    else:   # P1 / P2: native backbone -> NCHW fp32 features -> path
+        image_step = lambda inp: net.detect_features(net.backbone.features(inp[0]), **kw)
+    feat_ms = e2e_measure(host_feats, lambda inp: net.detect_features(inp, **kw))
+    e2e_ms = e2e_measure([host_images], image_step)
+    kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    feat_value = world * B * args.steps / (feat_ms * 1e-3)
+    h2d_bytes = host_images.numel() * 4
+    h2d_feat_bytes = sum(t.numel() * 4 for t in host_feats)
+
+    # ---- device-resident image -> detections (backbone included), for the record
+    dev_images = host_images.to(dev)
+    for _ in range(3):
+        image_step([dev_images])
+    sync_all()
+    evi = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    evi[0].record(stream)
+    for _ in range(args.steps):
+        det, cnt = image_step([dev_images])
+        if world > 1:
+            gather_detections(det, cnt, max_rows=max_det)
+    evi[1].record(stream)
+    sync_all()
+    img_ms = evi[0].elapsed_time(evi[1]) / args.steps
+    if world > 1:
+        t = torch.tensor([img_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        img_ms = float(t.item())
     d2h_bytes = host_cnt[0].numel() * 4 + host_det[0].numel() * 4
     cand = [int(v) for v in ((plan.pred[:, :, 4] * plan.pred[:, :, 5:].max(2)[0]) >= CONF_THRES).sum(1).cpu()]
-    kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
 
     if rank == 0:
         pk = peaks()
@@ -381,7 +429,15 @@ def run_native_arm(args):
                            "parallelism": f"dp{world} (images sharded, NCCL gather of detections)" if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps,
-                        "how": "wall clock; upload of step i+1 overlaps compute of step i (2 input sets, copy stream)"},
+                        "how": "wall clock; YoloBody.detect(pinned host image batch fp32) -> host detections; the native "
+                               "CSPDarknet backbone (+27.9 GFLOP/image, outside the metric and outside the reference arm) "
+                               "runs in front of the path; upload of step i+1 overlaps compute of step i (2 input sets, copy stream)",
+                        "from_features": {"value": feat_value, "unit": "images/s", "h2d_bytes_per_step": h2d_feat_bytes,
+                                          "ms_per_step": feat_ms / args.steps,
+                                          "how": "same, but YoloBody.detect_features(pinned host dark2..dark5 fp32 NCHW): "
+                                                 "exactly the metric's segment, PCIe-bound on 503 MB per step"}},
+                "with_backbone": {"value": world * B / (img_ms * 1e-3), "unit": "images/s", "ms_per_step": img_ms,
+                                  "what": "device-resident image batch -> backbone -> neck -> head -> NMS (CUDA events)"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",

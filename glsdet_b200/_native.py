@@ -40,6 +40,7 @@ class ConvDesc(C.Structure):
         ("pred_weight", C.c_void_p), ("pred_bias", C.c_void_p), ("pred_channels", C.c_int32), ("pred_act", C.c_int32),
         ("weight_batch_stride", C.c_int64), ("weight_ld", C.c_int32), ("src_shared", C.c_int32),
         ("src_shared_div", C.c_int32), ("patch_mode", C.c_int32),
+        ("ksize_w", C.c_int32), ("src0_row_pitch", C.c_int64), ("src0_img_pitch", C.c_int64),
     ]
 
 
@@ -111,6 +112,10 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_focus_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                     C.c_void_p]),
+    "glsdet_spp_maxpool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_se_gate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_scale_pixel_shuffle": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

@@ -1,0 +1,163 @@
+"""Execution plan of the CSPDarknet backbone (yolox-drone/models/ffa/darknet.py:10-37,115-195; the identical file is
+models/new/darknet.py and models/base/darknet.py) - SURVEY.md section 8(f) row 1, the caller side of the hot path.
+
+Image batch [B, 3, H, W] fp32 NCHW -> (dark2, dark3, dark4, dark5) as NHWC bf16 buffers, which are the input buffers of
+the neck plan when the two are chained (no NCHW fp32 round trip between backbone and neck):
+
+  * Focus (darknet.py:15-21): one kernel does the space-to-depth and the layout / type change of the image
+    (glsdet_focus_nchw_f32_to_nhwc_bf16, 16-channel pixels); the 3x3 stem conv reads it with zero weights on the 4 pad channels;
+  * every BaseConv = the tcgen05 implicit-GEMM conv with folded BatchNorm and SiLU in the epilogue;
+  * CSPLayer: conv1 | conv2 as one GEMM into the concat buffer, Bottleneck shortcut (darknet.py:59-63) as the bf16
+    post-residual of the 3x3 conv written in place, conv3 on the concat buffer;
+  * SPPBottleneck (darknet.py:24-37): conv1 writes window 0 of the 4C concat buffer, one kernel writes the 5/9/13 max
+    pools into windows 1..3 (cascaded separable 5-wide maxima in shared memory), conv2 reads the buffer.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+from .ops import ConvOp, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_weight, nhwc_to_nchw
+
+BN_EPS = 1e-3
+FEATURES = ("dark2", "dark3", "dark4", "dark5")
+
+
+def backbone_supported(base_channels: int) -> bool:
+    """The native plan needs channel counts that are multiples of 16 (phi = s, m, l, x; not tiny / nano)."""
+    return base_channels % 32 == 0
+
+
+class BackbonePlan:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], device=None,
+                 act: str = "silu", prefix: str = "backbone.backbone.", outs: Optional[Dict[str, torch.Tensor]] = None):
+        """`outs` optionally maps feature names ("dark2".."dark5") to existing NHWC bf16 tensors [B, H/s, W/s, C] (the
+        input buffers of a neck plan); missing ones are allocated here."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self.B = batch
+        self.in_h, self.in_w = int(input_hw[0]), int(input_hw[1])
+        if self.in_h % 32 or self.in_w % 32:
+            raise ValueError("input size must be a multiple of 32 (yolox-drone/yolo.py:34-36)")
+        self.act = N.ACT_BY_NAME[act]
+        self.sd = {k[len(prefix):]: v.detach().to(dev) for k, v in state_dict.items()
+                   if k.startswith(prefix) and not k.endswith("num_batches_tracked")}
+        if "stem.conv.conv.weight" not in self.sd:
+            raise KeyError(f"no CSPDarknet weights under prefix {prefix!r}")
+        self.base = self.sd["stem.conv.conv.weight"].shape[0]
+        if not backbone_supported(self.base):
+            raise NotImplementedError(f"CSPDarknet base width {self.base} is not a multiple of 32")
+        self.ops: List = []
+        self.flops = 0.0
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self.outs: Dict[str, torch.Tensor] = dict(outs or {})
+        self._build()
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name: str, stride: int, channels: int) -> torch.Tensor:
+        t = torch.empty((self.B, self.in_h // stride, self.in_w // stride, channels), dtype=torch.bfloat16, device=self.device)
+        self._bufs[name] = t
+        return t
+
+    def _folded(self, p: str):
+        sd = self.sd
+        return fold_bn(sd[p + ".conv.weight"], sd[p + ".bn.weight"], sd[p + ".bn.bias"], sd[p + ".bn.running_mean"],
+                       sd[p + ".bn.running_var"], BN_EPS)
+
+    def _conv(self, w, b, srcs, out, stride=1, **kw) -> ConvOp:
+        op = ConvOp(srcs, w, b, ksize=w.shape[-2], stride=stride, act=self.act, out=out, **kw)
+        self.ops.append(op)
+        self.flops += op.flops
+        return op
+
+    def _base_conv(self, p, srcs, out, stride=1, **kw):
+        w, b = self._folded(p)
+        return self._conv(w, b, srcs, out, stride, **kw)
+
+    def _csp(self, p: str, stride: int, src: View, out: View, shortcut: bool):
+        """CSPLayer.forward (darknet.py:91-112) with Bottleneck.forward (:59-63)."""
+        w1, b1 = self._folded(p + ".conv1")
+        w2, b2 = self._folded(p + ".conv2")
+        hid = w1.shape[0]
+        X = self._buf(p + ".X", stride, 2 * hid)
+        self._conv(torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), [src], View(X))
+        bb = self._buf(p + ".b", stride, hid)
+        j = 0
+        while f"{p}.m.{j}.conv1.conv.weight" in self.sd:
+            x1 = View(X, 0, hid)
+            self._base_conv(f"{p}.m.{j}.conv1", [x1], View(bb))
+            if shortcut:   # use_add: in_channels == out_channels always holds inside a CSPLayer (expansion 1.0)
+                self._base_conv(f"{p}.m.{j}.conv2", [View(bb)], x1, post_res=x1, post_shift=0)
+            else:
+                self._base_conv(f"{p}.m.{j}.conv2", [View(bb)], x1)
+            j += 1
+        self._base_conv(p + ".conv3", [View(X)], out)
+
+    def _out(self, name: str, stride: int, channels: int) -> torch.Tensor:
+        t = self.outs.get(name)
+        if t is None:
+            t = self._buf(name, stride, channels)
+            self.outs[name] = t
+        assert tuple(t.shape) == (self.B, self.in_h // stride, self.in_w // stride, channels) and t.dtype == torch.bfloat16, \
+            (name, tuple(t.shape))
+        return t
+
+    # ------------------------------------------------------------------ graph (CSPDarknet.forward, darknet.py:172-195)
+    def _build(self):
+        c = self.base
+        h2, w2 = self.in_h // 2, self.in_w // 2
+        w, b = self._folded("stem.conv")                       # [c, 12, 3, 3]
+        stem = self._buf("stem", 2, c)
+        if os.environ.get("GLSDET_STEM_UNFOLDED"):             # diagnostic: plain 3x3 conv over 16-channel pixels (K = 9 * 64)
+            s2d = self._buf("focus", 2, 16)
+            self.focus = FocusOp(s2d)
+            self._conv(torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 4)), b, [View(s2d)], View(stem))
+        else:
+            # kx taps folded into the channel view (K = 3 * 64): zero-bordered rows of 16-channel pixels, the conv reads
+            # 64 consecutive elements = (pixel x-1 | x | x+1 | ignored) per ky tap
+            flat = torch.zeros(self.B * h2 * (w2 + 2) * 16 + 64, dtype=torch.bfloat16, device=self.device)
+            self._bufs["focus"] = flat
+            fv = FoldedView(flat, self.B, h2, w2, 16)
+            self.focus = FocusOp(fv)
+            self._conv(fold_kx_weight(w, 16), b, [fv], View(stem), ksize_w=1)
+        self.ops[-1].flops = 2.0 * self.B * h2 * w2 * c * 12 * 9   # the reference's FLOPs (12 channels, 9 taps)
+        self.flops = self.ops[-1].flops
+        x = stem
+        for name, stride, cout in (("dark2", 4, 2 * c), ("dark3", 8, 4 * c), ("dark4", 16, 8 * c)):
+            t = self._buf(name + ".0", stride, cout)
+            self._base_conv(f"{name}.0", [View(x)], View(t), stride=2)
+            o = self._out(name, stride, cout)
+            self._csp(f"{name}.1", stride, View(t), View(o), shortcut=True)
+            x = o
+        t = self._buf("dark5.0", 32, 16 * c)
+        self._base_conv("dark5.0", [View(x)], View(t), stride=2)
+        hid = 8 * c
+        cat = self._buf("spp_cat", 32, 4 * hid)
+        self._base_conv("dark5.1.conv1", [View(t)], View(cat, 0, hid))
+        self.ops.append(SppPoolOp(cat, hid))
+        t2 = self._buf("spp_out", 32, 16 * c)
+        self._base_conv("dark5.1.conv2", [View(cat)], View(t2))
+        self._csp("dark5.2", 32, View(t2), View(self._out("dark5", 32, 16 * c)), shortcut=False)
+
+    # ------------------------------------------------------------------ execution
+    def run(self, image: torch.Tensor, stream=None) -> None:
+        self.focus.launch(image, stream)
+        for op in self.ops:
+            op.launch(stream)
+
+    def num_launches(self) -> int:
+        return 1 + len(self.ops)
+
+    def features_nchw(self, names: Sequence[str] = FEATURES, stream=None) -> Dict[str, torch.Tensor]:
+        """The dict CSPDarknet.forward returns (NCHW fp32)."""
+        res = {}
+        for n in names:
+            v = View(self.outs[n]) if n in self.outs else View(self._bufs[n])
+            b, h, w = v.bhw
+            t = torch.empty((b, v.c, h, w), dtype=torch.float32, device=self.device)
+            nhwc_to_nchw(v, t, stream)
+            res[n] = t
+        return res

@@ -1,0 +1,147 @@
+// CSPDarknet pieces that are not convolutions (yolox-drone/models/ffa/darknet.py):
+//   * Focus space-to-depth (darknet.py:15-21) fused with the NCHW fp32 -> NHWC bf16 layout change of the image,
+//   * the three stride-1 max pools of SPPBottleneck (darknet.py:28,33-36) as a cascade of separable 5-wide maxima.
+// Both are HBM / shared-memory bound byte movers; the convolutions of the backbone run on conv_gemm_kernel.
+#include <cuda_bf16.h>
+
+#include "../../include/glsdet_b200.h"
+#include "common.h"
+
+namespace glsdet {
+
+// ---------------------------------------------------------------------------------------------- Focus
+// dst[b, y, x, q*3 + c] = img[b, c, 2y + dy(q), 2x + dx(q)],  q = 0: top-left, 1: bottom-left, 2: top-right,
+// 3: bottom-right (the torch.cat order of darknet.py:16-20); channels 12..15 are zero so that a pixel is 32 bytes.
+// One thread per output pixel: six coalesced float2 loads (3 channels x 2 rows), two 16-byte stores.
+__global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst, int H, int W,
+                                                    int border, int64_t total) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int x = static_cast<int>(idx % Wo);
+  const int64_t t = idx / Wo;
+  const int y = static_cast<int>(t % Ho);
+  const int64_t b = t / Ho;
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const float* p = img + b * 3 * plane + static_cast<int64_t>(2 * y) * W + 2 * x;
+  float tl[3], bl[3], tr[3], br[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(p + c * plane));
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(p + c * plane + W));
+    tl[c] = r0.x; tr[c] = r0.y; bl[c] = r1.x; br[c] = r1.y;
+  }
+  __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    o[c] = __float2bfloat16_rn(tl[c]);
+    o[3 + c] = __float2bfloat16_rn(bl[c]);
+    o[6 + c] = __float2bfloat16_rn(tr[c]);
+    o[9 + c] = __float2bfloat16_rn(br[c]);
+  }
+#pragma unroll
+  for (int c = 12; c < 16; ++c) o[c] = __float2bfloat16_rn(0.f);
+  // border = 1: rows of Wo + 2 pixels, pixel x lands at x + 1 (zero border pixels left and right)
+  uint4* out = reinterpret_cast<uint4*>(dst + ((b * Ho + y) * (Wo + 2 * border) + x + border) * 16);
+  out[0] = reinterpret_cast<const uint4*>(o)[0];
+  out[1] = reinterpret_cast<const uint4*>(o)[1];
+}
+
+// ---------------------------------------------------------------------------------------------- SPP max pools
+__device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
+  uint4 r;
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+
+// One CTA = one image x 8 channels, the whole h x w map in shared memory (two ping-pong planes of 16-byte vectors).
+// MaxPool2d(k, 1, k/2) pads with -inf, i.e. the maximum runs over the in-bounds part of the window, and
+// pool9 = pool5(pool5), pool13 = pool5(pool9) exactly (maxima of nested windows), so three rounds of a separable
+// 5-wide maximum (row pass, column pass) produce the three outputs.
+__global__ void __launch_bounds__(1024) spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int h, int w, int ld, int coff_src,
+                                                        int coff5, int coff9, int coff13, int groups) {
+  extern __shared__ uint4 smem_pool[];
+  uint4* a = smem_pool;
+  uint4* t = smem_pool + h * w;
+  const int g = blockIdx.x % groups;
+  const int64_t b = blockIdx.x / groups;
+  __nv_bfloat16* base = buf + b * h * w * ld + g * 8;
+  const int n = h * w;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    a[i] = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(i) * ld + coff_src);
+  __syncthreads();
+  for (int round = 0; round < 3; ++round) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // row pass: a -> t
+      const int y = i / w, x = i - y * w;
+      uint4 m = a[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int xx = x + d;
+        if (d != 0 && xx >= 0 && xx < w) m = max8(m, a[y * w + xx]);
+      }
+      t[i] = m;
+    }
+    __syncthreads();
+    const int coff = round == 0 ? coff5 : round == 1 ? coff9 : coff13;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // column pass: t -> a (+ global)
+      const int y = i / w, x = i - y * w;
+      uint4 m = t[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int yy = y + d;
+        if (d != 0 && yy >= 0 && yy < h) m = max8(m, t[yy * w + x]);
+      }
+      *reinterpret_cast<uint4*>(base + static_cast<int64_t>(i) * ld + coff) = m;
+      // every thread rewrites only its own elements of `a`, and nobody reads `a` during this pass
+      a[i] = m;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace glsdet
+
+extern "C" int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t batch, int32_t height,
+                                                  int32_t width, int32_t dst_border, void* stream) {
+  GLSDET_REQUIRE(image && dst && batch > 0 && height > 0 && width > 0 && (dst_border == 0 || dst_border == 1),
+                 "focus: bad arguments");
+  GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "focus: height and width must be even (got %d x %d)", height, width);
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(image) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "focus: image must be 8-byte aligned and dst 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(batch) * (height / 2) * (width / 2);
+  glsdet::focus_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, reinterpret_cast<__nv_bfloat16*>(dst), height, width, dst_border, total);
+  return glsdet::count_launch("focus_kernel");
+}
+
+extern "C" int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                                  int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
+  GLSDET_REQUIRE(buf && batch > 0 && height > 0 && width > 0 && channels > 0, "spp_maxpool: bad arguments");
+  GLSDET_REQUIRE((channels % 8) == 0 && (ld % 8) == 0 && (src_coff % 8) == 0 && (coff5 % 8) == 0 && (coff9 % 8) == 0 &&
+                     (coff13 % 8) == 0, "spp_maxpool: channels, pitch and offsets must be multiples of 8");
+  const int32_t offs[4] = {src_coff, coff5, coff9, coff13};
+  for (int i = 0; i < 4; ++i) {
+    GLSDET_REQUIRE(offs[i] >= 0 && offs[i] + channels <= ld, "spp_maxpool: window %d exceeds the pitch", i);
+    for (int j = 0; j < i; ++j)
+      GLSDET_REQUIRE(offs[i] >= offs[j] + channels || offs[j] >= offs[i] + channels, "spp_maxpool: windows %d and %d overlap", j, i);
+  }
+  const size_t smem = static_cast<size_t>(height) * width * 2 * sizeof(uint4);
+  GLSDET_REQUIRE(smem <= 200 * 1024, "spp_maxpool: a %d x %d map does not fit shared memory (max 6400 pixels)", height, width);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  GLSDET_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !attr_set[dev]) {
+    GLSDET_CHECK_CUDA(cudaFuncSetAttribute(glsdet::spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[dev] = true;
+  }
+  const int groups = channels / 8;
+  const int pixels = height * width;
+  const int threads = pixels >= 1024 ? 1024 : ((pixels + 31) / 32) * 32;
+  glsdet::spp_pool_kernel<<<static_cast<unsigned>(batch) * groups, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(buf), height, width, ld, src_coff, coff5, coff9, coff13, groups);
+  return glsdet::count_launch("spp_pool_kernel");
+}

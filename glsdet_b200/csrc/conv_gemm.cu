@@ -54,7 +54,8 @@ struct alignas(64) ConvKParams {
   int32_t m_tiles, total_pairs;   // 2-CTA mode: a CTA pair takes M tiles (2i, 2i+1) of one N block
   int32_t block_n, N;
   int32_t taps, stride;
-  int32_t ksz;               // kernel size (1, 3, 5, 7); taps = ksz * ksz
+  int32_t ksz;               // kernel height (1, 3, 5, 7)
+  int32_t kw;                // kernel width: ksz, or 1 when the kx taps are folded into the channel view; taps = ksz * kw
   int32_t chunks0, chunks1;
   int32_t sa, sb;            // A / B ring depths
   int32_t nsub;              // MMA sub-steps per A step: 3 (ky taps of a 3x3 stride-1 conv) or 1
@@ -684,19 +685,20 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           if (nch == 0) continue;
           const int kbase = src ? p.taps * p.chunks0 : 0;  // weight K order: (source, tap, chunk)
           const int pad = p.ksz >> 1;
+          const int padx = p.kw >> 1;
           if (p.nsub > 1) {   // one A box of (rows + ksz - 1) rows per (kx, chunk) serves all ky taps
-            for (int kx = 0; kx < p.ksz; ++kx) {
+            for (int kx = 0; kx < p.kw; ++kx) {
               for (int ch = 0; ch < nch; ++ch) {
-                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - pad, 0, t.y0 - pad, ab);
+                load_a(&p.tmA[src], ch * kChunkK, t.x0 + kx - padx, 0, t.y0 - pad, ab);
                 if (p.bres) continue;
                 if (p.bgroup == 3) load_b3(src, kbase + kx * nch + ch, t.n0);         // ky = 0,1,2 in one box
-                else for (int ky = 0; ky < p.ksz; ++ky) load_b(kbase + (ky * p.ksz + kx) * nch + ch, t.n0);
+                else for (int ky = 0; ky < p.ksz; ++ky) load_b(kbase + (ky * p.kw + kx) * nch + ch, t.n0);
               }
             }
           } else {
             for (int tap = 0; tap < p.taps; ++tap) {
-              const int dy = tap / p.ksz - pad;
-              const int dx = tap % p.ksz - pad;
+              const int dy = tap / p.kw - pad;
+              const int dx = tap % p.kw - padx;
               for (int ch = 0; ch < nch; ++ch) {
                 load_a(&p.tmA[src], ch * kChunkK, t.x0 + dx, ac2, t.y0 + dy, ab);
                 load_b(kbase + tap * nch + ch, t.n0);
@@ -745,7 +747,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           uint32_t b_addr;
           bool last_of_b = false;
           if (p.bres) {
-            const int kchunk = (p.nsub > 1) ? (src ? p.taps * p.chunks0 : 0) + (sub * p.ksz + o) * nch + ch : a;
+            const int kchunk = (p.nsub > 1) ? (src ? p.taps * p.chunks0 : 0) + (sub * p.kw + o) * nch + ch : a;
             b_addr = smem_u32(smem_b + kchunk * b_tap_bytes);
           } else {
             if (bsub == 0) mbar_wait(&b_full[sb], phb);
@@ -781,7 +783,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
         if (++sa == p.sa) { sa = 0; pha ^= 1u; }
         if (++ch == nch) {
           ch = 0;
-          if (++o == p.ksz) { o = 0; ++src; }
+          if (++o == p.kw) { o = 0; ++src; }
         }
       }
     }
@@ -1147,7 +1149,7 @@ ConvKernelFn conv_kernel_for(int ec) {
 namespace {
 
 struct ConvGeom {
-  int taps, chunks0, chunks1, n_blocks, block_n, n_pad, k_pad, Ho, Wo;
+  int taps, kw, chunks0, chunks1, n_blocks, block_n, n_pad, k_pad, Ho, Wo;
 };
 
 int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
@@ -1157,7 +1159,13 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   GLSDET_REQUIRE(d->ksize <= 3 || d->stride == 1, "conv: 5x5 / 7x7 convs are stride 1");
   GLSDET_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   GLSDET_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, "conv: bad input size");
-  GLSDET_REQUIRE(d->src0_c > 0 && d->src0_ld >= d->src0_c, "conv: bad src0 channels/pitch");
+  GLSDET_REQUIRE(d->src0_c > 0 && (d->src0_ld >= d->src0_c || d->src0_row_pitch > 0), "conv: bad src0 channels/pitch");
+  GLSDET_REQUIRE(d->ksize_w == 0 || d->ksize_w == d->ksize || (d->ksize_w == 1 && d->stride == 1 && d->src1 == nullptr &&
+                                                                 d->patch_mode == 0 && d->src_shared == 0),
+                 "conv: ksize_w must be 0, ksize, or 1 (kx taps folded into the channel view: stride 1, single source)");
+  GLSDET_REQUIRE(d->src0_row_pitch >= 0 && d->src0_img_pitch >= 0 && (d->src0_row_pitch % 8) == 0 && (d->src0_img_pitch % 8) == 0 &&
+                     (d->src0_row_pitch == 0 || (d->stride == 1 && d->patch_mode == 0)),
+                 "conv: explicit src0 row / image pitches must be multiples of 8 elements (stride-1 convs only)");
   GLSDET_REQUIRE((d->src0_ld % 8) == 0, "conv: src0 pitch must be a multiple of 8 elements (TMA 16-byte strides)");
   GLSDET_REQUIRE(d->out_channels > 0, "conv: out_channels must be positive");
   if (d->stride == 2) {
@@ -1178,7 +1186,8 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
     GLSDET_REQUIRE((d->weight_batch_stride % 8) == 0 && (d->weight_ld % 8) == 0,
                    "conv: per-image weight strides must be multiples of 8 elements");
   }
-  g->taps = d->ksize * d->ksize;
+  g->kw = d->ksize_w > 0 ? d->ksize_w : d->ksize;
+  g->taps = d->ksize * g->kw;
   g->chunks0 = (d->src0_c + kChunkK - 1) / kChunkK;
   g->chunks1 = d->src1 ? (d->src1_c + kChunkK - 1) / kChunkK : 0;
   g->n_blocks = (d->out_channels + 255) / 256;
@@ -1194,7 +1203,7 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
 constexpr int kPatchView = 3;   // encode_act_map `stride` value selecting the 2x2 patch view
 
 int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B, int H, int W, int stride,
-                   int tile_w, int box_rows) {
+                   int tile_w, int box_rows, int64_t row_pitch = 0, int64_t img_pitch = 0) {
   EncodeTiledFn enc = get_encode_tiled();
   GLSDET_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
   GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "conv: source pointer must be 16-byte aligned");
@@ -1202,11 +1211,15 @@ int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B,
   cuuint64_t strides[4];
   const cuuint64_t e = 2;  // bf16
   if (stride == 1) {
+    // explicit pitches: rows / images of a padded buffer; with ld < c_view the pixels of the view overlap (the kx taps
+    // of a few-channel conv folded into the channel dimension: "channel" k of pixel x = element k of the row starting at x)
+    const cuuint64_t rp = row_pitch > 0 ? static_cast<cuuint64_t>(row_pitch) : static_cast<cuuint64_t>(W) * ld;
+    const cuuint64_t ip = img_pitch > 0 ? static_cast<cuuint64_t>(img_pitch) : static_cast<cuuint64_t>(H) * rp;
     dims[0] = c_view; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
     strides[0] = static_cast<cuuint64_t>(ld) * e;
-    strides[1] = static_cast<cuuint64_t>(W) * ld * e;
-    strides[2] = static_cast<cuuint64_t>(W) * ld * e;
-    strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
+    strides[1] = rp * e;
+    strides[2] = rp * e;
+    strides[3] = ip * e;
   } else if (stride == kPatchView) {
     // 2x2 patch views of a [B/4, 2H, 2W, ld] tensor: coordinate 2 = px, coordinate 4 = image * 2 + py
     dims[0] = c_view; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B / 2;
@@ -1281,10 +1294,10 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // pixels.  Measured (profiles/README.md): 3x3 N=256 at 256^2 491 -> 385 us (1.6 PF/s), N=128 299 -> 207 us.  Default
   // for 3x3 stride-1 convs; the small-K 1x1 convs stay on the 1-CTA kernel (resident weights, TMA-store epilogue).
   // GLSDET_CONV_2CTA=0 disables it, =1 also uses it for 1x1 convs.
-  bool two_cta = d->stride == 1 && d->ksize == 3 && (g.block_n % 32) == 0;
+  bool two_cta = d->stride == 1 && d->ksize == 3 && g.kw == 3 && (g.block_n % 32) == 0;
   if (const char* e = getenv("GLSDET_CONV_2CTA")) {
     if (e[0] == '0') two_cta = false;
-    if (e[0] == '1') two_cta = d->stride == 1 && d->ksize <= 3 && (g.block_n % 32) == 0;
+    if (e[0] == '1') two_cta = d->stride == 1 && d->ksize <= 3 && g.kw == d->ksize && (g.block_n % 32) == 0;
   }
   if (d->weight_batch_stride != 0 || d->patch_mode != 0) two_cta = false;
   op->two_cta = two_cta ? 1 : 0;
@@ -1342,10 +1355,11 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   const bool vreuse = (d->ksize >= 3 && d->stride == 1 && (super_h + d->ksize - 1) <= 256 &&
                        (getenv("GLSDET_CONV_NO_VREUSE") == nullptr || d->ksize > 3));
   k.ksz = d->ksize;
+  k.kw = g.kw;
   k.nsub = vreuse ? d->ksize : 1;
   const int box_rows = vreuse ? super_h + d->ksize - 1 : super_h;
   k.a_bytes = box_rows * best_w * kRowBytes;
-  k.a_steps = (vreuse ? d->ksize : g.taps) * (g.chunks0 + g.chunks1);
+  k.a_steps = (vreuse ? g.kw : g.taps) * (g.chunks0 + g.chunks1);
   k.m_tiles = k.tiles_x * k.tiles_y * k.B;
   k.total_pairs = ((k.m_tiles + 1) / 2) * k.n_blocks;
 
@@ -1487,7 +1501,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   int rc = 0;
   if (d->stride == 1) {
     rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width,
-                        patch ? kPatchView : 1, best_w, box_rows);
+                        patch ? kPatchView : 1, best_w, box_rows, d->src0_row_pitch, d->src0_img_pitch);
     if (!rc && d->src1)
       rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
     else if (!rc) k.tmA[1] = k.tmA[0];
@@ -1529,7 +1543,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
       if (nch == 0) continue;
       // (k, n, ky): ky advances three taps = 3 * nch chunks of 64 columns
       cuuint64_t dims3[3] = {static_cast<cuuint64_t>(g.k_pad), static_cast<cuuint64_t>(g.n_pad), 3};
-      cuuint64_t strides3[2] = {static_cast<cuuint64_t>(g.k_pad) * 2, static_cast<cuuint64_t>(3) * nch * kChunkK * 2};
+      cuuint64_t strides3[2] = {static_cast<cuuint64_t>(g.k_pad) * 2, static_cast<cuuint64_t>(g.kw) * nch * kChunkK * 2};
       cuuint32_t box3[3] = {static_cast<cuuint32_t>(kChunkK), b_rows, 3};
       cuuint32_t estr3[3] = {1, 1, 1};
       r = enc(&k.tmB3[src], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->weight), dims3, strides3, box3,

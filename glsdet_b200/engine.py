@@ -121,6 +121,7 @@ class FFAPathPlan:
         self.logits: List[torch.Tensor] = []
         self.pred: Optional[torch.Tensor] = None
         self.flops = 0.0
+        self.backbone = None      # BackbonePlan writing straight into self.inputs (attach_backbone)
         self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -574,6 +575,27 @@ class FFAPathPlan:
         # the second tower convs exist twice (raw + decoded variants); count them once, plus the prediction convs
         self.flops -= sum(op.flops for op in self.pred_dec_ops)
         self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
+
+    def attach_backbone(self, state_dict: Dict[str, torch.Tensor], prefix: str, act: str = "silu"):
+        """Chain the CSPDarknet plan (glsdet_b200/backbone.py) in front of the neck: its dark2..dark5 outputs ARE this
+        plan's NHWC bf16 input buffers, so an image batch goes backbone -> neck -> head without leaving the native
+        layout.  Not available for plans with per-input pre-loads (P1's Gram operands are
+        built from the NCHW fp32 features) or in the fp32 accuracy mode."""
+        from .backbone import FEATURES, BackbonePlan
+
+        if self.fp32 or self.pre_loads:
+            raise NotImplementedError("attach_backbone: bf16 plans without pre-loads only")
+        names = FEATURES[-len(self.inputs):]
+        self.backbone = BackbonePlan(state_dict, self.B, (self.in_h, self.in_w), device=self.device, act=act, prefix=prefix,
+                                     outs=dict(zip(names, self.inputs)))
+        return self.backbone
+
+    def forward_image(self, image: torch.Tensor, decoded: bool, stream=None):
+        """Image batch [B, 3, H, W] fp32 -> raw logits (decoded=False) or decoded rows [B, A, 5+nc] (decoded=True)."""
+        self.backbone.run(image, stream)
+        self.run_neck(stream)
+        self.run_head(decoded, stream)
+        return self.pred if decoded else self.logits
 
     # ------------------------------------------------------------------ execution
     def load_features(self, feats: Sequence[torch.Tensor], stream=None) -> None:

@@ -65,6 +65,54 @@ class View:
         return tuple(self.t.shape[:3])
 
 
+class FoldedView:
+    """Source view of a few-channel 3x3 conv with the kx taps folded into the channel dimension (glsdet_conv_desc.ksize_w
+    = 1): `t` is a zero-bordered NHWC bf16 buffer [B, H, W + 2, c_pix] (+ slack behind the last row); the conv sees, at
+    output pixel x, the 64 consecutive elements starting at padded pixel x = (pixel x-1 | pixel x | pixel x+1 | ...)."""
+
+    __slots__ = ("t", "c", "c_pix", "_bhw")
+
+    def __init__(self, flat: torch.Tensor, batch: int, height: int, width: int, c_pix: int):
+        assert flat.dtype == torch.bfloat16 and flat.dim() == 1 and 3 * c_pix <= 64 and c_pix % 8 == 0
+        assert flat.numel() >= batch * height * (width + 2) * c_pix + 64, "needs 64 elements of slack behind the last row"
+        self.t, self.c, self.c_pix, self._bhw = flat, 64, c_pix, (batch, height, width)
+
+    @property
+    def ld(self) -> int:
+        return self.c_pix
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+    @property
+    def bhw(self):
+        return self._bhw
+
+    @property
+    def row_pitch(self) -> int:
+        return (self._bhw[2] + 2) * self.c_pix
+
+    @property
+    def img_pitch(self) -> int:
+        return self._bhw[1] * self.row_pitch
+
+    def interior(self) -> torch.Tensor:
+        """[B, H, W, c_pix] view of the real pixels (tests)."""
+        b, h, w = self._bhw
+        return self.t[:b * h * (w + 2) * self.c_pix].view(b, h, w + 2, self.c_pix)[:, :, 1:w + 1]
+
+
+def fold_kx_weight(weight: torch.Tensor, c_pix: int) -> torch.Tensor:
+    """[N, C, 3, 3] -> [N, 64, 3, 1] for a FoldedView source: channel kx * c_pix + c of tap ky = weight[:, c, ky, kx]."""
+    n, c, kh, kw = weight.shape
+    assert kw == 3 and c <= c_pix and 3 * c_pix <= 64
+    out = torch.zeros((n, 64, kh, 1), dtype=weight.dtype, device=weight.device)
+    for kx in range(3):
+        out[:, kx * c_pix:kx * c_pix + c, :, 0] = weight[:, :, :, kx]
+    return out
+
+
 class ConvOp:
     """conv(+cat)(+bias)(+residual) -> act (+residual) -> store; see glsdet_conv_desc in include/glsdet_b200.h."""
 
@@ -74,7 +122,8 @@ class ConvOp:
                  post_res: Optional[View] = None, post_shift: int = 0, dec=(0.0, 0.0, 0.0),
                  pred_weight: Optional[torch.Tensor] = None, pred_bias: Optional[torch.Tensor] = None,
                  pred_act: int = N.ACT_NONE, weight_raw: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
-                 src_shared: int = 0, src_shared_div: int = 0, patch_mode: bool = False, batch: Optional[int] = None):
+                 src_shared: int = 0, src_shared_div: int = 0, patch_mode: bool = False, batch: Optional[int] = None,
+                 ksize_w: int = 0):
         """`weight_raw`: a bf16 device matrix [N rows, pitch] (shared) or [batch, N rows, pitch] (one per image) used
         as is (the batched products of the non-local block); `src_shared` = k > 0: srcs[0] holds k static matrices and image b reads matrix b mod k;
         `patch_mode`: srcs[0] / post_res / out are [B, H, W, .] tensors processed as their 4*B 2x2 patches."""
@@ -96,6 +145,10 @@ class ConvOp:
             d.src1, d.src1_c, d.src1_ld = srcs[1].ptr, srcs[1].c, srcs[1].ld
         d.batch, d.height, d.width = b, h, w
         d.ksize, d.stride = ksize, stride
+        d.ksize_w = ksize_w
+        if isinstance(srcs[0], FoldedView):
+            assert ksize_w == 1 and len(srcs) == 1 and stride == 1
+            d.src0_row_pitch, d.src0_img_pitch = srcs[0].row_pitch, srcs[0].img_pitch
         d.out_channels = n_out
         d.act = act
         n_pad, k_pad, block_n = C.c_int32(), C.c_int32(), C.c_int32()
@@ -157,7 +210,7 @@ class ConvOp:
         self.handle = C.c_void_p()
         N.check(lib.glsdet_conv_create(C.byref(d), C.byref(self.handle)), "glsdet_conv_create")
         self._lib = lib
-        self.flops = 2.0 * b * ho * wo * n_out * sum(s.c for s in srcs) * ksize * ksize
+        self.flops = 2.0 * b * ho * wo * n_out * sum(s.c for s in srcs) * ksize * (ksize_w or ksize)
 
     def launch(self, stream=None):
         N.check(self._lib.glsdet_conv_launch(self.handle, N.stream_ptr(stream)), "glsdet_conv_launch")
@@ -407,3 +460,42 @@ class NhwcTransposeOp:
         N.check(self._lib.glsdet_nhwc_transpose(s.t.data_ptr(), self.dst.data_ptr(), self.b, self.t, s.c, s.ld, s.coff,
                                                 self.dst.shape[1], self.dst.shape[2], N.stream_ptr(stream)),
                 "glsdet_nhwc_transpose")
+
+
+class FocusOp:
+    """Focus space-to-depth of the image batch (models/ffa/darknet.py:15-21): NCHW fp32 [B, 3, H, W] -> NHWC bf16
+    [B, H/2, W/2, 16] (12 channels in the reference's cat order + 4 zero channels)."""
+
+    def __init__(self, dst):
+        """`dst`: a contiguous [B, H/2, W/2, 16] tensor, or a FoldedView (zero-bordered rows, written at pixel x + 1)."""
+        if isinstance(dst, FoldedView):
+            assert dst.c_pix == 16
+            self.shape, self.border, self.dst = dst.bhw, 1, dst.t
+        else:
+            assert dst.dtype == torch.bfloat16 and dst.dim() == 4 and dst.shape[3] == 16 and dst.is_contiguous()
+            self.shape, self.border, self.dst = tuple(dst.shape[:3]), 0, dst
+        self._lib = N.load()
+
+    def launch(self, image: torch.Tensor, stream=None):
+        b, h2, w2 = self.shape
+        assert image.dtype == torch.float32 and image.is_contiguous() and image.is_cuda
+        assert tuple(image.shape) == (b, 3, 2 * h2, 2 * w2), (tuple(image.shape), self.shape)
+        N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_bf16(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
+                                                             self.border, N.stream_ptr(stream)),
+                "glsdet_focus_nchw_f32_to_nhwc_bf16")
+
+
+class SppPoolOp:
+    """MaxPool2d(5 / 9 / 13, 1, k // 2) of channel window 0 of an NHWC bf16 concat buffer [B, h, w, 4C] into windows
+    1..3 (SPPBottleneck.forward, models/ffa/darknet.py:33-36)."""
+
+    def __init__(self, cat: torch.Tensor, channels: int):
+        assert cat.dtype == torch.bfloat16 and cat.dim() == 4 and cat.is_contiguous() and cat.shape[3] == 4 * channels
+        self.cat, self.c = cat, channels
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        b, h, w, ld = self.cat.shape
+        c = self.c
+        N.check(self._lib.glsdet_spp_maxpool(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c,
+                                             N.stream_ptr(stream)), "glsdet_spp_maxpool")

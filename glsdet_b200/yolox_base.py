@@ -126,7 +126,10 @@ class YoloBody(_PlanOwner):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
-        return self.forward_features(self.backbone.features(x))
+        plan = self._fused_plan(x)
+        if plan is None:
+            return self.forward_features(self.backbone.features(x))
+        return [t.clone() for t in plan.forward_image(x.float().contiguous(), False)]
 
     @torch.no_grad()
     def decode_features(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .backbone import BackbonePlan, backbone_supported
 from .engine import FFAPathPlan
 from .utils_bbox import DeviceNMS
 
@@ -108,41 +109,6 @@ class SPPBottleneck(nn.Module):
         return self.conv2(torch.cat([x] + [m(x) for m in self.m], dim=1))
 
 
-class CSPDarknet(nn.Module):
-    """Backbone (models/ffa/darknet.py:115-195).  Upstream of the native path: plain PyTorch."""
-
-    def __init__(self, dep_mul, wid_mul, out_features=("dark2", "dark3", "dark4", "dark5"), depthwise=False,
-                 act="silu"):
-        super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported")
-        self.out_features = out_features
-        c = int(wid_mul * 64)
-        d = max(round(dep_mul * 3), 1)
-        self.stem = Focus(3, c, ksize=3, act=act)
-
-        def stage(cin, cout, n, shortcut=True, spp=False):
-            layers = [BaseConv(cin, cout, 3, 2, act=act, upstream=True)]
-            if spp:
-                layers.append(SPPBottleneck(cout, cout, activation=act))
-            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act, upstream=True))
-            return nn.Sequential(*layers)
-
-        self.dark2 = stage(c, c * 2, d)
-        self.dark3 = stage(c * 2, c * 4, d * 3)
-        self.dark4 = stage(c * 4, c * 8, d * 3)
-        self.dark5 = stage(c * 8, c * 16, d, shortcut=False, spp=True)
-
-    def forward(self, x):
-        outs = {}
-        x = self.stem(x)
-        outs["stem"] = x
-        for name in ("dark2", "dark3", "dark4", "dark5"):
-            x = getattr(self, name)(x)
-            outs[name] = x
-        return {k: v for k, v in outs.items() if k in self.out_features}
-
-
 class SE(nn.Module):
     """models/ffa/ffa.py:5-20 parameter layout (fc.0.weight, fc.2.weight)."""
 
@@ -223,6 +189,88 @@ class _PlanOwner(nn.Module):
                                variant=self._variant, decode=self._decode, precision=self.precision)
             self._plans[key] = plan
         return plan
+
+    def _fused_plan(self, x: torch.Tensor) -> Optional[FFAPathPlan]:
+        """Plan with the native CSPDarknet chained in front (image -> backbone -> neck -> head in NHWC bf16), or None
+        when the backbone cannot run natively for this input (CPU tensor, fp32 mode, phi='tiny') or the topology needs
+        the NCHW fp32 features (P1 pre-loads)."""
+        bb = self.backbone.backbone
+        if not (isinstance(bb, CSPDarknet) and bb.native_ok(x)):
+            return None
+        plan = self._plan(x.shape[0], x.shape[2:], x.device)
+        if plan.fp32 or plan.pre_loads:
+            return None
+        if plan.backbone is None:
+            plan.attach_backbone(bb.state_dict(), "", bb.act_name)
+        return plan
+
+
+class CSPDarknet(_PlanOwner):
+    """Backbone (models/ffa/darknet.py:115-195): forward(image batch) -> {"dark2": .., .. "dark5": ..} NCHW fp32.
+
+    On a CUDA device (bf16 precision, base width a multiple of 32: phi = s, m, l, x) the forward runs as the native
+    BackbonePlan (glsdet_b200/backbone.py: Focus kernel, tcgen05 convs, SPP pooling kernel).  The PyTorch layers below
+    hold the parameters; their own forward is what runs for CPU tensors (the bench's CPU baseline builds its inputs
+    with it), in the fp32 accuracy mode (which keeps the upstream part in PyTorch fp32) and for phi = tiny."""
+
+    def __init__(self, dep_mul, wid_mul, out_features=("dark2", "dark3", "dark4", "dark5"), depthwise=False,
+                 act="silu"):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError("depthwise (phi='nano') is not supported")
+        self.out_features = out_features
+        self.act_name = act
+        c = int(wid_mul * 64)
+        d = max(round(dep_mul * 3), 1)
+        self.base_channels = c
+        self.stem = Focus(3, c, ksize=3, act=act)
+
+        def stage(cin, cout, n, shortcut=True, spp=False):
+            layers = [BaseConv(cin, cout, 3, 2, act=act, upstream=True)]
+            if spp:
+                layers.append(SPPBottleneck(cout, cout, activation=act))
+            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act, upstream=True))
+            return nn.Sequential(*layers)
+
+        self.dark2 = stage(c, c * 2, d)
+        self.dark3 = stage(c * 2, c * 4, d * 3)
+        self.dark4 = stage(c * 4, c * 8, d * 3)
+        self.dark5 = stage(c * 8, c * 16, d, shortcut=False, spp=True)
+        self._bb_plans: Dict[tuple, BackbonePlan] = {}
+        super().train(False)
+
+    def invalidate_plans(self):
+        super().invalidate_plans()
+        if hasattr(self, "_bb_plans"):
+            self._bb_plans.clear()
+
+    def native_ok(self, x: torch.Tensor) -> bool:
+        return bool(x.is_cuda and self.precision == "bf16" and backbone_supported(self.base_channels)
+                    and x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0)
+
+    def native_plan(self, batch: int, input_hw: Sequence[int], device, outs=None, key_extra=None) -> BackbonePlan:
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), key_extra)
+        plan = self._bb_plans.get(key)
+        if plan is None:
+            if len(self._bb_plans) >= 4:
+                self._bb_plans.clear()
+            plan = BackbonePlan(self.state_dict(), batch, input_hw, device=device, act=self.act_name, prefix="", outs=outs)
+            self._bb_plans[key] = plan
+        return plan
+
+    @torch.no_grad()
+    def forward(self, x):
+        if self.native_ok(x):
+            plan = self.native_plan(x.shape[0], x.shape[2:], x.device)
+            plan.run(x.float().contiguous())
+            return plan.features_nchw(self.out_features)
+        outs = {}
+        x = self.stem(x)
+        outs["stem"] = x
+        for name in ("dark2", "dark3", "dark4", "dark5"):
+            x = getattr(self, name)(x)
+            outs[name] = x
+        return {k: v for k, v in outs.items() if k in self.out_features}
 
 
 class YOLOXHead(_PlanOwner):
@@ -343,7 +391,10 @@ class YoloBody(_PlanOwner):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
-        return self.forward_features(self.backbone.features(x))
+        plan = self._fused_plan(x)
+        if plan is None:
+            return self.forward_features(self.backbone.features(x))
+        return [t.clone() for t in plan.forward_image(x.float().contiguous(), False)]
 
     @torch.no_grad()
     def decode_features(self, feats: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -368,5 +419,11 @@ class YoloBody(_PlanOwner):
         return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy)
 
     @torch.no_grad()
-    def detect(self, x: torch.Tensor, **kw):
-        return self.detect_features(self.backbone.features(x), **kw)
+    def detect(self, x: torch.Tensor, conf_thres: float = 0.5, nms_thres: float = 0.4, strategy: str = "auto_cuda",
+               max_det: Optional[int] = None):
+        """Image batch -> detections: backbone -> neck -> head -> decode -> filter -> NMS, all native."""
+        plan = self._fused_plan(x)
+        if plan is None:
+            return self.detect_features(self.backbone.features(x), conf_thres, nms_thres, strategy, max_det)
+        pred = plan.forward_image(x.float().contiguous(), True)
+        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy)

@@ -118,6 +118,18 @@ typedef struct glsdet_conv_desc {
   int32_t patch_mode;          /* 1 (1x1 convs): src0, post_res and out are the 2x2 patch views of
                                   [batch/4, 2*height, 2*width, ld] tensors; image b' = (b*2 + py)*2 + px is patch
                                   (py, px) of image b (the split of Non_local_family.py:230-233) */
+  /*
+   * Few-channel 3x3 convs (the Focus stem of CSPDarknet, yolox-drone/models/ffa/darknet.py:12-21: 12 input channels).
+   * ksize_w = 1 folds the kx taps into the channel dimension: src0 is a zero-bordered buffer whose pixels are
+   * src0_ld elements apart, the conv reads src0_c (<= 64, > src0_ld) consecutive elements starting at the pixel LEFT of
+   * the output position - i.e. "channel" k = kx * src0_ld + c of the (kx, c) pair - and only runs the ky taps
+   * (K = ksize * 64 instead of ksize^2 * 64).  src0 then points at padded pixel 0 of row 0 (the left border pixel),
+   * src0_row_pitch / src0_img_pitch give the padded row / image pitches in elements, and the weight matrix is packed
+   * as a ksize x 1 kernel over src0_c channels.
+   */
+  int32_t ksize_w;             /* 0 = ksize (square kernel); 1 = kx taps folded into the channel view (stride 1) */
+  int64_t src0_row_pitch;      /* elements between rows of src0; 0 = width * src0_ld */
+  int64_t src0_img_pitch;      /* elements between images of src0; 0 = height * row pitch */
 } glsdet_conv_desc;
 
 /* library / device */
@@ -209,6 +221,25 @@ int glsdet_nhwc_transpose(const void* src, void* dst, int32_t batch, int32_t pix
  */
 int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int32_t height, int32_t width, int32_t channels,
                       int32_t src_ld, int32_t src_coff, int32_t dst_ld, int32_t dst_coff, void* stream);
+
+/*
+ * CSPDarknet backbone pieces that are not convolutions (the backbone's convolutions run on
+ * glsdet_conv_*):
+ * glsdet_focus_nchw_f32_to_nhwc_bf16: Focus.forward's space-to-depth (yolox-drone/models/ffa/darknet.py:15-21) fused with
+ *   the layout change of the image: image [B, 3, H, W] fp32 NCHW -> dst [B, H/2, W/2, 16] bf16 NHWC with channel
+ *   q*3 + c = image[b, c, 2y + dy, 2x + dx], q = top-left, bottom-left, top-right, bottom-right (the reference's cat order);
+ *   channels 12..15 are written as zeros (32-byte pixels for the TMA loads of the stem conv).  dst_border = 1: dst rows
+ *   hold W/2 + 2 pixels and the kernel writes pixels 1..W/2 (the border pixels stay as the caller zeroed them: the
+ *   horizontal padding of the kx-folded stem conv, glsdet_conv_desc.ksize_w).
+ * glsdet_spp_maxpool: the MaxPool2d(5 / 9 / 13, stride 1, padding k/2) branches of SPPBottleneck.forward
+ *   (darknet.py:28,33-36) on an NHWC bf16 buffer [B, H, W, ld]: reads the channel window at src_coff and writes the three
+ *   pooled maps into the windows at coff5 / coff9 / coff13 of the same buffer (the concat the following 1x1 conv reads).
+ *   H * W <= 6400 (the map of one image x 8 channels is processed in shared memory).
+ */
+int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                                       int32_t dst_border, void* stream);
+int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                       int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream);
 
 /*
  * MP-Det head pieces (yolox-ufp/mmdet/models/dense_heads/mp_head.py, gfl_head.py; BASELINE configs[2]).

@@ -340,8 +340,8 @@ def p2_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = Fals
 
 # ------------------------------------------------------------------------------------------ backbone (upstream)
 def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
-    """models/ffa/darknet.py:10-37,115-195.  Upstream of the measured path; restated only so that synthetic
-    feature maps with the right statistics can be produced where /root/reference is absent."""
+    """models/ffa/darknet.py:10-37,115-195 (Focus :15-21, SPPBottleneck :33-37, CSPDarknet.forward :172-195).
+    SURVEY.md section 8f row 1; pinned to tests/golden/backbone_s.npz (recorded from the real reference)."""
     with torch.no_grad():
         x = torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), dim=1)
         x = base_conv(sd, f"{p}.stem.conv", x)
@@ -357,6 +357,16 @@ def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") ->
                 x = csp_layer(sd, f"{p}.{name}.1", x, shortcut=True)
             outs.append(x)
         return outs
+
+
+def csp_darknet_bf16(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
+    """csp_darknet with the storage precision of the bf16 path (see neck_head_bf16)."""
+    global _EMULATE_BF16
+    _EMULATE_BF16 = True
+    try:
+        return csp_darknet(sd, _q(x), p)
+    finally:
+        _EMULATE_BF16 = False
 
 
 # ------------------------------------------------------------------------------------------ decode

@@ -103,3 +103,22 @@ def test_oracle_backbone_runs():
     sd = ref_path.synthetic_state_dict(3, "tiny", seed=0)
     feats = ref_path.csp_darknet(sd, torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(0)))
     assert [tuple(f.shape) for f in feats] == [(1, 48, 16, 16), (1, 96, 8, 8), (1, 192, 4, 4), (1, 384, 2, 2)]
+
+
+def test_oracle_backbone_pinned_to_reference_golden():
+    """oracle.ref_path.csp_darknet (and the whole image -> logits chain) against tests/golden/backbone_s.npz, which
+    tests/golden/make_golden_backbone.py recorded from the REAL models/ffa/yolox_ffa.py YoloBody run from an image."""
+    from pathlib import Path
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / "backbone_s.npz")
+    sd = ref_path.synthetic_state_dict(10, "s", seed=0, flavour="calibrated")
+    x = torch.from_numpy(z["image"])
+    feats = ref_path.csp_darknet(sd, x)
+    for name, f in zip(("dark2", "dark3", "dark4", "dark5"), feats):
+        ref = torch.from_numpy(z[name])
+        assert f.shape == ref.shape
+        assert (f - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), name
+    logits = ref_path.neck_head(sd, feats)
+    for i, t in enumerate(logits):
+        ref = torch.from_numpy(z[f"logits{i}"])
+        assert (t - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), i
