@@ -9,7 +9,9 @@ def main(path, step_index=1, out=None):
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    starts = [i for i, n in enumerate(names) if "nchw_to_nhwc" in n][::4]   # 4 converts open every step
+    # 4 consecutive converts (dark2..dark5 -> NHWC bf16) open every device-resident step
+    conv = [i for i, n in enumerate(names) if "nchw_to_nhwc" in n]
+    starts = [i for k, i in enumerate(conv) if conv[k:k + 4] == [i, i + 1, i + 2, i + 3] and (k == 0 or conv[k - 1] != i - 1)]
     start = starts[step_index]
     end = starts[step_index + 1] if step_index + 1 < len(starts) else len(rows)
     agg = collections.OrderedDict()
