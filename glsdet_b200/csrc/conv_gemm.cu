@@ -73,6 +73,9 @@ struct alignas(64) ConvKParams {
   int32_t a_shared;          // k > 0: image b reads activation image b % k (static matrices used as activations)
   int32_t a_div;             // with a_shared: image b reads activation image b / a_div instead of b % a_shared
   int32_t patch;             // src0 / post_res / out are 2x2 patch views (image b' = (b*2 + py)*2 + px)
+  int32_t egrp;              // 16-warp TMA-store class: two groups of 8 epilogue warps drain ALTERNATE work items (one
+                             // accumulator slot each) instead of all 16 sharing every item - the epilogue of a small-K
+                             // conv is a latency chain per tile, two tiles in flight nearly double its throughput
   const float* bias;
   int32_t act;
   int32_t act_epi;           // activation code of the fast bf16 epilogues (act, or kActSiluExact)
@@ -412,6 +415,7 @@ __device__ __forceinline__ void epi_walk(uint32_t taddr, int c_begin, int c_end,
 struct TsCtx {
   uint8_t* gbuf;      // this group's two staging tiles
   int nthr, bar_id;   // group size / named barrier
+  uint32_t bufmask;   // 1: two staging tiles (double-buffered); 0: one (the group waits for its previous store first)
   bool issuer;
   bool wide;          // block_n >= 128: each column half owns whole 64-channel tiles; else both halves share one
   int parts;          // column parts = epilogue warps / 4 (2, or 4 in the 16-warp variant: block_n 64 or 128 only)
@@ -430,8 +434,12 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
     kc_end = kc_begin + 1;
   }
   for (int kc = kc_begin; kc < kc_end; ++kc, ++sbuf) {
-    uint8_t* buf = g.gbuf + (sbuf & 1u) * kStageTileBytes;
+    uint8_t* buf = g.gbuf + (sbuf & g.bufmask) * kStageTileBytes;
     uint8_t* rowp = buf + (r >> 3) * 1024 + (r & 7) * kRowBytes;
+    if (g.bufmask == 0u) {   // single staging tile: the previous store must have finished reading it
+      if (g.issuer) tma_store_wait_read();
+      named_bar_sync(g.bar_id, g.nthr);
+    }
     int cb = g.wide ? kc * 4 : half * 2;
     int ce = g.wide ? kc * 4 + 4 : half * 2 + 2;
     if (g.parts == 4) {   // 32 columns per warp (block_n 128) or 16 (block_n 64)
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + p.sa * p.a_bytes;
   uint8_t* smem_stage = smem_b + b_region;                                          // [k_tiles][128 rows][128 B]
-  const int ts_groups = (p.block_n >= 128) ? 2 : 1;
+  const int ts_groups = (p.block_n >= 128 || (EW == 16 && p.egrp)) ? 2 : 1;   // warp groups with their own staging tiles
   uint8_t* smem_pw = smem_stage + (pred_mma ? k_tiles * kStageTileBytes               // [k_tiles][16 rows][128 B]
                                             : p.ts ? ts_groups * 2 * kStageTileBytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pw + (pred_mma ? k_tiles * kPredTileBytes : 0));
@@ -518,7 +526,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], k2 ? 2 * EW : EW);  // 2-CTA: the peer's epilogue warps arrive too
+      const int ew_arr = (EW == 16 && p.egrp) ? EW / 2 : EW;   // warps that drain one accumulator slot
+      mbar_init(&tempty_bar[s], k2 ? 2 * ew_arr : ew_arr);  // 2-CTA: the peer's epilogue warps arrive too
     }
     mbar_init(bres_full, 1);
     mbar_init(pred_bar, 1);
@@ -818,10 +827,34 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       tsg.issuer = (lane == 0) && (tsg.wide ? (q == 0) : (e == 0));
     }
     tsg.parts = EW / 4;
+    tsg.bufmask = 1u;
+    const bool egrp = (EW == 16) && p.egrp;
+    const int my_slot = half >> 1;   // egrp: the accumulator slot (= parity of the work item) this warp group drains
+    if (egrp && p.block_n >= 128) {
+      // group of 8 warps = the 8-warp wide layout: the four warps with (half & 1) == s own 64-channel tile s of the
+      // item, with ONE staging tile each (4 sub-groups x 16 KB; the other group's work hides the store wait)
+      const int sub = half & 1;
+      tsg.wide = true;
+      tsg.gbuf = smem_stage + (my_slot * 2 + sub) * kStageTileBytes;
+      tsg.nthr = 128;
+      tsg.bar_id = 6 + my_slot * 2 + sub;
+      tsg.issuer = (lane == 0) && (q == 0);
+      tsg.parts = 2;
+      tsg.bufmask = 0u;
+    } else if (egrp) {   // group of 8 warps = the 8-warp, one-64-channel-tile layout: column halves by (half & 1)
+      tsg.wide = false;
+      tsg.gbuf = smem_stage + my_slot * 2 * kStageTileBytes;
+      tsg.nthr = 256;
+      tsg.bar_id = 6 + my_slot;
+      tsg.issuer = (lane == 0) && (q == 0) && ((half & 1) == 0);
+      tsg.parts = 2;
+    }
+    const int half_ts = egrp ? (half & 1) : half;
     uint32_t sbuf = 0;     // staging tiles written by this warp group (TMA-store epilogue)
     int it = 0;
     uint32_t tcount = 0;   // tiles processed by this CTA (prediction-MMA barrier phase, FMA scratch slot)
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
+      if (egrp && (it & 1) != my_slot) continue;
       const TileCoord t = decode(tile);
       const int as = (k2 || p.nacc == 2) ? (it & 1) : 0;
       const uint32_t aph = static_cast<uint32_t>((k2 || p.nacc == 2) ? (it >> 1) : it) & 1u;
@@ -858,10 +891,10 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           }
           if constexpr (EC == EC_ALL || EC == EC_BF16_TS) if (p.ts) {
             const int y_tile = t.y0 + m * p.tile_h;
-            if (has_pre && has_post) epi_tile_ts<true, true>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else if (has_pre) epi_tile_ts<true, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else if (has_post) epi_tile_ts<false, true>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else epi_tile_ts<false, false>(p, tsg, taddr, r, half, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            if (has_pre && has_post) epi_tile_ts<true, true>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_pre) epi_tile_ts<true, false>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_post) epi_tile_ts<false, true>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else epi_tile_ts<false, false>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
             break;
           }
           if constexpr (EC == EC_ALL || EC == EC_BF16) {
@@ -1411,6 +1444,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // shared memory as a bf16 operand), else per-thread FMAs.
   bool pred_mma = fused_pred && g.n_blocks == 1 && (d->out_channels % 64) == 0 &&
                   getenv("GLSDET_CONV_PRED_FMA") == nullptr;
+  // two epilogue groups draining alternate work items (16-warp TMA-store class, one 64-channel tile per M tile)
+  const bool egrp_want = (g.block_n == 64 || (g.block_n == 128 && getenv("GLSDET_CONV_NO_EGRP128") == nullptr)) && (two_cta || k.nacc == 2) && getenv("GLSDET_CONV_EPI8") == nullptr &&
+                         getenv("GLSDET_CONV_ONE_KERNEL") == nullptr && getenv("GLSDET_CONV_NO_EGRP") == nullptr;
   const int b_tap_bytes = g.block_n * kRowBytes;
   bool bres = false;
   k.bgroup = 1;
@@ -1418,7 +1454,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     const int pred_smem = !fused_pred ? 0
                           : pred_mma ? (g.block_n / 64) * (kStageTileBytes + kPredTileBytes)
                                      : (g.block_n * 16 + 2 * kBlockM * 16) * 4;
-    const int ts_smem = ts ? (g.block_n >= 128 ? 4 : 2) * kStageTileBytes : 0;
+    const int ts_smem = ts ? ((g.block_n >= 128 || egrp_want) ? 4 : 2) * kStageTileBytes : 0;
     const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem + ts_smem;
     const int budget = kSmemLimit - fixed;
     bres = false;
@@ -1575,6 +1611,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   if (op->two_cta)   // the pair kernel: one all-epilogue binary, plus the prediction class with 16 epilogue warps
     op->ec = getenv("GLSDET_CONV_ONE_KERNEL") != nullptr ? EC2_ALL
              : op->ec == EC_PRED_MMA16 ? EC2_PRED_MMA16 : op->ec == EC_BF16_TS16 ? EC2_BF16_TS16 : EC2_ALL;
+  k.egrp = (egrp_want && (op->ec == EC_BF16_TS16 || op->ec == EC2_BF16_TS16)) ? 1 : 0;
   op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16 || op->ec == EC2_BF16_TS16)
                     ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
