@@ -13,6 +13,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libglsdet_b200.so"
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX, ACT_MMDET_BOX = range(7)
 OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
 NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
+PRED_ROWS, PRED_PLANES = range(2)
 SE_SLABS = 32
 
 ACT_BY_NAME = {"none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "lrelu": ACT_LRELU}
@@ -41,6 +42,7 @@ class ConvDesc(C.Structure):
         ("weight_batch_stride", C.c_int64), ("weight_ld", C.c_int32), ("src_shared", C.c_int32),
         ("src_shared_div", C.c_int32), ("patch_mode", C.c_int32),
         ("ksize_w", C.c_int32), ("src0_row_pitch", C.c_int64), ("src0_img_pitch", C.c_int64),
+        ("out_plane_stride", C.c_int64),
     ]
 
 
@@ -128,6 +130,8 @@ SIGNATURES = {
     "glsdet_nms_launch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "glsdet_nms_launch_scaled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glsdet_nms_launch_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_float, C.c_float, C.c_int32,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_nms_destroy": (None, [C.c_void_p]),
     "glsdet_decode_mmdet": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),

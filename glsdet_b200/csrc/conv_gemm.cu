@@ -64,7 +64,9 @@ struct alignas(64) ConvKParams {
   int32_t a_bytes;           // bytes of one A stage
   int32_t tmem_cols;
   int32_t mt;                // M tiles (vertically adjacent, one A box) per work item: every B stage feeds mt MMAs
-  int32_t nacc;              // accumulator ring depth in work items (2, or 1 when 2 * mt * block_n > 512 columns)
+  int32_t nacc;              // accumulator ring depth in work items: 2; 1 when 2 * mt * block_n > 512 columns; 3 for the
+                             // prediction-MMA class (its epilogue waits for a tcgen05.mma that queues behind the main-loop
+                             // MMAs already in flight, so the main loop needs to run two items ahead)
   int32_t bres;              // all weight chunks stay resident in shared memory (loaded once per CTA)
   int32_t b_chunks;          // number of 64-wide K chunks of the weight matrix
   int32_t pdl;               // launched with programmatic stream serialisation
@@ -86,6 +88,7 @@ struct alignas(64) ConvKParams {
   void* out;
   int32_t out_mode, out_ld, out_coff;
   int64_t out_bs;
+  int64_t out_plane;   // NCHW output: elements between channel planes (Ho * Wo, or the anchor count of all levels)
   float dec_stride, dec_in_w, dec_in_h;
   int32_t epi;   // EPI_* epilogue specialisation chosen at create time
   const float* pred_w;   // fused prediction conv: fp32 [pred_n][N]
@@ -350,39 +353,35 @@ __device__ __forceinline__ void pred_accumulate16(const uint32_t (&raw)[16], con
 // Output of the fused prediction conv for one pixel: raw logits (NCHW planes or NHWC rows), sigmoid rows, or the
 // YOLOX box decode (utils_bbox.py:270-305).
 __device__ __forceinline__ void store_pred(const ConvKParams& p, const float (&y)[16], int b, int oy, int ox) {
-  if (p.out_mode == GLSDET_OUT_NCHW_F32) {
-    const int64_t plane = static_cast<int64_t>(p.Ho) * p.Wo;
-    float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
-               static_cast<int64_t>(p.out_coff) * plane + static_cast<int64_t>(oy) * p.Wo + ox;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < p.pred_n) o[j * plane] = y[j];
-    return;
-  }
-  float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
-             (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
+  const bool planes = (p.out_mode == GLSDET_OUT_NCHW_F32);
+  // planes: lanes are consecutive x -> one coalesced run per channel; rows: [.., 5+nc] per pixel
+  float* o = planes ? reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+                          static_cast<int64_t>(p.out_coff) * p.out_plane + static_cast<int64_t>(oy) * p.Wo + ox
+                    : reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
+                          (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff;
+  const int64_t st = planes ? p.out_plane : 1;
   if (p.pred_act == GLSDET_ACT_YOLOX_BOX) {
     o[0] = ((y[0] + static_cast<float>(ox)) * p.dec_stride) / p.dec_in_w;
-    o[1] = ((y[1] + static_cast<float>(oy)) * p.dec_stride) / p.dec_in_h;
-    o[2] = (expf(y[2]) * p.dec_stride) / p.dec_in_w;
-    o[3] = (expf(y[3]) * p.dec_stride) / p.dec_in_h;
-    o[4] = 1.0f / (1.0f + expf(-y[4]));
+    o[st] = ((y[1] + static_cast<float>(oy)) * p.dec_stride) / p.dec_in_h;
+    o[2 * st] = (expf(y[2]) * p.dec_stride) / p.dec_in_w;
+    o[3 * st] = (expf(y[3]) * p.dec_stride) / p.dec_in_h;
+    o[4 * st] = 1.0f / (1.0f + expf(-y[4]));
   } else if (p.pred_act == GLSDET_ACT_MMDET_BOX) {
     // mmdet yolox_head.py:298-301: xy = pred * stride + prior (prior = cell index * stride), wh = exp(pred) * stride;
     // explicit roundings: no FMA contraction, like the PyTorch reference
     o[0] = __fadd_rn(__fmul_rn(y[0], p.dec_stride), static_cast<float>(ox) * p.dec_stride);
-    o[1] = __fadd_rn(__fmul_rn(y[1], p.dec_stride), static_cast<float>(oy) * p.dec_stride);
-    o[2] = __fmul_rn(expf(y[2]), p.dec_stride);
-    o[3] = __fmul_rn(expf(y[3]), p.dec_stride);
-    o[4] = 1.0f / (1.0f + expf(-y[4]));
+    o[st] = __fadd_rn(__fmul_rn(y[1], p.dec_stride), static_cast<float>(oy) * p.dec_stride);
+    o[2 * st] = __fmul_rn(expf(y[2]), p.dec_stride);
+    o[3 * st] = __fmul_rn(expf(y[3]), p.dec_stride);
+    o[4 * st] = 1.0f / (1.0f + expf(-y[4]));
   } else if (p.pred_act == GLSDET_ACT_SIGMOID) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < p.pred_n) o[j] = 1.0f / (1.0f + expf(-y[j]));
+      if (j < p.pred_n) o[j * st] = 1.0f / (1.0f + expf(-y[j]));
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < p.pred_n) o[j] = y[j];
+      if (j < p.pred_n) o[j * st] = y[j];
   }
 }
 
@@ -491,12 +490,12 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint64_t* b_full = bars + 2 * kMaxStages;
   uint64_t* b_empty = bars + 3 * kMaxStages;
   uint64_t* tfull_bar = bars + 4 * kMaxStages;
-  uint64_t* tempty_bar = bars + 4 * kMaxStages + 2;
-  uint64_t* bres_full = bars + 4 * kMaxStages + 4;
-  uint64_t* pred_bar = bars + 4 * kMaxStages + 5;
-  uint64_t* pstage_bar = bars + 4 * kMaxStages + 7;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 6);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 8);  // [n_blocks * block_n], zero padded
+  uint64_t* tempty_bar = bars + 4 * kMaxStages + 3;   // tfull / tempty: up to 3 accumulator slots each
+  uint64_t* bres_full = bars + 4 * kMaxStages + 6;
+  uint64_t* pred_bar = bars + 4 * kMaxStages + 7;
+  uint64_t* pstage_bar = bars + 4 * kMaxStages + 9;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 8);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 10);  // [n_blocks * block_n], zero padded
   float* s_pw = s_bias + p.n_blocks * p.block_n;                         // FMA prediction path: weights [N][16]
   float* s_red = s_pw + p.block_n * 16;                                  // [2][128][16] partial sums of the upper column half
 
@@ -524,7 +523,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&tfull_bar[s], 1);
       const int ew_arr = (EW == 16 && p.egrp) ? EW / 2 : EW;   // warps that drain one accumulator slot
       mbar_init(&tempty_bar[s], k2 ? 2 * ew_arr : ew_arr);  // 2-CTA: the peer's epilogue warps arrive too
@@ -622,8 +621,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       uint32_t ph = 0;
       int it = 0;
       for (int work = work0; work < total_work; work += work_stride, ++it) {
-        const int as = it & 1;
-        const uint32_t aph = static_cast<uint32_t>(it >> 1) & 1u;
+        const int as = it % p.nacc;
+        const uint32_t aph = static_cast<uint32_t>(it / p.nacc) & 1u;
         mbar_wait(&tempty_bar[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.block_n);
@@ -740,8 +739,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     int it = 0;
     if (p.bres && work0 < total_work) mbar_wait(bres_full, 0);
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
-      const int as = (p.nacc == 2) ? (it & 1) : 0;
-      const uint32_t aph = static_cast<uint32_t>(p.nacc == 2 ? (it >> 1) : it) & 1u;
+      const int as = it % p.nacc;
+      const uint32_t aph = static_cast<uint32_t>(it / p.nacc) & 1u;
       mbar_wait(&tempty_bar[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(as * p.mt * p.block_n);
@@ -856,8 +855,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     for (int tile = work0; tile < total_work; tile += work_stride, ++it) {
       if (egrp && (it & 1) != my_slot) continue;
       const TileCoord t = decode(tile);
-      const int as = (k2 || p.nacc == 2) ? (it & 1) : 0;
-      const uint32_t aph = static_cast<uint32_t>((k2 || p.nacc == 2) ? (it >> 1) : it) & 1u;
+      const int as = it % p.nacc;
+      const uint32_t aph = static_cast<uint32_t>(it / p.nacc) & 1u;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       for (int m = 0; m < mt; ++m, ++tcount) {
@@ -1513,6 +1512,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (!size_rings(want_b3)) { free(mem); set_error("conv_create: tile does not fit shared memory"); return 2; }
   }
   k.bres = bres ? 1 : 0;
+  // prediction-MMA class: three accumulator slots (see ConvKParams::nacc); GLSDET_CONV_NACC=2 restores two
+  if (pred_mma && mt == 1 && 3 * g.block_n <= 512 && !(getenv("GLSDET_CONV_NACC") && getenv("GLSDET_CONV_NACC")[0] == '2'))
+    k.nacc = 3;
   int cols = 32;
   while (cols < k.nacc * mt * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
@@ -1528,6 +1530,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
   k.post_res = reinterpret_cast<const __nv_bfloat16*>(d->post_res); k.post_shift = d->post_shift; k.post_ld = d->post_ld;
   k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
+  k.out_plane = d->out_plane_stride > 0 ? d->out_plane_stride : static_cast<int64_t>(g.Ho) * g.Wo;
   k.dec_stride = d->dec_stride; k.dec_in_w = d->dec_in_w; k.dec_in_h = d->dec_in_h;
   {
     k.pred_w = d->pred_weight; k.pred_b = d->pred_bias; k.pred_n = d->pred_channels; k.pred_act = d->pred_act;

@@ -57,6 +57,7 @@ struct Source {
   // decoded predictions [B][A][nch] (cx, cy, w, h, obj, cls...), or caller-supplied boxes/scores/labels
   const float* pred;
   int A, nch, nc;
+  int64_t sa, sc;        // element strides of the anchor / channel index of pred: (nch, 1) rows, (1, A) planes [B][nch][A]
   const float* boxes;
   const float* scores;
   const float* labels;
@@ -73,8 +74,9 @@ template <bool kFromPred>
 __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
   Cand c;
   if (kFromPred) {
-    const float* r = s.pred + (static_cast<int64_t>(b) * s.A + idx) * s.nch;
-    const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
+    const float* r = s.pred + static_cast<int64_t>(b) * s.A * s.nch + idx * s.sa;
+    const int64_t sc = s.sc;
+    const float cx = __ldg(r), cy = __ldg(r + sc), w = __ldg(r + 2 * sc), h = __ldg(r + 3 * sc);
     // utils_bbox.py:381-386: corner = centre -/+ size / 2
     c.box.x = __fsub_rn(cx, __fdiv_rn(w, 2.0f));
     c.box.y = __fsub_rn(cy, __fdiv_rn(h, 2.0f));
@@ -87,11 +89,11 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
       c.box.z = __fdiv_rn(c.box.z, __ldg(dv + 2));
       c.box.w = __fdiv_rn(c.box.w, __ldg(dv + 3));
     }
-    c.obj = __ldg(r + 4);
-    float best = __ldg(r + 5);
+    c.obj = __ldg(r + 4 * sc);
+    float best = __ldg(r + 5 * sc);
     int arg = 0;
     for (int k = 1; k < s.nc; ++k) {  // utils_bbox.py:398 torch.max: first maximal index
-      const float v = __ldg(r + 5 + k);
+      const float v = __ldg(r + (5 + k) * sc);
       if (v > best) { best = v; arg = k; }
     }
     c.cls_conf = best;
@@ -922,10 +924,20 @@ extern "C" int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf
 extern "C" int glsdet_nms_launch_scaled(glsdet_nms_t* op, const float* pred, const float* box_div, float conf_thres,
                                         float nms_thres, int32_t strategy, float* det, int32_t* det_count,
                                         int32_t* keep_index, void* stream) {
+  return glsdet_nms_launch_layout(op, pred, GLSDET_PRED_ROWS, box_div, conf_thres, nms_thres, strategy, det, det_count,
+                                  keep_index, stream);
+}
+
+extern "C" int glsdet_nms_launch_layout(glsdet_nms_t* op, const float* pred, int32_t layout, const float* box_div,
+                                        float conf_thres, float nms_thres, int32_t strategy, float* det,
+                                        int32_t* det_count, int32_t* keep_index, void* stream) {
   GLSDET_REQUIRE(op && pred && det && det_count, "nms_launch: null pointer");
   GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_MMCV, "nms_launch: bad strategy %d", strategy);
+  GLSDET_REQUIRE(layout == GLSDET_PRED_ROWS || layout == GLSDET_PRED_PLANES, "nms_launch: bad prediction layout %d", layout);
   Source s{};
   s.pred = pred; s.A = op->A; s.nch = 5 + op->nc; s.nc = op->nc; s.box_div = box_div;
+  s.sa = (layout == GLSDET_PRED_PLANES) ? 1 : s.nch;
+  s.sc = (layout == GLSDET_PRED_PLANES) ? s.A : 1;
   return run_pipeline<true>(s, op->w, conf_thres, nms_thres, strategy, op->max_det, det, det_count, keep_index,
                             static_cast<cudaStream_t>(stream));
 }

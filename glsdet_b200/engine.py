@@ -504,7 +504,7 @@ class FFAPathPlan:
         if "towers" not in self.parts:
             return
         self.logits = [torch.empty((self.B, nch, h, w), dtype=torch.float32, device=self.device) for h, w in self.level_hw]
-        self.pred = torch.empty((self.B, self.num_anchors, nch), dtype=torch.float32, device=self.device)
+        self._alloc_pred(nch)
         box_act = N.ACT_YOLOX_BOX if self.decode == "drone" else N.ACT_MMDET_BOX
         a_off = 0
         for k, (h, w) in enumerate(self.level_hw):
@@ -525,14 +525,35 @@ class FFAPathPlan:
             self._conv(self.pred_raw_ops, wc1, bc1, [View(tc)], self.logits[k], 3, out_coff=5, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             stride = float(self.in_h / h)
-            kw = dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch)
-            self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred, 3, out_coff=a_off * nch, pred_weight=w_ro,
+            kw, c_reg, c_cls = self._pred_out(nch, a_off)
+            self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
                        pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
-            self._conv(self.pred_dec_ops, wc1, bc1, [View(tc)], self.pred, 3, out_coff=a_off * nch + 5, pred_weight=w_cl,
+            self._conv(self.pred_dec_ops, wc1, bc1, [View(tc)], self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             a_off += h * w
         self.flops -= sum(op.flops for op in self.pred_dec_ops)
         self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
+
+    def _alloc_pred(self, nch: int):
+        """Decoded predictions.  bf16 plans store them as planes [B, 5+nc, A] - the physical layout of the tensor the
+        reference's decode_outputs returns (utils_bbox.py:266,306: cat along dim 2, then permute(0, 2, 1) as a view) - so
+        that the fused prediction convs store coalesced runs per channel and the score filter reads coalesced;
+        `self.pred` is the [B, A, 5+nc] view with strides ((5+nc) A, 1, A), exactly like the reference's.  The fp32
+        accuracy mode keeps contiguous rows."""
+        if self.fp32:
+            self.pred_store = torch.empty((self.B, self.num_anchors, nch), dtype=torch.float32, device=self.device)
+            self.pred = self.pred_store
+        else:
+            self.pred_store = torch.empty((self.B, nch, self.num_anchors), dtype=torch.float32, device=self.device)
+            self.pred = self.pred_store.permute(0, 2, 1)
+
+    def _pred_out(self, nch: int, a_off: int):
+        """Output addressing of a level's fused prediction convs: (kwargs, out_coff of reg|obj, out_coff of cls)."""
+        if self.fp32:
+            return (dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch),
+                    a_off * nch, a_off * nch + 5)
+        return (dict(out_mode=N.OUT_NCHW_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch,
+                     out_plane_stride=self.num_anchors, out_elem_offset=a_off), 0, 5)
 
     def _build_towers(self):
         """Towers + predictions: yolox_ffa.py:76-117 (level 0 uses tower index 3) / base/yolox.py / mmdet
@@ -541,7 +562,7 @@ class FFAPathPlan:
         nch = 5 + nc
         self.logits = [torch.empty((self.B, nch, h, w), dtype=torch.float32, device=self.device)
                        for h, w in self.level_hw]
-        self.pred = torch.empty((self.B, self.num_anchors, nch), dtype=torch.float32, device=self.device)
+        self._alloc_pred(nch)
         box_act = N.ACT_YOLOX_BOX if self.decode == "drone" else N.ACT_MMDET_BOX
         a_off = 0
         for k, (h, w) in enumerate(self.level_hw):
@@ -566,10 +587,10 @@ class FFAPathPlan:
             # Decoded variant: the decode runs in the same epilogue, rows of [B, A, 5+nc].  Stride as the reference
             # computes it: input_shape[0] / h (utils_bbox.py:285); equal to the integer mmdet stride.
             stride = float(self.in_h / h)
-            kw = dict(out_mode=N.OUT_NHWC_F32, out_ld=nch, out_batch_stride=self.num_anchors * nch)
-            self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred, 3, out_coff=a_off * nch, pred_weight=w_ro,
+            kw, c_reg, c_cls = self._pred_out(nch, a_off)
+            self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
                        pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
-            self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred, 3, out_coff=a_off * nch + 5, pred_weight=w_cl,
+            self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             a_off += h * w
         # the second tower convs exist twice (raw + decoded variants); count them once, plus the prediction convs

@@ -123,7 +123,7 @@ class ConvOp:
                  pred_weight: Optional[torch.Tensor] = None, pred_bias: Optional[torch.Tensor] = None,
                  pred_act: int = N.ACT_NONE, weight_raw: Optional[torch.Tensor] = None, n_out: Optional[int] = None,
                  src_shared: int = 0, src_shared_div: int = 0, patch_mode: bool = False, batch: Optional[int] = None,
-                 ksize_w: int = 0):
+                 ksize_w: int = 0, out_plane_stride: int = 0, out_elem_offset: int = 0):
         """`weight_raw`: a bf16 device matrix [N rows, pitch] (shared) or [batch, N rows, pitch] (one per image) used
         as is (the batched products of the non-local block); `src_shared` = k > 0: srcs[0] holds k static matrices and image b reads matrix b mod k;
         `patch_mode`: srcs[0] / post_res / out are [B, H, W, .] tensors processed as their 4*B 2x2 patches."""
@@ -193,9 +193,10 @@ class ConvOp:
             d.out_mode = N.OUT_NHWC_BF16 if out.t.dtype == torch.bfloat16 else N.OUT_NHWC_F32
             self._out_t = out.t
         else:  # raw tensor with explicit addressing (NCHW fp32 logits / [B, A, C] decoded rows)
-            d.out, d.out_ld, d.out_coff = out.data_ptr(), out_ld, out_coff
+            d.out, d.out_ld, d.out_coff = out.data_ptr() + out_elem_offset * out.element_size(), out_ld, out_coff
             d.out_batch_stride = out_batch_stride
             d.out_mode = out_mode
+            d.out_plane_stride = out_plane_stride
             self._out_t = out
         d.dec_stride, d.dec_in_w, d.dec_in_h = dec
         self.pred_weight = self.pred_bias = None

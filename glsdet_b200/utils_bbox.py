@@ -82,11 +82,21 @@ class DeviceNMS:
 
     def launch(self, pred: torch.Tensor, conf_thres: float, nms_thres: float, strategy: str = "auto_cuda",
                stream=None):
-        assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.is_cuda
-        assert tuple(pred.shape) == (self.batch, self.anchors, 5 + self.nc), (pred.shape, self.batch, self.anchors)
-        N.check(self._lib.glsdet_nms_launch(self.handle, pred.data_ptr(), float(conf_thres), float(nms_thres),
-                                            STRATEGIES[strategy], self.det.data_ptr(), self.count.data_ptr(),
-                                            self.keep_index.data_ptr(), N.stream_ptr(stream)), "glsdet_nms_launch")
+        """`pred`: [B, A, 5+nc] fp32, either contiguous rows or the permuted view of a [B, 5+nc, A] tensor (what the
+        reference's decode_outputs returns and what the fused path writes); anything else is made contiguous."""
+        assert pred.dtype == torch.float32 and pred.is_cuda
+        nch = 5 + self.nc
+        assert tuple(pred.shape) == (self.batch, self.anchors, nch), (pred.shape, self.batch, self.anchors)
+        if pred.is_contiguous():
+            layout = N.PRED_ROWS
+        elif tuple(pred.stride()) == (nch * self.anchors, 1, self.anchors):
+            layout = N.PRED_PLANES
+        else:
+            pred, layout = pred.contiguous(), N.PRED_ROWS
+        N.check(self._lib.glsdet_nms_launch_layout(self.handle, pred.data_ptr(), layout, None, float(conf_thres),
+                                                   float(nms_thres), STRATEGIES[strategy], self.det.data_ptr(),
+                                                   self.count.data_ptr(), self.keep_index.data_ptr(),
+                                                   N.stream_ptr(stream)), "glsdet_nms_launch_layout")
         return self.det, self.count
 
     def __del__(self):
@@ -121,7 +131,9 @@ def non_max_suppression(prediction: torch.Tensor, num_classes: int, input_shape,
         return [None for _ in range(b)]
     if not prediction.is_cuda:
         raise N.NativeError("non_max_suppression needs a CUDA tensor (glsdet_b200 has no CPU path)")
-    pred = prediction[..., :5 + num_classes].float().contiguous()
+    pred = prediction.float()
+    if pred.shape[-1] != 5 + num_classes:
+        pred = pred[..., :5 + num_classes].contiguous()
     op = _device_nms(b, a, num_classes, pred.device)
     det, count = op.launch(pred, conf_thres, nms_thres, strategy)
     counts = count.cpu().numpy()                 # the one device->host sync of the reference (:481)

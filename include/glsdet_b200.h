@@ -130,6 +130,9 @@ typedef struct glsdet_conv_desc {
   int32_t ksize_w;             /* 0 = ksize (square kernel); 1 = kx taps folded into the channel view (stride 1) */
   int64_t src0_row_pitch;      /* elements between rows of src0; 0 = width * src0_ld */
   int64_t src0_img_pitch;      /* elements between images of src0; 0 = height * row pitch */
+  int64_t out_plane_stride;    /* GLSDET_OUT_NCHW_F32: elements between channel planes; 0 = Ho * Wo.  With the fused
+                                  prediction conv and a non-zero stride the pred_act (sigmoid / box decode) is applied too:
+                                  decoded predictions as planes [B][5+nc][A], `out` pointing at this level's first anchor */
 } glsdet_conv_desc;
 
 /* library / device */
@@ -345,6 +348,15 @@ int glsdet_nms_launch(glsdet_nms_t* op, const float* pred, float conf_thres, flo
  * NMS and in the output rows: mmdet's `rescale` (dense_heads/yolox_head.py:283-285 divides the decoded corners by
  * scale_factor before _bboxes_nms).  box_div == NULL is glsdet_nms_launch. */
 int glsdet_nms_launch_scaled(glsdet_nms_t* op, const float* pred, const float* box_div, float conf_thres,
+                             float nms_thres, int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index,
+                             void* stream);
+/* Same with an explicit memory layout of the decoded predictions:
+ *   GLSDET_PRED_ROWS   [B][A][5+nc] contiguous rows (what .contiguous() of the reference's decode_outputs gives);
+ *   GLSDET_PRED_PLANES [B][5+nc][A] - the PHYSICAL layout of the tensor yolox-drone's decode_outputs returns
+ *                      (utils_bbox.py:266,306: cat of the flattened levels along dim 2, then permute(0, 2, 1) as a view),
+ *                      and the one the fused prediction convs write (coalesced stores, coalesced filter reads). */
+enum { GLSDET_PRED_ROWS = 0, GLSDET_PRED_PLANES = 1 };
+int glsdet_nms_launch_layout(glsdet_nms_t* op, const float* pred, int32_t layout, const float* box_div, float conf_thres,
                              float nms_thres, int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index,
                              void* stream);
 void glsdet_nms_destroy(glsdet_nms_t* op);
