@@ -375,9 +375,14 @@ __device__ __forceinline__ void store_pred(const ConvKParams& p, const float (&y
     o[3 * st] = __fmul_rn(expf(y[3]), p.dec_stride);
     o[4 * st] = 1.0f / (1.0f + expf(-y[4]));
   } else if (p.pred_act == GLSDET_ACT_SIGMOID) {
+    // all 16 columns unconditionally (independent chains overlap; a per-column branch on pred_n serialised ten
+    // exp + divide latency chains per pixel), then predicated stores
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 1.0f / (1.0f + expf(-y[j]));
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (j < p.pred_n) o[j * st] = 1.0f / (1.0f + expf(-y[j]));
+      if (j < p.pred_n) o[j * st] = v[j];
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
