@@ -10,7 +10,7 @@ timeout 300 python tools/conv_bench.py > gpurun_out/conv_bench_final.log 2>&1
 timeout 300 python tools/step_op_times.py p0 > gpurun_out/op_times_p0.txt 2>&1
 timeout 300 python tools/backbone_op_times.py > gpurun_out/backbone_op_times.txt 2>&1
 timeout 300 python tools/mpdet_bench.py 8 > gpurun_out/mpdet_bench.txt 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo ncu1 rc=$?
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo ncu1 rc=$?
 M="gpu__time_duration.sum,launch__grid_size,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum"
 timeout 500 ncu --profile-from-start off --metrics $M --clock-control none --csv --log-file gpurun_out/step_launches_p0.csv python tools/profile_step.py p0 > gpurun_out/ncu_step_p0.log 2>&1; echo ncu2 rc=$?
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv_gemm --launch-skip 3 --launch-count 1 -o gpurun_out/prof_final_head3x3_n256 -f python tools/conv_bench.py --cases head3x3_s4_n256 --iters 1 > gpurun_out/ncu_full.log 2>&1; echo ncu3 rc=$?
