@@ -304,9 +304,9 @@ def run_native_arm(args):
         plan.load_features(feats)
         seg[s][0].record(stream)
         plan.run_neck()
-        plan.run_head(True)
+        plan.run_head("det")
         seg[s][1].record(stream)
-        det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda")
+        det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
         if world > 1:
             gather_detections(det, cnt, max_rows=max_det)
     ev[1].record(stream)
@@ -409,6 +409,7 @@ def run_native_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         img_ms = float(t.item())
     d2h_bytes = host_cnt[0].numel() * 4 + host_det[0].numel() * 4
+    plan.run_head(True)   # decoded probabilities (the timed steps leave raw class logits in plan.pred)
     cand = [int(v) for v in ((plan.pred[:, :, 4] * plan.pred[:, :, 5:].max(2)[0]) >= CONF_THRES).sum(1).cpu()]
 
     if rank == 0:

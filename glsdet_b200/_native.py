@@ -13,7 +13,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libglsdet_b200.so"
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX, ACT_MMDET_BOX = range(7)
 OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
 NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
-PRED_ROWS, PRED_PLANES = range(2)
+PRED_ROWS, PRED_PLANES, PRED_CLS_LOGITS = 0, 1, 2
 SE_SLABS = 32
 
 ACT_BY_NAME = {"none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "lrelu": ACT_LRELU}

@@ -57,6 +57,7 @@ struct Source {
   // decoded predictions [B][A][nch] (cx, cy, w, h, obj, cls...), or caller-supplied boxes/scores/labels
   const float* pred;
   int A, nch, nc;
+  int cls_logits;        // class columns hold raw logits: sigmoid is applied here (GLSDET_PRED_CLS_LOGITS)
   int64_t sa, sc;        // element strides of the anchor / channel index of pred: (nch, 1) rows, (1, A) planes [B][nch][A]
   const float* boxes;
   const float* scores;
@@ -90,11 +91,32 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
       c.box.w = __fdiv_rn(c.box.w, __ldg(dv + 3));
     }
     c.obj = __ldg(r + 4 * sc);
-    float best = __ldg(r + 5 * sc);
+    float best;
     int arg = 0;
-    for (int k = 1; k < s.nc; ++k) {  // utils_bbox.py:398 torch.max: first maximal index
-      const float v = __ldg(r + (5 + k) * sc);
-      if (v > best) { best = v; arg = k; }
+    if (s.cls_logits) {
+      // The fused prediction conv left the class logits raw; the sigmoid formula is the one of its decoding epilogue, so
+      // the values are bit-identical to the decoded ones (utils_bbox.py:268 applies the sigmoid before the max of :398).
+      // The sigmoid is monotonic up to a few ulps, so only the classes within a small window below the largest logit
+      // (or in the saturated ranges) can attain the maximal probability: the sigmoid is evaluated for those only
+      // (normally one per anchor), and the first index attaining the maximum wins, as torch.max does.
+      float m = __ldg(r + 5 * sc);
+      for (int k = 1; k < s.nc; ++k) m = fmaxf(m, __ldg(r + (5 + k) * sc));
+      const float lim = m - 1e-3f * fmaxf(1.0f, fabsf(m));
+      const bool all = (m < -80.0f);
+      best = -1.0f;
+      for (int k = 0; k < s.nc; ++k) {
+        const float x = __ldg(r + (5 + k) * sc);
+        if (all || x >= lim || x > 15.0f) {
+          const float v = 1.0f / (1.0f + expf(-x));
+          if (v > best) { best = v; arg = k; }
+        }
+      }
+    } else {
+      best = __ldg(r + 5 * sc);
+      for (int k = 1; k < s.nc; ++k) {  // utils_bbox.py:398 torch.max: first maximal index
+        const float v = __ldg(r + (5 + k) * sc);
+        if (v > best) { best = v; arg = k; }
+      }
     }
     c.cls_conf = best;
     c.label = arg;
@@ -933,11 +955,12 @@ extern "C" int glsdet_nms_launch_layout(glsdet_nms_t* op, const float* pred, int
                                         int32_t* det_count, int32_t* keep_index, void* stream) {
   GLSDET_REQUIRE(op && pred && det && det_count, "nms_launch: null pointer");
   GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_MMCV, "nms_launch: bad strategy %d", strategy);
-  GLSDET_REQUIRE(layout == GLSDET_PRED_ROWS || layout == GLSDET_PRED_PLANES, "nms_launch: bad prediction layout %d", layout);
+  GLSDET_REQUIRE(layout >= 0 && layout <= (GLSDET_PRED_PLANES | GLSDET_PRED_CLS_LOGITS), "nms_launch: bad prediction layout %d", layout);
   Source s{};
   s.pred = pred; s.A = op->A; s.nch = 5 + op->nc; s.nc = op->nc; s.box_div = box_div;
-  s.sa = (layout == GLSDET_PRED_PLANES) ? 1 : s.nch;
-  s.sc = (layout == GLSDET_PRED_PLANES) ? s.A : 1;
+  s.cls_logits = (layout & GLSDET_PRED_CLS_LOGITS) ? 1 : 0;
+  s.sa = (layout & GLSDET_PRED_PLANES) ? 1 : s.nch;
+  s.sc = (layout & GLSDET_PRED_PLANES) ? s.A : 1;
   return run_pipeline<true>(s, op->w, conf_thres, nms_thres, strategy, op->max_det, det, det_count, keep_index,
                             static_cast<cudaStream_t>(stream));
 }

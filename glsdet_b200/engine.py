@@ -118,6 +118,7 @@ class FFAPathPlan:
         self.tower_ops: List = []
         self.pred_raw_ops: List = []
         self.pred_dec_ops: List = []
+        self.pred_det_ops: List = []   # decoded boxes / objectness + RAW class logits (the score filter applies the sigmoid)
         self.logits: List[torch.Tensor] = []
         self.pred: Optional[torch.Tensor] = None
         self.flops = 0.0
@@ -526,12 +527,18 @@ class FFAPathPlan:
                        pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             stride = float(self.in_h / h)
             kw, c_reg, c_cls = self._pred_out(nch, a_off)
-            self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
-                       pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
+            op = self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
+                            pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
             self._conv(self.pred_dec_ops, wc1, bc1, [View(tc)], self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
+            if not self.fp32:
+                self.pred_det_ops.append(op)
+                self._conv(self.pred_det_ops, wc1, bc1, [View(tc)], self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+                           pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             a_off += h * w
-        self.flops -= sum(op.flops for op in self.pred_dec_ops)
+        self.flops -= sum(op.flops for op in self.pred_dec_ops) + sum(op.flops for op in self.pred_det_ops[1::2])
+        if self.fp32:
+            self.pred_det_ops = self.pred_dec_ops
         self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
 
     def _alloc_pred(self, nch: int):
@@ -588,13 +595,19 @@ class FFAPathPlan:
             # computes it: input_shape[0] / h (utils_bbox.py:285); equal to the integer mmdet stride.
             stride = float(self.in_h / h)
             kw, c_reg, c_cls = self._pred_out(nch, a_off)
-            self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
-                       pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
+            op = self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
+                            pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
             self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
+            if not self.fp32:
+                self.pred_det_ops.append(op)
+                self._conv(self.pred_det_ops, wc1, bc1, cls_in, self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+                           pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             a_off += h * w
         # the second tower convs exist twice (raw + decoded variants); count them once, plus the prediction convs
-        self.flops -= sum(op.flops for op in self.pred_dec_ops)
+        self.flops -= sum(op.flops for op in self.pred_dec_ops) + sum(op.flops for op in self.pred_det_ops[1::2])
+        if self.fp32:
+            self.pred_det_ops = self.pred_dec_ops
         self.flops += sum(2.0 * self.B * h * w * hc * (5 + nc) for h, w in self.level_hw)
 
     def attach_backbone(self, state_dict: Dict[str, torch.Tensor], prefix: str, act: str = "silu"):
@@ -611,8 +624,8 @@ class FFAPathPlan:
                                      outs=dict(zip(names, self.inputs)))
         return self.backbone
 
-    def forward_image(self, image: torch.Tensor, decoded: bool, stream=None):
-        """Image batch [B, 3, H, W] fp32 -> raw logits (decoded=False) or decoded rows [B, A, 5+nc] (decoded=True)."""
+    def forward_image(self, image: torch.Tensor, decoded, stream=None):
+        """Image batch [B, 3, H, W] fp32 -> raw logits (decoded=False) or decoded rows [B, A, 5+nc] (decoded=True / "det")."""
         self.backbone.run(image, stream)
         self.run_neck(stream)
         self.run_head(decoded, stream)
@@ -651,11 +664,18 @@ class FFAPathPlan:
     def run_stems(self, stream=None) -> None:
         self._run(self.stem_ops, stream)
 
-    def run_towers(self, decoded: bool, stream=None) -> None:
+    def run_towers(self, decoded, stream=None) -> None:
+        """`decoded`: False = raw logits per level (YoloBody.forward), True = decoded predictions in self.pred
+        (decode_outputs), "det" = decoded boxes / objectness with RAW class logits in self.pred for the fused detect path
+        (DeviceNMS.launch(..., cls_logits=plan.det_cls_logits) applies the class sigmoid in the score filter)."""
         self._run(self.tower_ops, stream)
-        self._run(self.pred_dec_ops if decoded else self.pred_raw_ops, stream)
+        self._run(self.pred_det_ops if decoded == "det" else self.pred_dec_ops if decoded else self.pred_raw_ops, stream)
 
-    def run_head(self, decoded: bool, stream=None) -> None:
+    @property
+    def det_cls_logits(self) -> bool:
+        return not self.fp32
+
+    def run_head(self, decoded, stream=None) -> None:
         self.run_stems(stream)
         self.run_towers(decoded, stream)
 
@@ -686,6 +706,13 @@ class FFAPathPlan:
         self.load_features(feats, stream)
         self.run_neck(stream)
         self.run_head(True, stream)
+        return self.pred
+
+    def forward_detect(self, feats: Sequence[torch.Tensor], stream=None) -> torch.Tensor:
+        """forward_decoded for the fused detect path: class columns stay raw logits (see run_towers)."""
+        self.load_features(feats, stream)
+        self.run_neck(stream)
+        self.run_head("det", stream)
         return self.pred
 
     def num_launches(self, decoded: bool) -> int:

@@ -81,7 +81,7 @@ class DeviceNMS:
                                             nbytes, C.byref(self.handle)), "glsdet_nms_create")
 
     def launch(self, pred: torch.Tensor, conf_thres: float, nms_thres: float, strategy: str = "auto_cuda",
-               stream=None):
+               stream=None, cls_logits: bool = False):
         """`pred`: [B, A, 5+nc] fp32, either contiguous rows or the permuted view of a [B, 5+nc, A] tensor (what the
         reference's decode_outputs returns and what the fused path writes); anything else is made contiguous."""
         assert pred.dtype == torch.float32 and pred.is_cuda
@@ -93,6 +93,8 @@ class DeviceNMS:
             layout = N.PRED_PLANES
         else:
             pred, layout = pred.contiguous(), N.PRED_ROWS
+        if cls_logits:   # class columns are raw logits (FFAPathPlan detect mode): the filter applies the sigmoid
+            layout |= N.PRED_CLS_LOGITS
         N.check(self._lib.glsdet_nms_launch_layout(self.handle, pred.data_ptr(), layout, None, float(conf_thres),
                                                    float(nms_thres), STRATEGIES[strategy], self.det.data_ptr(),
                                                    self.count.data_ptr(), self.keep_index.data_ptr(),

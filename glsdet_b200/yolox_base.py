@@ -139,8 +139,8 @@ class YoloBody(_PlanOwner):
     def detect_features(self, feats: Sequence[torch.Tensor], conf_thres: float = 0.5, nms_thres: float = 0.4,
                         strategy: str = "auto_cuda", max_det: Optional[int] = None):
         plan = self.plan_for(feats)
-        pred = plan.forward_decoded(feats)
+        pred = plan.forward_detect(feats)
         key = (plan.B, plan.num_anchors, self.num_classes, max_det, str(plan.device))
         if key not in self._nms:
             self._nms = {key: DeviceNMS(plan.B, plan.num_anchors, self.num_classes, max_det=max_det, device=plan.device)}
-        return self._nms[key].launch(pred, conf_thres, nms_thres, strategy)
+        return self._nms[key].launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)

@@ -415,8 +415,8 @@ class YoloBody(_PlanOwner):
         """Whole hot path on the device.  Returns (det [B, max_det, 7], count [B]) device tensors; rows are
         (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score."""
         plan = self.plan_for(feats)
-        pred = plan.forward_decoded(feats)
-        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy)
+        pred = plan.forward_detect(feats)
+        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)
 
     @torch.no_grad()
     def detect(self, x: torch.Tensor, conf_thres: float = 0.5, nms_thres: float = 0.4, strategy: str = "auto_cuda",
@@ -425,5 +425,5 @@ class YoloBody(_PlanOwner):
         plan = self._fused_plan(x)
         if plan is None:
             return self.detect_features(self.backbone.features(x), conf_thres, nms_thres, strategy, max_det)
-        pred = plan.forward_image(x.float().contiguous(), True)
-        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy)
+        pred = plan.forward_image(x.float().contiguous(), "det")
+        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)

@@ -354,8 +354,11 @@ int glsdet_nms_launch_scaled(glsdet_nms_t* op, const float* pred, const float* b
  *   GLSDET_PRED_ROWS   [B][A][5+nc] contiguous rows (what .contiguous() of the reference's decode_outputs gives);
  *   GLSDET_PRED_PLANES [B][5+nc][A] - the PHYSICAL layout of the tensor yolox-drone's decode_outputs returns
  *                      (utils_bbox.py:266,306: cat of the flattened levels along dim 2, then permute(0, 2, 1) as a view),
- *                      and the one the fused prediction convs write (coalesced stores, coalesced filter reads). */
-enum { GLSDET_PRED_ROWS = 0, GLSDET_PRED_PLANES = 1 };
+ *                      and the one the fused prediction convs write (coalesced stores, coalesced filter reads);
+ *   | GLSDET_PRED_CLS_LOGITS: the class columns hold raw logits and the score filter applies the sigmoid itself (once per
+ *                      anchor and class, in a full-occupancy kernel) - the fused detect path leaves it out of the cls
+ *                      prediction conv's epilogue, where ten exp + divide chains per pixel sat on four warps per SM. */
+enum { GLSDET_PRED_ROWS = 0, GLSDET_PRED_PLANES = 1, GLSDET_PRED_CLS_LOGITS = 2 };
 int glsdet_nms_launch_layout(glsdet_nms_t* op, const float* pred, int32_t layout, const float* box_div, float conf_thres,
                              float nms_thres, int32_t strategy, float* det, int32_t* det_count, int32_t* keep_index,
                              void* stream);

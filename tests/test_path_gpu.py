@@ -365,3 +365,65 @@ def test_config4_yolox_l_544x1024(native_lib, cuda_device):
         n = int(cnt[b])
         assert n == min(1000, int(full_cnt[b]))
         assert torch.equal(det[b, :n], full[b, :n])
+
+
+def test_detect_mode_raw_class_logits_equals_decoded_mode(native_lib, cuda_device):
+    """The fused detect path leaves the class logits raw and lets the score filter apply the sigmoid
+    (GLSDET_PRED_CLS_LOGITS); its rows must be bit-identical to filter + NMS on the decoded probabilities."""
+    from glsdet_b200.synthetic import synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    sd = synthetic_state_dict(10, "s", seed=0, flavour="calibrated")
+    net = YoloBody(10, "s")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    g = torch.Generator().manual_seed(31)
+    feats = [torch.randn(2, c, 256 // s, 320 // s, generator=g).to(cuda_device) for c, s in ((64, 4), (128, 8), (256, 16), (512, 32))]
+    plan = net.plan_for(feats)
+    assert plan.det_cls_logits and len(plan.pred_det_ops) == len(plan.pred_dec_ops)
+    prob = plan.forward_decoded(feats).clone()
+    assert tuple(prob.stride()) == (15 * plan.num_anchors, 1, plan.num_anchors)      # the reference's permuted view
+    nms = net.nms_for(plan, None)
+    det_a, cnt_a = nms.launch(prob, 0.01, 0.65)
+    det_a, cnt_a = det_a.clone(), cnt_a.clone()
+    raw = plan.forward_detect(feats)
+    assert torch.equal(raw[..., :5], prob[..., :5])
+    assert (raw[..., 5:] < 0).any() and float(prob[..., 5:].min()) >= 0.0            # logits vs probabilities
+    det_b, cnt_b = net.detect_features(feats, conf_thres=0.01, nms_thres=0.65)
+    assert int(cnt_a.min()) > 0 and torch.equal(cnt_a, cnt_b)
+    for b in range(2):
+        assert torch.equal(det_a[b, :int(cnt_a[b])], det_b[b, :int(cnt_b[b])])
+    # rows layout (contiguous) gives the same result as the planes view
+    det_c, cnt_c = nms.launch(prob.contiguous(), 0.01, 0.65)
+    assert torch.equal(cnt_a, cnt_c) and torch.equal(det_a[0, :int(cnt_a[0])], det_c[0, :int(cnt_c[0])])
+
+
+def test_filter_sigmoid_window_exact_on_ties_and_saturation(native_lib, cuda_device):
+    """GLSDET_PRED_CLS_LOGITS evaluates the sigmoid only for the classes that can attain the maximal probability; the
+    chosen (class_conf, class_pred) must equal the first maximum over the probabilities of ALL classes, also for equal
+    and nearly equal logits and in the saturated ranges."""
+    from glsdet_b200.utils_bbox import DeviceNMS
+
+    g = torch.Generator().manual_seed(77)
+    A, nc = 4096, 10
+    logits = torch.randn(1, A, nc, generator=g) * 2.0 - 2.0
+    logits[0, :200] = torch.randn(200, 1, generator=g).expand(200, nc)                    # all classes equal
+    base = torch.randn(200, generator=g)
+    logits[0, 200:400, 3] = base
+    logits[0, 200:400, 7] = torch.nextafter(base, torch.full_like(base, 10.0))           # one ulp above an earlier class
+    logits[0, 400:600] = 16.0 + 20.0 * torch.rand(200, nc, generator=g)                   # saturated at 1.0
+    logits[0, 600:800] = -85.0 - 30.0 * torch.rand(200, nc, generator=g)                  # saturated at 0
+    logits[0, 800:1000, 2] = 15.5
+    logits[0, 800:1000, 5] = 16.5
+    boxes = torch.rand(1, A, 2, generator=g)
+    pred = torch.cat([boxes, 0.01 + 0.02 * torch.rand(1, A, 2, generator=g), torch.full((1, A, 1), 0.9), logits], 2)
+    raw = pred.to(cuda_device).contiguous()
+    prob = raw.clone()
+    prob[..., 5:] = 1.0 / (1.0 + torch.exp(-raw[..., 5:]))       # same formula as the kernels (expf, IEEE division)
+    nms = DeviceNMS(1, A, nc, device=cuda_device)
+    det_a, cnt_a = nms.launch(prob, 0.0, 0.99)
+    det_a, cnt_a = det_a.clone(), cnt_a.clone()
+    det_b, cnt_b = nms.launch(raw, 0.0, 0.99, cls_logits=True)
+    assert int(cnt_a[0]) > 3000 and torch.equal(cnt_a, cnt_b)
+    n = int(cnt_a[0])
+    assert torch.equal(det_a[0, :n], det_b[0, :n])

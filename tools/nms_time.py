@@ -17,18 +17,21 @@ def main():
     net = net.to(dev).eval()
     feats = bench.make_features(net, 16, 1000, dev)
     plan = net.plan_for(feats)
-    pred = plan.forward_decoded(feats).clone()
     nms = net.nms_for(plan, 1000)
-    for _ in range(5):
-        nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
-    e1.record()
-    torch.cuda.synchronize()
-    print(f"post-processing: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per batch of 16")
+    prob = plan.forward_decoded(feats).clone()       # probabilities, planes view
+    raw = plan.forward_detect(feats).clone()         # raw class logits, planes view
+    for name, pred, kw in (("planes, probabilities", prob, {}), ("planes, raw class logits", raw, dict(cls_logits=True)),
+                           ("rows, probabilities", prob.contiguous(), {})):
+        for _ in range(5):
+            nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda", **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            nms.launch(pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda", **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"post-processing ({name}): {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per batch of 16")
 
 
 if __name__ == "__main__":

@@ -32,11 +32,11 @@ def main():
     def step():
         plan.load_features(feats)
         plan.run_neck()
-        plan.run_head(True)
-        nms.launch(plan.pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda")
+        plan.run_head("det")
+        nms.launch(plan.pred, bench.CONF_THRES, bench.NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
 
     ops = []
-    for group, lst in (("neck", plan.neck_ops), ("stems", plan.stem_ops), ("tower", plan.tower_ops), ("pred", plan.pred_dec_ops)):
+    for group, lst in (("neck", plan.neck_ops), ("stems", plan.stem_ops), ("tower", plan.tower_ops), ("pred", plan.pred_det_ops)):
         for op in lst:
             if isinstance(op, ConvOp):
                 d = op.desc

@@ -24,7 +24,7 @@ def main():
     B = 16
     feats = bench.make_features(net, B, 1000, dev)
     plan = net.plan_for(feats)
-    groups = (("neck", plan.neck_ops), ("stems", plan.stem_ops), ("tower", plan.tower_ops), ("pred", plan.pred_dec_ops))
+    groups = (("neck", plan.neck_ops), ("stems", plan.stem_ops), ("tower", plan.tower_ops), ("pred", plan.pred_det_ops))
     ops = [(g, op) for g, lst in groups for op in lst]
     reps = 12
     times = [[] for _ in ops]
