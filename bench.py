@@ -203,11 +203,13 @@ def run_reference_arm(args):
         return 0
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    from oracle import ref_path
+
     sd = make_weights()
-    net = body_class()(NUM_CLASSES, PHI)
-    net.load_state_dict(sd, strict=True)
     n = max(1, min(args.cpu_images, 2))
-    feats = make_features(net, n, 1000, torch.device("cpu"))
+    feats = ref_path.csp_darknet(sd, make_images(n, 1000))   # backbone features on the host (not timed)
+    if VARIANT == "p2":
+        feats = feats[1:]
     times = []
     cand = kept = None
     for s in range(args.warmup + args.steps):

@@ -20,22 +20,28 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import ConvOp, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_weight, nhwc_to_nchw
+from .ops import ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_weight, nhwc_to_nchw
 
 BN_EPS = 1e-3
 FEATURES = ("dark2", "dark3", "dark4", "dark5")
 
 
 def backbone_supported(base_channels: int) -> bool:
-    """The native plan needs channel counts that are multiples of 16 (phi = s, m, l, x; not tiny / nano)."""
-    return base_channels % 32 == 0
+    """The native plan needs channel counts that are multiples of 8 (TMA strides of 16 bytes): every phi of the reference
+    except the depthwise 'nano' (base 16, 24 for 'tiny', 32 for 's', ...)."""
+    return base_channels % 8 == 0
 
 
 class BackbonePlan:
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], device=None,
-                 act: str = "silu", prefix: str = "backbone.backbone.", outs: Optional[Dict[str, torch.Tensor]] = None):
-        """`outs` optionally maps feature names ("dark2".."dark5") to existing NHWC bf16 tensors [B, H/s, W/s, C] (the
-        input buffers of a neck plan); missing ones are allocated here."""
+                 act: str = "silu", prefix: str = "backbone.backbone.", outs: Optional[Dict[str, torch.Tensor]] = None,
+                 precision: str = "bf16"):
+        """`outs` optionally maps feature names ("dark2".."dark5") to existing NHWC tensors [B, H/s, W/s, C] (the input
+        buffers of a neck plan); missing ones are allocated here.  `precision` "fp32" = the accuracy mode (every tensor
+        fp32, SIMT fp32 convs of csrc/fp32_path.cu, fp32 Focus / pooling kernels)."""
+        assert precision in ("bf16", "fp32")
+        self.fp32 = precision == "fp32"
+        self.dtype = torch.float32 if self.fp32 else torch.bfloat16
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.B = batch
@@ -49,7 +55,7 @@ class BackbonePlan:
             raise KeyError(f"no CSPDarknet weights under prefix {prefix!r}")
         self.base = self.sd["stem.conv.conv.weight"].shape[0]
         if not backbone_supported(self.base):
-            raise NotImplementedError(f"CSPDarknet base width {self.base} is not a multiple of 32")
+            raise NotImplementedError(f"CSPDarknet base width {self.base} is not a multiple of 8")
         self.ops: List = []
         self.flops = 0.0
         self._bufs: Dict[str, torch.Tensor] = {}
@@ -58,7 +64,7 @@ class BackbonePlan:
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name: str, stride: int, channels: int) -> torch.Tensor:
-        t = torch.empty((self.B, self.in_h // stride, self.in_w // stride, channels), dtype=torch.bfloat16, device=self.device)
+        t = torch.empty((self.B, self.in_h // stride, self.in_w // stride, channels), dtype=self.dtype, device=self.device)
         self._bufs[name] = t
         return t
 
@@ -67,8 +73,9 @@ class BackbonePlan:
         return fold_bn(sd[p + ".conv.weight"], sd[p + ".bn.weight"], sd[p + ".bn.bias"], sd[p + ".bn.running_mean"],
                        sd[p + ".bn.running_var"], BN_EPS)
 
-    def _conv(self, w, b, srcs, out, stride=1, **kw) -> ConvOp:
-        op = ConvOp(srcs, w, b, ksize=w.shape[-2], stride=stride, act=self.act, out=out, **kw)
+    def _conv(self, w, b, srcs, out, stride=1, **kw):
+        cls = ConvOpF32 if self.fp32 else ConvOp
+        op = cls(srcs, w, b, ksize=w.shape[-2], stride=stride, act=self.act, out=out, **kw)
         self.ops.append(op)
         self.flops += op.flops
         return op
@@ -101,7 +108,7 @@ class BackbonePlan:
         if t is None:
             t = self._buf(name, stride, channels)
             self.outs[name] = t
-        assert tuple(t.shape) == (self.B, self.in_h // stride, self.in_w // stride, channels) and t.dtype == torch.bfloat16, \
+        assert tuple(t.shape) == (self.B, self.in_h // stride, self.in_w // stride, channels) and t.dtype == self.dtype, \
             (name, tuple(t.shape))
         return t
 
@@ -111,7 +118,11 @@ class BackbonePlan:
         h2, w2 = self.in_h // 2, self.in_w // 2
         w, b = self._folded("stem.conv")                       # [c, 12, 3, 3]
         stem = self._buf("stem", 2, c)
-        if os.environ.get("GLSDET_STEM_UNFOLDED"):             # diagnostic: plain 3x3 conv over 16-channel pixels (K = 9 * 64)
+        if self.fp32:                                          # accuracy mode: plain 3x3 conv over the 12 Focus channels
+            s2d = self._buf("focus", 2, 12)
+            self.focus = FocusOp(s2d)
+            self._conv(w, b, [View(s2d)], View(stem))
+        elif os.environ.get("GLSDET_STEM_UNFOLDED"):           # diagnostic: plain 3x3 conv over 16-channel pixels (K = 9 * 64)
             s2d = self._buf("focus", 2, 16)
             self.focus = FocusOp(s2d)
             self._conv(torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 4)), b, [View(s2d)], View(stem))

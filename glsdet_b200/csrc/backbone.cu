@@ -4,6 +4,8 @@
 // Both are HBM / shared-memory bound byte movers; the convolutions of the backbone run on conv_gemm_kernel.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "../../include/glsdet_b200.h"
 #include "common.h"
 
@@ -47,6 +49,30 @@ __global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ im
   out[1] = reinterpret_cast<const uint4*>(o)[1];
 }
 
+// fp32 accuracy mode: dst [B, H/2, W/2, 12] fp32 NHWC, same channel order, no padding channels
+__global__ void __launch_bounds__(256) focus_f32_kernel(const float* __restrict__ img, float* __restrict__ dst, int H, int W,
+                                                        int64_t total) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int x = static_cast<int>(idx % Wo);
+  const int64_t t = idx / Wo;
+  const int y = static_cast<int>(t % Ho);
+  const int64_t b = t / Ho;
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  const float* p = img + b * 3 * plane + static_cast<int64_t>(2 * y) * W + 2 * x;
+  float o[12];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float2 r0 = __ldg(reinterpret_cast<const float2*>(p + c * plane));
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(p + c * plane + W));
+    o[c] = r0.x; o[3 + c] = r1.x; o[6 + c] = r0.y; o[9 + c] = r1.y;
+  }
+  float4* out = reinterpret_cast<float4*>(dst + idx * 12);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) out[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+}
+
 // ---------------------------------------------------------------------------------------------- SPP max pools
 __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
   uint4 r;
@@ -58,18 +84,33 @@ __device__ __forceinline__ uint4 max8(uint4 a, uint4 b) {
   return r;
 }
 
-// One CTA = one image x 8 channels, the whole h x w map in shared memory (two ping-pong planes of 16-byte vectors).
+__device__ __forceinline__ uint4 max4f(uint4 a, uint4 b) {   // four fp32 values
+  uint4 r;
+  r.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)));
+  r.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y)));
+  r.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)));
+  r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
+  return r;
+}
+template <bool F32>
+__device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return F32 ? max4f(a, b) : max8(a, b); }
+
+// One CTA = one image x 8 channels (bf16; 4 channels in the fp32 accuracy mode: 16-byte vectors either way), the whole h x w map in shared memory (two ping-pong planes of 16-byte vectors).
 // MaxPool2d(k, 1, k/2) pads with -inf, i.e. the maximum runs over the in-bounds part of the window, and
 // pool9 = pool5(pool5), pool13 = pool5(pool9) exactly (maxima of nested windows), so three rounds of a separable
 // 5-wide maximum (row pass, column pass) produce the three outputs.
-__global__ void __launch_bounds__(1024) spp_pool_kernel(__nv_bfloat16* __restrict__ buf, int h, int w, int ld, int coff_src,
+template <bool F32>
+__global__ void __launch_bounds__(1024) spp_pool_kernel(void* __restrict__ buf_v, int h, int w, int ld, int coff_src,
                                                         int coff5, int coff9, int coff13, int groups) {
+  using T = typename std::conditional<F32, float, __nv_bfloat16>::type;
+  constexpr int kVec = F32 ? 4 : 8;
+  T* buf = reinterpret_cast<T*>(buf_v);
   extern __shared__ uint4 smem_pool[];
   uint4* a = smem_pool;
   uint4* t = smem_pool + h * w;
   const int g = blockIdx.x % groups;
   const int64_t b = blockIdx.x / groups;
-  __nv_bfloat16* base = buf + b * h * w * ld + g * 8;
+  T* base = buf + b * h * w * ld + g * kVec;
   const int n = h * w;
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     a[i] = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(i) * ld + coff_src);
@@ -81,7 +122,7 @@ __global__ void __launch_bounds__(1024) spp_pool_kernel(__nv_bfloat16* __restric
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int xx = x + d;
-        if (d != 0 && xx >= 0 && xx < w) m = max8(m, a[y * w + xx]);
+        if (d != 0 && xx >= 0 && xx < w) m = vmax<F32>(m, a[y * w + xx]);
       }
       t[i] = m;
     }
@@ -93,7 +134,7 @@ __global__ void __launch_bounds__(1024) spp_pool_kernel(__nv_bfloat16* __restric
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int yy = y + d;
-        if (d != 0 && yy >= 0 && yy < h) m = max8(m, t[yy * w + x]);
+        if (d != 0 && yy >= 0 && yy < h) m = vmax<F32>(m, t[yy * w + x]);
       }
       *reinterpret_cast<uint4*>(base + static_cast<int64_t>(i) * ld + coff) = m;
       // every thread rewrites only its own elements of `a`, and nobody reads `a` during this pass
@@ -118,11 +159,15 @@ extern "C" int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst,
   return glsdet::count_launch("focus_kernel");
 }
 
-extern "C" int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
-                                  int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
+namespace {
+template <bool F32>
+int spp_maxpool_impl(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld, int32_t src_coff,
+                     int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
+  constexpr int kVec = F32 ? 4 : 8;
   GLSDET_REQUIRE(buf && batch > 0 && height > 0 && width > 0 && channels > 0, "spp_maxpool: bad arguments");
-  GLSDET_REQUIRE((channels % 8) == 0 && (ld % 8) == 0 && (src_coff % 8) == 0 && (coff5 % 8) == 0 && (coff9 % 8) == 0 &&
-                     (coff13 % 8) == 0, "spp_maxpool: channels, pitch and offsets must be multiples of 8");
+  GLSDET_REQUIRE((channels % kVec) == 0 && (ld % kVec) == 0 && (src_coff % kVec) == 0 && (coff5 % kVec) == 0 &&
+                     (coff9 % kVec) == 0 && (coff13 % kVec) == 0,
+                 "spp_maxpool: channels, pitch and offsets must be multiples of %d", kVec);
   const int32_t offs[4] = {src_coff, coff5, coff9, coff13};
   for (int i = 0; i < 4; ++i) {
     GLSDET_REQUIRE(offs[i] >= 0 && offs[i] + channels <= ld, "spp_maxpool: window %d exceeds the pitch", i);
@@ -135,13 +180,36 @@ extern "C" int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int3
   int dev = 0;
   GLSDET_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    GLSDET_CHECK_CUDA(cudaFuncSetAttribute(glsdet::spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GLSDET_CHECK_CUDA(cudaFuncSetAttribute(glsdet::spp_pool_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
-  const int groups = channels / 8;
+  const int groups = channels / kVec;
   const int pixels = height * width;
   const int threads = pixels >= 1024 ? 1024 : ((pixels + 31) / 32) * 32;
-  glsdet::spp_pool_kernel<<<static_cast<unsigned>(batch) * groups, threads, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<__nv_bfloat16*>(buf), height, width, ld, src_coff, coff5, coff9, coff13, groups);
+  glsdet::spp_pool_kernel<F32><<<static_cast<unsigned>(batch) * groups, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+      buf, height, width, ld, src_coff, coff5, coff9, coff13, groups);
   return glsdet::count_launch("spp_pool_kernel");
+}
+}  // namespace
+
+extern "C" int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                                  int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
+  return spp_maxpool_impl<false>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+}
+
+extern "C" int glsdet_spp_maxpool_f32(float* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                                      int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
+  return spp_maxpool_impl<true>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+}
+
+extern "C" int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst, int32_t batch, int32_t height, int32_t width,
+                                                 void* stream) {
+  GLSDET_REQUIRE(image && dst && batch > 0 && height > 0 && width > 0, "focus_f32: bad arguments");
+  GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "focus_f32: height and width must be even (got %d x %d)", height, width);
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(image) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                 "focus_f32: image must be 8-byte aligned and dst 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(batch) * (height / 2) * (width / 2);
+  glsdet::focus_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, dst, height, width, total);
+  return glsdet::count_launch("focus_f32_kernel");
 }

@@ -469,9 +469,13 @@ class FocusOp:
 
     def __init__(self, dst):
         """`dst`: a contiguous [B, H/2, W/2, 16] tensor, or a FoldedView (zero-bordered rows, written at pixel x + 1)."""
+        self.f32 = False
         if isinstance(dst, FoldedView):
             assert dst.c_pix == 16
             self.shape, self.border, self.dst = dst.bhw, 1, dst.t
+        elif dst.dtype == torch.float32:   # fp32 accuracy mode: [B, H/2, W/2, 12]
+            assert dst.dim() == 4 and dst.shape[3] == 12 and dst.is_contiguous()
+            self.shape, self.border, self.dst, self.f32 = tuple(dst.shape[:3]), 0, dst, True
         else:
             assert dst.dtype == torch.bfloat16 and dst.dim() == 4 and dst.shape[3] == 16 and dst.is_contiguous()
             self.shape, self.border, self.dst = tuple(dst.shape[:3]), 0, dst
@@ -481,6 +485,10 @@ class FocusOp:
         b, h2, w2 = self.shape
         assert image.dtype == torch.float32 and image.is_contiguous() and image.is_cuda
         assert tuple(image.shape) == (b, 3, 2 * h2, 2 * w2), (tuple(image.shape), self.shape)
+        if self.f32:
+            N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_f32(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
+                                                                N.stream_ptr(stream)), "glsdet_focus_nchw_f32_to_nhwc_f32")
+            return
         N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_bf16(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
                                                              self.border, N.stream_ptr(stream)),
                 "glsdet_focus_nchw_f32_to_nhwc_bf16")
@@ -491,12 +499,12 @@ class SppPoolOp:
     1..3 (SPPBottleneck.forward, models/ffa/darknet.py:33-36)."""
 
     def __init__(self, cat: torch.Tensor, channels: int):
-        assert cat.dtype == torch.bfloat16 and cat.dim() == 4 and cat.is_contiguous() and cat.shape[3] == 4 * channels
+        assert cat.dtype in (torch.bfloat16, torch.float32) and cat.dim() == 4 and cat.is_contiguous() and cat.shape[3] == 4 * channels
         self.cat, self.c = cat, channels
         self._lib = N.load()
 
     def launch(self, stream=None):
         b, h, w, ld = self.cat.shape
         c = self.c
-        N.check(self._lib.glsdet_spp_maxpool(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c,
-                                             N.stream_ptr(stream)), "glsdet_spp_maxpool")
+        fn = self._lib.glsdet_spp_maxpool_f32 if self.cat.dtype == torch.float32 else self._lib.glsdet_spp_maxpool
+        N.check(fn(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c, N.stream_ptr(stream)), "glsdet_spp_maxpool")

@@ -5,7 +5,7 @@ Same constructors, forward signatures (NCHW fp32 in and out), level order (strid
 the reference (654 keys for phi='s').  The modules only hold parameters; the math runs in the
 native plan (engine.FFAPathPlan, variant "p1"): the patch non-local attention is evaluated in its reassociated form
 (engine.FFAPathPlan._build_nonlocal) by the tcgen05 conv kernel with per-image weight matrices.  The CSPDarknet
-backbone is upstream of the path and is the one piece executed by PyTorch.
+backbone runs as the native BackbonePlan (glsdet_b200/backbone.py).
 """
 from __future__ import annotations
 

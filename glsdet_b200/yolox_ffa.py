@@ -6,9 +6,8 @@ the reference, so `yolox-drone/yolo.py` can load it by module
 `load_state_dict(torch.load(path))` strictly (yolo.py:105).
 
 The modules below only HOLD parameters with the reference's names.  The math of the neck, the FFA block, the
-head, the decode and the NMS runs in the native plan (glsdet_b200/engine.py -> libglsdet_b200.so); there is no
-PyTorch fallback for it.  The CSPDarknet backbone is upstream of this path and is the one
-piece executed by PyTorch.
+head, the decode and the NMS runs in the native plan (glsdet_b200/engine.py -> libglsdet_b200.so), the CSPDarknet
+backbone in glsdet_b200/backbone.py; there is no PyTorch fallback for any of it.
 """
 from __future__ import annotations
 
@@ -16,7 +15,6 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .backbone import BackbonePlan, backbone_supported
 from .engine import FFAPathPlan
@@ -26,87 +24,58 @@ _DEPTH = {"nano": 0.33, "tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.00, "x": 1.33
 _WIDTH = {"nano": 0.25, "tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.00, "x": 1.25}
 
 
-def _activation(x: torch.Tensor, name: str) -> torch.Tensor:
-    if name == "silu":
-        return x * torch.sigmoid(x)
-    if name == "relu":
-        return torch.relu(x)
-    if name == "lrelu":
-        return F.leaky_relu(x, 0.1)
-    raise AttributeError(f"Unsupported act type: {name}")
-
-
 class BaseConv(nn.Module):
     """Parameter holder for conv(bias=False) + BatchNorm2d(eps=1e-3, momentum=0.03) + activation
-    (reference: models/base/baseConv.py:6-16).  `upstream=True` marks backbone layers, the only ones whose
-    forward is evaluated by PyTorch."""
+    (reference: models/base/baseConv.py:6-16).  No layer has a PyTorch forward: neck, head and backbone all run in
+    native plans owned by their parent modules."""
 
-    def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="silu", upstream=False):
+    def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="silu"):
         super().__init__()
         self.conv = nn.Conv2d(in_channels, out_channels, ksize, stride, (ksize - 1) // 2, groups=groups, bias=bias)
         self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0.03)
         self.act_name = act
-        self.upstream = upstream
 
     def forward(self, x):
-        if not self.upstream:
-            raise RuntimeError("this layer belongs to the native GLSDet path and is executed by libglsdet_b200.so "
-                               "through its parent module (YOLOPAFPN / YOLOXHead / YoloBody); it has no PyTorch forward")
-        return _activation(self.bn(self.conv(x)), self.act_name)
+        raise RuntimeError("this layer belongs to the native GLSDet path and is executed by libglsdet_b200.so "
+                           "through its parent module (CSPDarknet / YOLOPAFPN / YOLOXHead / YoloBody); it has no PyTorch forward")
 
 
 class Bottleneck(nn.Module):
-    def __init__(self, cin, cout, shortcut=True, expansion=0.5, act="silu", upstream=False):
+    def __init__(self, cin, cout, shortcut=True, expansion=0.5, act="silu"):
         super().__init__()
         hidden = int(cout * expansion)
-        self.conv1 = BaseConv(cin, hidden, 1, 1, act=act, upstream=upstream)
-        self.conv2 = BaseConv(hidden, cout, 3, 1, act=act, upstream=upstream)
+        self.conv1 = BaseConv(cin, hidden, 1, 1, act=act)
+        self.conv2 = BaseConv(hidden, cout, 3, 1, act=act)
         self.use_add = shortcut and cin == cout
-
-    def forward(self, x):
-        y = self.conv2(self.conv1(x))
-        return y + x if self.use_add else y
 
 
 class CSPLayer(nn.Module):
     """models/ffa/darknet.py:66-112 layout: conv1, conv2, conv3, m.<j>.conv{1,2}."""
 
-    def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu",
-                 upstream=False):
+    def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
         super().__init__()
         if depthwise:
             raise NotImplementedError("depthwise (phi='nano') blocks are not part of the native path")
         hidden = int(out_channels * expansion)
-        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act, upstream=upstream)
-        self.conv2 = BaseConv(in_channels, hidden, 1, 1, act=act, upstream=upstream)
-        self.conv3 = BaseConv(2 * hidden, out_channels, 1, 1, act=act, upstream=upstream)
-        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, act=act, upstream=upstream)
-                                 for _ in range(n)])
-
-    def forward(self, x):
-        return self.conv3(torch.cat((self.m(self.conv1(x)), self.conv2(x)), dim=1))
+        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act)
+        self.conv2 = BaseConv(in_channels, hidden, 1, 1, act=act)
+        self.conv3 = BaseConv(2 * hidden, out_channels, 1, 1, act=act)
+        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, act=act) for _ in range(n)])
 
 
 class Focus(nn.Module):
     def __init__(self, in_channels, out_channels, ksize=1, stride=1, act="silu"):
         super().__init__()
-        self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act, upstream=True)
-
-    def forward(self, x):
-        return self.conv(torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1))
+        self.conv = BaseConv(in_channels * 4, out_channels, ksize, stride, act=act)
 
 
 class SPPBottleneck(nn.Module):
     def __init__(self, in_channels, out_channels, kernel_sizes=(5, 9, 13), activation="silu"):
         super().__init__()
         hidden = in_channels // 2
-        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=activation, upstream=True)
+        self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=activation)
         self.m = nn.ModuleList([nn.MaxPool2d(ks, 1, ks // 2) for ks in kernel_sizes])
-        self.conv2 = BaseConv(hidden * (len(kernel_sizes) + 1), out_channels, 1, 1, act=activation, upstream=True)
-
-    def forward(self, x):
-        x = self.conv1(x)
-        return self.conv2(torch.cat([x] + [m(x) for m in self.m], dim=1))
+        self.conv2 = BaseConv(hidden * (len(kernel_sizes) + 1), out_channels, 1, 1, act=activation)
 
 
 class SE(nn.Module):
@@ -208,10 +177,9 @@ class _PlanOwner(nn.Module):
 class CSPDarknet(_PlanOwner):
     """Backbone (models/ffa/darknet.py:115-195): forward(image batch) -> {"dark2": .., .. "dark5": ..} NCHW fp32.
 
-    On a CUDA device (bf16 precision, base width a multiple of 32: phi = s, m, l, x) the forward runs as the native
-    BackbonePlan (glsdet_b200/backbone.py: Focus kernel, tcgen05 convs, SPP pooling kernel).  The PyTorch layers below
-    hold the parameters; their own forward is what runs for CPU tensors (the bench's CPU baseline builds its inputs
-    with it), in the fp32 accuracy mode (which keeps the upstream part in PyTorch fp32) and for phi = tiny."""
+    The forward runs as the native BackbonePlan (glsdet_b200/backbone.py: Focus kernel, tcgen05 convs - SIMT fp32 convs in
+    the fp32 accuracy mode -, SPP pooling kernel).  The PyTorch layers below only hold the parameters: there is no PyTorch
+    or CPU fallback, a CPU tensor raises."""
 
     def __init__(self, dep_mul, wid_mul, out_features=("dark2", "dark3", "dark4", "dark5"), depthwise=False,
                  act="silu"):
@@ -226,10 +194,10 @@ class CSPDarknet(_PlanOwner):
         self.stem = Focus(3, c, ksize=3, act=act)
 
         def stage(cin, cout, n, shortcut=True, spp=False):
-            layers = [BaseConv(cin, cout, 3, 2, act=act, upstream=True)]
+            layers = [BaseConv(cin, cout, 3, 2, act=act)]
             if spp:
                 layers.append(SPPBottleneck(cout, cout, activation=act))
-            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act, upstream=True))
+            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act))
             return nn.Sequential(*layers)
 
         self.dark2 = stage(c, c * 2, d)
@@ -245,32 +213,29 @@ class CSPDarknet(_PlanOwner):
             self._bb_plans.clear()
 
     def native_ok(self, x: torch.Tensor) -> bool:
+        """True when the backbone can be chained in front of a bf16 neck plan for this input."""
         return bool(x.is_cuda and self.precision == "bf16" and backbone_supported(self.base_channels)
                     and x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0)
 
     def native_plan(self, batch: int, input_hw: Sequence[int], device, outs=None, key_extra=None) -> BackbonePlan:
-        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), key_extra)
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), key_extra, self.precision)
         plan = self._bb_plans.get(key)
         if plan is None:
             if len(self._bb_plans) >= 4:
                 self._bb_plans.clear()
-            plan = BackbonePlan(self.state_dict(), batch, input_hw, device=device, act=self.act_name, prefix="", outs=outs)
+            plan = BackbonePlan(self.state_dict(), batch, input_hw, device=device, act=self.act_name, prefix="", outs=outs,
+                                precision=self.precision)
             self._bb_plans[key] = plan
         return plan
 
     @torch.no_grad()
     def forward(self, x):
-        if self.native_ok(x):
-            plan = self.native_plan(x.shape[0], x.shape[2:], x.device)
-            plan.run(x.float().contiguous())
-            return plan.features_nchw(self.out_features)
-        outs = {}
-        x = self.stem(x)
-        outs["stem"] = x
-        for name in ("dark2", "dark3", "dark4", "dark5"):
-            x = getattr(self, name)(x)
-            outs[name] = x
-        return {k: v for k, v in outs.items() if k in self.out_features}
+        if not x.is_cuda:
+            raise RuntimeError("CSPDarknet belongs to the native GLSDet path and is executed by libglsdet_b200.so on a CUDA "
+                               "device; there is no CPU / PyTorch forward")
+        plan = self.native_plan(x.shape[0], x.shape[2:], x.device)
+        plan.run(x.float().contiguous())
+        return plan.features_nchw(self.out_features)
 
 
 class YOLOXHead(_PlanOwner):

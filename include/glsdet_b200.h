@@ -243,6 +243,11 @@ int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t ba
                                        int32_t dst_border, void* stream);
 int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
                        int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream);
+/* fp32 accuracy-mode twins (every tensor fp32; Focus output [B, H/2, W/2, 12] without padding channels) */
+int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst, int32_t batch, int32_t height, int32_t width,
+                                      void* stream);
+int glsdet_spp_maxpool_f32(float* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                           int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream);
 
 /*
  * MP-Det head pieces (yolox-ufp/mmdet/models/dense_heads/mp_head.py, gfl_head.py; BASELINE configs[2]).

@@ -196,3 +196,47 @@ def test_stock_model_from_image(native_lib, cuda_device):
     emu = ref_path.stock_neck_head(sd, ref_path.csp_darknet_bf16(sd, x)[1:], bf16=True)
     for i, t in enumerate(logits):
         assert rel_l2(t, ref[i]) <= max(2e-2, 1.3 * rel_l2(emu[i], ref[i])), (i, rel_l2(t, ref[i]), rel_l2(emu[i], ref[i]))
+
+
+def test_backbone_fp32_accuracy_mode(native_lib, cuda_device):
+    """set_precision('fp32'): Focus / convs / pools in fp32 (SIMT) - the 1e-3 bar of BASELINE configs[0] extended to the
+    backbone: golden feature maps and image -> logits of the real reference."""
+    from glsdet_b200.synthetic import synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    z = np.load(GOLD / "backbone_s.npz")
+    sd = synthetic_state_dict(10, "s", seed=0, flavour="calibrated")
+    net = _net(YoloBody, sd, cuda_device).set_precision("fp32")
+    x = torch.from_numpy(z["image"]).to(cuda_device)
+    n0 = native_lib.glsdet_launch_count()
+    feats = net.backbone.backbone(x)
+    assert native_lib.glsdet_launch_count() - n0 >= 30
+    for name, f in feats.items():
+        assert_close_rel(f, torch.from_numpy(z[name]), tol=1e-3, what="fp32 " + name)
+    logits = net(x)
+    for i, t in enumerate(logits):
+        assert_close_rel(t, torch.from_numpy(z[f"logits{i}"]), tol=1e-3, what=f"fp32 logits{i}")
+
+
+def test_backbone_tiny_width(native_lib, cuda_device):
+    """phi='tiny' (base width 24: channel counts that are multiples of 8 but not of 16) against the oracle."""
+    from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    sd = synthetic_state_dict(3, "tiny", seed=3, flavour="calibrated")
+    net = YoloBody(3, "tiny")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    x = synthetic_images(2, 128, 160, seed=2)
+    feats = net.backbone.backbone(x.to(cuda_device))
+    ref = ref_path.csp_darknet(sd, x)
+    emu = ref_path.csp_darknet_bf16(sd, x)
+    for (name, f), r, e in zip(feats.items(), ref, emu):
+        assert_close_rel(f, r, tol=max(2e-2, 1.3 * rel_l2(e, r)), what="tiny " + name, max_factor=8.0)
+
+
+def test_backbone_rejects_cpu_tensor(native_lib):
+    from glsdet_b200.yolox_ffa import CSPDarknet
+
+    with pytest.raises(RuntimeError, match="no CPU"):
+        CSPDarknet(0.33, 0.5)(torch.zeros(1, 3, 64, 64))

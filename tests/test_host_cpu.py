@@ -60,13 +60,11 @@ def test_strict_load_of_reference_style_checkpoint_and_no_torch_forward():
         net.head.stems[0](torch.zeros(1, 96, 4, 4))
     with pytest.raises(RuntimeError, match="inference-only"):
         net.train()
-    # backbone is plain PyTorch and must agree with the oracle's restatement of CSPDarknet
-    x = torch.randn(1, 3, 64, 96, generator=torch.Generator().manual_seed(1))
-    with torch.no_grad():
-        mine = net.backbone.features(x)
-    ref = ref_path.csp_darknet(sd, x)
-    for a, b in zip(mine, ref):
-        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    # the backbone is native too: no PyTorch / CPU forward anywhere
+    with pytest.raises(RuntimeError, match="native GLSDet path"):
+        net.backbone.backbone.dark2[0](torch.zeros(1, 24, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        net.backbone.features(torch.zeros(1, 3, 64, 96))
 
 
 def test_fold_bn_and_pack_order():
