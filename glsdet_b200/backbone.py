@@ -23,6 +23,8 @@ from . import _native as N
 from .ops import ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_weight, nhwc_to_nchw
 
 BN_EPS = 1e-3
+IMAGENET_MEAN = (0.485, 0.456, 0.406)   # models/core/utils.py:49-50
+IMAGENET_STD = (0.229, 0.224, 0.225)
 FEATURES = ("dark2", "dark3", "dark4", "dark5")
 
 
@@ -156,6 +158,15 @@ class BackbonePlan:
     # ------------------------------------------------------------------ execution
     def run(self, image: torch.Tensor, stream=None) -> None:
         self.focus.launch(image, stream)
+        for op in self.ops:
+            op.launch(stream)
+
+    def run_uint8(self, image_u8: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD, stream=None) -> None:
+        """Same from a uint8 HWC batch [B, H, W, 3] (letterboxed to the network size): preprocess_input
+        (models/core/utils.py:47-51) and the HWC -> CHW transpose (yolo.py:134) are fused into the Focus kernel."""
+        if self.fp32:
+            raise NotImplementedError("the uint8 entry point exists for bf16 plans")
+        self.focus.launch_u8(image_u8, mean, std, stream)
         for op in self.ops:
             op.launch(stream)
 

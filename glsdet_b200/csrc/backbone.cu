@@ -4,6 +4,8 @@
 // Both are HBM / shared-memory bound byte movers; the convolutions of the backbone run on conv_gemm_kernel.
 #include <cuda_bf16.h>
 
+#include <string.h>
+
 #include <type_traits>
 
 #include "../../include/glsdet_b200.h"
@@ -44,6 +46,48 @@ __global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ im
 #pragma unroll
   for (int c = 12; c < 16; ++c) o[c] = __float2bfloat16_rn(0.f);
   // border = 1: rows of Wo + 2 pixels, pixel x lands at x + 1 (zero border pixels left and right)
+  uint4* out = reinterpret_cast<uint4*>(dst + ((b * Ho + y) * (Wo + 2 * border) + x + border) * 16);
+  out[0] = reinterpret_cast<const uint4*>(o)[0];
+  out[1] = reinterpret_cast<const uint4*>(o)[1];
+}
+
+// uint8 HWC image (what the camera / decoder delivers) -> the same Focus output, with the reference's normalisation
+// (models/core/utils.py:47-51 preprocess_input: float32 x /= 255.0; then -= mean and /= std against float64 arrays, i.e.
+// computed in double and rounded to float32 each time) applied on the fly: bit-identical to normalising on the host and
+// calling focus_kernel, at a quarter of the upload bytes.
+// The input has 256 values per channel, so the host tabulates the three statements once (IEEE float / double arithmetic,
+// the same as numpy's) and the kernel only looks the bf16 results up.
+struct NormLut {
+  uint16_t v[3][256];   // bf16 bits of ((float(u) / 255.0f) - mean[c]) / std[c]
+};
+__global__ void __launch_bounds__(256) focus_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ dst, int H,
+                                                       int W, int border, const __grid_constant__ NormLut lut, int64_t total) {
+  __shared__ uint16_t s_lut[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i >> 8][i & 255] = lut.v[i >> 8][i & 255];
+  __syncthreads();
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int Wo = W >> 1, Ho = H >> 1;
+  const int x = static_cast<int>(idx % Wo);
+  const int64_t t = idx / Wo;
+  const int y = static_cast<int>(t % Ho);
+  const int64_t b = t / Ho;
+  const uint8_t* p = img + ((b * H + 2 * y) * W + 2 * x) * 3;   // [B, H, W, 3]; 6 bytes per row, 2-byte aligned
+  __align__(16) uint16_t o[16];
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(p + static_cast<int64_t>(dy) * W * 3);
+    const uint32_t w0 = __ldg(row), w1 = __ldg(row + 1), w2 = __ldg(row + 2);
+    const uint8_t px[6] = {static_cast<uint8_t>(w0 & 255u), static_cast<uint8_t>(w0 >> 8), static_cast<uint8_t>(w1 & 255u),
+                           static_cast<uint8_t>(w1 >> 8), static_cast<uint8_t>(w2 & 255u), static_cast<uint8_t>(w2 >> 8)};
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        o[(dx * 2 + dy) * 3 + c] = s_lut[c][px[dx * 3 + c]];   // q = top-left, bottom-left, top-right, bottom-right
+  }
+#pragma unroll
+  for (int c = 12; c < 16; ++c) o[c] = 0;
   uint4* out = reinterpret_cast<uint4*>(dst + ((b * Ho + y) * (Wo + 2 * border) + x + border) * 16);
   out[0] = reinterpret_cast<const uint4*>(o)[0];
   out[1] = reinterpret_cast<const uint4*>(o)[1];
@@ -212,4 +256,31 @@ extern "C" int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst,
   glsdet::focus_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       image, dst, height, width, total);
   return glsdet::count_launch("focus_f32_kernel");
+}
+
+extern "C" int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                                            int32_t dst_border, const double* mean, const double* std, void* stream) {
+  GLSDET_REQUIRE(image && dst && mean && std && batch > 0 && height > 0 && width > 0 && (dst_border == 0 || dst_border == 1),
+                 "focus_u8: bad arguments");
+  GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "focus_u8: height and width must be even (got %d x %d)", height, width);
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "focus_u8: dst must be 16-byte aligned");
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(image) & 1) == 0, "focus_u8: image must be 2-byte aligned");
+  glsdet::NormLut lut;
+  for (int c = 0; c < 3; ++c) {
+    GLSDET_REQUIRE(std[c] != 0.0, "focus_u8: std[%d] is zero", c);
+    for (int u = 0; u < 256; ++u) {
+      volatile float v = static_cast<float>(u) / 255.0f;                       // image /= 255.0          (float32)
+      v = static_cast<float>(static_cast<double>(v) - mean[c]);                // image -= float64 array  (double, rounded)
+      v = static_cast<float>(static_cast<double>(v) / std[c]);                 // image /= float64 array
+      const float f = v;
+      uint32_t bits;
+      memcpy(&bits, &f, 4);
+      bits += 0x7FFFu + ((bits >> 16) & 1u);                                   // round to nearest even (finite values)
+      lut.v[c][u] = static_cast<uint16_t>(bits >> 16);
+    }
+  }
+  const int64_t total = static_cast<int64_t>(batch) * (height / 2) * (width / 2);
+  glsdet::focus_u8_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      image, reinterpret_cast<__nv_bfloat16*>(dst), height, width, dst_border, lut, total);
+  return glsdet::count_launch("focus_u8_kernel");
 }

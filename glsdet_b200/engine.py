@@ -631,6 +631,13 @@ class FFAPathPlan:
         self.run_head(decoded, stream)
         return self.pred if decoded else self.logits
 
+    def forward_image_uint8(self, image_u8: torch.Tensor, decoded, stream=None, **norm):
+        """uint8 HWC batch [B, H, W, 3] -> like forward_image (normalisation fused into the Focus kernel)."""
+        self.backbone.run_uint8(image_u8, stream=stream, **norm)
+        self.run_neck(stream)
+        self.run_head(decoded, stream)
+        return self.pred if decoded else self.logits
+
     # ------------------------------------------------------------------ execution
     def load_features(self, feats: Sequence[torch.Tensor], stream=None) -> None:
         """Backbone features, NCHW fp32 -> internal NHWC bf16 buffers: (dark2, dark3, dark4, dark5) for the FFA

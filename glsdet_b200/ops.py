@@ -494,6 +494,17 @@ class FocusOp:
                 "glsdet_focus_nchw_f32_to_nhwc_bf16")
 
 
+    def launch_u8(self, image_u8: torch.Tensor, mean, std, stream=None):
+        """uint8 HWC image batch [B, H, W, 3]; normalisation of models/core/utils.py:47-51 fused (bf16 plans only)."""
+        b, h2, w2 = self.shape
+        assert not self.f32 and image_u8.dtype == torch.uint8 and image_u8.is_contiguous() and image_u8.is_cuda
+        assert tuple(image_u8.shape) == (b, 2 * h2, 2 * w2, 3), (tuple(image_u8.shape), self.shape)
+        m = (C.c_double * 3)(*[float(v) for v in mean])
+        s = (C.c_double * 3)(*[float(v) for v in std])
+        N.check(self._lib.glsdet_focus_u8_to_nhwc_bf16(image_u8.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
+                                                       self.border, m, s, N.stream_ptr(stream)), "glsdet_focus_u8_to_nhwc_bf16")
+
+
 class SppPoolOp:
     """MaxPool2d(5 / 9 / 13, 1, k // 2) of channel window 0 of an NHWC bf16 concat buffer [B, h, w, 4C] into windows
     1..3 (SPPBottleneck.forward, models/ffa/darknet.py:33-36)."""

@@ -163,10 +163,13 @@ class _PlanOwner(nn.Module):
         """Plan with the native CSPDarknet chained in front (image -> backbone -> neck -> head in NHWC bf16), or None
         when the backbone cannot run natively for this input (CPU tensor, fp32 mode, phi='tiny') or the topology needs
         the NCHW fp32 features (P1 pre-loads)."""
+        return self._fused_plan_for(x.shape[0], x.shape[2], x.shape[3], x.device)
+
+    def _fused_plan_for(self, batch: int, height: int, width: int, device) -> Optional[FFAPathPlan]:
         bb = self.backbone.backbone
-        if not (isinstance(bb, CSPDarknet) and bb.native_ok(x)):
+        if not (isinstance(bb, CSPDarknet) and bb.native_ok_for(height, width, device)):
             return None
-        plan = self._plan(x.shape[0], x.shape[2:], x.device)
+        plan = self._plan(batch, (height, width), device)
         if plan.fp32 or plan.pre_loads:
             return None
         if plan.backbone is None:
@@ -213,9 +216,12 @@ class CSPDarknet(_PlanOwner):
             self._bb_plans.clear()
 
     def native_ok(self, x: torch.Tensor) -> bool:
+        return self.native_ok_for(x.shape[2], x.shape[3], x.device)
+
+    def native_ok_for(self, height: int, width: int, device) -> bool:
         """True when the backbone can be chained in front of a bf16 neck plan for this input."""
-        return bool(x.is_cuda and self.precision == "bf16" and backbone_supported(self.base_channels)
-                    and x.shape[2] % 32 == 0 and x.shape[3] % 32 == 0)
+        return bool(torch.device(device).type == "cuda" and self.precision == "bf16" and
+                    backbone_supported(self.base_channels) and height % 32 == 0 and width % 32 == 0)
 
     def native_plan(self, batch: int, input_hw: Sequence[int], device, outs=None, key_extra=None) -> BackbonePlan:
         key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), key_extra, self.precision)
@@ -381,6 +387,19 @@ class YoloBody(_PlanOwner):
         (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score."""
         plan = self.plan_for(feats)
         pred = plan.forward_detect(feats)
+        return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)
+
+    @torch.no_grad()
+    def detect_uint8(self, images_u8: torch.Tensor, conf_thres: float = 0.5, nms_thres: float = 0.4,
+                     strategy: str = "auto_cuda", max_det: Optional[int] = None, **norm):
+        """uint8 HWC image batch [B, H, W, 3] on the device (already letterboxed to the network size, yolo.py:130) ->
+        detections.  preprocess_input (models/core/utils.py:47-51) and the transpose of yolo.py:134 run inside the Focus
+        kernel, bit-identical to the host preprocessing; `mean=` / `std=` override the ImageNet constants."""
+        b, h, w, _ = images_u8.shape
+        plan = self._fused_plan_for(b, h, w, images_u8.device)
+        if plan is None:
+            raise NotImplementedError("detect_uint8 needs the chained native backbone (bf16 plan without pre-loads)")
+        pred = plan.forward_image_uint8(images_u8.contiguous(), "det", **norm)
         return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)
 
     @torch.no_grad()

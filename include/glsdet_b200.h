@@ -243,6 +243,13 @@ int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t ba
                                        int32_t dst_border, void* stream);
 int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
                        int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream);
+/* glsdet_focus_u8_to_nhwc_bf16: the same Focus output from a uint8 HWC image batch [B, H, W, 3] (host pointers mean[3], std[3]):
+ *   the normalisation of yolox-drone/models/core/utils.py:47-51 preprocess_input (x / 255 in float32, then - mean and / std
+ *   in double, rounded to float32 each time, as numpy does for the float64 constant arrays) and the HWC -> CHW transpose of
+ *   yolo.py:134 are applied on the fly - bit-identical to preprocessing on the host, a quarter of the upload bytes
+ *   (the normalisation part of the YOLO facade). */
+int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                                 int32_t dst_border, const double* mean, const double* std, void* stream);
 /* fp32 accuracy-mode twins (every tensor fp32; Focus output [B, H/2, W/2, 12] without padding channels) */
 int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst, int32_t batch, int32_t height, int32_t width,
                                       void* stream);

@@ -240,3 +240,32 @@ def test_backbone_rejects_cpu_tensor(native_lib):
 
     with pytest.raises(RuntimeError, match="no CPU"):
         CSPDarknet(0.33, 0.5)(torch.zeros(1, 3, 64, 64))
+
+
+def test_uint8_entry_bit_identical_to_host_preprocessing(native_lib, cuda_device):
+    """detect_uint8(uint8 HWC batch): the normalisation of models/core/utils.py:47-51 and the transpose of yolo.py:134 run
+    inside the Focus kernel; the Focus output and the detections equal those of the float path fed with the host-side
+    preprocessing (numpy, exactly the reference's statements)."""
+    from glsdet_b200.ops import FocusOp, FoldedView
+    from glsdet_b200.synthetic import synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    rng = np.random.default_rng(5)
+    b, h, w = 2, 128, 160
+    img = rng.integers(0, 256, (b, h, w, 3), dtype=np.uint8)
+    x = np.array(img, dtype="float32")                      # yolo.py:134
+    x /= 255.0                                              # utils.py:48-50
+    x -= np.array([0.485, 0.456, 0.406])
+    x /= np.array([0.229, 0.224, 0.225])
+    x = torch.from_numpy(np.ascontiguousarray(np.transpose(x, (0, 3, 1, 2)))).to(cuda_device)
+    fa = FoldedView(torch.zeros(b * (h // 2) * (w // 2 + 2) * 16 + 64, dtype=torch.bfloat16, device=cuda_device), b, h // 2, w // 2, 16)
+    fb = FoldedView(torch.zeros_like(fa.t), b, h // 2, w // 2, 16)
+    FocusOp(fa).launch(x)
+    FocusOp(fb).launch_u8(torch.from_numpy(img).to(cuda_device), (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+    assert torch.equal(fa.t, fb.t)
+    sd = synthetic_state_dict(10, "s", seed=0, flavour="calibrated")
+    net = _net(YoloBody, sd, cuda_device)
+    det_a, cnt_a = net.detect(x, conf_thres=0.01, nms_thres=0.65)
+    det_a, cnt_a = det_a.clone(), cnt_a.clone()
+    det_b, cnt_b = net.detect_uint8(torch.from_numpy(img).to(cuda_device), conf_thres=0.01, nms_thres=0.65)
+    assert torch.equal(cnt_a, cnt_b) and torch.equal(det_a, det_b)
