@@ -380,9 +380,9 @@ def run_native_arm(args):
         return ms
 
     kw = dict(conf_thres=CONF_THRES, nms_thres=NMS_THRES, strategy="auto_cuda", max_det=max_det)
-    if VARIANT == "p0":
+    if VARIANT in ("p0", "p2"):   # the backbone chains into the plan (no NCHW fp32 round trip)
         image_step = lambda inp: net.detect(inp[0], **kw)
-    else:   # P1 / P2: native backbone -> NCHW fp32 features -> path
+    else:   # P1: native backbone -> NCHW fp32 features (its Gram operands are built from them) -> path
         image_step = lambda inp: net.detect_features(net.backbone.features(inp[0]), **kw)
     feat_ms = e2e_measure(host_feats, lambda inp: net.detect_features(inp, **kw))
     e2e_ms = e2e_measure([host_images], image_step)

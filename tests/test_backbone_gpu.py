@@ -269,3 +269,43 @@ def test_uint8_entry_bit_identical_to_host_preprocessing(native_lib, cuda_device
     det_a, cnt_a = det_a.clone(), cnt_a.clone()
     det_b, cnt_b = net.detect_uint8(torch.from_numpy(img).to(cuda_device), conf_thres=0.01, nms_thres=0.65)
     assert torch.equal(cnt_a, cnt_b) and torch.equal(det_a, det_b)
+
+
+def test_large_model_from_image(native_lib, cuda_device):
+    """phi='l' (BASELINE configs[3] widths: base 64, up to 1024 channels = several N blocks per conv, SPP over 512 hidden
+    channels, three bottlenecks per stage) from an image with a non-square size, against the oracle."""
+    from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    sd = synthetic_state_dict(3, "l", seed=4, flavour="calibrated")
+    net = YoloBody(3, "l")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    x = synthetic_images(1, 160, 288, seed=6)
+    feats = net.backbone.backbone(x.to(cuda_device))
+    ref = ref_path.csp_darknet(sd, x)
+    emu = ref_path.csp_darknet_bf16(sd, x)
+    for (name, f), r, e in zip(feats.items(), ref, emu):
+        assert_close_rel(f, r, tol=max(2e-2, 1.3 * rel_l2(e, r)), what="l " + name, max_factor=8.0)
+    logits = net(x.to(cuda_device))
+    ref_l = ref_path.neck_head(sd, ref)
+    emu_l = ref_path.neck_head_bf16(sd, emu)
+    for i, t in enumerate(logits):
+        assert rel_l2(t, ref_l[i]) <= max(2e-2, 1.3 * rel_l2(emu_l[i], ref_l[i])), (i, rel_l2(t, ref_l[i]), rel_l2(emu_l[i], ref_l[i]))
+
+
+def test_p2_model_chains_the_backbone(native_lib, cuda_device):
+    """GLSDet P2 has no per-input pre-loads, so forward(image) chains the native backbone into its plan; the result is
+    bit-identical to going through the NCHW fp32 feature maps (bf16 values survive that round trip exactly)."""
+    from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
+    from glsdet_b200.yolo_patch_nonlocal_plus import YoloBody
+
+    sd = synthetic_state_dict(10, "s", seed=0, flavour="calibrated", variant="p2")
+    net = _net(YoloBody, sd, cuda_device)
+    x = synthetic_images(2, 256, 320, seed=8).to(cuda_device)
+    a = [t.clone() for t in net(x)]
+    plan = net._fused_plan(x)
+    assert plan is not None and plan.backbone is not None
+    b = net.forward_features(net.backbone.features(x))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
