@@ -386,13 +386,14 @@ def run_native_arm(args):
         image_step = lambda inp: net.detect_features(net.backbone.features(inp[0]), **kw)
     feat_ms = e2e_measure(host_feats, lambda inp: net.detect_features(inp, **kw))
     e2e_ms = e2e_measure([host_images], image_step)
+    kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
     u8_ms = None
     if VARIANT == "p0":   # uint8 HWC frames (what a decoder delivers): normalisation fused into the Focus kernel
         mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
         std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
         host_u8 = ((host_images * std + mean) * 255.0).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
         u8_ms = e2e_measure([host_u8], lambda inp: net.detect_uint8(inp[0], **kw))
-    kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
+        kept_u8 = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     feat_value = world * B * args.steps / (feat_ms * 1e-3)
     h2d_bytes = host_images.numel() * 4
@@ -449,7 +450,8 @@ def run_native_arm(args):
                     "value": world * B * args.steps / (u8_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * IN_H * IN_W * 3,
                     "ms_per_step": u8_ms / args.steps,
                     "how": "YoloBody.detect_uint8(pinned host uint8 HWC frames): preprocess_input (utils.py:47-51) fused into "
-                           "the Focus kernel; the same synthetic images quantised to 8 bits"},
+                           "the Focus kernel; the same synthetic images clipped and quantised to 8 bits (a different "
+                           "NMS load: see kept_per_image)", "kept_per_image": kept_u8},
                 "with_backbone": {"value": world * B / (img_ms * 1e-3), "unit": "images/s", "ms_per_step": img_ms,
                                   "what": "device-resident image batch -> backbone -> neck -> head -> NMS (CUDA events)"},
                 "gpu_launches": int(launches),
