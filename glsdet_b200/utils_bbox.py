@@ -171,3 +171,25 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
                                    STRATEGIES[strategy], ws.data_ptr(), nbytes, keep.data_ptr(), cnt.data_ptr(),
                                    N.stream_ptr()), "glsdet_batched_nms")
     return keep[:int(cnt.item())].long()
+
+
+def detection_lines(result: Optional[np.ndarray], class_names: Sequence[str], keep_classes: Optional[Sequence[str]] = None) -> List[str]:
+    """The detection-results wire format of yolox-drone/yolo.py:288-303 (get_map_txt): one line
+    "<class> <score[:6]> <left> <top> <right> <bottom>" per row of a non_max_suppression result (rows are
+    (top, left, bottom, right, obj_conf, class_conf, class_pred)); score = str(obj_conf * class_conf)[:6] of the numpy
+    float32 product, coordinates truncated with int().  `keep_classes` mirrors the `class_names` filter of :298-299."""
+    if result is None:
+        return []
+    lines = []
+    top_label = np.array(result[:, 6], dtype="int32")
+    top_conf = result[:, 4] * result[:, 5]
+    top_boxes = result[:, :4]
+    for i, c in enumerate(top_label):
+        predicted_class = class_names[int(c)]
+        if keep_classes is not None and predicted_class not in keep_classes:
+            continue
+        top, left, bottom, right = top_boxes[i]
+        score = str(top_conf[i])
+        lines.append("%s %s %s %s %s %s" % (predicted_class, score[:6], str(int(left)), str(int(top)), str(int(right)),
+                                            str(int(bottom))))
+    return lines

@@ -114,3 +114,30 @@ def test_cpu_tensors_are_rejected_loudly(native_lib):
         non_max_suppression(torch.zeros(1, 16, 15), 10, [32, 32], np.array([32, 32]), False)
     with pytest.raises(N.NativeError):
         batched_nms(torch.zeros(3, 4), torch.zeros(3), torch.zeros(3), 0.5)
+
+
+def test_detection_lines_wire_format():
+    """yolo.py:288-303: "<class> <score[:6]> <left> <top> <right> <bottom>" per detection row."""
+    import io
+
+    from glsdet_b200.utils_bbox import detection_lines
+
+    names = ["pedestrian", "car", "van"]
+    res = np.array([[10.7, 20.2, 110.9, 220.5, 0.9, 0.8123456, 1.0],
+                    [-3.2, 5.0, 40.0, 50.0, 0.5, 0.1, 0.0],
+                    [1.0, 2.0, 3.0, 4.0, 1.0, 1e-5, 2.0]], dtype=np.float32)
+    # the reference's own statements (yolo.py:288-303), executed verbatim on the same rows
+    f = io.StringIO()
+    top_label = np.array(res[:, 6], dtype='int32')
+    top_conf = res[:, 4] * res[:, 5]
+    top_boxes = res[:, :4]
+    for i, c in list(enumerate(top_label)):
+        predicted_class = names[int(c)]
+        box = top_boxes[i]
+        score = str(top_conf[i])
+        top, left, bottom, right = box
+        f.write("%s %s %s %s %s %s\n" % (predicted_class, score[:6], str(int(left)), str(int(top)), str(int(right)), str(int(bottom))))
+    assert detection_lines(res, names) == f.getvalue().splitlines()
+    assert detection_lines(res, names)[0] == "car 0.7311 20 10 220 110"
+    assert detection_lines(res, names, keep_classes=["car"]) == ["car 0.7311 20 10 220 110"]
+    assert detection_lines(None, names) == []
