@@ -20,7 +20,8 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_weight, nhwc_to_nchw
+from .ops import (ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_pair_weight, fold_kx_weight,
+                  nhwc_to_nchw)
 
 BN_EPS = 1e-3
 IMAGENET_MEAN = (0.485, 0.456, 0.406)   # models/core/utils.py:49-50
@@ -135,7 +136,14 @@ class BackbonePlan:
             self._bufs["focus"] = flat
             fv = FoldedView(flat, self.B, h2, w2, 16)
             self.focus = FocusOp(fv)
-            self._conv(fold_kx_weight(w, 16), b, [fv], View(stem), ksize_w=1)
+            if w2 % 2 == 0 and (2 * c) % 64 == 0 and not os.environ.get("GLSDET_STEM_SINGLE"):
+                # pair form: one GEMM row = output pixels (2X, 2X+1); the window at step X covers input pixels 2X-1 .. 2X+2
+                # with no padding left in K, N = 2c >= 64 (TMA-store epilogue) and the output is the [.., W/2, 2c] view
+                pair = FoldedView(flat, self.B, h2, w2 // 2, 32, row_pitch=(w2 + 2) * 16)
+                wp, bp = fold_kx_pair_weight(w, b, 16)
+                self._conv(wp, bp, [pair], View(stem.view(self.B, h2, w2 // 2, 2 * c)), ksize_w=1)
+            else:
+                self._conv(fold_kx_weight(w, 16), b, [fv], View(stem), ksize_w=1)
         self.ops[-1].flops = 2.0 * self.B * h2 * w2 * c * 12 * 9   # the reference's FLOPs (12 channels, 9 taps)
         self.flops = self.ops[-1].flops
         x = stem

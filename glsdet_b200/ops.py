@@ -70,11 +70,15 @@ class FoldedView:
     = 1): `t` is a zero-bordered NHWC bf16 buffer [B, H, W + 2, c_pix] (+ slack behind the last row); the conv sees, at
     output pixel x, the 64 consecutive elements starting at padded pixel x = (pixel x-1 | pixel x | pixel x+1 | ...)."""
 
-    __slots__ = ("t", "c", "c_pix", "_bhw")
+    __slots__ = ("t", "c", "c_pix", "_bhw", "_row_pitch")
 
-    def __init__(self, flat: torch.Tensor, batch: int, height: int, width: int, c_pix: int):
-        assert flat.dtype == torch.bfloat16 and flat.dim() == 1 and 3 * c_pix <= 64 and c_pix % 8 == 0
-        assert flat.numel() >= batch * height * (width + 2) * c_pix + 64, "needs 64 elements of slack behind the last row"
+    def __init__(self, flat: torch.Tensor, batch: int, height: int, width: int, c_pix: int, row_pitch: int = 0):
+        """`row_pitch` (elements) overrides (width + 2) * c_pix: the PAIR view of a 16-channel buffer - c_pix = 32 (two
+        pixels per step), width = W / 2, row_pitch = (W + 2) * 16 - whose 64-element window at step X covers pixels
+        2X-1 .. 2X+2, i.e. the inputs of the two output pixels 2X and 2X+1 (see fold_kx_pair_weight)."""
+        assert flat.dtype == torch.bfloat16 and flat.dim() == 1 and c_pix % 8 == 0 and c_pix <= 64
+        self._row_pitch = row_pitch if row_pitch else (width + 2) * c_pix
+        assert flat.numel() >= batch * height * self._row_pitch + 64, "needs 64 elements of slack behind the last row"
         self.t, self.c, self.c_pix, self._bhw = flat, 64, c_pix, (batch, height, width)
 
     @property
@@ -91,7 +95,7 @@ class FoldedView:
 
     @property
     def row_pitch(self) -> int:
-        return (self._bhw[2] + 2) * self.c_pix
+        return self._row_pitch
 
     @property
     def img_pitch(self) -> int:
@@ -111,6 +115,21 @@ def fold_kx_weight(weight: torch.Tensor, c_pix: int) -> torch.Tensor:
     for kx in range(3):
         out[:, kx * c_pix:kx * c_pix + c, :, 0] = weight[:, :, :, kx]
     return out
+
+
+def fold_kx_pair_weight(weight: torch.Tensor, bias: torch.Tensor, c_pix: int = 16):
+    """[N, C, 3, 3] (C <= c_pix = 16) -> ([2N, 64, 3, 1], [2N]) for the PAIR view: one GEMM row = two horizontally adjacent
+    output pixels.  The 64-element window holds pixel slots s = 0..3 = input pixels 2X-1 .. 2X+2; output half h (pixel
+    2X + h) uses slot s with tap kx = s - h.  No zero padding of K is left (3 x 64 against 9 x 64 for the plain form) and
+    N = 2N output channels are the two pixels' channels side by side - a contiguous [.., W/2, 2N] view of the output."""
+    n, c, kh, kw = weight.shape
+    assert kw == 3 and c <= c_pix and 4 * c_pix == 64
+    out = torch.zeros((2 * n, 64, kh, 1), dtype=weight.dtype, device=weight.device)
+    for h in range(2):
+        for kx in range(3):
+            s_ = kx + h
+            out[h * n:(h + 1) * n, s_ * c_pix:s_ * c_pix + c, :, 0] = weight[:, :, :, kx]
+    return out, torch.cat([bias, bias], 0)
 
 
 class ConvOp:

@@ -309,3 +309,24 @@ def test_p2_model_chains_the_backbone(native_lib, cuda_device):
     b = net.forward_features(net.backbone.features(x))
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_kx_folded_pair_conv_matches_torch(native_lib, cuda_device):
+    """Pair form of the folded stem conv (two output pixels per GEMM row, fold_kx_pair_weight) against fp64 torch."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, FoldedView, View, fold_kx_pair_weight
+
+    g = torch.Generator().manual_seed(4)
+    for b, h, w, n in ((2, 24, 40, 32), (1, 64, 64, 32), (3, 5, 6, 64), (1, 1, 130, 32)):
+        x = torch.randn(b, 12, h, w, generator=g).to(cuda_device).to(torch.bfloat16)
+        wt = (torch.randn(n, 12, 3, 3, generator=g) / 10).to(cuda_device)
+        bias = torch.randn(n, generator=g).to(cuda_device)
+        flat = torch.zeros(b * h * (w + 2) * 16 + 64, dtype=torch.bfloat16, device=cuda_device)
+        FoldedView(flat, b, h, w, 16).interior()[..., :12] = x.permute(0, 2, 3, 1)
+        pair = FoldedView(flat, b, h, w // 2, 32, row_pitch=(w + 2) * 16)
+        out = torch.zeros(b, h, w, n, dtype=torch.bfloat16, device=cuda_device)
+        wp, bp = fold_kx_pair_weight(wt, bias, 16)
+        ConvOp([pair], wp, bp, ksize=3, ksize_w=1, act=N.ACT_SILU, out=View(out.view(b, h, w // 2, 2 * n))).launch()
+        ref = F.conv2d(x.double(), wt.to(torch.bfloat16).double(), bias.double(), padding=1)
+        ref = ref * torch.sigmoid(ref)
+        assert_close_rel(out.permute(0, 3, 1, 2), ref.float(), tol=1e-2, what=f"pair {b}x{h}x{w}->{n}")
