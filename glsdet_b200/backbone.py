@@ -21,7 +21,7 @@ import torch
 
 from . import _native as N
 from .ops import (ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_pair_weight, fold_kx_weight,
-                  nhwc_to_nchw)
+                  nhwc_to_nchw, pair_stride2_weight)
 
 BN_EPS = 1e-3
 IMAGENET_MEAN = (0.485, 0.456, 0.406)   # models/core/utils.py:49-50
@@ -149,7 +149,16 @@ class BackbonePlan:
         x = stem
         for name, stride, cout in (("dark2", 4, 2 * c), ("dark3", 8, 4 * c), ("dark4", 16, 8 * c)):
             t = self._buf(name + ".0", stride, cout)
-            self._base_conv(f"{name}.0", [View(x)], View(t), stride=2)
+            cin = x.shape[3]
+            if not self.fp32 and 2 * cin == 64 and x.shape[2] % 2 == 0 and not os.environ.get("GLSDET_NO_PAIR_STRIDE2"):
+                # 32 input channels: the pixel-pair form (K = 6 x 64 instead of 9 x 64 half-empty chunks, dense TMA boxes)
+                w_, b_ = self._folded(f"{name}.0")
+                xp = x.view(x.shape[0], x.shape[1], x.shape[2] // 2, 2 * cin)
+                self._conv(pair_stride2_weight(w_), b_, [View(xp)], View(t), stride=2, ksize_w=2)
+                self.ops[-1].flops = 2.0 * self.B * t.shape[1] * t.shape[2] * cout * cin * 9
+                self.flops += self.ops[-1].flops - 2.0 * self.B * t.shape[1] * t.shape[2] * cout * 2 * cin * 6
+            else:
+                self._base_conv(f"{name}.0", [View(x)], View(t), stride=2)
             o = self._out(name, stride, cout)
             self._csp(f"{name}.1", stride, View(t), View(o), shortcut=True)
             x = o

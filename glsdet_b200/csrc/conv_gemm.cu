@@ -719,6 +719,19 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
             }
           }
         }
+      } else if (p.kw == 2) {
+        // stride 2 over pixel pairs (two input pixels = one 2C-channel pixel): input row 2*oy + ky - 1 -> (half row,
+        // parity in coordinate 2); columns are dense with taps dx = -1 (the pair left of the output) and 0
+        for (int ky = 0; ky < 3; ++ky) {
+          const int py = (ky == 1) ? 0 : 1;
+          const int yh = t.y0 + (ky == 0 ? -1 : 0);
+          for (int kx = 0; kx < 2; ++kx) {
+            for (int ch = 0; ch < p.chunks0; ++ch) {
+              load_a(&p.tmA[0], ch * kChunkK, t.x0 + kx - 1, py, yh, ab);
+              load_b((ky * 2 + kx) * p.chunks0 + ch, t.n0);
+            }
+          }
+        }
       } else {
         // stride 2: input row 2*oy + ky - 1 -> (half row, parity); tmA[0] holds even columns, tmA[1] odd ones
         for (int tap = 0; tap < 9; ++tap) {
@@ -1197,9 +1210,12 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   GLSDET_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2 (got %d)", d->stride);
   GLSDET_REQUIRE(d->batch > 0 && d->height > 0 && d->width > 0, "conv: bad input size");
   GLSDET_REQUIRE(d->src0_c > 0 && (d->src0_ld >= d->src0_c || d->src0_row_pitch > 0), "conv: bad src0 channels/pitch");
-  GLSDET_REQUIRE(d->ksize_w == 0 || d->ksize_w == d->ksize || (d->ksize_w == 1 && d->stride == 1 && d->src1 == nullptr &&
-                                                                 d->patch_mode == 0 && d->src_shared == 0),
-                 "conv: ksize_w must be 0, ksize, or 1 (kx taps folded into the channel view: stride 1, single source)");
+  const bool row_strided = d->ksize_w == 2 && d->stride == 2 && d->ksize == 3 && d->src1 == nullptr && d->patch_mode == 0 &&
+                           d->src_shared == 0;   // 3x3 stride-2 conv over PIXEL PAIRS: rows stride 2, columns taps {-1, 0}
+  GLSDET_REQUIRE(d->ksize_w == 0 || d->ksize_w == d->ksize || row_strided ||
+                     (d->ksize_w == 1 && d->stride == 1 && d->src1 == nullptr && d->patch_mode == 0 && d->src_shared == 0),
+                 "conv: ksize_w must be 0, ksize, 1 (kx taps folded into the channel view: stride 1, single source) or 2 "
+                 "(3x3 stride-2 conv over pixel pairs)");
   GLSDET_REQUIRE(d->src0_row_pitch >= 0 && d->src0_img_pitch >= 0 && (d->src0_row_pitch % 8) == 0 && (d->src0_img_pitch % 8) == 0 &&
                      (d->src0_row_pitch == 0 || (d->stride == 1 && d->patch_mode == 0)),
                  "conv: explicit src0 row / image pitches must be multiples of 8 elements (stride-1 convs only)");
@@ -1207,7 +1223,7 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   GLSDET_REQUIRE(d->out_channels > 0, "conv: out_channels must be positive");
   if (d->stride == 2) {
     GLSDET_REQUIRE(d->ksize == 3 && d->src1 == nullptr, "conv: stride 2 needs ksize 3 and a single source");
-    GLSDET_REQUIRE((d->height % 2) == 0 && (d->width % 2) == 0, "conv: stride 2 needs even height/width");
+    GLSDET_REQUIRE((d->height % 2) == 0 && ((d->width % 2) == 0 || row_strided), "conv: stride 2 needs even height/width");
   }
   if (d->src1 != nullptr) {
     GLSDET_REQUIRE(d->src1_c > 0 && d->src1_ld >= d->src1_c && (d->src1_ld % 8) == 0, "conv: bad src1 channels/pitch");
@@ -1233,11 +1249,12 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   g->n_pad = g->n_blocks * g->block_n;
   g->k_pad = g->taps * (g->chunks0 + g->chunks1) * kChunkK;
   g->Ho = d->height / d->stride;
-  g->Wo = d->width / d->stride;
+  g->Wo = row_strided ? d->width : d->width / d->stride;
   return 0;
 }
 
 constexpr int kPatchView = 3;   // encode_act_map `stride` value selecting the 2x2 patch view
+constexpr int kRowStride2 = 4;  // rows split by parity (coordinate 2), columns dense: the pixel-pair form of a stride-2 conv
 
 int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B, int H, int W, int stride,
                    int tile_w, int box_rows, int64_t row_pitch = 0, int64_t img_pitch = 0) {
@@ -1257,6 +1274,12 @@ int encode_act_map(CUtensorMap* tm, const void* base, int c_view, int ld, int B,
     strides[1] = rp * e;
     strides[2] = rp * e;
     strides[3] = ip * e;
+  } else if (stride == kRowStride2) {
+    dims[0] = c_view; dims[1] = W; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = static_cast<cuuint64_t>(ld) * e;
+    strides[1] = static_cast<cuuint64_t>(W) * ld * e;
+    strides[2] = static_cast<cuuint64_t>(2) * W * ld * e;
+    strides[3] = static_cast<cuuint64_t>(H) * W * ld * e;
   } else if (stride == kPatchView) {
     // 2x2 patch views of a [B/4, 2H, 2W, ld] tensor: coordinate 2 = px, coordinate 4 = image * 2 + py
     dims[0] = c_view; dims[1] = W; dims[2] = 2; dims[3] = H; dims[4] = B / 2;
@@ -1549,6 +1572,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (!rc && d->src1)
       rc = encode_act_map(&k.tmA[1], d->src1, d->src1_c, d->src1_ld, d->batch, d->height, d->width, 1, best_w, box_rows);
     else if (!rc) k.tmA[1] = k.tmA[0];
+  } else if (g.kw == 2) {   // stride-2 conv over pixel pairs: one map, row parity in coordinate 2
+    rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width, kRowStride2, best_w, box_rows);
+    k.tmA[1] = k.tmA[0];
   } else {
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(d->src0);
     rc = encode_act_map(&k.tmA[0], s, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w, box_rows);

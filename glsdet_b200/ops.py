@@ -132,6 +132,19 @@ def fold_kx_pair_weight(weight: torch.Tensor, bias: torch.Tensor, c_pix: int = 1
     return out, torch.cat([bias, bias], 0)
 
 
+def pair_stride2_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[N, C, 3, 3] of a stride-2 conv -> [N, 2C, 3, 2] for the pixel-pair form (glsdet_conv_desc.ksize_w = 2): the input is
+    viewed as [B, H, W/2, 2C] (pair X = pixels 2X, 2X+1); output column x reads pixels 2x-1, 2x, 2x+1 = the right pixel of
+    pair x-1 (tap 0: kx = 0) and both pixels of pair x (tap 1: kx = 1, 2)."""
+    n, c, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    out = torch.zeros((n, 2 * c, 3, 2), dtype=weight.dtype, device=weight.device)
+    out[:, c:, :, 0] = weight[:, :, :, 0]
+    out[:, :c, :, 1] = weight[:, :, :, 1]
+    out[:, c:, :, 1] = weight[:, :, :, 2]
+    return out
+
+
 class ConvOp:
     """conv(+cat)(+bias)(+residual) -> act (+residual) -> store; see glsdet_conv_desc in include/glsdet_b200.h."""
 
@@ -191,6 +204,8 @@ class ConvOp:
         d.weight = self.packed.data_ptr()
         d.bias = 0 if self.bias is None else self.bias.data_ptr()
         ho, wo = h // stride, w // stride
+        if stride == 2 and ksize_w == 2:   # stride-2 conv over pixel pairs: the width is already halved by the view
+            wo = w
         if pre_res is not None:
             assert pre_res.t.dtype == torch.float32
             assert pre_res.bhw == (b, max(ho >> pre_shift, 1), max(wo >> pre_shift, 1)), (pre_res.bhw, b, ho, wo, pre_shift)

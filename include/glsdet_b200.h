@@ -127,7 +127,11 @@ typedef struct glsdet_conv_desc {
    * src0_row_pitch / src0_img_pitch give the padded row / image pitches in elements, and the weight matrix is packed
    * as a ksize x 1 kernel over src0_c channels.
    */
-  int32_t ksize_w;             /* 0 = ksize (square kernel); 1 = kx taps folded into the channel view (stride 1) */
+  int32_t ksize_w;             /* 0 = ksize (square kernel); 1 = kx taps folded into the channel view (stride 1);
+                                  2 (ksize 3, stride 2) = 3x3 stride-2 conv over PIXEL PAIRS: src0 is the [B, H, W/2, 2C] view of
+                                  a [B, H, W, C] tensor (width = W/2, src0_c = 2C), rows are strided by 2, columns are dense
+                                  with taps dx = -1 (only the right pixel of the left pair has non-zero weights) and 0; the
+                                  output is [B, H/2, W/2, N].  K = 6 * 2C instead of 9 * 64 for C = 32, dense TMA boxes. */
   int64_t src0_row_pitch;      /* elements between rows of src0; 0 = width * src0_ld */
   int64_t src0_img_pitch;      /* elements between images of src0; 0 = height * row pitch */
   int64_t out_plane_stride;    /* GLSDET_OUT_NCHW_F32: elements between channel planes; 0 = Ho * Wo.  With the fused

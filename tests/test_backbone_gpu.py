@@ -330,3 +330,24 @@ def test_kx_folded_pair_conv_matches_torch(native_lib, cuda_device):
         ref = F.conv2d(x.double(), wt.to(torch.bfloat16).double(), bias.double(), padding=1)
         ref = ref * torch.sigmoid(ref)
         assert_close_rel(out.permute(0, 3, 1, 2), ref.float(), tol=1e-2, what=f"pair {b}x{h}x{w}->{n}")
+
+
+def test_pair_stride2_conv_matches_torch(native_lib, cuda_device):
+    """3x3 stride-2 conv over 32-channel pixels in the pixel-pair form (glsdet_conv_desc.ksize_w = 2, pair_stride2_weight)
+    against fp64 torch; ragged tiles and several sizes."""
+    from glsdet_b200 import _native as N
+    from glsdet_b200.ops import ConvOp, View, pair_stride2_weight
+
+    g = torch.Generator().manual_seed(6)
+    for b, h, w, n in ((2, 32, 48, 64), (1, 64, 64, 64), (3, 6, 20, 128), (1, 2, 260, 64)):
+        x = torch.randn(b, 32, h, w, generator=g).to(cuda_device).to(torch.bfloat16)
+        wt = (torch.randn(n, 32, 3, 3, generator=g) / 12).to(cuda_device)
+        bias = torch.randn(n, generator=g).to(cuda_device)
+        xin = x.permute(0, 2, 3, 1).contiguous()                       # [B, H, W, 32]
+        out = torch.zeros(b, h // 2, w // 2, n, dtype=torch.bfloat16, device=cuda_device)
+        op = ConvOp([View(xin.view(b, h, w // 2, 64))], pair_stride2_weight(wt), bias, ksize=3, stride=2, ksize_w=2,
+                    act=N.ACT_SILU, out=View(out))
+        op.launch()
+        ref = F.conv2d(x.double(), wt.to(torch.bfloat16).double(), bias.double(), stride=2, padding=1)
+        ref = ref * torch.sigmoid(ref)
+        assert_close_rel(out.permute(0, 3, 1, 2), ref.float(), tol=1e-2, what=f"pair stride 2 {b}x{h}x{w}->{n}")
