@@ -150,7 +150,8 @@ class BackbonePlan:
         for name, stride, cout in (("dark2", 4, 2 * c), ("dark3", 8, 4 * c), ("dark4", 16, 8 * c)):
             t = self._buf(name + ".0", stride, cout)
             cin = x.shape[3]
-            if not self.fp32 and 2 * cin == 64 and x.shape[2] % 2 == 0 and not os.environ.get("GLSDET_NO_PAIR_STRIDE2"):
+            maxc = int(os.environ.get("GLSDET_PAIR_STRIDE2_MAXC", "32"))
+            if not self.fp32 and cin % 32 == 0 and cin <= maxc and x.shape[2] % 2 == 0 and not os.environ.get("GLSDET_NO_PAIR_STRIDE2"):
                 # 32 input channels: the pixel-pair form (K = 6 x 64 instead of 9 x 64 half-empty chunks, dense TMA boxes)
                 w_, b_ = self._folded(f"{name}.0")
                 xp = x.view(x.shape[0], x.shape[1], x.shape[2] // 2, 2 * cin)
