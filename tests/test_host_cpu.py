@@ -141,3 +141,51 @@ def test_detection_lines_wire_format():
     assert detection_lines(res, names)[0] == "car 0.7311 20 10 220 110"
     assert detection_lines(res, names, keep_classes=["car"]) == ["car 0.7311 20 10 220 110"]
     assert detection_lines(None, names) == []
+
+
+def _folded_windows(x_nhwc16: torch.Tensor, step: int) -> torch.Tensor:
+    """CPU model of the overlapping TMA view of a zero-bordered 16-channel row buffer: 64 consecutive elements starting
+    at padded pixel step * X (rows padded with one zero pixel on each side, slack behind the last row)."""
+    b, h, w, c = x_nhwc16.shape
+    padded = F.pad(x_nhwc16, (0, 0, 1, 1))                      # [B, H, W + 2, 16]
+    flat = torch.cat([padded.reshape(b, h, -1), torch.zeros(b, h, 64)], 2)
+    n = w // step
+    idx = (torch.arange(n) * step * c)[:, None] + torch.arange(64)[None, :]
+    return flat[:, :, idx]                                      # [B, H, n, 64]
+
+
+def test_kx_folded_weight_transforms_reproduce_the_conv():
+    """fold_kx_weight / fold_kx_pair_weight (Focus stem: kx taps folded into an overlapping channel view) and
+    pair_stride2_weight (stride-2 conv over pixel pairs) against F.conv2d, with the views modelled on the CPU."""
+    from glsdet_b200.ops import fold_kx_pair_weight, fold_kx_weight, pair_stride2_weight
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 12, 6, 8, generator=g)
+    w = torch.randn(5, 12, 3, 3, generator=g)
+    bias = torch.randn(5, generator=g)
+    ref = F.conv2d(x, w, bias, padding=1)
+    x16 = F.pad(x.permute(0, 2, 3, 1), (0, 4))                  # [B, H, W, 16]
+    # single form: K = (ky, 64-element window at pixel x - 1)
+    win = F.pad(_folded_windows(x16, 1), (0, 0, 0, 0, 1, 1))    # rows padded for the ky taps: [B, H + 2, W, 64]
+    wf = fold_kx_weight(w, 16)                                  # [N, 64, 3, 1]
+    out = sum(torch.einsum("bhwk,nk->bnhw", win[:, ky:ky + 6], wf[:, :, ky, 0]) for ky in range(3)) + bias.view(1, -1, 1, 1)
+    assert torch.allclose(out, ref, atol=1e-4)
+    # pair form: one row of the GEMM = output pixels (2X, 2X + 1)
+    winp = F.pad(_folded_windows(x16, 2), (0, 0, 0, 0, 1, 1))   # [B, H + 2, W / 2, 64]
+    wp, bp = fold_kx_pair_weight(w, bias, 16)                   # [2N, 64, 3, 1], [2N]
+    outp = sum(torch.einsum("bhwk,nk->bnhw", winp[:, ky:ky + 6], wp[:, :, ky, 0]) for ky in range(3)) + bp.view(1, -1, 1, 1)
+    outp = outp.view(2, 2, 5, 6, 4).permute(0, 2, 3, 4, 1).reshape(2, 5, 6, 8)     # (half, n) -> pixels 2X + half
+    assert torch.allclose(outp, ref, atol=1e-4)
+    # stride-2 conv over pixel pairs: input [B, H, W/2, 2C], taps (ky, pair x - 1 | pair x), rows strided
+    x2 = torch.randn(2, 32, 8, 12, generator=g)
+    w2 = torch.randn(7, 32, 3, 3, generator=g)
+    ref2 = F.conv2d(x2, w2, None, stride=2, padding=1)
+    pairs = x2.permute(0, 2, 3, 1).reshape(2, 8, 6, 64)
+    pp = F.pad(pairs, (0, 0, 1, 0, 1, 1))                       # one zero pair on the left, one zero row above / below
+    ws = pair_stride2_weight(w2)                                # [N, 64, 3, 2]
+    out2 = torch.zeros_like(ref2)
+    for ky in range(3):
+        rows = pp[:, ky:ky + 8:2]                               # input row 2 * oy + ky - 1
+        for kx in range(2):
+            out2 += torch.einsum("bhwk,nk->bnhw", rows[:, :, kx:kx + 6], ws[:, :, ky, kx])
+    assert torch.allclose(out2, ref2, atol=1e-4)
