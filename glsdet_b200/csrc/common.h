@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -40,6 +41,33 @@ inline int count_launch(const char* what) {
   }
   return 0;
 }
+
+// Programmatic dependent launch for the small kernels of a step: the launch carries programmaticStreamSerialization, the
+// kernel starts with pdl_prologue() - it lets ITS dependents start their launch right away (they block in their own
+// griddepcontrol.wait until this grid has completed and flushed) and waits for its own prerequisites before touching
+// memory.  Launch latency and the kernel-boundary drain of ~35 tiny launches per step overlap instead of adding up.
+// GLSDET_NO_PDL=1 launches them plainly.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool plain = getenv("GLSDET_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = plain ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in count_launch (cudaGetLastError)
+}
+#endif
 
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

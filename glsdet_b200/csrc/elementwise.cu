@@ -16,6 +16,7 @@ constexpr int kTP = 32;  // pixels per transpose tile   (32 fp32 = 128 bytes on 
 // [B, C, HW] fp32 -> [B, HW, ld] bf16 (channels coff..coff+C)
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                            int C, int HW, int ld, int coff) {
+  pdl_prologue();
   __shared__ float tile[kTC][kTP + 1];
   const int p0 = blockIdx.x * kTP, c0 = blockIdx.y * kTC, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
 // stage 1: per (image, slab of pixels) channel sums, fixed summation order (deterministic)
 __global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ scratch,
                                                          int HW, int C, int ld) {
+  pdl_prologue();
   extern __shared__ float red[];  // [rows_par][C]
   const int slab = blockIdx.x, b = blockIdx.y;
   const int per = (HW + GLSDET_SE_SLABS - 1) / GLSDET_SE_SLABS;
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __
 __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ scratch, const float* __restrict__ w1,
                                                     const float* __restrict__ w2, float* __restrict__ gate, int HW,
                                                     int C, int hidden) {
+  pdl_prologue();
   extern __shared__ float sm[];  // mean[C] | hid[hidden]
   float* mean = sm;
   float* hid = sm + C;
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(256) scale_shuffle_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ gate,
                                                             __nv_bfloat16* __restrict__ dst, int B, int H, int W,
                                                             int Cout, int ld, int coff) {
+  pdl_prologue();
   const int vec_per_pix = (4 * Cout) >> 3;
   const int64_t total = static_cast<int64_t>(B) * H * W * vec_per_pix;
   const int cvn = Cout >> 3;
@@ -256,7 +260,7 @@ extern "C" int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t
   const int HW = height * width;
   dim3 grid((HW + kTP - 1) / kTP, (channels + kTC - 1) / kTC, batch);
   GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nchw_to_nhwc: grid too large");
-  nchw_to_nhwc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(nchw_to_nhwc_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), 
       src, reinterpret_cast<__nv_bfloat16*>(dst), channels, HW, dst_ld, dst_coff);
   return count_launch("nchw_to_nhwc_kernel");
 }
@@ -286,11 +290,11 @@ extern "C" int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t 
   const size_t smem1 = static_cast<size_t>(rows_par) * channels * sizeof(float);
   GLSDET_REQUIRE(smem1 <= 48 * 1024, "se_gate: too many channels (%d)", channels);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  se_partial_kernel<<<dim3(GLSDET_SE_SLABS, batch), 256, smem1, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), scratch,
+  launch_pdl(se_partial_kernel, dim3(GLSDET_SE_SLABS, batch), 256, smem1, st, reinterpret_cast<const __nv_bfloat16*>(x), scratch,
                                                                      hw, channels, x_ld);
   if (int rc = count_launch("se_partial_kernel")) return rc;
   const size_t smem2 = static_cast<size_t>(channels + hidden) * sizeof(float);
-  se_fc_kernel<<<batch, 256, smem2, st>>>(scratch, w1, w2, gate, hw, channels, hidden);
+  launch_pdl(se_fc_kernel, batch, 256, smem2, st, scratch, w1, w2, gate, hw, channels, hidden);
   return count_launch("se_fc_kernel");
 }
 
@@ -299,7 +303,7 @@ extern "C" int glsdet_se_fc(const float* scratch, const float* w1, const float* 
   GLSDET_REQUIRE(scratch && w1 && w2 && gate && batch > 0 && hw > 0 && channels > 0 && hidden > 0, "se_fc: bad arguments");
   const size_t smem2 = static_cast<size_t>(channels + hidden) * sizeof(float);
   GLSDET_REQUIRE(smem2 <= 48 * 1024, "se_fc: too many channels (%d)", channels);
-  se_fc_kernel<<<batch, 256, smem2, static_cast<cudaStream_t>(stream)>>>(scratch, w1, w2, gate, hw, channels, hidden);
+  launch_pdl(se_fc_kernel, batch, 256, smem2, static_cast<cudaStream_t>(stream), scratch, w1, w2, gate, hw, channels, hidden);
   return count_launch("se_fc_kernel");
 }
 
@@ -314,7 +318,7 @@ extern "C" int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
   if (blocks > cap) blocks = cap;
-  scale_shuffle_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(scale_shuffle_kernel, static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(x), gate, reinterpret_cast<__nv_bfloat16*>(dst), batch, height, width,
       out_channels, dst_ld, dst_coff);
   return count_launch("scale_shuffle_kernel");

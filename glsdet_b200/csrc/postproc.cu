@@ -184,6 +184,7 @@ __device__ __forceinline__ ImageMode image_mode(const Work& w, int b, int strate
 }
 
 __global__ void reset_kernel(Work w) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < w.B) {
     w.cand_count[i] = 0;
@@ -195,6 +196,7 @@ __global__ void reset_kernel(Work w) {
 // ---------------------------------------------------------------------------------------------- filter
 template <bool kFromPred>
 __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float conf_thres) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
   for (int base = blockIdx.x * blockDim.x; base < s.A; base += gridDim.x * blockDim.x) {
@@ -241,6 +243,7 @@ __device__ __forceinline__ int sort_extent(int n) {
 }
 
 __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int n = w.cand_count[b];
   const int pb = sort_extent(n);
@@ -263,6 +266,7 @@ __device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
 
 // sorts every kSortChunk-sized chunk (all levels k <= kSortChunk), direction alternating by global index
 __global__ void __launch_bounds__(kSortThreads) bitonic_local_sort_kernel(Work w) {
+  pdl_prologue();
   __shared__ uint64_t sk[kSortChunk];
   const int b = blockIdx.y;
   const int pb = sort_extent(w.cand_count[b]);
@@ -286,6 +290,7 @@ __global__ void __launch_bounds__(kSortThreads) bitonic_local_sort_kernel(Work w
 
 // one compare-exchange step (level k, distance j >= kSortChunk) over the whole padded array
 __global__ void __launch_bounds__(256) bitonic_global_step_kernel(Work w, int k, int j) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int pb = sort_extent(w.cand_count[b]);
   if (k > pb) return;
@@ -300,6 +305,7 @@ __global__ void __launch_bounds__(256) bitonic_global_step_kernel(Work w, int k,
 
 // finishes level k inside each chunk (distances kSortChunk/2 .. 1)
 __global__ void __launch_bounds__(kSortThreads) bitonic_local_merge_kernel(Work w, int k) {
+  pdl_prologue();
   __shared__ uint64_t sk[kSortChunk];
   const int b = blockIdx.y;
   const int pb = sort_extent(w.cand_count[b]);
@@ -321,6 +327,7 @@ __global__ void __launch_bounds__(kSortThreads) bitonic_local_merge_kernel(Work 
 
 // ---------------------------------------------------------------------------------------------- segments
 __global__ void segment_bounds_kernel(Work w, int strategy) {
+  pdl_prologue();
   const int b = blockIdx.x;
   const int n = w.cand_count[b];
   const ImageMode m = image_mode(w, b, strategy);
@@ -359,6 +366,7 @@ __device__ __forceinline__ bool iou_exceeds(const float4& a, float aarea, const 
 // NMS-space box of every sorted candidate: raw box, or box + label * (max_coord + 1) for the coordinate trick
 template <bool kFromPred>
 __global__ void __launch_bounds__(256) box_prep_kernel(Source s, Work w, int strategy) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int n = w.cand_count[b];
   const ImageMode m = image_mode(w, b, strategy);
@@ -390,6 +398,7 @@ __device__ __forceinline__ float box_area(const float4& b) {
 // One block: decide which segments get a bitmask (in segment order, until the word budget is spent) and build the
 // tile work list.  Segment ids are b * nc + c.
 __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
+  pdl_prologue();
   __shared__ long long s_words[1024];
   __shared__ int s_tiles[1024];
   __shared__ long long carry_words;
@@ -437,6 +446,7 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
 // boxes staged in shared memory and emits one 64-bit word.
 constexpr int kMaskGroups = 4;
 __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, float thr) {
+  pdl_prologue();
   __shared__ float4 cbox[kMaskGroups][64];
   __shared__ float carea[kMaskGroups][64];
   const int total_seg = w.B * w.nc;
@@ -511,6 +521,7 @@ __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, fl
 // chunk only walks the flagged rows.  The diagonal words of chunk r+1 are prefetched while chunk r is resolved.
 constexpr int kScanThreads = 512;
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
+  pdl_prologue();
   extern __shared__ unsigned long long scan_smem[];  // removed[T] | any[T]
   __shared__ unsigned long long diag[2][64];
   __shared__ unsigned long long kept_bits_s;
@@ -606,6 +617,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
 
 template <bool kFromPred>
 __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work w, float thr, int strategy) {
+  pdl_prologue();
   __shared__ float4 kbox[kKeptSmem];
   __shared__ float karea[kKeptSmem];
   __shared__ float4 cbox[64];
@@ -718,6 +730,7 @@ __global__ void __launch_bounds__(kNmsThreads) nms_segment_kernel(Source s, Work
 template <bool kFromPred>
 __global__ void __launch_bounds__(256) rank_gather_kernel(Source s, Work w, int max_det, float* det,
                                                           int32_t* det_count, int32_t* keep_index) {
+  pdl_prologue();
   __shared__ int sstart[kMaxClasses + 1];
   __shared__ int skept[kMaxClasses];
   const int b = blockIdx.y;
@@ -847,59 +860,59 @@ template <bool kFromPred>
 int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thres, int strategy, int max_det,
                  float* det, int32_t* det_count, int32_t* keep_index, cudaStream_t st) {
   const int B = w.B;
-  reset_kernel<<<(B + 255) / 256, 256, 0, st>>>(w);
+  launch_pdl(reset_kernel, (B + 255) / 256, 256, 0, st, w);
   if (int rc = count_launch("reset_kernel")) return rc;
   {
     int gx = (s.A + 255) / 256;
     if (gx > 4096) gx = 4096;
-    filter_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, conf_thres);
+    launch_pdl(filter_kernel<kFromPred>, dim3(gx, B), 256, 0, st, s, w, conf_thres);
     if (int rc = count_launch("filter_kernel")) return rc;
   }
   {
     int gx = w.P / 256;
     if (gx > 1024) gx = 1024;
-    build_keys_kernel<<<dim3(gx, B), 256, 0, st>>>(w, strategy);
+    launch_pdl(build_keys_kernel, dim3(gx, B), 256, 0, st, w, strategy);
     if (int rc = count_launch("build_keys_kernel")) return rc;
   }
   const int chunks = w.P / kSortChunk;
-  bitonic_local_sort_kernel<<<dim3(chunks, B), kSortThreads, 0, st>>>(w);
+  launch_pdl(bitonic_local_sort_kernel, dim3(chunks, B), kSortThreads, 0, st, w);
   if (int rc = count_launch("bitonic_local_sort_kernel")) return rc;
   for (int k = 2 * kSortChunk; k <= w.P; k <<= 1) {
     for (int j = k >> 1; j >= kSortChunk; j >>= 1) {
       int gx = w.P / 2 / 256;
       if (gx > 2048) gx = 2048;
-      bitonic_global_step_kernel<<<dim3(gx, B), 256, 0, st>>>(w, k, j);
+      launch_pdl(bitonic_global_step_kernel, dim3(gx, B), 256, 0, st, w, k, j);
       if (int rc = count_launch("bitonic_global_step_kernel")) return rc;
     }
-    bitonic_local_merge_kernel<<<dim3(chunks, B), kSortThreads, 0, st>>>(w, k);
+    launch_pdl(bitonic_local_merge_kernel, dim3(chunks, B), kSortThreads, 0, st, w, k);
     if (int rc = count_launch("bitonic_local_merge_kernel")) return rc;
   }
-  segment_bounds_kernel<<<B, 256, 0, st>>>(w, strategy);
+  launch_pdl(segment_bounds_kernel, B, 256, 0, st, w, strategy);
   if (int rc = count_launch("segment_bounds_kernel")) return rc;
   {
     int gx = (w.cap + 255) / 256;
     if (gx > 1024) gx = 1024;
-    box_prep_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, strategy);
+    launch_pdl(box_prep_kernel<kFromPred>, dim3(gx, B), 256, 0, st, s, w, strategy);
     if (int rc = count_launch("box_prep_kernel")) return rc;
   }
-  seg_plan_kernel<<<1, 1024, 0, st>>>(w);
+  launch_pdl(seg_plan_kernel, 1, 1024, 0, st, w);
   if (int rc = count_launch("seg_plan_kernel")) return rc;
   if (w.topk == 0) {
-    mask_tiles_kernel<<<device_sm_count() * 6, 64 * kMaskGroups, 0, st>>>(w, nms_thres);
+    launch_pdl(mask_tiles_kernel, device_sm_count() * 6, 64 * kMaskGroups, 0, st, w, nms_thres);
     if (int rc = count_launch("mask_tiles_kernel")) return rc;
   }
   if (w.topk == 0) {
     int t = (w.cap + 63) / 64;
     if (t > kMaxScanTiles) t = kMaxScanTiles;
-    scan_kernel<<<dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 16, st>>>(w);
+    launch_pdl(scan_kernel, dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 16, st, w);
     if (int rc = count_launch("scan_kernel")) return rc;
   }
-  nms_segment_kernel<kFromPred><<<dim3(w.nc, B), kNmsThreads, 0, st>>>(s, w, nms_thres, strategy);
+  launch_pdl(nms_segment_kernel<kFromPred>, dim3(w.nc, B), kNmsThreads, 0, st, s, w, nms_thres, strategy);
   if (int rc = count_launch("nms_segment_kernel")) return rc;
   {
     int gx = (w.cap + 255) / 256;
     if (gx > 256) gx = 256;
-    rank_gather_kernel<kFromPred><<<dim3(gx, B), 256, 0, st>>>(s, w, max_det, det, det_count, keep_index);
+    launch_pdl(rank_gather_kernel<kFromPred>, dim3(gx, B), 256, 0, st, s, w, max_det, det, det_count, keep_index);
     if (int rc = count_launch("rank_gather_kernel")) return rc;
   }
   return 0;
