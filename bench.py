@@ -313,7 +313,6 @@ def run_native_arm(args):
             gather_detections(det, cnt, max_rows=max_det)
     ev[1].record(stream)
     sync_all()
-    clocks = clock.stop()
     launches = lib.glsdet_launch_count() - launches0
     elapsed_ms = ev[0].elapsed_time(ev[1])
     conv_ms = sum(a.elapsed_time(b) for a, b in seg) / args.steps
@@ -386,6 +385,8 @@ def run_native_arm(args):
         image_step = lambda inp: net.detect_features(net.backbone.features(inp[0]), **kw)
     feat_ms = e2e_measure(host_feats, lambda inp: net.detect_features(inp, **kw))
     e2e_ms = e2e_measure([host_images], image_step)
+    clocks = clock.stop()   # sampled over the device-resident timed region and the two end-to-end regions above
+    clocks["sampled_over"] = "device-resident timed region + e2e regions (features, images), 5 ms interval"
     kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
     u8_ms = None
     if VARIANT == "p0":   # uint8 HWC frames (what a decoder delivers): normalisation fused into the Focus kernel
