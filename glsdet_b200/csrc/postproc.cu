@@ -197,8 +197,16 @@ __global__ void reset_kernel(Work w) {
 template <bool kFromPred>
 __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float conf_thres) {
   pdl_prologue();
+  // Compaction with ONE atomicAdd per CTA and iteration (warp ballots -> shared prefix -> a single slot range), and one
+  // atomicMax / atomicMin per CTA for the coordinate range: per-warp atomics on the 16 per-image counters serialised at
+  // the L2 (2 700 same-address atomics per counter).  The order of the compacted candidates is irrelevant: the sort keys
+  // carry the anchor index.
+  __shared__ int s_cnt[8];
+  __shared__ int s_base;
+  __shared__ float s_hi[8], s_lo[8];
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float hi = -INFINITY, lo = INFINITY;
   for (int base = blockIdx.x * blockDim.x; base < s.A; base += gridDim.x * blockDim.x) {
     const int a = base + threadIdx.x;
     bool pass = false;
@@ -210,26 +218,37 @@ __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float con
       pass = kFromPred ? (score >= conf_thres) : true;  // utils_bbox.py:403 (>=)
     }
     const uint32_t mask = __ballot_sync(0xffffffffu, pass);
-    if (mask == 0u) continue;
-    int slot0 = 0;
-    if (lane == 0) slot0 = atomicAdd(&w.cand_count[b], __popc(mask));
-    slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-    float hi = -INFINITY, lo = INFINITY;
+    if (lane == 0) s_cnt[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const int n = s_cnt[i]; s_cnt[i] = tot; tot += n; }   // exclusive prefix
+      s_base = tot ? atomicAdd(&w.cand_count[b], tot) : 0;
+    }
+    __syncthreads();
     if (pass) {
-      const int slot = slot0 + __popc(mask & ((1u << lane) - 1u));
+      const int slot = s_base + s_cnt[warp] + __popc(mask & ((1u << lane) - 1u));
       const int64_t o = static_cast<int64_t>(b) * w.cap + slot;
       w.cand_score[o] = score;
       w.cand_idx[o] = a;
       w.cand_label[o] = static_cast<uint8_t>(c.label);
-      hi = fmaxf(fmaxf(c.box.x, c.box.y), fmaxf(c.box.z, c.box.w));
-      lo = fminf(fminf(c.box.x, c.box.y), fminf(c.box.z, c.box.w));
+      hi = fmaxf(hi, fmaxf(fmaxf(c.box.x, c.box.y), fmaxf(c.box.z, c.box.w)));
+      lo = fminf(lo, fminf(fminf(c.box.x, c.box.y), fminf(c.box.z, c.box.w)));
     }
+    __syncthreads();   // s_cnt / s_base are rewritten by the next iteration
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    }
-    if (lane == 0) {
+  for (int o = 16; o > 0; o >>= 1) {
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+  }
+  if (lane == 0) { s_hi[warp] = hi; s_lo[warp] = lo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { hi = fmaxf(hi, s_hi[i]); lo = fminf(lo, s_lo[i]); }
+    if (hi != -INFINITY) {   // at least one candidate in this CTA
       atomicMax(&w.max_bits[b], float_order_bits(hi));
       atomicMin(&w.min_bits[b], float_order_bits(lo));
     }
