@@ -15,6 +15,38 @@ OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
 NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
 PRED_ROWS, PRED_PLANES, PRED_CLS_LOGITS = 0, 1, 2
 SE_SLABS = 32
+DT_BF16, DT_F16 = 0, 1   # GLSDET_DT_*: 16-bit storage type of an activation / weight tensor
+
+
+def dt_code(dtype) -> int:
+    """GLSDET_DT_* of a torch dtype (the two 16-bit storage types of the tensor-core path)."""
+    import torch
+
+    if dtype == torch.bfloat16:
+        return DT_BF16
+    if dtype == torch.float16:
+        return DT_F16
+    raise TypeError(f"not a 16-bit storage type of the native path: {dtype}")
+
+
+def storage_dtype(stride: int, mode: str = None, role: str = "head"):
+    """Storage policy of the tensor-core path.  "mixed" (default): the tensors of the HEAD at the
+    stride-4 level (head.csp, the level-0 towers: two thirds of the FLOPs behind a chain of fewer than ten layers) are bf16,
+    everything else - the backbone, the plan inputs, the neck, FFA and the coarser head levels, which sit behind 25-50
+    layers - is fp16.  bf16's 8-bit mantissa alone costs 2-4 % relative error against the fp32 reference along those
+    chains (BASELINE.json bounds it by 2e-2), fp16's 11 bits 0.1-0.5 %; tcgen05.mma kind::f16 takes either type at the
+    same rate.  fp16 stores saturate at +-65504 and flush below 6e-8: activations of a trained network are O(1), but an
+    untrained one whose activations collapse (the reference's own N(0, 0.02) init at width 1.0) needs "bf16".
+    GLSDET_STORAGE=bf16 | f16 forces one type everywhere.  `role`: "head" | "input" | "backbone"."""
+    import torch
+
+    mode = mode or os.environ.get("GLSDET_STORAGE", "mixed")
+    if mode == "bf16":
+        return torch.bfloat16
+    if mode == "f16":
+        return torch.float16
+    assert mode == "mixed", mode
+    return torch.bfloat16 if (stride <= 4 and role == "head") else torch.float16
 
 ACT_BY_NAME = {"none": ACT_NONE, "silu": ACT_SILU, "relu": ACT_RELU, "lrelu": ACT_LRELU}
 
@@ -43,6 +75,7 @@ class ConvDesc(C.Structure):
         ("src_shared_div", C.c_int32), ("patch_mode", C.c_int32),
         ("ksize_w", C.c_int32), ("src0_row_pitch", C.c_int64), ("src0_img_pitch", C.c_int64),
         ("out_plane_stride", C.c_int64),
+        ("src_dtype", C.c_int32), ("out_dtype", C.c_int32), ("post_dtype", C.c_int32),
     ]
 
 
@@ -85,6 +118,22 @@ SIGNATURES = {
                                                C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_nchw_f32_to_nhwc_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_nhwc_16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_patch_transpose_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "glsdet_nhwc_transpose_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_void_p]),
+    "glsdet_gather_bias_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_spp_maxpool_16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_se_gate_16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "glsdet_scale_pixel_shuffle_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_patch_transpose": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_void_p]),
     "glsdet_gather_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -118,6 +167,10 @@ SIGNATURES = {
                                                      C.c_void_p]),
     "glsdet_spp_maxpool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_focus_nchw_f32_to_nhwc_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                   C.c_int32, C.c_void_p]),
+    "glsdet_focus_u8_to_nhwc_16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
     "glsdet_focus_u8_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
     "glsdet_focus_nchw_f32_to_nhwc_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -174,7 +227,7 @@ def load():
         fn.argtypes = args
     if missing and not os.environ.get("GLSDET_ALLOW_PARTIAL_LIB"):
         raise NativeError(f"libglsdet_b200.so lacks symbols declared in include/glsdet_b200.h: {missing}")
-    if lib.glsdet_abi_version() != 1:
+    if lib.glsdet_abi_version() != 2:
         raise NativeError("libglsdet_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -38,13 +38,13 @@ def backbone_supported(base_channels: int) -> bool:
 class BackbonePlan:
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], device=None,
                  act: str = "silu", prefix: str = "backbone.backbone.", outs: Optional[Dict[str, torch.Tensor]] = None,
-                 precision: str = "bf16"):
+                 precision: str = "bf16", storage: Optional[str] = None):
         """`outs` optionally maps feature names ("dark2".."dark5") to existing NHWC tensors [B, H/s, W/s, C] (the input
         buffers of a neck plan); missing ones are allocated here.  `precision` "fp32" = the accuracy mode (every tensor
         fp32, SIMT fp32 convs of csrc/fp32_path.cu, fp32 Focus / pooling kernels)."""
         assert precision in ("bf16", "fp32")
         self.fp32 = precision == "fp32"
-        self.dtype = torch.float32 if self.fp32 else torch.bfloat16
+        self.storage = storage   # 16-bit storage policy (see _native.storage_dtype); None = GLSDET_STORAGE / "mixed"
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         self.B = batch
@@ -66,8 +66,11 @@ class BackbonePlan:
         self._build()
 
     # ------------------------------------------------------------------ helpers
+    def _dt(self, stride: int):
+        return torch.float32 if self.fp32 else N.storage_dtype(stride, self.storage, role="backbone")
+
     def _buf(self, name: str, stride: int, channels: int) -> torch.Tensor:
-        t = torch.empty((self.B, self.in_h // stride, self.in_w // stride, channels), dtype=self.dtype, device=self.device)
+        t = torch.empty((self.B, self.in_h // stride, self.in_w // stride, channels), dtype=self._dt(stride), device=self.device)
         self._bufs[name] = t
         return t
 
@@ -111,8 +114,8 @@ class BackbonePlan:
         if t is None:
             t = self._buf(name, stride, channels)
             self.outs[name] = t
-        assert tuple(t.shape) == (self.B, self.in_h // stride, self.in_w // stride, channels) and t.dtype == self.dtype, \
-            (name, tuple(t.shape))
+        assert tuple(t.shape) == (self.B, self.in_h // stride, self.in_w // stride, channels) and t.dtype == self._dt(stride), \
+            (name, tuple(t.shape), t.dtype)
         return t
 
     # ------------------------------------------------------------------ graph (CSPDarknet.forward, darknet.py:172-195)
@@ -132,7 +135,7 @@ class BackbonePlan:
         else:
             # kx taps folded into the channel view (K = 3 * 64): zero-bordered rows of 16-channel pixels, the conv reads
             # 64 consecutive elements = (pixel x-1 | x | x+1 | ignored) per ky tap
-            flat = torch.zeros(self.B * h2 * (w2 + 2) * 16 + 64, dtype=torch.bfloat16, device=self.device)
+            flat = torch.zeros(self.B * h2 * (w2 + 2) * 16 + 64, dtype=self._dt(2), device=self.device)
             self._bufs["focus"] = flat
             fv = FoldedView(flat, self.B, h2, w2, 16)
             self.focus = FocusOp(fv)

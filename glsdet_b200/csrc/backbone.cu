@@ -3,6 +3,7 @@
 //   * the three stride-1 max pools of SPPBottleneck (darknet.py:28,33-36) as a cascade of separable 5-wide maxima.
 // Both are HBM / shared-memory bound byte movers; the convolutions of the backbone run on conv_gemm_kernel.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <string.h>
 
@@ -10,6 +11,7 @@
 
 #include "../../include/glsdet_b200.h"
 #include "common.h"
+#include "ptx.cuh"
 
 namespace glsdet {
 
@@ -17,8 +19,8 @@ namespace glsdet {
 // dst[b, y, x, q*3 + c] = img[b, c, 2y + dy(q), 2x + dx(q)],  q = 0: top-left, 1: bottom-left, 2: top-right,
 // 3: bottom-right (the torch.cat order of darknet.py:16-20); channels 12..15 are zero so that a pixel is 32 bytes.
 // One thread per output pixel: six coalesced float2 loads (3 channels x 2 rows), two 16-byte stores.
-__global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ dst, int H, int W,
-                                                    int border, int64_t total) {
+__global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ img, uint16_t* __restrict__ dst, int H, int W,
+                                                    int border, int64_t total, int f16) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int Wo = W >> 1, Ho = H >> 1;
@@ -35,16 +37,16 @@ __global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ im
     const float2 r1 = __ldg(reinterpret_cast<const float2*>(p + c * plane + W));
     tl[c] = r0.x; tr[c] = r0.y; bl[c] = r1.x; br[c] = r1.y;
   }
-  __align__(16) __nv_bfloat16 o[16];
+  __align__(16) uint16_t o[16];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    o[c] = __float2bfloat16_rn(tl[c]);
-    o[3 + c] = __float2bfloat16_rn(bl[c]);
-    o[6 + c] = __float2bfloat16_rn(tr[c]);
-    o[9 + c] = __float2bfloat16_rn(br[c]);
+    o[c] = to_16(tl[c], f16);
+    o[3 + c] = to_16(bl[c], f16);
+    o[6 + c] = to_16(tr[c], f16);
+    o[9 + c] = to_16(br[c], f16);
   }
 #pragma unroll
-  for (int c = 12; c < 16; ++c) o[c] = __float2bfloat16_rn(0.f);
+  for (int c = 12; c < 16; ++c) o[c] = 0;
   // border = 1: rows of Wo + 2 pixels, pixel x lands at x + 1 (zero border pixels left and right)
   uint4* out = reinterpret_cast<uint4*>(dst + ((b * Ho + y) * (Wo + 2 * border) + x + border) * 16);
   out[0] = reinterpret_cast<const uint4*>(o)[0];
@@ -58,9 +60,9 @@ __global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ im
 // The input has 256 values per channel, so the host tabulates the three statements once (IEEE float / double arithmetic,
 // the same as numpy's) and the kernel only looks the bf16 results up.
 struct NormLut {
-  uint16_t v[3][256];   // bf16 bits of ((float(u) / 255.0f) - mean[c]) / std[c]
+  uint16_t v[3][256];   // bf16 (or fp16) bits of ((float(u) / 255.0f) - mean[c]) / std[c]
 };
-__global__ void __launch_bounds__(256) focus_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ dst, int H,
+__global__ void __launch_bounds__(256) focus_u8_kernel(const uint8_t* __restrict__ img, uint16_t* __restrict__ dst, int H,
                                                        int W, int border, const __grid_constant__ NormLut lut, int64_t total_pairs) {
   // one thread = two horizontally adjacent output pixels: 12 contiguous bytes per input row (three aligned 32-bit loads),
   // 24 table look-ups, 64 contiguous output bytes; persistent CTAs amortise the table copy
@@ -141,18 +143,28 @@ __device__ __forceinline__ uint4 max4f(uint4 a, uint4 b) {   // four fp32 values
   r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
   return r;
 }
-template <bool F32>
-__device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return F32 ? max4f(a, b) : max8(a, b); }
+__device__ __forceinline__ uint4 max8h(uint4 a, uint4 b) {   // eight fp16 values
+  uint4 r;
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(pa[i], pb[i]);
+  return r;
+}
+// KIND: 0 = bf16, 1 = fp32 (accuracy mode), 2 = fp16
+template <int KIND>
+__device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return KIND == 1 ? max4f(a, b) : KIND == 2 ? max8h(a, b) : max8(a, b); }
 
 // One CTA = one image x 8 channels (bf16; 4 channels in the fp32 accuracy mode: 16-byte vectors either way), the whole h x w map in shared memory (two ping-pong planes of 16-byte vectors).
 // MaxPool2d(k, 1, k/2) pads with -inf, i.e. the maximum runs over the in-bounds part of the window, and
 // pool9 = pool5(pool5), pool13 = pool5(pool9) exactly (maxima of nested windows), so three rounds of a separable
 // 5-wide maximum (row pass, column pass) produce the three outputs.
-template <bool F32>
+template <int KIND>
 __global__ void __launch_bounds__(1024) spp_pool_kernel(void* __restrict__ buf_v, int h, int w, int ld, int coff_src,
                                                         int coff5, int coff9, int coff13, int groups) {
-  using T = typename std::conditional<F32, float, __nv_bfloat16>::type;
-  constexpr int kVec = F32 ? 4 : 8;
+  using T = typename std::conditional<KIND == 1, float, uint16_t>::type;
+  constexpr int kVec = KIND == 1 ? 4 : 8;
   T* buf = reinterpret_cast<T*>(buf_v);
   extern __shared__ uint4 smem_pool[];
   uint4* a = smem_pool;
@@ -171,7 +183,7 @@ __global__ void __launch_bounds__(1024) spp_pool_kernel(void* __restrict__ buf_v
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int xx = x + d;
-        if (d != 0 && xx >= 0 && xx < w) m = vmax<F32>(m, a[y * w + xx]);
+        if (d != 0 && xx >= 0 && xx < w) m = vmax<KIND>(m, a[y * w + xx]);
       }
       t[i] = m;
     }
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(1024) spp_pool_kernel(void* __restrict__ buf_v
 #pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int yy = y + d;
-        if (d != 0 && yy >= 0 && yy < h) m = vmax<F32>(m, t[yy * w + x]);
+        if (d != 0 && yy >= 0 && yy < h) m = vmax<KIND>(m, t[yy * w + x]);
       }
       *reinterpret_cast<uint4*>(base + static_cast<int64_t>(i) * ld + coff) = m;
       // every thread rewrites only its own elements of `a`, and nobody reads `a` during this pass
@@ -197,6 +209,12 @@ __global__ void __launch_bounds__(1024) spp_pool_kernel(void* __restrict__ buf_v
 
 extern "C" int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t batch, int32_t height,
                                                   int32_t width, int32_t dst_border, void* stream) {
+  return glsdet_focus_nchw_f32_to_nhwc_16(image, dst, batch, height, width, dst_border, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_focus_nchw_f32_to_nhwc_16(const float* image, void* dst, int32_t batch, int32_t height,
+                                                int32_t width, int32_t dst_border, int32_t dtype, void* stream) {
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "focus: bad storage dtype");
   GLSDET_REQUIRE(image && dst && batch > 0 && height > 0 && width > 0 && (dst_border == 0 || dst_border == 1),
                  "focus: bad arguments");
   GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "focus: height and width must be even (got %d x %d)", height, width);
@@ -204,15 +222,15 @@ extern "C" int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst,
                  "focus: image must be 8-byte aligned and dst 16-byte aligned");
   const int64_t total = static_cast<int64_t>(batch) * (height / 2) * (width / 2);
   glsdet::focus_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      image, reinterpret_cast<__nv_bfloat16*>(dst), height, width, dst_border, total);
+      image, reinterpret_cast<uint16_t*>(dst), height, width, dst_border, total, static_cast<int>(dtype));
   return glsdet::count_launch("focus_kernel");
 }
 
 namespace {
-template <bool F32>
+template <int KIND>
 int spp_maxpool_impl(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld, int32_t src_coff,
                      int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
-  constexpr int kVec = F32 ? 4 : 8;
+  constexpr int kVec = KIND == 1 ? 4 : 8;
   GLSDET_REQUIRE(buf && batch > 0 && height > 0 && width > 0 && channels > 0, "spp_maxpool: bad arguments");
   GLSDET_REQUIRE((channels % kVec) == 0 && (ld % kVec) == 0 && (src_coff % kVec) == 0 && (coff5 % kVec) == 0 &&
                      (coff9 % kVec) == 0 && (coff13 % kVec) == 0,
@@ -229,13 +247,13 @@ int spp_maxpool_impl(void* buf, int32_t batch, int32_t height, int32_t width, in
   int dev = 0;
   GLSDET_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !attr_set[dev]) {
-    GLSDET_CHECK_CUDA(cudaFuncSetAttribute(glsdet::spp_pool_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GLSDET_CHECK_CUDA(cudaFuncSetAttribute(glsdet::spp_pool_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[dev] = true;
   }
   const int groups = channels / kVec;
   const int pixels = height * width;
   const int threads = pixels >= 1024 ? 1024 : ((pixels + 31) / 32) * 32;
-  glsdet::spp_pool_kernel<F32><<<static_cast<unsigned>(batch) * groups, threads, smem, static_cast<cudaStream_t>(stream)>>>(
+  glsdet::spp_pool_kernel<KIND><<<static_cast<unsigned>(batch) * groups, threads, smem, static_cast<cudaStream_t>(stream)>>>(
       buf, height, width, ld, src_coff, coff5, coff9, coff13, groups);
   return glsdet::count_launch("spp_pool_kernel");
 }
@@ -243,12 +261,21 @@ int spp_maxpool_impl(void* buf, int32_t batch, int32_t height, int32_t width, in
 
 extern "C" int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
                                   int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
-  return spp_maxpool_impl<false>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+  return spp_maxpool_impl<0>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+}
+
+extern "C" int glsdet_spp_maxpool_16(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                                     int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, int32_t dtype,
+                                     void* stream) {
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "spp_maxpool: bad storage dtype");
+  if (dtype == GLSDET_DT_F16)
+    return spp_maxpool_impl<2>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+  return spp_maxpool_impl<0>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
 }
 
 extern "C" int glsdet_spp_maxpool_f32(float* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
                                       int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream) {
-  return spp_maxpool_impl<true>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
+  return spp_maxpool_impl<1>(buf, batch, height, width, channels, ld, src_coff, coff5, coff9, coff13, stream);
 }
 
 extern "C" int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst, int32_t batch, int32_t height, int32_t width,
@@ -265,6 +292,13 @@ extern "C" int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst,
 
 extern "C" int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
                                             int32_t dst_border, const double* mean, const double* std, void* stream) {
+  return glsdet_focus_u8_to_nhwc_16(image, dst, batch, height, width, dst_border, mean, std, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_focus_u8_to_nhwc_16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                                          int32_t dst_border, const double* mean, const double* std, int32_t dtype,
+                                          void* stream) {
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "focus_u8: bad storage dtype");
   GLSDET_REQUIRE(image && dst && mean && std && batch > 0 && height > 0 && width > 0 && (dst_border == 0 || dst_border == 1),
                  "focus_u8: bad arguments");
   GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "focus_u8: height and width must be even (got %d x %d)", height, width);
@@ -277,10 +311,14 @@ extern "C" int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int
       v = static_cast<float>(static_cast<double>(v) - mean[c]);                // image -= float64 array  (double, rounded)
       v = static_cast<float>(static_cast<double>(v) / std[c]);                 // image /= float64 array
       const float f = v;
-      uint32_t bits;
-      memcpy(&bits, &f, 4);
-      bits += 0x7FFFu + ((bits >> 16) & 1u);                                   // round to nearest even (finite values)
-      lut.v[c][u] = static_cast<uint16_t>(bits >> 16);
+      if (dtype == GLSDET_DT_F16) {
+        lut.v[c][u] = __half_as_ushort(__float2half_rn(f));                    // round to nearest even
+      } else {
+        uint32_t bits;
+        memcpy(&bits, &f, 4);
+        bits += 0x7FFFu + ((bits >> 16) & 1u);                                 // round to nearest even (finite values)
+        lut.v[c][u] = static_cast<uint16_t>(bits >> 16);
+      }
     }
   }
   GLSDET_REQUIRE((width % 4) == 0 && (reinterpret_cast<uintptr_t>(image) & 3) == 0,
@@ -290,6 +328,6 @@ extern "C" int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int
   const int64_t cap = static_cast<int64_t>(glsdet::device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   glsdet::focus_u8_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      image, reinterpret_cast<__nv_bfloat16*>(dst), height, width, dst_border, lut, total_pairs);
+      image, reinterpret_cast<uint16_t*>(dst), height, width, dst_border, lut, total_pairs);
   return glsdet::count_launch("focus_u8_kernel");
 }

@@ -91,6 +91,9 @@ struct alignas(64) ConvKParams {
   int64_t out_plane;   // NCHW output: elements between channel planes (Ho * Wo, or the anchor count of all levels)
   float dec_stride, dec_in_w, dec_in_h;
   int32_t epi;   // EPI_* epilogue specialisation chosen at create time
+  int32_t a_f16;     // sources, weights (and the staged operand of the prediction MMA) are fp16 instead of bf16
+  int32_t out_f16;   // 16-bit NHWC output is fp16
+  int32_t post_f16;  // post-activation residual is fp16
   const float* pred_w;   // fused prediction conv: fp32 [pred_n][N]
   const float* pred_b;
   int32_t pred_n, pred_act;
@@ -155,6 +158,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// 16 fp32 values -> 16 stored 16-bit values (two 16-byte vectors); `f16` is warp-uniform (a kernel parameter)
+__device__ __forceinline__ void pack16_row(const float (&v)[16], int f16, uint4& a, uint4& c) {
+  if (f16) {
+    a.x = pack_f16x2(v[0], v[1]);  a.y = pack_f16x2(v[2], v[3]);
+    a.z = pack_f16x2(v[4], v[5]);  a.w = pack_f16x2(v[6], v[7]);
+    c.x = pack_f16x2(v[8], v[9]);  c.y = pack_f16x2(v[10], v[11]);
+    c.z = pack_f16x2(v[12], v[13]); c.w = pack_f16x2(v[14], v[15]);
+  } else {
+    a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
+    a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
+    c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
+    c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+  }
+}
+
 // Epilogue for 16 consecutive output channels [n_g, n_g+16) of one output pixel.
 // s_bias: shared-memory copy of the (zero-padded) bias, already offset to channel n_g.
 __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uint32_t (&raw)[16],
@@ -213,14 +231,16 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          v[h * 8 + q * 2] += __uint_as_float(w[q] << 16);
-          v[h * 8 + q * 2 + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+          float lo, hi;
+          unpack_16x2(w[q], p.post_f16, lo, hi);
+          v[h * 8 + q * 2] += lo;
+          v[h * 8 + q * 2 + 1] += hi;
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (n_g + j < p.N) v[j] += __bfloat162float(r[j]);
+        if (n_g + j < p.N) v[j] += from_16(reinterpret_cast<const uint16_t*>(r)[j], p.post_f16);
     }
   }
 
@@ -229,16 +249,13 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
                        (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + n_g;
     if (full && ((p.out_ld | p.out_coff) & 7) == 0) {
       uint4 a, c;
-      a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
-      a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
-      c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
-      c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+      pack16_row(v, p.out_f16, a, c);
       reinterpret_cast<uint4*>(o)[0] = a;
       reinterpret_cast<uint4*>(o)[1] = c;
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
-        if (n_g + j < p.N) o[j] = __float2bfloat16_rn(v[j]);
+        if (n_g + j < p.N) reinterpret_cast<uint16_t*>(o)[j] = to_16(v[j], p.out_f16);
     }
   } else if (p.out_mode == GLSDET_OUT_NHWC_F32) {
     float* o = reinterpret_cast<float*>(p.out) + static_cast<int64_t>(b) * p.out_bs +
@@ -266,7 +283,8 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
 // loops).  bf16 NHWC output of 16 channels = two 16-byte stores.
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, int act,
-                                           const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1) {
+                                           const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1,
+                                           int dt) {   // dt: bit 0 = fp16 output, bit 1 = fp16 post residual
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
@@ -298,25 +316,32 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
     for (int h = 0; h < 2; ++h) {
       const uint4 t = __ldg(reinterpret_cast<const uint4*>(post) + h);
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+      if (dt & 2) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        v[h * 8 + q * 2] += __uint_as_float(w[q] << 16);
-        v[h * 8 + q * 2 + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        for (int q = 0; q < 4; ++q) {
+          float lo, hi;
+          unpack_f16x2(w[q], lo, hi);
+          v[h * 8 + q * 2] += lo;
+          v[h * 8 + q * 2 + 1] += hi;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[h * 8 + q * 2] += __uint_as_float(w[q] << 16);
+          v[h * 8 + q * 2 + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+        }
       }
     }
   }
   uint4 a, c;
-  a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);
-  a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
-  c.x = pack_bf16x2(v[8], v[9]);  c.y = pack_bf16x2(v[10], v[11]);
-  c.z = pack_bf16x2(v[12], v[13]); c.w = pack_bf16x2(v[14], v[15]);
+  pack16_row(v, dt & 1, a, c);
   *o0 = a;
   *o1 = c;
 }
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, int act,
-                                           const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o) {
-  epi16_bf16<PRE, POST>(raw, s_bias, act, pre, post, reinterpret_cast<uint4*>(o), reinterpret_cast<uint4*>(o) + 1);
+                                           const float* pre, const __nv_bfloat16* post, __nv_bfloat16* o, int dt) {
+  epi16_bf16<PRE, POST>(raw, s_bias, act, pre, post, reinterpret_cast<uint4*>(o), reinterpret_cast<uint4*>(o) + 1, dt);
 }
 
 // bias only, fp32 NHWC, 16 channels = four 16-byte stores (low-resolution partial sums)
@@ -446,6 +471,7 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
     }
     int cb = g.wide ? kc * 4 : half * 2;
     int ce = g.wide ? kc * 4 + 4 : half * 2 + 2;
+    const int dt = p.out_f16 | (p.post_f16 << 1);
     if (g.parts == 4) {   // 32 columns per warp (block_n 128) or 16 (block_n 64)
       cb = g.wide ? kc * 4 + (half & 1) * 2 : half;
       ce = g.wide ? cb + 2 : half + 1;
@@ -455,7 +481,7 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
         const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte staging row
         epi16_bf16<PRE, POST>(raw, sb + c * 16, act, PRE ? pre + c * 16 : nullptr, POST ? post + c * 16 : nullptr,
                               reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)),
-                              reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)));
+                              reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)), dt);
       }
     });
     fence_proxy_async_smem();
@@ -560,7 +586,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       const float v = (ng < p.pred_n && k < p.N) ? __ldg(p.pred_w + static_cast<int64_t>(ng) * p.N + k) : 0.0f;
       const int kc = k >> 6, kk = k & 63;
       const int off = kc * kPredTileBytes + (n >> 3) * 1024 + (n & 7) * kRowBytes + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(smem_pw + off) = __float2bfloat16_rn(v);
+      *reinterpret_cast<uint16_t*>(smem_pw + off) = to_16(v, p.a_f16);
     }
     fence_proxy_async_smem();
   }
@@ -620,7 +646,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
     // issues.  A divergent single-lane loop costs a register->uniform-register move per operand of every MMA.
     if (cta_rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(2 * kBlockM, static_cast<uint32_t>(p.block_n));
+      const uint32_t idesc = umma_idesc_16(2 * kBlockM, static_cast<uint32_t>(p.block_n), p.a_f16 != 0);
       const int a_sub_bytes = kRowBytes << p.tile_w_log2;
       int s = 0;
       uint32_t ph = 0;
@@ -749,7 +775,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     }
   } else if (!k2 && warp == 1) {
     // ------------------------------------------------------------ MMA issuer (whole warp, one elected lane issues)
-    const uint32_t idesc = umma_idesc_bf16(kBlockM, static_cast<uint32_t>(p.block_n));
+    const uint32_t idesc = umma_idesc_16(kBlockM, static_cast<uint32_t>(p.block_n), p.a_f16 != 0);
     const int a_sub_bytes = kRowBytes << p.tile_w_log2;  // tile_w rows
     const int a_m_bytes = p.tile_h * a_sub_bytes;         // distance between the M tiles of a work item
     int sa = 0, sb = 0;
@@ -915,23 +941,24 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
             break;
           }
           if constexpr (EC == EC_ALL || EC == EC_BF16) {
+          const int dtf = p.out_f16 | (p.post_f16 << 1);
           __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<int64_t>(t.b) * p.out_bs +
                                 (static_cast<int64_t>(oy) * p.Wo + ox) * p.out_ld + p.out_coff + t.n0;
           if (has_pre && has_post) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, true>(raw, sb + c * 16, p.act_epi, pre + c * 16, post + c * 16, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, true>(raw, sb + c * 16, p.act_epi, pre + c * 16, post + c * 16, orow + c * 16, dtf);
             });
           } else if (has_pre) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, false>(raw, sb + c * 16, p.act_epi, pre + c * 16, nullptr, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<true, false>(raw, sb + c * 16, p.act_epi, pre + c * 16, nullptr, orow + c * 16, dtf);
             });
           } else if (has_post) {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, true>(raw, sb + c * 16, p.act_epi, nullptr, post + c * 16, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, true>(raw, sb + c * 16, p.act_epi, nullptr, post + c * 16, orow + c * 16, dtf);
             });
           } else {
             epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
-              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, p.act_epi, nullptr, nullptr, orow + c * 16);
+              if (valid && t.n0 + c * 16 < p.N) epi16_bf16<false, false>(raw, sb + c * 16, p.act_epi, nullptr, nullptr, orow + c * 16, dtf);
             });
           }
           }  // direct stores
@@ -1054,10 +1081,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
             }
             uint4 lo, hi;
-            lo.x = pack_bf16x2(v[0], v[1]);  lo.y = pack_bf16x2(v[2], v[3]);
-            lo.z = pack_bf16x2(v[4], v[5]);  lo.w = pack_bf16x2(v[6], v[7]);
-            hi.x = pack_bf16x2(v[8], v[9]);  hi.y = pack_bf16x2(v[10], v[11]);
-            hi.z = pack_bf16x2(v[12], v[13]); hi.w = pack_bf16x2(v[14], v[15]);
+            pack16_row(v, p.a_f16, lo, hi);
             uint8_t* rowp = smem_stage + (c >> 2) * kStageTileBytes + (r >> 3) * 1024 + (r & 7) * kRowBytes;
             const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte row
             *reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)) = lo;
@@ -1077,7 +1101,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
                 mbar_wait(pstage_bar, tcount & 1u);
                 tc_fence_after();
                 if (elect_one()) {
-                  const uint32_t idesc_p = umma_idesc_bf16(2 * kBlockM, 16);
+                  const uint32_t idesc_p = umma_idesc_16(2 * kBlockM, 16, p.a_f16 != 0);
                   const uint32_t d_pred = tmem_base + tcol;
                   for (int kc = 0; kc < k_tiles; ++kc) {
                     const uint64_t da = umma_desc_k_sw128(smem_u32(smem_stage + kc * kStageTileBytes));
@@ -1095,7 +1119,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           } else if (e == 0) {
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t idesc_p = umma_idesc_bf16(kBlockM, 16);
+              const uint32_t idesc_p = umma_idesc_16(kBlockM, 16, p.a_f16 != 0);
               const uint32_t d_pred = tmem_base + tcol;
               for (int kc = 0; kc < k_tiles; ++kc) {
                 const uint64_t da = umma_desc_k_sw128(smem_u32(smem_stage + kc * kStageTileBytes));
@@ -1324,6 +1348,8 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   GLSDET_REQUIRE(d->src0 && d->weight && d->out, "conv_create: null src0/weight/out pointer");
   GLSDET_REQUIRE(d->out_mode >= 0 && d->out_mode <= 2, "conv_create: bad out_mode %d", d->out_mode);
   GLSDET_REQUIRE(d->act >= 0 && d->act <= GLSDET_ACT_YOLOX_BOX, "conv_create: bad act %d", d->act);  // MMDET_BOX: fused preds only
+  GLSDET_REQUIRE((d->src_dtype | d->out_dtype | d->post_dtype) >= 0 && d->src_dtype <= GLSDET_DT_F16 &&
+                     d->out_dtype <= GLSDET_DT_F16 && d->post_dtype <= GLSDET_DT_F16, "conv_create: bad storage dtype");
   if (d->pred_weight != nullptr) {
     GLSDET_REQUIRE(d->pred_bias != nullptr && d->pred_channels >= 1 && d->pred_channels <= 16,
                    "conv_create: fused prediction conv needs a bias and 1..16 channels");
@@ -1554,9 +1580,16 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   k.patch = patch ? 1 : 0;
 
   k.bias = d->bias; k.act = d->act;
-  k.act_epi = (d->act == GLSDET_ACT_SILU && getenv("GLSDET_CONV_EXACT_SILU") != nullptr) ? kActSiluExact : d->act;
+  // tanh.approx SiLU (relative error 2^-11) sits below the bf16 rounding of the stored value but is as large as the fp16
+  // rounding: layers that store (or stage, for the fused prediction conv) fp16 use the ex2 + rcp form.  Those are the
+  // coarse levels, a fraction of the pixels, so the longer epilogue does not pace the step.
+  const bool f16_store = (d->pred_weight != nullptr) ? d->src_dtype == GLSDET_DT_F16
+                                                     : (d->out_mode == GLSDET_OUT_NHWC_BF16 && d->out_dtype == GLSDET_DT_F16);
+  const bool exact_silu = getenv("GLSDET_CONV_EXACT_SILU") != nullptr || (f16_store && getenv("GLSDET_CONV_FAST_SILU_F16") == nullptr);
+  k.act_epi = (d->act == GLSDET_ACT_SILU && exact_silu) ? kActSiluExact : d->act;
   k.pre_res = d->pre_res; k.pre_shift = d->pre_shift; k.pre_ld = d->pre_ld;
   k.post_res = reinterpret_cast<const __nv_bfloat16*>(d->post_res); k.post_shift = d->post_shift; k.post_ld = d->post_ld;
+  k.a_f16 = d->src_dtype == GLSDET_DT_F16; k.out_f16 = d->out_dtype == GLSDET_DT_F16; k.post_f16 = d->post_dtype == GLSDET_DT_F16;
   k.out = d->out; k.out_mode = d->out_mode; k.out_ld = d->out_ld; k.out_coff = d->out_coff; k.out_bs = d->out_batch_stride;
   k.out_plane = d->out_plane_stride > 0 ? d->out_plane_stride : static_cast<int64_t>(g.Ho) * g.Wo;
   k.dec_stride = d->dec_stride; k.dec_in_w = d->dec_in_w; k.dec_in_h = d->dec_in_h;

@@ -14,8 +14,8 @@ constexpr int kTC = 64;  // channels per transpose tile (64 bf16 = 128 bytes on 
 constexpr int kTP = 32;  // pixels per transpose tile   (32 fp32 = 128 bytes on the NCHW side)
 
 // [B, C, HW] fp32 -> [B, HW, ld] bf16 (channels coff..coff+C)
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                           int C, int HW, int ld, int coff) {
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                                           int C, int HW, int ld, int coff, int f16) {
   pdl_prologue();
   __shared__ float tile[kTC][kTP + 1];
   const int p0 = blockIdx.x * kTP, c0 = blockIdx.y * kTC, b = blockIdx.z;
@@ -31,39 +31,36 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   const int pl = threadIdx.x >> 3, cv = threadIdx.x & 7;  // 32 pixels x 8 vectors of 8 channels
   const int p = p0 + pl, c = c0 + cv * 8;
   if (p < HW && c < C) {
-    __nv_bfloat16* o = dst + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
+    uint16_t* o = dst + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
     if (c + 8 <= C && ((ld | coff) & 7) == 0) {
       uint4 v;
-      v.x = pack_bf16x2(tile[cv * 8 + 0][pl], tile[cv * 8 + 1][pl]);
-      v.y = pack_bf16x2(tile[cv * 8 + 2][pl], tile[cv * 8 + 3][pl]);
-      v.z = pack_bf16x2(tile[cv * 8 + 4][pl], tile[cv * 8 + 5][pl]);
-      v.w = pack_bf16x2(tile[cv * 8 + 6][pl], tile[cv * 8 + 7][pl]);
+      v.x = pack_16x2(tile[cv * 8 + 0][pl], tile[cv * 8 + 1][pl], f16);
+      v.y = pack_16x2(tile[cv * 8 + 2][pl], tile[cv * 8 + 3][pl], f16);
+      v.z = pack_16x2(tile[cv * 8 + 4][pl], tile[cv * 8 + 5][pl], f16);
+      v.w = pack_16x2(tile[cv * 8 + 6][pl], tile[cv * 8 + 7][pl], f16);
       *reinterpret_cast<uint4*>(o) = v;
     } else {
-      for (int j = 0; j < 8 && c + j < C; ++j) o[j] = __float2bfloat16_rn(tile[cv * 8 + j][pl]);
+      for (int j = 0; j < 8 && c + j < C; ++j) o[j] = to_16(tile[cv * 8 + j][pl], f16);
     }
   }
 }
 
 // [B, HW, ld] bf16 (channels coff..coff+C) -> [B, C, HW] fp32
-__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
-                                                           int C, int HW, int ld, int coff) {
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst,
+                                                           int C, int HW, int ld, int coff, int f16) {
   __shared__ float tile[kTC][kTP + 1];
   const int p0 = blockIdx.x * kTP, c0 = blockIdx.y * kTC, b = blockIdx.z;
   const int pl = threadIdx.x >> 3, cv = threadIdx.x & 7;
   const int p = p0 + pl, c = c0 + cv * 8;
   if (p < HW && c < C) {
-    const __nv_bfloat16* s = src + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
+    const uint16_t* s = src + (static_cast<int64_t>(b) * HW + p) * ld + coff + c;
     if (c + 8 <= C && ((ld | coff) & 7) == 0) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(s));
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        tile[cv * 8 + 2 * q][pl] = __uint_as_float(w[q] << 16);
-        tile[cv * 8 + 2 * q + 1][pl] = __uint_as_float(w[q] & 0xFFFF0000u);
-      }
+      for (int q = 0; q < 4; ++q) unpack_16x2(w[q], f16, tile[cv * 8 + 2 * q][pl], tile[cv * 8 + 2 * q + 1][pl]);
     } else {
-      for (int j = 0; j < 8; ++j) tile[cv * 8 + j][pl] = (c + j < C) ? __bfloat162float(s[j]) : 0.0f;
+      for (int j = 0; j < 8; ++j) tile[cv * 8 + j][pl] = (c + j < C) ? from_16(s[j], f16) : 0.0f;
     }
   }
   __syncthreads();
@@ -79,8 +76,8 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const __nv_bfloat16* 
 
 // ---------------------------------------------------------------------------------------------- SE gate
 // stage 1: per (image, slab of pixels) channel sums, fixed summation order (deterministic)
-__global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ scratch,
-                                                         int HW, int C, int ld) {
+__global__ void __launch_bounds__(256) se_partial_kernel(const uint16_t* __restrict__ x, float* __restrict__ scratch,
+                                                         int HW, int C, int ld, int f16) {
   pdl_prologue();
   extern __shared__ float red[];  // [rows_par][C]
   const int slab = blockIdx.x, b = blockIdx.y;
@@ -101,8 +98,10 @@ __global__ void __launch_bounds__(256) se_partial_kernel(const __nv_bfloat16* __
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          acc[2 * q] += __uint_as_float(w[q] << 16);
-          acc[2 * q + 1] += __uint_as_float(w[q] & 0xFFFF0000u);
+          float lo, hi;
+          unpack_16x2(w[q], f16, lo, hi);
+          acc[2 * q] += lo;
+          acc[2 * q + 1] += hi;
         }
       }
 #pragma unroll
@@ -150,10 +149,10 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ sc
 }
 
 // dst[b, 2y+i, 2x+j, coff + c] = x[b, y, x, (2i+j)*Cout + c] * gate[b, (2i+j)*Cout + c]
-__global__ void __launch_bounds__(256) scale_shuffle_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256) scale_shuffle_kernel(const uint16_t* __restrict__ x,
                                                             const float* __restrict__ gate,
-                                                            __nv_bfloat16* __restrict__ dst, int B, int H, int W,
-                                                            int Cout, int ld, int coff) {
+                                                            uint16_t* __restrict__ dst, int B, int H, int W,
+                                                            int Cout, int ld, int coff, int xf16, int df16) {
   pdl_prologue();
   const int vec_per_pix = (4 * Cout) >> 3;
   const int64_t total = static_cast<int64_t>(B) * H * W * vec_per_pix;
@@ -171,12 +170,17 @@ __global__ void __launch_bounds__(256) scale_shuffle_kernel(const __nv_bfloat16*
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<int64_t>(b) * 4 * Cout + vec * 8));
     const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + static_cast<int64_t>(b) * 4 * Cout + vec * 8) + 1);
     uint4 o;
-    o.x = pack_bf16x2(__uint_as_float(v.x << 16) * g0.x, __uint_as_float(v.x & 0xFFFF0000u) * g0.y);
-    o.y = pack_bf16x2(__uint_as_float(v.y << 16) * g0.z, __uint_as_float(v.y & 0xFFFF0000u) * g0.w);
-    o.z = pack_bf16x2(__uint_as_float(v.z << 16) * g1.x, __uint_as_float(v.z & 0xFFFF0000u) * g1.y);
-    o.w = pack_bf16x2(__uint_as_float(v.w << 16) * g1.z, __uint_as_float(v.w & 0xFFFF0000u) * g1.w);
+    float a0, a1, a2, a3, a4, a5, a6, a7;
+    unpack_16x2(v.x, xf16, a0, a1);
+    unpack_16x2(v.y, xf16, a2, a3);
+    unpack_16x2(v.z, xf16, a4, a5);
+    unpack_16x2(v.w, xf16, a6, a7);
+    o.x = pack_16x2(a0 * g0.x, a1 * g0.y, df16);
+    o.y = pack_16x2(a2 * g0.z, a3 * g0.w, df16);
+    o.z = pack_16x2(a4 * g1.x, a5 * g1.y, df16);
+    o.w = pack_16x2(a6 * g1.z, a7 * g1.w, df16);
     const int oy = 2 * yy + (ij >> 1), ox = 2 * xx + (ij & 1);
-    __nv_bfloat16* d = dst + ((static_cast<int64_t>(b) * 2 * H + oy) * (2 * W) + ox) * ld + coff + cv * 8;
+    uint16_t* d = dst + ((static_cast<int64_t>(b) * 2 * H + oy) * (2 * W) + ox) * ld + coff + cv * 8;
     *reinterpret_cast<uint4*>(d) = o;
   }
 }
@@ -255,33 +259,54 @@ using namespace glsdet;
 extern "C" int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int32_t channels,
                                             int32_t height, int32_t width, int32_t dst_ld, int32_t dst_coff,
                                             void* stream) {
+  return glsdet_nchw_f32_to_nhwc_16(src, dst, batch, channels, height, width, dst_ld, dst_coff, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_nchw_f32_to_nhwc_16(const float* src, void* dst, int32_t batch, int32_t channels,
+                                          int32_t height, int32_t width, int32_t dst_ld, int32_t dst_coff,
+                                          int32_t dtype, void* stream) {
   GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0 && height > 0 && width > 0, "nchw_to_nhwc: bad arguments");
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "nchw_to_nhwc: bad storage dtype");
   GLSDET_REQUIRE(dst_coff >= 0 && dst_coff + channels <= dst_ld, "nchw_to_nhwc: channel window exceeds pitch");
   const int HW = height * width;
   dim3 grid((HW + kTP - 1) / kTP, (channels + kTC - 1) / kTC, batch);
   GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nchw_to_nhwc: grid too large");
   launch_pdl(nchw_to_nhwc_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), 
-      src, reinterpret_cast<__nv_bfloat16*>(dst), channels, HW, dst_ld, dst_coff);
+      src, reinterpret_cast<uint16_t*>(dst), channels, HW, dst_ld, dst_coff, static_cast<int>(dtype));
   return count_launch("nchw_to_nhwc_kernel");
 }
 
 extern "C" int glsdet_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels,
                                             int32_t height, int32_t width, int32_t src_ld, int32_t src_coff,
                                             void* stream) {
+  return glsdet_nhwc_16_to_nchw_f32(src, dst, batch, channels, height, width, src_ld, src_coff, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_nhwc_16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels,
+                                          int32_t height, int32_t width, int32_t src_ld, int32_t src_coff,
+                                          int32_t dtype, void* stream) {
   GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0 && height > 0 && width > 0, "nhwc_to_nchw: bad arguments");
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "nhwc_to_nchw: bad storage dtype");
   GLSDET_REQUIRE(src_coff >= 0 && src_coff + channels <= src_ld, "nhwc_to_nchw: channel window exceeds pitch");
   const int HW = height * width;
   dim3 grid((HW + kTP - 1) / kTP, (channels + kTC - 1) / kTC, batch);
   GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nhwc_to_nchw: grid too large");
   nhwc_to_nchw_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), dst, channels, HW, src_ld, src_coff);
+      reinterpret_cast<const uint16_t*>(src), dst, channels, HW, src_ld, src_coff, static_cast<int>(dtype));
   return count_launch("nhwc_to_nchw_kernel");
 }
 
 extern "C" int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld,
                               const float* w1, const float* w2, int32_t hidden, float* scratch, float* gate,
                               void* stream) {
+  return glsdet_se_gate_16(x, batch, hw, channels, x_ld, w1, w2, hidden, scratch, gate, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_se_gate_16(const void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld,
+                                 const float* w1, const float* w2, int32_t hidden, float* scratch, float* gate,
+                                 int32_t x_dtype, void* stream) {
   GLSDET_REQUIRE(x && w1 && w2 && scratch && gate, "se_gate: null pointer");
+  GLSDET_REQUIRE(x_dtype == GLSDET_DT_BF16 || x_dtype == GLSDET_DT_F16, "se_gate: bad storage dtype");
   GLSDET_REQUIRE(batch > 0 && hw > 0 && channels > 0 && hidden > 0, "se_gate: bad sizes");
   GLSDET_REQUIRE((channels % 8) == 0 && (x_ld % 8) == 0 && x_ld >= channels, "se_gate: channels/pitch must be multiples of 8");
   const int nvec = channels / 8;
@@ -290,8 +315,8 @@ extern "C" int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t 
   const size_t smem1 = static_cast<size_t>(rows_par) * channels * sizeof(float);
   GLSDET_REQUIRE(smem1 <= 48 * 1024, "se_gate: too many channels (%d)", channels);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  launch_pdl(se_partial_kernel, dim3(GLSDET_SE_SLABS, batch), 256, smem1, st, reinterpret_cast<const __nv_bfloat16*>(x), scratch,
-                                                                     hw, channels, x_ld);
+  launch_pdl(se_partial_kernel, dim3(GLSDET_SE_SLABS, batch), 256, smem1, st, reinterpret_cast<const uint16_t*>(x), scratch,
+             hw, channels, x_ld, static_cast<int>(x_dtype));
   if (int rc = count_launch("se_partial_kernel")) return rc;
   const size_t smem2 = static_cast<size_t>(channels + hidden) * sizeof(float);
   launch_pdl(se_fc_kernel, batch, 256, smem2, st, scratch, w1, w2, gate, hw, channels, hidden);
@@ -310,7 +335,16 @@ extern "C" int glsdet_se_fc(const float* scratch, const float* w1, const float* 
 extern "C" int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
                                           int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
                                           void* stream) {
+  return glsdet_scale_pixel_shuffle_16(x, gate, dst, batch, height, width, out_channels, dst_ld, dst_coff, GLSDET_DT_BF16,
+                                       GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_scale_pixel_shuffle_16(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
+                                             int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
+                                             int32_t x_dtype, int32_t dst_dtype, void* stream) {
   GLSDET_REQUIRE(x && gate && dst, "scale_pixel_shuffle: null pointer");
+  GLSDET_REQUIRE((x_dtype == GLSDET_DT_BF16 || x_dtype == GLSDET_DT_F16) && (dst_dtype == GLSDET_DT_BF16 || dst_dtype == GLSDET_DT_F16),
+                 "scale_pixel_shuffle: bad storage dtype");
   GLSDET_REQUIRE(batch > 0 && height > 0 && width > 0 && out_channels > 0, "scale_pixel_shuffle: bad sizes");
   GLSDET_REQUIRE((out_channels % 8) == 0 && (dst_ld % 8) == 0 && (dst_coff % 8) == 0 && dst_coff + out_channels <= dst_ld,
                  "scale_pixel_shuffle: channels/pitch/offset must be multiples of 8");
@@ -319,8 +353,8 @@ extern "C" int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   launch_pdl(scale_shuffle_kernel, static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(x), gate, reinterpret_cast<__nv_bfloat16*>(dst), batch, height, width,
-      out_channels, dst_ld, dst_coff);
+      reinterpret_cast<const uint16_t*>(x), gate, reinterpret_cast<uint16_t*>(dst), batch, height, width,
+      out_channels, dst_ld, dst_coff, static_cast<int>(x_dtype), static_cast<int>(dst_dtype));
   return count_launch("scale_shuffle_kernel");
 }
 
@@ -384,8 +418,9 @@ namespace glsdet {
 // written once at plan build time and never touched here.  PAIR: one thread per two pixels of a row (needs an even
 // patch width so that a pair never straddles two patches), else one thread per pixel.
 template <bool PAIR>
-__global__ void __launch_bounds__(256) patch_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                              int C, int H, int W, int rows, int t_ld) {
+__global__ void __launch_bounds__(256) patch_transpose_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                                              int C, int H, int W, int rows, int t_ld, int f16,
+                                                              float scale) {
   const int h2 = H >> 1, w2 = W >> 1;
   const int b = blockIdx.y;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -399,30 +434,37 @@ __global__ void __launch_bounds__(256) patch_transpose_kernel(const float* __res
   const int py = y >= h2, px = x >= w2;
   const int bp = (b * 2 + py) * 2 + px;
   const int t = (y - py * h2) * w2 + (x - px * w2);
-  __nv_bfloat16* o = dst + (static_cast<int64_t>(bp) * rows + c) * t_ld + t;
+  uint16_t* o = dst + (static_cast<int64_t>(bp) * rows + c) * t_ld + t;
   if (PAIR) {
     const float2 v = __ldg(reinterpret_cast<const float2*>(s));
-    *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<uint32_t*>(o) = pack_16x2(v.x * scale, v.y * scale, f16);
   } else {
-    *o = __float2bfloat16_rn(__ldg(s));
+    *o = to_16(__ldg(s) * scale, f16);
   }
 }
 
 // bias[b'][n] = base[n] + w[b'][n][col]  (the bias column of the per-patch effective weight matrix)
-__global__ void __launch_bounds__(256) gather_bias_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ base,
+__global__ void __launch_bounds__(256) gather_bias_kernel(const uint16_t* __restrict__ w, const float* __restrict__ base,
                                                           float* __restrict__ bias, int n_rows, int ld, int col,
-                                                          int64_t batch_stride, int base_groups, int total) {
+                                                          int64_t batch_stride, int base_groups, int total, int f16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = i / n_rows, n = i - b * n_rows;
-  bias[i] = base[(b % base_groups) * n_rows + n] + __bfloat162float(w[static_cast<int64_t>(b) * batch_stride + static_cast<int64_t>(n) * ld + col]);
+  bias[i] = base[(b % base_groups) * n_rows + n] + from_16(w[static_cast<int64_t>(b) * batch_stride + static_cast<int64_t>(n) * ld + col], f16);
 }
 
 }  // namespace glsdet
 
 extern "C" int glsdet_patch_transpose(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
                                       int32_t width, int32_t dst_rows, int32_t dst_ld, void* stream) {
+  return glsdet_patch_transpose_16(src, dst, batch, channels, height, width, dst_rows, dst_ld, GLSDET_DT_BF16, 1.0f, stream);
+}
+
+extern "C" int glsdet_patch_transpose_16(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                                         int32_t width, int32_t dst_rows, int32_t dst_ld, int32_t dtype, float scale,
+                                         void* stream) {
   GLSDET_REQUIRE(src && dst && batch > 0 && channels > 0, "patch_transpose: bad arguments");
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "patch_transpose: bad storage dtype");
   GLSDET_REQUIRE((height % 2) == 0 && (width % 2) == 0, "patch_transpose: height and width must be even "
                  "(equal 2x2 patches; odd splits of Non_local_family.py:230-233 are not supported)");
   GLSDET_REQUIRE(dst_rows >= channels && dst_ld >= (height / 2) * (width / 2) && (dst_ld % 2) == 0,
@@ -432,20 +474,28 @@ extern "C" int glsdet_patch_transpose(const float* src, void* dst, int32_t batch
   dim3 grid(static_cast<unsigned>((n + 255) / 256), batch);
   if (pair)
     glsdet::patch_transpose_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, reinterpret_cast<__nv_bfloat16*>(dst), channels, height, width, dst_rows, dst_ld);
+        src, reinterpret_cast<uint16_t*>(dst), channels, height, width, dst_rows, dst_ld, static_cast<int>(dtype), scale);
   else
     glsdet::patch_transpose_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, reinterpret_cast<__nv_bfloat16*>(dst), channels, height, width, dst_rows, dst_ld);
+        src, reinterpret_cast<uint16_t*>(dst), channels, height, width, dst_rows, dst_ld, static_cast<int>(dtype), scale);
   return glsdet::count_launch("patch_transpose_kernel");
 }
 
 extern "C" int glsdet_gather_bias(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows,
                                   int32_t ld, int32_t col, int64_t batch_stride, int32_t base_groups, void* stream) {
+  return glsdet_gather_bias_16(w, base, bias, batch, n_rows, ld, col, batch_stride, base_groups, GLSDET_DT_BF16, stream);
+}
+
+extern "C" int glsdet_gather_bias_16(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows,
+                                     int32_t ld, int32_t col, int64_t batch_stride, int32_t base_groups, int32_t dtype,
+                                     void* stream) {
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "gather_bias: bad storage dtype");
   GLSDET_REQUIRE(w && base && bias && batch > 0 && n_rows > 0 && col >= 0 && col < ld && base_groups > 0,
                  "gather_bias: bad arguments");
   const int total = batch * n_rows;
   glsdet::gather_bias_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(w), base, bias, n_rows, ld, col, batch_stride, base_groups, total);
+      reinterpret_cast<const uint16_t*>(w), base, bias, n_rows, ld, col, batch_stride, base_groups, total,
+      static_cast<int>(dtype));
   return glsdet::count_launch("gather_bias_kernel");
 }
 
@@ -520,14 +570,18 @@ __global__ void __launch_bounds__(256) rect_copy_kernel(const __nv_bfloat16* __r
 }
 
 // [B, T, ld] bf16 (channels coff..coff+C) -> [B, rows, t_ld] bf16 with dst[b][c][t] = src[b][t][c]; 32 x 32 smem tiles
-__global__ void __launch_bounds__(256) nhwc_transpose_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                                             int T, int C, int sld, int scoff, int rows, int t_ld) {
-  __shared__ __nv_bfloat16 tile[32][34];
+// `scaled`: elements are converted, multiplied by `scale` and rounded again (f16: dtype flag); else a plain 16-bit copy
+__global__ void __launch_bounds__(256) nhwc_transpose_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst,
+                                                             int T, int C, int sld, int scoff, int rows, int t_ld,
+                                                             int scaled, int f16, float scale) {
+  __shared__ uint16_t tile[32][34];
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32, b = blockIdx.z;
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   for (int i = ly; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + lx;
-    tile[i][lx] = (t < T && c < C) ? src[(static_cast<int64_t>(b) * T + t) * sld + scoff + c] : __float2bfloat16_rn(0.0f);
+    uint16_t v = (t < T && c < C) ? src[(static_cast<int64_t>(b) * T + t) * sld + scoff + c] : static_cast<uint16_t>(0);
+    if (scaled) v = to_16(from_16(v, f16) * scale, f16);
+    tile[i][lx] = v;
   }
   __syncthreads();
   for (int i = ly; i < 32; i += 8) {
@@ -567,12 +621,20 @@ extern "C" int glsdet_rect_copy(const void* src, int32_t src_h, int32_t src_w, i
 
 extern "C" int glsdet_nhwc_transpose(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels,
                                      int32_t src_ld, int32_t src_coff, int32_t dst_rows, int32_t dst_ld, void* stream) {
+  return glsdet_nhwc_transpose_16(src, dst, batch, pixels, channels, src_ld, src_coff, dst_rows, dst_ld, GLSDET_DT_BF16, 1.0f,
+                                  stream);
+}
+
+extern "C" int glsdet_nhwc_transpose_16(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels,
+                                        int32_t src_ld, int32_t src_coff, int32_t dst_rows, int32_t dst_ld, int32_t dtype,
+                                        float scale, void* stream) {
+  GLSDET_REQUIRE(dtype == GLSDET_DT_BF16 || dtype == GLSDET_DT_F16, "nhwc_transpose: bad storage dtype");
   GLSDET_REQUIRE(src && dst && batch > 0 && pixels > 0 && channels > 0, "nhwc_transpose: bad arguments");
   GLSDET_REQUIRE(src_coff + channels <= src_ld && dst_rows >= channels && dst_ld >= pixels, "nhwc_transpose: sizes");
   dim3 grid((pixels + 31) / 32, (channels + 31) / 32, batch);
   GLSDET_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "nhwc_transpose: grid too large");
   glsdet::nhwc_transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), pixels, channels, src_ld, src_coff,
-      dst_rows, dst_ld);
+      reinterpret_cast<const uint16_t*>(src), reinterpret_cast<uint16_t*>(dst), pixels, channels, src_ld, src_coff,
+      dst_rows, dst_ld, scale != 1.0f ? 1 : 0, static_cast<int>(dtype), scale);
   return glsdet::count_launch("nhwc_transpose_kernel");
 }

@@ -169,6 +169,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// same with the operand format chosen at run time: A and B both fp16 (format code 0) or both bf16 (code 1); kind::f16
+// covers the two at the same rate
+__host__ __device__ constexpr uint32_t umma_idesc_16(uint32_t m, uint32_t n, bool f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 // ---------------------------------------------------------------- 2-CTA (cta_group::2) variants
 // A CTA pair (cluster of 2 on one TPC) runs one tcgen05.mma of M=256: each CTA supplies its 128 rows of A and half
@@ -274,6 +279,44 @@ __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("grid
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// fp16 storage (the deep levels of the path): saturating conversion, so that an activation beyond
+// the fp16 range is stored as +-65504 instead of infinity
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit storage type picked at run time (warp-uniform flag): 0 = bf16, 1 = fp16
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
+  asm("{\n\t"
+      ".reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t"
+      "}\n"
+      : "=f"(lo), "=f"(hi)
+      : "r"(w));
+}
+__device__ __forceinline__ void unpack_16x2(uint32_t w, int f16, float& lo, float& hi) {
+  if (f16) {
+    unpack_f16x2(w, lo, hi);
+  } else {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xFFFF0000u);
+  }
+}
+// one 16-bit element (scalar paths)
+__device__ __forceinline__ uint16_t to_16(float v, int f16) {
+  return static_cast<uint16_t>(pack_16x2(v, 0.0f, f16) & 0xFFFFu);
+}
+__device__ __forceinline__ float from_16(uint16_t v, int f16) {
+  float lo, hi;
+  unpack_16x2(static_cast<uint32_t>(v), f16, lo, hi);
+  return lo;
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 

@@ -49,7 +49,7 @@ class FFAPathPlan:
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch: int, input_hw: Sequence[int], num_classes: int,
                  device=None, act: str = "silu", neck_prefix: str = "backbone.", head_prefix: str = "head.",
                  parts: Sequence[str] = ("neck", "head"), variant: str = "ffa", decode: str = "drone",
-                 precision: str = "bf16"):
+                 precision: str = "bf16", storage: Optional[str] = None):
         """`parts` selects which op lists are built - "neck", "stems" (everything producing the per-level head
         inputs), "towers" (tower + prediction convs), "head" = stems + towers - because a stand-alone neck or head
         module only owns its own weights; `decode` picks the decoded-row flavour: "drone" (normalised) or "mmdet"
@@ -57,7 +57,9 @@ class FFAPathPlan:
         (every tensor fp32, SIMT fp32 convs, csrc/fp32_path.cu; parity bar 1e-3 relative)."""
         assert precision in ("bf16", "fp32")
         self.fp32 = precision == "fp32"
-        self.dtype = torch.float32 if self.fp32 else torch.bfloat16
+        # 16-bit storage policy of the tensor-core path: "mixed" (default) = bf16 at stride 4, fp16 at the coarser
+        # levels (glsdet_b200/_native.py::storage_dtype); "bf16" / "f16" force one type
+        self.storage = storage
         if self.fp32 and variant in ("p1", "p2"):
             raise NotImplementedError("the fp32 accuracy mode covers the P0 and stock topologies")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -126,9 +128,14 @@ class FFAPathPlan:
         self._build()
 
     # ------------------------------------------------------------------ helpers
+    def _dt(self, stride: int, role: str = "head"):
+        """Storage type of a tensor at `stride`: fp32 in the accuracy mode, else the 16-bit policy."""
+        return torch.float32 if self.fp32 else N.storage_dtype(stride, self.storage, role)
+
     def _buf(self, name: str, stride: int, channels: int, dtype=None) -> torch.Tensor:
         h, w = self.stride_hw[stride]
-        t = torch.empty((self.B, h, w, channels), dtype=self.dtype if dtype is None else dtype, device=self.device)
+        role = "input" if name in ("dark2", "dark3", "dark4", "dark5") else "head"
+        t = torch.empty((self.B, h, w, channels), dtype=self._dt(stride, role) if dtype is None else dtype, device=self.device)
         self._bufs[name] = t
         return t
 
@@ -326,10 +333,10 @@ class FFAPathPlan:
             h2, w2 = H // 2, W_ // 2
             for pos, (y0, x0, ph, pw) in (("lt", (0, 0, h2, w2)), ("rt", (0, w2, h2, W_ - w2)),
                                           ("lb", (h2, 0, H - h2, w2)), ("rb", (h2, w2, H - h2, W_ - w2))):
-                xp = torch.empty((B, ph, pw, C), dtype=torch.bfloat16, device=dev)
+                xp = torch.empty((B, ph, pw, C), dtype=x.dtype, device=dev)
                 ops.append(RectCopyOp(View(x), View(xp), B, [(0, y0, x0, 0, 0, 0, ph, pw)]))
-                xt, Ca = self._nonlocal_operand(f"{p}.{pos}", B, C, ph * pw)
-                ops.append(NhwcTransposeOp(View(xp), xt))
+                xt, Ca = self._nonlocal_operand(f"{p}.{pos}", B, C, ph * pw, x.dtype)
+                ops.append(NhwcTransposeOp(View(xp), xt, scale=(ph * pw) ** -0.5))
                 Wm, bias = self._nonlocal_gemms(ops, p, xt, C, ph * pw, B, dict(src_shared=1), positions=(pos,))
                 nlp = torch.empty_like(xp)
                 self._conv(ops, None, None, [View(xp)], View(nlp), 1, act=N.ACT_NONE, weight_raw=Wm.view(B, C, Ca),
@@ -339,26 +346,28 @@ class FFAPathPlan:
         else:
             T = (H // 2) * (W_ // 2)
             Bp = 4 * B
-            xt, Ca = self._nonlocal_operand(p, Bp, C, T)
-            self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_)))
+            xt, Ca = self._nonlocal_operand(p, Bp, C, T, x.dtype)
+            self.pre_loads.append((in_idx, PatchTransposeOp(xt, C, H, W_, scale=T ** -0.5)))
             Wm, bias = self._nonlocal_gemms(ops, p, xt, C, T, Bp, dict(src_shared=4))
             self._conv(ops, None, None, [View(x)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
                        patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
         self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
 
-    def _nonlocal_operand(self, p: str, Bp: int, C: int, T: int):
-        """Per-patch transposed operand Xt[b'][c][t] with the ones row (channel sums / conv biases) preset."""
+    def _nonlocal_operand(self, p: str, Bp: int, C: int, T: int, dtype):
+        """Per-patch transposed operand Xt[b'][c][t] / sqrt(T) with the ones row (channel sums / conv biases) preset.
+        The 1 / sqrt(T) on both Gram operands makes S = Xt Xt^T the MEAN outer product (the 1 / T of
+        Non_local_family.py:29), whose entries are O(1) - the plain sum over T = 4096 pixels would leave the fp16 range."""
         Tp = (T + 63) // 64 * 64
         Ca = C + 64
-        xt = torch.zeros((Bp, Ca, Tp), dtype=torch.bfloat16, device=self.device)
-        xt[:, C, :T] = 1.0
+        xt = torch.zeros((Bp, Ca, Tp), dtype=dtype, device=self.device)
+        xt[:, C, :T] = T ** -0.5
         self._bufs[p + ".xt"] = xt
         return xt, Ca
 
     def _nonlocal_gemms(self, ops, p: str, xt: torch.Tensor, C: int, T: int, Bp: int, shared_kw: dict,
                         positions=("lt", "rt", "lb", "rb")):
         """Gram matrix and the two C x C products of the reassociated non-local block for Bp patch images; returns
-        (W [Bp, 1, C, Ca] bf16: columns 0..C-1 = W_eff, column C = b_eff - b_o;  bias [Bp, 1, 1, C] fp32 = b_eff).
+        (W [Bp, 1, C, Ca] 16-bit: columns 0..C-1 = W_eff, column C = b_eff - b_o;  bias [Bp, 1, 1, C] fp32 = b_eff).
         `shared_kw` tells the conv operator how a patch image selects its position's static matrices
         (position order lt, rt, lb, rb = py * 2 + px)."""
         sd, dev = self.sd, self.device
@@ -373,18 +382,19 @@ class FFAPathPlan:
             bg, bt, bp = (sd[q + n + ".bias"].double() for n in ("g", "theta", "phi"))
             G = torch.cat([wg, bg[:, None]], 1)          # [Ci, C+1]
             Phi = torch.cat([wp, bp[:, None]], 1)        # [Ci, C+1]
-            a1[i, :, :C + 1] = wo @ G / T                # [C, C+1]
+            a1[i, :, :C + 1] = wo @ G                    # [C, C+1]; the 1 / T sits in S (see _nonlocal_operand)
             a2 = Phi.t() @ torch.cat([wt, bt[:, None]], 1)   # [C+1, C+1]: columns 0..C-1 -> W_eff, column C -> b_eff - bo
             a2t[i, :C + 1, :C + 1] = a2.t()
             bo[i] = sd[q + "conv_out.bias"].float()
-        a1 = a1.to(torch.bfloat16).view(npos, 1, C, Ca).contiguous()
-        a2t = a2t.to(torch.bfloat16).view(npos, 1, Ca, Ca).contiguous()
+        dt = xt.dtype
+        a1 = a1.to(dt).view(npos, 1, C, Ca).contiguous()
+        a2t = a2t.to(dt).view(npos, 1, Ca, Ca).contiguous()
         div = shared_kw.get("src_shared_div", 0)
         img_pos = (torch.arange(Bp, device=dev) // div) if div else (torch.arange(Bp, device=dev) % npos)
         bo_full = bo[img_pos].contiguous()               # [Bp, C]: b_o of every patch image
-        S = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
-        Zt = torch.empty((Bp, 1, Ca, Ca), dtype=torch.bfloat16, device=dev)
-        Wm = torch.empty((Bp, 1, C, Ca), dtype=torch.bfloat16, device=dev)
+        S = torch.empty((Bp, 1, Ca, Ca), dtype=dt, device=dev)
+        Zt = torch.empty((Bp, 1, Ca, Ca), dtype=dt, device=dev)
+        Wm = torch.empty((Bp, 1, C, Ca), dtype=dt, device=dev)
         bias = torch.empty((Bp, 1, 1, C), dtype=torch.float32, device=dev)
         none = N.ACT_NONE
         # S[c][c'] = sum_t Xt[c][t] Xt[c'][t]
@@ -415,25 +425,26 @@ class FFAPathPlan:
         hq, wq = h2 // stride, w2 // stride
         pos_yx = ((0, 0), (0, 1), (1, 0), (1, 1))    # lt, rt, lb, rb
         names = ("lt", "rt", "lb", "rb")
-        xp = torch.empty((4 * B, h2, w2, Cin), dtype=torch.bfloat16, device=dev)
+        dt = x.dtype
+        xp = torch.empty((4 * B, h2, w2, Cin), dtype=dt, device=dev)
         ops.append(RectCopyOp(View(x), View(xp), B, [(0, py * h2, px * w2, i * B, 0, 0, h2, w2)
                                                      for i, (py, px) in enumerate(pos_yx)]))
-        y = torch.empty((4 * B, hq, wq, mid), dtype=torch.bfloat16, device=dev)
+        y = torch.empty((4 * B, hq, wq, mid), dtype=dt, device=dev)
         for i, nm in enumerate(names):
             self._base_conv(ops, f"{p}.feat_patchconv_{nm}", [View(xp[i * B:(i + 1) * B])], View(y[i * B:(i + 1) * B]),
                             stride=stride)
         if nonlocal_:
             T = hq * wq
-            xt, Ca = self._nonlocal_operand(p, 4 * B, mid, T)
-            ops.append(NhwcTransposeOp(View(y), xt))
+            xt, Ca = self._nonlocal_operand(p, 4 * B, mid, T, dt)
+            ops.append(NhwcTransposeOp(View(y), xt, scale=T ** -0.5))
             Wm, bias = self._nonlocal_gemms(ops, p, xt, mid, T, 4 * B, dict(src_shared=4, src_shared_div=B))
             nl = torch.empty_like(y)
             self._conv(ops, None, None, [View(y)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(4 * B, mid, Ca),
                        n_out=mid, pre_res=View(bias), pre_shift=30, post_res=View(y), post_shift=0)
         else:
             nl = y
-        lr_in = torch.empty((2 * B, 2 * hq, wq, mid), dtype=torch.bfloat16, device=dev)   # L images, then R images
-        tb_in = torch.empty((2 * B, hq, 2 * wq, mid), dtype=torch.bfloat16, device=dev)   # T images, then B images
+        lr_in = torch.empty((2 * B, 2 * hq, wq, mid), dtype=dt, device=dev)   # L images, then R images
+        tb_in = torch.empty((2 * B, hq, 2 * wq, mid), dtype=dt, device=dev)   # T images, then B images
         ops.append(RectCopyOp(View(nl), View(lr_in), B, [(i * B, 0, 0, px * B, py * hq, 0, hq, wq)
                                                          for i, (py, px) in enumerate(pos_yx)]))
         ops.append(RectCopyOp(View(nl), View(tb_in), B, [(i * B, 0, 0, py * B, 0, px * wq, hq, wq)
@@ -443,7 +454,7 @@ class FFAPathPlan:
         self._base_conv(ops, f"{p}.feat_patchconv_r", [View(lr_in[B:])], View(lr_o[B:]))
         self._base_conv(ops, f"{p}.feat_patchconv_t", [View(tb_in[:B])], View(tb_o[:B]))
         self._base_conv(ops, f"{p}.feat_patchconv_b", [View(tb_in[B:])], View(tb_o[B:]))
-        cc = torch.empty((B, 2 * hq, 2 * wq, 2 * mid), dtype=torch.bfloat16, device=dev)   # [cat(l, r; W) | cat(t, b; H)]
+        cc = torch.empty((B, 2 * hq, 2 * wq, 2 * mid), dtype=dt, device=dev)   # [cat(l, r; W) | cat(t, b; H)]
         ops.append(RectCopyOp(View(lr_o), View(cc, 0, mid), B, [(0, 0, 0, 0, 0, 0, 2 * hq, wq), (B, 0, 0, 0, 0, wq, 2 * hq, wq)]))
         ops.append(RectCopyOp(View(tb_o), View(cc, mid, mid), B, [(0, 0, 0, 0, 0, 0, hq, 2 * wq), (B, 0, 0, 0, hq, 0, hq, 2 * wq)]))
         self._conv(ops, sd[p + ".channel_conv.weight"].float(), sd[p + ".channel_conv.bias"].float(), [View(cc)], out, 1,

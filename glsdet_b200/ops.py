@@ -20,9 +20,10 @@ def fold_bn(conv_weight: torch.Tensor, bn_weight, bn_bias, bn_mean, bn_var, eps:
     return w.float(), b.float()
 
 
-def pack_conv_weight(weight: torch.Tensor, splits: Sequence[int], n_pad: int, k_pad: int) -> torch.Tensor:
-    """[N, Cin, kh, kw] fp32 -> bf16 [n_pad, k_pad] in the K order the kernel streams:
-    (source, tap = ky*kw + kx, channel) with every (source, tap) segment zero-padded to 64 channels."""
+def pack_conv_weight(weight: torch.Tensor, splits: Sequence[int], n_pad: int, k_pad: int,
+                     dtype=torch.bfloat16) -> torch.Tensor:
+    """[N, Cin, kh, kw] fp32 -> 16-bit [n_pad, k_pad] (the storage type of the conv's sources) in the K order the
+    kernel streams: (source, tap = ky*kw + kx, channel) with every (source, tap) segment zero-padded to 64 channels."""
     n, cin, kh, kw = weight.shape
     assert sum(splits) == cin, (splits, cin)
     segs = []
@@ -36,13 +37,15 @@ def pack_conv_weight(weight: torch.Tensor, splits: Sequence[int], n_pad: int, k_
         a += c
     packed = torch.cat(segs, dim=1)
     assert packed.shape[1] == k_pad, (packed.shape, k_pad)
-    out = torch.zeros((n_pad, k_pad), dtype=torch.bfloat16, device=weight.device)
-    out[:n] = packed.to(torch.bfloat16)
+    out = torch.zeros((n_pad, k_pad), dtype=dtype, device=weight.device)
+    if dtype == torch.float16:   # saturate like the kernels' fp16 stores do
+        packed = packed.clamp(-65504.0, 65504.0)
+    out[:n] = packed.to(dtype)
     return out.contiguous()
 
 
 class View:
-    """A channel window of an NHWC buffer: tensor [B, H, W, ld] (bf16 or fp32), channels [coff, coff + c)."""
+    """A channel window of an NHWC buffer: tensor [B, H, W, ld] (bf16 / fp16 or fp32), channels [coff, coff + c)."""
 
     __slots__ = ("t", "coff", "c")
 
@@ -76,7 +79,7 @@ class FoldedView:
         """`row_pitch` (elements) overrides (width + 2) * c_pix: the PAIR view of a 16-channel buffer - c_pix = 32 (two
         pixels per step), width = W / 2, row_pitch = (W + 2) * 16 - whose 64-element window at step X covers pixels
         2X-1 .. 2X+2, i.e. the inputs of the two output pixels 2X and 2X+1 (see fold_kx_pair_weight)."""
-        assert flat.dtype == torch.bfloat16 and flat.dim() == 1 and c_pix % 8 == 0 and c_pix <= 64
+        assert flat.dtype in (torch.bfloat16, torch.float16) and flat.dim() == 1 and c_pix % 8 == 0 and c_pix <= 64
         self._row_pitch = row_pitch if row_pitch else (width + 2) * c_pix
         assert flat.numel() >= batch * height * self._row_pitch + 64, "needs 64 elements of slack behind the last row"
         self.t, self.c, self.c_pix, self._bhw = flat, 64, c_pix, (batch, height, width)
@@ -162,8 +165,9 @@ class ConvOp:
         lib = N.load()
         assert 1 <= len(srcs) <= 2
         b, h, w = srcs[0].bhw
+        sdt = srcs[0].t.dtype
         for s in srcs:
-            assert s.bhw == (b, h, w) and s.t.dtype == torch.bfloat16
+            assert s.bhw == (b, h, w) and s.t.dtype == sdt and sdt in (torch.bfloat16, torch.float16)
         if patch_mode:
             assert h % 2 == 0 and w % 2 == 0 and ksize == 1
             b, h, w = 4 * b, h // 2, w // 2
@@ -188,9 +192,9 @@ class ConvOp:
                 "glsdet_conv_weight_shape")
         self.block_n = block_n.value
         if weight_raw is None:
-            self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value)
+            self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value, sdt)
         else:
-            assert weight_raw.dtype == torch.bfloat16 and weight_raw.is_contiguous() and ksize == 1
+            assert weight_raw.dtype == sdt and weight_raw.is_contiguous() and ksize == 1
             assert weight_raw.shape[-1] >= k_pad.value and weight_raw.shape[-2] >= n_out, (weight_raw.shape, k_pad.value)
             self.packed = weight_raw
             d.weight_ld = weight_raw.shape[-1]
@@ -200,6 +204,7 @@ class ConvOp:
         d.src_shared = int(src_shared)
         d.src_shared_div = int(src_shared_div)
         d.patch_mode = 1 if patch_mode else 0
+        d.src_dtype = N.dt_code(sdt)
         self.bias = None if bias is None else bias.detach().float().contiguous()
         d.weight = self.packed.data_ptr()
         d.bias = 0 if self.bias is None else self.bias.data_ptr()
@@ -211,7 +216,7 @@ class ConvOp:
             assert pre_res.bhw == (b, max(ho >> pre_shift, 1), max(wo >> pre_shift, 1)), (pre_res.bhw, b, ho, wo, pre_shift)
             d.pre_res, d.pre_shift, d.pre_ld = pre_res.ptr, pre_shift, pre_res.ld
         if post_res is not None:
-            assert post_res.t.dtype == torch.bfloat16
+            d.post_dtype = N.dt_code(post_res.t.dtype)
             if patch_mode:
                 assert post_res.bhw == (b // 4, 2 * ho, 2 * wo) and post_shift == 0
             else:
@@ -224,7 +229,10 @@ class ConvOp:
                 assert out.bhw == (b, ho, wo) and (out.c >= n_out or pred_weight is not None)
             d.out, d.out_ld, d.out_coff = out.t.data_ptr(), out.ld, out.coff
             d.out_batch_stride = ho * wo * out.ld
-            d.out_mode = N.OUT_NHWC_BF16 if out.t.dtype == torch.bfloat16 else N.OUT_NHWC_F32
+            if out.t.dtype == torch.float32:
+                d.out_mode = N.OUT_NHWC_F32
+            else:
+                d.out_mode, d.out_dtype = N.OUT_NHWC_BF16, N.dt_code(out.t.dtype)
             self._out_t = out.t
         else:  # raw tensor with explicit addressing (NCHW fp32 logits / [B, A, C] decoded rows)
             d.out, d.out_ld, d.out_coff = out.data_ptr() + out_elem_offset * out.element_size(), out_ld, out_coff
@@ -270,9 +278,9 @@ def nchw_to_nhwc(src: torch.Tensor, dst: View, stream=None) -> None:
         N.check(lib.glsdet_nchw_nhwc_f32(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff, 1,
                                          N.stream_ptr(stream)), "glsdet_nchw_nhwc_f32")
         return
-    assert dst.bhw == (b, h, w) and dst.c == c and dst.t.dtype == torch.bfloat16
-    N.check(lib.glsdet_nchw_f32_to_nhwc_bf16(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff,
-                                             N.stream_ptr(stream)), "glsdet_nchw_f32_to_nhwc_bf16")
+    assert dst.bhw == (b, h, w) and dst.c == c
+    N.check(lib.glsdet_nchw_f32_to_nhwc_16(src.data_ptr(), dst.t.data_ptr(), b, c, h, w, dst.ld, dst.coff,
+                                           N.dt_code(dst.t.dtype), N.stream_ptr(stream)), "glsdet_nchw_f32_to_nhwc_16")
 
 
 def nhwc_to_nchw(src: View, dst: torch.Tensor, stream=None) -> None:
@@ -284,16 +292,15 @@ def nhwc_to_nchw(src: View, dst: torch.Tensor, stream=None) -> None:
         N.check(lib.glsdet_nchw_nhwc_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff, 0,
                                          N.stream_ptr(stream)), "glsdet_nchw_nhwc_f32")
         return
-    assert src.t.dtype == torch.bfloat16
-    N.check(lib.glsdet_nhwc_bf16_to_nchw_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff,
-                                             N.stream_ptr(stream)), "glsdet_nhwc_bf16_to_nchw_f32")
+    N.check(lib.glsdet_nhwc_16_to_nchw_f32(src.t.data_ptr(), dst.data_ptr(), b, src.c, h, w, src.ld, src.coff,
+                                           N.dt_code(src.t.dtype), N.stream_ptr(stream)), "glsdet_nhwc_16_to_nchw_f32")
 
 
 class SeGateOp:
     """gate[b, c] = 1 + sigmoid(W2 relu(W1 mean_hw(x)))  (models/ffa/ffa.py:16-20 and :77)."""
 
     def __init__(self, x: View, w1: torch.Tensor, w2: torch.Tensor):
-        assert x.coff == 0 and x.t.dtype in (torch.bfloat16, torch.float32)
+        assert x.coff == 0 and x.t.dtype in (torch.bfloat16, torch.float16, torch.float32)
         b, h, w = x.bhw
         self.x, self.b, self.hw, self.c = x, b, h * w, x.c
         self.w1 = w1.detach().float().contiguous()
@@ -312,9 +319,10 @@ class SeGateOp:
             N.check(self._lib.glsdet_se_fc(self.scratch.data_ptr(), self.w1.data_ptr(), self.w2.data_ptr(), self.hidden,
                                            self.gate.data_ptr(), self.b, self.hw, self.c, st), "glsdet_se_fc")
             return
-        N.check(self._lib.glsdet_se_gate(self.x.ptr, self.b, self.hw, self.c, self.x.ld, self.w1.data_ptr(),
-                                         self.w2.data_ptr(), self.hidden, self.scratch.data_ptr(),
-                                         self.gate.data_ptr(), N.stream_ptr(stream)), "glsdet_se_gate")
+        N.check(self._lib.glsdet_se_gate_16(self.x.ptr, self.b, self.hw, self.c, self.x.ld, self.w1.data_ptr(),
+                                            self.w2.data_ptr(), self.hidden, self.scratch.data_ptr(),
+                                            self.gate.data_ptr(), N.dt_code(self.x.t.dtype), N.stream_ptr(stream)),
+                "glsdet_se_gate_16")
 
 
 class ScaleShuffleOp:
@@ -335,9 +343,10 @@ class ScaleShuffleOp:
                                                              self.dst.coff, N.stream_ptr(stream)),
                     "glsdet_scale_pixel_shuffle_f32")
             return
-        N.check(self._lib.glsdet_scale_pixel_shuffle(self.x.ptr, self.gate.data_ptr(), self.dst.t.data_ptr(), self.b,
-                                                     self.h, self.w, self.cout, self.dst.ld, self.dst.coff,
-                                                     N.stream_ptr(stream)), "glsdet_scale_pixel_shuffle")
+        N.check(self._lib.glsdet_scale_pixel_shuffle_16(self.x.ptr, self.gate.data_ptr(), self.dst.t.data_ptr(), self.b,
+                                                        self.h, self.w, self.cout, self.dst.ld, self.dst.coff,
+                                                        N.dt_code(self.x.t.dtype), N.dt_code(self.dst.t.dtype),
+                                                        N.stream_ptr(stream)), "glsdet_scale_pixel_shuffle_16")
 
 
 class _Call:
@@ -353,25 +362,25 @@ class _Call:
 class PatchTransposeOp:
     """NCHW fp32 map -> per-patch transposed bf16 matrices [4B, rows, t_ld] (Gram operand of the non-local block)."""
 
-    def __init__(self, dst: torch.Tensor, channels: int, height: int, width: int):
-        assert dst.dtype == torch.bfloat16 and dst.dim() == 3 and dst.is_contiguous()
-        self.dst, self.c, self.h, self.w = dst, channels, height, width
+    def __init__(self, dst: torch.Tensor, channels: int, height: int, width: int, scale: float = 1.0):
+        assert dst.dtype in (torch.bfloat16, torch.float16) and dst.dim() == 3 and dst.is_contiguous()
+        self.dst, self.c, self.h, self.w, self.scale = dst, channels, height, width, float(scale)
         self._lib = N.load()
 
     def launch(self, src: torch.Tensor, stream=None):
         assert src.dtype == torch.float32 and src.is_contiguous() and src.is_cuda
         b = src.shape[0]
         assert tuple(src.shape) == (b, self.c, self.h, self.w) and self.dst.shape[0] == 4 * b
-        N.check(self._lib.glsdet_patch_transpose(src.data_ptr(), self.dst.data_ptr(), b, self.c, self.h, self.w,
-                                                 self.dst.shape[1], self.dst.shape[2], N.stream_ptr(stream)),
-                "glsdet_patch_transpose")
+        N.check(self._lib.glsdet_patch_transpose_16(src.data_ptr(), self.dst.data_ptr(), b, self.c, self.h, self.w,
+                                                    self.dst.shape[1], self.dst.shape[2], N.dt_code(self.dst.dtype),
+                                                    self.scale, N.stream_ptr(stream)), "glsdet_patch_transpose_16")
 
 
 class GatherBiasOp:
     """bias[b][n] = base[b mod groups][n] + w[b][n][col]."""
 
     def __init__(self, w: torch.Tensor, base: torch.Tensor, bias: torch.Tensor, col: int):
-        assert w.dtype == torch.bfloat16 and w.dim() == 3 and w.is_contiguous()
+        assert w.dtype in (torch.bfloat16, torch.float16) and w.dim() == 3 and w.is_contiguous()
         assert base.dtype == torch.float32 and bias.dtype == torch.float32 and base.is_contiguous()
         self.w, self.base, self.bias, self.col = w, base, bias, col
         self.groups = base.shape[0]
@@ -380,9 +389,9 @@ class GatherBiasOp:
 
     def launch(self, stream=None):
         w = self.w
-        N.check(self._lib.glsdet_gather_bias(w.data_ptr(), self.base.data_ptr(), self.bias.data_ptr(), w.shape[0],
-                                             w.shape[1], w.shape[2], self.col, w.shape[1] * w.shape[2], self.groups,
-                                             N.stream_ptr(stream)), "glsdet_gather_bias")
+        N.check(self._lib.glsdet_gather_bias_16(w.data_ptr(), self.base.data_ptr(), self.bias.data_ptr(), w.shape[0],
+                                                w.shape[1], w.shape[2], self.col, w.shape[1] * w.shape[2], self.groups,
+                                                N.dt_code(w.dtype), N.stream_ptr(stream)), "glsdet_gather_bias_16")
 
 
 class Upsample2xOp:
@@ -391,7 +400,7 @@ class Upsample2xOp:
     def __init__(self, src: View, dst: View):
         b, h, w = src.bhw
         assert dst.bhw == (b, 2 * h, 2 * w) and dst.c == src.c
-        assert src.t.dtype == torch.bfloat16 and dst.t.dtype == torch.bfloat16
+        assert src.t.dtype == dst.t.dtype and src.t.dtype in (torch.bfloat16, torch.float16)   # a plain 16-bit copy
         self.src, self.dst = src, dst
         self._lib = N.load()
 
@@ -464,7 +473,7 @@ class RectCopyOp:
     rects = [(src_image0, sy, sx, dst_image0, dy, dx, h, w), ...], each applied to `batch` consecutive images."""
 
     def __init__(self, src: View, dst: View, batch: int, rects):
-        assert src.t.dtype == torch.bfloat16 and dst.t.dtype == torch.bfloat16 and src.c == dst.c
+        assert src.t.dtype == dst.t.dtype and src.t.dtype in (torch.bfloat16, torch.float16) and src.c == dst.c
         assert 1 <= len(rects) <= 8
         self.src, self.dst, self.batch = src, dst, batch
         self.rects = (N.Rect * len(rects))(*[N.Rect(*r) for r in rects])
@@ -483,8 +492,9 @@ class RectCopyOp:
 class NhwcTransposeOp:
     """NHWC bf16 [B', h, w, C] window -> per-image transposed matrices dst[b'][c][t] (Gram operand)."""
 
-    def __init__(self, src: View, dst: torch.Tensor):
-        assert src.t.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16 and dst.dim() == 3 and dst.is_contiguous()
+    def __init__(self, src: View, dst: torch.Tensor, scale: float = 1.0):
+        self.scale = float(scale)
+        assert src.t.dtype == dst.dtype and dst.dtype in (torch.bfloat16, torch.float16) and dst.dim() == 3 and dst.is_contiguous()
         b, h, w = src.bhw
         assert dst.shape[0] == b and dst.shape[1] >= src.c and dst.shape[2] >= h * w
         self.src, self.dst, self.b, self.t = src, dst, b, h * w
@@ -492,9 +502,9 @@ class NhwcTransposeOp:
 
     def launch(self, stream=None):
         s = self.src
-        N.check(self._lib.glsdet_nhwc_transpose(s.t.data_ptr(), self.dst.data_ptr(), self.b, self.t, s.c, s.ld, s.coff,
-                                                self.dst.shape[1], self.dst.shape[2], N.stream_ptr(stream)),
-                "glsdet_nhwc_transpose")
+        N.check(self._lib.glsdet_nhwc_transpose_16(s.t.data_ptr(), self.dst.data_ptr(), self.b, self.t, s.c, s.ld, s.coff,
+                                                   self.dst.shape[1], self.dst.shape[2], N.dt_code(self.dst.dtype),
+                                                   self.scale, N.stream_ptr(stream)), "glsdet_nhwc_transpose_16")
 
 
 class FocusOp:
@@ -511,7 +521,7 @@ class FocusOp:
             assert dst.dim() == 4 and dst.shape[3] == 12 and dst.is_contiguous()
             self.shape, self.border, self.dst, self.f32 = tuple(dst.shape[:3]), 0, dst, True
         else:
-            assert dst.dtype == torch.bfloat16 and dst.dim() == 4 and dst.shape[3] == 16 and dst.is_contiguous()
+            assert dst.dtype in (torch.bfloat16, torch.float16) and dst.dim() == 4 and dst.shape[3] == 16 and dst.is_contiguous()
             self.shape, self.border, self.dst = tuple(dst.shape[:3]), 0, dst
         self._lib = N.load()
 
@@ -523,9 +533,9 @@ class FocusOp:
             N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_f32(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
                                                                 N.stream_ptr(stream)), "glsdet_focus_nchw_f32_to_nhwc_f32")
             return
-        N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_bf16(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
-                                                             self.border, N.stream_ptr(stream)),
-                "glsdet_focus_nchw_f32_to_nhwc_bf16")
+        N.check(self._lib.glsdet_focus_nchw_f32_to_nhwc_16(image.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
+                                                           self.border, N.dt_code(self.dst.dtype), N.stream_ptr(stream)),
+                "glsdet_focus_nchw_f32_to_nhwc_16")
 
 
     def launch_u8(self, image_u8: torch.Tensor, mean, std, stream=None):
@@ -535,8 +545,9 @@ class FocusOp:
         assert tuple(image_u8.shape) == (b, 2 * h2, 2 * w2, 3), (tuple(image_u8.shape), self.shape)
         m = (C.c_double * 3)(*[float(v) for v in mean])
         s = (C.c_double * 3)(*[float(v) for v in std])
-        N.check(self._lib.glsdet_focus_u8_to_nhwc_bf16(image_u8.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
-                                                       self.border, m, s, N.stream_ptr(stream)), "glsdet_focus_u8_to_nhwc_bf16")
+        N.check(self._lib.glsdet_focus_u8_to_nhwc_16(image_u8.data_ptr(), self.dst.data_ptr(), b, 2 * h2, 2 * w2,
+                                                     self.border, m, s, N.dt_code(self.dst.dtype), N.stream_ptr(stream)),
+                "glsdet_focus_u8_to_nhwc_16")
 
 
 class SppPoolOp:
@@ -544,12 +555,16 @@ class SppPoolOp:
     1..3 (SPPBottleneck.forward, models/ffa/darknet.py:33-36)."""
 
     def __init__(self, cat: torch.Tensor, channels: int):
-        assert cat.dtype in (torch.bfloat16, torch.float32) and cat.dim() == 4 and cat.is_contiguous() and cat.shape[3] == 4 * channels
+        assert cat.dtype in (torch.bfloat16, torch.float16, torch.float32) and cat.dim() == 4 and cat.is_contiguous() and cat.shape[3] == 4 * channels
         self.cat, self.c = cat, channels
         self._lib = N.load()
 
     def launch(self, stream=None):
         b, h, w, ld = self.cat.shape
         c = self.c
-        fn = self._lib.glsdet_spp_maxpool_f32 if self.cat.dtype == torch.float32 else self._lib.glsdet_spp_maxpool
-        N.check(fn(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c, N.stream_ptr(stream)), "glsdet_spp_maxpool")
+        if self.cat.dtype == torch.float32:
+            N.check(self._lib.glsdet_spp_maxpool_f32(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c,
+                                                     N.stream_ptr(stream)), "glsdet_spp_maxpool_f32")
+            return
+        N.check(self._lib.glsdet_spp_maxpool_16(self.cat.data_ptr(), b, h, w, c, ld, 0, c, 2 * c, 3 * c,
+                                                N.dt_code(self.cat.dtype), N.stream_ptr(stream)), "glsdet_spp_maxpool_16")

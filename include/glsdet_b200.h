@@ -15,7 +15,10 @@
  *     message of the last failing call of the calling thread.  No exceptions cross the ABI.
  *   - all launches are asynchronous on the caller's stream; no internal device synchronisation.
  *   - the library never allocates or frees caller tensors; op handles own only their descriptors.
- *   - activations inside the path are NHWC bf16 (channels contiguous), accumulation is fp32.
+ *   - activations inside the path are NHWC with a 16-bit storage type per tensor (GLSDET_DT_BF16 or GLSDET_DT_F16,
+ *     channels contiguous), accumulation is fp32.  tcgen05.mma kind::f16 takes either operand type at the same rate;
+ *     fp16 storage (3 more mantissa bits) is what keeps the 25-35 layer chains of the deep levels within the 2e-2
+ *     parity bar, bf16 stays the type of the stride-4 level, where most of the FLOPs are and the chain is short.
  */
 #ifndef GLSDET_B200_H_
 #define GLSDET_B200_H_
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GLSDET_ABI_VERSION 1
+#define GLSDET_ABI_VERSION 2
 
 /* activation applied in the conv epilogue (reference: models/base/activation.py:9-17, plus the
  * decode of models/core/utils_bbox.py:266-305 when the conv is a prediction conv) */
@@ -42,9 +45,12 @@ enum {
                                 core/anchor/point_generator.py with offset 0) */
 };
 
+/* 16-bit storage type of an activation / weight tensor */
+enum { GLSDET_DT_BF16 = 0, GLSDET_DT_F16 = 1 };
+
 /* output layouts of the conv epilogue */
 enum {
-  GLSDET_OUT_NHWC_BF16 = 0,  /* out[b*bs + (y*W+x)*ld + coff + n]  bf16 */
+  GLSDET_OUT_NHWC_BF16 = 0,  /* out[b*bs + (y*W+x)*ld + coff + n]  16-bit (bf16, or fp16 with out_dtype = GLSDET_DT_F16) */
   GLSDET_OUT_NHWC_F32 = 1,   /* same addressing, fp32 */
   GLSDET_OUT_NCHW_F32 = 2    /* out[b*bs + (coff+n)*H*W + y*W + x] fp32 (reference tensor layout) */
 };
@@ -137,6 +143,12 @@ typedef struct glsdet_conv_desc {
   int64_t out_plane_stride;    /* GLSDET_OUT_NCHW_F32: elements between channel planes; 0 = Ho * Wo.  With the fused
                                   prediction conv and a non-zero stride the pred_act (sigmoid / box decode) is applied too:
                                   decoded predictions as planes [B][5+nc][A], `out` pointing at this level's first anchor */
+  /* 16-bit storage types (GLSDET_DT_*; 0 = bf16 keeps older callers valid): src_dtype covers src0, src1 AND the packed
+   * weights (one MMA operand format per conv), out_dtype the GLSDET_OUT_NHWC_BF16 output, post_dtype the post residual.
+   * fp16 stores saturate at +-65504. */
+  int32_t src_dtype;
+  int32_t out_dtype;
+  int32_t post_dtype;
 } glsdet_conv_desc;
 
 /* library / device */
@@ -186,6 +198,12 @@ int glsdet_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t batch, int
 int glsdet_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels, int32_t height,
                                  int32_t width, int32_t src_ld, int32_t src_coff, void* stream);
 
+/* Same converters with the 16-bit storage type of the NHWC side given explicitly (GLSDET_DT_*). */
+int glsdet_nchw_f32_to_nhwc_16(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                               int32_t width, int32_t dst_ld, int32_t dst_coff, int32_t dtype, void* stream);
+int glsdet_nhwc_16_to_nchw_f32(const void* src, float* dst, int32_t batch, int32_t channels, int32_t height,
+                               int32_t width, int32_t src_ld, int32_t src_coff, int32_t dtype, void* stream);
+
 /*
  * Non-local helpers (yolox-drone/models/new/Non_local_family.py:32-48, 229-250).
  * glsdet_patch_transpose: the four 2x2 patches of an NCHW fp32 map (split of :230-233, equal halves only) as
@@ -200,6 +218,12 @@ int glsdet_patch_transpose(const float* src, void* dst, int32_t batch, int32_t c
                            int32_t width, int32_t dst_rows, int32_t dst_ld, void* stream);
 int glsdet_gather_bias(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows, int32_t ld,
                        int32_t col, int64_t batch_stride, int32_t base_groups, void* stream);
+/* explicit 16-bit storage type (GLSDET_DT_*) of dst / w */
+/* (every element multiplied by `scale` before rounding: 1 / sqrt(T) on both Gram operands yields the MEAN outer product) */
+int glsdet_patch_transpose_16(const float* src, void* dst, int32_t batch, int32_t channels, int32_t height,
+                              int32_t width, int32_t dst_rows, int32_t dst_ld, int32_t dtype, float scale, void* stream);
+int glsdet_gather_bias_16(const void* w, const float* base, float* bias, int32_t batch, int32_t n_rows, int32_t ld,
+                          int32_t col, int64_t batch_stride, int32_t base_groups, int32_t dtype, void* stream);
 
 /*
  * Rectangle copies between NHWC bf16 tensors (up to 8 per launch): the patch split, the seam halves and the re-tiling
@@ -220,6 +244,9 @@ int glsdet_rect_copy(const void* src, int32_t src_h, int32_t src_w, int32_t src_
  */
 int glsdet_nhwc_transpose(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels, int32_t src_ld,
                           int32_t src_coff, int32_t dst_rows, int32_t dst_ld, void* stream);
+/* explicit 16-bit storage type (GLSDET_DT_*) and a scale applied to every element (1.0 = plain copy) */
+int glsdet_nhwc_transpose_16(const void* src, void* dst, int32_t batch, int32_t pixels, int32_t channels, int32_t src_ld,
+                             int32_t src_coff, int32_t dst_rows, int32_t dst_ld, int32_t dtype, float scale, void* stream);
 
 /*
  * nn.Upsample(scale_factor=2, mode="nearest") of an NHWC bf16 channel window into a channel window of a concat
@@ -247,6 +274,8 @@ int glsdet_focus_nchw_f32_to_nhwc_bf16(const float* image, void* dst, int32_t ba
                                        int32_t dst_border, void* stream);
 int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
                        int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, void* stream);
+int glsdet_spp_maxpool_16(void* buf, int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ld,
+                          int32_t src_coff, int32_t coff5, int32_t coff9, int32_t coff13, int32_t dtype, void* stream);
 /* glsdet_focus_u8_to_nhwc_bf16: the same Focus output from a uint8 HWC image batch [B, H, W, 3] (host pointers mean[3], std[3]):
  *   the normalisation of yolox-drone/models/core/utils.py:47-51 preprocess_input (x / 255 in float32, then - mean and / std
  *   in double, rounded to float32 each time, as numpy does for the float64 constant arrays) and the HWC -> CHW transpose of
@@ -254,6 +283,11 @@ int glsdet_spp_maxpool(void* buf, int32_t batch, int32_t height, int32_t width, 
  *   (the normalisation part of the YOLO facade). */
 int glsdet_focus_u8_to_nhwc_bf16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
                                  int32_t dst_border, const double* mean, const double* std, void* stream);
+/* the two Focus entry points with an explicit 16-bit storage type (GLSDET_DT_*) of dst */
+int glsdet_focus_nchw_f32_to_nhwc_16(const float* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                                     int32_t dst_border, int32_t dtype, void* stream);
+int glsdet_focus_u8_to_nhwc_16(const uint8_t* image, void* dst, int32_t batch, int32_t height, int32_t width,
+                               int32_t dst_border, const double* mean, const double* std, int32_t dtype, void* stream);
 /* fp32 accuracy-mode twins (every tensor fp32; Focus output [B, H/2, W/2, 12] without padding channels) */
 int glsdet_focus_nchw_f32_to_nhwc_f32(const float* image, float* dst, int32_t batch, int32_t height, int32_t width,
                                       void* stream);
@@ -306,6 +340,12 @@ int glsdet_se_gate(const void* x, int32_t batch, int32_t hw, int32_t channels, i
 int glsdet_scale_pixel_shuffle(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
                                int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
                                void* stream);
+/* explicit 16-bit storage types (GLSDET_DT_*): x_dtype of the input, dst_dtype of the shuffled output */
+int glsdet_se_gate_16(const void* x, int32_t batch, int32_t hw, int32_t channels, int32_t x_ld, const float* w1,
+                      const float* w2, int32_t hidden, float* scratch, float* gate, int32_t x_dtype, void* stream);
+int glsdet_scale_pixel_shuffle_16(const void* x, const float* gate, void* dst, int32_t batch, int32_t height,
+                                  int32_t width, int32_t out_channels, int32_t dst_ld, int32_t dst_coff,
+                                  int32_t x_dtype, int32_t dst_dtype, void* stream);
 
 /*
  * decode_outputs (yolox-drone/models/core/utils_bbox.py:254-306) for callers that hold raw NCHW logits:

@@ -38,12 +38,59 @@ def _act(x: torch.Tensor, act: str) -> torch.Tensor:
     raise AttributeError(f"Unsupported act type: {act}")
 
 
-_EMULATE_BF16 = False  # see neck_head_bf16()
+_EMULATE_BF16 = False  # see neck_head_bf16(): storage-precision emulation of the native 16-bit path
+_EMU_IN_H = None       # network input height while emulating: the stride of a map is _EMU_IN_H / its height
+_EMU_STORAGE = "mixed"  # "mixed": bf16 for the head's tensors at stride <= 4, fp16 for everything else (the policy of
+                        # glsdet_b200/_native.py::storage_dtype, restated here because the oracle imports nothing from
+                        # the product); "bf16" / "f16": one type everywhere
+_EMU_ROLE = "head"      # "head" | "backbone": which part of the graph is being emulated
 
 
-def _q(t: torch.Tensor) -> torch.Tensor:
-    """Round to bf16 and back when the bf16-storage emulation is on (identity otherwise)."""
-    return t.to(torch.bfloat16).float() if _EMULATE_BF16 else t
+def _emu_dtype(t: torch.Tensor, role: str):
+    if _EMU_STORAGE == "bf16":
+        return torch.bfloat16
+    if _EMU_STORAGE == "f16":
+        return torch.float16
+    head_fine = role == "head" and (_EMU_IN_H is None or t.dim() != 4 or _EMU_IN_H / t.shape[2] <= 4)
+    return torch.bfloat16 if head_fine else torch.float16
+
+
+def _q(t: torch.Tensor, like: torch.Tensor = None, role: str = None) -> torch.Tensor:
+    """Round to the 16-bit storage type of the tensor and back when the storage emulation is on (identity otherwise).
+    A tensor that already carries its storage type (attribute `_st`, set here) is returned as is.  `like`: the
+    activation a weight tensor multiplies - weights are stored in the type of their conv's input."""
+    if not _EMULATE_BF16:
+        return t
+    if like is None:
+        if getattr(t, "_st", None) is not None:
+            return t
+        dt = _emu_dtype(t, role or _EMU_ROLE)
+        out = t.to(dt).float()
+        out._st = dt
+        return out
+    dt = getattr(like, "_st", None) or _emu_dtype(like, role or _EMU_ROLE)
+    return t.to(dt).float()
+
+
+def _qin(feats):
+    """Plan inputs (backbone features converted from NCHW fp32): stored in the input type of the policy."""
+    return [None if f is None else _q(f, role="input") for f in feats]
+
+
+class _emulate:
+    """with _emulate(on, in_h, storage): ... - scoped storage emulation."""
+
+    def __init__(self, on: bool, in_h=None, storage: str = "mixed", role: str = "head"):
+        self.new = (bool(on), in_h, storage, role)
+
+    def __enter__(self):
+        global _EMULATE_BF16, _EMU_IN_H, _EMU_STORAGE, _EMU_ROLE
+        self.old = (_EMULATE_BF16, _EMU_IN_H, _EMU_STORAGE, _EMU_ROLE)
+        _EMULATE_BF16, _EMU_IN_H, _EMU_STORAGE, _EMU_ROLE = self.new
+
+    def __exit__(self, *exc):
+        global _EMULATE_BF16, _EMU_IN_H, _EMU_STORAGE, _EMU_ROLE
+        _EMULATE_BF16, _EMU_IN_H, _EMU_STORAGE, _EMU_ROLE = self.old
 
 
 def base_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int = 1, act: str = "silu") -> torch.Tensor:
@@ -56,7 +103,7 @@ def base_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int = 1, act: str 
         scale = sd[p + ".bn.weight"].double() / torch.sqrt(sd[p + ".bn.running_var"].double() + BN_EPS)
         wf = (w.double() * scale.view(-1, 1, 1, 1)).float()
         bf = (sd[p + ".bn.bias"].double() - sd[p + ".bn.running_mean"].double() * scale).float()
-        return _q(_act(F.conv2d(_q(x), _q(wf), bf, stride=stride, padding=(k - 1) // 2), act))
+        return _q(_act(F.conv2d(_q(x), _q(wf, x), bf, stride=stride, padding=(k - 1) // 2), act))
     y = F.conv2d(x, w, None, stride=stride, padding=(k - 1) // 2)
     y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],
                      sd[p + ".bn.bias"], training=False, eps=BN_EPS)
@@ -134,10 +181,10 @@ def yolox_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -
     for k, x in enumerate(proc):
         i = 3 if k == 0 else k - 1
         cf = base_conv(sd, f"{p}.cls_convs.{i}.1", base_conv(sd, f"{p}.cls_convs.{i}.0", x))
-        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{i}.weight"]), sd[f"{p}.cls_preds.{i}.bias"])
+        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{i}.weight"], cf), sd[f"{p}.cls_preds.{i}.bias"])
         rf = base_conv(sd, f"{p}.reg_convs.{i}.1", base_conv(sd, f"{p}.reg_convs.{i}.0", x))
-        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{i}.weight"]), sd[f"{p}.reg_preds.{i}.bias"])
-        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{i}.weight"]), sd[f"{p}.obj_preds.{i}.bias"])
+        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{i}.weight"], rf), sd[f"{p}.reg_preds.{i}.bias"])
+        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{i}.weight"], rf), sd[f"{p}.obj_preds.{i}.bias"])
         outs.append(torch.cat([reg_out, obj_out, cls_out], 1))               # :116
     return outs
 
@@ -148,26 +195,22 @@ def stock_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -
     for k, x in enumerate(inputs):
         x = base_conv(sd, f"{p}.stems.{k}", x)
         cf = base_conv(sd, f"{p}.cls_convs.{k}.1", base_conv(sd, f"{p}.cls_convs.{k}.0", x))
-        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"]), sd[f"{p}.cls_preds.{k}.bias"])
+        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"], cf), sd[f"{p}.cls_preds.{k}.bias"])
         rf = base_conv(sd, f"{p}.reg_convs.{k}.1", base_conv(sd, f"{p}.reg_convs.{k}.0", x))
-        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"]), sd[f"{p}.reg_preds.{k}.bias"])
-        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"]), sd[f"{p}.obj_preds.{k}.bias"])
+        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"], rf), sd[f"{p}.reg_preds.{k}.bias"])
+        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"], rf), sd[f"{p}.obj_preds.{k}.bias"])
         outs.append(torch.cat([reg_out, obj_out, cls_out], 1))
     return outs
 
 
-def stock_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+def stock_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False,
+                    storage: str = "mixed") -> List[torch.Tensor]:
     """models/base/yolox.py YoloBody.forward minus CSPDarknet: feats = (dark3, dark4, dark5).  The neck is the same
     PAFPN as yolox_ffa.py (the FFA variant only adds dark2 as a pass-through fourth input)."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = bf16
-    try:
-        with torch.no_grad():
-            f = [_q(t) for t in feats]
-            neck = pafpn_neck(sd, [None] + list(f))
-            return stock_head(sd, neck[1:])
-    finally:
-        _EMULATE_BF16 = False
+    with _emulate(bf16, 8 * feats[0].shape[2], storage), torch.no_grad():
+        f = _qin(feats)
+        neck = pafpn_neck(sd, [None] + list(f))
+        return stock_head(sd, neck[1:])
 
 
 def neck_head(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -176,29 +219,20 @@ def neck_head(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor
         return yolox_head(sd, pafpn_neck(sd, feats))
 
 
-def neck_bf16(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """pafpn_neck with bf16 storage precision (see neck_head_bf16)."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = True
-    try:
-        with torch.no_grad():
-            return pafpn_neck(sd, [_q(f) for f in feats])
-    finally:
-        _EMULATE_BF16 = False
+def neck_bf16(sd: StateDict, feats: Sequence[torch.Tensor], storage: str = "mixed") -> List[torch.Tensor]:
+    """pafpn_neck with the storage precision of the 16-bit path (see neck_head_bf16)."""
+    with _emulate(True, 4 * feats[0].shape[2], storage), torch.no_grad():
+        return pafpn_neck(sd, _qin(feats))
 
 
-def neck_head_bf16(sd: StateDict, feats: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    """The same graph evaluated with the STORAGE precision of the bf16 path (inputs, folded weights and every
-    layer output rounded to bf16; fp32 accumulation).  Separates two error sources in the tests: the CUDA path must
-    match this closely (kernel correctness), while its distance to neck_head() is the quantisation error that
-    BASELINE.json bounds by 2e-2."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = True
-    try:
-        with torch.no_grad():
-            return yolox_head(sd, pafpn_neck(sd, [_q(f) for f in feats]))
-    finally:
-        _EMULATE_BF16 = False
+def neck_head_bf16(sd: StateDict, feats: Sequence[torch.Tensor], storage: str = "mixed") -> List[torch.Tensor]:
+    """The same graph evaluated with the STORAGE precision of the native 16-bit path (inputs, folded weights and
+    every layer output rounded to the storage type of their level - bf16 at stride 4, fp16 at the coarser levels for
+    storage="mixed", the product's default; "bf16" / "f16" = one type everywhere; fp32 accumulation).  Separates two
+    error sources in the tests: the CUDA path must match this closely (kernel correctness), while its distance to
+    neck_head() is the quantisation error that BASELINE.json bounds by 2e-2."""
+    with _emulate(True, 4 * feats[0].shape[2], storage), torch.no_grad():
+        return yolox_head(sd, pafpn_neck(sd, _qin(feats)))
 
 
 # ------------------------------------------------------------------------------------------ P1: models/new/yolox10.py
@@ -207,13 +241,13 @@ def non_local_block(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
     bias and no BN; pairwise = theta^T phi / T with T = H*W (the divisor is pairwise.shape[-1], :29); no softmax."""
     n, _, h, w = x.shape
     ci = sd[p + ".g.weight"].shape[0]
-    g_x = F.conv2d(_q(x), _q(sd[p + ".g.weight"]), sd[p + ".g.bias"]).view(n, ci, -1).permute(0, 2, 1)          # [N, T, Ci]
-    theta_x = F.conv2d(_q(x), _q(sd[p + ".theta.weight"]), sd[p + ".theta.bias"]).view(n, ci, -1).permute(0, 2, 1)
-    phi_x = F.conv2d(_q(x), _q(sd[p + ".phi.weight"]), sd[p + ".phi.bias"]).view(n, ci, -1)                     # [N, Ci, T]
+    g_x = F.conv2d(_q(x), _q(sd[p + ".g.weight"], x), sd[p + ".g.bias"]).view(n, ci, -1).permute(0, 2, 1)          # [N, T, Ci]
+    theta_x = F.conv2d(_q(x), _q(sd[p + ".theta.weight"], x), sd[p + ".theta.bias"]).view(n, ci, -1).permute(0, 2, 1)
+    phi_x = F.conv2d(_q(x), _q(sd[p + ".phi.weight"], x), sd[p + ".phi.bias"]).view(n, ci, -1)                     # [N, Ci, T]
     pairwise = torch.matmul(theta_x, phi_x)
     pairwise = pairwise / pairwise.shape[-1]                                                                    # :29
     y = torch.matmul(pairwise, g_x).permute(0, 2, 1).reshape(n, ci, h, w)                                       # :44-45
-    return x + F.conv2d(y, _q(sd[p + ".conv_out.weight"]), sd[p + ".conv_out.bias"])                            # :46
+    return x + F.conv2d(y, _q(sd[p + ".conv_out.weight"], x), sd[p + ".conv_out.bias"])                            # :46
 
 
 def patch_conv_nonlocal_new(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
@@ -251,24 +285,20 @@ def p1_head(sd: StateDict, inputs: Sequence[torch.Tensor], p: str = "head") -> L
         parts = [x, down] + ([_up2(xs[k + 1])] if k < 2 else [])
         cf = torch.cat(parts, 1)
         cf = base_conv(sd, f"{p}.cls_convs.{k}.1", base_conv(sd, f"{p}.cls_convs.{k}.0", cf))
-        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"]), sd[f"{p}.cls_preds.{k}.bias"])
+        cls_out = F.conv2d(cf, _q(sd[f"{p}.cls_preds.{k}.weight"], cf), sd[f"{p}.cls_preds.{k}.bias"])
         rf = base_conv(sd, f"{p}.reg_convs.{k}.1", base_conv(sd, f"{p}.reg_convs.{k}.0", x))
-        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"]), sd[f"{p}.reg_preds.{k}.bias"])
-        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"]), sd[f"{p}.obj_preds.{k}.bias"])
+        reg_out = F.conv2d(rf, _q(sd[f"{p}.reg_preds.{k}.weight"], rf), sd[f"{p}.reg_preds.{k}.bias"])
+        obj_out = F.conv2d(rf, _q(sd[f"{p}.obj_preds.{k}.weight"], rf), sd[f"{p}.obj_preds.{k}.bias"])
         outs.append(torch.cat([reg_out, obj_out, cls_out], 1))
     return outs
 
 
-def p1_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+def p1_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False,
+                 storage: str = "mixed") -> List[torch.Tensor]:
     """models/new/yolox10.py YoloBody.forward (:339-345) minus the CSPDarknet call; `bf16` = storage-precision
     emulation as in neck_head_bf16."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = bf16
-    try:
-        with torch.no_grad():
-            return p1_head(sd, p1_neck(sd, [_q(f) for f in feats]))
-    finally:
-        _EMULATE_BF16 = False
+    with _emulate(bf16, 4 * feats[0].shape[2], storage), torch.no_grad():
+        return p1_head(sd, p1_neck(sd, _qin(feats)))
 
 
 # ------------------------------------------------------------------------------------------ P2: yolo_patch_nonlocal_plus.py
@@ -282,7 +312,7 @@ def _patch_seams(sd: StateDict, p: str, lt, lb, rt, rb) -> torch.Tensor:
     t = base_conv(sd, p + ".feat_patchconv_t", torch.cat((lt, rt), dim=3))
     b = base_conv(sd, p + ".feat_patchconv_b", torch.cat((lb, rb), dim=3))
     y = torch.cat((torch.cat((l, r), dim=3), torch.cat((t, b), dim=2)), dim=1)
-    return _q(F.conv2d(y, _q(sd[p + ".channel_conv.weight"]), sd[p + ".channel_conv.bias"]))
+    return _q(F.conv2d(y, _q(sd[p + ".channel_conv.weight"], y), sd[p + ".channel_conv.bias"]))
 
 
 def patch_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int, nonlocal_: bool) -> torch.Tensor:
@@ -304,7 +334,7 @@ def identity_conv(sd: StateDict, p: str, x: torch.Tensor) -> torch.Tensor:
     """Identity_Conv_{three,five,seven}.forward (Identity_Conv.py:27-84): a plain k x k nn.Conv2d with bias and
     padding k // 2 (the identity initialisation only matters for training from scratch)."""
     w = sd[p + ".conv.weight"]
-    return _q(F.conv2d(_q(x), _q(w), sd[p + ".conv.bias"], padding=w.shape[-1] // 2))
+    return _q(F.conv2d(_q(x), _q(w, x), sd[p + ".conv.bias"], padding=w.shape[-1] // 2))
 
 
 def p2_neck(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "backbone") -> List[torch.Tensor]:
@@ -326,16 +356,12 @@ def p2_neck(sd: StateDict, feats: Sequence[torch.Tensor], p: str = "backbone") -
     return [P3_out, P4_out, P5_out]
 
 
-def p2_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False) -> List[torch.Tensor]:
+def p2_neck_head(sd: StateDict, feats: Sequence[torch.Tensor], bf16: bool = False,
+                 storage: str = "mixed") -> List[torch.Tensor]:
     """yolo_patch_nonlocal_plus.py YoloBody.forward minus the CSPDarknet call; the head (:6-147) is the stock
     three-level decoupled head."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = bf16
-    try:
-        with torch.no_grad():
-            return stock_head(sd, p2_neck(sd, [_q(f) for f in feats]))
-    finally:
-        _EMULATE_BF16 = False
+    with _emulate(bf16, 8 * feats[0].shape[2], storage), torch.no_grad():
+        return stock_head(sd, p2_neck(sd, _qin(feats)))
 
 
 # ------------------------------------------------------------------------------------------ backbone (upstream)
@@ -359,14 +385,11 @@ def csp_darknet(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") ->
         return outs
 
 
-def csp_darknet_bf16(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone") -> List[torch.Tensor]:
-    """csp_darknet with the storage precision of the bf16 path (see neck_head_bf16)."""
-    global _EMULATE_BF16
-    _EMULATE_BF16 = True
-    try:
-        return csp_darknet(sd, _q(x), p)
-    finally:
-        _EMULATE_BF16 = False
+def csp_darknet_bf16(sd: StateDict, x: torch.Tensor, p: str = "backbone.backbone",
+                     storage: str = "mixed") -> List[torch.Tensor]:
+    """csp_darknet with the storage precision of the 16-bit path (see neck_head_bf16)."""
+    with _emulate(True, x.shape[2], storage, role="backbone"):
+        return csp_darknet(sd, x, p)   # the Focus kernel rounds the space-to-depth image (base_conv quantises its input)
 
 
 # ------------------------------------------------------------------------------------------ decode

@@ -1,9 +1,9 @@
 """GPU parity of the native CSPDarknet backbone (glsdet_b200/backbone.py) through the C ABI.
 
-Tolerances follow tests/test_path_gpu.py: relative l2 error <= max(2e-2, 1.3 x the inherent error of a bf16-storage
-evaluation of the same graph, oracle.ref_path.csp_darknet_bf16) against the fp32 golden vectors of the real reference /
-the fp32 oracle (dark4 sits behind 20 layers and the emulation alone is 2.3e-2 away), and <= 2e-2 against that
-emulation (kernel error only); the two byte-moving kernels are bit-exact.
+Tolerances follow tests/test_path_gpu.py: relative l2 error <= 2e-2 (the plain BASELINE.json bound) against the fp32
+golden vectors of the real reference / the fp32 oracle, and <= 2e-2 against the storage-precision emulation of the same
+graph (oracle.ref_path.csp_darknet_bf16; kernel error only); the two byte-moving kernels are bit-exact.  The backbone
+stores fp16 (glsdet_b200/_native.py::storage_dtype): measured 0.1 - 0.8 %, bf16 storage alone would cost 2 - 6 %.
 """
 from pathlib import Path
 
@@ -101,12 +101,11 @@ def test_backbone_against_reference_golden(native_lib, cuda_device):
     feats = net.backbone.backbone(torch.from_numpy(z["image"]).to(cuda_device))
     assert native_lib.glsdet_launch_count() - n0 >= 30        # the native plan ran, not the PyTorch layers
     assert list(feats) == ["dark2", "dark3", "dark4", "dark5"]
-    # inherent error of bf16 storage along the chain (dark4 sits behind 20 layers: 2.3e-2 by itself)
     emu = dict(zip(("dark2", "dark3", "dark4", "dark5"), ref_path.csp_darknet_bf16(sd, torch.from_numpy(z["image"]))))
     for name, f in feats.items():
         assert f.dtype == torch.float32 and tuple(f.shape) == z[name].shape
         ref = torch.from_numpy(z[name])
-        tol = max(2e-2, 1.3 * rel_l2(emu[name], ref))
+        tol = 2e-2
         assert_close_rel(f, ref, tol=tol, what=name, max_factor=6.0)
         assert rel_l2(f, emu[name]) <= 2e-2, (name, rel_l2(f, emu[name]))
 
@@ -123,14 +122,13 @@ def test_image_to_logits_against_reference_golden(native_lib, cuda_device):
     logits = net(x.to(cuda_device))
     plan = net._fused_plan(x.to(cuda_device))
     assert plan is not None and plan.backbone is not None
-    # inherent error of bf16 storage along the same graph (weights and every activation rounded to bf16, fp32 math)
+    # storage-precision emulation of the same graph (weights and every activation rounded to their storage type, fp32 math)
     feats_q = ref_path.csp_darknet_bf16(sd, x)
     emu = ref_path.neck_head_bf16(sd, feats_q)
     for i, t in enumerate(logits):
         ref = torch.from_numpy(z[f"logits{i}"])
-        inherent = rel_l2(emu[i], ref)
         err = rel_l2(t, ref)
-        assert err <= max(2e-2, 1.3 * inherent), (i, err, inherent)
+        assert err <= 2e-2, (i, err)
         assert rel_l2(t, emu[i]) <= 2e-2, (i, rel_l2(t, emu[i]))
 
 
@@ -148,10 +146,8 @@ def test_backbone_1024_against_oracle_and_batch_invariance(native_lib, cuda_devi
     got = plan.features_nchw()
     emu = ref_path.csp_darknet_bf16(sd, x)
     for name, r, e in zip(("dark2", "dark3", "dark4", "dark5"), ref, emu):
-        inherent = rel_l2(e, r)
-        assert_close_rel(got[name], r, tol=max(2e-2, 1.3 * inherent), what=name, max_factor=8.0)
-        # two bf16-storage evaluations diverge by independent rounding flips: their distance is ~sqrt(2) x the inherent error
-        assert rel_l2(got[name], e) <= max(2e-2, 1.6 * inherent), (name, rel_l2(got[name], e), inherent)
+        assert_close_rel(got[name], r, tol=2e-2, what=name, max_factor=8.0)
+        assert rel_l2(got[name], e) <= 2e-2, (name, rel_l2(got[name], e))
     plan3 = BackbonePlan(sd, 3, (1024, 1024), device=cuda_device)
     x3 = torch.cat([x[1:], x, ])[:3].contiguous()     # images (1, 0, 1)
     plan3.run(x3.to(cuda_device))
@@ -195,7 +191,7 @@ def test_stock_model_from_image(native_lib, cuda_device):
     ref = ref_path.stock_neck_head(sd, feats)
     emu = ref_path.stock_neck_head(sd, ref_path.csp_darknet_bf16(sd, x)[1:], bf16=True)
     for i, t in enumerate(logits):
-        assert rel_l2(t, ref[i]) <= max(2e-2, 1.3 * rel_l2(emu[i], ref[i])), (i, rel_l2(t, ref[i]), rel_l2(emu[i], ref[i]))
+        assert rel_l2(t, ref[i]) <= 2e-2, (i, rel_l2(t, ref[i]), rel_l2(emu[i], ref[i]))
 
 
 def test_backbone_fp32_accuracy_mode(native_lib, cuda_device):
@@ -232,7 +228,7 @@ def test_backbone_tiny_width(native_lib, cuda_device):
     ref = ref_path.csp_darknet(sd, x)
     emu = ref_path.csp_darknet_bf16(sd, x)
     for (name, f), r, e in zip(feats.items(), ref, emu):
-        assert_close_rel(f, r, tol=max(2e-2, 1.3 * rel_l2(e, r)), what="tiny " + name, max_factor=8.0)
+        assert_close_rel(f, r, tol=2e-2, what="tiny " + name, max_factor=8.0)
 
 
 def test_backbone_rejects_cpu_tensor(native_lib):
@@ -277,7 +273,7 @@ def test_large_model_from_image(native_lib, cuda_device):
     from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
     from glsdet_b200.yolox_ffa import YoloBody
 
-    sd = synthetic_state_dict(3, "l", seed=4, flavour="calibrated")
+    sd = synthetic_state_dict(3, "l", seed=6, flavour="calibrated")
     net = YoloBody(3, "l")
     net.load_state_dict(sd, strict=True)
     net = net.to(cuda_device).eval()
@@ -286,12 +282,12 @@ def test_large_model_from_image(native_lib, cuda_device):
     ref = ref_path.csp_darknet(sd, x)
     emu = ref_path.csp_darknet_bf16(sd, x)
     for (name, f), r, e in zip(feats.items(), ref, emu):
-        assert_close_rel(f, r, tol=max(2e-2, 1.3 * rel_l2(e, r)), what="l " + name, max_factor=8.0)
+        assert_close_rel(f, r, tol=2e-2, what="l " + name, max_factor=8.0)
     logits = net(x.to(cuda_device))
     ref_l = ref_path.neck_head(sd, ref)
     emu_l = ref_path.neck_head_bf16(sd, emu)
     for i, t in enumerate(logits):
-        assert rel_l2(t, ref_l[i]) <= max(2e-2, 1.3 * rel_l2(emu_l[i], ref_l[i])), (i, rel_l2(t, ref_l[i]), rel_l2(emu_l[i], ref_l[i]))
+        assert rel_l2(t, ref_l[i]) <= 2e-2, (i, rel_l2(t, ref_l[i]), rel_l2(emu_l[i], ref_l[i]))
 
 
 def test_p2_model_chains_the_backbone(native_lib, cuda_device):

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     for name in declared:
         assert hasattr(native_lib, name), f"{name} is declared in include/glsdet_b200.h but not exported"
-    assert native_lib.glsdet_abi_version() == 1
+    assert native_lib.glsdet_abi_version() == 2
 
 
 def test_no_compute_without_gpu_but_errors_are_reported(native_lib):

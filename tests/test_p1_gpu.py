@@ -144,15 +144,13 @@ def test_p1_model_matches_reference_golden(native_lib, cuda_device):
         ref_path._EMULATE_BF16 = False
     for i in range(1, 4):
         ref_i = torch.from_numpy(z[f"neck{i}"])
-        inherent = ((neck_emu[i] - ref_i).norm() / ref_i.norm()).item()
-        assert_close_rel(neck[i], ref_i, max(TOL, 1.15 * inherent), f"p1 neck{i}")
+        assert_close_rel(neck[i], ref_i, TOL, f"p1 neck{i}")
     logits = net.forward_features(feats)
     emu = ref_path.p1_neck_head(sd, cpu_feats, bf16=True)
     assert len(logits) == 3
     for i in range(3):
         ref_i = torch.from_numpy(z[f"logits{i}"])
-        inherent = ((emu[i] - ref_i).norm() / ref_i.norm()).item()
-        assert_close_rel(logits[i], ref_i, max(TOL, 1.15 * inherent), f"p1 logits{i}", frac=2e-2)
+        assert_close_rel(logits[i], ref_i, TOL, f"p1 logits{i}", frac=2e-2)
         assert_close_rel(logits[i], emu[i], 1.5e-2, f"p1 logits{i} vs bf16-storage emulation", max_factor=4.0, frac=5e-2)
     hl = net.head([torch.from_numpy(z[f"neck{i}"]).to(cuda_device) for i in range(4)])
     for i in range(3):
@@ -196,13 +194,9 @@ def test_p1_nonlocal_stage_vs_oracle(native_lib, cuda_device):
 def test_p1_model_vs_oracle_1024(native_lib, cuda_device):
     """P1-s at 1024 x 1024 (SURVEY.md section 8d row 2'): one image against the oracle, batch invariance, detections.
 
-    This graph is 35 layers deep on the cls branch and the calibrated synthetic weights make it ill-conditioned in
-    bf16: a plain fp32 evaluation with bf16-rounded weights / layer outputs (the emulation) is itself 2.7e-2 .. 3.5e-2
-    away from the fp32 oracle at the logits (1.3e-2 .. 2.3e-2 at the neck outputs, 0.4e-2 .. 0.5e-2 right after the
-    non-local stage).  Measured for the CUDA path (tools/p1_error_report.py): 3.3e-2 .. 4.2e-2 against the oracle,
-    3.4e-2 .. 4.4e-2 against the emulation, i.e. 1.2x the inherent error (two bf16 evaluations with different rounding
-    points differ from each other by about sqrt(2) x the error of one).  The bounds below are therefore relative to
-    the inherent error; the 2e-2 bar of BASELINE.json is met by the non-local stage and the small golden case."""
+    The cls branch of this graph is 35 layers deep; with bf16 storage everywhere the logits were 3.3e-2 .. 4.2e-2 from the
+    fp32 oracle.  Every tensor of P1 coarser than stride 4 is stored in fp16 now (glsdet_b200/_native.py::storage_dtype):
+    measured 1e-3 .. 2e-3 (profiles/r2_parity_rel_l2.txt), so the plain 2e-2 bound of BASELINE.json applies."""
     from glsdet_b200.synthetic import synthetic_images
 
     sd = ref_path.synthetic_state_dict(10, "s", seed=0, flavour="calibrated", variant="p1")
@@ -213,9 +207,8 @@ def test_p1_model_vs_oracle_1024(native_lib, cuda_device):
     dfeats = [f.to(cuda_device) for f in feats]
     out = net.forward_features(dfeats)
     for i in range(3):
-        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
-        assert_close_rel(out[i][:1], ref[i], max(TOL, 1.3 * inherent), f"p1 1024 logits{i}", frac=5e-2)
-        assert_close_rel(out[i][:1], emu[i], max(1.5e-2, 1.6 * inherent), f"p1 1024 logits{i} vs bf16-storage emulation",
+        assert_close_rel(out[i][:1], ref[i], TOL, f"p1 1024 logits{i}", frac=5e-2)
+        assert_close_rel(out[i][:1], emu[i], 1.5e-2, f"p1 1024 logits{i} vs bf16-storage emulation",
                          frac=8e-2)
     pred2 = net.decode_features(dfeats).clone()
     assert pred2.shape == (2, 128 * 128 + 64 * 64 + 32 * 32, 15)
@@ -234,7 +227,7 @@ def test_p1_config4_yolox_l_544x1024_unequal_patches(native_lib, cuda_device):
     from glsdet_b200.yolox10 import YoloBody
 
     nc = 3
-    sd = ref_path.synthetic_state_dict(nc, "l", seed=4, flavour="calibrated", variant="p1")
+    sd = ref_path.synthetic_state_dict(nc, "l", seed=6, flavour="calibrated", variant="p1")
     net = YoloBody(nc, "l")
     net.load_state_dict(sd, strict=True)
     net = net.to(cuda_device).eval()
@@ -254,8 +247,7 @@ def test_p1_config4_yolox_l_544x1024_unequal_patches(native_lib, cuda_device):
     out = net.forward_features(dfeats)
     assert [tuple(o.shape[2:]) for o in out] == [(68, 128), (34, 64), (17, 32)]
     for i in range(3):
-        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
-        assert_close_rel(out[i], ref[i], max(TOL, 1.3 * inherent), f"P1-l 544x1024 logits{i}", frac=5e-2)
+        assert_close_rel(out[i], ref[i], TOL, f"P1-l 544x1024 logits{i}", frac=5e-2)
     det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65, max_det=1000)
     torch.cuda.synchronize()
     assert det.shape == (1, 1000, 7) and 0 <= int(cnt[0]) <= 1000

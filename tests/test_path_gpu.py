@@ -2,12 +2,12 @@
 
 Tolerances (BASELINE.json north_star: "feature maps and logits within ... 2e-2 relative in bf16", "NMS
 keep-indices bit-exact when fed identical scores"):
-  * against the fp32 oracle (quantisation + kernel error): ||diff||_2 <= 2e-2 * ||ref||_2 (for the deepest neck
-    maps: max(2e-2, 1.15 x the error of the bf16-storage emulation, which reaches 2.0e-2 there by itself), 99 % of the elements
-    within 2e-2 * max|ref| and every element within 8e-2 * max|ref| (a plain fp32 evaluation of the graph with
-    bf16-rounded weights/activations - oracle.ref_path.neck_head_bf16 - is itself 1.2e-2 / 3.2e-2 away);
-  * against that bf16-storage emulation of the oracle (kernel error only): ||diff||_2 <= 1.5e-2 * ||ref||_2 (both sides round to bf16 at every layer, so they
-    diverge by individual rounding flips; measured 0.4e-2 .. 1.1e-2);
+  * against the fp32 oracle (quantisation + kernel error): ||diff||_2 <= 2e-2 * ||ref||_2 for every neck map and every
+    logit level - the plain bound, no allowance relative to any "inherent" error - with 99 % of the elements within
+    2e-2 * max|ref| and every element within 8e-2 * max|ref|.  Measured (profiles/r2_parity_rel_l2.txt): 0.03 - 0.25 %
+    with the default storage policy (bf16 for the stride-4 head level, fp16 for everything else);
+  * against the storage-precision emulation of the oracle (oracle.ref_path.neck_head_bf16: fp32 math, weights and
+    activations rounded to the storage type of their level; kernel error only): ||diff||_2 <= 1.5e-2 * ||ref||_2;
   * decode within 1e-5; NMS rows bit-exact when fed identical predictions.
 """
 import json
@@ -270,19 +270,14 @@ def test_model_matches_reference_golden(meta, native_lib, cuda_device):
     feats = [torch.from_numpy(z[f"feat{i}"]).to(cuda_device) for i in range(4)]
 
     neck = net.backbone.forward_features(feats)
-    neck_emu = ref_path.neck_bf16(sd, [f.cpu() for f in feats])
     for i in range(1, 4):
         ref_i = torch.from_numpy(z[f"neck{i}"])
-        # the deepest maps sit at the bf16 limit: an fp32 evaluation with bf16-rounded storage is itself ~2e-2 away
-        # from the reference there, so the bound is the larger of 2e-2 and 1.15 x that inherent error
-        inherent = ((neck_emu[i] - ref_i).norm() / ref_i.norm()).item()
-        assert_close_rel(neck[i], ref_i, max(TOL, 1.15 * inherent), f"neck{i}")
+        assert_close_rel(neck[i], ref_i, TOL, f"neck{i}")
     logits = net.forward_features(feats)
     emu = ref_path.neck_head_bf16(sd, [f.cpu() for f in feats])
     for i in range(4):
         ref_i = torch.from_numpy(z[f"logits{i}"])
-        inherent = ((emu[i] - ref_i).norm() / ref_i.norm()).item()
-        assert_close_rel(logits[i], ref_i, max(TOL, 1.15 * inherent), f"logits{i}", frac=2e-2)
+        assert_close_rel(logits[i], ref_i, TOL, f"logits{i}", frac=2e-2)
         assert_close_rel(logits[i], emu[i], 1.5e-2, f"logits{i} vs bf16-storage emulation", max_factor=4.0, frac=5e-2)
     # stand-alone head module fed with the reference's own neck outputs
     hl = net.head([torch.from_numpy(z[f"neck{i}"]).to(cuda_device) for i in range(4)])
@@ -317,8 +312,7 @@ def test_model_vs_oracle_1024_and_batch_invariance(native_lib, cuda_device):
     dfeats = [f.to(cuda_device) for f in feats]
     out4 = net.forward_features(dfeats)
     for i in range(4):
-        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()   # error of bf16 storage by itself
-        assert_close_rel(out4[i][:1], ref[i], max(TOL, 1.15 * inherent), f"1024 logits{i}")
+        assert_close_rel(out4[i][:1], ref[i], TOL, f"1024 logits{i}")
         assert_close_rel(out4[i][:1], emu[i], 1.5e-2, f"1024 logits{i} vs bf16-storage emulation", frac=5e-2)
     pred4 = net.decode_features(dfeats).clone()
     ref_pred = ref_path.decode_outputs(ref, [1024, 1024])
@@ -342,7 +336,7 @@ def test_config4_yolox_l_544x1024(native_lib, cuda_device):
     from glsdet_b200.yolox_ffa import YoloBody
 
     nc, in_h, in_w = 3, 544, 1024
-    sd = ref_path.synthetic_state_dict(nc, "l", seed=4, flavour="calibrated")
+    sd = ref_path.synthetic_state_dict(nc, "l", seed=6, flavour="calibrated")   # trained-like conditioning, see calibrate_synthetic.py --bn-beta
     net = YoloBody(nc, "l")
     net.load_state_dict(sd, strict=True)
     net = net.to(cuda_device).eval()
@@ -353,8 +347,7 @@ def test_config4_yolox_l_544x1024(native_lib, cuda_device):
     dfeats = [f.to(cuda_device) for f in feats]
     logits = net.forward_features(dfeats)
     for i in range(4):
-        inherent = ((emu[i] - ref[i]).norm() / ref[i].norm()).item()
-        assert_close_rel(logits[i][:1], ref[i], max(TOL, 1.15 * inherent), f"l-544 logits{i}", frac=2e-2)
+        assert_close_rel(logits[i][:1], ref[i], TOL, f"l-544 logits{i}", frac=2e-2)
     det, cnt = net.detect_features(dfeats, conf_thres=0.01, nms_thres=0.65, max_det=1000)
     torch.cuda.synchronize()
     assert det.shape == (2, 1000, 7) and (cnt.cpu() <= 1000).all() and (cnt.cpu() > 0).all()

@@ -36,10 +36,23 @@ def main():
     ap.add_argument("--obj-std", type=float, default=2.0)
     ap.add_argument("--target-pass", type=float, default=0.04, help="fraction of anchors with obj*cls >= 0.01")
     ap.add_argument("--cls-std", type=float, default=0.5)
+    ap.add_argument("--bn-beta", type=float, default=None,
+                    help="mean of the BatchNorm shifts beta (std 0.1).  Default: keep the base weights' N(0, 0.1).  With beta "
+                         "= 0 the pre-activations are N(0, 1), where SiLU + re-normalisation multiplies any relative "
+                         "perturbation by 1.10 per layer (chaotic regime of a random net: sqrt(E[silu'(z)^2] Var z / Var "
+                         "silu(z))): through the ~45 layers of YOLOX-l even fp16 rounding noise grows to 2-3 %.  A trained "
+                         "network does not sit there; beta = 1 gives a factor of 1.03 per layer.")
+    ap.add_argument("--out", default=None, help="output .npz (default glsdet_b200/data/calib_<variant>_<phi>_nc<nc>_seed<seed>.npz)")
     args = ap.parse_args()
     torch.set_num_threads(8)
     sd = synthetic_state_dict(args.nc, args.phi, seed=args.seed, flavour="kaiming", variant=args.variant)
     changed = {}
+    if args.bn_beta is not None:
+        g = torch.Generator().manual_seed(args.seed + 977)
+        for k in list(sd):
+            if k.endswith(".bn.bias"):
+                sd[k] = args.bn_beta + 0.1 * torch.randn(sd[k].shape, generator=g)
+                changed[k] = sd[k]
     orig = ref_path.base_conv
 
     def calibrating_base_conv(sd_, p, x, stride=1, act="silu"):
@@ -111,7 +124,7 @@ def main():
         sd[key] = sd[key] + 0.5 * (lo + hi)
         changed[key] = sd[key]
     tag = "p0" if args.variant == "ffa" else args.variant
-    out = ROOT / "glsdet_b200" / "data" / f"calib_{tag}_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
+    out = Path(args.out) if args.out else ROOT / "glsdet_b200" / "data" / f"calib_{tag}_{args.phi}_nc{args.nc}_seed{args.seed}.npz"
     np.savez_compressed(out, **{k: v.numpy().astype(np.float32) for k, v in changed.items()})
     # report
     with torch.no_grad():

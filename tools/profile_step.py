@@ -27,7 +27,9 @@ def main():
     B = 16
     feats = bench.make_features(net, B, 1000, dev)
     plan = net.plan_for(feats)
-    nms = net.nms_for(plan, 1000)
+    import os
+    md = int(os.environ.get('GLSDET_PROFILE_MAXDET', '0'))
+    nms = net.nms_for(plan, md if md > 0 else None)
 
     def step():
         plan.load_features(feats)
