@@ -14,6 +14,7 @@ ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX, ACT_MMDET_B
 OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
 NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
 PRED_ROWS, PRED_PLANES, PRED_CLS_LOGITS = 0, 1, 2
+DECODE_SIGMOID_OBJ, DECODE_SIGMOID_CLS, DECODE_NORMALISE, DECODE_XYXY = 1, 2, 4, 8
 SE_SLABS = 32
 DT_BF16, DT_F16 = 0, 1   # GLSDET_DT_*: 16-bit storage type of an activation / weight tensor
 
@@ -182,6 +183,8 @@ SIGNATURES = {
                                              C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_decode_outputs": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glsdet_decode_outputs_mode": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "glsdet_nms_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "glsdet_nms_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
                                     C.POINTER(C.c_void_p)]),
@@ -198,6 +201,8 @@ SIGNATURES = {
                                       C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_void_p,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "glsdet_batched_nms_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_int32,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms_workspace_bytes": (C.c_int64, [C.c_int32]),
 }
 

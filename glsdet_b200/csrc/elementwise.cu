@@ -192,9 +192,10 @@ struct DecodeLevels {
   int num;
 };
 
-// models/core/utils_bbox.py:254-306 - one thread per (image, anchor)
+// models/core/utils_bbox.py:254-306 and its variants (:36-251) - one thread per (image, anchor).
+// mode bits (GLSDET_DECODE_*): sigmoid on the objectness / on the classes, normalise by the input size, corner form.
 __global__ void __launch_bounds__(256) decode_kernel(DecodeLevels lv, int B, int A, int nch, float in_h, float in_w,
-                                                     float* __restrict__ pred) {
+                                                     float* __restrict__ pred, int mode) {
   const int64_t total = static_cast<int64_t>(B) * A;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -208,11 +209,24 @@ __global__ void __launch_bounds__(256) decode_kernel(DecodeLevels lv, int B, int
     const float stride = in_h / static_cast<float>(lv.h[l]);  // utils_bbox.py:285 (H-stride on both axes)
     const float* s = lv.ptr[l] + static_cast<int64_t>(b) * nch * hw + cell;
     float* o = pred + i * nch;
-    o[0] = ((__ldg(s) + static_cast<float>(gx)) * stride) / in_w;
-    o[1] = ((__ldg(s + hw) + static_cast<float>(gy)) * stride) / in_h;
-    o[2] = (expf(__ldg(s + 2 * static_cast<int64_t>(hw))) * stride) / in_w;
-    o[3] = (expf(__ldg(s + 3 * static_cast<int64_t>(hw))) * stride) / in_h;
-    for (int c = 4; c < nch; ++c) o[c] = 1.0f / (1.0f + expf(-__ldg(s + c * static_cast<int64_t>(hw))));
+    float cx = (__ldg(s) + static_cast<float>(gx)) * stride;
+    float cy = (__ldg(s + hw) + static_cast<float>(gy)) * stride;
+    float bw = expf(__ldg(s + 2 * static_cast<int64_t>(hw))) * stride;
+    float bh = expf(__ldg(s + 3 * static_cast<int64_t>(hw))) * stride;
+    if (mode & GLSDET_DECODE_NORMALISE) { cx = cx / in_w; cy = cy / in_h; bw = bw / in_w; bh = bh / in_h; }
+    if (mode & GLSDET_DECODE_XYXY) {   // utils_bbox.py:84-89: corners = centre -/+ size / 2 (explicit roundings, no FMA)
+      o[0] = __fsub_rn(cx, __fdiv_rn(bw, 2.0f)); o[1] = __fsub_rn(cy, __fdiv_rn(bh, 2.0f));
+      o[2] = __fadd_rn(cx, __fdiv_rn(bw, 2.0f)); o[3] = __fadd_rn(cy, __fdiv_rn(bh, 2.0f));
+    } else {
+      o[0] = cx; o[1] = cy; o[2] = bw; o[3] = bh;
+    }
+    const float ob = __ldg(s + 4 * static_cast<int64_t>(hw));
+    o[4] = (mode & GLSDET_DECODE_SIGMOID_OBJ) ? 1.0f / (1.0f + expf(-ob)) : ob;
+    if (mode & GLSDET_DECODE_SIGMOID_CLS) {
+      for (int c = 5; c < nch; ++c) o[c] = 1.0f / (1.0f + expf(-__ldg(s + c * static_cast<int64_t>(hw))));
+    } else {
+      for (int c = 5; c < nch; ++c) o[c] = __ldg(s + c * static_cast<int64_t>(hw));
+    }
   }
 }
 
@@ -361,7 +375,15 @@ extern "C" int glsdet_scale_pixel_shuffle_16(const void* x, const float* gate, v
 extern "C" int glsdet_decode_outputs(const float* const* levels, const int32_t* heights, const int32_t* widths,
                                      int32_t num_levels, int32_t batch, int32_t num_classes, int32_t in_h,
                                      int32_t in_w, float* pred, void* stream) {
+  return glsdet_decode_outputs_mode(levels, heights, widths, num_levels, batch, num_classes, in_h, in_w,
+                                    GLSDET_DECODE_SIGMOID_OBJ | GLSDET_DECODE_SIGMOID_CLS | GLSDET_DECODE_NORMALISE, pred, stream);
+}
+
+extern "C" int glsdet_decode_outputs_mode(const float* const* levels, const int32_t* heights, const int32_t* widths,
+                                          int32_t num_levels, int32_t batch, int32_t num_classes, int32_t in_h,
+                                          int32_t in_w, int32_t mode, float* pred, void* stream) {
   GLSDET_REQUIRE(levels && heights && widths && pred, "decode_outputs: null pointer");
+  GLSDET_REQUIRE(mode >= 0 && mode < 16, "decode_outputs: bad mode %d", mode);
   GLSDET_REQUIRE(num_levels > 0 && num_levels <= 8, "decode_outputs: 1..8 levels supported (got %d)", num_levels);
   GLSDET_REQUIRE(batch > 0 && num_classes > 0 && in_h > 0 && in_w > 0, "decode_outputs: bad sizes");
   DecodeLevels lv;
@@ -377,7 +399,7 @@ extern "C" int glsdet_decode_outputs(const float* const* levels, const int32_t* 
   const int64_t cap = static_cast<int64_t>(device_sm_count()) * 32;
   if (blocks > cap) blocks = cap;
   decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      lv, batch, a, 5 + num_classes, static_cast<float>(in_h), static_cast<float>(in_w), pred);
+      lv, batch, a, 5 + num_classes, static_cast<float>(in_h), static_cast<float>(in_w), pred, static_cast<int>(mode));
   return count_launch("decode_kernel");
 }
 

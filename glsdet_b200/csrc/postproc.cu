@@ -5,9 +5,13 @@
 //
 // NMS proper, per (image, class) segment of n score-sorted boxes:
 //   1. mask_tiles_kernel  - all 64x64 IoU tiles of the upper triangle, one 64-bit suppression word per (row,
-//      column tile), computed by the whole GPU (persistent CTAs pulling tiles from a device-side work list);
-//   2. scan_kernel        - one CTA per segment walks the 64-box chunks in order: the diagonal word resolves the
-//      chunk greedily, the kept rows' words are OR-ed into the 'removed' bitmap of the later chunks.
+//      column tile), computed by the whole GPU (persistent CTAs pulling tiles from a device-side work list), plus the
+//      in-degree of every box (how many better boxes overlap it beyond the threshold);
+//   2. resolve_kernel     - greedy NMS as a propagation over that sparse DAG, one CTA per segment: a box is KEPT once
+//      all better overlapping boxes are known to be suppressed (in-degree counted down to zero) and SUPPRESSED as soon as
+//      one kept box overlaps it.  Kept boxes mark their targets removed, suppressed boxes release theirs; every round
+//      handles the whole frontier in parallel, and the number of rounds is the longest kept/suppressed alternation in a
+//      cluster of boxes (a handful), not the number of 64-box chunks of the segment.  Same keep set as the serial walk.
 //   Segments whose mask does not fit the workspace budget fall back to nms_segment_kernel (blocked greedy against
 //   the kept list, no mask memory).  Both are the same greedy algorithm and give identical keep sets.
 //
@@ -24,31 +28,35 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <new>
+#include <utility>
+#include <vector>
 
 #include "../../include/glsdet_b200.h"
 #include "common.h"
 
 namespace glsdet {
 
-constexpr int kSortChunk = 4096;    // keys sorted per CTA in shared memory
-constexpr int kSortThreads = 512;
+constexpr int kSortMin = 1024;        // smallest sort extent (the key array is padded to a power of two)
+constexpr int kSortSmemKeys = 16384;  // keys one CTA sorts entirely in shared memory (128 KB)
+constexpr int kSortThreads = 1024;
 constexpr int kNmsThreads = 1024;   // 8 warps per scheduler: the kept-list sweep of a chunk is latency-bound
 constexpr int kKeptSmem = 1536;     // kept boxes cached in shared memory per segment
 constexpr int kMaxClasses = 256;    // 8 label bits in the sort key
 constexpr uint64_t kPadKey = ~0ull;
 
-// key = [63:56] label (0 when the image runs class-agnostic) | [55:24] ~score bits | [23:0] anchor index
-__device__ __forceinline__ uint64_t make_key(uint32_t label, float score, uint32_t idx) {
-  return (static_cast<uint64_t>(label) << 56) | (static_cast<uint64_t>(~__float_as_uint(score)) << 24) | idx;
-}
-__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return static_cast<uint32_t>(k & 0xFFFFFFu); }
-__device__ __forceinline__ float key_score(uint64_t k) { return __uint_as_float(~static_cast<uint32_t>(k >> 24)); }
-
 __device__ __forceinline__ uint32_t float_order_bits(float f) {
   const uint32_t b = __float_as_uint(f);
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+// key = [63:56] label (0 when the image runs class-agnostic) | [55:24] ~(order-preserving score bits) | [23:0] index.
+// float_order_bits is monotonic over ALL floats (caller-supplied scores may be negative, e.g. raw logits), so ascending
+// keys = descending scores, ties by ascending index - the stable descending sort of torchvision.
+__device__ __forceinline__ uint64_t make_key(uint32_t label, float score, uint32_t idx) {
+  return (static_cast<uint64_t>(label) << 56) | (static_cast<uint64_t>(~float_order_bits(score)) << 24) | idx;
+}
+__device__ __forceinline__ uint32_t key_idx(uint64_t k) { return static_cast<uint32_t>(k & 0xFFFFFFu); }
 __device__ __forceinline__ float order_bits_float(uint32_t e) {
   return __uint_as_float((e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e);
 }
@@ -62,6 +70,8 @@ struct Source {
   const float* boxes;
   const float* scores;
   const float* labels;
+  const int32_t* label_ids;  // optional dense class ids 0..255 of the caller-supplied labels (sort key / segments); the
+                             // coordinate-trick offsets always use the original label values
   const float* box_div;  // optional [B][4] divisors of the corner boxes (mmdet rescale), pred mode only
 };
 
@@ -101,12 +111,15 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
       // (normally one per anchor), and the first index attaining the maximum wins, as torch.max does.
       float m = __ldg(r + 5 * sc);
       for (int k = 1; k < s.nc; ++k) m = fmaxf(m, __ldg(r + (5 + k) * sc));
+      // window below the largest logit m inside which another class can round to the same fp32 probability: the sigmoid's
+      // slope is e^-m for large m while one ulp of a probability near 1 is 2^-24, so the window grows like 2^-23 e^m;
+      // from m = 9 on (window 1e-3) every logit above 9 is evaluated, below that 1e-3 * max(1, |m|) covers it
       const float lim = m - 1e-3f * fmaxf(1.0f, fabsf(m));
       const bool all = (m < -80.0f);
       best = -1.0f;
       for (int k = 0; k < s.nc; ++k) {
         const float x = __ldg(r + (5 + k) * sc);
-        if (all || x >= lim || x > 15.0f) {
+        if (all || x >= lim || x > 9.0f) {
           const float v = 1.0f / (1.0f + expf(-x));
           if (v > best) { best = v; arg = k; }
         }
@@ -126,7 +139,7 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
     c.obj = __ldg(s.scores + idx);
     c.cls_conf = 1.0f;
     c.label_f = __ldg(s.labels + idx);
-    c.label = static_cast<int>(c.label_f);
+    c.label = s.label_ids ? __ldg(s.label_ids + idx) : static_cast<int>(c.label_f);
   }
   return c;
 }
@@ -147,9 +160,14 @@ struct Work {
   float4* nbox;          // [B][cap]   NMS-space box of every sorted candidate (offset applied for the trick)
   int32_t* seg_tile_off; // [B*nc + 1] exclusive prefix of per-segment tile counts (mask path)
   int64_t* seg_word_off; // [B*nc]     first mask word of the segment, or -1 when it runs on the fallback kernel
-  unsigned long long* row_any;  // [B][P/64] bit i set: sorted candidate i suppresses at least one later box
+  int32_t* pending;      // [B][cap]   in-degree of every sorted candidate: better boxes of its segment that overlap it beyond thr
+  unsigned long long* row_tiles;  // [B][cap]  per sorted candidate: which column tiles of its mask row hold suppression bits
+                                  // (bit k covers column tiles [k << shift, (k + 1) << shift), shift = tile_shift(T));
+                                  // zero = the box suppresses nothing
   unsigned long long* mask;  // [mask_words]
   int64_t mask_words;
+  float trick_label_max;     // largest |label| (labels integral), or < 0: the coordinate trick may only be decomposed by
+                             // class when distinct labels are at least 1 apart and every offset stays below 2^21
   int32_t max_scan_tiles;    // segments with more 64-box chunks than this use the fallback kernel
   int32_t topk;              // > 0: only the `topk` best kept boxes per image are wanted (max_det) and the kept list of
                              // a segment fits shared memory: every segment runs on the blocked-greedy kernel, which
@@ -177,7 +195,8 @@ __device__ __forceinline__ ImageMode image_mode(const Work& w, int b, int strate
   m.offset_scale = __fadd_rn(maxc, 1.0f);
   // class separation needs a positive gap after rounding: min >= -0.5 leaves 0.5, and offsets below 2^21 keep
   // every rounding error under 0.125
-  m.per_class = !trick || (n > 0 && minc >= -0.5f && static_cast<float>(w.nc) * m.offset_scale < 2097152.0f);
+  m.per_class = !trick || (n > 0 && minc >= -0.5f && w.trick_label_max >= 0.0f &&
+                           (w.trick_label_max + 1.0f) * m.offset_scale < 2097152.0f);
   // mmcv: from split_thr = 10000 boxes on, NMS runs class by class (on the shifted boxes)
   if (strategy == GLSDET_NMS_MMCV && n >= 10000) m.per_class = true;
   return m;
@@ -256,7 +275,7 @@ __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float con
 }
 
 __device__ __forceinline__ int sort_extent(int n) {
-  int p = kSortChunk;
+  int p = kSortMin;
   while (p < n) p <<= 1;
   return p;
 }
@@ -274,7 +293,8 @@ __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
       k = make_key(m.per_class ? w.cand_label[o] : 0u, w.cand_score[o], static_cast<uint32_t>(w.cand_idx[o]));
     }
     w.keys[static_cast<int64_t>(b) * w.P + i] = k;
-    if ((i & 63) == 0) w.row_any[static_cast<int64_t>(b) * (w.P >> 6) + (i >> 6)] = 0ull;
+    if (i < w.cap) w.pending[static_cast<int64_t>(b) * w.cap + i] = 0;
+    if (i < w.cap) w.row_tiles[static_cast<int64_t>(b) * w.cap + i] = 0ull;
   }
 }
 
@@ -283,65 +303,58 @@ __device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
   if ((a > b) == asc) { const uint64_t t = a; a = b; b = t; }
 }
 
-// sorts every kSortChunk-sized chunk (all levels k <= kSortChunk), direction alternating by global index
-__global__ void __launch_bounds__(kSortThreads) bitonic_local_sort_kernel(Work w) {
+// One CTA sorts the keys of one image (ascending = label, score desc, index asc).  Up to kSortSmemKeys keys the whole
+// network runs in shared memory - one launch instead of the 21 of a multi-kernel bitonic sort, whose global steps were
+// pure launch latency at <= 12 k keys per image.  Larger images (every anchor a candidate) run the levels above the
+// chunk size as global-memory steps of the same CTA and the rest chunk by chunk in shared memory.
+__global__ void __launch_bounds__(kSortThreads) sort_keys_kernel(Work w) {
   pdl_prologue();
-  __shared__ uint64_t sk[kSortChunk];
-  const int b = blockIdx.y;
+  extern __shared__ uint64_t sk[];
+  const int b = blockIdx.x;
   const int pb = sort_extent(w.cand_count[b]);
-  const int base = blockIdx.x * kSortChunk;
-  if (base >= pb) return;
-  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P + base;
-  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = g[i];
-  __syncthreads();
-  for (int k = 2; k <= kSortChunk; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < kSortChunk / 2; t += kSortThreads) {
+  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
+  const int chunk = pb < kSortSmemKeys ? pb : kSortSmemKeys;
+  // levels k <= chunk: every chunk is sorted on its own, direction alternating by global index
+  for (int base = 0; base < pb; base += chunk) {
+    for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = g[base + i];
+    __syncthreads();
+    for (int k = 2; k <= chunk; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < chunk / 2; t += kSortThreads) {
+          const int i = 2 * j * (t / j) + (t % j);
+          cmp_swap(sk[i], sk[i + j], ((base + i) & k) == 0);
+        }
+        __syncthreads();
+      }
+    }
+    for (int i = threadIdx.x; i < chunk; i += kSortThreads) g[base + i] = sk[i];
+    __syncthreads();
+  }
+  // levels k > chunk: distances >= chunk through global memory (same CTA: __syncthreads orders them), then each chunk
+  // finishes the level in shared memory
+  for (int k = 2 * chunk; k <= pb; k <<= 1) {
+    for (int j = k >> 1; j >= chunk; j >>= 1) {
+      for (int t = threadIdx.x; t < pb / 2; t += kSortThreads) {
         const int i = 2 * j * (t / j) + (t % j);
-        const bool asc = (((base + i) & k) == 0);
-        cmp_swap(sk[i], sk[i + j], asc);
+        uint64_t a = g[i], c = g[i + j];
+        if ((a > c) == ((i & k) == 0)) { g[i] = c; g[i + j] = a; }
       }
       __syncthreads();
     }
-  }
-  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) g[i] = sk[i];
-}
-
-// one compare-exchange step (level k, distance j >= kSortChunk) over the whole padded array
-__global__ void __launch_bounds__(256) bitonic_global_step_kernel(Work w, int k, int j) {
-  pdl_prologue();
-  const int b = blockIdx.y;
-  const int pb = sort_extent(w.cand_count[b]);
-  if (k > pb) return;
-  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < pb / 2; t += gridDim.x * blockDim.x) {
-    const int i = 2 * j * (t / j) + (t % j);
-    const bool asc = ((i & k) == 0);
-    uint64_t a = g[i], c = g[i + j];
-    if ((a > c) == asc) { g[i] = c; g[i + j] = a; }
-  }
-}
-
-// finishes level k inside each chunk (distances kSortChunk/2 .. 1)
-__global__ void __launch_bounds__(kSortThreads) bitonic_local_merge_kernel(Work w, int k) {
-  pdl_prologue();
-  __shared__ uint64_t sk[kSortChunk];
-  const int b = blockIdx.y;
-  const int pb = sort_extent(w.cand_count[b]);
-  const int base = blockIdx.x * kSortChunk;
-  if (k > pb || base >= pb) return;
-  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P + base;
-  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) sk[i] = g[i];
-  __syncthreads();
-  for (int j = kSortChunk >> 1; j > 0; j >>= 1) {
-    for (int t = threadIdx.x; t < kSortChunk / 2; t += kSortThreads) {
-      const int i = 2 * j * (t / j) + (t % j);
-      const bool asc = (((base + i) & k) == 0);
-      cmp_swap(sk[i], sk[i + j], asc);
+    for (int base = 0; base < pb; base += chunk) {
+      for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = g[base + i];
+      __syncthreads();
+      for (int j = chunk >> 1; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < chunk / 2; t += kSortThreads) {
+          const int i = 2 * j * (t / j) + (t % j);
+          cmp_swap(sk[i], sk[i + j], ((base + i) & k) == 0);
+        }
+        __syncthreads();
+      }
+      for (int i = threadIdx.x; i < chunk; i += kSortThreads) g[base + i] = sk[i];
+      __syncthreads();
     }
-    __syncthreads();
   }
-  for (int i = threadIdx.x; i < kSortChunk; i += kSortThreads) g[i] = sk[i];
 }
 
 // ---------------------------------------------------------------------------------------------- segments
@@ -409,6 +422,13 @@ __device__ __forceinline__ int64_t tri_tile(int T, int r, int c) {
   return static_cast<int64_t>(r) * T - (static_cast<int64_t>(r) * (r - 1)) / 2 + (c - r);
 }
 __device__ __forceinline__ int64_t tri_word(int T, int r, int i, int c) { return tri_tile(T, r, c) * 64 + i; }
+
+// column tiles per bit of a row's tile bitmap: the smallest power of two that maps T tiles onto 64 bits
+__device__ __forceinline__ int tile_shift(int T) {
+  int s = 0;
+  while (((T - 1) >> s) > 63) ++s;
+  return s;
+}
 
 __device__ __forceinline__ float box_area(const float4& b) {
   return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
@@ -507,46 +527,70 @@ __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, fl
       const float4 rb = bx[ri];
       const float ra = box_area(rb);
       const int jn = min(64, n - cc * 64);
-      const int j0 = (cc == r) ? tid + 1 : 0;
       if (thr_nonneg) {
-        // common case first: two subtractions decide "no overlap" (inter == 0 never exceeds thr >= 0); the exact
-        // IEEE division runs only for the few pairs that really intersect
+        // Phase 1, branch-free: which column boxes intersect this row box at all (inter == 0 never exceeds thr >= 0).
+        // Phase 2: the exact IEEE IoU only for those - a few per row.  Fused into one loop, the division ran whenever
+        // ANY of the 32 rows of the warp intersected the column box, i.e. on most iterations.
         uint32_t lo = 0u, hi = 0u;
-#pragma unroll 4
-        for (int j = j0; j < jn; ++j) {
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
           const float4 cb = cbox[grp][j];
           const float ww = __fsub_rn(fminf(rb.z, cb.z), fmaxf(rb.x, cb.x));
           const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
-          if (fminf(ww, hh) > 0.0f) {
-            if (iou_exceeds(rb, ra, cb, carea[grp][j], thr, true)) {
-              if (j < 32) lo |= 1u << j; else hi |= 1u << (j - 32);
-            }
-          }
+          lo |= (fminf(ww, hh) > 0.0f ? 1u : 0u) << j;
         }
-        bits = (static_cast<unsigned long long>(hi) << 32) | lo;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) {
+          const float4 cb = cbox[grp][32 + j];
+          const float ww = __fsub_rn(fminf(rb.z, cb.z), fmaxf(rb.x, cb.x));
+          const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
+          hi |= (fminf(ww, hh) > 0.0f ? 1u : 0u) << j;
+        }
+        unsigned long long m = (static_cast<unsigned long long>(hi) << 32) | lo;
+        if (jn < 64) m &= (1ull << jn) - 1ull;                       // stale columns of a ragged tile
+        if (cc == r) m &= (tid < 63) ? ~((2ull << tid) - 1ull) : 0ull;   // diagonal tile: later boxes only
+        while (m) {
+          const int j = __ffsll(static_cast<long long>(m)) - 1;
+          m &= m - 1ull;
+          if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, true)) bits |= 1ull << j;
+        }
       } else {
+        const int j0 = (cc == r) ? tid + 1 : 0;
         for (int j = j0; j < jn; ++j)
           if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, false)) bits |= (1ull << j);
       }
-      if (bits) atomicOr(&w.row_any[static_cast<int64_t>(b) * (w.P >> 6) + ((s0 + ri) >> 6)], 1ull << ((s0 + ri) & 63));
+      if (bits) {
+        atomicOr(&w.row_tiles[static_cast<int64_t>(b) * w.cap + s0 + ri], 1ull << (cc >> tile_shift(T)));
+        // in-degree of the suppressed boxes (sparse: a few bits per row)
+        int32_t* pend = w.pending + static_cast<int64_t>(b) * w.cap + s0 + cc * 64;
+        unsigned long long m = bits;
+        while (m) {
+          const int j = __ffsll(static_cast<long long>(m)) - 1;
+          m &= m - 1ull;
+          atomicAdd(pend + j, 1);
+        }
+      }
     }
     w.mask[w.seg_word_off[sgm] + tri_word(T, r, tid, cc)] = bits;
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
   }
 }
 
-// One CTA per mask-path segment: sequential over 64-box chunks, parallel inside.  Suppression is sparse (most
-// boxes suppress nothing), so only rows flagged in row_any are ever read from the mask, and the serial part of a
-// chunk only walks the flagged rows.  The diagonal words of chunk r+1 are prefetched while chunk r is resolved.
-constexpr int kScanThreads = 512;
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
+// One CTA per mask-path segment: greedy NMS as a propagation over the sparse suppression DAG (edges = mask bits, from
+// the better box to the worse one; pending = in-degree).
+//   kept(j)       <=>  every better neighbour of j is suppressed   (pending[j] counted down to 0)
+//   suppressed(j) <=>  some better neighbour of j is kept          (removed bit set by that neighbour)
+// Round 0 keeps every box without a better neighbour.  Each later round takes the boxes decided in the previous one
+// (only those with outgoing edges are listed): a kept box marks its targets removed, a suppressed box releases its
+// targets (pending - 1; at zero the target is kept).  One thread per listed box: its row's tile bitmap names the few
+// mask words that hold its edges.  The rounds needed = the longest kept / suppressed alternation among overlapping
+// boxes, independent of the segment length.
+constexpr int kResolveThreads = 1024;
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(Work w) {
   pdl_prologue();
-  extern __shared__ unsigned long long scan_smem[];  // removed[T] | any[T]
-  __shared__ unsigned long long diag[2][64];
-  __shared__ unsigned long long kept_bits_s;
-  __shared__ int sup_rows[64];
-  __shared__ int sup_n;
-  __shared__ int kept_n;
+  extern __shared__ uint32_t resolve_smem[];  // removed[W] | keptb[W]
+  __shared__ int list_n[2];
+  __shared__ int warp_tot[kResolveThreads / 32];
   const int seg = blockIdx.x, b = blockIdx.y;
   const int sgm = b * w.nc + seg;
   const int64_t woff = w.seg_word_off[sgm];
@@ -554,84 +598,108 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(Work w) {
   const int s0 = w.seg_start[b * (w.nc + 1) + seg];
   const int n = w.seg_start[b * (w.nc + 1) + seg + 1] - s0;
   const int T = (n + 63) >> 6;
-  unsigned long long* removed = scan_smem;
-  unsigned long long* any_s = scan_smem + T;
+  const int W = (n + 31) >> 5;
+  const int shift = tile_shift(T);
+  uint32_t* removed = resolve_smem;
+  uint32_t* keptb = resolve_smem + W;
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
   const unsigned long long* mask = w.mask + woff;
-  const unsigned long long* any_words = w.row_any + static_cast<int64_t>(b) * (w.P >> 6);
+  const unsigned long long* row_tiles = w.row_tiles + static_cast<int64_t>(b) * w.cap + s0;
+  int32_t* pend = w.pending + static_cast<int64_t>(b) * w.cap + s0;
+  // the kept-box spill area (16 bytes per box) is unused on the mask path: two frontier lists of n entries each
+  int32_t* lists = reinterpret_cast<int32_t*>(w.kept_box + static_cast<int64_t>(b) * w.cap + s0);
   const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
   uint64_t* gk_key = w.kept_key + static_cast<int64_t>(b) * w.cap + s0;
-  for (int r = tid; r < T; r += kScanThreads) {
-    removed[r] = 0ull;
-    // 64 'suppresses something' flags of chunk r (the segment need not start on a word boundary)
-    const int g0 = s0 + r * 64;
-    unsigned long long any = any_words[g0 >> 6] >> (g0 & 63);
-    if (g0 & 63) any |= any_words[(g0 >> 6) + 1] << (64 - (g0 & 63));
-    const int mc = min(64, n - r * 64);
-    if (mc < 64) any &= ((1ull << mc) - 1ull);
-    any_s[r] = any;
-  }
-  if (tid == 0) kept_n = 0;
+  for (int i = tid; i < 2 * W; i += kResolveThreads) resolve_smem[i] = 0u;
+  if (tid < 2) list_n[tid] = 0;
   __syncthreads();
-  if (tid < 64) {
-    const unsigned long long a0 = any_s[0];
-    diag[0][tid] = ((a0 >> tid) & 1ull) ? mask[tri_word(T, 0, tid, 0)] : 0ull;
+  // round 0: boxes nobody better overlaps
+  for (int j = tid; j < n; j += kResolveThreads) {
+    if (pend[j] == 0) {
+      atomicOr(&keptb[j >> 5], 1u << (j & 31));
+      if (row_tiles[j] != 0ull) lists[atomicAdd(&list_n[0], 1)] = j;
+    }
   }
   __syncthreads();
-  for (int r = 0; r < T; ++r) {
-    const int mcnt = min(64, n - r * 64);
-    const int cur = r & 1;
-    const unsigned long long any = any_s[r];
-    // prefetch: keys of this chunk, diagonal words of the next one (both independent of the resolve below)
-    uint64_t my_key = 0;
-    if (tid < mcnt) my_key = keys[r * 64 + tid];
-    unsigned long long next_diag = 0ull;
-    if (tid >= 64 && tid < 128 && r + 1 < T) {
-      const int i = tid - 64;
-      if ((any_s[r + 1] >> i) & 1ull) next_diag = mask[tri_word(T, r + 1, i, r + 1)];
-    }
-    if (tid == 0) {
-      unsigned long long alive = ~removed[r];
-      if (mcnt < 64) alive &= ((1ull << mcnt) - 1ull);
-      int ns = 0;
-      unsigned long long m = alive & any;   // only flagged rows can suppress; walk them in score order
-      while (m) {
-        const int i = __ffsll(static_cast<long long>(m)) - 1;
-        m &= m - 1ull;
-        if ((alive >> i) & 1ull) {
-          const unsigned long long d = diag[cur][i];
-          alive &= ~d;
-          m &= ~d;
-          sup_rows[ns++] = i;
-        }
-      }
-      kept_bits_s = alive;
-      sup_n = ns;
-    }
+  int cur = 0;
+  while (true) {
+    const int cnt = list_n[cur];
+    if (cnt == 0) break;
+    const int nxt = cur ^ 1;
+    __syncthreads();               // everybody has read list_n[cur] ...
+    if (tid == 0) list_n[nxt] = 0; // ... and nobody pushes before the next barrier
     __syncthreads();
-    const unsigned long long kept = kept_bits_s;
-    const int ns = sup_n;
-    const int kn = kept_n;
-    if (tid < mcnt && ((kept >> tid) & 1ull))
-      gk_key[kn + __popcll(kept & ((1ull << tid) - 1ull))] = my_key & 0x00FFFFFFFFFFFFFFull;
-    if (tid >= 64 && tid < 128) diag[cur ^ 1][tid - 64] = next_diag;
-    // OR the kept, suppressing rows into the bitmap of the later chunks: warps take rows, lanes take column tiles
-    const int ncol = T - r - 1;
-    if (ncol > 0 && ns > 0) {
-      const int64_t tbase = tri_tile(T, r, r + 1) * 64;
-      for (int k = warp; k < ns; k += kScanThreads / 32) {
-        const int i = sup_rows[k];
-        for (int c = lane; c < ncol; c += 32) {
-          const unsigned long long mm = mask[tbase + static_cast<int64_t>(c) * 64 + i];
-          if (mm) atomicOr(&removed[r + 1 + c], mm);
+    const int32_t* in = lists + cur * n;
+    int32_t* out = lists + nxt * n;
+    for (int e = tid; e < cnt; e += kResolveThreads) {
+      const int ent = in[e];
+      const int i = ent & 0x7FFFFFFF;
+      const bool kept_i = ent >= 0;
+      const int r = i >> 6;
+      const int64_t rbase = tri_tile(T, r, r) * 64 + (i & 63);   // word of column tile c: rbase + (c - r) * 64
+      unsigned long long tw = row_tiles[i];
+      while (tw) {
+        const int k = __ffsll(static_cast<long long>(tw)) - 1;
+        tw &= tw - 1ull;
+        const int c_lo = max(k << shift, r), c_hi = min((k + 1) << shift, T);
+        for (int c = c_lo; c < c_hi; ++c) {
+          unsigned long long word = mask[rbase + static_cast<int64_t>(c - r) * 64];
+          while (word) {
+            const int jb = __ffsll(static_cast<long long>(word)) - 1;
+            word &= word - 1ull;
+            const int j = c * 64 + jb;
+            const uint32_t bit = 1u << (j & 31);
+            if (kept_i) {
+              const uint32_t old = atomicOr(&removed[j >> 5], bit);
+              if (!(old & bit) && row_tiles[j] != 0ull) out[atomicAdd(&list_n[nxt], 1)] = j | static_cast<int>(0x80000000u);
+            } else if (!(removed[j >> 5] & bit)) {
+              // a kept better neighbour never releases, so pending reaches zero only if all of them are suppressed
+              if (atomicSub(&pend[j], 1) == 1) {
+                atomicOr(&keptb[j >> 5], bit);
+                if (row_tiles[j] != 0ull) out[atomicAdd(&list_n[nxt], 1)] = j;
+              }
+            }
+          }
         }
       }
     }
     __syncthreads();
-    if (tid == 0) kept_n = kn + __popcll(kept);  // read again only after the next barrier
+    cur = nxt;
   }
-  if (tid == 0) w.seg_kept[sgm] = kept_n;
+  // kept boxes in score order: exclusive prefix of the per-word popcounts (contiguous words per thread)
+  const int per = (W + kResolveThreads - 1) / kResolveThreads;
+  const int w_lo = min(tid * per, W), w_hi = min(w_lo + per, W);
+  int mine = 0;
+  for (int i = w_lo; i < w_hi; ++i) mine += __popc(keptb[i]);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int v = tid < kResolveThreads / 32 ? warp_tot[tid] : 0;
+    int sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, sc, o);
+      if (tid >= o) sc += u;
+    }
+    if (tid < kResolveThreads / 32) warp_tot[tid] = sc - v;   // exclusive
+    if (tid == 31) w.seg_kept[sgm] = sc;
+  }
+  __syncthreads();
+  int pos = warp_tot[tid >> 5] + incl - mine;
+  for (int i = w_lo; i < w_hi; ++i) {
+    uint32_t bits = keptb[i];
+    while (bits) {
+      const int jb = __ffs(static_cast<int>(bits)) - 1;
+      bits &= bits - 1u;
+      gk_key[pos++] = keys[i * 32 + jb] & 0x00FFFFFFFFFFFFFFull;
+    }
+  }
 }
 
 template <bool kFromPred>
@@ -802,10 +870,10 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
-      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowany, off_mask, mask_words, total;
+      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowtiles, off_pending, off_mask, mask_words, total;
 };
 
-constexpr int kMaxScanTiles = 2816;  // 2 x 22 KB of shared memory for the 'removed' and 'any' bitmaps
+constexpr int kMaxScanTiles = 2816;  // 2 x 22 KB of shared memory for the 'removed' and 'kept' bitmaps of a segment
 
 inline int64_t mask_budget_words(int B, int cap) {
   int64_t bytes = static_cast<int64_t>(B) * cap * 768;
@@ -831,7 +899,8 @@ Layout make_layout(int B, int cap, int P, int nc) {
   l.off_nbox = o; o = align_up(o + 16ll * B * cap, 256);
   l.off_tileoff = o; o = align_up(o + 4ll * (static_cast<int64_t>(B) * nc + 1), 256);
   l.off_wordoff = o; o = align_up(o + 8ll * B * nc, 256);
-  l.off_rowany = o; o = align_up(o + 8ll * B * (P / 64 + 2), 256);
+  l.off_rowtiles = o; o = align_up(o + 8ll * B * cap, 256);
+  l.off_pending = o; o = align_up(o + 4ll * B * cap, 256);
   l.mask_words = mask_budget_words(B, cap);
   l.off_mask = o; o = align_up(o + 8ll * l.mask_words, 256);
   l.total = o;
@@ -839,7 +908,7 @@ Layout make_layout(int B, int cap, int P, int nc) {
 }
 
 Work make_work(void* ws, int B, int cap, int nc) {
-  const int P = pow2_ceil(cap < kSortChunk ? kSortChunk : cap);
+  const int P = pow2_ceil(cap < kSortMin ? kSortMin : cap);
   const Layout l = make_layout(B, cap, P, nc);
   uint8_t* p = static_cast<uint8_t*>(ws);
   Work w;
@@ -858,7 +927,8 @@ Work make_work(void* ws, int B, int cap, int nc) {
   w.nbox = reinterpret_cast<float4*>(p + l.off_nbox);
   w.seg_tile_off = reinterpret_cast<int32_t*>(p + l.off_tileoff);
   w.seg_word_off = reinterpret_cast<int64_t*>(p + l.off_wordoff);
-  w.row_any = reinterpret_cast<unsigned long long*>(p + l.off_rowany);
+  w.row_tiles = reinterpret_cast<unsigned long long*>(p + l.off_rowtiles);
+  w.pending = reinterpret_cast<int32_t*>(p + l.off_pending);
   w.mask = reinterpret_cast<unsigned long long*>(p + l.off_mask);
   w.mask_words = l.mask_words;
   if (const char* e = getenv("GLSDET_NMS_MASK_WORDS")) {  // tests: shrink the budget to force the fallback kernel
@@ -867,12 +937,27 @@ Work make_work(void* ws, int B, int cap, int nc) {
   }
   w.max_scan_tiles = kMaxScanTiles;
   w.topk = 0;
+  w.trick_label_max = static_cast<float>(nc - 1);
   return w;
 }
 
 int64_t workspace_bytes(int B, int cap, int nc) {
-  const int P = pow2_ceil(cap < kSortChunk ? kSortChunk : cap);
+  const int P = pow2_ceil(cap < kSortMin ? kSortMin : cap);
   return make_layout(B, cap, P, nc).total;
+}
+
+// opt-in to more than 48 KB of dynamic shared memory, once per device and kernel
+int ensure_smem_attr(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  GLSDET_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& d : done)
+    if (d.first == kernel && d.second == dev) return 0;
+  GLSDET_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(kernel, dev);
+  return 0;
 }
 
 template <bool kFromPred>
@@ -893,18 +978,11 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
     launch_pdl(build_keys_kernel, dim3(gx, B), 256, 0, st, w, strategy);
     if (int rc = count_launch("build_keys_kernel")) return rc;
   }
-  const int chunks = w.P / kSortChunk;
-  launch_pdl(bitonic_local_sort_kernel, dim3(chunks, B), kSortThreads, 0, st, w);
-  if (int rc = count_launch("bitonic_local_sort_kernel")) return rc;
-  for (int k = 2 * kSortChunk; k <= w.P; k <<= 1) {
-    for (int j = k >> 1; j >= kSortChunk; j >>= 1) {
-      int gx = w.P / 2 / 256;
-      if (gx > 2048) gx = 2048;
-      launch_pdl(bitonic_global_step_kernel, dim3(gx, B), 256, 0, st, w, k, j);
-      if (int rc = count_launch("bitonic_global_step_kernel")) return rc;
-    }
-    launch_pdl(bitonic_local_merge_kernel, dim3(chunks, B), kSortThreads, 0, st, w, k);
-    if (int rc = count_launch("bitonic_local_merge_kernel")) return rc;
+  {
+    const int keys = w.P < kSortSmemKeys ? w.P : kSortSmemKeys;
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(sort_keys_kernel), kSortSmemKeys * 8)) return rc;
+    launch_pdl(sort_keys_kernel, B, kSortThreads, static_cast<size_t>(keys) * 8, st, w);
+    if (int rc = count_launch("sort_keys_kernel")) return rc;
   }
   launch_pdl(segment_bounds_kernel, B, 256, 0, st, w, strategy);
   if (int rc = count_launch("segment_bounds_kernel")) return rc;
@@ -923,8 +1001,8 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   if (w.topk == 0) {
     int t = (w.cap + 63) / 64;
     if (t > kMaxScanTiles) t = kMaxScanTiles;
-    launch_pdl(scan_kernel, dim3(w.nc, B), kScanThreads, static_cast<size_t>(t) * 16, st, w);
-    if (int rc = count_launch("scan_kernel")) return rc;
+    launch_pdl(resolve_kernel, dim3(w.nc, B), kResolveThreads, static_cast<size_t>(t) * 16, st, w);
+    if (int rc = count_launch("resolve_kernel")) return rc;
   }
   launch_pdl(nms_segment_kernel<kFromPred>, dim3(w.nc, B), kNmsThreads, 0, st, s, w, nms_thres, strategy);
   if (int rc = count_launch("nms_segment_kernel")) return rc;
@@ -1007,6 +1085,13 @@ extern "C" int64_t glsdet_batched_nms_workspace_bytes(int32_t k) {
 extern "C" int glsdet_batched_nms(const float* boxes, const float* scores, const float* labels, int32_t k,
                                   float nms_thres, int32_t strategy, void* workspace, int64_t workspace_bytes_given,
                                   int32_t* keep, int32_t* keep_count, void* stream) {
+  return glsdet_batched_nms_ids(boxes, scores, labels, nullptr, 255.0f, k, nms_thres, strategy, workspace,
+                                workspace_bytes_given, keep, keep_count, stream);
+}
+
+extern "C" int glsdet_batched_nms_ids(const float* boxes, const float* scores, const float* labels, const int32_t* label_ids,
+                                      float label_abs_max, int32_t k, float nms_thres, int32_t strategy, void* workspace,
+                                      int64_t workspace_bytes_given, int32_t* keep, int32_t* keep_count, void* stream) {
   GLSDET_REQUIRE(keep_count != nullptr, "batched_nms: null keep_count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (k <= 0) {
@@ -1020,9 +1105,10 @@ extern "C" int glsdet_batched_nms(const float* boxes, const float* scores, const
   GLSDET_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
                  "batched_nms: workspace must be 256-byte aligned");
   GLSDET_REQUIRE(workspace_bytes_given >= workspace_bytes(1, k, kMaxClasses), "batched_nms: workspace too small");
-  const Work w = make_work(workspace, 1, k, kMaxClasses);
+  Work w = make_work(workspace, 1, k, kMaxClasses);
+  w.trick_label_max = label_abs_max;
   Source s{};
   s.A = k; s.nch = 0; s.nc = kMaxClasses;
-  s.boxes = boxes; s.scores = scores; s.labels = labels;
+  s.boxes = boxes; s.scores = scores; s.labels = labels; s.label_ids = label_ids;
   return run_pipeline<false>(s, w, 0.0f, nms_thres, strategy, k, nullptr, keep_count, keep, st);
 }

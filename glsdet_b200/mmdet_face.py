@@ -164,7 +164,7 @@ class YOLOXPAFPN(_PlanOwner):
 
     def _plan_state_dict(self):
         out = {}
-        for k, v in self.state_dict().items():
+        for k, v in self._source_state_dict().items():
             if k.startswith("out_convs."):
                 out["head.stems." + k[len("out_convs."):]] = v
                 continue
@@ -242,7 +242,7 @@ class YOLOXHead(_PlanOwner):
                ("multi_level_conv_cls.", "cls_preds."), ("multi_level_conv_reg.", "reg_preds."),
                ("multi_level_conv_obj.", "obj_preds."))
         out = {}
-        for k, v in self.state_dict().items():
+        for k, v in self._source_state_dict().items():
             for a, b in ren:
                 if k.startswith(a):
                     k = b + k[len(a):]
@@ -304,14 +304,13 @@ class YOLOXHead(_PlanOwner):
         if rescale:
             sf = [list(m["scale_factor"]) for m in img_metas]
             div = torch.tensor(sf, dtype=torch.float32, device=dev).contiguous()
-        N.check(lib.glsdet_nms_launch_scaled(op.handle, pred.data_ptr(), N.ptr(div), float(cfg["score_thr"]),
-                                             float(nms_cfg["iou_threshold"]), STRATEGIES["mmcv"], op.det.data_ptr(),
-                                             op.count.data_ptr(), op.keep_index.data_ptr(), N.stream_ptr()),
-                "glsdet_nms_launch_scaled")
-        counts = op.count.cpu().tolist()
+        det, count = op.launch(pred, float(cfg["score_thr"]), float(nms_cfg["iou_threshold"]), "mmcv", box_div=div)
+        # the one host synchronisation of get_bboxes: the per-image (dets [n_i, 5], labels [n_i]) tensors it returns are
+        # sized by the counts (mmdet's own _bboxes_nms indexes with boolean masks, which synchronises per image)
+        counts = count.cpu().tolist()
         results = []
         for i in range(b):
-            rows = op.det[i, :counts[i]]
+            rows = det[i, :counts[i]]
             dets = torch.cat([rows[:, :4], (rows[:, 4] * rows[:, 5]).unsqueeze(1)], dim=1)
             results.append((dets, rows[:, 6].long()))
         return results

@@ -24,6 +24,30 @@ STRATEGIES = {"trick": N.NMS_COORD_TRICK, "per_class": N.NMS_PER_CLASS, "auto_cu
 def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
     """utils_bbox.py:254-306: list of raw [B, 5+nc, h, w] maps -> [B, sum(h*w), 5+nc] with normalised
     (cx, cy, w, h), sigmoid(obj), sigmoid(cls)."""
+    return _decode(outputs, input_shape, N.DECODE_SIGMOID_OBJ | N.DECODE_SIGMOID_CLS | N.DECODE_NORMALISE)
+
+
+def decode_outputs_no_sigmoid(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """utils_bbox.py:149-200 (decode_mode 'obj_sigmoid', yolo.py:77-78): sigmoid on the objectness only, classes raw."""
+    return _decode(outputs, input_shape, N.DECODE_SIGMOID_OBJ | N.DECODE_NORMALISE)
+
+
+def decode_outputs_no_sigmoid_all(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """utils_bbox.py:202-251 (decode_mode 'no_sigmoid', yolo.py:79-80): objectness and classes stay raw."""
+    return _decode(outputs, input_shape, N.DECODE_NORMALISE)
+
+
+def decode_outputs_cls_sigmoid(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """utils_bbox.py:95-147 (decode_mode 'cls_sigmoid', yolo.py:81-82): sigmoid on the classes only, objectness raw."""
+    return _decode(outputs, input_shape, N.DECODE_SIGMOID_CLS | N.DECODE_NORMALISE)
+
+
+def decode_outputs_xyxy(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) -> torch.Tensor:
+    """utils_bbox.py:36-93: corner boxes (x1, y1, x2, y2) in input pixels, raw objectness / class logits."""
+    return _decode(outputs, input_shape, N.DECODE_XYXY)
+
+
+def _decode(outputs: Sequence[torch.Tensor], input_shape: Sequence[int], mode: int) -> torch.Tensor:
     lib = N.load()
     outs = [o.float().contiguous() for o in outputs]
     if not outs or not outs[0].is_cuda:
@@ -35,8 +59,8 @@ def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) 
     ws = (C.c_int32 * n)(*[o.shape[3] for o in outs])
     a = sum(o.shape[2] * o.shape[3] for o in outs)
     pred = torch.empty((b, a, nch), dtype=torch.float32, device=outs[0].device)
-    N.check(lib.glsdet_decode_outputs(ptrs, hs, ws, n, b, nch - 5, int(input_shape[0]), int(input_shape[1]),
-                                      pred.data_ptr(), N.stream_ptr()), "glsdet_decode_outputs")
+    N.check(lib.glsdet_decode_outputs_mode(ptrs, hs, ws, n, b, nch - 5, int(input_shape[0]), int(input_shape[1]), mode,
+                                           pred.data_ptr(), N.stream_ptr()), "glsdet_decode_outputs_mode")
     return pred
 
 
@@ -73,17 +97,20 @@ class DeviceNMS:
         if nbytes <= 0:
             raise N.NativeError("glsdet_nms_workspace_bytes rejected the problem size")
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.det = torch.zeros((batch, self.max_det, 7), dtype=torch.float32, device=dev)
-        self.count = torch.zeros((batch,), dtype=torch.int32, device=dev)
-        self.keep_index = torch.zeros((batch, self.max_det), dtype=torch.int32, device=dev)
+        self.device = dev
+        self.det = self.count = self.keep_index = None   # results of the most recent launch
         self.handle = C.c_void_p()
         N.check(self._lib.glsdet_nms_create(batch, anchors, num_classes, self.max_det, self.workspace.data_ptr(),
                                             nbytes, C.byref(self.handle)), "glsdet_nms_create")
 
     def launch(self, pred: torch.Tensor, conf_thres: float, nms_thres: float, strategy: str = "auto_cuda",
-               stream=None, cls_logits: bool = False):
+               stream=None, cls_logits: bool = False, out=None, box_div: Optional[torch.Tensor] = None):
         """`pred`: [B, A, 5+nc] fp32, either contiguous rows or the permuted view of a [B, 5+nc, A] tensor (what the
-        reference's decode_outputs returns and what the fused path writes); anything else is made contiguous."""
+        reference's decode_outputs returns and what the fused path writes); anything else is made contiguous.
+        Every launch returns FRESH (det, count) tensors (caching-allocator blocks, no synchronisation), so a caller may keep
+        step i's detections across step i+1; rows beyond count[b] are unspecified.  `out=(det, count, keep_index)` writes
+        into caller-provided tensors instead (e.g. double buffers of a pipelined loop).  `box_div`: optional [B, 4] fp32
+        divisors of the corner boxes (mmdet's rescale, yolox_head.py:283-285)."""
         assert pred.dtype == torch.float32 and pred.is_cuda
         nch = 5 + self.nc
         assert tuple(pred.shape) == (self.batch, self.anchors, nch), (pred.shape, self.batch, self.anchors)
@@ -95,7 +122,18 @@ class DeviceNMS:
             pred, layout = pred.contiguous(), N.PRED_ROWS
         if cls_logits:   # class columns are raw logits (FFAPathPlan detect mode): the filter applies the sigmoid
             layout |= N.PRED_CLS_LOGITS
-        N.check(self._lib.glsdet_nms_launch_layout(self.handle, pred.data_ptr(), layout, None, float(conf_thres),
+        if out is None:
+            self.det = torch.empty((self.batch, self.max_det, 7), dtype=torch.float32, device=self.device)
+            self.count = torch.empty((self.batch,), dtype=torch.int32, device=self.device)
+            self.keep_index = torch.empty((self.batch, self.max_det), dtype=torch.int32, device=self.device)
+        else:
+            self.det, self.count, self.keep_index = out
+            assert tuple(self.det.shape) == (self.batch, self.max_det, 7) and self.det.dtype == torch.float32 and self.det.is_contiguous()
+            assert tuple(self.count.shape) == (self.batch,) and self.count.dtype == torch.int32
+            assert tuple(self.keep_index.shape) == (self.batch, self.max_det) and self.keep_index.dtype == torch.int32
+        if box_div is not None:
+            assert box_div.dtype == torch.float32 and tuple(box_div.shape) == (self.batch, 4) and box_div.is_contiguous()
+        N.check(self._lib.glsdet_nms_launch_layout(self.handle, pred.data_ptr(), layout, N.ptr(box_div), float(conf_thres),
                                                    float(nms_thres), STRATEGIES[strategy], self.det.data_ptr(),
                                                    self.count.data_ptr(), self.keep_index.data_ptr(),
                                                    N.stream_ptr(stream)), "glsdet_nms_launch_layout")
@@ -163,14 +201,36 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
     bx = boxes.float().contiguous()
     sc = scores.float().contiguous()
     lb = idxs.float().contiguous()
-    nbytes = lib.glsdet_batched_nms_workspace_bytes(k)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=boxes.device)
+    # any idxs (negative, batch * nc + cls, > 255): dense ids 0..U-1 pick the class segments, the original values keep
+    # driving the coordinate-trick offsets exactly like torchvision's idxs * (max + 1)
+    uniq, ids = torch.unique(idxs, return_inverse=True)
+    if uniq.numel() > 256:
+        raise NotImplementedError(f"batched_nms: {uniq.numel()} distinct idxs (at most 256 class segments are supported)")
+    ids = ids.to(torch.int32).contiguous()
+    uf = uniq.float()
+    lmax = float(uf.abs().max()) if bool((uf == uf.round()).all()) else -1.0
+    nbytes, ws = _batched_nms_workspace(k, boxes.device)
     keep = torch.empty((k,), dtype=torch.int32, device=boxes.device)
     cnt = torch.zeros((1,), dtype=torch.int32, device=boxes.device)
-    N.check(lib.glsdet_batched_nms(bx.data_ptr(), sc.data_ptr(), lb.data_ptr(), k, float(iou_threshold),
-                                   STRATEGIES[strategy], ws.data_ptr(), nbytes, keep.data_ptr(), cnt.data_ptr(),
-                                   N.stream_ptr()), "glsdet_batched_nms")
+    N.check(lib.glsdet_batched_nms_ids(bx.data_ptr(), sc.data_ptr(), lb.data_ptr(), ids.data_ptr(), lmax, k, float(iou_threshold),
+                                       STRATEGIES[strategy], ws.data_ptr(), nbytes, keep.data_ptr(), cnt.data_ptr(),
+                                       N.stream_ptr()), "glsdet_batched_nms_ids")
     return keep[:int(cnt.item())].long()
+
+
+_bnms_ws = {}
+
+
+def _batched_nms_workspace(k: int, device):
+    """Workspace of batched_nms, cached per device and grown geometrically (it was allocated on every call)."""
+    lib = N.load()
+    key = str(device)
+    cap, ws = _bnms_ws.get(key, (0, None))
+    if k > cap:
+        cap = max(k, 2 * cap, 1024)
+        ws = torch.empty(lib.glsdet_batched_nms_workspace_bytes(cap), dtype=torch.uint8, device=device)
+        _bnms_ws[key] = (cap, ws)
+    return ws.numel(), ws
 
 
 def detection_lines(result: Optional[np.ndarray], class_names: Sequence[str], keep_classes: Optional[Sequence[str]] = None) -> List[str]:

@@ -11,6 +11,7 @@ backbone in glsdet_b200/backbone.py; there is no Py
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -126,7 +127,20 @@ class _PlanOwner(nn.Module):
     def __init__(self):
         super().__init__()
         self._plans: Dict[tuple, FFAPathPlan] = {}
+        self._plan_lock = threading.Lock()
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_plans())
+
+    def _replicate_for_data_parallel(self):
+        """nn.DataParallel (yolox-drone/yolo.py:110) re-creates shallow replicas of the module on every forward and strips
+        their parameters into plain attributes.  The native plans are built from the ORIGINAL module's state_dict (copied to
+        the replica's device once) and live in the original's plan cache, which the replicas share (the cache key holds the
+        device); `_plan_lock` serialises the replica threads while a plan is being built."""
+        replica = super()._replicate_for_data_parallel()
+        replica._dp_source = getattr(self, "_dp_source", self)
+        return replica
+
+    def _source_state_dict(self):
+        return getattr(self, "_dp_source", self).state_dict()
 
     def invalidate_plans(self):
         self._plans.clear()
@@ -145,18 +159,20 @@ class _PlanOwner(nn.Module):
 
     def _plan_state_dict(self):
         """state_dict in yolox-drone naming (subclasses with other naming translate here)."""
-        return self.state_dict()
+        return self._source_state_dict()
 
     def _plan(self, batch: int, input_hw: Sequence[int], device) -> FFAPathPlan:
-        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), self.precision)
-        plan = self._plans.get(key)
-        if plan is None:
-            if len(self._plans) >= 4:
-                self._plans.clear()
-            plan = FFAPathPlan(self._plan_state_dict(), batch, input_hw, self._num_classes(), device=device,
-                               neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts,
-                               variant=self._variant, decode=self._decode, precision=self.precision)
-            self._plans[key] = plan
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(torch.device(device)), self.precision)
+        with self._plan_lock:
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 8:
+                    self._plans.clear()
+                with torch.cuda.device(torch.device(device)):
+                    plan = FFAPathPlan(self._plan_state_dict(), batch, input_hw, self._num_classes(), device=device,
+                                       neck_prefix=self._neck_prefix, head_prefix=self._head_prefix, parts=self._parts,
+                                       variant=self._variant, decode=self._decode, precision=self.precision)
+                self._plans[key] = plan
         return plan
 
     def _fused_plan(self, x: torch.Tensor) -> Optional[FFAPathPlan]:
@@ -172,8 +188,10 @@ class _PlanOwner(nn.Module):
         plan = self._plan(batch, (height, width), device)
         if plan.fp32 or plan.pre_loads:
             return None
-        if plan.backbone is None:
-            plan.attach_backbone(bb.state_dict(), "", bb.act_name)
+        with self._plan_lock:
+            if plan.backbone is None:
+                with torch.cuda.device(torch.device(device)):
+                    plan.attach_backbone(bb._source_state_dict(), "", bb.act_name)
         return plan
 
 
@@ -224,14 +242,16 @@ class CSPDarknet(_PlanOwner):
                     backbone_supported(self.base_channels) and height % 32 == 0 and width % 32 == 0)
 
     def native_plan(self, batch: int, input_hw: Sequence[int], device, outs=None, key_extra=None) -> BackbonePlan:
-        key = (batch, int(input_hw[0]), int(input_hw[1]), str(device), key_extra, self.precision)
-        plan = self._bb_plans.get(key)
-        if plan is None:
-            if len(self._bb_plans) >= 4:
-                self._bb_plans.clear()
-            plan = BackbonePlan(self.state_dict(), batch, input_hw, device=device, act=self.act_name, prefix="", outs=outs,
-                                precision=self.precision)
-            self._bb_plans[key] = plan
+        key = (batch, int(input_hw[0]), int(input_hw[1]), str(torch.device(device)), key_extra, self.precision)
+        with self._plan_lock:
+            plan = self._bb_plans.get(key)
+            if plan is None:
+                if len(self._bb_plans) >= 8:
+                    self._bb_plans.clear()
+                with torch.cuda.device(torch.device(device)):
+                    plan = BackbonePlan(self._source_state_dict(), batch, input_hw, device=device, act=self.act_name, prefix="",
+                                        outs=outs, precision=self.precision)
+                self._bb_plans[key] = plan
         return plan
 
     @torch.no_grad()

@@ -356,6 +356,19 @@ int glsdet_decode_outputs(const float* const* levels, const int32_t* heights, co
                           float* pred, void* stream);
 
 /*
+ * The decode variants the YOLO facade dispatches on `decode_mode` (yolox-drone/yolo.py:75-82; utils_bbox.py:36-251):
+ *   decode_outputs               SIGMOID_OBJ | SIGMOID_CLS | NORMALISE   (:254-306, 'default')
+ *   decode_outputs_no_sigmoid    SIGMOID_OBJ | NORMALISE                 (:149-200, 'obj_sigmoid')
+ *   decode_outputs_no_sigmoid_all              NORMALISE                 (:202-251, 'no_sigmoid')
+ *   decode_outputs_cls_sigmoid   SIGMOID_CLS | NORMALISE                 (:95-147,  'cls_sigmoid')
+ *   decode_outputs_xyxy          XYXY (input pixels, corner form, raw obj / cls logits)   (:36-93)
+ */
+enum { GLSDET_DECODE_SIGMOID_OBJ = 1, GLSDET_DECODE_SIGMOID_CLS = 2, GLSDET_DECODE_NORMALISE = 4, GLSDET_DECODE_XYXY = 8 };
+int glsdet_decode_outputs_mode(const float* const* levels, const int32_t* heights, const int32_t* widths,
+                               int32_t num_levels, int32_t batch, int32_t num_classes, int32_t in_h, int32_t in_w,
+                               int32_t mode, float* pred, void* stream);
+
+/*
  * mmdet flavour of the decode (yolox-ufp/mmdet/models/dense_heads/yolox_head.py:255-308 with the priors of
  * core/anchor/point_generator.py:148-175, offset 0): three lists of raw NCHW fp32 maps (cls [B,nc,h,w],
  * bbox [B,4,h,w], objectness [B,1,h,w]; pass the same base pointers with channel strides for views) ->
@@ -425,6 +438,15 @@ void glsdet_nms_destroy(glsdet_nms_t* op);
 int glsdet_batched_nms(const float* boxes, const float* scores, const float* labels, int32_t k, float nms_thres,
                        int32_t strategy, void* workspace, int64_t workspace_bytes, int32_t* keep,
                        int32_t* keep_count, void* stream);
+/* Same with dense class ids: label_ids int32 [K] in 0..255 (one id per distinct label value) drive the class segments,
+ * while the coordinate-trick offsets keep using the original label values (torchvision: offsets = idxs * (max + 1)).
+ * glsdet_batched_nms casts the labels themselves to class ids, i.e. needs integral labels in 0..255; arbitrary idxs
+ * (negative, batch * nc + cls, ...) go through this entry point.  label_abs_max: max |label| when every label is
+ * integral (the coordinate trick is then evaluated class by class, which is identical as long as the offsets stay below
+ * 2^21), negative when they are not (the trick then runs literally, as one class-agnostic NMS on the shifted boxes). */
+int glsdet_batched_nms_ids(const float* boxes, const float* scores, const float* labels, const int32_t* label_ids,
+                           float label_abs_max, int32_t k, float nms_thres, int32_t strategy, void* workspace, int64_t workspace_bytes,
+                           int32_t* keep, int32_t* keep_count, void* stream);
 int64_t glsdet_batched_nms_workspace_bytes(int32_t k);
 
 #ifdef __cplusplus

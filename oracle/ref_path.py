@@ -414,6 +414,40 @@ def decode_outputs(outputs: Sequence[torch.Tensor], input_shape: Sequence[int]) 
 
 
 # ------------------------------------------------------------------------------------------ post-processing
+def decode_outputs_variant(outputs: Sequence[torch.Tensor], input_shape: Sequence[int], variant: str) -> torch.Tensor:
+    """The decode variants of models/core/utils_bbox.py:36-251 that yolo.py:75-82 dispatches on decode_mode:
+    'no_sigmoid' (:149-200, sigmoid on obj only), 'no_sigmoid_all' (:202-251, no sigmoid), 'cls_sigmoid' (:95-147,
+    sigmoid on the classes only), 'xyxy' (:36-93: no sigmoid, no normalisation, corner boxes in input pixels)."""
+    hw = [tuple(x.shape[-2:]) for x in outputs]
+    out = torch.cat([x.flatten(start_dim=2) for x in outputs], dim=2).permute(0, 2, 1).contiguous().clone()
+    if variant == "no_sigmoid":
+        out[:, :, 4] = torch.sigmoid(out[:, :, 4])
+    elif variant == "cls_sigmoid":
+        out[:, :, 5:] = torch.sigmoid(out[:, :, 5:])
+    elif variant not in ("no_sigmoid_all", "xyxy"):
+        raise ValueError(variant)
+    grids, strides = [], []
+    for h, w in hw:
+        gy, gx = torch.meshgrid([torch.arange(h), torch.arange(w)], indexing="ij")
+        grid = torch.stack((gx, gy), 2).view(1, -1, 2)
+        grids.append(grid)
+        strides.append(torch.full((1, grid.shape[1], 1), input_shape[0] / h))
+    grids = torch.cat(grids, dim=1).type(out.type())
+    strides = torch.cat(strides, dim=1).type(out.type())
+    out[..., :2] = (out[..., :2] + grids) * strides
+    out[..., 2:4] = torch.exp(out[..., 2:4]) * strides
+    if variant == "xyxy":
+        c = out.clone()
+        out[..., 0] = c[..., 0] - c[..., 2] / 2
+        out[..., 1] = c[..., 1] - c[..., 3] / 2
+        out[..., 2] = c[..., 0] + c[..., 2] / 2
+        out[..., 3] = c[..., 1] + c[..., 3] / 2
+        return out
+    out[..., [0, 2]] = out[..., [0, 2]] / input_shape[1]
+    out[..., [1, 3]] = out[..., [1, 3]] / input_shape[0]
+    return out
+
+
 def yolo_correct_boxes(box_xy, box_wh, input_shape, image_shape, letterbox_image):
     """models/core/utils_bbox.py:8-33 (numpy, float64 intermediates exactly as numpy promotes them)."""
     box_yx = box_xy[..., ::-1]

@@ -264,7 +264,9 @@ def test_uint8_entry_bit_identical_to_host_preprocessing(native_lib, cuda_device
     det_a, cnt_a = net.detect(x, conf_thres=0.01, nms_thres=0.65)
     det_a, cnt_a = det_a.clone(), cnt_a.clone()
     det_b, cnt_b = net.detect_uint8(torch.from_numpy(img).to(cuda_device), conf_thres=0.01, nms_thres=0.65)
-    assert torch.equal(cnt_a, cnt_b) and torch.equal(det_a, det_b)
+    assert torch.equal(cnt_a, cnt_b)
+    for i in range(b):
+        assert torch.equal(det_a[i, :int(cnt_a[i])], det_b[i, :int(cnt_b[i])])   # rows beyond count are unspecified
 
 
 def test_large_model_from_image(native_lib, cuda_device):

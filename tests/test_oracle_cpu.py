@@ -122,3 +122,15 @@ def test_oracle_backbone_pinned_to_reference_golden():
     for i, t in enumerate(logits):
         ref = torch.from_numpy(z[f"logits{i}"])
         assert (t - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), i
+
+
+def test_oracle_decode_variants_pinned_to_reference_golden():
+    """decode_outputs_{no_sigmoid, no_sigmoid_all, cls_sigmoid, xyxy} (utils_bbox.py:36-251): the restatement against the
+    outputs of the real functions (tests/golden/make_golden_decode.py)."""
+    z = np.load(GOLD / "decode_variants.npz")
+    levels = [torch.from_numpy(z[f"level{i}"]) for i in range(3)]
+    shape = [int(v) for v in z["input_shape"]]
+    np.testing.assert_allclose(ref_path.decode_outputs(levels, shape).numpy(), z["default"], rtol=1e-6, atol=1e-6)
+    for name in ("no_sigmoid", "no_sigmoid_all", "cls_sigmoid", "xyxy"):
+        got = ref_path.decode_outputs_variant(levels, shape, name).numpy()
+        np.testing.assert_allclose(got, z[name], rtol=1e-6, atol=1e-6, err_msg=name)

@@ -147,6 +147,67 @@ def test_batched_nms_edge_cases(native_lib, cuda_device):
     np.testing.assert_array_equal(got, nms_oracle.batched_nms(boxes, scores, labels, 0.5, "trick"))
 
 
+def test_batched_nms_negative_scores_and_arbitrary_idxs(native_lib, cuda_device):
+    """torchvision's contract: scores may be raw logits (negative) and idxs any values (batch * nc + cls, negative,
+    non-integral); checked against the oracle and against torchvision itself on the CPU."""
+    import torchvision
+
+    from glsdet_b200.utils_bbox import batched_nms
+
+    rng = np.random.default_rng(77)
+    boxes, scores, labels = _clustered(rng, 3000, 12)
+    logit = np.log(scores / (1 - scores)).astype(np.float32)          # negative for half of the boxes
+    for lab in (labels * 37 + 300, -labels - 1, labels * 0.25, labels * 1e6):
+        lab = lab.astype(np.float32)
+        tb, ts, tl = (torch.from_numpy(a).to(cuda_device) for a in (boxes, logit, lab))
+        for strat in ("trick", "per_class"):
+            got = batched_nms(tb, ts, tl, 0.55, strat).cpu().numpy()
+            np.testing.assert_array_equal(got, nms_oracle.batched_nms(boxes, logit, lab, 0.55, strat))
+        # the real torchvision op (CPU dispatch: 4 * 3000 > 4000 elements -> per-class branch)
+        tv = torchvision.ops.boxes.batched_nms(torch.from_numpy(boxes), torch.from_numpy(logit), torch.from_numpy(lab), 0.55)
+        np.testing.assert_array_equal(batched_nms(tb, ts, tl, 0.55, "auto_cpu").cpu().numpy(), tv.numpy())
+    with pytest.raises(NotImplementedError):
+        batched_nms(tb[:600], ts[:600], torch.arange(600, device=cuda_device, dtype=torch.float32), 0.5)
+
+
+def test_filter_argmax_of_near_tied_saturated_logits(native_lib, cuda_device):
+    """Fused detect path: class logits around 12-15 saturate to (almost) the same fp32 probability; torch.max returns the
+    FIRST index among equal probabilities, so the filter must evaluate every candidate class, not only the largest logit."""
+    from glsdet_b200.utils_bbox import DeviceNMS
+
+    B, A, nc = 1, 4096, 10
+    g = torch.Generator().manual_seed(5)
+    logits = torch.full((B, A, nc), -6.0)
+    m = 9.0 + 8.0 * torch.rand(A, generator=g)                  # largest logit 9 .. 17
+    hi = torch.randint(1, nc, (A,), generator=g)                  # its class (never class 0)
+    lo = (hi - 1 - torch.randint(0, 3, (A,), generator=g)).clamp(min=0)   # a lower-index class slightly below it
+    gap = 0.2 * torch.rand(A, generator=g) ** 3
+    idx = torch.arange(A)
+    logits[0, idx, hi] = m
+    logits[0, idx, lo] = m - gap
+    pred = torch.zeros((B, A, 5 + nc))
+    cx = ((idx % 64).float() + 0.5) / 64
+    cy = ((idx // 64).float() + 0.5) / 64
+    pred[0, :, 0], pred[0, :, 1], pred[0, :, 2], pred[0, :, 3], pred[0, :, 4] = cx, cy, 0.004, 0.004, 0.9
+    pred[0, :, 5:] = logits[0]
+    dpred = pred.to(cuda_device)
+    dprob = dpred.clone()
+    dprob[0, :, 5:] = 1.0 / (1.0 + torch.exp(-dpred[0, :, 5:]))    # the prediction epilogue's formula, fp32 on the device
+    conf, label = dprob[0, :, 5:].max(1)                           # torch.max: first index among equal probabilities
+    assert (label.cpu() != hi).float().mean() > 0.05, "the case must contain ties that resolve to the lower index"
+    op = DeviceNMS(B, A, nc)
+    det, cnt = op.launch(dpred, 0.01, 0.65, "per_class", cls_logits=True)
+    torch.cuda.synchronize()
+    assert int(cnt[0]) == A
+    anchor = op.keep_index[0, :A].long()
+    assert torch.equal(det[0, :A, 6], label[anchor].float())
+    assert torch.equal(det[0, :A, 5], conf[anchor])
+    ref_det = det.clone()
+    det2, cnt2 = op.launch(dprob, 0.01, 0.65, "per_class")         # same probabilities, decoded: identical rows
+    torch.cuda.synchronize()
+    assert int(cnt2[0]) == A and torch.equal(det2, ref_det)
+
+
 def test_nms_fallback_kernel_without_mask_budget(native_lib, cuda_device, monkeypatch):
     """With no bitmask budget every segment runs on the blocked-greedy fallback kernel: same keep sets."""
     from glsdet_b200.utils_bbox import batched_nms
