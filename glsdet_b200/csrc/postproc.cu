@@ -45,6 +45,8 @@ constexpr int kNmsThreads = 1024;   // 8 warps per scheduler: the kept-list swee
 constexpr int kKeptSmem = 1536;     // kept boxes cached in shared memory per segment
 constexpr int kMaxClasses = 256;    // 8 label bits in the sort key
 constexpr uint64_t kPadKey = ~0ull;
+constexpr int kGrid = 32;             // spatial grid per segment (kGrid x kGrid cells) for the tile culling
+constexpr int kCells = kGrid * kGrid;
 
 __device__ __forceinline__ uint32_t float_order_bits(float f) {
   const uint32_t b = __float_as_uint(f);
@@ -164,6 +166,13 @@ struct Work {
   unsigned long long* row_tiles;  // [B][cap]  per sorted candidate: which column tiles of its mask row hold suppression bits
                                   // (bit k covers column tiles [k << shift, (k + 1) << shift), shift = tile_shift(T));
                                   // zero = the box suppresses nothing
+  int32_t* cell_hist;        // [B*nc][kCells]  counting sort of a segment's boxes by grid cell: counts, then cursors
+  uint16_t* cell_id;         // [B][cap]        grid cell of every sorted candidate
+  int32_t* srank;            // [B][cap]        spatial order: position -> index of the box in the score order (image-wide)
+  float4* sbox;              // [B][cap]        NMS-space boxes in spatial order
+  unsigned long long* tile_list;  // [max_tiles]   (segment << 40 | row chunk << 20 | column chunk) of every IoU tile to compute
+  int32_t* counters;         // [0] tiles listed, [2..3] (int64) mask words in use
+  int32_t max_tiles;
   unsigned long long* mask;  // [mask_words]
   int64_t mask_words;
   float trick_label_max;     // largest |label| (labels integral), or < 0: the coordinate trick may only be decomposed by
@@ -296,6 +305,9 @@ __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
     if (i < w.cap) w.pending[static_cast<int64_t>(b) * w.cap + i] = 0;
     if (i < w.cap) w.row_tiles[static_cast<int64_t>(b) * w.cap + i] = 0ull;
   }
+  int32_t* hist = w.cell_hist + static_cast<int64_t>(b) * w.nc * kCells;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.nc * kCells; i += gridDim.x * blockDim.x) hist[i] = 0;
+  if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.counters[0] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------- bitonic sort
@@ -474,63 +486,201 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
       }
       carry_words = cw;
       carry_tiles = ct;
-      if (base + 1024 >= total) w.seg_tile_off[total] = ct;
+      if (base + 1024 >= total) {
+        w.seg_tile_off[total] = ct;
+        *reinterpret_cast<long long*>(w.counters + 2) = cw;   // mask words in use (zeroed by cell_count_kernel)
+      }
     }
     __syncthreads();
   }
 }
 
-// Persistent CTAs of 4 x 64 threads; every 64-thread group owns one 64x64 tile at a time (row tile r, column tile
-// c >= r), statically strided over the work list.  Thread i of the group tests row box i against the 64 column
-// boxes staged in shared memory and emits one 64-bit word.
+// ---- spatial culling of the IoU tiles
+// All-pairs IoU inside a class is O(n^2) (330 M pairs per 16-image step at 7 k boxes of the dominant class) although a box
+// only overlaps its neighbours.  The boxes of a segment are therefore put into a spatially coherent order - counting
+// sort by the grid cell of the box centre, row-major cells - and cut into chunks of 64; two chunks are compared only if
+// their bounding boxes intersect (exact: boxes that do not intersect cannot exceed an IoU threshold >= 0).  The order
+// only decides how many tiles survive, never the result: every surviving tile writes its suppression bits straight into
+// the SCORE-ordered triangular mask (row = better box, bit = worse box), so the resolve step is unchanged.
+__device__ __forceinline__ int segment_of(const Work& w, int b, int i) {   // class segment of sorted candidate i
+  const int32_t* st = w.seg_start + b * (w.nc + 1);
+  int lo = 0, hi = w.nc;   // st[lo] <= i < st[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (st[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// grid cell of every box on the mask path + per-segment cell histogram; also zeroes the mask words in use
+__global__ void __launch_bounds__(256) cell_count_kernel(Work w, int strategy) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const int n = w.cand_count[b];
+  {   // zero the used part of the suppression mask (16-byte stores, all CTAs)
+    const long long used = *reinterpret_cast<const long long*>(w.counters + 2);
+    uint4* m4 = reinterpret_cast<uint4*>(w.mask);
+    const long long n4 = (used + 1) >> 1;
+    const long long stride = static_cast<long long>(gridDim.x) * gridDim.y * blockDim.x;
+    for (long long i = (static_cast<long long>(b) * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride)
+      m4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if (n == 0) return;
+  const ImageMode m = image_mode(w, b, strategy);
+  // Cells: the raw coordinate range of the image is cut into kGrid x kGrid cells.  Per-class segments of the coordinate
+  // trick carry one constant offset each, which only rotates the (periodic) cell index; the literal trick (one segment
+  // over all classes) stretches the grid over all offsets instead.  The cell only orders the boxes - the culling itself
+  // uses the true chunk bounding boxes - so any assignment is correct.
+  const float minc = order_bits_float(w.min_bits[b]), maxc = order_bits_float(w.max_bits[b]);
+  const bool literal = m.use_offsets && !m.per_class;
+  const float span = fmaxf(maxc - minc, 1e-12f) + (literal ? fmaxf(w.trick_label_max, 0.0f) * m.offset_scale : 0.0f);
+  const float sc = static_cast<float>(kGrid) / span;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = segment_of(w, b, i);
+    if (w.seg_word_off[b * w.nc + c] < 0) continue;
+    const float4 bx = w.nbox[static_cast<int64_t>(b) * w.cap + i];
+    float fx = floorf((0.5f * (bx.x + bx.z) - minc) * sc), fy = floorf((0.5f * (bx.y + bx.w) - minc) * sc);
+    fx = fminf(fmaxf(fx, -1.0e9f), 1.0e9f);   // NaN -> -1e9 (fmaxf drops the NaN), then an ordinary integer
+    fy = fminf(fmaxf(fy, -1.0e9f), 1.0e9f);
+    const int cx = static_cast<int>(fx) & (kGrid - 1), cy = static_cast<int>(fy) & (kGrid - 1);
+    const int cid = cy * kGrid + cx;
+    w.cell_id[static_cast<int64_t>(b) * w.cap + i] = static_cast<uint16_t>(cid);
+    atomicAdd(&w.cell_hist[(static_cast<int64_t>(b) * w.nc + c) * kCells + cid], 1);
+  }
+}
+
+// counts -> first position of every cell (exclusive scan of kCells = 1024 counters per segment)
+__global__ void __launch_bounds__(kCells) cell_scan_kernel(Work w) {
+  pdl_prologue();
+  __shared__ int wsum[kCells / 32];
+  const int sgm = blockIdx.y * w.nc + blockIdx.x;
+  if (w.seg_word_off[sgm] < 0) return;
+  int32_t* h = w.cell_hist + static_cast<int64_t>(sgm) * kCells;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int v = h[tid];
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    const int x = wsum[tid];
+    int sc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, sc, o);
+      if (tid >= o) sc += u;
+    }
+    wsum[tid] = sc - x;
+  }
+  __syncthreads();
+  h[tid] = wsum[tid >> 5] + incl - v;
+}
+
+// scatter into spatial order: srank[pos] = index in the score order, sbox[pos] = its NMS-space box
+__global__ void __launch_bounds__(256) cell_scatter_kernel(Work w) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const int n = w.cand_count[b];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = segment_of(w, b, i);
+    if (w.seg_word_off[b * w.nc + c] < 0) continue;
+    const int64_t o = static_cast<int64_t>(b) * w.cap;
+    const int cid = w.cell_id[o + i];
+    const int pos = w.seg_start[b * (w.nc + 1) + c] + atomicAdd(&w.cell_hist[(static_cast<int64_t>(b) * w.nc + c) * kCells + cid], 1);
+    w.srank[o + pos] = i;
+    w.sbox[o + pos] = w.nbox[o + i];
+  }
+}
+
+// One CTA per segment: bounding box of every 64-box chunk (spatial order), then the list of chunk pairs (r <= c) whose
+// bounding boxes intersect.
+constexpr int kTileListThreads = 512;
+__global__ void __launch_bounds__(kTileListThreads) tile_list_kernel(Work w, float thr) {
+  pdl_prologue();
+  extern __shared__ float4 chunk_bb[];   // [T]
+  const int seg = blockIdx.x, b = blockIdx.y;
+  const int sgm = b * w.nc + seg;
+  if (w.seg_word_off[sgm] < 0) return;
+  const int s0 = w.seg_start[b * (w.nc + 1) + seg];
+  const int n = w.seg_start[b * (w.nc + 1) + seg + 1] - s0;
+  const int T = (n + 63) >> 6;
+  const float4* sb = w.sbox + static_cast<int64_t>(b) * w.cap + s0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < T; r += kTileListThreads / 32) {
+    float x1 = INFINITY, y1 = INFINITY, x2 = -INFINITY, y2 = -INFINITY;
+    for (int k = lane; k < 64; k += 32) {
+      const int i = r * 64 + k;
+      if (i < n) {
+        const float4 q = sb[i];   // NaN coordinates drop out of fminf / fmaxf: such a box never intersects anything
+        x1 = fminf(x1, q.x); y1 = fminf(y1, q.y); x2 = fmaxf(x2, q.z); y2 = fmaxf(y2, q.w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x1 = fminf(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = fminf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+      x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, o)); y2 = fmaxf(y2, __shfl_xor_sync(0xffffffffu, y2, o));
+    }
+    if (lane == 0) chunk_bb[r] = make_float4(x1, y1, x2, y2);
+  }
+  __syncthreads();
+  const bool cull = (thr >= 0.0f);   // a negative threshold suppresses disjoint boxes too: every pair counts
+  const long long pairs = static_cast<long long>(T) * T;
+  for (long long p = threadIdx.x; p < pairs; p += kTileListThreads) {
+    const int r = static_cast<int>(p / T), c = static_cast<int>(p - static_cast<long long>(r) * T);
+    if (c < r) continue;
+    if (cull) {
+      const float4 a = chunk_bb[r], q = chunk_bb[c];
+      if (!(fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))) continue;
+    }
+    const int slot = atomicAdd(&w.counters[0], 1);
+    if (slot < w.max_tiles)
+      w.tile_list[slot] = (static_cast<unsigned long long>(sgm) << 40) | (static_cast<unsigned long long>(r) << 20) |
+                          static_cast<unsigned long long>(c);
+  }
+}
+
+// Persistent CTAs of 4 x 64 threads; every 64-thread group owns one listed tile at a time.  Thread i of the group tests
+// row box i (chunk r, spatial order) against the 64 boxes of chunk c staged in shared memory; every pair beyond the
+// threshold becomes one bit of the score-ordered mask: row = the better box of the pair, column = the worse one.
 constexpr int kMaskGroups = 4;
 __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, float thr) {
   pdl_prologue();
   __shared__ float4 cbox[kMaskGroups][64];
   __shared__ float carea[kMaskGroups][64];
-  const int total_seg = w.B * w.nc;
-  const int total_tiles = w.seg_tile_off[total_seg];
+  __shared__ int crank[kMaskGroups][64];
+  const int total_tiles = min(w.counters[0], w.max_tiles);
   const bool thr_nonneg = (thr >= 0.0f);
   const int grp = threadIdx.x >> 6, tid = threadIdx.x & 63;
-  int cur_lo = 0, cur_hi = 0, sgm = 0, s0 = 0, n = 0, T = 0, b = 0;
   for (int t = blockIdx.x * kMaskGroups + grp; t < total_tiles; t += gridDim.x * kMaskGroups) {
-    if (t >= cur_hi || t < cur_lo) {
-      int lo = 0, hi = total_seg;  // seg_tile_off[lo] <= t < seg_tile_off[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (w.seg_tile_off[mid] <= t) lo = mid; else hi = mid;
-      }
-      sgm = lo;
-      cur_lo = w.seg_tile_off[sgm];
-      cur_hi = w.seg_tile_off[sgm + 1];
-      b = sgm / w.nc;
-      const int c = sgm % w.nc;
-      s0 = w.seg_start[b * (w.nc + 1) + c];
-      n = w.seg_start[b * (w.nc + 1) + c + 1] - s0;
-      T = (n + 63) >> 6;
-    }
-    // invert local = r*T - r(r-1)/2 + (c - r)
-    const int local = t - cur_lo;
-    const float fT = static_cast<float>(2 * T + 1);
-    int r = static_cast<int>((fT - sqrtf(fmaxf(fT * fT - 8.0f * static_cast<float>(local), 0.0f))) * 0.5f);
-    r = max(0, min(r, T - 1));
-    while (r > 0 && static_cast<int>(tri_tile(T, r, r)) > local) --r;
-    while (r + 1 < T && static_cast<int>(tri_tile(T, r + 1, r + 1)) <= local) ++r;
-    const int cc = r + (local - static_cast<int>(tri_tile(T, r, r)));
-    const float4* bx = w.nbox + static_cast<int64_t>(b) * w.cap + s0;
+    const unsigned long long e = w.tile_list[t];
+    const int sgm = static_cast<int>(e >> 40), r = static_cast<int>((e >> 20) & 0xFFFFF), cc = static_cast<int>(e & 0xFFFFF);
+    const int b = sgm / w.nc, c = sgm - b * w.nc;
+    const int s0 = w.seg_start[b * (w.nc + 1) + c];
+    const int n = w.seg_start[b * (w.nc + 1) + c + 1] - s0;
+    const int T = (n + 63) >> 6;
+    const int64_t o = static_cast<int64_t>(b) * w.cap + s0;
     const int cj = cc * 64 + tid;
-    if (cj < n) { cbox[grp][tid] = bx[cj]; carea[grp][tid] = box_area(cbox[grp][tid]); }
+    if (cj < n) {
+      const float4 q = w.sbox[o + cj];
+      cbox[grp][tid] = q;
+      carea[grp][tid] = box_area(q);
+      crank[grp][tid] = w.srank[o + cj] - s0;
+    }
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
     const int ri = r * 64 + tid;
-    unsigned long long bits = 0ull;
     if (ri < n) {
-      const float4 rb = bx[ri];
+      const float4 rb = w.sbox[o + ri];
       const float ra = box_area(rb);
+      const int rrank = w.srank[o + ri] - s0;
       const int jn = min(64, n - cc * 64);
+      unsigned long long m;
       if (thr_nonneg) {
-        // Phase 1, branch-free: which column boxes intersect this row box at all (inter == 0 never exceeds thr >= 0).
-        // Phase 2: the exact IEEE IoU only for those - a few per row.  Fused into one loop, the division ran whenever
-        // ANY of the 32 rows of the warp intersected the column box, i.e. on most iterations.
+        // phase 1, branch-free: which column boxes intersect this row box at all (inter == 0 never exceeds thr >= 0);
+        // phase 2: the exact IEEE IoU only for those
         uint32_t lo = 0u, hi = 0u;
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) {
@@ -546,32 +696,24 @@ __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, fl
           const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
           hi |= (fminf(ww, hh) > 0.0f ? 1u : 0u) << j;
         }
-        unsigned long long m = (static_cast<unsigned long long>(hi) << 32) | lo;
-        if (jn < 64) m &= (1ull << jn) - 1ull;                       // stale columns of a ragged tile
-        if (cc == r) m &= (tid < 63) ? ~((2ull << tid) - 1ull) : 0ull;   // diagonal tile: later boxes only
-        while (m) {
-          const int j = __ffsll(static_cast<long long>(m)) - 1;
-          m &= m - 1ull;
-          if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, true)) bits |= 1ull << j;
-        }
+        m = (static_cast<unsigned long long>(hi) << 32) | lo;
       } else {
-        const int j0 = (cc == r) ? tid + 1 : 0;
-        for (int j = j0; j < jn; ++j)
-          if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, false)) bits |= (1ull << j);
+        m = ~0ull;
       }
-      if (bits) {
-        atomicOr(&w.row_tiles[static_cast<int64_t>(b) * w.cap + s0 + ri], 1ull << (cc >> tile_shift(T)));
-        // in-degree of the suppressed boxes (sparse: a few bits per row)
-        int32_t* pend = w.pending + static_cast<int64_t>(b) * w.cap + s0 + cc * 64;
-        unsigned long long m = bits;
-        while (m) {
-          const int j = __ffsll(static_cast<long long>(m)) - 1;
-          m &= m - 1ull;
-          atomicAdd(pend + j, 1);
+      if (jn < 64) m &= (1ull << jn) - 1ull;                             // stale columns of a ragged chunk
+      if (cc == r) m &= (tid < 63) ? ~((2ull << tid) - 1ull) : 0ull;     // diagonal tile: every pair once
+      while (m) {
+        const int j = __ffsll(static_cast<long long>(m)) - 1;
+        m &= m - 1ull;
+        if (iou_exceeds(rb, ra, cbox[grp][j], carea[grp][j], thr, thr_nonneg)) {
+          const int ja = crank[grp][j];
+          const int a = min(rrank, ja), d = max(rrank, ja);              // a: better (suppressor), d: worse (suppressed)
+          atomicOr(&w.mask[w.seg_word_off[sgm] + tri_word(T, a >> 6, a & 63, d >> 6)], 1ull << (d & 63));
+          atomicOr(&w.row_tiles[o + a], 1ull << ((d >> 6) >> tile_shift(T)));
+          atomicAdd(&w.pending[o + d], 1);
         }
       }
     }
-    w.mask[w.seg_word_off[sgm] + tri_word(T, r, tid, cc)] = bits;
     asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory");
   }
 }
@@ -870,7 +1012,8 @@ inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
   int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
-      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowtiles, off_pending, off_mask, mask_words, total;
+      off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowtiles, off_pending, off_hist, off_cellid, off_srank, off_sbox, off_tilelist,
+      off_counters, off_mask, mask_words, max_tiles, total;
 };
 
 constexpr int kMaxScanTiles = 2816;  // 2 x 22 KB of shared memory for the 'removed' and 'kept' bitmaps of a segment
@@ -901,7 +1044,14 @@ Layout make_layout(int B, int cap, int P, int nc) {
   l.off_wordoff = o; o = align_up(o + 8ll * B * nc, 256);
   l.off_rowtiles = o; o = align_up(o + 8ll * B * cap, 256);
   l.off_pending = o; o = align_up(o + 4ll * B * cap, 256);
+  l.off_hist = o; o = align_up(o + 4ll * B * nc * kCells, 256);
+  l.off_cellid = o; o = align_up(o + 2ll * B * cap, 256);
+  l.off_srank = o; o = align_up(o + 4ll * B * cap, 256);
+  l.off_sbox = o; o = align_up(o + 16ll * B * cap, 256);
+  l.off_counters = o; o = align_up(o + 64, 256);
   l.mask_words = mask_budget_words(B, cap);
+  l.max_tiles = l.mask_words / 64;
+  l.off_tilelist = o; o = align_up(o + 8ll * l.max_tiles, 256);
   l.off_mask = o; o = align_up(o + 8ll * l.mask_words, 256);
   l.total = o;
   return l;
@@ -929,6 +1079,13 @@ Work make_work(void* ws, int B, int cap, int nc) {
   w.seg_word_off = reinterpret_cast<int64_t*>(p + l.off_wordoff);
   w.row_tiles = reinterpret_cast<unsigned long long*>(p + l.off_rowtiles);
   w.pending = reinterpret_cast<int32_t*>(p + l.off_pending);
+  w.cell_hist = reinterpret_cast<int32_t*>(p + l.off_hist);
+  w.cell_id = reinterpret_cast<uint16_t*>(p + l.off_cellid);
+  w.srank = reinterpret_cast<int32_t*>(p + l.off_srank);
+  w.sbox = reinterpret_cast<float4*>(p + l.off_sbox);
+  w.tile_list = reinterpret_cast<unsigned long long*>(p + l.off_tilelist);
+  w.counters = reinterpret_cast<int32_t*>(p + l.off_counters);
+  w.max_tiles = static_cast<int32_t>(l.max_tiles < INT32_MAX ? l.max_tiles : INT32_MAX);
   w.mask = reinterpret_cast<unsigned long long*>(p + l.off_mask);
   w.mask_words = l.mask_words;
   if (const char* e = getenv("GLSDET_NMS_MASK_WORDS")) {  // tests: shrink the budget to force the fallback kernel
@@ -995,6 +1152,19 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   launch_pdl(seg_plan_kernel, 1, 1024, 0, st, w);
   if (int rc = count_launch("seg_plan_kernel")) return rc;
   if (w.topk == 0) {
+    int gx = (w.cap + 255) / 256;
+    if (gx > 256) gx = 256;
+    if (gx * B < device_sm_count()) gx = (device_sm_count() + B - 1) / B;   // enough CTAs to zero the mask words
+    launch_pdl(cell_count_kernel, dim3(gx, B), 256, 0, st, w, strategy);
+    if (int rc = count_launch("cell_count_kernel")) return rc;
+    launch_pdl(cell_scan_kernel, dim3(w.nc, B), kCells, 0, st, w);
+    if (int rc = count_launch("cell_scan_kernel")) return rc;
+    launch_pdl(cell_scatter_kernel, dim3(gx, B), 256, 0, st, w);
+    if (int rc = count_launch("cell_scatter_kernel")) return rc;
+    int t = (w.cap + 63) / 64;
+    if (t > kMaxScanTiles) t = kMaxScanTiles;
+    launch_pdl(tile_list_kernel, dim3(w.nc, B), kTileListThreads, static_cast<size_t>(t) * 16, st, w, nms_thres);
+    if (int rc = count_launch("tile_list_kernel")) return rc;
     launch_pdl(mask_tiles_kernel, device_sm_count() * 6, 64 * kMaskGroups, 0, st, w, nms_thres);
     if (int rc = count_launch("mask_tiles_kernel")) return rc;
   }
