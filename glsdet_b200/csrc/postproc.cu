@@ -46,7 +46,8 @@ constexpr int kKeptSmem = 1536;     // kept boxes cached in shared memory per se
 constexpr int kMaxClasses = 256;    // 8 label bits in the sort key
 constexpr uint64_t kPadKey = ~0ull;
 constexpr int kGrid = 32;             // spatial grid per segment (kGrid x kGrid cells) for the tile culling
-constexpr int kCells = kGrid * kGrid;
+constexpr int kSizeClasses = 4;       // boxes are first split by size (a few large boxes would blow up every chunk's bounds)
+constexpr int kCells = kSizeClasses * kGrid * kGrid;
 
 __device__ __forceinline__ uint32_t float_order_bits(float f) {
   const uint32_t b = __float_as_uint(f);
@@ -151,12 +152,15 @@ struct Work {
   int32_t* cand_count;   // [B]
   uint32_t* max_bits;    // [B]
   uint32_t* min_bits;    // [B]
+  int32_t* cls_count;    // [B][nc]    candidates per class (score filter)
+  int32_t* cls_cursor;   // [B][nc]    scatter cursors of build_keys_kernel
   int32_t* seg_start;    // [B][nc+1]
   int32_t* seg_kept;     // [B][nc]
   float* cand_score;     // [B][cap]
   int32_t* cand_idx;     // [B][cap]
   uint8_t* cand_label;   // [B][cap]
-  uint64_t* keys;        // [B][P]
+  uint64_t* keys;        // [B][P]     sorted keys (class segments, score desc inside)
+  uint64_t* keys_raw;    // [B][P]     keys in arrival order per class, then sorted runs (input of the rank merge)
   uint64_t* kept_key;    // [B][cap]
   float4* kept_box;      // [B][cap]   spill of the kept list beyond shared memory (fallback kernel)
   float4* nbox;          // [B][cap]   NMS-space box of every sorted candidate (offset applied for the trick)
@@ -219,6 +223,10 @@ __global__ void reset_kernel(Work w) {
     w.max_bits[i] = 0u;
     w.min_bits[i] = 0xFFFFFFFFu;
   }
+  if (i < w.B * w.nc) {
+    w.cls_count[i] = 0;
+    w.cls_cursor[i] = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- filter
@@ -232,8 +240,11 @@ __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float con
   __shared__ int s_cnt[8];
   __shared__ int s_base;
   __shared__ float s_hi[8], s_lo[8];
+  __shared__ int s_cls[kMaxClasses];   // candidates of this CTA per class: one global atomic per class and CTA
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < w.nc; i += blockDim.x) s_cls[i] = 0;
+  __syncthreads();
   float hi = -INFINITY, lo = INFINITY;
   for (int base = blockIdx.x * blockDim.x; base < s.A; base += gridDim.x * blockDim.x) {
     const int a = base + threadIdx.x;
@@ -261,6 +272,7 @@ __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float con
       w.cand_score[o] = score;
       w.cand_idx[o] = a;
       w.cand_label[o] = static_cast<uint8_t>(c.label);
+      atomicAdd(&s_cls[c.label & (kMaxClasses - 1)], 1);
       hi = fmaxf(hi, fmaxf(fmaxf(c.box.x, c.box.y), fmaxf(c.box.z, c.box.w)));
       lo = fminf(lo, fminf(fminf(c.box.x, c.box.y), fminf(c.box.z, c.box.w)));
     }
@@ -281,6 +293,8 @@ __global__ void __launch_bounds__(256) filter_kernel(Source s, Work w, float con
       atomicMin(&w.min_bits[b], float_order_bits(lo));
     }
   }
+  for (int i = threadIdx.x; i < w.nc; i += blockDim.x)
+    if (s_cls[i]) atomicAdd(&w.cls_count[b * w.nc + i], s_cls[i]);
 }
 
 __device__ __forceinline__ int sort_extent(int n) {
@@ -289,19 +303,37 @@ __device__ __forceinline__ int sort_extent(int n) {
   return p;
 }
 
+// Class segments of an image: [seg_start[c], seg_start[c+1]) of its sorted key array.  Known from the class counts of the
+// score filter, so the keys can be written class by class right away and every segment sorted on its own.
+__global__ void segment_bounds_kernel(Work w, int strategy) {
+  pdl_prologue();
+  const int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const int n = w.cand_count[b];
+  const ImageMode m = image_mode(w, b, strategy);
+  int32_t* st = w.seg_start + b * (w.nc + 1);
+  int pos = 0;
+  for (int c = 0; c < w.nc; ++c) {
+    st[c] = m.per_class ? pos : (c == 0 ? 0 : n);
+    pos += w.cls_count[b * w.nc + c];
+  }
+  st[w.nc] = n;
+}
+
 __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
   pdl_prologue();
   const int b = blockIdx.y;
   const int n = w.cand_count[b];
-  const int pb = sort_extent(n);
   const ImageMode m = image_mode(w, b, strategy);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pb; i += gridDim.x * blockDim.x) {
-    uint64_t k = kPadKey;
+  const int32_t* st = w.seg_start + b * (w.nc + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (i < n) {
       const int64_t o = static_cast<int64_t>(b) * w.cap + i;
-      k = make_key(m.per_class ? w.cand_label[o] : 0u, w.cand_score[o], static_cast<uint32_t>(w.cand_idx[o]));
+      const uint32_t label = m.per_class ? w.cand_label[o] : 0u;
+      // position inside the class segment in arrival order (the segment is sorted afterwards)
+      const int pos = st[label] + atomicAdd(&w.cls_cursor[b * w.nc + label], 1);
+      w.keys_raw[static_cast<int64_t>(b) * w.P + pos] = make_key(label, w.cand_score[o], static_cast<uint32_t>(w.cand_idx[o]));
     }
-    w.keys[static_cast<int64_t>(b) * w.P + i] = k;
     if (i < w.cap) w.pending[static_cast<int64_t>(b) * w.cap + i] = 0;
     if (i < w.cap) w.row_tiles[static_cast<int64_t>(b) * w.cap + i] = 0ull;
   }
@@ -310,86 +342,86 @@ __global__ void __launch_bounds__(256) build_keys_kernel(Work w, int strategy) {
   if (b == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.counters[0] = 0;
 }
 
-// ---------------------------------------------------------------------------------------------- bitonic sort
+// ---------------------------------------------------------------------------------------------- sort
 __device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
   if ((a > b) == asc) { const uint64_t t = a; a = b; b = t; }
 }
 
-// One CTA sorts the keys of one image (ascending = label, score desc, index asc).  Up to kSortSmemKeys keys the whole
-// network runs in shared memory - one launch instead of the 21 of a multi-kernel bitonic sort, whose global steps were
-// pure launch latency at <= 12 k keys per image.  Larger images (every anchor a candidate) run the levels above the
-// chunk size as global-memory steps of the same CTA and the rest chunk by chunk in shared memory.
-__global__ void __launch_bounds__(kSortThreads) sort_keys_kernel(Work w) {
-  pdl_prologue();
-  extern __shared__ uint64_t sk[];
-  const int b = blockIdx.x;
-  const int pb = sort_extent(w.cand_count[b]);
-  uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
-  const int chunk = pb < kSortSmemKeys ? pb : kSortSmemKeys;
-  // levels k <= chunk: every chunk is sorted on its own, direction alternating by global index
-  for (int base = 0; base < pb; base += chunk) {
-    for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = g[base + i];
-    __syncthreads();
-    for (int k = 2; k <= chunk; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = threadIdx.x; t < chunk / 2; t += kSortThreads) {
-          const int i = 2 * j * (t / j) + (t % j);
-          cmp_swap(sk[i], sk[i + j], ((base + i) & k) == 0);
-        }
-        __syncthreads();
-      }
-    }
-    for (int i = threadIdx.x; i < chunk; i += kSortThreads) g[base + i] = sk[i];
-    __syncthreads();
+// Sorting the keys of a class segment (ascending = score desc, index asc) in two kernels:
+//   sort_runs_kernel  - the segment is cut into runs of kRunKeys keys; one CTA sorts one run in shared memory
+//                       (bitonic network over <= 4096 keys: a quarter of the compare-exchanges per key of a 16 k network,
+//                       and the runs of all segments spread over the whole GPU);
+//   merge_runs_kernel - keys are unique, so the final position of a key is its index in its own run plus the number of
+//                       smaller keys in every other run of the segment: a few binary searches per key, no merge passes.
+// One class usually holds most candidates of an image (11 k of 11.5 k), which made a one-CTA-per-segment bitonic sort as
+// slow as sorting the whole image (190 us); runs + rank merge take ~40 us on the same load and scale to any segment size.
+constexpr int kRunKeys = 4096;
+constexpr int kRunThreads = 1024;
+
+// run index -> (segment, run inside the segment); returns false when the image has fewer runs
+__device__ __forceinline__ bool locate_run(const Work& w, int b, int run, int* seg, int* local) {
+  const int32_t* st = w.seg_start + b * (w.nc + 1);
+  int acc = 0;
+  for (int c = 0; c < w.nc; ++c) {
+    const int r = (st[c + 1] - st[c] + kRunKeys - 1) / kRunKeys;
+    if (run < acc + r) { *seg = c; *local = run - acc; return true; }
+    acc += r;
   }
-  // levels k > chunk: distances >= chunk through global memory (same CTA: __syncthreads orders them), then each chunk
-  // finishes the level in shared memory
-  for (int k = 2 * chunk; k <= pb; k <<= 1) {
-    for (int j = k >> 1; j >= chunk; j >>= 1) {
-      for (int t = threadIdx.x; t < pb / 2; t += kSortThreads) {
-        const int i = 2 * j * (t / j) + (t % j);
-        uint64_t a = g[i], c = g[i + j];
-        if ((a > c) == ((i & k) == 0)) { g[i] = c; g[i + j] = a; }
-      }
-      __syncthreads();
-    }
-    for (int base = 0; base < pb; base += chunk) {
-      for (int i = threadIdx.x; i < chunk; i += kSortThreads) sk[i] = g[base + i];
-      __syncthreads();
-      for (int j = chunk >> 1; j > 0; j >>= 1) {
-        for (int t = threadIdx.x; t < chunk / 2; t += kSortThreads) {
-          const int i = 2 * j * (t / j) + (t % j);
-          cmp_swap(sk[i], sk[i + j], ((base + i) & k) == 0);
-        }
-        __syncthreads();
-      }
-      for (int i = threadIdx.x; i < chunk; i += kSortThreads) g[base + i] = sk[i];
-      __syncthreads();
-    }
-  }
+  return false;
 }
 
-// ---------------------------------------------------------------------------------------------- segments
-__global__ void segment_bounds_kernel(Work w, int strategy) {
+__global__ void __launch_bounds__(kRunThreads) sort_runs_kernel(Work w) {
   pdl_prologue();
-  const int b = blockIdx.x;
+  __shared__ uint64_t sk[kRunKeys];
+  const int b = blockIdx.y;
+  int seg, local;
+  if (!locate_run(w, b, blockIdx.x, &seg, &local)) return;
+  const int s0 = w.seg_start[b * (w.nc + 1) + seg] + local * kRunKeys;
+  const int n = min(kRunKeys, w.seg_start[b * (w.nc + 1) + seg + 1] - s0);
+  int pb = 2;
+  while (pb < n) pb <<= 1;
+  uint64_t* g = w.keys_raw + static_cast<int64_t>(b) * w.P + s0;
+  for (int i = threadIdx.x; i < pb; i += kRunThreads) sk[i] = i < n ? g[i] : kPadKey;
+  __syncthreads();
+  for (int k = 2; k <= pb; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < pb / 2; t += kRunThreads) {
+        const int i = 2 * j * (t / j) + (t % j);
+        cmp_swap(sk[i], sk[i + j], (i & k) == 0);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += kRunThreads) g[i] = sk[i];
+}
+
+__global__ void __launch_bounds__(256) merge_runs_kernel(Work w) {
+  pdl_prologue();
+  const int b = blockIdx.y;
   const int n = w.cand_count[b];
-  const ImageMode m = image_mode(w, b, strategy);
-  const uint64_t* g = w.keys + static_cast<int64_t>(b) * w.P;
-  for (int c = threadIdx.x; c <= w.nc; c += blockDim.x) {
-    int pos;
-    if (!m.per_class) {
-      pos = (c == 0) ? 0 : n;
-    } else {
-      const uint64_t target = static_cast<uint64_t>(c) << 56;  // first key with label >= c
-      int lo = 0, hi = n;
+  const uint64_t* src = w.keys_raw + static_cast<int64_t>(b) * w.P;
+  uint64_t* dst = w.keys + static_cast<int64_t>(b) * w.P;
+  const int32_t* st = w.seg_start + b * (w.nc + 1);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t key = src[i];
+    int lo_c = 0, hi_c = w.nc;   // class segment of position i: st[lo_c] <= i < st[hi_c]
+    while (hi_c - lo_c > 1) {
+      const int mid = (lo_c + hi_c) >> 1;
+      if (st[mid] <= i) lo_c = mid; else hi_c = mid;
+    }
+    const int s0 = st[lo_c], s1 = st[lo_c + 1];
+    const int own = (i - s0) / kRunKeys;
+    int rank = (i - s0) - own * kRunKeys;
+    for (int r0 = s0, r = 0; r0 < s1; r0 += kRunKeys, ++r) {
+      if (r == own) continue;
+      int lo = r0, hi = min(r0 + kRunKeys, s1);   // keys of the other run that are smaller than this key
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (g[mid] < target) lo = mid + 1; else hi = mid;
+        if (src[mid] < key) lo = mid + 1; else hi = mid;
       }
-      pos = (c == w.nc) ? n : lo;
+      rank += lo - r0;
     }
-    w.seg_start[b * (w.nc + 1) + c] = pos;
+    dst[s0 + rank] = key;
   }
 }
 
@@ -543,22 +575,27 @@ __global__ void __launch_bounds__(256) cell_count_kernel(Work w, int strategy) {
     fx = fminf(fmaxf(fx, -1.0e9f), 1.0e9f);   // NaN -> -1e9 (fmaxf drops the NaN), then an ordinary integer
     fy = fminf(fmaxf(fy, -1.0e9f), 1.0e9f);
     const int cx = static_cast<int>(fx) & (kGrid - 1), cy = static_cast<int>(fy) & (kGrid - 1);
-    const int cid = cy * kGrid + cx;
+    // size class: 0 = larger than a quarter of the range ... 3 = at most 1/16 of it (NaN sizes land in class 0)
+    const float sz = fmaxf(bx.z - bx.x, bx.w - bx.y) * sc;   // in cells
+    const int sz_class = sz <= 0.0625f * kGrid ? 3 : sz <= 0.125f * kGrid ? 2 : sz <= 0.25f * kGrid ? 1 : 0;
+    const int cid = (sz_class * kGrid + cy) * kGrid + cx;
     w.cell_id[static_cast<int64_t>(b) * w.cap + i] = static_cast<uint16_t>(cid);
     atomicAdd(&w.cell_hist[(static_cast<int64_t>(b) * w.nc + c) * kCells + cid], 1);
   }
 }
 
-// counts -> first position of every cell (exclusive scan of kCells = 1024 counters per segment)
-__global__ void __launch_bounds__(kCells) cell_scan_kernel(Work w) {
+// counts -> first position of every cell (exclusive scan of the kCells counters of a segment; 4 consecutive per thread)
+constexpr int kScanThreads = kCells / 4;
+__global__ void __launch_bounds__(kScanThreads) cell_scan_kernel(Work w) {
   pdl_prologue();
-  __shared__ int wsum[kCells / 32];
+  __shared__ int wsum[32];
   const int sgm = blockIdx.y * w.nc + blockIdx.x;
   if (w.seg_word_off[sgm] < 0) return;
-  int32_t* h = w.cell_hist + static_cast<int64_t>(sgm) * kCells;
+  int4* h = reinterpret_cast<int4*>(w.cell_hist + static_cast<int64_t>(sgm) * kCells);
   const int tid = threadIdx.x, lane = tid & 31;
-  const int v = h[tid];
-  int incl = v;
+  const int4 v = h[tid];
+  const int mine = v.x + v.y + v.z + v.w;
+  int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const int u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -567,7 +604,7 @@ __global__ void __launch_bounds__(kCells) cell_scan_kernel(Work w) {
   if (lane == 31) wsum[tid >> 5] = incl;
   __syncthreads();
   if (tid < 32) {
-    const int x = wsum[tid];
+    const int x = tid < kScanThreads / 32 ? wsum[tid] : 0;
     int sc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -577,7 +614,8 @@ __global__ void __launch_bounds__(kCells) cell_scan_kernel(Work w) {
     wsum[tid] = sc - x;
   }
   __syncthreads();
-  h[tid] = wsum[tid >> 5] + incl - v;
+  const int base = wsum[tid >> 5] + incl - mine;
+  h[tid] = make_int4(base, base + v.x, base + v.x + v.y, base + v.x + v.y + v.z);
 }
 
 // scatter into spatial order: srank[pos] = index in the score order, sbox[pos] = its NMS-space box
@@ -628,18 +666,26 @@ __global__ void __launch_bounds__(kTileListThreads) tile_list_kernel(Work w, flo
   }
   __syncthreads();
   const bool cull = (thr >= 0.0f);   // a negative threshold suppresses disjoint boxes too: every pair counts
-  const long long pairs = static_cast<long long>(T) * T;
-  for (long long p = threadIdx.x; p < pairs; p += kTileListThreads) {
-    const int r = static_cast<int>(p / T), c = static_cast<int>(p - static_cast<long long>(r) * T);
-    if (c < r) continue;
-    if (cull) {
-      const float4 a = chunk_bb[r], q = chunk_bb[c];
-      if (!(fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y))) continue;
+  // warp per row chunk, lanes over the column chunks; one slot range per warp and iteration (ballot + one atomic)
+  for (int r = warp; r < T; r += kTileListThreads / 32) {
+    const float4 a = chunk_bb[r];
+    for (int c0 = r; c0 < T; c0 += 32) {
+      const int c = c0 + lane;
+      bool hit = c < T;
+      if (hit && cull) {
+        const float4 q = chunk_bb[c];
+        hit = fminf(a.z, q.z) > fmaxf(a.x, q.x) && fminf(a.w, q.w) > fmaxf(a.y, q.y);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+      if (bal == 0u) continue;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&w.counters[0], __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int slot = base + __popc(bal & ((1u << lane) - 1u));
+      if (hit && slot < w.max_tiles)
+        w.tile_list[slot] = (static_cast<unsigned long long>(sgm) << 40) | (static_cast<unsigned long long>(r) << 20) |
+                            static_cast<unsigned long long>(c);
     }
-    const int slot = atomicAdd(&w.counters[0], 1);
-    if (slot < w.max_tiles)
-      w.tile_list[slot] = (static_cast<unsigned long long>(sgm) << 40) | (static_cast<unsigned long long>(r) << 20) |
-                          static_cast<unsigned long long>(c);
   }
 }
 
@@ -681,22 +727,23 @@ __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, fl
       if (thr_nonneg) {
         // phase 1, branch-free: which column boxes intersect this row box at all (inter == 0 never exceeds thr >= 0);
         // phase 2: the exact IEEE IoU only for those
+        // min(x2) - max(x1) > 0  <=>  both right edges lie beyond both left edges: four compares chained into one
+        // predicate and one predicated OR per pair (a NaN coordinate fails the compares; such a box has a NaN area and
+        // can never exceed the threshold, so dropping it here is exact).  The row box's own "x2 > x1 && y2 > y1" part is
+        // hoisted out of the loop.
+        const bool row_ok = rb.z > rb.x && rb.w > rb.y;
         uint32_t lo = 0u, hi = 0u;
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float4 cb = cbox[grp][j];
-          const float ww = __fsub_rn(fminf(rb.z, cb.z), fmaxf(rb.x, cb.x));
-          const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
-          lo |= (fminf(ww, hh) > 0.0f ? 1u : 0u) << j;
+          if (rb.z > cb.x && cb.z > rb.x && rb.w > cb.y && cb.w > rb.y) lo |= 1u << j;
         }
-#pragma unroll 8
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float4 cb = cbox[grp][32 + j];
-          const float ww = __fsub_rn(fminf(rb.z, cb.z), fmaxf(rb.x, cb.x));
-          const float hh = __fsub_rn(fminf(rb.w, cb.w), fmaxf(rb.y, cb.y));
-          hi |= (fminf(ww, hh) > 0.0f ? 1u : 0u) << j;
+          if (rb.z > cb.x && cb.z > rb.x && rb.w > cb.y && cb.w > rb.y) hi |= 1u << j;
         }
-        m = (static_cast<unsigned long long>(hi) << 32) | lo;
+        m = row_ok ? ((static_cast<unsigned long long>(hi) << 32) | lo) : 0ull;
       } else {
         m = ~0ull;
       }
@@ -727,7 +774,20 @@ __global__ void __launch_bounds__(64 * kMaskGroups) mask_tiles_kernel(Work w, fl
 // targets (pending - 1; at zero the target is kept).  One thread per listed box: its row's tile bitmap names the few
 // mask words that hold its edges.  The rounds needed = the longest kept / suppressed alternation among overlapping
 // boxes, independent of the segment length.
+// warp-aggregated slot allocation: the threads of a warp that reach this call together take one atomicAdd for all of
+// them (thousands of pushes onto one shared-memory counter would otherwise serialise)
+__device__ __forceinline__ int agg_slot(int* counter) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(static_cast<int>(m)) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + __popc(m & ((1u << lane) - 1u));
+}
+
 constexpr int kResolveThreads = 1024;
+constexpr int kResolveSmemN = 24576;   // segments up to this size keep their in-degree counters in shared memory
 __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(Work w) {
   pdl_prologue();
   extern __shared__ uint32_t resolve_smem[];  // removed[W] | keptb[W]
@@ -748,6 +808,11 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(Work w) {
   const unsigned long long* mask = w.mask + woff;
   const unsigned long long* row_tiles = w.row_tiles + static_cast<int64_t>(b) * w.cap + s0;
   int32_t* pend = w.pending + static_cast<int64_t>(b) * w.cap + s0;
+  if (n <= kResolveSmemN) {   // shared-memory copy: the count-downs are shared-memory atomics instead of L2 round trips
+    int32_t* pend_s = reinterpret_cast<int32_t*>(resolve_smem + 2 * W);
+    for (int j = threadIdx.x; j < n; j += kResolveThreads) pend_s[j] = pend[j];
+    pend = pend_s;
+  }
   // the kept-box spill area (16 bytes per box) is unused on the mask path: two frontier lists of n entries each
   int32_t* lists = reinterpret_cast<int32_t*>(w.kept_box + static_cast<int64_t>(b) * w.cap + s0);
   const uint64_t* keys = w.keys + static_cast<int64_t>(b) * w.P + s0;
@@ -759,7 +824,7 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(Work w) {
   for (int j = tid; j < n; j += kResolveThreads) {
     if (pend[j] == 0) {
       atomicOr(&keptb[j >> 5], 1u << (j & 31));
-      if (row_tiles[j] != 0ull) lists[atomicAdd(&list_n[0], 1)] = j;
+      if (row_tiles[j] != 0ull) lists[agg_slot(&list_n[0])] = j;
     }
   }
   __syncthreads();
@@ -793,12 +858,12 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(Work w) {
             const uint32_t bit = 1u << (j & 31);
             if (kept_i) {
               const uint32_t old = atomicOr(&removed[j >> 5], bit);
-              if (!(old & bit) && row_tiles[j] != 0ull) out[atomicAdd(&list_n[nxt], 1)] = j | static_cast<int>(0x80000000u);
+              if (!(old & bit) && row_tiles[j] != 0ull) out[agg_slot(&list_n[nxt])] = j | static_cast<int>(0x80000000u);
             } else if (!(removed[j >> 5] & bit)) {
               // a kept better neighbour never releases, so pending reaches zero only if all of them are suppressed
               if (atomicSub(&pend[j], 1) == 1) {
                 atomicOr(&keptb[j >> 5], bit);
-                if (row_tiles[j] != 0ull) out[atomicAdd(&list_n[nxt], 1)] = j;
+                if (row_tiles[j] != 0ull) out[agg_slot(&list_n[nxt])] = j;
               }
             }
           }
@@ -1011,7 +1076,7 @@ inline int pow2_ceil(int v) {
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 struct Layout {
-  int64_t off_count, off_max, off_min, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys,
+  int64_t off_count, off_max, off_min, off_clscount, off_clscursor, off_segstart, off_segkept, off_score, off_idx, off_label, off_keys, off_keysraw,
       off_keptkey, off_keptbox, off_nbox, off_tileoff, off_wordoff, off_rowtiles, off_pending, off_hist, off_cellid, off_srank, off_sbox, off_tilelist,
       off_counters, off_mask, mask_words, max_tiles, total;
 };
@@ -1031,12 +1096,15 @@ Layout make_layout(int B, int cap, int P, int nc) {
   l.off_count = o; o = align_up(o + 4ll * B, 256);
   l.off_max = o; o = align_up(o + 4ll * B, 256);
   l.off_min = o; o = align_up(o + 4ll * B, 256);
+  l.off_clscount = o; o = align_up(o + 4ll * B * nc, 256);
+  l.off_clscursor = o; o = align_up(o + 4ll * B * nc, 256);
   l.off_segstart = o; o = align_up(o + 4ll * B * (nc + 1), 256);
   l.off_segkept = o; o = align_up(o + 4ll * B * nc, 256);
   l.off_score = o; o = align_up(o + 4ll * B * cap, 256);
   l.off_idx = o; o = align_up(o + 4ll * B * cap, 256);
   l.off_label = o; o = align_up(o + 1ll * B * cap, 256);
   l.off_keys = o; o = align_up(o + 8ll * B * P, 256);
+  l.off_keysraw = o; o = align_up(o + 8ll * B * P, 256);
   l.off_keptkey = o; o = align_up(o + 8ll * B * cap, 256);
   l.off_keptbox = o; o = align_up(o + 16ll * B * cap, 256);
   l.off_nbox = o; o = align_up(o + 16ll * B * cap, 256);
@@ -1066,12 +1134,15 @@ Work make_work(void* ws, int B, int cap, int nc) {
   w.cand_count = reinterpret_cast<int32_t*>(p + l.off_count);
   w.max_bits = reinterpret_cast<uint32_t*>(p + l.off_max);
   w.min_bits = reinterpret_cast<uint32_t*>(p + l.off_min);
+  w.cls_count = reinterpret_cast<int32_t*>(p + l.off_clscount);
+  w.cls_cursor = reinterpret_cast<int32_t*>(p + l.off_clscursor);
   w.seg_start = reinterpret_cast<int32_t*>(p + l.off_segstart);
   w.seg_kept = reinterpret_cast<int32_t*>(p + l.off_segkept);
   w.cand_score = reinterpret_cast<float*>(p + l.off_score);
   w.cand_idx = reinterpret_cast<int32_t*>(p + l.off_idx);
   w.cand_label = p + l.off_label;
   w.keys = reinterpret_cast<uint64_t*>(p + l.off_keys);
+  w.keys_raw = reinterpret_cast<uint64_t*>(p + l.off_keysraw);
   w.kept_key = reinterpret_cast<uint64_t*>(p + l.off_keptkey);
   w.kept_box = reinterpret_cast<float4*>(p + l.off_keptbox);
   w.nbox = reinterpret_cast<float4*>(p + l.off_nbox);
@@ -1121,7 +1192,7 @@ template <bool kFromPred>
 int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thres, int strategy, int max_det,
                  float* det, int32_t* det_count, int32_t* keep_index, cudaStream_t st) {
   const int B = w.B;
-  launch_pdl(reset_kernel, (B + 255) / 256, 256, 0, st, w);
+  launch_pdl(reset_kernel, (B * w.nc + 255) / 256, 256, 0, st, w);
   if (int rc = count_launch("reset_kernel")) return rc;
   {
     int gx = (s.A + 255) / 256;
@@ -1129,20 +1200,23 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
     launch_pdl(filter_kernel<kFromPred>, dim3(gx, B), 256, 0, st, s, w, conf_thres);
     if (int rc = count_launch("filter_kernel")) return rc;
   }
+  launch_pdl(segment_bounds_kernel, B, 32, 0, st, w, strategy);
+  if (int rc = count_launch("segment_bounds_kernel")) return rc;
   {
-    int gx = w.P / 256;
+    int gx = (w.cap + 255) / 256;
     if (gx > 1024) gx = 1024;
     launch_pdl(build_keys_kernel, dim3(gx, B), 256, 0, st, w, strategy);
     if (int rc = count_launch("build_keys_kernel")) return rc;
   }
   {
-    const int keys = w.P < kSortSmemKeys ? w.P : kSortSmemKeys;
-    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(sort_keys_kernel), kSortSmemKeys * 8)) return rc;
-    launch_pdl(sort_keys_kernel, B, kSortThreads, static_cast<size_t>(keys) * 8, st, w);
-    if (int rc = count_launch("sort_keys_kernel")) return rc;
+    const int runs = (w.cap + kRunKeys - 1) / kRunKeys + w.nc;   // upper bound of the runs of an image
+    launch_pdl(sort_runs_kernel, dim3(runs, B), kRunThreads, 0, st, w);
+    if (int rc = count_launch("sort_runs_kernel")) return rc;
+    int gx = (w.cap + 255) / 256;
+    if (gx > 256) gx = 256;
+    launch_pdl(merge_runs_kernel, dim3(gx, B), 256, 0, st, w);
+    if (int rc = count_launch("merge_runs_kernel")) return rc;
   }
-  launch_pdl(segment_bounds_kernel, B, 256, 0, st, w, strategy);
-  if (int rc = count_launch("segment_bounds_kernel")) return rc;
   {
     int gx = (w.cap + 255) / 256;
     if (gx > 1024) gx = 1024;
@@ -1157,7 +1231,7 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
     if (gx * B < device_sm_count()) gx = (device_sm_count() + B - 1) / B;   // enough CTAs to zero the mask words
     launch_pdl(cell_count_kernel, dim3(gx, B), 256, 0, st, w, strategy);
     if (int rc = count_launch("cell_count_kernel")) return rc;
-    launch_pdl(cell_scan_kernel, dim3(w.nc, B), kCells, 0, st, w);
+    launch_pdl(cell_scan_kernel, dim3(w.nc, B), kScanThreads, 0, st, w);
     if (int rc = count_launch("cell_scan_kernel")) return rc;
     launch_pdl(cell_scatter_kernel, dim3(gx, B), 256, 0, st, w);
     if (int rc = count_launch("cell_scatter_kernel")) return rc;
@@ -1171,7 +1245,9 @@ int run_pipeline(const Source& s, const Work& w, float conf_thres, float nms_thr
   if (w.topk == 0) {
     int t = (w.cap + 63) / 64;
     if (t > kMaxScanTiles) t = kMaxScanTiles;
-    launch_pdl(resolve_kernel, dim3(w.nc, B), kResolveThreads, static_cast<size_t>(t) * 16, st, w);
+    const size_t smem = static_cast<size_t>(t) * 16 + static_cast<size_t>(w.cap < kResolveSmemN ? w.cap : kResolveSmemN) * 4;
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(resolve_kernel), kMaxScanTiles * 16 + kResolveSmemN * 4)) return rc;
+    launch_pdl(resolve_kernel, dim3(w.nc, B), kResolveThreads, smem, st, w);
     if (int rc = count_launch("resolve_kernel")) return rc;
   }
   launch_pdl(nms_segment_kernel<kFromPred>, dim3(w.nc, B), kNmsThreads, 0, st, s, w, nms_thres, strategy);
