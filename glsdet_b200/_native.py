@@ -115,6 +115,7 @@ SIGNATURES = {
     "glsdet_conv_create": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
     "glsdet_conv_launch": (C.c_int, [C.c_void_p, C.c_void_p]),
     "glsdet_conv_destroy": (None, [C.c_void_p]),
+    "glsdet_conv_read_trace": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "glsdet_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_nhwc_bf16_to_nchw_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -91,13 +91,23 @@ struct alignas(64) ConvKParams {
   int64_t out_plane;   // NCHW output: elements between channel planes (Ho * Wo, or the anchor count of all levels)
   float dec_stride, dec_in_w, dec_in_h;
   int32_t epi;   // EPI_* epilogue specialisation chosen at create time
+  int32_t hbias;     // s_bias holds bias / 2 (fast SiLU epilogues: EPI_BF16* and the prediction-MMA class)
   int32_t a_f16;     // sources, weights (and the staged operand of the prediction MMA) are fp16 instead of bf16
   int32_t out_f16;   // 16-bit NHWC output is fp16
   int32_t post_f16;  // post-activation residual is fp16
   const float* pred_w;   // fused prediction conv: fp32 [pred_n][N]
   const float* pred_b;
   int32_t pred_n, pred_act;
+  unsigned long long* trace;   // diagnostic (GLSDET_CONV_TRACE=1): %globaltimer stamps of CTA 0, see glsdet_conv_read_trace
 };
+
+__device__ __forceinline__ void trace_stamp(const ConvKParams& p, int slot) {
+  if (p.trace != nullptr && blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[slot] = t;
+  }
+}
 
 enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F32_PLAIN = 4, EPI_NCHW_RAW = 5,
        EPI_ROWS_BOX = 6, EPI_ROWS_SIGMOID = 7, EPI_TOWER_PRED = 8, EPI_TOWER_PRED_MMA = 9, EPI_BF16_PREPOST = 10 };
@@ -286,6 +296,27 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
                                            const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1,
                                            int dt) {   // dt: bit 0 = fp16 output, bit 1 = fp16 post residual
   float v[16];
+  if (act == GLSDET_ACT_SILU) {
+    // s_bias holds bias / 2 (ConvKParams::hbias): h = x / 2 in one FMA, silu(x) = h + h * tanh(h)
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(s_bias + j);
+      v[j] = fmaf(__uint_as_float(raw[j]), 0.5f, bv.x);
+      v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), 0.5f, bv.y);
+      v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), 0.5f, bv.z);
+      v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), 0.5f, bv.w);
+    }
+    if (PRE) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(pre + j));
+        v[j] = fmaf(t.x, 0.5f, v[j]); v[j + 1] = fmaf(t.y, 0.5f, v[j + 1]);
+        v[j + 2] = fmaf(t.z, 0.5f, v[j + 2]); v[j + 3] = fmaf(t.w, 0.5f, v[j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], tanh_approx(v[j]), v[j]);
+  } else {
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
     const float4 bv = *reinterpret_cast<const float4*>(s_bias + j);
@@ -301,9 +332,8 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
       v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
     }
   }
+  }
   if (act == GLSDET_ACT_SILU) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
   } else if (act == kActSiluExact) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
@@ -521,17 +551,18 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint64_t* b_full = bars + 2 * kMaxStages;
   uint64_t* b_empty = bars + 3 * kMaxStages;
   uint64_t* tfull_bar = bars + 4 * kMaxStages;
-  uint64_t* tempty_bar = bars + 4 * kMaxStages + 3;   // tfull / tempty: up to 3 accumulator slots each
-  uint64_t* bres_full = bars + 4 * kMaxStages + 6;
-  uint64_t* pred_bar = bars + 4 * kMaxStages + 7;
-  uint64_t* pstage_bar = bars + 4 * kMaxStages + 9;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 8);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 10);  // [n_blocks * block_n], zero padded
+  uint64_t* tempty_bar = bars + 4 * kMaxStages + 4;   // tfull / tempty: up to 4 accumulator slots each
+  uint64_t* bres_full = bars + 4 * kMaxStages + 8;
+  uint64_t* pred_bar = bars + 4 * kMaxStages + 9;
+  uint64_t* pstage_bar = bars + 4 * kMaxStages + 11;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 10);
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 12);  // [n_blocks * block_n], zero padded (x 0.5: hbias)
   float* s_pw = s_bias + p.n_blocks * p.block_n;                         // FMA prediction path: weights [N][16]
   float* s_red = s_pw + p.block_n * 16;                                  // [2][128][16] partial sums of the upper column half
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   const uint32_t cta_rank = k2 ? cluster_ctarank() : 0u;
   const int work0 = k2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int work_stride = k2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -554,7 +585,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&tfull_bar[s], 1);
       const int ew_arr = (EW == 16 && p.egrp) ? EW / 2 : EW;   // warps that drain one accumulator slot
       mbar_init(&tempty_bar[s], k2 ? 2 * ew_arr : ew_arr);  // 2-CTA: the peer's epilogue warps arrive too
@@ -574,8 +605,13 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     griddep_wait();
     griddep_launch_dependents();
   }
-  for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
-    s_bias[i] = (p.bias != nullptr && i < p.N) ? __ldg(p.bias + i) : 0.0f;
+  if (threadIdx.x == 0) trace_stamp(p, 1);
+  {
+    // hbias: the tanh-form SiLU epilogues work on h = x / 2 = fma(acc, 0.5, bias / 2) - one FMA-pipe op less per element
+    const float bscale = p.hbias ? 0.5f : 1.0f;
+    for (int i = threadIdx.x; i < p.n_blocks * p.block_n; i += kThreads)
+      s_bias[i] = (p.bias != nullptr && i < p.N) ? bscale * __ldg(p.bias + i) : 0.0f;
+  }
   if (pred_mma) {
     // prediction weights fp32 [pred_n][N] -> bf16 B operand (16 rows, K-major, 128-byte swizzle) per 64-channel tile
     // (2-CTA: the M256 x N16 prediction MMA takes 8 of the 16 rows from each CTA, at the same shared-memory offset)
@@ -601,6 +637,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   if (k2) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace_stamp(p, 2);
 
   if (k2 && warp == 0 && lane == 0) {
     // ------------------------------------------------------------ TMA producer, 2-CTA mode (single ring)
@@ -690,6 +727,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       mbar_wait(&a_empty[sa], pha ^ 1u);
       mbar_arrive_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
       tma_load_5d(smem_a + sa * p.a_bytes, tm, &a_full[sa], c0, c1, c2, c3, c4);
+      if (p.trace != nullptr && p.trace[3] == 0ull) trace_stamp(p, 3);
       if (++sa == p.sa) { sa = 0; pha ^= 1u; }
     };
     int wb = 0;   // image index of the weight matrix (per-image weights)
@@ -792,6 +830,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       int src = 0, o = 0, ch = 0;   // position of this A step in the producer's (source, kx | tap, chunk) order
       for (int a = 0; a < p.a_steps; ++a) {
         mbar_wait(&a_full[sa], pha);
+        if (p.trace != nullptr && lane == 0 && p.trace[4] == 0ull) trace_stamp(p, 4);
         const uint32_t a_addr = smem_u32(smem_a + sa * p.a_bytes);
         const int nch = src ? p.chunks1 : p.chunks0;
         for (int sub = 0; sub < p.nsub; ++sub) {
@@ -838,6 +877,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           if (++o == p.kw) { o = 0; ++src; }
         }
       }
+      if (lane == 0) trace_stamp(p, 5);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -903,6 +943,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       const uint32_t aph = static_cast<uint32_t>(it / p.nacc) & 1u;
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (p.trace != nullptr && warp == 4 && lane == 0 && p.trace[6] == 0ull) trace_stamp(p, 6);
       for (int m = 0; m < mt; ++m, ++tcount) {
       const uint32_t tcol = static_cast<uint32_t>((as * mt + m) * p.block_n);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tcol;
@@ -1062,20 +1103,21 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
           // the first 16 columns of this (already drained) accumulator, and the lower-half warps decode + store.
           epi_walk(taddr, c_begin, c_end, [&](const uint32_t (&raw)[16], int c) {
             float v[16];
+            const float ascale = p.hbias ? 0.5f : 1.0f;   // hbias: sb holds bias / 2, v = x / 2
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
               const float4 bv = *reinterpret_cast<const float4*>(sb + c * 16 + j);
-              v[j] = __uint_as_float(raw[j]) + bv.x;
-              v[j + 1] = __uint_as_float(raw[j + 1]) + bv.y;
-              v[j + 2] = __uint_as_float(raw[j + 2]) + bv.z;
-              v[j + 3] = __uint_as_float(raw[j + 3]) + bv.w;
+              v[j] = fmaf(__uint_as_float(raw[j]), ascale, bv.x);
+              v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), ascale, bv.y);
+              v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), ascale, bv.z);
+              v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), ascale, bv.w);
             }
             if (silu && p.act_epi == kActSiluExact) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
             } else if (silu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+              for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], tanh_approx(v[j]), v[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -1167,16 +1209,20 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
         else mbar_arrive(&tempty_bar[as]);
       }
     }
+    if (warp == 4 && lane == 0) trace_stamp(p, 7);
     if (p.ts && tsg.issuer) tma_store_wait_all();   // shared memory must outlive the bulk stores
+    if (warp == 4 && lane == 0) trace_stamp(p, 8);
   }
 
   tc_fence_before();
   __syncthreads();
   if (k2) cluster_sync_all();   // the peer may still be reading operands / signalling barriers of this CTA
   tc_fence_after();
+  if (threadIdx.x == 0) trace_stamp(p, 9);
   if (warp == 2) {
     if (k2) tmem2_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
     else tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (lane == 0) trace_stamp(p, 10);
   }
 }
 
@@ -1414,7 +1460,16 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (const char* e = getenv("GLSDET_CONV_MT_MAXN")) mt_max_n = atoi(e);
     int w2 = 16;
     const int64_t items2 = pick_tile(2, &w2) * d->batch * g.n_blocks;
-    const bool legal = !two_cta && mt_mode != 1 && g.block_n <= mt_max_n && 2 * g.block_n <= 512;
+    // resident-weight 1x1 convs gain nothing from sharing a weight stage between two tiles; with one tile per item the
+    // 128-column accumulators fit four slots (two per epilogue group, see nacc): 128 -> 128 at 256^2 156 -> 146 us,
+    // 256 -> 128 at 128^2 84 -> 80 us.  K = 64 (one A stage per tile) measured slower that way (87 -> 90 us) and keeps
+    // two-tile items.  GLSDET_CONV_BRES_MT1=0 disables it.
+    const bool bres_likely = g.n_blocks == 1 && d->weight_batch_stride == 0 &&
+                             g.taps * (g.chunks0 + g.chunks1) * g.block_n * kRowBytes <= 96 * 1024;
+    const char* mt1_env = getenv("GLSDET_CONV_BRES_MT1");
+    const bool mt1_bres = !(mt1_env && mt1_env[0] == '0') && bres_likely && d->ksize == 1 && g.block_n == 128 &&
+                          (g.chunks0 + g.chunks1) >= 2;
+    const bool legal = !two_cta && mt_mode != 1 && !mt1_bres && g.block_n <= mt_max_n && 2 * g.block_n <= 512;
     if (legal && (mt_mode == 2 || items2 >= 2 * static_cast<int64_t>(sms))) { mt = 2; best_w = w2; }
     else pick_tile(1, &best_w);
   }
@@ -1569,6 +1624,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // prediction-MMA class: three accumulator slots (see ConvKParams::nacc); GLSDET_CONV_NACC=2 restores two
   if (pred_mma && mt == 1 && 3 * g.block_n <= 512 && !(getenv("GLSDET_CONV_NACC") && getenv("GLSDET_CONV_NACC")[0] == '2'))
     k.nacc = 3;
+  // two epilogue groups on alternate work items: four accumulator slots give each group two, so the MMAs of a group's
+  // next item run while it drains the current one (with two slots the MMA + commit latency is exposed once per item)
+  {
+    const bool will_egrp = egrp_want && ts && (g.block_n == 64 || g.block_n == 128);
+    if (will_egrp && k.nacc == 2 && 4 * mt * g.block_n <= 512 && getenv("GLSDET_CONV_NO_NACC4") == nullptr) k.nacc = 4;
+  }
   int cols = 32;
   while (cols < k.nacc * mt * g.block_n) cols <<= 1;
   k.tmem_cols = cols;
@@ -1598,6 +1659,14 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (fused_pred) k.epi = pred_mma ? EPI_TOWER_PRED_MMA : EPI_TOWER_PRED;
   }
 
+  k.trace = nullptr;
+  if (getenv("GLSDET_CONV_TRACE") != nullptr) {
+    void* tp = nullptr;
+    if (cudaMalloc(&tp, 16 * sizeof(unsigned long long)) == cudaSuccess) {
+      cudaMemset(tp, 0, 16 * sizeof(unsigned long long));
+      k.trace = static_cast<unsigned long long*>(tp);
+    }
+  }
   int rc = 0;
   if (d->stride == 1) {
     rc = encode_act_map(&k.tmA[0], d->src0, d->src0_c, d->src0_ld, d->batch, d->height, d->width,
@@ -1675,6 +1744,9 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // as the MMAs of two tiles with two warps per scheduler; four warps per scheduler halve the per-thread work
   if (op->ec == EC_PRED_MMA && (g.block_n % 64) == 0 && getenv("GLSDET_CONV_EPI8") == nullptr) op->ec = EC_PRED_MMA16;
   if (getenv("GLSDET_CONV_ONE_KERNEL") != nullptr) op->ec = EC_ALL;
+  k.hbias = (k.act_epi == GLSDET_ACT_SILU &&
+             (k.epi == EPI_BF16 || k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST || k.epi == EPI_BF16_PREPOST ||
+              k.epi == EPI_TOWER_PRED_MMA)) ? 1 : 0;
   if (op->two_cta)   // the pair kernel: one all-epilogue binary, plus the prediction class with 16 epilogue warps
     op->ec = getenv("GLSDET_CONV_ONE_KERNEL") != nullptr ? EC2_ALL
              : op->ec == EC_PRED_MMA16 ? EC2_PRED_MMA16 : op->ec == EC_BF16_TS16 ? EC2_BF16_TS16 : EC2_ALL;
@@ -1754,5 +1826,16 @@ extern "C" int glsdet_conv_launch(glsdet_conv_t* op, void* stream) {
 }
 
 extern "C" void glsdet_conv_destroy(glsdet_conv_t* op) {
-  if (op) free(op);
+  if (op) {
+    if (op->kp.trace) cudaFree(op->kp.trace);
+    free(op);
+  }
+}
+
+extern "C" int glsdet_conv_read_trace(glsdet_conv_t* op, uint64_t* out16) {
+  GLSDET_REQUIRE(op != nullptr && out16 != nullptr, "conv_read_trace: null argument");
+  GLSDET_REQUIRE(op->kp.trace != nullptr, "conv_read_trace: the op was not created with GLSDET_CONV_TRACE=1");
+  GLSDET_CHECK_CUDA(cudaMemcpy(out16, op->kp.trace, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  GLSDET_CHECK_CUDA(cudaMemset(op->kp.trace, 0, 16 * sizeof(uint64_t)));
+  return 0;
 }

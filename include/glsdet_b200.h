@@ -162,6 +162,11 @@ int glsdet_conv_weight_shape(const glsdet_conv_desc* desc, int32_t* n_pad, int32
 int glsdet_conv_create(const glsdet_conv_desc* desc, glsdet_conv_t** op);
 int glsdet_conv_launch(glsdet_conv_t* op, void* stream);
 void glsdet_conv_destroy(glsdet_conv_t* op);
+/* Diagnostic: ops created while GLSDET_CONV_TRACE=1 record %globaltimer stamps (ns) of CTA 0 - 0 kernel entry, 1 after
+ * griddepcontrol.wait, 2 set-up done, 3 first TMA load issued, 4 first operand stage landed, 5 last MMA committed,
+ * 6 first accumulator ready, 7 epilogue done, 8 bulk stores drained, 9 CTA joined, 10 TMEM released.  Copies the 16
+ * slots to the host (synchronous) and clears them.  Not part of the reference's interface. */
+int glsdet_conv_read_trace(glsdet_conv_t* op, uint64_t* out16);
 
 /*
  * fp32 evaluation of the same operator (accuracy mode: BASELINE.json configs[0], parity bar 1e-3 relative in fp32).
