@@ -23,6 +23,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
+    "-Xcompiler", "-ffp-contract=off",   # host float32 arithmetic of ufp.cu follows NumPy (no fused multiply-add)
 ]
 
 

@@ -454,6 +454,28 @@ int glsdet_batched_nms_ids(const float* boxes, const float* scores, const float*
                            int32_t* keep, int32_t* keep_count, void* stream);
 int64_t glsdet_batched_nms_workspace_bytes(int32_t k);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * UFP stage of UFPMP-Det (reference: /root/reference/yolox-ufp).
+ *
+ * glsdet_ufp_pack (HOST function, no device work): replaces mmdet.core.UnifiedForegroundPacking(bbox_list, scale,
+ *   input_shape) (mmdet/core/ufp/unified_foreground_packing.py:185-197 = scale_boxes :6-32 + ForegroundRegionGeneration
+ *   :68-103 + Packing :140-181 over spp.py:69-168 phsppog).  boxes: n x 4 float32 (x1, y1, x2, y2) coarse detections;
+ *   rows: n x 7 doubles out [x0, y0, w, h, new_x, new_y, factor]; returns the row count and the mosaic extent.
+ * glsdet_ufp_mosaic: replaces display_merge_result (ufpmp_det_eval.py:182-193): image uint8 HWC (what cv2.imread
+ *   returns) on the device, chips = n x 7 int32 (floor of the rows), canvas uint8 [can_h, can_w, 3] zero-filled, every
+ *   chip cropped, resized by its integer factor exactly like cv2.resize(INTER_LINEAR) and pasted.
+ * glsdet_ufp_merge: replaces the map-back loop + per-class py_cpu_nms (ufpmp_det_eval.py:270-306, :149-179).  dets:
+ *   [K, 5] float32 second-stage detections (x1, y1, x2, y2, score) grouped by class, cls_off[num_classes + 1] their
+ *   class offsets; mapped / out: [num_classes, cap, 5] float32 (cap <= 4096); out rows are the kept detections of each
+ *   class in score order, out_count[c] their number, mapped_count[c] the number of mapped detections (> cap = overflow). */
+int glsdet_ufp_pack(const float* boxes, int32_t n, float scale, int32_t in_w, int32_t in_h, double* rows, int32_t* n_rows,
+                    double* new_w, double* new_h);
+int glsdet_ufp_mosaic(const uint8_t* image, int32_t img_h, int32_t img_w, const int32_t* chips, int32_t n_chips,
+                      uint8_t* canvas, int32_t can_h, int32_t can_w, void* stream);
+int glsdet_ufp_merge(const float* dets, const int32_t* cls_off, int32_t num_classes, const int32_t* chips, int32_t n_chips,
+                     float nms_thresh, float* mapped, int32_t cap, float* out, int32_t* out_count, int32_t* mapped_count,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,3 +31,13 @@ def _clustered(rng, k, nc, spread=0.004, lo=0.05):
     return boxes, scores, labels
 
 
+
+
+def ufp_synth_image(seed: int, h: int, w: int) -> np.ndarray:
+    """Deterministic BGR uint8 test image of the UFP goldens (integer arithmetic only, so tests/golden/make_golden_ufp.py
+    and the tests rebuild the same bytes on any machine): smooth structure plus seeded noise."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+    rng = np.random.default_rng(seed)
+    chans = [((xx * (3 + c) + yy * (5 - c) + ((xx * xx + 3 * yy * yy) >> (5 + c)) + 40 * c) & 255) for c in range(3)]
+    img = np.stack(chans, -1) + rng.integers(-24, 25, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
