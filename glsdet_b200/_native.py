@@ -205,6 +205,11 @@ SIGNATURES = {
     "glsdet_batched_nms_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "glsdet_pil_bicubic_ksize": (C.c_int, [C.c_int32, C.c_int32]),
+    "glsdet_pil_bicubic_table": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glsdet_resize_bicubic_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "glsdet_ufp_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                   C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "glsdet_ufp_mosaic": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,

@@ -476,6 +476,21 @@ int glsdet_ufp_merge(const float* dets, const int32_t* cls_off, int32_t num_clas
                      float nms_thresh, float* mapped, int32_t cap, float* out, int32_t* out_count, int32_t* mapped_count,
                      void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * YOLO facade: resize_image (yolox-drone/models/core/utils.py:21-34; yolo.py:130) = PIL Image.resize(size, BICUBIC),
+ * optionally letterboxed onto a (128, 128, 128) canvas, on the device and bit-exact to Pillow's 8-bit resampler.
+ *   glsdet_pil_bicubic_ksize / _table (HOST functions): window size and per-output-pixel (first tap, tap count) bounds +
+ *     22-bit fixed-point weights [out_size][ksize] for resampling in_size -> out_size samples.
+ *   glsdet_resize_bicubic_u8: image uint8 HWC [in_h, in_w, 3] on the device -> canvas uint8 [can_h, can_w, 3]; the
+ *     resized image (out_h x out_w) lands at (off_y, off_x), the rest of the canvas is `fill`; tmp: [in_h, out_w, 3]
+ *     intermediate of the horizontal pass (needed when both sizes change). */
+int glsdet_pil_bicubic_ksize(int32_t in_size, int32_t out_size);
+int glsdet_pil_bicubic_table(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* kk);
+int glsdet_resize_bicubic_u8(const uint8_t* image, int32_t in_h, int32_t in_w, uint8_t* canvas, int32_t can_h, int32_t can_w,
+                             int32_t out_h, int32_t out_w, int32_t off_y, int32_t off_x, int32_t fill, uint8_t* tmp,
+                             const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v,
+                             const int32_t* kk_v, int32_t ksize_v, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,52 @@ def test_kx_folded_weight_transforms_reproduce_the_conv():
         for kx in range(2):
             out2 += torch.einsum("bhwk,nk->bnhw", rows[:, :, kx:kx + 6], ws[:, :, ky, kx])
     assert torch.allclose(out2, ref2, atol=1e-4)
+
+
+def test_pil_bicubic_tables_reproduce_pillow(native_lib):
+    """glsdet_pil_bicubic_table is a HOST function of the C ABI: its windows / 22-bit weights, applied with Pillow's two
+    passes in numpy, reproduce Image.resize(..., BICUBIC) byte for byte (the device kernels apply the same tables)."""
+    import ctypes as C
+
+    Image = pytest.importorskip("PIL.Image")
+    from glsdet_b200 import _native as N
+
+    def table(i, o):
+        ks = native_lib.glsdet_pil_bicubic_ksize(i, o)
+        b = np.zeros((o, 2), np.int32)
+        k = np.zeros((o, ks), np.int32)
+        N.check(native_lib.glsdet_pil_bicubic_table(i, o, b.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p)))
+        return b, k
+
+    def resample(img, ow, oh):
+        ih, iw, _ = img.shape
+        cur = img.astype(np.int64)
+        if ow != iw:
+            b, k = table(iw, ow)
+            out = np.zeros((ih, ow, 3), np.int64)
+            for x in range(ow):
+                lo, n = b[x]
+                out[:, x, :] = (1 << 21) + (cur[:, lo:lo + n, :] * k[x, :n][None, :, None]).sum(1)
+            cur = np.clip(out >> 22, 0, 255)
+        if oh != ih:
+            b, k = table(ih, oh)
+            out = np.zeros((oh, cur.shape[1], 3), np.int64)
+            for y in range(oh):
+                lo, n = b[y]
+                out[y] = (1 << 21) + (cur[lo:lo + n] * k[y, :n][:, None, None]).sum(0)
+            cur = np.clip(out >> 22, 0, 255)
+        return cur.astype(np.uint8)
+
+    rng = np.random.default_rng(0)
+    for ih, iw, oh, ow in ((153, 272, 256, 256), (100, 37, 64, 96), (50, 50, 50, 96), (33, 200, 128, 200), (17, 19, 160, 128)):
+        img = rng.integers(0, 256, (ih, iw, 3), dtype=np.uint8)
+        want = np.array(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))
+        assert np.array_equal(resample(img, ow, oh), want), (ih, iw, oh, ow)
+
+
+def test_letterbox_geometry_follows_reference():
+    from glsdet_b200.utils import letterbox_geometry
+
+    assert letterbox_geometry(500, 300, 416, 416, True) == (416, 249, 0, 83)      # models/core/utils.py:24-33
+    assert letterbox_geometry(333, 765, 640, 512, True) == (222, 511, 209, 0)      # int(765 * (512 / 765)) truncates to 511
+    assert letterbox_geometry(500, 300, 416, 416, False) == (416, 416, 0, 0)
