@@ -56,6 +56,13 @@ def parse_args():
     ap.add_argument("--cpu-images", type=int, default=16, help="images per pass of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample: repeat passes for about this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--total-batch", type=int, default=0,
+                    help="BASELINE configs[4]: a step is this many images in total, split evenly over the ranks and run as "
+                         "micro-batches of --batch images (strong scaling); 0 (default) = --batch images per GPU per step (weak)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE.json configs: cfg2 (index 1, the judged metric, default) = P0 YOLOX-s, 16 x 1024^2 per GPU; "
+                         "cfg3 (index 2) = MP-Det FPN + MPHead at 800x1344; cfg4 (index 3) = P0 YOLOX-l, 64 x 544x1024, "
+                         "top-1000 detections; cfg5 (index 4) = cfg2 with --total-batch 256")
     ap.add_argument("--variant", default="p0", choices=["p0", "p1", "p2"],
                     help="p0 = BASELINE configs[1] (models/ffa/yolox_ffa.py, the default and the judged metric); "
                          "p1 = models/new/yolox10.py (patch non-local attention neck, SURVEY.md section 8d row 2')")
@@ -73,11 +80,14 @@ def peaks():
 
 def conv_traffic(batch):
     """DRAM bytes (read + write) of the conv segment of one step, from the committed ncu capture (same batch only)."""
-    f = ROOT / "profiles" / "r1_conv_traffic.json"
-    if f.exists():
-        d = json.loads(f.read_text())
-        if d.get("batch") == batch:
-            return d["total_bytes_per_step"]
+    if VARIANT != "p0" or PHI != "s" or (IN_H, IN_W) != (1024, 1024):
+        return None
+    for name in ("r2_conv_traffic.json", "r1_conv_traffic.json"):
+        f = ROOT / "profiles" / name
+        if f.exists():
+            d = json.loads(f.read_text())
+            if d.get("batch") == batch:
+                return d["total_bytes_per_step"]
     return None
 
 
@@ -223,10 +233,11 @@ def run_reference_arm(args):
             times.append(dt)
     total = sum(times)
     value = n * len(times) / total
-    line = {"impl": "reference", "metric": "images/sec at 1024^2 (neck+head+NMS)", "value": value, "unit": "images/s",
+    line = {"impl": "reference", "metric": f"images/sec at {IN_H}x{IN_W} (neck+head+NMS)" if (IN_H, IN_W) != (1024, 1024) else "images/sec at 1024^2 (neck+head+NMS)",
+            "value": value, "unit": "images/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"GLSDet YOLOX-s neck+head+decode+NMS, {n} synthetic 1024x1024 images per step on the host CPU",
+            "config": {"workload": f"GLSDet YOLOX-{PHI} neck+head+decode+NMS, {n} synthetic {IN_H}x{IN_W} images per step on the host CPU",
                        "num_classes": NUM_CLASSES, "conf_thres": CONF_THRES, "nms_thres": NMS_THRES,
                        "candidates_per_image": cand, "kept_per_image": kept},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
@@ -243,7 +254,7 @@ def run_native_arm(args):
     import torch.distributed as dist
 
     from glsdet_b200 import _native as N
-    from glsdet_b200.dist import gather_detections
+    from glsdet_b200.dist import DetectionGather
 
     YoloBody = body_class()
 
@@ -275,6 +286,16 @@ def run_native_arm(args):
     net.load_state_dict(sd, strict=True)
     net = net.to(dev).eval()
     B = args.batch
+    inner = 1            # micro-batches per step and rank (strong-scaling runs: --total-batch)
+    if args.total_batch > 0:
+        if args.total_batch % world:
+            raise SystemExit(f"--total-batch {args.total_batch} is not divisible by {world} ranks")
+        per_rank = args.total_batch // world
+        B = min(B, per_rank)
+        if per_rank % B:
+            raise SystemExit(f"{per_rank} images per rank are not a multiple of the micro-batch {B}")
+        inner = per_rank // B
+    step_images = world * B * inner     # images of one step over all ranks
     host_images = make_images(B, 1000 + rank).pin_memory()
     feats = make_features(net, B, 1000 + rank, dev, images=host_images)
     host_feats = [t.cpu().pin_memory() for t in feats]
@@ -283,11 +304,26 @@ def run_native_arm(args):
     rows_cap = max_det if max_det is not None else min(args.gather_rows, plan.num_anchors)   # fixed-layout copy-out / gather rows
     nms = net.nms_for(plan, max_det)
 
-    def device_step():
+    # multi-GPU: ONE all_gather per (micro-)step, issued asynchronously into double-buffered outputs and consumed one step
+    # later, so the gather of step i overlaps the compute of step i + 1 (glsdet_b200/dist.py::DetectionGather)
+    gather = DetectionGather(B, rows_cap, dev) if world > 1 else None
+    pending = [None]
+
+    def gather_step(det, cnt, last=False):
+        if gather is None:
+            return
+        t = gather.submit(det, cnt)
+        if pending[0] is not None:
+            gather.result(pending[0])
+        pending[0] = t
+        if last:
+            gather.result(pending[0])
+            pending[0] = None
+
+    def device_step(last=False):
         det, cnt = net.detect_features(feats, conf_thres=CONF_THRES, nms_thres=NMS_THRES, strategy="auto_cuda",
                                        max_det=max_det)
-        if world > 1:
-            gather_detections(det, cnt, max_rows=rows_cap)
+        gather_step(det, cnt, last)
         return det, cnt
 
     stream = torch.cuda.current_stream()
@@ -300,15 +336,16 @@ def run_native_arm(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing (value) with the conv segment bracketed for the roofline
-    for _ in range(args.warmup):
-        device_step()
+    for i in range(args.warmup):
+        device_step(last=(i == args.warmup - 1))
     sync_all()
     launches0 = lib.glsdet_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    seg = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
+    n_micro = args.steps * inner
+    seg = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(n_micro)]
     clock.start()
     ev[0].record(stream)
-    for s in range(args.steps):
+    for s in range(n_micro):
         plan.load_features(feats)
         seg[s][0].record(stream)
         plan.run_neck()
@@ -316,19 +353,19 @@ def run_native_arm(args):
         seg[s][1].record(stream)
         det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
         seg[s][2].record(stream)
-        if world > 1:
-            gather_detections(det, cnt, max_rows=rows_cap)
+        gather_step(det, cnt, last=(s == n_micro - 1))
     ev[1].record(stream)
     sync_all()
     launches = lib.glsdet_launch_count() - launches0
+    kept_value = [int(v) for v in cnt.cpu()]     # survivors per image of the last timed (micro-)step
     elapsed_ms = ev[0].elapsed_time(ev[1])
-    conv_ms = sum(a.elapsed_time(b) for a, b, _ in seg) / args.steps
-    post_ms = sum(b.elapsed_time(c) for _, b, c in seg) / args.steps   # score filter + sort + NMS + row gather
+    conv_ms = sum(a.elapsed_time(b) for a, b, _ in seg) / n_micro      # per micro-batch of B images
+    post_ms = sum(b.elapsed_time(c) for _, b, c in seg) / n_micro      # score filter + sort + NMS + row gather
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    value = world * B * args.steps / (elapsed_ms * 1e-3)
+    value = step_images * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end-to-end through the public module API with HOST buffers, every step: pinned host input -> device ->
     # path -> detections (counts + rows) back on the host.  Two device input sets: the upload of step i+1 (copy
@@ -367,8 +404,7 @@ def run_native_arm(args):
                 stream.wait_event(uploaded[slot])
                 det, cnt = step_fn(dev_in[slot])
                 consumed[slot].record(stream)
-                if world > 1:
-                    gather_detections(det, cnt, max_rows=rows_cap)
+                gather_step(det, cnt, last=(i == n_steps - 1))
                 # the reference's copy-out (utils_bbox.py:481 output[i].cpu()): counts first, then the rows that exist
                 host_cnt[slot].copy_(cnt, non_blocking=True)
                 done[slot].record(stream)
@@ -384,7 +420,7 @@ def run_native_arm(args):
         run(max(2, args.warmup // 2))
         sync_all()
         t0 = time.perf_counter()
-        run(args.steps)
+        run(args.steps * inner)
         sync_all()
         ms = (time.perf_counter() - t0) * 1e3
         if world > 1:
@@ -399,22 +435,32 @@ def run_native_arm(args):
         image_step = lambda inp: net.detect(inp[0], **kw)
     else:   # P1: native backbone -> NCHW fp32 features (its Gram operands are built from them) -> path
         image_step = lambda inp: net.detect_features(net.backbone.features(inp[0]), **kw)
+    last_slot = (args.steps * inner - 1) & 1
     feat_ms = e2e_measure(host_feats, lambda inp: net.detect_features(inp, **kw))
-    e2e_ms = e2e_measure([host_images], image_step)
-    clocks = clock.stop()   # sampled over the device-resident timed region and the two end-to-end regions above
-    clocks["sampled_over"] = "device-resident timed region + e2e regions (features, images), 5 ms interval"
-    kept = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
+    img32_ms = e2e_measure([host_images], image_step)
+    kept_img32 = [int(v) for v in host_cnt[last_slot]]
+    d2h_rows_img32 = d2h_rows[0]
     u8_ms = None
-    if VARIANT == "p0":   # uint8 HWC frames (what a decoder delivers): normalisation fused into the Focus kernel
+    if VARIANT == "p0":   # uint8 HWC frames (what a decoder / the resize of yolo.py:130 delivers): normalisation fused into Focus
         mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
         std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
         host_u8 = ((host_images * std + mean) * 255.0).round_().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().pin_memory()
         u8_ms = e2e_measure([host_u8], lambda inp: net.detect_uint8(inp[0], **kw))
-        kept_u8 = [int(v) for v in host_cnt[(args.steps - 1) & 1]]
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    feat_value = world * B * args.steps / (feat_ms * 1e-3)
-    h2d_bytes = host_images.numel() * 4
-    h2d_feat_bytes = sum(t.numel() * 4 for t in host_feats)
+        kept_u8 = [int(v) for v in host_cnt[last_slot]]
+        d2h_rows_u8 = d2h_rows[0]
+    clocks = clock.stop()   # sampled over the device-resident timed region and the end-to-end regions above
+    clocks["sampled_over"] = "device-resident timed region + e2e regions (features, fp32 images, uint8 frames), 5 ms interval"
+    n_e2e = step_images * args.steps
+    img32_value = n_e2e / (img32_ms * 1e-3)
+    feat_value = n_e2e / (feat_ms * 1e-3)
+    h2d_img32_bytes = host_images.numel() * 4 * inner
+    h2d_feat_bytes = sum(t.numel() * 4 for t in host_feats) * inner
+    # headline e2e: the facade's input is an image, i.e. uint8 frames (YOLO.detect_image -> resize_image -> uint8 HWC,
+    # yolo.py:130-139); the fp32-image and fp32-feature entry points are reported next to it
+    if u8_ms is not None:
+        e2e_ms, e2e_value, h2d_bytes, kept, e2e_rows = u8_ms, n_e2e / (u8_ms * 1e-3), B * IN_H * IN_W * 3 * inner, kept_u8, d2h_rows_u8
+    else:
+        e2e_ms, e2e_value, h2d_bytes, kept, e2e_rows = img32_ms, img32_value, h2d_img32_bytes, kept_img32, d2h_rows_img32
 
     # ---- device-resident image -> detections (backbone included), for the record
     dev_images = host_images.to(dev)
@@ -423,10 +469,9 @@ def run_native_arm(args):
     sync_all()
     evi = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     evi[0].record(stream)
-    for _ in range(args.steps):
+    for i in range(args.steps):
         det, cnt = image_step([dev_images])
-        if world > 1:
-            gather_detections(det, cnt, max_rows=rows_cap)
+        gather_step(det, cnt, last=(i == args.steps - 1))
     evi[1].record(stream)
     sync_all()
     img_ms = evi[0].elapsed_time(evi[1]) / args.steps
@@ -434,48 +479,63 @@ def run_native_arm(args):
         t = torch.tensor([img_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         img_ms = float(t.item())
-    d2h_bytes = host_cnt[0].numel() * 4 + B * d2h_rows[0] * 7 * 4   # counts + the [B, max kept, 7] rows of the last step
+    d2h_bytes = (host_cnt[0].numel() * 4 + B * e2e_rows * 7 * 4) * inner   # counts + the [B, max kept, 7] rows of the last step
     plan.run_head(True)   # decoded probabilities (the timed steps leave raw class logits in plan.pred)
     cand = [int(v) for v in ((plan.pred[:, :, 4] * plan.pred[:, :, 5:].max(2)[0]) >= CONF_THRES).sum(1).cpu()]
 
     if rank == 0:
         pk = peaks()
-        algo_gflop = ALGO_GFLOP_PER_IMAGE if VARIANT == "p0" else (plan.flops + getattr(plan, "attn_flops", 0.0)) / B / 1e9
+        algo_gflop = (ALGO_GFLOP_PER_IMAGE if (VARIANT == "p0" and PHI == "s" and (IN_H, IN_W) == (1024, 1024)) else
+                      (plan.flops + getattr(plan, "attn_flops", 0.0)) / B / 1e9)
         achieved_tf = algo_gflop * B / conv_ms  # GFLOP / ms = TFLOP/s
         # denominator: the burst figure unless the timed region is long enough (>= 2 s) for the sustained one to apply
         long_region = elapsed_ms >= 2000.0
         tf_peak = pk["tf_sustained"] if long_region else pk["tf_burst"]
-        line = {"metric": "images/sec at 1024^2 (neck+head+NMS)", "value": value, "unit": "images/s", "n_gpus": world,
+        model_name = {"p0": f"GLSDet YOLOX-{PHI} (yolox_ffa YoloBody({NUM_CLASSES},'{PHI}')) neck+FFA+head+decode+filter+NMS",
+                      "p1": f"GLSDet P1 YOLOX-{PHI} (yolox10 YoloBody({NUM_CLASSES},'{PHI}')) non-local neck+head+decode+filter+NMS",
+                      "p2": f"GLSDet P2 YOLOX-{PHI} (yolo_patch_nonlocal_plus) patch-conv neck+head+decode+filter+NMS"}[VARIANT]
+        cfg_name = {"cfg2": "BASELINE configs[1]", "cfg4": "BASELINE configs[3]", "cfg5": "BASELINE configs[4]"}.get(args.config, args.config)
+        if args.total_batch > 0:
+            batch_txt = (f"{args.total_batch} synthetic {IN_H}x{IN_W} images per step in total, {args.total_batch // world} per GPU "
+                         f"as {inner} micro-batches of {B} (strong scaling)")
+        else:
+            batch_txt = f"batch {B} of synthetic {IN_H}x{IN_W} images per GPU (weak scaling)"
+        feat_mb = sum(t.numel() * 4 for t in host_feats) / 1e6
+        e2e_how = ("wall clock; YoloBody.detect_uint8(pinned host uint8 HWC frames, what YOLO.detect_image's resize_image "
+                   "delivers, yolo.py:130) -> host detections; preprocess_input + transpose (yolo.py:134) fused into the "
+                   "Focus kernel; the native CSPDarknet backbone (+27.9 GFLOP/image at s-1024^2, outside the metric and outside "
+                   "the reference arm) runs in front of the path; upload of step i+1 overlaps compute of step i (2 input "
+                   "sets, copy stream); frames = the synthetic images clipped and quantised to 8 bits (its own NMS load: "
+                   "kept_per_image)") if u8_ms is not None else (
+                   "wall clock; native backbone on pinned host fp32 images -> path -> host detections")
+        line = {"metric": f"images/sec at {IN_H}x{IN_W} (neck+head+NMS)" if (IN_H, IN_W) != (1024, 1024) else "images/sec at 1024^2 (neck+head+NMS)",
+                "value": value, "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": ("GLSDet YOLOX-s (yolox_ffa YoloBody(10,'s')) neck+FFA+head+decode+filter+NMS, "
-                                        f"batch {B} of synthetic 1024x1024 images per GPU (BASELINE configs[1])") if VARIANT == "p0" else
-                                       ("GLSDet P1 YOLOX-s (yolox10 YoloBody(10,'s')) non-local neck+head+decode+filter+NMS, "
-                                        f"batch {B} of synthetic 1024x1024 images per GPU (SURVEY 8d row 2')"),
-                           "images_per_gpu": B, "num_classes": NUM_CLASSES, "conf_thres": CONF_THRES,
+                "higher_is_better": True, "scaling": "strong" if args.total_batch > 0 else "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{model_name}, {batch_txt} ({cfg_name})",
+                           "images_per_gpu": B * inner, "micro_batch": B, "num_classes": NUM_CLASSES, "conf_thres": CONF_THRES,
                            "nms_thres": NMS_THRES, "nms_strategy": "torchvision auto dispatch for CUDA tensors",
-                           "l2": "inputs (503 MB fp32 feature maps per batch) exceed the 126 MB L2; no explicit flush",
-                           "candidates_per_image": cand, "kept_per_image": kept,
+                           "l2": f"inputs ({feat_mb:.0f} MB fp32 feature maps per micro-batch) exceed the 126 MB L2; no explicit flush",
+                           "candidates_per_image": cand, "kept_per_image": kept_value,
                            "max_det": max_det if max_det is not None else "none (every NMS survivor, utils_bbox.py:414-420)",
                            "postprocess_ms": post_ms,
-                           "parallelism": f"dp{world} (images sharded, NCCL gather of detections)" if world > 1 else "single GPU"},
+                           "storage": "16-bit activations (bf16 at stride 4, fp16 at strides 8-32), fp32 accumulation",
+                           "parallelism": (f"dp{world} (images sharded; one asynchronous NCCL all_gather of the detections per "
+                                           "step, overlapped with the next step)") if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
-                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps,
-                        "how": "wall clock; YoloBody.detect(pinned host image batch fp32) -> host detections; the native "
-                               "CSPDarknet backbone (+27.9 GFLOP/image, outside the metric and outside the reference arm) "
-                               "runs in front of the path; upload of step i+1 overlaps compute of step i (2 input sets, copy stream)",
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "how": e2e_how,
+                        "kept_per_image": kept,
+                        "from_fp32_images": {"value": img32_value, "unit": "images/s", "h2d_bytes_per_step": h2d_img32_bytes,
+                                             "ms_per_step": img32_ms / args.steps, "kept_per_image": kept_img32,
+                                             "how": "same, but YoloBody.detect(pinned host fp32 NCHW image batch) - the tensor "
+                                                    "yolo.py:134-139 uploads after preprocessing on the host"},
                         "from_features": {"value": feat_value, "unit": "images/s", "h2d_bytes_per_step": h2d_feat_bytes,
                                           "ms_per_step": feat_ms / args.steps,
                                           "how": "same, but YoloBody.detect_features(pinned host dark2..dark5 fp32 NCHW): "
-                                                 "exactly the metric's segment, PCIe-bound on 503 MB per step"}},
-                "e2e_uint8": None if u8_ms is None else {
-                    "value": world * B * args.steps / (u8_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * IN_H * IN_W * 3,
-                    "ms_per_step": u8_ms / args.steps,
-                    "how": "YoloBody.detect_uint8(pinned host uint8 HWC frames): preprocess_input (utils.py:47-51) fused into "
-                           "the Focus kernel; the same synthetic images clipped and quantised to 8 bits (a different "
-                           "NMS load: see kept_per_image)", "kept_per_image": kept_u8},
+                                                 "exactly the metric's segment, PCIe-bound on the feature upload"}},
                 "with_backbone": {"value": world * B / (img_ms * 1e-3), "unit": "images/s", "ms_per_step": img_ms,
-                                  "what": "device-resident image batch -> backbone -> neck -> head -> NMS (CUDA events)"},
+                                  "what": "device-resident fp32 image micro-batch -> backbone -> neck -> head -> NMS (CUDA events)"},
                 "gpu_launches": int(launches),
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf_peak, "unit": "TFLOP/s",
@@ -506,10 +566,153 @@ def run_native_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------ configs[2]: MP-Det
+def run_mpdet_arm(args):
+    """BASELINE configs[2]: MP-Det FPN + MPHead + GFL post-processing on the UFP mosaic shape (800 x 1344 -> C2..C5 of a
+    ResNet-50; SURVEY.md section 8d row 3, config reconstructed there).  Same JSON contract; single GPU (the mosaics are
+    independent units, N ranks would run N replicas)."""
+    import torch
+
+    import glsdet_b200.mpdet  # noqa: F401
+    from glsdet_b200 import _native as N
+    from glsdet_b200.mmdet_face import HEADS, NECKS
+    from oracle import mmdet_ref as M   # synthetic weights of the reconstructed config + the CPU port (baseline leg only)
+
+    H, W = 800, 1344
+    batch = 8 if args.batch == 16 else args.batch
+    test_cfg = dict(nms_pre=1000, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.6), max_per_img=500)
+    sd = M.mpdet_synthetic_state_dict(0)
+    nsd = {k[5:]: v for k, v in sd.items() if k.startswith("neck.")}
+    hsd = {k[10:]: v for k, v in sd.items() if k.startswith("bbox_head.")}
+    g = torch.Generator().manual_seed(0)
+    host_in = [torch.randn(batch, c, H // s, W // s, generator=g) for c, s in zip((256, 512, 1024, 2048), (4, 8, 16, 32))]
+    metas = [dict(img_shape=(H, W - 11, 3), scale_factor=1.0)] * batch
+
+    def cpu_run(n_img, threads):
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        kept = []
+        with torch.no_grad():
+            for i in range(n_img):
+                cpu = [t[i:i + 1] for t in host_in]
+                outs = M.fpn_forward(nsd, cpu)
+                cs, bp = M.mp_head_forward(hsd, outs)
+                d, _ = M.gfl_get_bboxes_single([c[0] for c in cs], [b[0] for b in bp], (H, W - 11))
+                kept.append(len(d))
+        return time.perf_counter() - t0, kept
+
+    metric = "images/sec at 800x1344 (MP-Det FPN+MPHead+GFL post-processing)"
+    workload = (f"MP-Det ResNet-50 neck/head: FPN(256..2048 -> 256, 5 levels) + MPHead(10 classes, 4 GN towers, 42 proxies) + "
+                f"select/NMS/max_per_img 500, batch {batch} of synthetic 800x1344 mosaics' backbone maps (BASELINE configs[2])")
+    threads = os.cpu_count() or 1
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        times = []
+        for s_ in range(args.warmup + args.steps):
+            dt, kept = cpu_run(1, threads)
+            if s_ >= args.warmup:
+                times.append(dt)
+        v = len(times) / sum(times)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": workload + ", one image per step on the host CPU", "kept_per_image": kept},
+                          "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                           "sample": "one image per step, fp32, torch CPU; PARITY UNPINNED port (mmcv absent)"},
+                          "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (product arm) needs a CUDA device: there is no CPU path")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    lib = N.load()
+    neck = NECKS.build(dict(type="FPN", in_channels=[256, 512, 1024, 2048], out_channels=256, start_level=1,
+                            add_extra_convs="on_output", num_outs=5))
+    head = HEADS.build(dict(type="MPHead", num_classes=10, in_channels=256, stacked_convs=4, feat_channels=256, test_cfg=test_cfg))
+    neck.load_state_dict(nsd, strict=True)
+    head.load_state_dict(hsd, strict=True)
+    neck, head = neck.to(dev).eval(), head.to(dev).eval()
+    ins = [t.to(dev) for t in host_in]
+    pinned = [t.pin_memory() for t in host_in]
+
+    def step(inputs):
+        return head.detect(neck(inputs), metas)
+
+    for _ in range(max(3, args.warmup)):
+        res = step(ins)
+    torch.cuda.synchronize()
+    clock = ClockSampler(dev.index or 0)
+    clock.start()
+    n0 = lib.glsdet_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res = step(ins)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.glsdet_launch_count() - n0
+    ms = e0.elapsed_time(e1) / args.steps
+    # end to end: pinned host maps -> device -> detections on the host
+    dev_in = [torch.empty_like(t, device=dev) for t in host_in]
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        for d, h in zip(dev_in, pinned):
+            d.copy_(h, non_blocking=True)
+        out = step(dev_in)
+        host_out = [(d.cpu(), l.cpu()) for d, l in out]
+        d2h = sum(d.numel() * 4 + l.numel() * 8 for d, l in host_out)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = clock.stop()
+    pk = peaks()
+    flops = sum(op.flops for op in neck._plan(ins).ops if hasattr(op, "flops"))
+    hp = head._plan(neck(ins))
+    flops += sum(op.flops for lv in hp.levels for kind, op in lv["ops"] if kind == "conv")
+    gf_img = flops / batch / 1e9
+    achieved = gf_img * batch / ms
+    line = {"metric": metric, "value": batch / ms * 1e3, "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload, "images_per_gpu": batch, "kept_per_image": [len(r[0]) for r in res],
+                       "l2": f"inputs ({sum(t.numel() * 4 for t in host_in) / 1e6:.0f} MB fp32 maps per batch) exceed the 126 MB L2; no explicit flush",
+                       "parity": "oracle restated from the vendored mmdet sources, PARITY UNPINNED (mmcv absent)"},
+            "e2e": {"value": batch / e2e_ms * 1e3, "unit": "images/s", "h2d_bytes_per_step": sum(t.numel() * 4 for t in host_in),
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                    "how": "wall clock; pinned host C2..C5 maps -> FPN.forward -> MPHead.detect -> (dets, labels) on the host"},
+            "gpu_launches": int(launches), "launches_per_step": int(launches) // args.steps, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                         "traffic": None, "kernel": "conv_gemm_kernel (FPN + tower + prediction convs; the step also runs GroupNorm, proxy scores, decode, select, NMS)",
+                         "algorithmic_gflop_per_image": gf_img, "segment_ms": ms, "peak_source": pk["source"] + ", burst figure"}}
+    if not args.no_cpu_baseline:
+        dt, kept = cpu_run(1, threads)   # warm-up
+        total, n_img = 0.0, 0
+        while total < args.cpu_seconds and n_img < 64:
+            dt, kept = cpu_run(1, threads)
+            total += dt
+            n_img += 1
+        line["cpu_baseline"] = {"value": n_img / total, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"{n_img} passes over one image, fp32, torch CPU {threads} threads, {total:.1f} s; PARITY UNPINNED port",
+                                "kept_per_image": kept}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
-    global VARIANT
+    global VARIANT, PHI, NUM_CLASSES, IN_H, IN_W, WEIGHT_SEED
     args = parse_args()
     VARIANT = args.variant
+    if args.config == "cfg3":
+        return run_mpdet_arm(args)
+    if args.config == "cfg5" and args.total_batch == 0:
+        args.total_batch = 256
+    if args.config == "cfg4":   # BASELINE configs[3]: YOLOX-l, UAVDT-shaped 1024x540 -> 544x1024 (SURVEY D8), nc=3, batch 64, top 1000
+        PHI, NUM_CLASSES, IN_H, IN_W, WEIGHT_SEED = "l", 3, 544, 1024, 6
+        if args.batch == 16:
+            args.batch = 64
+        if args.max_det == 0:
+            args.max_det = 1000
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_native_arm(args)
