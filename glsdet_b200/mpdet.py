@@ -202,10 +202,36 @@ class MPHead(_Native):
         return plan.cls_maps(), plan.bbox_maps()
 
     @torch.no_grad()
-    def detect(self, feats: Sequence[torch.Tensor], img_metas, cfg=None):
+    def detect(self, feats: Sequence[torch.Tensor], img_metas, cfg=None, rescale=False):
         """forward + get_bboxes without materialising the NCHW maps: [(dets [n, 5], labels [n])] per image."""
         plan = self._plan(feats)
-        return plan.get_bboxes(feats, img_metas, self.test_cfg if cfg is None else dict(cfg))
+        return plan.get_bboxes(feats, img_metas, self.test_cfg if cfg is None else dict(cfg), rescale=rescale)
+
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, bbox_preds, score_factors=None, img_metas=None, cfg=None, rescale=False, with_nms=True, **kwargs):
+        """base_dense_head.py:62-150 get_bboxes(cls_scores, bbox_preds, img_metas=..., cfg=..., rescale=..., with_nms=True)
+        on maps returned by forward(): [(dets [n, 5], labels [n])] per image."""
+        if not with_nms or score_factors is not None:
+            raise NotImplementedError("MPHead.get_bboxes: with_nms=True and no score factors (GFL has none)")
+        shapes = tuple((cls_scores[0].shape[0], self.in_channels) + tuple(c.shape[2:]) for c in cls_scores) + (str(cls_scores[0].device),)
+        plan = self._plans.get(shapes)
+        if plan is None:
+            raise RuntimeError("MPHead.get_bboxes: call forward() on the same feature shapes first (the plan owns the buffers)")
+        return plan.get_bboxes(None, img_metas, self.test_cfg if cfg is None else dict(cfg), rescale=rescale, maps=(cls_scores, bbox_preds))
+
+    @torch.no_grad()
+    def simple_test(self, feats, img_metas, rescale=False):
+        """dense_test_mixins.py simple_test_bboxes: forward + get_bboxes; the fused path skips the NCHW maps."""
+        return self.detect(feats, img_metas, rescale=rescale)
+
+
+def _scale4(sf):
+    """img_meta['scale_factor'] -> (w, h, w, h) divisors (mmdet stores a 4-vector or a scalar)."""
+    try:
+        v = [float(x) for x in sf]
+    except TypeError:
+        v = [float(sf)] * 4
+    return v if len(v) == 4 else [v[0], v[1 % len(v)], v[0], v[1 % len(v)]]
 
 
 class _MPHeadPlan:
@@ -287,6 +313,17 @@ class _MPHeadPlan:
                                               float(img_shape[1]), float(img_shape[0]), self.boxes.data_ptr(), self.A * 4,
                                               self.row0[l], st), "glsdet_gfl_decode")
 
+    def load_maps(self, cls_scores, bbox_preds, img_shape):
+        """Given per-level NCHW maps (what MPHead.forward returned) -> the plan's score rows and decoded boxes."""
+        m, lib, st = self.m, self.lib, N.stream_ptr(None)
+        nc, bins = m.num_classes, m.reg_max + 1
+        for l, (lv, (h, w)) in enumerate(zip(self.levels, self.hw)):
+            self.rows[:, self.row0[l]:self.row0[l] + h * w] = cls_scores[l].float().permute(0, 2, 3, 1).reshape(self.B, h * w, nc)
+            lv["reg32"][..., :4 * bins] = bbox_preds[l].float().permute(0, 2, 3, 1)
+            N.check(lib.glsdet_gfl_decode(lv["reg32"].data_ptr(), self.reg_ld, bins, self.B, h, w, float(m.strides[l]),
+                                          float(img_shape[1]), float(img_shape[0]), self.boxes.data_ptr(), self.A * 4,
+                                          self.row0[l], st), "glsdet_gfl_decode")
+
     def cls_maps(self):
         nc = self.m.num_classes
         return [self.rows[:, r0:r0 + h * w].reshape(self.B, h, w, nc).permute(0, 3, 1, 2).contiguous()
@@ -296,16 +333,23 @@ class _MPHeadPlan:
         n = 4 * (self.m.reg_max + 1)
         return [lv["reg32"][..., :n].permute(0, 3, 1, 2).contiguous() for lv in self.levels]
 
-    def get_bboxes(self, feats, img_metas, cfg):
+    def get_bboxes(self, feats, img_metas, cfg, rescale=False, maps=None):
         """_get_bboxes_single + _bbox_post_process (gfl_head.py:426-471, base_dense_head.py:276-301); every image of the
-        batch must share img_shape (the clamp bounds are launch parameters)."""
+        batch must share img_shape (the clamp bounds are launch parameters).  `maps=(cls_scores, bbox_preds)` post-processes
+        given NCHW maps (the reference's get_bboxes signature) instead of running the head on `feats`."""
         m, lib, st = self.m, self.lib, N.stream_ptr(None)
         img_shape = tuple(img_metas[0]["img_shape"][:2])
         assert all(tuple(im["img_shape"][:2]) == img_shape for im in img_metas)
         score_thr, nms_pre = float(cfg.get("score_thr", 0.05)), int(cfg.get("nms_pre", 1000))
         iou = float(dict(cfg["nms"]).get("iou_threshold", 0.6))
         max_per_img = int(cfg.get("max_per_img", 100))
-        self.run(feats, img_shape)
+        nms_max = dict(cfg["nms"]).get("max_num", -1)       # mmcv nms_cfg 'max_num': keep at most that many
+        if nms_max is not None and int(nms_max) > 0:
+            max_per_img = min(max_per_img, int(nms_max))
+        if maps is None:
+            self.run(feats, img_shape)
+        else:
+            self.load_maps(maps[0], maps[1], img_shape)
         nc = m.num_classes
         cap = nms_pre * len(self.levels)
         big = max(h * w for h, w in self.hw) * nc
@@ -325,17 +369,36 @@ class _MPHeadPlan:
                                           h * w, nc, score_thr, nms_pre, self.B, self.keys.data_ptr(), kstride,
                                           self.ccount.data_ptr(), self.cboxes.data_ptr(), self.cscores.data_ptr(),
                                           self.clabels.data_ptr(), cap, st), "glsdet_gfl_select")
-        counts = self.ccount.cpu().tolist()
-        results = []
+        # Post-processing without per-image host round trips: every image runs the mmcv-style batched NMS on its FULL
+        # candidate buffer (cap rows); rows beyond the image's candidate count are padding - zero boxes (IoU 0 with
+        # everything, they never suppress and never raise the coordinate-trick offset) with the lowest score, so they sort
+        # behind every real candidate.  One device->host read of the B counts at the end sizes the returned tensors
+        # (mmdet returns variable-length (dets, labels) per image, so that read is part of the interface).
+        pad = torch.arange(cap, device=self.dev)[None, :] >= self.ccount[:, None]
+        self.cboxes.masked_fill_(pad[:, :, None], 0.0)
+        self.cscores.masked_fill_(pad, -3.0e38)
+        self.clabels.masked_fill_(pad, 0.0)
+        if rescale:   # base_dense_head.py:282-283: mlvl_bboxes /= scale_factor, before the NMS
+            sf = torch.tensor([list(_scale4(im["scale_factor"])) for im in img_metas], dtype=torch.float32, device=self.dev)
+            self.cboxes.div_(sf[:, None, :])
+        from .utils_bbox import STRATEGIES, _batched_nms_workspace
+        nbytes, ws = _batched_nms_workspace(cap, self.dev)
+        if getattr(self, "keep", None) is None or self.keep.shape[1] != cap:
+            self.keep = torch.empty((self.B, cap), dtype=torch.int32, device=self.dev)
+            self.kcount = torch.zeros((self.B,), dtype=torch.int32, device=self.dev)
+        ids = self.clabels.to(torch.int32)
         for b in range(self.B):
-            n = min(counts[b], cap)
-            bx, sc, lb = self.cboxes[b, :n], self.cscores[b, :n], self.clabels[b, :n]
-            if n == 0:
-                results.append((torch.zeros((0, 5), device=self.dev), torch.zeros((0,), dtype=torch.long, device=self.dev)))
-                continue
-            keep = batched_nms(bx, sc, lb, iou, "mmcv")[:max_per_img]
-            results.append((torch.cat([bx[keep], sc[keep][:, None]], 1), lb[keep].long()))
-        return results
+            N.check(lib.glsdet_batched_nms_ids(self.cboxes[b].data_ptr(), self.cscores[b].data_ptr(), self.clabels[b].data_ptr(),
+                                               ids[b].data_ptr(), float(nc - 1), cap, iou, STRATEGIES["mmcv"], ws.data_ptr(), nbytes,
+                                               self.keep[b].data_ptr(), self.kcount[b:b + 1].data_ptr(), st), "glsdet_batched_nms_ids")
+        keep = self.keep.long()
+        real = (keep < self.ccount[:, None].long()) & (torch.arange(cap, device=self.dev)[None, :] < self.kcount[:, None])
+        n_real = real.sum(1).clamp(max=max_per_img)                     # kept real candidates lead the score order
+        top = keep[:, :max_per_img].clamp(0, cap - 1)
+        dets = torch.cat([torch.gather(self.cboxes, 1, top[:, :, None].expand(-1, -1, 4)), torch.gather(self.cscores, 1, top)[:, :, None]], 2)
+        labels = torch.gather(self.clabels, 1, top).long()
+        counts = n_real.cpu().tolist()
+        return [(dets[b, :counts[b]], labels[b, :counts[b]]) for b in range(self.B)]
 
 
 from .mmdet_face import HEADS, NECKS  # noqa: E402  (same minimal registries; mmdet's own when it is installed)

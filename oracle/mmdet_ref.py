@@ -8,9 +8,14 @@ mmcv 1.x pieces they call (mmcv-full>=1.3.17,<=1.5.0, requirements/mminstall.txt
   * mmcv.ops.nms.batched_nms = boxes + label * (max + 1); one nms when K < split_thr (10000) else one per class on the
                                shifted boxes; result sorted by score; returns (cat(boxes, scores)[keep], keep)
   * mmcv.ops.nms.nms         = greedy NMS, suppress iff IoU > thr, offset 0 (same arithmetic as torchvision's)
-PARITY UNPINNED for the mmcv pieces (no reference test pins them, the library is absent).  The conv/decode math is
-pinned indirectly: with weights renamed by the key map of SURVEY.md section 8c this path must reproduce the outputs of
-yolox-drone/models/base/yolox.py, whose real outputs are committed as tests/golden/stock_s_calibrated.npz.
+PARITY UNPINNED for the mmcv pieces only (no reference test pins them, the library is absent).  What IS pinned:
+  * MP-Det (fpn_forward, mp_forward_proxy, mp_head_forward, gfl_decode_level, gfl_get_bboxes_single): against
+    tests/golden/mpdet_cases.npz, recorded by tests/golden/make_golden_mpdet.py, which EXECUTES the reference's own source
+    of FPN.forward, MPHead.forward_single / forward_proxy, Integral, GFLHead._get_bboxes_single / anchor_center,
+    BaseDenseHead._bbox_post_process, filter_scores_and_topk, distance2bbox and DistancePointBBoxCoder.decode (compiled
+    from the files under /root/reference/yolox-ufp through `ast`, bound to attribute-only stand-in objects);
+  * YOLOX neck / head conv and decode math: with weights renamed by the key map of SURVEY.md section 8c this path must
+    reproduce the outputs of yolox-drone/models/base/yolox.py, whose real outputs are tests/golden/stock_s_calibrated.npz.
 """
 from __future__ import annotations
 
@@ -281,7 +286,7 @@ def gfl_decode_level(bbox_pred: torch.Tensor, stride: int, img_shape, reg_max: i
 
 
 def gfl_get_bboxes_single(cls_scores, bbox_preds, img_shape, score_thr=0.05, nms_pre=1000, iou_thr=0.6, max_per_img=500,
-                          strides=MP_STRIDES):
+                          strides=MP_STRIDES, scale_factor=None):
     """_get_bboxes_single (gfl_head.py:426-471) + filter_scores_and_topk (core/utils/misc.py:143-165) +
     _bbox_post_process (base_dense_head.py:276-301) for ONE image: per-level maps [nc, H, W] / [68, H, W].
     Ties in the per-level sort are broken by (anchor, class) order (torch.sort is not stable; documented choice)."""
@@ -296,6 +301,8 @@ def gfl_get_bboxes_single(cls_scores, bbox_preds, img_shape, score_thr=0.05, nms
         idx = idx[order]
         ms.append(flat[idx]); ml.append(idx % nc); mb.append(boxes[idx // nc])
     boxes, scores, labels = torch.cat(mb), torch.cat(ms), torch.cat(ml)
+    if scale_factor is not None:      # rescale=True: mlvl_bboxes /= mlvl_bboxes.new_tensor(scale_factor) (base_dense_head.py:282-283)
+        boxes = boxes / boxes.new_tensor(scale_factor)
     if boxes.numel() == 0:
         return torch.zeros((0, 5)), labels
     _, keep = mmcv_batched_nms(boxes.numpy(), scores.numpy(), labels.float().numpy(), iou_thr)

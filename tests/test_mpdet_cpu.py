@@ -43,3 +43,39 @@ def test_mpdet_oracle_shapes_and_proxy_scores():
     dets, labels = M.gfl_get_bboxes_single([c[0] for c in cls], [b[0] for b in box], (128, 190))
     assert dets.shape[1] == 5 and len(dets) == len(labels) <= 500
     assert (dets[:-1, 4] >= dets[1:, 4]).all() and float(dets[:, 2].max()) <= 190.0 and float(dets[:, 3].max()) <= 128.0
+
+
+def _golden_case(case):
+    import numpy as np
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / "mpdet_cases.npz")
+    H, W, seed = (int(v) for v in z[f"{case}_meta"])
+    g = torch.Generator().manual_seed(seed)
+    ins = [torch.randn(1, c, -(-H // s), -(-W // s), generator=g) for c, s in zip((256, 512, 1024, 2048), (4, 8, 16, 32))]
+    return z, H, W, ins
+
+
+def test_mpdet_oracle_pinned_to_reference_source_golden():
+    """oracle/mmdet_ref.py against outputs recorded by executing the reference's own FPN.forward / MPHead.forward_single /
+    forward_proxy / Integral / _get_bboxes_single / filter_scores_and_topk / distance2bbox / _bbox_post_process sources
+    (tests/golden/make_golden_mpdet.py).  Only the mmcv pieces (ConvModule, Scale, anchors, batched_nms) are restated."""
+    import numpy as np
+
+    sd = M.mpdet_synthetic_state_dict(0)
+    nsd = {k[5:]: v for k, v in sd.items() if k.startswith("neck.")}
+    hsd = {k[10:]: v for k, v in sd.items() if k.startswith("bbox_head.")}
+    for case in ("small", "odd"):
+        z, H, W, ins = _golden_case(case)
+        fs, bs = (int(v) for v in z[f"{case}_stride"])
+        with torch.no_grad():
+            outs = M.fpn_forward(nsd, ins)
+            cls, box = M.mp_head_forward(hsd, outs)
+            dets, labels = M.gfl_get_bboxes_single([c[0] for c in cls], [b[0] for b in box], (H, W - 11))
+        for l in range(5):
+            assert np.allclose(outs[l][:, ::fs].numpy(), z[f"{case}_fpn{l}"], rtol=1e-5, atol=1e-5), (case, "fpn", l)
+            assert np.allclose(cls[l].numpy(), z[f"{case}_cls{l}"], rtol=1e-4, atol=1e-4), (case, "cls", l)
+            assert np.allclose(box[l][:, ::bs].numpy(), z[f"{case}_box{l}"], rtol=1e-4, atol=1e-4), (case, "box", l)
+        assert dets.shape == z[f"{case}_dets"].shape, (case, dets.shape)
+        assert np.array_equal(labels.numpy(), z[f"{case}_labels"])
+        assert np.allclose(dets.numpy(), z[f"{case}_dets"], rtol=1e-5, atol=1e-4)

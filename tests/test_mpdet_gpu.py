@@ -132,3 +132,49 @@ def test_mpdet_get_bboxes_vs_oracle(native_lib, cuda_device):
         assert torch.equal(got_l, labels)
         assert torch.allclose(got_d[:, 4], dets[:, 4], rtol=0, atol=2e-6)
         assert torch.allclose(got_d[:, :4], dets[:, :4], rtol=0, atol=2e-3)
+
+
+def test_mpdet_vs_reference_source_golden(native_lib, cuda_device):
+    """FPN / MPHead maps against outputs recorded by executing the reference's own sources (tests/golden/make_golden_mpdet.py,
+    case 'small'): the neck from the inputs, the head from the golden-consistent oracle FPN maps."""
+    import numpy as np
+    from pathlib import Path
+
+    z = np.load(Path(__file__).parent / "golden" / "mpdet_cases.npz")
+    H, W, seed = (int(v) for v in z["small_meta"])
+    fs, bs = (int(v) for v in z["small_stride"])
+    g = torch.Generator().manual_seed(seed)
+    ins = [torch.randn(1, c, H // s, W // s, generator=g) for c, s in zip((256, 512, 1024, 2048), (4, 8, 16, 32))]
+    neck, head, nsd, hsd = _models(cuda_device)
+    outs = neck([t.to(cuda_device) for t in ins])
+    for l in range(5):
+        assert_close_rel(outs[l][:, ::fs], torch.from_numpy(z[f"small_fpn{l}"]), TOL, f"FPN out {l} vs golden")
+    with torch.no_grad():
+        ref_fpn = M.fpn_forward(nsd, ins)
+    cls, box = head([t.to(cuda_device) for t in ref_fpn])
+    for l in range(5):
+        assert_close_rel(cls[l], torch.from_numpy(z[f"small_cls{l}"]), 3e-2, f"cls {l} vs golden", frac=5e-2)
+        assert_close_rel(box[l][:, ::bs], torch.from_numpy(z[f"small_box{l}"]), 3e-2, f"box {l} vs golden", frac=5e-2)
+
+
+def test_mpdet_get_bboxes_api_rescale_and_max_num(native_lib, cuda_device):
+    """get_bboxes(cls_scores, bbox_preds, img_metas=..., rescale=...) on forward()'s maps == the fused detect(); rescale
+    divides the boxes by scale_factor before the NMS (base_dense_head.py:282-283); nms max_num caps the result."""
+    H, W = 192, 256
+    neck, head, nsd, hsd = _models(cuda_device, seed=3)
+    g = torch.Generator().manual_seed(5)
+    ins = [torch.randn(2, c, H // s, W // s, generator=g) for c, s in zip((256, 512, 1024, 2048), (4, 8, 16, 32))]
+    feats = neck([t.to(cuda_device) for t in ins])
+    metas = [dict(img_shape=(H, W, 3), scale_factor=[2.0, 2.0, 2.0, 2.0])] * 2
+    fused = head.simple_test(feats, metas, rescale=False)
+    cls, box = head(feats)
+    api = head.get_bboxes(cls, box, img_metas=metas, rescale=False)
+    for (d0, l0), (d1, l1) in zip(fused, api):
+        assert torch.equal(l0, l1) and torch.equal(d0, d1) and len(d0) > 5
+    scaled = head.get_bboxes(cls, box, img_metas=metas, rescale=True)
+    for b in range(2):
+        dets, labels = M.gfl_get_bboxes_single([c[b].cpu() for c in cls], [x[b].cpu() for x in box], (H, W), scale_factor=2.0)
+        assert scaled[b][0].shape == dets.shape and torch.equal(scaled[b][1].cpu(), labels)
+        assert torch.allclose(scaled[b][0].cpu(), dets, rtol=0, atol=2e-3)
+    capped = head.detect(feats, metas, cfg=dict(nms_pre=1000, score_thr=0.05, nms=dict(type="nms", iou_threshold=0.6, max_num=7), max_per_img=500))
+    assert all(len(d) == min(7, len(f[0])) and torch.equal(d, f[0][:7]) for (d, _), f in zip(capped, fused))
