@@ -336,7 +336,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   if (act == GLSDET_ACT_SILU) {
   } else if (act == kActSiluExact) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+    for (int j = 0; j < 16; ++j) v[j] = silu_newton(v[j]);
   } else if (act == GLSDET_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.0f);
@@ -1114,7 +1114,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
             }
             if (silu && p.act_epi == kActSiluExact) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+              for (int j = 0; j < 16; ++j) v[j] = silu_newton(v[j]);
             } else if (silu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], tanh_approx(v[j]), v[j]);

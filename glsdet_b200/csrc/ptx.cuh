@@ -320,6 +320,22 @@ __device__ __forceinline__ float from_16(uint16_t v, int f16) {
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// x * sigmoid(x) with ONE MUFU op (ex2) and the reciprocal of d = 1 + e^-x on the FMA pipe: bit-trick seed (12 % off) and
+// three Newton steps r <- r (2 - d r) (1.5 %, 2e-4, 6e-8).  The fp16-storage layers need the ~1e-6 form (tanh.approx's
+// 2^-11 is as large as the fp16 rounding); ex2 + rcp costs two of the 16 MUFU lanes/clk/SM per element and made their
+// epilogues XU-bound, this form moves the second one to the 128 FMA lanes.  d >= 1, the exponent is clamped so that d stays
+// finite (silu(-60) = -5e-25 rounds to -0 in any 16-bit type).
+__device__ __forceinline__ float silu_newton(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(x, -60.0f) * -1.4426950408889634f));
+  const float d = 1.0f + e;
+  float r = __uint_as_float(0x7EF311C7u - __float_as_uint(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return x * r;
+}
+
 // x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op (tanh.approx.f32, relative error <= 2^-11) and two FMA-pipe
 // ops per element.  The epilogue of these convs is paced by instruction issue and the MUFU pipe (4 lanes/clk/SMSP),
 // not by the MMAs, whenever K < 512; ex2 + rcp + 6 ALU ops per element made it 3x as expensive.  Error: |h| * 2^-11

@@ -86,3 +86,31 @@ def test_registry_and_state_dict_keys():
     assert set(back) == set(want)
     for k in want:
         assert torch.equal(back[k], want[k]), k
+
+
+def test_mmdet_oracle_pinned_to_reference_source_golden():
+    """oracle/mmdet_ref.py's YOLOX neck / head / get_bboxes against outputs recorded by executing the reference's own
+    YOLOXPAFPN.forward, CSPLayer.forward, DarknetBottleneck.forward, YOLOXHead.forward / get_bboxes / _bbox_decode /
+    _bboxes_nms and MlvlPointGenerator sources (tests/golden/make_golden_mmdet_yolox.py)."""
+    import torch
+
+    z = np.load(GOLD / "mmdet_yolox_cases.npz")
+    H, W, seed = (int(v) for v in z["meta"])
+    nsd, hsd = mmdet_ref.drone_to_mmdet_keys(_stock_sd())
+    in_ch = [nsd["reduce_layers.1.conv.weight"].shape[0], nsd["reduce_layers.0.conv.weight"].shape[0], nsd["reduce_layers.0.conv.weight"].shape[1]]
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(2, c, H // s, W // s, generator=g) for c, s in zip(in_ch, (8, 16, 32))]
+    outs = mmdet_ref.yolox_pafpn(nsd, feats)
+    cls, box, obj = mmdet_ref.yolox_head_forward(hsd, outs)
+    for l in range(3):
+        assert np.allclose(outs[l].numpy(), z[f"neck{l}"], rtol=1e-5, atol=1e-5)
+        assert np.allclose(cls[l].numpy(), z[f"cls{l}"], rtol=1e-4, atol=1e-5)
+        assert np.allclose(box[l].numpy(), z[f"box{l}"], rtol=1e-4, atol=1e-5)
+        assert np.allclose(obj[l].numpy(), z[f"obj{l}"], rtol=1e-4, atol=1e-5)
+    gold_maps = [[torch.from_numpy(z[f"{n}{l}"]) for l in range(3)] for n in ("cls", "box", "obj")]
+    sf = [[1.0, 1.0, 1.0, 1.0], [1.25, 1.5, 1.25, 1.5]]
+    for tag, scale in (("plain", None), ("scaled", sf)):
+        res = mmdet_ref.get_bboxes(*gold_maps, (8, 16, 32), 0.01, 0.65, scale_factors=scale)
+        for i, (d, l) in enumerate(res):
+            assert np.array_equal(np.asarray(l), z[f"{tag}_labels{i}"]), (tag, i)
+            assert np.allclose(np.asarray(d), z[f"{tag}_dets{i}"], rtol=1e-6, atol=1e-5), (tag, i)

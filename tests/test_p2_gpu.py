@@ -130,3 +130,22 @@ def test_p2_model_vs_oracle_1024(native_lib, cuda_device):
     det, cnt = net.detect_features(dfeats, conf_thres=0.02, nms_thres=0.65)
     torch.cuda.synchronize()
     assert (cnt.cpu() >= 0).all() and det.shape[0] == 2
+
+
+@pytest.mark.parametrize("size", [(96, 160), (544, 1024)])
+def test_p2_odd_patch_sizes(size, native_lib, cuda_device):
+    """Every legal input (a multiple of 32, yolo.py:34-36) splits into EQUAL 2 x 2 patches at dark3 / dark4
+    (dark3 = 4m rows -> halves 2m -> stride-2 conv -> m; dark4 = 2m rows -> halves m), but for odd m the patches, the
+    left/right/top/bottom halves and the stride-2 outputs have odd sizes: 96 x 160 (m = 3, 5) and config 4's 544 x 1024
+    (m = 17: 17 x 32 patches).  Checked against the oracle (which follows Identity_Conv.py:292-384 slice by slice)."""
+    from glsdet_b200.synthetic import synthetic_images
+
+    in_h, in_w = size
+    sd = ref_path.synthetic_state_dict(10, "s", seed=0, flavour="calibrated", variant="p2")
+    net = _net(sd, cuda_device)
+    feats = ref_path.csp_darknet(sd, synthetic_images(1, in_h, in_w, seed=31))[1:]
+    assert feats[1].shape[2] // 2 % 2 == 1                     # odd patch height at dark4
+    ref = ref_path.p2_neck_head(sd, feats)
+    out = net.forward_features([f.to(cuda_device) for f in feats])
+    for i in range(3):
+        assert_close_rel(out[i], ref[i], TOL, f"p2 {in_h}x{in_w} logits{i}", frac=5e-2)

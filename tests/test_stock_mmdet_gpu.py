@@ -123,3 +123,36 @@ def test_mmcv_strategy_large_k(native_lib, cuda_device):
         got = batched_nms(*(torch.from_numpy(a).to(cuda_device) for a in (boxes, scores, labels)), 0.6, "mmcv").cpu().numpy()
         _, keep = mmdet_ref.mmcv_batched_nms(boxes, scores, labels.astype(np.int64), 0.6)
         np.testing.assert_array_equal(got, keep)
+
+
+def test_mmdet_face_vs_reference_source_golden(native_lib, cuda_device):
+    """The registry classes against outputs recorded by executing the reference's own YOLOXPAFPN / CSPLayer / YOLOXHead
+    sources (tests/golden/make_golden_mmdet_yolox.py): neck and head maps within the 16-bit tolerance, get_bboxes fed the
+    golden maps equal to the golden detections (labels and order identical), with and without rescale."""
+    from glsdet_b200.mmdet_face import HEADS, NECKS
+
+    z = np.load(GOLD / "mmdet_yolox_cases.npz")
+    H, W, seed = (int(v) for v in z["meta"])
+    nsd, hsd = mmdet_ref.drone_to_mmdet_keys(_stock_sd())
+    test_cfg = dict(score_thr=0.01, nms=dict(type="nms", iou_threshold=0.65))
+    neck = NECKS.build(dict(type="YOLOXPAFPN", in_channels=[128, 256, 512], out_channels=128, num_csp_blocks=1))
+    head = HEADS.build(dict(type="YOLOXHead", num_classes=META["nc"], in_channels=128, feat_channels=128, test_cfg=test_cfg))
+    neck.load_state_dict(nsd, strict=True)
+    head.load_state_dict(hsd, strict=True)
+    neck, head = neck.to(cuda_device).eval(), head.to(cuda_device).eval()
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(2, c, H // s, W // s, generator=g) for c, s in zip((128, 256, 512), (8, 16, 32))]
+    got_p = neck(tuple(f.to(cuda_device) for f in feats))
+    for l in range(3):
+        assert_close_rel(got_p[l], torch.from_numpy(z[f"neck{l}"]), 2.5e-2, f"neck out{l} vs golden")
+    cls, box, obj = head([torch.from_numpy(z[f"neck{l}"]).to(cuda_device) for l in range(3)])
+    for l in range(3):
+        assert_close_rel(torch.cat([box[l], obj[l], cls[l]], 1),
+                         torch.from_numpy(np.concatenate([z[f"box{l}"], z[f"obj{l}"], z[f"cls{l}"]], 1)), TOL, f"head level {l} vs golden")
+    maps = [[torch.from_numpy(z[f"{n}{l}"]).to(cuda_device) for l in range(3)] for n in ("cls", "box", "obj")]
+    sf = [[1.0, 1.0, 1.0, 1.0], [1.25, 1.5, 1.25, 1.5]]
+    metas = [dict(scale_factor=np.array(s, np.float32)) for s in sf]
+    for tag, rescale in (("plain", False), ("scaled", True)):
+        got = head.get_bboxes(*maps, img_metas=metas, rescale=rescale)
+        for i in range(2):
+            _match_dets(got[i], (z[f"{tag}_dets{i}"], z[f"{tag}_labels{i}"]))
