@@ -63,6 +63,9 @@ def parse_args():
                     help="BASELINE.json configs: cfg2 (index 1, the judged metric, default) = P0 YOLOX-s, 16 x 1024^2 per GPU; "
                          "cfg3 (index 2) = MP-Det FPN + MPHead at 800x1344; cfg4 (index 3) = P0 YOLOX-l, 64 x 544x1024, "
                          "top-1000 detections; cfg5 (index 4) = cfg2 with --total-batch 256")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay neck -> head -> filter -> NMS as one CUDA graph per step (engine.GraphedPath) in the "
+                         "device-resident loop; the roofline segment is then not bracketed separately")
     ap.add_argument("--variant", default="p0", choices=["p0", "p1", "p2"],
                     help="p0 = BASELINE configs[1] (models/ffa/yolox_ffa.py, the default and the judged metric); "
                          "p1 = models/new/yolox10.py (patch non-local attention neck, SURVEY.md section 8d row 2')")
@@ -345,18 +348,34 @@ def run_native_arm(args):
     seg = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(n_micro)]
     clock.start()
     ev[0].record(stream)
+    graphed = None
+    if args.graph:
+        from glsdet_b200.engine import GraphedPath
+        graphed = GraphedPath(plan, nms, CONF_THRES, NMS_THRES, "auto_cuda")
+        graph_kernels = 0
+        n_before = lib.glsdet_launch_count()
+        graphed._body()
+        graph_kernels = lib.glsdet_launch_count() - n_before
+        torch.cuda.synchronize()
+        launches0 = lib.glsdet_launch_count()
     for s in range(n_micro):
         plan.load_features(feats)
         seg[s][0].record(stream)
-        plan.run_neck()
-        plan.run_head("det")
-        seg[s][1].record(stream)
-        det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
+        if graphed is not None:
+            det, cnt = graphed.replay()
+            seg[s][1].record(stream)
+        else:
+            plan.run_neck()
+            plan.run_head("det")
+            seg[s][1].record(stream)
+            det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
         seg[s][2].record(stream)
         gather_step(det, cnt, last=(s == n_micro - 1))
     ev[1].record(stream)
     sync_all()
     launches = lib.glsdet_launch_count() - launches0
+    if graphed is not None:
+        launches += graph_kernels * n_micro      # kernels inside the replayed graphs (counted once, eagerly, above)
     kept_value = [int(v) for v in cnt.cpu()]     # survivors per image of the last timed (micro-)step
     elapsed_ms = ev[0].elapsed_time(ev[1])
     conv_ms = sum(a.elapsed_time(b) for a, b, _ in seg) / n_micro      # per micro-batch of B images
@@ -520,6 +539,7 @@ def run_native_arm(args):
                            "candidates_per_image": cand, "kept_per_image": kept_value,
                            "max_det": max_det if max_det is not None else "none (every NMS survivor, utils_bbox.py:414-420)",
                            "postprocess_ms": post_ms,
+                           "cuda_graph": bool(args.graph),
                            "storage": "16-bit activations (bf16 at stride 4, fp16 at strides 8-32), fp32 accumulation",
                            "parallelism": (f"dp{world} (images sharded; one asynchronous NCCL all_gather of the detections per "
                                            "step, overlapped with the next step)") if world > 1 else "single GPU"},

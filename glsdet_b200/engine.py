@@ -740,3 +740,45 @@ class FFAPathPlan:
 
     def buffer(self, name: str) -> torch.Tensor:
         return self._bufs[name]
+
+
+class GraphedPath:
+    """CUDA-graph capture of the device-resident part of a detect step for one plan (fixed weights, batch, input size):
+    neck -> head (fused decode) -> score filter -> NMS, ~65 launches replayed as ONE graph launch (SURVEY.md section 7
+    step 9).  The programmatic-dependent-launch attribute of every kernel becomes a programmatic edge of the graph.
+    Inputs are the plan's own NHWC buffers (filled by plan.load_features or the chained backbone before `replay`), outputs
+    the fixed (det, count, keep_index) tensors of this object - a replay overwrites them, so a caller that keeps results
+    across steps copies them (or alternates two GraphedPath objects)."""
+
+    def __init__(self, plan: "FFAPathPlan", nms, conf_thres: float, nms_thres: float, strategy: str = "auto_cuda"):
+        self.plan, self.nms = plan, nms
+        dev = plan.device
+        self.det = torch.empty((nms.batch, nms.max_det, 7), dtype=torch.float32, device=dev)
+        self.count = torch.empty((nms.batch,), dtype=torch.int32, device=dev)
+        self.keep_index = torch.empty((nms.batch, nms.max_det), dtype=torch.int32, device=dev)
+        self.args = (float(conf_thres), float(nms_thres), strategy)
+        self.graph = None
+        self._capture()
+
+    def _body(self):
+        self.plan.run_neck()
+        self.plan.run_head("det")
+        self.nms.launch(self.plan.pred, self.args[0], self.args[1], self.args[2], cls_logits=self.plan.det_cls_logits,
+                        out=(self.det, self.count, self.keep_index))
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.plan.device)
+        side.wait_stream(torch.cuda.current_stream(self.plan.device))
+        with torch.cuda.stream(side):
+            self._body()            # warm-up on the capture stream: lazy one-time initialisation must not be captured
+            self._body()
+        torch.cuda.current_stream(self.plan.device).wait_stream(side)
+        torch.cuda.synchronize(self.plan.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            self._body()
+        self.graph = g
+
+    def replay(self):
+        self.graph.replay()
+        return self.det, self.count

@@ -402,10 +402,22 @@ class YoloBody(_PlanOwner):
 
     @torch.no_grad()
     def detect_features(self, feats: Sequence[torch.Tensor], conf_thres: float = 0.5, nms_thres: float = 0.4,
-                        strategy: str = "auto_cuda", max_det: Optional[int] = None):
+                        strategy: str = "auto_cuda", max_det: Optional[int] = None, graph: bool = False):
         """Whole hot path on the device.  Returns (det [B, max_det, 7], count [B]) device tensors; rows are
-        (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score."""
+        (x1, y1, x2, y2 normalised network coordinates, obj_conf, class_conf, class_pred), sorted by score.
+        `graph=True` replays a CUDA graph of neck -> head -> filter -> NMS captured once per plan (engine.GraphedPath); the
+        returned tensors are then the graph's fixed outputs, overwritten by the next call."""
         plan = self.plan_for(feats)
+        if graph:
+            key = (max_det, float(conf_thres), float(nms_thres), strategy)
+            graphs = plan.__dict__.setdefault("_graphs", {})     # the captured graphs live and die with their plan
+            gp = graphs.get(key)
+            if gp is None:
+                from .engine import GraphedPath
+                graphs.clear()
+                gp = graphs[key] = GraphedPath(plan, self.nms_for(plan, max_det), conf_thres, nms_thres, strategy)
+            plan.load_features(feats)
+            return gp.replay()
         pred = plan.forward_detect(feats)
         return self.nms_for(plan, max_det).launch(pred, conf_thres, nms_thres, strategy, cls_logits=plan.det_cls_logits)
 

@@ -118,3 +118,30 @@ def test_device_nms_results_do_not_alias_across_launches(native_lib, cuda_device
     det3, cnt3 = op.launch(pred.to(cuda_device), 0.2, 0.5, out=out)
     torch.cuda.synchronize()
     assert det3.data_ptr() == out[0].data_ptr() and torch.equal(cnt3, c1)
+
+
+def test_cuda_graph_replay_equals_eager(native_lib, cuda_device):
+    """neck -> head -> filter -> NMS captured once per plan as a CUDA graph (with the
+    programmatic-dependent-launch edges) must return exactly the eager results, also for new inputs and after re-capture."""
+    from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
+    from glsdet_b200.yolox_ffa import YoloBody
+
+    sd = synthetic_state_dict(10, "s", seed=3, flavour="calibrated")
+    net = YoloBody(10, "s")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    lib_count = native_lib.glsdet_launch_count
+    for seed in (1, 2):
+        x = synthetic_images(2, 256, 320, seed=seed).to(cuda_device)
+        feats = [f.float().contiguous() for f in net.backbone.features(x)]
+        det, cnt = net.detect_features(feats, conf_thres=0.02, nms_thres=0.65)
+        det, cnt = det.clone(), cnt.clone()
+        n0 = lib_count()
+        gdet, gcnt = net.detect_features(feats, conf_thres=0.02, nms_thres=0.65, graph=True)
+        torch.cuda.synchronize()
+        launched = lib_count() - n0
+        assert torch.equal(gcnt, cnt) and int(cnt.sum()) > 0
+        for b in range(2):
+            assert torch.equal(gdet[b, :int(cnt[b])], det[b, :int(cnt[b])])
+        if seed == 2:   # the second call replays: only the four layout converters are launched from the host
+            assert launched == 4, launched
