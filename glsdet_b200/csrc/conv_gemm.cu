@@ -1316,6 +1316,21 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
   g->n_blocks = (d->out_channels + 255) / 256;
   int per = (d->out_channels + g->n_blocks - 1) / g->n_blocks;
   g->block_n = (per + 15) / 16 * 16;
+  {
+    // 1x1 convs with 256+ output channels and a 16-bit output: N blocks of 128 instead of 256.  Their epilogue, not their
+    // MMAs, paces them (one 128 x 256 tile: 2 us of MMAs at K = 512 against ~6 us in the 8-warp epilogue); 128-wide blocks
+    // run in the 16-warp TMA-store class with two epilogue groups (~1.4 us per 128 x 128 tile).  The A tile is loaded once
+    // per N block (consecutive work items share it through L2).  Opt-in (GLSDET_CONV_SPLIT_N=1), see below.
+    const char* e = getenv("GLSDET_CONV_SPLIT_N");
+    const bool on = (e && e[0] == '1');   // measured slower (2884 vs 2864 us per step): these layers are bound by operand streaming from L2, not by the epilogue
+    const int kpad = d->ksize * (d->ksize_w > 0 ? d->ksize_w : d->ksize) * (g->chunks0 + g->chunks1) * kChunkK;
+    if (on && d->ksize == 1 && d->stride == 1 && d->out_channels >= 256 && (d->out_channels % 128) == 0 &&
+        d->out_mode == GLSDET_OUT_NHWC_BF16 && d->pred_weight == nullptr && d->weight_batch_stride == 0 &&
+        d->patch_mode == 0 && kpad <= 640) {
+      g->n_blocks = d->out_channels / 128;
+      g->block_n = 128;
+    }
+  }
   g->n_pad = g->n_blocks * g->block_n;
   g->k_pad = g->taps * (g->chunks0 + g->chunks1) * kChunkK;
   g->Ho = d->height / d->stride;
@@ -1427,6 +1442,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   // for 3x3 stride-1 convs; the small-K 1x1 convs stay on the 1-CTA kernel (resident weights, TMA-store epilogue).
   // GLSDET_CONV_2CTA=0 disables it, =1 also uses it for 1x1 convs.
   bool two_cta = d->stride == 1 && d->ksize == 3 && g.kw == 3 && (g.block_n % 32) == 0;
+  // wide 1x1 convs (K >= 256, 256-wide N blocks) stream 384 KB of operands per tile from L2 and are bound by it: the pair
+  // kernel halves the weight traffic (512 -> 512 at 64^2 52 -> 42 us, 256 -> 256 at 128^2 62 -> 54 us).  The small-K / narrow
+  // 1x1 convs (resident weights, TMA-store epilogue) measured slower in pairs and stay on the 1-CTA kernel.
+  if (d->stride == 1 && d->ksize == 1 && g.kw == 1 && g.block_n == 256 && (g.chunks0 + g.chunks1) >= 4 &&
+      getenv("GLSDET_CONV_NO_2CTA_1X1") == nullptr)
+    two_cta = true;
   if (const char* e = getenv("GLSDET_CONV_2CTA")) {
     if (e[0] == '0') two_cta = false;
     if (e[0] == '1') two_cta = d->stride == 1 && d->ksize <= 3 && g.kw == d->ksize && (g.block_n % 32) == 0;
