@@ -4,7 +4,7 @@ Tolerances (BASELINE.json north_star: "feature maps and logits within ... 2e-2 r
 keep-indices bit-exact when fed identical scores"):
   * against the fp32 oracle (quantisation + kernel error): ||diff||_2 <= 2e-2 * ||ref||_2 for every neck map and every
     logit level - the plain bound, no allowance relative to any "inherent" error - with 99 % of the elements within
-    2e-2 * max|ref| and every element within 8e-2 * max|ref|.  Measured (profiles/r2_parity_rel_l2.txt): 0.03 - 0.25 %
+    2e-2 * max|ref| and every element within 8e-2 * max|ref|.  Measured (profiles/r2_parity_report.txt): 0.03 - 0.25 %
     with the default storage policy (bf16 for the stride-4 head level, fp16 for everything else);
   * against the storage-precision emulation of the oracle (oracle.ref_path.neck_head_bf16: fp32 math, weights and
     activations rounded to the storage type of their level; kernel error only): ||diff||_2 <= 1.5e-2 * ||ref||_2;

@@ -51,7 +51,20 @@ def main(path, ops_path=None, out=None):
     print(s)
     if out:
         open(out, "w").write(s + "\n")
+    return per
+
+
+def conv_traffic_json(per, out_json, batch=16):
+    """DRAM bytes (read + write) of the conv_gemm launches of the profiled step -> profiles/r2_conv_traffic.json."""
+    rd = sum(d.get("dram__bytes_read.sum", 0) for d in per.values() if "conv_gemm" in d["name"]) * 1e6
+    wr = sum(d.get("dram__bytes_write.sum", 0) for d in per.values() if "conv_gemm" in d["name"]) * 1e6
+    n = sum(1 for d in per.values() if "conv_gemm" in d["name"])
+    json.dump({"batch": batch, "conv_launches": n, "dram_read_bytes": rd, "dram_write_bytes": wr, "total_bytes_per_step": rd + wr,
+               "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over tools/profile_step.py p0 (one step, cold caches per launch)"},
+              open(out_json, "w"), indent=1)
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    per_ = main(*sys.argv[1:4])
+    if len(sys.argv) > 4:
+        conv_traffic_json(per_, sys.argv[4])
