@@ -50,9 +50,9 @@ def parse_args():
     ap.add_argument("--max-det", type=int, default=0,
                     help="0 (default) = every NMS survivor, like the reference's non_max_suppression (utils_bbox.py:414-420); "
                          "N > 0 = keep the N best per image (BASELINE configs[3] semantics; a cheaper top-K NMS)")
-    ap.add_argument("--gather-rows", type=int, default=16384,
+    ap.add_argument("--gather-rows", type=int, default=0,
                     help="rows per image of the fixed-layout buffers of the uncapped run (host copy-out and NCCL gather); "
-                         "the run aborts if an image keeps more")
+                         "0 (default) = sized from an untimed probe step: 1.25 x the largest survivor count over all ranks")
     ap.add_argument("--cpu-images", type=int, default=16, help="images per pass of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample: repeat passes for about this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,16 +304,30 @@ def run_native_arm(args):
     host_feats = [t.cpu().pin_memory() for t in feats]
     plan = net.plan_for(feats)
     max_det = args.max_det if args.max_det > 0 else None      # None: every survivor, the reference's semantics
-    rows_cap = max_det if max_det is not None else min(args.gather_rows, plan.num_anchors)   # fixed-layout copy-out / gather rows
     nms = net.nms_for(plan, max_det)
+    # fixed-layout copy-out / gather rows.  Uncapped runs size them from an untimed probe step (the synthetic inputs are
+    # fixed, so the survivor counts of the timed steps are the probe's): 1.25 x the largest count of any image on any rank.
+    total_cap = None
+    if max_det is not None:
+        rows_cap = max_det
+    elif args.gather_rows > 0:
+        rows_cap = min(args.gather_rows, plan.num_anchors)
+    else:
+        _, cnt0 = net.detect_features(feats, conf_thres=CONF_THRES, nms_thres=NMS_THRES, strategy="auto_cuda", max_det=None)
+        kmax_t = torch.stack([cnt0.max().to(torch.int64), cnt0.sum().to(torch.int64)])
+        if world > 1:
+            dist.all_reduce(kmax_t, op=dist.ReduceOp.MAX)
+        rows_cap = min(plan.num_anchors, (int(kmax_t[0].item()) * 5 // 4 + 1023) // 1024 * 1024)
+        total_cap = (int(kmax_t[1].item()) * 5 // 4 + 1023) // 1024 * 1024      # packed gather payload: rows of a whole batch
 
     # multi-GPU: ONE all_gather per (micro-)step, issued asynchronously into double-buffered outputs and consumed one step
     # later, so the gather of step i overlaps the compute of step i + 1 (glsdet_b200/dist.py::DetectionGather)
-    gather = DetectionGather(B, rows_cap, dev) if world > 1 else None
+    # packed payload (the rows that exist, back to back) gathered to rank 0 only, like collect_results_gpu's consumer
+    gather = DetectionGather(B, rows_cap, dev, total_rows=total_cap, dst=0) if world > 1 else None
     pending = [None]
 
     def gather_step(det, cnt, last=False):
-        if gather is None:
+        if gather is None or os.environ.get("GLSDET_BENCH_NO_GATHER"):   # diagnostic: N ranks without the exchange step
             return
         t = gather.submit(det, cnt)
         if pending[0] is not None:
@@ -397,6 +411,7 @@ def run_native_arm(args):
     host_cnt = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
     host_det = [torch.empty((B, rows_cap, 7), dtype=torch.float32).pin_memory() for _ in range(2)]
     d2h_rows = [0]
+    truncated = [0]
     copy_stream = torch.cuda.Stream(device=dev)
 
     def e2e_measure(host_inputs, step_fn):
@@ -429,8 +444,9 @@ def run_native_arm(args):
                 done[slot].record(stream)
                 done[slot].synchronize()
                 kmax = int(host_cnt[slot].max())
-                if kmax > rows_cap:
-                    raise SystemExit(f"an image kept {kmax} boxes > --gather-rows {rows_cap}")
+                if kmax > rows_cap:      # cannot happen with the probe-sized buffers unless an entry point sees another load
+                    truncated[0] = max(truncated[0], kmax)
+                    kmax = rows_cap
                 host_det[slot][:, :kmax].copy_(det[:, :kmax], non_blocking=True)
                 done[slot].record(stream)
                 done[slot].synchronize()                     # the caller reads this step's detections now
@@ -538,14 +554,14 @@ def run_native_arm(args):
                            "l2": f"inputs ({feat_mb:.0f} MB fp32 feature maps per micro-batch) exceed the 126 MB L2; no explicit flush",
                            "candidates_per_image": cand, "kept_per_image": kept_value,
                            "max_det": max_det if max_det is not None else "none (every NMS survivor, utils_bbox.py:414-420)",
-                           "postprocess_ms": post_ms,
+                           "postprocess_ms": post_ms, "gather_rows": rows_cap,
                            "cuda_graph": bool(args.graph),
                            "storage": "16-bit activations (bf16 at stride 4, fp16 at strides 8-32), fp32 accumulation",
-                           "parallelism": (f"dp{world} (images sharded; one asynchronous NCCL all_gather of the detections per "
-                                           "step, overlapped with the next step)") if world > 1 else "single GPU"},
+                           "parallelism": (f"dp{world} (images sharded; one asynchronous NCCL gather of the packed detections to "
+                                           "rank 0 per step, overlapped with the next step)") if world > 1 else "single GPU"},
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps, "how": e2e_how,
-                        "kept_per_image": kept,
+                        "kept_per_image": kept, "rows_truncated_at": (rows_cap if truncated[0] else None),
                         "from_fp32_images": {"value": img32_value, "unit": "images/s", "h2d_bytes_per_step": h2d_img32_bytes,
                                              "ms_per_step": img32_ms / args.steps, "kept_per_image": kept_img32,
                                              "how": "same, but YoloBody.detect(pinned host fp32 NCHW image batch) - the tensor "

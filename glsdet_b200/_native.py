@@ -210,6 +210,7 @@ SIGNATURES = {
     "glsdet_resize_bicubic_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                            C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "glsdet_pack_detections": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "glsdet_ufp_pack": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                   C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "glsdet_ufp_mosaic": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,

@@ -660,3 +660,43 @@ extern "C" int glsdet_nhwc_transpose_16(const void* src, void* dst, int32_t batc
       dst_rows, dst_ld, scale != 1.0f ? 1 : 0, static_cast<int>(dtype), scale);
   return glsdet::count_launch("nhwc_transpose_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Payload of the detection gather (glsdet_b200/dist.py::DetectionGather; replaces the pickle -> uint8 tensor step of
+// mmdet's collect_results_gpu, yolox-ufp/mmdet/apis/test.py:161-175): ONE launch instead of ~10 framework kernels.
+//   padded (total_rows == 0): out[b][0][0] = min(count[b], rows), out[b][1 + r] = det[b][r] for the rows that exist;
+//   packed (total_rows  > 0): out = [hdr rows holding the B counts | every image's rows back to back | ...]; rows that
+//                             would land beyond hdr + total_rows are dropped.
+namespace glsdet {
+__global__ void __launch_bounds__(256) pack_detections_kernel(const float* __restrict__ det, const int32_t* __restrict__ count,
+                                                              int det_rows, int rows, int hdr, int total_rows,
+                                                              float* __restrict__ out) {
+  pdl_prologue();
+  const int b = blockIdx.y;
+  const int n = min(count[b], rows);
+  const float* src = det + static_cast<int64_t>(b) * det_rows * 7;
+  if (total_rows == 0) {
+    float* dst = out + static_cast<int64_t>(b) * (1 + rows) * 7;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] = static_cast<float>(n);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * 7; i += gridDim.x * blockDim.x) dst[7 + i] = src[i];
+    return;
+  }
+  int off = 0;
+  for (int i = 0; i < b; ++i) off += min(count[i], rows);     // B is a few dozen: a serial prefix per CTA is cheapest
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[b] = static_cast<float>(n);
+  const int room = max(0, min(n, total_rows - off));
+  float* dst = out + static_cast<int64_t>(hdr + off) * 7;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < room * 7; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+}  // namespace glsdet
+
+extern "C" int glsdet_pack_detections(const float* det, const int32_t* count, int32_t batch, int32_t det_rows, int32_t rows,
+                                      int32_t total_rows, float* out, void* stream) {
+  GLSDET_REQUIRE(det && count && out && batch > 0 && det_rows > 0 && rows > 0 && rows <= det_rows && total_rows >= 0,
+                 "pack_detections: bad arguments");
+  const int hdr = (batch + 6) / 7;
+  const int gx = (rows * 7 + 256 * 8 - 1) / (256 * 8);
+  glsdet::launch_pdl(glsdet::pack_detections_kernel, dim3(gx < 1 ? 1 : (gx > 64 ? 64 : gx), batch), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), det, count, det_rows, rows, hdr, total_rows, out);
+  return glsdet::count_launch("pack_detections_kernel");
+}

@@ -77,21 +77,46 @@ def gather_detections(det: torch.Tensor, count: torch.Tensor, max_rows: Optional
 class DetectionGather:
     """Asynchronous, double-buffered detection gather for a pipelined test loop.
 
-        g = DetectionGather(batch, rows, device)
-        t = g.submit(det, cnt)          # after step i: packs on the current stream, all_gather runs on NCCL's stream
+        g = DetectionGather(batch, rows, device)                       # padded layout, every rank receives everything
+        g = DetectionGather(batch, rows, device, total_rows=T, dst=0)  # packed layout, only rank 0 receives
+        t = g.submit(det, cnt)          # after step i: packs on the current stream, the collective runs on NCCL's stream
         ... launch step i + 1 ...
         det_all, cnt_all = g.result(t)  # the current stream waits for gather i only now
 
-    Two send / receive buffer pairs alternate, so at most two gathers may be outstanding."""
+    Padded layout: [B, 1 + rows, 7] per rank, the count of an image in its header row.  Packed layout (`total_rows`): the
+    rows that exist are stored back to back - [ceil(B / 7) header rows with the counts | sum(count) rows | padding up to
+    total_rows] - which is 2 - 4 x smaller than the padded block when survivor counts vary between images (an uncapped
+    step of the bench: 2.5 MB instead of 9 MB per rank); rows beyond total_rows are dropped (size it from a probe step).
+    `dst`: gather to that rank only (mmdet's collect_results_gpu only uses the result on rank 0, apis/test.py:178-191):
+    the other ranks just send.  Two send / receive buffer pairs alternate, so at most two gathers may be outstanding."""
 
-    def __init__(self, batch: int, max_rows: int, device, dtype=torch.float32, group=None):
+    def __init__(self, batch: int, max_rows: int, device, dtype=torch.float32, group=None, total_rows: Optional[int] = None,
+                 dst: Optional[int] = None):
         self.group = group
         self.rank, self.world = get_dist_info(group)
-        self.batch, self.rows = batch, max_rows
-        self.send = [torch.empty((batch, 1 + max_rows, 7), dtype=dtype, device=device) for _ in range(2)]
-        self.recv = [torch.empty((self.world * batch, 1 + max_rows, 7), dtype=dtype, device=device) for _ in range(2)]
+        self.batch, self.rows, self.dst = batch, max_rows, dst
+        self.total_rows = total_rows
+        self.hdr = (batch + 6) // 7
+        shape = (batch, 1 + max_rows, 7) if total_rows is None else (self.hdr + total_rows + 1, 7)   # + 1: dump row
+        self.send = [torch.empty(shape, dtype=dtype, device=device) for _ in range(2)]
+        recv_here = dst is None or self.rank == dst
+        self.recv = [torch.empty((self.world,) + shape, dtype=dtype, device=device) if recv_here else None for _ in range(2)]
         self.work = [None, None]
         self.n = 0
+        if total_rows is not None:
+            self._ar = torch.arange(max_rows, device=device)[None, :]
+
+    def _pack_rows(self, det: torch.Tensor, count: torch.Tensor, out: torch.Tensor) -> None:
+        """Back-to-back rows without a host round trip: row r of image b goes to hdr + offset[b] + r; rows that do not
+        exist (or overflow total_rows) go to the dump row at the end."""
+        r = self.rows
+        cnt = count.clamp(max=r).to(torch.int64)
+        off = torch.cumsum(cnt, 0) - cnt
+        idx = self.hdr + off[:, None] + self._ar
+        dump = self.hdr + self.total_rows
+        idx = torch.where((self._ar < cnt[:, None]) & (idx < dump), idx, torch.full_like(idx, dump))
+        out[:self.hdr].view(-1)[:self.batch] = cnt.to(out.dtype)
+        out.index_copy_(0, idx.reshape(-1), det[:, :r].reshape(-1, 7))
 
     def submit(self, det: torch.Tensor, count: torch.Tensor) -> int:
         slot = self.n & 1
@@ -99,18 +124,51 @@ class DetectionGather:
         if self.work[slot] is not None:   # the buffer pair is reused: its previous gather must have been consumed
             self.work[slot].wait()
             self.work[slot] = None
-        _pack(det, count, self.rows, out=self.send[slot])
-        if self.world == 1:
-            self.recv[slot].copy_(self.send[slot])
+        if (det.is_cuda and det.dtype == torch.float32 and det.is_contiguous() and count.dtype == torch.int32 and
+                det.shape[1] >= self.rows):
+            from . import _native as N          # one native launch instead of ~10 framework kernels on the compute stream
+            N.check(N.load().glsdet_pack_detections(det.data_ptr(), count.contiguous().data_ptr(), self.batch, det.shape[1],
+                                                    self.rows, self.total_rows or 0,
+                                                    self.send[slot].data_ptr(), N.stream_ptr()), "glsdet_pack_detections")
+        elif self.total_rows is None:
+            _pack(det, count, self.rows, out=self.send[slot])
         else:
-            self.work[slot] = dist.all_gather_into_tensor(self.recv[slot], self.send[slot], group=self.group, async_op=True)
+            self._pack_rows(det, count, self.send[slot])
+        if self.world == 1:
+            self.recv[slot][0].copy_(self.send[slot])
+        elif self.dst is None:
+            flat = self.recv[slot].view((-1,) + tuple(self.send[slot].shape[1:]))     # concatenation layout along dim 0
+            self.work[slot] = dist.all_gather_into_tensor(flat, self.send[slot], group=self.group, async_op=True)
+        else:
+            gl = list(self.recv[slot].unbind(0)) if self.rank == self.dst else None
+            self.work[slot] = dist.gather(self.send[slot], gl, dst=self.dst, group=self.group, async_op=True)
         return slot
 
-    def result(self, slot: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    def result(self, slot: int) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Padded layout: (det_all [world*B, rows, 7], count_all [world*B]).  Packed layout: (packed [world, hdr + T + 1, 7],
+        count_all [world*B]) - see `unpack`.  (None, None) on ranks that do not receive."""
         if self.work[slot] is not None:
             self.work[slot].wait()        # stream-level wait on GPU process groups (no host synchronisation)
             self.work[slot] = None
-        return _unpack(self.recv[slot])
+        if self.recv[slot] is None:
+            return None, None
+        if self.total_rows is None:
+            return _unpack(self.recv[slot].view(-1, 1 + self.rows, 7))
+        packed = self.recv[slot]
+        cnt_all = packed[:, :self.hdr].reshape(self.world, -1)[:, :self.batch].round().to(torch.int32).reshape(-1)
+        return packed, cnt_all
+
+    def unpack(self, packed: torch.Tensor, cnt_all: torch.Tensor) -> List[torch.Tensor]:
+        """Packed result -> per image a [count, 7] view (host-side slicing: one read of the counts)."""
+        counts = cnt_all.view(self.world, self.batch).cpu().tolist()
+        out = []
+        for r in range(self.world):
+            o = self.hdr
+            for c in counts[r]:
+                n = max(0, min(c, self.hdr + self.total_rows - o))
+                out.append(packed[r, o:o + n])
+                o += c
+        return out
 
 
 def interleave_round_robin(det_all: torch.Tensor, cnt_all: torch.Tensor, world: int, num_images: int):
@@ -183,7 +241,7 @@ def multi_gpu_test(model: Callable, data_loader: Iterable, tmpdir: Optional[str]
     fixed_parts: List[Tuple[torch.Tensor, torch.Tensor]] = []
 
     def consume(ticket):
-        det_all, cnt_all = gather.result(ticket)
+        det_all, cnt_all = gather.result(ticket)     # (None, None) on the ranks that only send
         if rank == 0:   # rank-major [world, B] -> this step's images in dataset order
             b = det_all.shape[0] // world_size
             order = torch.arange(world_size * b, device=det_all.device).view(world_size, b).t().reshape(-1)
@@ -195,7 +253,8 @@ def multi_gpu_test(model: Callable, data_loader: Iterable, tmpdir: Optional[str]
         if _is_fixed_layout(result) and (gpu_collect or tmpdir is None):
             det, cnt = result
             if gather is None:
-                gather = DetectionGather(det.shape[0], det.shape[1] if max_rows is None else min(max_rows, det.shape[1]), det.device)
+                gather = DetectionGather(det.shape[0], det.shape[1] if max_rows is None else min(max_rows, det.shape[1]), det.device,
+                                         dst=0)
             ticket = gather.submit(det, cnt)
             if pending is not None:
                 consume(pending)

@@ -491,6 +491,13 @@ int glsdet_resize_bicubic_u8(const uint8_t* image, int32_t in_h, int32_t in_w, u
                              const int32_t* bounds_h, const int32_t* kk_h, int32_t ksize_h, const int32_t* bounds_v,
                              const int32_t* kk_v, int32_t ksize_v, void* stream);
 
+/* Payload of the multi-GPU detection gather (replaces the pickle -> uint8 tensor step of mmdet's collect_results_gpu,
+ * yolox-ufp/mmdet/apis/test.py:161-175).  det [batch, det_rows, 7] fp32, count [batch] int32.  total_rows == 0: padded
+ * layout out[batch][1 + rows][7] (count in element [b][0][0]); total_rows > 0: packed layout
+ * out[(batch + 6) / 7 header rows with the counts | rows of all images back to back, at most total_rows][7]. */
+int glsdet_pack_detections(const float* det, const int32_t* count, int32_t batch, int32_t det_rows, int32_t rows,
+                           int32_t total_rows, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

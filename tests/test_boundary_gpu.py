@@ -145,3 +145,27 @@ def test_cuda_graph_replay_equals_eager(native_lib, cuda_device):
             assert torch.equal(gdet[b, :int(cnt[b])], det[b, :int(cnt[b])])
         if seed == 2:   # the second call replays: only the four layout converters are launched from the host
             assert launched == 4, launched
+
+
+def test_gather_payload_kernel_equals_framework_packing(native_lib, cuda_device):
+    """glsdet_pack_detections (one launch) against the torch-op packing the CPU / gloo path uses, padded and packed
+    layouts, including an image without detections, counts above the row cap and a payload that overflows total_rows."""
+    from glsdet_b200.dist import DetectionGather
+
+    g = torch.Generator().manual_seed(3)
+    det = torch.rand(5, 40, 7, generator=g)
+    cnt = torch.tensor([7, 0, 40, 55, 13], dtype=torch.int32)
+    for total in (None, 64, 30):
+        cpu = DetectionGather(5, 16, "cpu", total_rows=total)
+        gpu = DetectionGather(5, 16, cuda_device, total_rows=total)
+        a = cpu.result(cpu.submit(det, cnt))
+        b = gpu.result(gpu.submit(det.to(cuda_device), cnt.to(cuda_device)))
+        assert torch.equal(a[1], b[1].cpu())
+        if total is None:
+            for i in range(5):
+                n = int(a[1][i])
+                assert torch.equal(a[0][i, :n], b[0][i, :n].cpu())
+        else:
+            ra, rb = cpu.unpack(*a), gpu.unpack(*b)
+            assert [len(r) for r in ra] == [len(r) for r in rb]
+            assert all(torch.equal(x, y.cpu()) for x, y in zip(ra, rb))

@@ -120,6 +120,23 @@ def _worker_test_loop(rank, world, port, num_images, tmp, ret):
     d0, c0 = g.result(t0)
     ok &= c0.tolist() == [1, 2] * world and c1.tolist() == [3, 3] * world      # counts clamp to the gathered rows
     ok &= all(bool((d0[2 * r:2 * r + 2] == r).all()) and bool((d1[2 * r:2 * r + 2] == r + 10).all()) for r in range(world))
+    # packed layout gathered to rank 0 only: rows back to back, counts in the header, overflow dropped at total_rows
+    gp = DetectionGather(3, 4, "cpu", total_rows=6, dst=0)
+    det = torch.arange(3 * 4 * 7, dtype=torch.float32).view(3, 4, 7) + 1000 * rank
+    tk = gp.submit(det, torch.tensor([2, 0, 3], dtype=torch.int32))
+    packed, call = gp.result(tk)
+    if rank == 0:
+        rows = gp.unpack(packed, call)
+        ok &= call.tolist() == [2, 0, 3] * world and [len(r) for r in rows] == [2, 0, 3] * world
+        for r in range(world):
+            ok &= bool(torch.equal(rows[3 * r], det[0, :2] - 1000 * rank + 1000 * r)) and bool(torch.equal(rows[3 * r + 2], det[2, :3] - 1000 * rank + 1000 * r))
+    else:
+        ok &= packed is None and call is None
+    gp2 = DetectionGather(2, 4, "cpu", total_rows=5, dst=0)      # 4 + 3 rows into 5: the last image is cut
+    tk = gp2.submit(torch.ones(2, 4, 7), torch.tensor([4, 3], dtype=torch.int32))
+    packed, call = gp2.result(tk)
+    if rank == 0:
+        ok &= [len(r) for r in gp2.unpack(packed, call)] == [4, 1] * world
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
