@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(1024) seg_plan_kernel(Work w) {
 // ---- spatial culling of the IoU tiles
 // All-pairs IoU inside a class is O(n^2) (330 M pairs per 16-image step at 7 k boxes of the dominant class) although a box
 // only overlaps its neighbours.  The boxes of a segment are therefore put into a spatially coherent order - counting
-// sort by the grid cell of the box centre, row-major cells - and cut into chunks of 64; two chunks are compared only if
+// sort by the grid cell of the box centre, cells in Morton order - and cut into chunks of 64; two chunks are compared only if
 // their bounding boxes intersect (exact: boxes that do not intersect cannot exceed an IoU threshold >= 0).  The order
 // only decides how many tiles survive, never the result: every surviving tile writes its suppression bits straight into
 // the SCORE-ordered triangular mask (row = better box, bit = worse box), so the resolve step is unchanged.
@@ -590,7 +590,16 @@ __global__ void __launch_bounds__(256) cell_count_kernel(Work w, int strategy) {
     // size class: 0 = larger than a quarter of the range ... 3 = at most 1/16 of it (NaN sizes land in class 0)
     const float sz = fmaxf(bx.z - bx.x, bx.w - bx.y) * sc;   // in cells
     const int sz_class = sz <= 0.0625f * kGrid ? 3 : sz <= 0.125f * kGrid ? 2 : sz <= 0.25f * kGrid ? 1 : 0;
-    const int cid = (sz_class * kGrid + cy) * kGrid + cx;
+    // Morton (Z-order) index of the cell instead of row-major: 64 consecutive boxes then cover a compact block of cells
+    // rather than a strip of one cell row, and compact chunks have far fewer intersecting chunk bounding boxes
+    auto spread = [](uint32_t v) {   // 5 bits -> every other bit
+      v = (v | (v << 8)) & 0x00FF00FFu;
+      v = (v | (v << 4)) & 0x0F0F0F0Fu;
+      v = (v | (v << 2)) & 0x33333333u;
+      v = (v | (v << 1)) & 0x55555555u;
+      return v;
+    };
+    const int cid = sz_class * kGrid * kGrid + static_cast<int>(spread(static_cast<uint32_t>(cx)) | (spread(static_cast<uint32_t>(cy)) << 1));
     w.cell_id[static_cast<int64_t>(b) * w.cap + i] = static_cast<uint16_t>(cid);
     atomicAdd(&w.cell_hist[(static_cast<int64_t>(b) * w.nc + c) * kCells + cid], 1);
   }
