@@ -52,7 +52,7 @@ class BackbonePlan:
         if self.in_h % 32 or self.in_w % 32:
             raise ValueError("input size must be a multiple of 32 (yolox-drone/yolo.py:34-36)")
         self.act = N.ACT_BY_NAME[act]
-        self.sd = {k[len(prefix):]: v.detach().to(dev) for k, v in state_dict.items()
+        self.sd = {k[len(prefix):]: v.detach().cpu() for k, v in state_dict.items()   # host side: see engine.FFAPathPlan
                    if k.startswith(prefix) and not k.endswith("num_batches_tracked")}
         if "stem.conv.conv.weight" not in self.sd:
             raise KeyError(f"no CSPDarknet weights under prefix {prefix!r}")

@@ -76,9 +76,11 @@ class FFAPathPlan:
             if k.endswith("num_batches_tracked"):
                 continue
             if "neck" in self.parts and k.startswith(neck_prefix) and not k.startswith(neck_prefix + "backbone."):
-                sd["backbone." + k[len(neck_prefix):]] = v.detach().to(dev)   # CSPDarknet entries are skipped
+                sd["backbone." + k[len(neck_prefix):]] = v.detach().cpu()     # CSPDarknet entries are skipped
             elif ({"stems", "towers"} & self.parts) and k.startswith(head_prefix):
-                sd["head." + k[len(head_prefix):]] = v.detach().to(dev)
+                sd["head." + k[len(head_prefix):]] = v.detach().cpu()
+        # the weights stay on the HOST while the plan is built (BatchNorm folding in fp64, concatenations, permutations,
+        # packing: CPU tensor ops); every operator uploads its packed weights once (ops.ConvOp)
         self.sd = sd
         self.B = batch
         self.in_h, self.in_w = int(input_hw[0]), int(input_hw[1])
@@ -297,7 +299,7 @@ class FFAPathPlan:
         self._base_conv(hd, f + ".scale", [View(p4out)], View(s_a), act=relu)
         self._base_conv(hd, f + ".create_content_extractor.0", [View(s_a)], View(s_b), act=relu)
         # PixelShuffle(2): out[c, 2y+i, 2x+j] = in[4c+2i+j, y, x]  ->  store channels in (i, j, c) order
-        perm = torch.arange(4 * hc, device=self.device).view(hc, 4).t().reshape(-1)  # new n' -> old 4c + (2i+j)
+        perm = torch.arange(4 * hc).view(hc, 4).t().reshape(-1)  # new n' -> old 4c + (2i+j)
         w, b = self._folded(f + ".create_content_extractor.1")
         self._conv(hd, w[perm].contiguous(), b[perm].contiguous(), [View(s_b)], View(s_a), 1, act=relu)
         se = SeGateOp(View(s_a), self.sd[f + ".se1.fc.0.weight"][:, perm], self.sd[f + ".se1.fc.2.weight"][perm])
@@ -373,9 +375,9 @@ class FFAPathPlan:
         sd, dev = self.sd, self.device
         Ca, Tp = xt.shape[1], xt.shape[2]
         npos = len(positions)
-        a1 = torch.zeros((npos, C, Ca), dtype=torch.float64, device=dev)
-        a2t = torch.zeros((npos, Ca, Ca), dtype=torch.float64, device=dev)
-        bo = torch.zeros((npos, C), dtype=torch.float32, device=dev)
+        a1 = torch.zeros((npos, C, Ca), dtype=torch.float64)
+        a2t = torch.zeros((npos, Ca, Ca), dtype=torch.float64)
+        bo = torch.zeros((npos, C), dtype=torch.float32)
         for i, pos in enumerate(positions):
             q = f"{p}.feat_patchconv_{pos}_nonlocal."
             wg, wt, wp, wo = (sd[q + n + ".weight"].double().flatten(1) for n in ("g", "theta", "phi", "conv_out"))
@@ -387,11 +389,11 @@ class FFAPathPlan:
             a2t[i, :C + 1, :C + 1] = a2.t()
             bo[i] = sd[q + "conv_out.bias"].float()
         dt = xt.dtype
-        a1 = a1.to(dt).view(npos, 1, C, Ca).contiguous()
-        a2t = a2t.to(dt).view(npos, 1, Ca, Ca).contiguous()
+        a1 = a1.to(dt).view(npos, 1, C, Ca).contiguous().to(dev)
+        a2t = a2t.to(dt).view(npos, 1, Ca, Ca).contiguous().to(dev)
         div = shared_kw.get("src_shared_div", 0)
-        img_pos = (torch.arange(Bp, device=dev) // div) if div else (torch.arange(Bp, device=dev) % npos)
-        bo_full = bo[img_pos].contiguous()               # [Bp, C]: b_o of every patch image
+        img_pos = (torch.arange(Bp) // div) if div else (torch.arange(Bp) % npos)
+        bo_full = bo[img_pos].contiguous().to(dev)       # [Bp, C]: b_o of every patch image
         S = torch.empty((Bp, 1, Ca, Ca), dtype=dt, device=dev)
         Zt = torch.empty((Bp, 1, Ca, Ca), dtype=dt, device=dev)
         Wm = torch.empty((Bp, 1, C, Ca), dtype=dt, device=dev)

@@ -191,8 +191,11 @@ class ConvOp:
         N.check(lib.glsdet_conv_weight_shape(C.byref(d), C.byref(n_pad), C.byref(k_pad), C.byref(block_n)),
                 "glsdet_conv_weight_shape")
         self.block_n = block_n.value
+        dev = srcs[0].t.device
         if weight_raw is None:
-            self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value, sdt)
+            # weights are folded / packed wherever they live (the plans keep them on the HOST: a plan build is then a few
+            # hundred small CPU ops and one upload per layer instead of ~1000 framework kernels) and uploaded here
+            self.packed = pack_conv_weight(weight, [s.c for s in srcs], n_pad.value, k_pad.value, sdt).to(dev)
         else:
             assert weight_raw.dtype == sdt and weight_raw.is_contiguous() and ksize == 1
             assert weight_raw.shape[-1] >= k_pad.value and weight_raw.shape[-2] >= n_out, (weight_raw.shape, k_pad.value)
@@ -205,7 +208,7 @@ class ConvOp:
         d.src_shared_div = int(src_shared_div)
         d.patch_mode = 1 if patch_mode else 0
         d.src_dtype = N.dt_code(sdt)
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.bias = None if bias is None else bias.detach().float().contiguous().to(dev)
         d.weight = self.packed.data_ptr()
         d.bias = 0 if self.bias is None else self.bias.data_ptr()
         ho, wo = h // stride, w // stride
@@ -243,9 +246,9 @@ class ConvOp:
         d.dec_stride, d.dec_in_w, d.dec_in_h = dec
         self.pred_weight = self.pred_bias = None
         if pred_weight is not None:   # fused prediction conv on the activated tile (never stored)
-            self.pred_weight = pred_weight.detach().float().reshape(pred_weight.shape[0], -1).contiguous()
+            self.pred_weight = pred_weight.detach().float().reshape(pred_weight.shape[0], -1).contiguous().to(dev)
             assert self.pred_weight.shape[1] == n_out and self.pred_weight.shape[0] <= 16
-            self.pred_bias = pred_bias.detach().float().contiguous()
+            self.pred_bias = pred_bias.detach().float().contiguous().to(dev)
             d.pred_weight, d.pred_bias = self.pred_weight.data_ptr(), self.pred_bias.data_ptr()
             d.pred_channels, d.pred_act = self.pred_weight.shape[0], pred_act
         self._keep = (srcs, pre_res, post_res, weight_raw)
@@ -303,8 +306,8 @@ class SeGateOp:
         assert x.coff == 0 and x.t.dtype in (torch.bfloat16, torch.float16, torch.float32)
         b, h, w = x.bhw
         self.x, self.b, self.hw, self.c = x, b, h * w, x.c
-        self.w1 = w1.detach().float().contiguous()
-        self.w2 = w2.detach().float().contiguous()
+        self.w1 = w1.detach().float().contiguous().to(x.t.device)
+        self.w2 = w2.detach().float().contiguous().to(x.t.device)
         self.hidden = self.w1.shape[0]
         assert tuple(self.w1.shape) == (self.hidden, self.c) and tuple(self.w2.shape) == (self.c, self.hidden)
         self.scratch = torch.empty((b, N.SE_SLABS, self.c), dtype=torch.float32, device=x.t.device)
@@ -431,8 +434,9 @@ class ConvOpF32:
         for s in srcs:
             segs.append(weight[:, a:a + s.c].permute(0, 2, 3, 1).reshape(n_out, -1))
             a += s.c
-        self.packed = torch.cat(segs, 1).float().contiguous()
-        self.bias = None if bias is None else bias.detach().float().contiguous()
+        dev = srcs[0].t.device
+        self.packed = torch.cat(segs, 1).float().contiguous().to(dev)
+        self.bias = None if bias is None else bias.detach().float().contiguous().to(dev)
         d = N.ConvF32Desc()
         d.src0, d.src0_c, d.src0_ld = srcs[0].ptr, srcs[0].c, srcs[0].ld
         if len(srcs) == 2:
