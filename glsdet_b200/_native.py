@@ -158,6 +158,8 @@ SIGNATURES = {
     "glsdet_group_norm_scratch_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "glsdet_proxy_scores": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_float, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
+    "glsdet_proxy_aggregate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_float, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "glsdet_gfl_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "glsdet_gfl_select": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
@@ -205,6 +207,10 @@ SIGNATURES = {
     "glsdet_batched_nms_ids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_float, C.c_int32,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "glsdet_batched_nms_workspace_bytes": (C.c_int64, [C.c_int32]),
+    "glsdet_batched_nms_batch_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "glsdet_batched_nms_ids_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]),
     "glsdet_pil_bicubic_ksize": (C.c_int, [C.c_int32, C.c_int32]),
     "glsdet_pil_bicubic_table": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "glsdet_resize_bicubic_u8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

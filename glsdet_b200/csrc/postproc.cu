@@ -138,11 +138,12 @@ __device__ __forceinline__ Cand load_cand(const Source& s, int b, int idx) {
     c.label = arg;
     c.label_f = static_cast<float>(arg);
   } else {
-    c.box = __ldg(reinterpret_cast<const float4*>(s.boxes) + idx);
-    c.obj = __ldg(s.scores + idx);
+    const int64_t o = static_cast<int64_t>(b) * s.A + idx;    // caller-supplied arrays are [B][A] (B = 1 for one image)
+    c.box = __ldg(reinterpret_cast<const float4*>(s.boxes) + o);
+    c.obj = __ldg(s.scores + o);
     c.cls_conf = 1.0f;
-    c.label_f = __ldg(s.labels + idx);
-    c.label = s.label_ids ? __ldg(s.label_ids + idx) : static_cast<int>(c.label_f);
+    c.label_f = __ldg(s.labels + o);
+    c.label = s.label_ids ? __ldg(s.label_ids + o) : static_cast<int>(c.label_f);
   }
   return c;
 }
@@ -1347,6 +1348,35 @@ extern "C" void glsdet_nms_destroy(glsdet_nms_t* op) { delete op; }
 extern "C" int64_t glsdet_batched_nms_workspace_bytes(int32_t k) {
   if (k <= 0) return 256;
   return workspace_bytes(1, k, kMaxClasses);
+}
+
+extern "C" int64_t glsdet_batched_nms_batch_workspace_bytes(int32_t batch, int32_t k, int32_t num_ids) {
+  if (batch <= 0 || k <= 0 || num_ids <= 0 || num_ids > kMaxClasses) return -1;
+  return workspace_bytes(batch, k, num_ids);
+}
+
+// B images at once: every array is [batch][k]; image b's kept indices (into its own k candidates, score order) land in
+// keep[b][0 .. keep_count[b]).  Each image is an independent NMS problem with the semantics of glsdet_batched_nms_ids
+// (the coordinate-trick maximum is per image), so the result equals `batch` separate calls - in one pipeline launch
+// sequence instead of `batch` of them.
+extern "C" int glsdet_batched_nms_ids_batch(const float* boxes, const float* scores, const float* labels,
+                                            const int32_t* label_ids, float label_abs_max, int32_t num_ids, int32_t batch,
+                                            int32_t k, float nms_thres, int32_t strategy, void* workspace,
+                                            int64_t workspace_bytes_given, int32_t* keep, int32_t* keep_count, void* stream) {
+  GLSDET_REQUIRE(boxes && scores && labels && label_ids && keep && keep_count, "batched_nms_batch: null pointer");
+  GLSDET_REQUIRE(batch > 0 && k > 0 && k < (1 << 24), "batched_nms_batch: bad sizes");
+  GLSDET_REQUIRE(num_ids > 0 && num_ids <= kMaxClasses, "batched_nms_batch: 1..%d class ids", kMaxClasses);
+  GLSDET_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "batched_nms_batch: boxes must be 16-byte aligned");
+  GLSDET_REQUIRE(strategy >= 0 && strategy <= GLSDET_NMS_MMCV, "batched_nms_batch: bad strategy %d", strategy);
+  GLSDET_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                 "batched_nms_batch: workspace must be 256-byte aligned");
+  GLSDET_REQUIRE(workspace_bytes_given >= workspace_bytes(batch, k, num_ids), "batched_nms_batch: workspace too small");
+  Work w = make_work(workspace, batch, k, num_ids);
+  w.trick_label_max = label_abs_max;
+  Source s{};
+  s.A = k; s.nch = 0; s.nc = num_ids;
+  s.boxes = boxes; s.scores = scores; s.labels = labels; s.label_ids = label_ids;
+  return run_pipeline<false>(s, w, 0.0f, nms_thres, strategy, k, nullptr, keep_count, keep, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int glsdet_batched_nms(const float* boxes, const float* scores, const float* labels, int32_t k,

@@ -254,6 +254,9 @@ class _MPHeadPlan:
         for n in m.proxies_list:
             starts.append(starts[-1] + n)
         self.centers, self.cls_start = centers, torch.tensor(starts, dtype=torch.int32, device=dev)
+        self.n_prox_pad = (centers.shape[0] + 15) // 16 * 16
+        self.proxy_w = torch.zeros((self.n_prox_pad, fc, 1, 1), dtype=torch.float32, device=dev)
+        self.proxy_w[:centers.shape[0], :, 0, 0] = centers
         self.levels = []
         reg_ld = (4 * bins + 15) // 16 * 16
         self.reg_ld = reg_ld
@@ -264,7 +267,8 @@ class _MPHeadPlan:
             tb = torch.empty_like(ta)
             ra = torch.empty_like(ta)
             rb = torch.empty_like(ta)
-            feat32 = torch.empty((B, h, w, fc), dtype=torch.float32, device=dev)
+            feat16 = torch.empty((B, h, w, fc), dtype=torch.bfloat16, device=dev)     # class features (bf16: operand of the proxy GEMM)
+            sims = torch.empty((B, h, w, self.n_prox_pad), dtype=torch.float32, device=dev)
             reg32 = torch.zeros((B, h, w, reg_ld), dtype=torch.float32, device=dev)
             ops = []
 
@@ -282,11 +286,13 @@ class _MPHeadPlan:
             cf = tower(m.cls_convs, x, ta, tb)
             rf = tower(m.reg_convs, x, ra, rb)
             ops.append(("conv", ConvOp([View(cf)], m.gfl_cls_conv.weight.detach().float(), m.gfl_cls_conv.bias.detach().float(),
-                                       ksize=3, act=N.ACT_NONE, out=View(feat32))))
+                                       ksize=3, act=N.ACT_NONE, out=View(feat16))))
+            # forward_proxy (mp_head.py:105-121): similarities to the normalised proxies = a 1x1 conv on the tensor core
+            ops.append(("conv", ConvOp([View(feat16)], self.proxy_w, None, ksize=1, act=N.ACT_NONE, out=View(sims))))
             sc = float(m.scales[l].scale.detach())
             ops.append(("conv", ConvOp([View(rf)], m.gfl_reg.weight.detach().float() * sc, m.gfl_reg.bias.detach().float() * sc,
                                        ksize=3, act=N.ACT_NONE, out=View(reg32, 0, 4 * bins))))
-            self.levels.append(dict(x=x, feat32=feat32, reg32=reg32, ops=ops, keep=(ta, tb, ra, rb)))
+            self.levels.append(dict(x=x, feat16=feat16, sims=sims, reg32=reg32, ops=ops, keep=(ta, tb, ra, rb)))
         # candidate buffers of get_bboxes
         self.cap = 0
         self.keys = None
@@ -305,9 +311,9 @@ class _MPHeadPlan:
                     N.check(lib.glsdet_group_norm_relu(buf.data_ptr(), self.B, h * w, buf.shape[3], buf.shape[3], 32,
                                                        g.data_ptr(), b_.data_ptr(), eps, self.gn_scratch.data_ptr(), st),
                             "glsdet_group_norm_relu")
-            N.check(lib.glsdet_proxy_scores(lv["feat32"].data_ptr(), self.centers.data_ptr(), self.cls_start.data_ptr(), nc,
-                                            self.centers.shape[0], m.feat_channels, self.B, h * w, m.gamma,
-                                            self.rows.data_ptr(), nc, self.A * nc, self.row0[l], st), "glsdet_proxy_scores")
+            N.check(lib.glsdet_proxy_aggregate(lv["feat16"].data_ptr(), lv["sims"].data_ptr(), self.n_prox_pad,
+                                               self.cls_start.data_ptr(), nc, m.feat_channels, self.B, h * w, m.gamma,
+                                               self.rows.data_ptr(), nc, self.A * nc, self.row0[l], st), "glsdet_proxy_aggregate")
             if img_shape is not None:
                 N.check(lib.glsdet_gfl_decode(lv["reg32"].data_ptr(), self.reg_ld, bins, self.B, h, w, float(m.strides[l]),
                                               float(img_shape[1]), float(img_shape[0]), self.boxes.data_ptr(), self.A * 4,
@@ -381,16 +387,18 @@ class _MPHeadPlan:
         if rescale:   # base_dense_head.py:282-283: mlvl_bboxes /= scale_factor, before the NMS
             sf = torch.tensor([list(_scale4(im["scale_factor"])) for im in img_metas], dtype=torch.float32, device=self.dev)
             self.cboxes.div_(sf[:, None, :])
-        from .utils_bbox import STRATEGIES, _batched_nms_workspace
-        nbytes, ws = _batched_nms_workspace(cap, self.dev)
+        from .utils_bbox import STRATEGIES
         if getattr(self, "keep", None) is None or self.keep.shape[1] != cap:
             self.keep = torch.empty((self.B, cap), dtype=torch.int32, device=self.dev)
             self.kcount = torch.zeros((self.B,), dtype=torch.int32, device=self.dev)
+            nbytes = int(lib.glsdet_batched_nms_batch_workspace_bytes(self.B, cap, nc))
+            self.nms_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
         ids = self.clabels.to(torch.int32)
-        for b in range(self.B):
-            N.check(lib.glsdet_batched_nms_ids(self.cboxes[b].data_ptr(), self.cscores[b].data_ptr(), self.clabels[b].data_ptr(),
-                                               ids[b].data_ptr(), float(nc - 1), cap, iou, STRATEGIES["mmcv"], ws.data_ptr(), nbytes,
-                                               self.keep[b].data_ptr(), self.kcount[b:b + 1].data_ptr(), st), "glsdet_batched_nms_ids")
+        # all images in ONE pipeline launch sequence (each image stays its own NMS problem: per-image coordinate-trick maximum)
+        N.check(lib.glsdet_batched_nms_ids_batch(self.cboxes.data_ptr(), self.cscores.data_ptr(), self.clabels.data_ptr(),
+                                                 ids.data_ptr(), float(nc - 1), nc, self.B, cap, iou, STRATEGIES["mmcv"],
+                                                 self.nms_ws.data_ptr(), self.nms_ws.numel(), self.keep.data_ptr(),
+                                                 self.kcount.data_ptr(), st), "glsdet_batched_nms_ids_batch")
         keep = self.keep.long()
         real = (keep < self.ccount[:, None].long()) & (torch.arange(cap, device=self.dev)[None, :] < self.kcount[:, None])
         n_real = real.sum(1).clamp(max=max_per_img)                     # kept real candidates lead the score order

@@ -319,6 +319,12 @@ int64_t glsdet_group_norm_scratch_floats(int32_t batch, int32_t channels);
 int glsdet_proxy_scores(const float* feat, const float* centers, const int32_t* cls_start, int32_t num_classes,
                         int32_t num_proxies, int32_t channels, int32_t batch, int32_t hw, float gamma, float* rows,
                         int32_t rows_ld, int64_t rows_batch_stride, int32_t row0, void* stream);
+/* Second half of MPHead.forward_proxy (mp_head.py:105-121) when the similarities come from a 1x1 conv of the bf16 class
+ * features with the normalised proxies (glsdet_conv_*, fp32 output sims[pixel][sims_ld]): L2 norm of the features and the
+ * per-class softmax(gamma * s)-weighted sum, raw class scores into rows like glsdet_proxy_scores. */
+int glsdet_proxy_aggregate(const void* feat, const float* sims, int32_t sims_ld, const int32_t* cls_start, int32_t num_classes,
+                           int32_t channels, int32_t batch, int32_t hw, float gamma, float* rows, int32_t rows_ld,
+                           int64_t rows_batch_stride, int32_t row0, void* stream);
 int glsdet_gfl_decode(const float* reg, int32_t reg_ld, int32_t bins, int32_t batch, int32_t height, int32_t width,
                       float stride, float max_x, float max_y, float* boxes, int64_t boxes_batch_stride, int32_t row0,
                       void* stream);
@@ -453,6 +459,14 @@ int glsdet_batched_nms_ids(const float* boxes, const float* scores, const float*
                            float label_abs_max, int32_t k, float nms_thres, int32_t strategy, void* workspace, int64_t workspace_bytes,
                            int32_t* keep, int32_t* keep_count, void* stream);
 int64_t glsdet_batched_nms_workspace_bytes(int32_t k);
+/* `batch` independent problems of glsdet_batched_nms_ids in one launch sequence (mmdet's per-image _bbox_post_process /
+ * _bboxes_nms loop, base_dense_head.py:276-301, yolox_head.py:286-294): every array is [batch][k], label_ids in
+ * 0..num_ids-1 (num_ids <= 256), keep int32 [batch][k], keep_count int32 [batch]. */
+int64_t glsdet_batched_nms_batch_workspace_bytes(int32_t batch, int32_t k, int32_t num_ids);
+int glsdet_batched_nms_ids_batch(const float* boxes, const float* scores, const float* labels, const int32_t* label_ids,
+                                 float label_abs_max, int32_t num_ids, int32_t batch, int32_t k, float nms_thres,
+                                 int32_t strategy, void* workspace, int64_t workspace_bytes, int32_t* keep, int32_t* keep_count,
+                                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * UFP stage of UFPMP-Det (reference: /root/reference/yolox-ufp).

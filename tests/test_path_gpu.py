@@ -481,3 +481,36 @@ def test_filter_sigmoid_window_exact_on_ties_and_saturation(native_lib, cuda_dev
     assert int(cnt_a[0]) > 3000 and torch.equal(cnt_a, cnt_b)
     n = int(cnt_a[0])
     assert torch.equal(det_a[0, :n], det_b[0, :n])
+
+
+def test_batched_nms_ids_batch_equals_per_image_calls(native_lib, cuda_device):
+    """glsdet_batched_nms_ids_batch (B independent problems in one launch sequence) == B calls of batched_nms, for the
+    mmcv and the torchvision strategies; images of different coordinate ranges (per-image coordinate-trick maxima)."""
+    import ctypes as C
+
+    from glsdet_b200 import _native as N
+    from glsdet_b200.utils_bbox import STRATEGIES, batched_nms
+
+    rng = np.random.default_rng(17)
+    B, k, nc = 3, 1500, 7
+    boxes, scores, labels = [], [], []
+    for b in range(B):
+        bx, sc, lb = _clustered(rng, k, nc)
+        boxes.append(bx * (100.0 * (b + 1)))          # different extents per image
+        scores.append(sc)
+        labels.append(lb)
+    bx = torch.from_numpy(np.stack(boxes)).to(cuda_device).contiguous()
+    sc = torch.from_numpy(np.stack(scores)).to(cuda_device).contiguous()
+    lb = torch.from_numpy(np.stack(labels)).to(cuda_device).contiguous()
+    ids = lb.to(torch.int32)
+    for strategy in ("mmcv", "auto_cuda", "per_class"):
+        nbytes = int(native_lib.glsdet_batched_nms_batch_workspace_bytes(B, k, nc))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda_device)
+        keep = torch.empty((B, k), dtype=torch.int32, device=cuda_device)
+        cnt = torch.zeros((B,), dtype=torch.int32, device=cuda_device)
+        N.check(native_lib.glsdet_batched_nms_ids_batch(bx.data_ptr(), sc.data_ptr(), lb.data_ptr(), ids.data_ptr(), float(nc - 1), nc, B, k,
+                                                        0.6, STRATEGIES[strategy], ws.data_ptr(), nbytes, keep.data_ptr(), cnt.data_ptr(),
+                                                        N.stream_ptr()), "glsdet_batched_nms_ids_batch")
+        for b in range(B):
+            want = batched_nms(bx[b], sc[b], lb[b], 0.6, strategy)
+            assert torch.equal(keep[b, :int(cnt[b])].long(), want), (strategy, b)
