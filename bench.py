@@ -131,7 +131,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop_evt.wait(0.005)
+            self._stop_evt.wait(float(os.environ.get("GLSDET_BENCH_CLOCK_INTERVAL", "0.005")))
 
     def stop(self):
         self._stop_evt.set()
@@ -372,6 +372,9 @@ def run_native_arm(args):
         graph_kernels = lib.glsdet_launch_count() - n_before
         torch.cuda.synchronize()
         launches0 = lib.glsdet_launch_count()
+    use_gather = gather is not None and not os.environ.get("GLSDET_BENCH_NO_GATHER")
+    packed = None          # payload of the previous step, its collective not issued yet
+    waiting = None         # collective in flight
     for s in range(n_micro):
         plan.load_features(feats)
         seg[s][0].record(stream)
@@ -382,9 +385,27 @@ def run_native_arm(args):
             plan.run_neck()
             plan.run_head("det")
             seg[s][1].record(stream)
+            if packed is not None:
+                # the gather of step s-1 is issued HERE: ordered after this step's conv segment, it overlaps the small-grid
+                # post-processing kernels instead of taking an SM away from a persistent conv kernel
+                if waiting is not None:
+                    gather.result(waiting)
+                gather.launch(packed)
+                waiting, packed = packed, None
             det, cnt = nms.launch(plan.pred, CONF_THRES, NMS_THRES, "auto_cuda", cls_logits=plan.det_cls_logits)
         seg[s][2].record(stream)
-        gather_step(det, cnt, last=(s == n_micro - 1))
+        if use_gather:
+            if packed is not None:      # graph mode: no split point inside the step
+                if waiting is not None:
+                    gather.result(waiting)
+                gather.launch(packed)
+                waiting = packed
+            packed = gather.pack(det, cnt)
+    if use_gather:
+        if waiting is not None:
+            gather.result(waiting)
+        gather.launch(packed)
+        gather.result(packed)
     ev[1].record(stream)
     sync_all()
     launches = lib.glsdet_launch_count() - launches0

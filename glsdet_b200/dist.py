@@ -118,7 +118,8 @@ class DetectionGather:
         out[:self.hdr].view(-1)[:self.batch] = cnt.to(out.dtype)
         out.index_copy_(0, idx.reshape(-1), det[:, :r].reshape(-1, 7))
 
-    def submit(self, det: torch.Tensor, count: torch.Tensor) -> int:
+    def pack(self, det: torch.Tensor, count: torch.Tensor) -> int:
+        """Build the payload of a step on the current stream; the collective is issued by `launch(slot)`."""
         slot = self.n & 1
         self.n += 1
         if self.work[slot] is not None:   # the buffer pair is reused: its previous gather must have been consumed
@@ -134,6 +135,13 @@ class DetectionGather:
             _pack(det, count, self.rows, out=self.send[slot])
         else:
             self._pack_rows(det, count, self.send[slot])
+        return slot
+
+    def launch(self, slot: int) -> None:
+        """Issue the collective of a packed slot.  It is ordered after everything enqueued on the current stream so far, so
+        WHERE this is called decides what it overlaps: the persistent conv kernels hold every SM (one CTA each), and an NCCL
+        kernel that takes an SM away makes one of them wait a full CTA lifetime - call it before the (small-grid)
+        post-processing kernels of the next step rather than before its conv segment."""
         if self.world == 1:
             self.recv[slot][0].copy_(self.send[slot])
         elif self.dst is None:
@@ -142,6 +150,10 @@ class DetectionGather:
         else:
             gl = list(self.recv[slot].unbind(0)) if self.rank == self.dst else None
             self.work[slot] = dist.gather(self.send[slot], gl, dst=self.dst, group=self.group, async_op=True)
+
+    def submit(self, det: torch.Tensor, count: torch.Tensor) -> int:
+        slot = self.pack(det, count)
+        self.launch(slot)
         return slot
 
     def result(self, slot: int) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
