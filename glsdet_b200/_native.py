@@ -164,7 +164,8 @@ SIGNATURES = {
                                     C.c_float, C.c_float, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "glsdet_gfl_select": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
-                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "glsdet_gfl_select_scratch_ints": (C.c_int64, [C.c_int32]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "glsdet_focus_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -1331,6 +1331,24 @@ int conv_geometry(const glsdet_conv_desc* d, ConvGeom* g) {
       g->block_n = 128;
     }
   }
+  {
+    // Small 3x3 launches (MP-Det towers on the 25 x 42 .. 7 x 11 levels: 8 .. 96 tiles of K = 2304) leave most SMs idle while
+    // each CTA issues 36 k-steps of 128 x 256 MMAs (~10 us at the full tensor rate, 24 us measured per launch).  Narrower N
+    // blocks spread the same MMAs over more SMs.  GLSDET_CONV_SMALL_SPLIT=0 disables it.
+    const char* e = getenv("GLSDET_CONV_SMALL_SPLIT");
+    if (!(e && e[0] == '0') && d->ksize == 3 && d->stride == 1 && d->ksize_w == 0 && d->weight_batch_stride == 0 &&
+        d->patch_mode == 0 && d->pred_weight == nullptr && d->src1 == nullptr && (d->out_channels % 64) == 0 &&
+        g->n_blocks == 1 && g->block_n >= 128) {
+      const int64_t tiles = static_cast<int64_t>(d->batch) * ((d->height + 7) / 8) * ((d->width + 15) / 16);
+      const int sms = device_sm_count();
+      int bn = g->block_n;
+      while (bn > 64 && (bn % 2) == 0 && ((bn / 2) % 32) == 0 && tiles * (d->out_channels / (bn / 2)) <= sms) bn /= 2;
+      if (bn != g->block_n && (d->out_channels % bn) == 0) {
+        g->block_n = bn;
+        g->n_blocks = d->out_channels / bn;
+      }
+    }
+  }
   g->n_pad = g->n_blocks * g->block_n;
   g->k_pad = g->taps * (g->chunks0 + g->chunks1) * kChunkK;
   g->Ho = d->height / d->stride;

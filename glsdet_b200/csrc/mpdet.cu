@@ -11,12 +11,17 @@
 
 namespace glsdet {
 
-constexpr int kGnSlabs = 16;
+constexpr int kGnSlabs = 64;   // pixel slabs per image: 64 x batch CTAs read the map (16 left a 69 MB map to 128 CTAs: 1.7 TB/s)
 
 // ---------------------------------------------------------------------------------------------- GroupNorm + ReLU
-// stage 1: per (image, slab of pixels) channel sums and sums of squares, fixed order (deterministic)
-__global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ scratch,
-                                                         int HW, int C, int ld) {
+// stage 1: per (image, slab of pixels) channel sums and sums of squares, fixed order (deterministic).
+// stage 2 runs in the last CTA of an image to finish (arrival counter in `counters`, left at zero): group statistics ->
+// per (image, channel) scale a and shift s with  y = relu(x * a + s).  One thread per channel sums its slab partials in
+// fixed order, then the channels of a group are added in fixed order.  (A separate finalize launch cost 11 us x 40.)
+__global__ void __launch_bounds__(256, 4) gn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ scratch,
+                                                         int HW, int C, int ld, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ ab,
+                                                         int* __restrict__ counters, int groups, float eps) {
   pdl_prologue();
   const int slab = blockIdx.x, b = blockIdx.y;
   const int per = (HW + kGnSlabs - 1) / kGnSlabs;
@@ -38,7 +43,8 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
       }
     }
   }
-  extern __shared__ float red[];   // [lanes][2][C]
+  extern __shared__ __align__(16) unsigned char gn_smem[];
+  float* red = reinterpret_cast<float*>(gn_smem);   // [lanes][2][C]
   if (pl < lanes) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -53,33 +59,37 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const __nv_bfloat16* __
     for (int l = 0; l < lanes; ++l) t += red[(l * 2 + which) * C + ch];
     scratch[((static_cast<int64_t>(b) * kGnSlabs + slab) * 2 + which) * C + ch] = t;
   }
-}
-
-// stage 2: group statistics -> per (image, channel) scale a and shift s with  y = relu(x * a + s).
-// One thread per channel sums its slab partials (16 independent loads; round 1 walked slabs x channels of a group
-// serially in one thread: 256 dependent loads, 20 us per launch), then the channels of a group are added in fixed order.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restrict__ scratch, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, float* __restrict__ ab, int HW, int C,
-                                                          int groups, float eps) {
-  pdl_prologue();
-  const int b = blockIdx.x;
+  __shared__ int last_s;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_s = (atomicAdd(&counters[b], 1) == kGnSlabs - 1);
+  __syncthreads();
+  if (!last_s) return;
+  __threadfence();
   const int cpg = C / groups;
-  extern __shared__ double gn_fin[];   // [2][C] channel sums
+  double* fin = reinterpret_cast<double*>(gn_smem);   // [2][C] channel sums
   __shared__ float mean_s[64], rstd_s[64];
   for (int c = threadIdx.x; c < C; c += 256) {
+    // 16 slabs (32 loads) in flight per batch: the loads, not the adds, pace this tail (one dependent load at a time took
+    // 11 us), while 64 at once cost the streaming loop above its occupancy (128 registers)
     double sm = 0.0, sq = 0.0;
+    for (int k0 = 0; k0 < kGnSlabs; k0 += 16) {
+      float ps[16], pq[16];
 #pragma unroll
-    for (int k = 0; k < kGnSlabs; ++k) {
-      sm += scratch[((static_cast<int64_t>(b) * kGnSlabs + k) * 2 + 0) * C + c];
-      sq += scratch[((static_cast<int64_t>(b) * kGnSlabs + k) * 2 + 1) * C + c];
+      for (int k = 0; k < 16; ++k) {
+        ps[k] = __ldcg(&scratch[((static_cast<int64_t>(b) * kGnSlabs + k0 + k) * 2 + 0) * C + c]);
+        pq[k] = __ldcg(&scratch[((static_cast<int64_t>(b) * kGnSlabs + k0 + k) * 2 + 1) * C + c]);
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { sm += ps[k]; sq += pq[k]; }
     }
-    gn_fin[c] = sm;
-    gn_fin[C + c] = sq;
+    fin[c] = sm;
+    fin[C + c] = sq;
   }
   __syncthreads();
   for (int g = threadIdx.x; g < groups; g += 256) {
     double sm = 0.0, sq = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { sm += gn_fin[c]; sq += gn_fin[C + c]; }
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { sm += fin[c]; sq += fin[C + c]; }
     const double n = static_cast<double>(HW) * cpg;
     const double m = sm / n;
     const double var = fmax(sq / n - m * m, 0.0);
@@ -93,31 +103,39 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float* __restric
     ab[(static_cast<int64_t>(b) * 2 + 0) * C + c] = a;
     ab[(static_cast<int64_t>(b) * 2 + 1) * C + c] = beta[c] - mean_s[g] * a;
   }
+  if (threadIdx.x == 0) counters[b] = 0;
 }
 
-// stage 3: in place  x = relu(x * a[b][c] + s[b][c])
+// stage 3: in place  x = relu(x * a[b][c] + s[b][c]).  A CTA owns one pixel slab of one image, so a thread keeps the
+// scale / shift of its eight channels in registers and streams 16-byte vectors (round 1 re-read 16 scalars per vector
+// through L1: 1.9 TB/s on the 100 x 168 level).
 __global__ void __launch_bounds__(256) gn_apply_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ ab, int HW, int C,
-                                                       int ld, int64_t total) {
+                                                       int ld) {
   pdl_prologue();
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  const int slab = blockIdx.x, b = blockIdx.y;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = slab * per, p1 = min(HW, p0 + per);
   const int nvec = C >> 3;
-  const int v = static_cast<int>(i % nvec);
-  const int64_t pix = i / nvec;
-  const int b = static_cast<int>(pix / HW);
-  uint4* ptr = reinterpret_cast<uint4*>(x + pix * ld) + v;
-  const uint4 u = *ptr;
-  const float* a = ab + (static_cast<int64_t>(b) * 2) * C + v * 8;
-  const float* s = a + C;
-  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  uint32_t o[4];
+  const int lanes = 256 / nvec;                       // pixels in flight per iteration
+  const int v = threadIdx.x % nvec, pl = threadIdx.x / nvec;
+  if (pl >= lanes) return;
+  float a[8], sh[8];
+  const float* ap = ab + (static_cast<int64_t>(b) * 2) * C + v * 8;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float lo = fmaxf(fmaf(__uint_as_float(w[k] << 16), a[2 * k], s[2 * k]), 0.0f);
-    const float hi = fmaxf(fmaf(__uint_as_float(w[k] & 0xFFFF0000u), a[2 * k + 1], s[2 * k + 1]), 0.0f);
-    o[k] = pack_bf16x2(lo, hi);
+  for (int k = 0; k < 8; ++k) { a[k] = ap[k]; sh[k] = ap[C + k]; }
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    uint4* ptr = reinterpret_cast<uint4*>(x + (static_cast<int64_t>(b) * HW + p) * ld) + v;
+    const uint4 u = *ptr;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float lo = fmaxf(fmaf(__uint_as_float(w[k] << 16), a[2 * k], sh[2 * k]), 0.0f);
+      const float hi = fmaxf(fmaf(__uint_as_float(w[k] & 0xFFFF0000u), a[2 * k + 1], sh[2 * k + 1]), 0.0f);
+      o[k] = pack_bf16x2(lo, hi);
+    }
+    *ptr = make_uint4(o[0], o[1], o[2], o[3]);
   }
-  *ptr = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 // ---------------------------------------------------------------------------------------------- proxy classification
@@ -223,6 +241,12 @@ __global__ void __launch_bounds__(256) proxy_aggregate_kernel(const __nv_bfloat1
   const int nvec = C >> 3;   // 16-byte vectors per pixel
   for (int64_t pix = static_cast<int64_t>(blockIdx.x) * wpb + warp; pix < total_pix; pix += static_cast<int64_t>(gridDim.x) * wpb) {
     const uint4* f = reinterpret_cast<const uint4*>(feat + pix * C);
+    // the class lanes fetch their similarities first, so that both loads of a pixel are in flight together
+    const float* sp = sims + pix * sims_ld;
+    const int j0 = lane < nc ? cls_s[lane] : 0, j1 = lane < nc ? cls_s[lane + 1] : 0;
+    float sv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sv[k] = (j0 + k < j1) ? __ldg(sp + j0 + k) : 0.0f;
     float nn = 0.0f;
     for (int v = lane; v < nvec; v += 32) {
       const uint4 u = __ldg(f + v);
@@ -238,12 +262,22 @@ __global__ void __launch_bounds__(256) proxy_aggregate_kernel(const __nv_bfloat1
     for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
     const float inv = 1.0f / fmaxf(sqrtf(nn), 1e-12f);   // F.normalize eps
     if (lane < nc) {   // lane c = class c: softmax(gamma s)-weighted sum of its proxies' similarities (mp_head.py:112-118)
-      const float* sp = sims + pix * sims_ld;
-      const int j0 = cls_s[lane], j1 = cls_s[lane + 1];
       float mx = -1e30f;
-      for (int j = j0; j < j1; ++j) mx = fmaxf(mx, sp[j] * inv * gamma);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (j0 + k < j1) mx = fmaxf(mx, sv[k] * inv * gamma);
+      for (int j = j0 + 8; j < j1; ++j) mx = fmaxf(mx, sp[j] * inv * gamma);
       float den = 0.0f, num = 0.0f;
-      for (int j = j0; j < j1; ++j) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (j0 + k < j1) {
+          const float sj = sv[k] * inv;
+          const float e = expf(sj * gamma - mx);
+          den += e;
+          num += e * sj;
+        }
+      }
+      for (int j = j0 + 8; j < j1; ++j) {
         const float sj = sp[j] * inv;
         const float e = expf(sj * gamma - mx);
         den += e;
@@ -292,84 +326,142 @@ __global__ void __launch_bounds__(256) gfl_decode_kernel(const float* __restrict
 // follows the candidate count.
 constexpr int kSelBins = 2048;   // histogram of the score bits above the threshold, 2^15 ulps (2^-8 relative) per bin
 constexpr int kSelCap = 4096;    // candidates sorted in shared memory
-__global__ void __launch_bounds__(1024) gfl_select_kernel(const float* __restrict__ rows, int rows_ld, int64_t rows_bs,
-                                                          const float* __restrict__ boxes, int64_t boxes_bs, int row0, int A_l,
-                                                          int nc, float thr, int topk, unsigned long long* __restrict__ keys,
-                                                          int64_t keys_bs, int* __restrict__ cand_count, float* __restrict__ cboxes,
-                                                          float* __restrict__ cscores, float* __restrict__ clabels, int cap) {
-  // Only the best `topk` of up to anchors x classes candidates are needed, so the full sort of round 1 (a single-CTA
-  // bitonic network over up to 2^18 keys in global memory: 1.9 ms per level, half of an MP-Det step) is replaced by a
-  // selection: pass 1 histograms the score bits, the bin b* in which the topk-th best score lies is found, pass 2 collects
-  // the candidates of the bins >= b* (topk plus the rest of one bin), and only those are sorted - in shared memory.
-  // Same keys as before ((~score bits) << 32 | flattened index), so the result is identical.
+constexpr int kSelScratch = kSelBins + 8;   // ints per image: histogram + collected-count
+
+// Only the best `topk` of up to anchors x classes candidates are needed, so the full sort of round 1 (a single-CTA bitonic
+// network over up to 2^18 keys in global memory: 1.9 ms per level, half of an MP-Det step) is replaced by a selection in
+// three small kernels: (1) histogram of the score bits over the whole grid, (2) every CTA finds the bin b* in which the
+// topk-th best score lies and collects the candidates of the bins >= b* (topk plus the rest of one bin), (3) one CTA per
+// image sorts only those - in shared memory - and appends the best topk to the image's candidate list.
+// Same keys as before ((~score bits) << 32 | flattened index), so the result is identical.
+__device__ __forceinline__ int sel_bin(float sc, uint32_t thr_bits) {
+  return min(kSelBins - 1, static_cast<int>((__float_as_uint(sc) - thr_bits) >> 15));
+}
+
+__global__ void __launch_bounds__(256) gfl_select_hist_kernel(const float* __restrict__ rows, int rows_ld, int64_t rows_bs, int row0,
+                                                              int A_l, int nc, float thr, int* __restrict__ scratch) {
   pdl_prologue();
-  const int b = blockIdx.x;
   __shared__ int hist[kSelBins];
-  __shared__ unsigned long long sk[kSelCap];
-  __shared__ int n_s, base_s, bstar_s, m_s;
+  const int b = blockIdx.y;
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hist[i] = 0;
-  if (threadIdx.x == 0) { n_s = 0; m_s = 0; }
   __syncthreads();
+  const float* rb = rows + b * rows_bs + static_cast<int64_t>(row0) * rows_ld;
+  const int total = A_l * nc;
+  const uint32_t thr_bits = __float_as_uint(fmaxf(thr, 0.0f));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int a = i / nc, c = i - a * nc;
+    const float sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
+    if (sc > thr) atomicAdd(&hist[sel_bin(sc, thr_bits)], 1);
+  }
+  __syncthreads();
+  int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x)
+    if (hist[i]) atomicAdd(&gh[i], hist[i]);
+}
+
+// one warp: (b*, candidates in bins >= b*... not needed, total candidate count) from an image's histogram
+__device__ __forceinline__ void sel_threshold_bin(const int* hist, int topk, int lane, int* bstar_out, int* total_out) {
+  int cum = 0, bstar = 0;
+  bool found = false;
+  for (int hi = kSelBins; hi > 0; hi -= 64) {
+    const int b0 = hi - 1 - 2 * lane;          // lanes own bins (b0, b0 - 1), descending
+    const int h0 = hist[b0], h1 = hist[b0 - 1];
+    int incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int before = cum + incl - h0 - h1;     // candidates in strictly better bins than b0
+    if (!found) {
+      const bool hit0 = before + h0 >= topk, hit1 = before + h0 + h1 >= topk;
+      const unsigned m = __ballot_sync(0xffffffffu, hit0 || hit1);
+      if (m) {
+        const int l = __ffs(m) - 1;
+        bstar = __shfl_sync(0xffffffffu, hit0 ? b0 : b0 - 1, l);
+        found = true;
+      }
+    }
+    cum += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  *bstar_out = found ? bstar : 0;
+  *total_out = cum;
+}
+
+__global__ void __launch_bounds__(256) gfl_select_collect_kernel(const float* __restrict__ rows, int rows_ld, int64_t rows_bs, int row0,
+                                                                 int A_l, int nc, float thr, int topk, int* __restrict__ scratch,
+                                                                 unsigned long long* __restrict__ keys, int64_t keys_bs) {
+  pdl_prologue();
+  __shared__ int bstar_s;
+  __shared__ int hs[kSelBins];   // the scan walks the bins serially: from shared memory (25 us of dependent global loads otherwise)
+  const int b = blockIdx.y;
+  int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = __ldcg(&gh[i]);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int bs, tot;
+    sel_threshold_bin(hs, topk, static_cast<int>(threadIdx.x), &bs, &tot);
+    if (threadIdx.x == 0) bstar_s = bs;
+  }
+  __syncthreads();
+  const int bstar = bstar_s;
   unsigned long long* kb = keys + b * keys_bs;
   const float* rb = rows + b * rows_bs + static_cast<int64_t>(row0) * rows_ld;
   const int total = A_l * nc;
   const uint32_t thr_bits = __float_as_uint(fmaxf(thr, 0.0f));
-  auto bin_of = [&](float sc) { return min(kSelBins - 1, static_cast<int>((__float_as_uint(sc) - thr_bits) >> 15)); };
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int a = i / nc, c = i - a * nc;
-    const float sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
-    if (sc > thr) atomicAdd(&hist[bin_of(sc)], 1);
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {   // one warp walks the histogram from the best bin down, 64 bins per step
-    int cum = 0, bstar = 0, ntot = 0;
-    bool found = false;
-    for (int hi = kSelBins; hi > 0; hi -= 64) {
-      const int b0 = hi - 1 - 2 * static_cast<int>(threadIdx.x);          // lanes own bins (b0, b0 - 1), descending
-      const int h0 = hist[b0], h1 = hist[b0 - 1];
-      int incl = h0 + h1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (static_cast<int>(threadIdx.x) >= o) incl += v;
-      }
-      const int before = cum + incl - h0 - h1;     // candidates in strictly better bins than b0
-      if (!found) {
-        const bool hit0 = before + h0 >= topk, hit1 = before + h0 + h1 >= topk;
-        const unsigned m = __ballot_sync(0xffffffffu, hit0 || hit1);
-        if (m) {
-          const int l = __ffs(m) - 1;
-          const int bs = __shfl_sync(0xffffffffu, hit0 ? b0 : b0 - 1, l);
-          bstar = bs;
-          found = true;
-        }
-      }
-      cum += __shfl_sync(0xffffffffu, incl, 31);
+  const int lane = threadIdx.x & 31;
+  const int rounded = (total + 31) & ~31;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+    bool hit = false;
+    float sc = 0.0f;
+    if (i < total) {
+      const int a = i / nc, c = i - a * nc;
+      sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
+      hit = sc > thr && sel_bin(sc, thr_bits) >= bstar;
     }
-    ntot = cum;
-    if (threadIdx.x == 0) { n_s = ntot; bstar_s = found ? bstar : 0; }
-  }
-  __syncthreads();
-  const int n = n_s, bstar = bstar_s;
-  const int take = min(n, topk);
-  // pass 2: collect the candidates of the bins >= b*
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int a = i / nc, c = i - a * nc;
-    const float sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
-    if (sc > thr && bin_of(sc) >= bstar) {
-      const int pos = atomicAdd(&m_s, 1);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&gh[kSelBins], __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
       // descending score, ascending index: key = (~score_bits << 32) | index, sorted ascending
-      const unsigned long long key = (static_cast<unsigned long long>(~__float_as_uint(sc)) << 32) | static_cast<unsigned int>(i);
-      if (pos < kSelCap) sk[pos] = key;
-      kb[pos] = key;      // global copy: only read when the collected set does not fit shared memory
+      if (hit) kb[base + __popc(m & ((1u << lane) - 1u))] =
+          (static_cast<unsigned long long>(~__float_as_uint(sc)) << 32) | static_cast<unsigned int>(i);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) gfl_select_sort_kernel(const float* __restrict__ boxes, int64_t boxes_bs, int row0, int nc,
+                                                               int topk, int* __restrict__ scratch, unsigned long long* __restrict__ keys,
+                                                               int64_t keys_bs, int* __restrict__ cand_count, float* __restrict__ cboxes,
+                                                               float* __restrict__ cscores, float* __restrict__ clabels, int cap) {
+  pdl_prologue();
+  const int b = blockIdx.x;
+  __shared__ unsigned long long sk[kSelCap];
+  __shared__ int base_s, n_s;
+  int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
+  unsigned long long* kb = keys + b * keys_bs;
+  {
+    int* hs = reinterpret_cast<int*>(sk);   // staged histogram (the sort buffer is not in use yet)
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = __ldcg(&gh[i]);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int bs, tot;
+      sel_threshold_bin(hs, topk, static_cast<int>(threadIdx.x), &bs, &tot);
+      if (threadIdx.x == 0) n_s = tot;
     }
   }
   __syncthreads();
-  const int m = m_s;
+  const int n = n_s, m = __ldcg(&gh[kSelBins]);
+  const int take = min(n, topk);
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSelScratch; i += blockDim.x) gh[i] = 0;   // clean for the next level / call
   int P = 1;
   while (P < m) P <<= 1;
   const bool in_smem = m <= kSelCap;
   unsigned long long* sv = in_smem ? sk : kb;
+  if (in_smem)
+    for (int i = threadIdx.x; i < m; i += blockDim.x) sk[i] = kb[i];
   for (int i = m + threadIdx.x; i < P; i += blockDim.x) sv[i] = ~0ull;
   __syncthreads();
   for (int k = 2; k <= P; k <<= 1) {
@@ -411,23 +503,23 @@ extern "C" int glsdet_group_norm_relu(void* x, int32_t batch, int32_t hw, int32_
   GLSDET_REQUIRE(groups > 0 && groups <= 64 && (channels % groups) == 0, "group_norm_relu: bad group count");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int lanes = 256 / (channels / 8);
-  const size_t smem = static_cast<size_t>(lanes) * 2 * channels * sizeof(float);
+  size_t smem = static_cast<size_t>(lanes) * 2 * channels * sizeof(float);
+  if (smem < static_cast<size_t>(2 * channels) * sizeof(double)) smem = static_cast<size_t>(2 * channels) * sizeof(double);
   GLSDET_REQUIRE(smem <= 48 * 1024, "group_norm_relu: too many channels for the reduction buffer");
   float* ab = scratch + static_cast<int64_t>(batch) * kGnSlabs * 2 * channels;
+  int* counters = reinterpret_cast<int*>(ab + static_cast<int64_t>(batch) * 2 * channels);
   launch_pdl(gn_partial_kernel, dim3(kGnSlabs, batch), dim3(256), smem, st, reinterpret_cast<const __nv_bfloat16*>(x), scratch, hw,
-             channels, x_ld);
+             channels, x_ld, gamma, beta, ab, counters, groups, eps);
   if (int rc = count_launch("gn_partial_kernel")) return rc;
-  launch_pdl(gn_finalize_kernel, dim3(batch), dim3(256), static_cast<size_t>(2 * channels) * sizeof(double), st, scratch, gamma, beta,
-             ab, hw, channels, groups, eps);
-  if (int rc = count_launch("gn_finalize_kernel")) return rc;
-  const int64_t total = static_cast<int64_t>(batch) * hw * (channels / 8);
-  launch_pdl(gn_apply_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<__nv_bfloat16*>(x),
-             ab, hw, channels, x_ld, total);
+  const int pix_per_cta = 256 / (channels / 8) * 16;     // 16 iterations per thread
+  const int slabs = (hw + pix_per_cta - 1) / pix_per_cta;
+  launch_pdl(gn_apply_kernel, dim3(slabs < 1 ? 1 : (slabs > 1024 ? 1024 : slabs), batch), dim3(256), 0, st,
+             reinterpret_cast<__nv_bfloat16*>(x), ab, hw, channels, x_ld);
   return count_launch("gn_apply_kernel");
 }
 
 extern "C" int64_t glsdet_group_norm_scratch_floats(int32_t batch, int32_t channels) {
-  return static_cast<int64_t>(batch) * (kGnSlabs * 2 + 2) * channels;
+  return static_cast<int64_t>(batch) * (kGnSlabs * 2 + 2) * channels + batch;   // partials, scale / shift, arrival counters
 }
 
 extern "C" int glsdet_proxy_scores(const float* feat, const float* centers, const int32_t* cls_start, int32_t num_classes,
@@ -458,7 +550,13 @@ extern "C" int glsdet_proxy_aggregate(const void* feat, const float* sims, int32
                  "channels a multiple of 8");
   const int64_t total = static_cast<int64_t>(batch) * hw;
   const int64_t want = (total + 7) / 8;
-  const int64_t cap_ctas = 8ll * device_sm_count();
+  static int per_sm = 0;   // resident CTAs per SM: a persistent grid larger than that runs a second, mostly empty wave
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, proxy_aggregate_kernel, 256, 0) != cudaSuccess || n <= 0) n = 4;
+    per_sm = n;
+  }
+  const int64_t cap_ctas = static_cast<int64_t>(per_sm) * device_sm_count();
   launch_pdl(proxy_aggregate_kernel, dim3(static_cast<unsigned>(want < cap_ctas ? want : cap_ctas)), dim3(256), 0,
              static_cast<cudaStream_t>(stream), reinterpret_cast<const __nv_bfloat16*>(feat), sims, sims_ld, cls_start, num_classes,
              channels, hw, total, gamma, rows, rows_ld, rows_batch_stride, row0);
@@ -476,18 +574,32 @@ extern "C" int glsdet_gfl_decode(const float* reg, int32_t reg_ld, int32_t bins,
   return count_launch("gfl_decode_kernel");
 }
 
+extern "C" int64_t glsdet_gfl_select_scratch_ints(int32_t batch) { return static_cast<int64_t>(batch) * kSelScratch; }
+
 extern "C" int glsdet_gfl_select(const float* rows, int32_t rows_ld, int64_t rows_batch_stride, const float* boxes,
                                  int64_t boxes_batch_stride, int32_t row0, int32_t level_anchors, int32_t num_classes,
                                  float score_thr, int32_t topk, int32_t batch, void* keys, int64_t keys_batch_stride,
                                  int32_t* cand_count, float* cand_boxes, float* cand_scores, float* cand_labels,
-                                 int32_t cand_capacity, void* stream) {
-  GLSDET_REQUIRE(rows && boxes && keys && cand_count && cand_boxes && cand_scores && cand_labels, "gfl_select: null pointer");
+                                 int32_t cand_capacity, int32_t* scratch, void* stream) {
+  GLSDET_REQUIRE(rows && boxes && keys && cand_count && cand_boxes && cand_scores && cand_labels && scratch, "gfl_select: null pointer");
   GLSDET_REQUIRE(batch > 0 && level_anchors > 0 && num_classes > 0 && topk > 0 && cand_capacity > 0, "gfl_select: bad sizes");
   int64_t need = 1;
   while (need < static_cast<int64_t>(level_anchors) * num_classes) need <<= 1;
   GLSDET_REQUIRE(keys_batch_stride >= need, "gfl_select: key buffer too small (needs the next power of two of anchors * classes)");
-  launch_pdl(gfl_select_kernel, dim3(batch), dim3(1024), 0, static_cast<cudaStream_t>(stream), rows, rows_ld, rows_batch_stride, boxes,
-             boxes_batch_stride, row0, level_anchors, num_classes, score_thr, topk, reinterpret_cast<unsigned long long*>(keys),
-             keys_batch_stride, cand_count, cand_boxes, cand_scores, cand_labels, cand_capacity);
-  return count_launch("gfl_select_kernel");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = static_cast<int64_t>(level_anchors) * num_classes;
+  int chunks = static_cast<int>((total + 256 * 8 - 1) / (256 * 8));
+  const int cap_chunks = 2 * device_sm_count() / batch + 1;
+  if (chunks > cap_chunks) chunks = cap_chunks;
+  if (chunks < 1) chunks = 1;
+  launch_pdl(gfl_select_hist_kernel, dim3(chunks, batch), dim3(256), 0, st, rows, rows_ld, rows_batch_stride, row0, level_anchors,
+             num_classes, score_thr, scratch);
+  if (int rc = count_launch("gfl_select_hist_kernel")) return rc;
+  launch_pdl(gfl_select_collect_kernel, dim3(chunks, batch), dim3(256), 0, st, rows, rows_ld, rows_batch_stride, row0, level_anchors,
+             num_classes, score_thr, topk, scratch, reinterpret_cast<unsigned long long*>(keys), keys_batch_stride);
+  if (int rc = count_launch("gfl_select_collect_kernel")) return rc;
+  launch_pdl(gfl_select_sort_kernel, dim3(batch), dim3(1024), 0, st, boxes, boxes_batch_stride, row0, num_classes, topk, scratch,
+             reinterpret_cast<unsigned long long*>(keys), keys_batch_stride, cand_count, cand_boxes, cand_scores, cand_labels,
+             cand_capacity);
+  return count_launch("gfl_select_sort_kernel");
 }

@@ -248,7 +248,7 @@ class _MPHeadPlan:
         self.row0 = [sum(h * w for h, w in self.hw[:l]) for l in range(len(feats))]
         self.rows = torch.empty((B, self.A, nc), dtype=torch.float32, device=dev)     # raw class scores
         self.boxes = torch.empty((B, self.A, 4), dtype=torch.float32, device=dev)     # decoded xyxy
-        self.gn_scratch = torch.empty(int(lib.glsdet_group_norm_scratch_floats(B, fc)), dtype=torch.float32, device=dev)
+        self.gn_scratch = torch.zeros(int(lib.glsdet_group_norm_scratch_floats(B, fc)), dtype=torch.float32, device=dev)
         centers = torch.nn.functional.normalize(m.proxies.detach().float(), p=2, dim=1).contiguous()
         starts = [0]
         for n in m.proxies_list:
@@ -297,27 +297,68 @@ class _MPHeadPlan:
         self.cap = 0
         self.keys = None
 
+    # The five levels are independent until the candidates are selected.  The 100 x 168 level fills the device; the three
+    # coarse levels are chains of ~30 launches of <= 96 CTAs that are bound by launch and pipeline-fill latency, so they run
+    # on side streams underneath the fine levels (GLSDET_MPDET_STREAMS=0 puts everything on the caller's stream).
+    _LEVEL_STREAM = (0, 1, 2, 2, 2)
+
+    def _streams(self):
+        if self.__dict__.get("_side") is None:
+            import os
+            on = os.environ.get("GLSDET_MPDET_STREAMS", "1") != "0"
+            self._side = [torch.cuda.Stream(self.dev) for _ in range(2)] if on else []
+            self._fork = torch.cuda.Event()
+            self._join = [torch.cuda.Event() for _ in self._side]
+            n = int(self.lib.glsdet_group_norm_scratch_floats(self.B, self.m.feat_channels))
+            self._gn_scratch = [self.gn_scratch] + [torch.zeros(n, dtype=torch.float32, device=self.dev) for _ in self._side]
+        return self._side
+
     def run(self, feats, img_shape):
+        side = self._streams()
+        main = torch.cuda.current_stream()
+        if not side:
+            for l in range(len(self.levels)):
+                self._run_level(l, feats, img_shape, self.gn_scratch)
+            return
+        self._fork.record(main)
+        order = sorted(range(len(self.levels)), key=lambda l: -self._LEVEL_STREAM[min(l, 4)])
+        used = set()
+        for l in order:               # coarse chains are issued first: they start while the host still issues the fine ones
+            si = self._LEVEL_STREAM[min(l, 4)]
+            if si == 0:
+                self._run_level(l, feats, img_shape, self._gn_scratch[0])
+                continue
+            st = side[si - 1]
+            if si not in used:
+                st.wait_event(self._fork)
+                used.add(si)
+            with torch.cuda.stream(st):
+                self._run_level(l, feats, img_shape, self._gn_scratch[si])
+        for si in sorted(used):
+            self._join[si - 1].record(side[si - 1])
+            main.wait_event(self._join[si - 1])
+
+    def _run_level(self, l, feats, img_shape, gn_scratch):
         m, lib, st = self.m, self.lib, N.stream_ptr(None)
         nc, bins = m.num_classes, m.reg_max + 1
-        for l, lv in enumerate(self.levels):
-            nchw_to_nhwc(feats[l].float().contiguous(), View(lv["x"]))
-            h, w = self.hw[l]
-            for kind, op in lv["ops"]:
-                if kind == "conv":
-                    op.launch()
-                else:
-                    buf, g, b_, eps = op
-                    N.check(lib.glsdet_group_norm_relu(buf.data_ptr(), self.B, h * w, buf.shape[3], buf.shape[3], 32,
-                                                       g.data_ptr(), b_.data_ptr(), eps, self.gn_scratch.data_ptr(), st),
-                            "glsdet_group_norm_relu")
-            N.check(lib.glsdet_proxy_aggregate(lv["feat16"].data_ptr(), lv["sims"].data_ptr(), self.n_prox_pad,
-                                               self.cls_start.data_ptr(), nc, m.feat_channels, self.B, h * w, m.gamma,
-                                               self.rows.data_ptr(), nc, self.A * nc, self.row0[l], st), "glsdet_proxy_aggregate")
-            if img_shape is not None:
-                N.check(lib.glsdet_gfl_decode(lv["reg32"].data_ptr(), self.reg_ld, bins, self.B, h, w, float(m.strides[l]),
-                                              float(img_shape[1]), float(img_shape[0]), self.boxes.data_ptr(), self.A * 4,
-                                              self.row0[l], st), "glsdet_gfl_decode")
+        lv = self.levels[l]
+        nchw_to_nhwc(feats[l].float().contiguous(), View(lv["x"]))
+        h, w = self.hw[l]
+        for kind, op in lv["ops"]:
+            if kind == "conv":
+                op.launch()
+            else:
+                buf, g, b_, eps = op
+                N.check(lib.glsdet_group_norm_relu(buf.data_ptr(), self.B, h * w, buf.shape[3], buf.shape[3], 32,
+                                                   g.data_ptr(), b_.data_ptr(), eps, gn_scratch.data_ptr(), st),
+                        "glsdet_group_norm_relu")
+        N.check(lib.glsdet_proxy_aggregate(lv["feat16"].data_ptr(), lv["sims"].data_ptr(), self.n_prox_pad,
+                                           self.cls_start.data_ptr(), nc, m.feat_channels, self.B, h * w, m.gamma,
+                                           self.rows.data_ptr(), nc, self.A * nc, self.row0[l], st), "glsdet_proxy_aggregate")
+        if img_shape is not None:
+            N.check(lib.glsdet_gfl_decode(lv["reg32"].data_ptr(), self.reg_ld, bins, self.B, h, w, float(m.strides[l]),
+                                          float(img_shape[1]), float(img_shape[0]), self.boxes.data_ptr(), self.A * 4,
+                                          self.row0[l], st), "glsdet_gfl_decode")
 
     def load_maps(self, cls_scores, bbox_preds, img_shape):
         """Given per-level NCHW maps (what MPHead.forward returned) -> the plan's score rows and decoded boxes."""
@@ -369,12 +410,13 @@ class _MPHeadPlan:
             self.cboxes = torch.empty((self.B, cap, 4), dtype=torch.float32, device=self.dev)
             self.cscores = torch.empty((self.B, cap), dtype=torch.float32, device=self.dev)
             self.clabels = torch.empty((self.B, cap), dtype=torch.float32, device=self.dev)
+            self.sel_scratch = torch.zeros(int(lib.glsdet_gfl_select_scratch_ints(self.B)), dtype=torch.int32, device=self.dev)
         self.ccount.zero_()
         for l, (h, w) in enumerate(self.hw):
             N.check(lib.glsdet_gfl_select(self.rows.data_ptr(), nc, self.A * nc, self.boxes.data_ptr(), self.A * 4, self.row0[l],
                                           h * w, nc, score_thr, nms_pre, self.B, self.keys.data_ptr(), kstride,
                                           self.ccount.data_ptr(), self.cboxes.data_ptr(), self.cscores.data_ptr(),
-                                          self.clabels.data_ptr(), cap, st), "glsdet_gfl_select")
+                                          self.clabels.data_ptr(), cap, self.sel_scratch.data_ptr(), st), "glsdet_gfl_select")
         # Post-processing without per-image host round trips: every image runs the mmcv-style batched NMS on its FULL
         # candidate buffer (cap rows); rows beyond the image's candidate count are padding - zero boxes (IoU 0 with
         # everything, they never suppress and never raise the coordinate-trick offset) with the lowest score, so they sort

@@ -302,7 +302,8 @@ int glsdet_spp_maxpool_f32(float* buf, int32_t batch, int32_t height, int32_t wi
 /*
  * MP-Det head pieces (yolox-ufp/mmdet/models/dense_heads/mp_head.py, gfl_head.py; BASELINE configs[2]).
  * glsdet_group_norm_relu: in place x = relu(GroupNorm(x)) on NHWC bf16 (the norm + activation of mmcv ConvModule in the
- *   shared towers, mp_head.py:46-62); scratch = glsdet_group_norm_scratch_floats(batch, channels) floats.
+ *   shared towers, mp_head.py:46-62); scratch = glsdet_group_norm_scratch_floats(batch, channels) floats,
+ *   zero-initialised once by the caller (arrival counters at its end; every call leaves them at zero).
  * glsdet_proxy_scores: MPHead.forward_proxy (mp_head.py:105-121): feat fp32 NHWC [batch*hw, channels], centers = the
  *   L2-normalised proxies fp32 [num_proxies, channels], cls_start[num_classes + 1] = first proxy of each class;
  *   rows[b][row0 + pixel][class] = gamma * sum_j softmax(gamma * sim)_j * sim_j  (raw class scores).
@@ -328,11 +329,13 @@ int glsdet_proxy_aggregate(const void* feat, const float* sims, int32_t sims_ld,
 int glsdet_gfl_decode(const float* reg, int32_t reg_ld, int32_t bins, int32_t batch, int32_t height, int32_t width,
                       float stride, float max_x, float max_y, float* boxes, int64_t boxes_batch_stride, int32_t row0,
                       void* stream);
+/* scratch: glsdet_gfl_select_scratch_ints(batch) int32, zero-initialised once by the caller (the call leaves it zeroed) */
+int64_t glsdet_gfl_select_scratch_ints(int32_t batch);
 int glsdet_gfl_select(const float* rows, int32_t rows_ld, int64_t rows_batch_stride, const float* boxes,
                       int64_t boxes_batch_stride, int32_t row0, int32_t level_anchors, int32_t num_classes,
                       float score_thr, int32_t topk, int32_t batch, void* keys, int64_t keys_batch_stride,
                       int32_t* cand_count, float* cand_boxes, float* cand_scores, float* cand_labels,
-                      int32_t cand_capacity, void* stream);
+                      int32_t cand_capacity, int32_t* scratch, void* stream);
 
 /*
  * SE gate of FFA (yolox-drone/models/ffa/ffa.py:5-20,77): partial[b][p][c] = sum over a slab of pixels of

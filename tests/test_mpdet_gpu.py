@@ -25,7 +25,7 @@ def test_group_norm_relu_kernel(native_lib, cuda_device):
         gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
         ref = torch.relu(F.group_norm(x.float(), 32, gamma, beta, eps=1e-5))
         buf = x.permute(0, 2, 3, 1).contiguous().to(dev)
-        scratch = torch.empty(int(native_lib.glsdet_group_norm_scratch_floats(B, C)), device=dev)
+        scratch = torch.zeros(int(native_lib.glsdet_group_norm_scratch_floats(B, C)), device=dev)
         dg, db = gamma.to(dev), beta.to(dev)
         N.check(native_lib.glsdet_group_norm_relu(buf.data_ptr(), B, H * W, C, C, 32, dg.data_ptr(), db.data_ptr(), 1e-5,
                                                   scratch.data_ptr(), None), "gn")

@@ -1,0 +1,14 @@
+set -x
+timeout 900 python -m pytest tests/test_mpdet_gpu.py tests/test_conv_gpu.py -m gpu -q -x 2>&1 | tail -5
+run() { # name, env...
+  name=$1; shift
+  env "$@" timeout 300 python bench.py --config cfg3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/cfg3_$name.json 2> gpurun_out/cfg3_$name.err; echo rc=$?; tail -2 gpurun_out/cfg3_$name.err
+  python -c "
+import json; d=json.load(open('gpurun_out/cfg3_$name.json')); print('$name', round(d['value'],1), round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1))"
+}
+run all A=1
+run nostream GLSDET_MPDET_STREAMS=0
+run nosplit GLSDET_CONV_SMALL_SPLIT=0
+run neither GLSDET_MPDET_STREAMS=0 GLSDET_CONV_SMALL_SPLIT=0
+GLSDET_MPDET_STREAMS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/mpdet_launches.csv python tools/profile_mpdet.py > gpurun_out/mpdet_ncu.log 2>&1; echo rc=$?
+python tools/launch_table.py gpurun_out/mpdet_launches.csv > gpurun_out/mpdet_launch_table.txt; grep -A16 "^total" gpurun_out/mpdet_launch_table.txt
