@@ -5,6 +5,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "../../include/glsdet_b200.h"
 #include "common.h"
 #include "ptx.cuh"
@@ -334,12 +336,14 @@ constexpr int kSelScratch = kSelBins + 8;   // ints per image: histogram + colle
 // topk-th best score lies and collects the candidates of the bins >= b* (topk plus the rest of one bin), (3) one CTA per
 // image sorts only those - in shared memory - and appends the best topk to the image's candidate list.
 // Same keys as before ((~score bits) << 32 | flattened index), so the result is identical.
-__device__ __forceinline__ int sel_bin(float sc, uint32_t thr_bits) {
-  return min(kSelBins - 1, static_cast<int>((__float_as_uint(sc) - thr_bits) >> 15));
+// bins of 2^shift ulps above the threshold; the host picks shift so that score 1.0 lands below kSelBins (no clamping:
+// sub-bins of a bin stay ordered, see the refinement in the sort kernel)
+__device__ __forceinline__ int sel_bin(uint32_t score_bits, uint32_t thr_bits, int shift) {
+  return min(kSelBins - 1, static_cast<int>((score_bits - thr_bits) >> shift));
 }
 
 __global__ void __launch_bounds__(256) gfl_select_hist_kernel(const float* __restrict__ rows, int rows_ld, int64_t rows_bs, int row0,
-                                                              int A_l, int nc, float thr, int* __restrict__ scratch) {
+                                                              int A_l, int nc, float thr, int shift, int* __restrict__ scratch) {
   pdl_prologue();
   __shared__ int hist[kSelBins];
   const int b = blockIdx.y;
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(256) gfl_select_hist_kernel(const float* __res
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int a = i / nc, c = i - a * nc;
     const float sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
-    if (sc > thr) atomicAdd(&hist[sel_bin(sc, thr_bits)], 1);
+    if (sc > thr) atomicAdd(&hist[sel_bin(__float_as_uint(sc), thr_bits, shift)], 1);
   }
   __syncthreads();
   int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
@@ -359,37 +363,60 @@ __global__ void __launch_bounds__(256) gfl_select_hist_kernel(const float* __res
     if (hist[i]) atomicAdd(&gh[i], hist[i]);
 }
 
-// one warp: (b*, candidates in bins >= b*... not needed, total candidate count) from an image's histogram
-__device__ __forceinline__ void sel_threshold_bin(const int* hist, int topk, int lane, int* bstar_out, int* total_out) {
-  int cum = 0, bstar = 0;
-  bool found = false;
-  for (int hi = kSelBins; hi > 0; hi -= 64) {
-    const int b0 = hi - 1 - 2 * lane;          // lanes own bins (b0, b0 - 1), descending
-    const int h0 = hist[b0], h1 = hist[b0 - 1];
-    int incl = h0 + h1;
+// Whole CTA (blockDim a multiple of 32, at most 32 warps, kSelBins / warps a multiple of 64): b* = the bin in which the
+// topk-th best score lies (0 if there are fewer candidates) and the total candidate count, from an image's histogram in
+// shared memory.  Warp w owns the bins [kSelBins - (w + 1) * seg, kSelBins - w * seg), best scores first; every warp adds up
+// its segment, then the one warp whose segment holds the crossing walks it again (one warp over all 2048 bins: 32
+// dependent rounds, 10 us per launch).  Call from all threads; results are valid after the closing barrier.
+__device__ __forceinline__ void sel_threshold_bin(const int* hist, int topk, int* bstar_s, int* total_s, int* wsum_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int seg = kSelBins / nwarps;
+  const int hi0 = kSelBins - warp * seg;
+  int mine = 0;
+  for (int hi = hi0; hi > hi0 - seg; hi -= 64) {
+    const int b0 = hi - 1 - 2 * lane;
+    mine += hist[b0] + hist[b0 - 1];
+  }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int before = cum + incl - h0 - h1;     // candidates in strictly better bins than b0
-    if (!found) {
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) wsum_s[warp] = mine;
+  if (threadIdx.x == 0) *bstar_s = 0;
+  __syncthreads();
+  int before_w = 0, total = 0;
+  for (int w = 0; w < nwarps; ++w) {
+    const int v = wsum_s[w];
+    if (w < warp) before_w += v;
+    total += v;
+  }
+  if (threadIdx.x == 0) *total_s = total;
+  if (before_w < topk && before_w + mine >= topk) {   // warp-uniform: the crossing is in this segment
+    int cum = before_w;
+    for (int hi = hi0; hi > hi0 - seg; hi -= 64) {
+      const int b0 = hi - 1 - 2 * lane;          // lanes own bins (b0, b0 - 1), descending
+      const int h0 = hist[b0], h1 = hist[b0 - 1];
+      int incl = h0 + h1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int before = cum + incl - h0 - h1;     // candidates in strictly better bins than b0
       const bool hit0 = before + h0 >= topk, hit1 = before + h0 + h1 >= topk;
       const unsigned m = __ballot_sync(0xffffffffu, hit0 || hit1);
       if (m) {
         const int l = __ffs(m) - 1;
-        bstar = __shfl_sync(0xffffffffu, hit0 ? b0 : b0 - 1, l);
-        found = true;
+        const int bs = __shfl_sync(0xffffffffu, hit0 ? b0 : b0 - 1, l);
+        if (lane == 0) *bstar_s = bs;
+        break;
       }
+      cum += __shfl_sync(0xffffffffu, incl, 31);
     }
-    cum += __shfl_sync(0xffffffffu, incl, 31);
   }
-  *bstar_out = found ? bstar : 0;
-  *total_out = cum;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) gfl_select_collect_kernel(const float* __restrict__ rows, int rows_ld, int64_t rows_bs, int row0,
-                                                                 int A_l, int nc, float thr, int topk, int* __restrict__ scratch,
+                                                                 int A_l, int nc, float thr, int shift, int topk, int* __restrict__ scratch,
                                                                  unsigned long long* __restrict__ keys, int64_t keys_bs) {
   pdl_prologue();
   __shared__ int bstar_s;
@@ -398,12 +425,8 @@ __global__ void __launch_bounds__(256) gfl_select_collect_kernel(const float* __
   int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
   for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = __ldcg(&gh[i]);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    int bs, tot;
-    sel_threshold_bin(hs, topk, static_cast<int>(threadIdx.x), &bs, &tot);
-    if (threadIdx.x == 0) bstar_s = bs;
-  }
-  __syncthreads();
+  __shared__ int total_s, wsum_s[32];
+  sel_threshold_bin(hs, topk, &bstar_s, &total_s, wsum_s);
   const int bstar = bstar_s;
   unsigned long long* kb = keys + b * keys_bs;
   const float* rb = rows + b * rows_bs + static_cast<int64_t>(row0) * rows_ld;
@@ -417,7 +440,7 @@ __global__ void __launch_bounds__(256) gfl_select_collect_kernel(const float* __
     if (i < total) {
       const int a = i / nc, c = i - a * nc;
       sc = 1.0f / (1.0f + expf(-rb[static_cast<int64_t>(a) * rows_ld + c]));
-      hit = sc > thr && sel_bin(sc, thr_bits) >= bstar;
+      hit = sc > thr && sel_bin(__float_as_uint(sc), thr_bits, shift) >= bstar;
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (m) {
@@ -432,42 +455,92 @@ __global__ void __launch_bounds__(256) gfl_select_collect_kernel(const float* __
 }
 
 __global__ void __launch_bounds__(1024) gfl_select_sort_kernel(const float* __restrict__ boxes, int64_t boxes_bs, int row0, int nc,
-                                                               int topk, int* __restrict__ scratch, unsigned long long* __restrict__ keys,
-                                                               int64_t keys_bs, int* __restrict__ cand_count, float* __restrict__ cboxes,
+                                                               float thr, int shift, int topk, int* __restrict__ scratch,
+                                                               unsigned long long* __restrict__ keys, int64_t keys_bs,
+                                                               int* __restrict__ cand_count, float* __restrict__ cboxes,
                                                                float* __restrict__ cscores, float* __restrict__ clabels, int cap) {
   pdl_prologue();
   const int b = blockIdx.x;
   __shared__ unsigned long long sk[kSelCap];
-  __shared__ int base_s, n_s;
+  __shared__ int base_s, n_s, bstar_s, wsum_s[32], above_s, sstar_s, sub_total_s, m2_s;
   int* gh = scratch + static_cast<int64_t>(b) * kSelScratch;
   unsigned long long* kb = keys + b * keys_bs;
-  {
-    int* hs = reinterpret_cast<int*>(sk);   // staged histogram (the sort buffer is not in use yet)
-    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = __ldcg(&gh[i]);
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int bs, tot;
-      sel_threshold_bin(hs, topk, static_cast<int>(threadIdx.x), &bs, &tot);
-      if (threadIdx.x == 0) n_s = tot;
-    }
-  }
+  int* hs = reinterpret_cast<int*>(sk);   // staged histograms (the sort buffer is not in use yet)
+  for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = __ldcg(&gh[i]);
+  if (threadIdx.x == 0) { above_s = 0; m2_s = 0; }
   __syncthreads();
-  const int n = n_s, m = __ldcg(&gh[kSelBins]);
+  sel_threshold_bin(hs, topk, &bstar_s, &n_s, wsum_s);
+  const int n = n_s, bstar = bstar_s;
+  int m = __ldcg(&gh[kSelBins]);
   const int take = min(n, topk);
   __syncthreads();
   for (int i = threadIdx.x; i < kSelScratch; i += blockDim.x) gh[i] = 0;   // clean for the next level / call
-  int P = 1;
-  while (P < m) P <<= 1;
-  const bool in_smem = m <= kSelCap;
+  const uint32_t thr_bits = __float_as_uint(fmaxf(thr, 0.0f));
+  bool staged = false;
+  if (m > kSelCap / 2) {
+    // Many candidates share the crossing bin (narrow score distributions): refine inside it with 2048 sub-bins, keep
+    // everything above the crossing sub-bin, so that the network below sorts ~topk keys instead of thousands.
+    const int sub_shift = shift > 11 ? shift - 11 : 0;
+    const uint32_t sub_mask = (shift >= 32) ? 0xFFFFFFFFu : ((1u << shift) - 1u);
+    for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) hs[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (int i0 = 0; i0 < m; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      bool up = false;
+      if (i < m) {
+        const uint32_t bits = ~static_cast<uint32_t>(kb[i] >> 32);
+        const int bin = sel_bin(bits, thr_bits, shift);
+        up = bin > bstar;
+        if (bin == bstar) atomicAdd(&hs[min(kSelBins - 1, static_cast<int>(((bits - thr_bits) & sub_mask) >> sub_shift))], 1);
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, up);
+      if (lane == 0 && mk) atomicAdd(&above_s, __popc(mk));
+    }
+    __syncthreads();
+    const int above = above_s;
+    sel_threshold_bin(hs, topk - above, &sstar_s, &sub_total_s, wsum_s);
+    const int sstar = sstar_s;
+    __syncthreads();   // hs (= sk) is free from here
+    // survivors: bins above b*, and the sub-bins >= s* of b*
+    for (int i0 = 0; i0 < m; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      bool keep = false;
+      unsigned long long key = 0;
+      if (i < m) {
+        key = kb[i];
+        const uint32_t bits = ~static_cast<uint32_t>(key >> 32);
+        const int bin = sel_bin(bits, thr_bits, shift);
+        keep = bin > bstar ||
+               (bin == bstar && min(kSelBins - 1, static_cast<int>(((bits - thr_bits) & sub_mask) >> sub_shift)) >= sstar);
+      }
+      const unsigned mk = __ballot_sync(0xffffffffu, keep);
+      int base = 0;
+      if (lane == 0 && mk) base = atomicAdd(&m2_s, __popc(mk));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) {
+        const int slot = base + __popc(mk & ((1u << lane) - 1u));
+        if (slot < kSelCap) sk[slot] = key;
+      }
+    }
+    __syncthreads();
+    if (m2_s <= kSelCap) { m = m2_s; staged = true; }   // else (ties beyond the sub-bins): sort everything in global memory
+    __syncthreads();
+  }
+  int P = 1, lp = 0;
+  while (P < m) { P <<= 1; ++lp; }
+  const bool in_smem = staged || m <= kSelCap;
   unsigned long long* sv = in_smem ? sk : kb;
-  if (in_smem)
+  if (in_smem && !staged)
     for (int i = threadIdx.x; i < m; i += blockDim.x) sk[i] = kb[i];
   for (int i = m + threadIdx.x; i < P; i += blockDim.x) sv[i] = ~0ull;
   __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
+  for (int lk = 1; lk <= lp; ++lk) {
+    const int k = 1 << lk;
+    for (int lj = lk - 1; lj >= 0; --lj) {
+      const int j = 1 << lj;
       for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
-        const int i = 2 * j * (t / j) + (t % j);
+        const int i = ((t >> lj) << (lj + 1)) | (t & (j - 1));
         const bool asc = ((i & k) == 0);
         const unsigned long long x = sv[i], y = sv[i + j];
         if ((x > y) == asc) { sv[i] = y; sv[i + j] = x; }
@@ -592,13 +665,22 @@ extern "C" int glsdet_gfl_select(const float* rows, int32_t rows_ld, int64_t row
   const int cap_chunks = 2 * device_sm_count() / batch + 1;
   if (chunks > cap_chunks) chunks = cap_chunks;
   if (chunks < 1) chunks = 1;
+  int shift = 0;   // histogram bin = 2^shift ulps of the score, the range (threshold, 1.0] fits kSelBins bins
+  {
+    const float t = score_thr > 0.0f ? score_thr : 0.0f;
+    uint32_t tb, one = 0x3F800000u;
+    memcpy(&tb, &t, sizeof(tb));
+    const uint32_t range = tb < one ? one - tb : 1u;
+    while ((range >> shift) >= static_cast<uint32_t>(kSelBins)) ++shift;
+  }
   launch_pdl(gfl_select_hist_kernel, dim3(chunks, batch), dim3(256), 0, st, rows, rows_ld, rows_batch_stride, row0, level_anchors,
-             num_classes, score_thr, scratch);
+             num_classes, score_thr, shift, scratch);
   if (int rc = count_launch("gfl_select_hist_kernel")) return rc;
   launch_pdl(gfl_select_collect_kernel, dim3(chunks, batch), dim3(256), 0, st, rows, rows_ld, rows_batch_stride, row0, level_anchors,
-             num_classes, score_thr, topk, scratch, reinterpret_cast<unsigned long long*>(keys), keys_batch_stride);
+             num_classes, score_thr, shift, topk, scratch, reinterpret_cast<unsigned long long*>(keys), keys_batch_stride);
   if (int rc = count_launch("gfl_select_collect_kernel")) return rc;
-  launch_pdl(gfl_select_sort_kernel, dim3(batch), dim3(1024), 0, st, boxes, boxes_batch_stride, row0, num_classes, topk, scratch,
+  launch_pdl(gfl_select_sort_kernel, dim3(batch), dim3(1024), 0, st, boxes, boxes_batch_stride, row0, num_classes, score_thr, shift,
+             topk, scratch,
              reinterpret_cast<unsigned long long*>(keys), keys_batch_stride, cand_count, cand_boxes, cand_scores, cand_labels,
              cand_capacity);
   return count_launch("gfl_select_sort_kernel");
