@@ -48,6 +48,8 @@ struct alignas(64) ConvKParams {
   CUtensorMap tmB;
   CUtensorMap tmB3[2];       // per source: 3-D view (k, n, ky) of the weights, one box = the three ky taps
   CUtensorMap tmO;           // TMA-store epilogue: the bf16 NHWC output window, box = one 128-pixel x 64-channel tile
+  CUtensorMap tmRpost;       // res_tma: the post-activation residual (16-bit), box = 64 channels x the tile's pixels >> post_shift
+  CUtensorMap tmRpre;        // res_tma: the fp32 pre-activation residual viewed as 2-byte elements, box = 32 floats x pixels >> pre_shift
   int32_t B, Ho, Wo;
   int32_t tile_w_log2, tile_h;
   int32_t tiles_x, tiles_y, n_blocks, total_tiles;
@@ -75,6 +77,9 @@ struct alignas(64) ConvKParams {
   int32_t a_shared;          // k > 0: image b reads activation image b % k (static matrices used as activations)
   int32_t a_div;             // with a_shared: image b reads activation image b / a_div instead of b % a_shared
   int32_t patch;             // src0 / post_res / out are 2x2 patch views (image b' = (b*2 + py)*2 + px)
+  int32_t res_tma;           // residual operands of the TMA-store epilogue staged through shared memory by TMA (see epi_tile_ts)
+  int32_t res_post_bytes, res_pre_half_bytes, res_slot_bytes;   // per staging sub-group: post tile | pre channels 0..31 | 32..63
+  int32_t res_nbuf;          // residual slots per sub-group (1)
   int32_t egrp;              // 16-warp TMA-store class: two groups of 8 epilogue warps drain ALTERNATE work items (one
                              // accumulator slot each) instead of all 16 sharing every item - the epilogue of a small-K
                              // conv is a latency chain per tile, two tiles in flight nearly double its throughput
@@ -99,6 +104,7 @@ struct alignas(64) ConvKParams {
   const float* pred_b;
   int32_t pred_n, pred_act;
   unsigned long long* trace;   // diagnostic (GLSDET_CONV_TRACE=1): %globaltimer stamps of CTA 0, see glsdet_conv_read_trace
+  int32_t dbg;                 // diagnostic (GLSDET_CONV_DBG bits; wrong results): 1 = no TMA store, 2 = no epilogue math / staging writes
 };
 
 __device__ __forceinline__ void trace_stamp(const ConvKParams& p, int slot) {
@@ -115,7 +121,9 @@ enum { EPI_GENERIC = 0, EPI_BF16 = 1, EPI_BF16_PRE = 2, EPI_BF16_POST = 3, EPI_F
 // Epilogue classes: the kernel is instantiated once per class so that each binary only carries its own epilogue
 // (smaller instruction footprint - the all-in-one kernel lost 18 % of its epilogue issue slots to instruction-cache
 // misses - and registers sized for that epilogue).  EC_ALL keeps every path (2-CTA kernel, generic fallback).
-enum { EC_ALL = 0, EC_BF16 = 1, EC_BF16_TS = 2, EC_F32 = 3, EC_SMALL = 4, EC_PRED_FMA = 5, EC_PRED_MMA = 6, EC_COUNT = 7 };
+// EC_BF16_TSR = EC_BF16_TS plus the TMA-staged residual operands: a class of its own, so that the plain TMA-store kernel
+// (96 registers with 16 epilogue warps, no headroom) does not pay for that code
+enum { EC_ALL = 0, EC_BF16 = 1, EC_BF16_TS = 2, EC_F32 = 3, EC_SMALL = 4, EC_PRED_FMA = 5, EC_PRED_MMA = 6, EC_BF16_TSR = 7, EC_COUNT = 8 };
 constexpr int kActSiluExact = 100;   // diagnostic (GLSDET_CONV_EXACT_SILU=1): ex2 + rcp SiLU instead of tanh.approx
 constexpr int kStageTileBytes = kBlockM * kRowBytes;   // one 128-row x 64-channel K-major SW128 operand tile
 constexpr int kPredTileBytes = 16 * kRowBytes;         // prediction weights: 16 rows x 64 channels
@@ -291,10 +299,27 @@ __device__ __forceinline__ void epilogue_store16(const ConvKParams& p, const uin
 
 // Specialised epilogues (chosen per op at create time; everything warp-uniform is hoisted out of the element
 // loops).  bf16 NHWC output of 16 channels = two 16-byte stores.
+// Residual operands staged in shared memory by TMA (128-byte rows, 128-byte swizzle): this pixel's rows and the position
+// of the 16-channel chunk inside the 64-channel tile.
+struct ResRows {
+  const uint8_t* post;    // 64 x 16-bit channels
+  const uint8_t* pre0;    // fp32 channels 0..31
+  const uint8_t* pre1;    // fp32 channels 32..63
+  int sw_post, sw_pre;    // row & 7 of the post / pre rows (swizzle phase)
+  int cc;                 // chunk of 16 channels, 0..3
+};
+__device__ __forceinline__ float4 res_pre4(const ResRows& rr, int q) {      // floats 4q .. 4q+3 of the chunk
+  const uint8_t* row = (rr.cc & 2) ? rr.pre1 : rr.pre0;
+  return *reinterpret_cast<const float4*>(row + (((((rr.cc & 1) << 2) | q) ^ rr.sw_pre) << 4));
+}
+__device__ __forceinline__ uint4 res_post8(const ResRows& rr, int h) {      // 16-bit values 8h .. 8h+7 of the chunk
+  return *reinterpret_cast<const uint4*>(rr.post + ((((rr.cc << 1) | h) ^ rr.sw_post) << 4));
+}
+
 template <bool PRE, bool POST>
 __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const float* s_bias, int act,
                                            const float* pre, const __nv_bfloat16* post, uint4* o0, uint4* o1,
-                                           int dt) {   // dt: bit 0 = fp16 output, bit 1 = fp16 post residual
+                                           int dt, const ResRows* rs = nullptr) {   // dt: bit 0 = fp16 output, bit 1 = fp16 post residual
   float v[16];
   if (act == GLSDET_ACT_SILU) {
     // s_bias holds bias / 2 (ConvKParams::hbias): h = x / 2 in one FMA, silu(x) = h + h * tanh(h)
@@ -309,7 +334,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
     if (PRE) {
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(pre + j));
+        const float4 t = rs ? res_pre4(*rs, j >> 2) : __ldg(reinterpret_cast<const float4*>(pre + j));
         v[j] = fmaf(t.x, 0.5f, v[j]); v[j + 1] = fmaf(t.y, 0.5f, v[j + 1]);
         v[j + 2] = fmaf(t.z, 0.5f, v[j + 2]); v[j + 3] = fmaf(t.w, 0.5f, v[j + 3]);
       }
@@ -328,7 +353,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   if (PRE) {
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(pre + j));
+      const float4 t = rs ? res_pre4(*rs, j >> 2) : __ldg(reinterpret_cast<const float4*>(pre + j));
       v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
     }
   }
@@ -344,7 +369,7 @@ __device__ __forceinline__ void epi16_bf16(const uint32_t (&raw)[16], const floa
   if (POST) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(post) + h);
+      const uint4 t = rs ? res_post8(*rs, h) : __ldg(reinterpret_cast<const uint4*>(post) + h);
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
       if (dt & 2) {
 #pragma unroll
@@ -478,9 +503,15 @@ struct TsCtx {
   bool issuer;
   bool wide;          // block_n >= 128: each column half owns whole 64-channel tiles; else both halves share one
   int parts;          // column parts = epilogue warps / 4 (2, or 4 in the 16-warp variant: block_n 64 or 128 only)
+  // res_tma: this sub-group's residual slot, its arrival barrier and the phase of the next arrival
+  const uint8_t* res;
+  uint64_t* res_bar;
+  uint32_t res_count;  // residual tiles consumed by this sub-group (barrier phase = count & 1)
+  int res_row;        // this pixel's row in the post / pre residual tiles
+  int res_row_pre;
 };
-template <bool PRE, bool POST>
-__device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g, uint32_t taddr, int r, int half,
+template <bool PRE, bool POST, int RS>   // RS: residual operands staged by TMA - 0 never, 1 decided at run time, 2 always
+__device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, TsCtx& g, uint32_t taddr, int r, int half,
                                             int k_tiles, bool valid, int act, const float* sb, const float* pre,
                                             const __nv_bfloat16* post, const TileCoord& t, int y_tile,
                                             uint32_t& sbuf) {
@@ -506,18 +537,38 @@ __device__ __forceinline__ void epi_tile_ts(const ConvKParams& p, const TsCtx& g
       cb = g.wide ? kc * 4 + (half & 1) * 2 : half;
       ce = g.wide ? cb + 2 : half + 1;
     }
+    ResRows rs;
+    const bool use_rs = (RS == 2) ? (PRE || POST) : (RS == 1 && (PRE || POST) && g.res_bar != nullptr);
+    if (use_rs) {   // the residual tiles of this (work item, 64-channel tile) were requested before the accumulator wait
+      mbar_wait(g.res_bar, g.res_count & 1u);
+      ++g.res_count;
+      rs.post = g.res + g.res_row * kRowBytes;
+      rs.pre0 = g.res + p.res_post_bytes + g.res_row_pre * kRowBytes;
+      rs.pre1 = rs.pre0 + p.res_pre_half_bytes;
+      rs.sw_post = g.res_row & 7;
+      rs.sw_pre = g.res_row_pre & 7;
+    }
+    if (!(p.dbg & 2))
     epi_walk(taddr, cb, ce, [&](const uint32_t (&raw)[16], int c) {
       if (valid) {
         const int cc = (c & 3) * 2;   // 16-byte chunk of the 128-byte staging row
+        if (use_rs) {
+          ResRows q = rs;
+          q.cc = c & 3;
+          epi16_bf16<PRE, POST>(raw, sb + c * 16, act, nullptr, nullptr,
+                                reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)),
+                                reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)), dt, &q);
+        } else {
         epi16_bf16<PRE, POST>(raw, sb + c * 16, act, PRE ? pre + c * 16 : nullptr, POST ? post + c * 16 : nullptr,
                               reinterpret_cast<uint4*>(rowp + ((cc ^ (r & 7)) << 4)),
                               reinterpret_cast<uint4*>(rowp + (((cc + 1) ^ (r & 7)) << 4)), dt);
+        }
       }
     });
     fence_proxy_async_smem();
     if (g.issuer) tma_store_wait_read();
     named_bar_sync(g.bar_id, g.nthr);
-    if (g.issuer) {
+    if (g.issuer && !(p.dbg & 1)) {
       tma_store_5d(&p.tmO, buf, t.n0 + kc * kChunkK, t.x0, c2, y_tile, c4);
       tma_store_commit();
     }
@@ -543,8 +594,9 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint8_t* smem_b = smem + p.sa * p.a_bytes;
   uint8_t* smem_stage = smem_b + b_region;                                          // [k_tiles][128 rows][128 B]
   const int ts_groups = (p.block_n >= 128 || (EW == 16 && p.egrp)) ? 2 : 1;   // warp groups with their own staging tiles
-  uint8_t* smem_pw = smem_stage + (pred_mma ? k_tiles * kStageTileBytes               // [k_tiles][16 rows][128 B]
-                                            : p.ts ? ts_groups * 2 * kStageTileBytes : 0);
+  uint8_t* smem_res = smem_stage + (p.ts ? ts_groups * 2 * kStageTileBytes : 0);   // res_tma: 4 residual slots
+  uint8_t* smem_pw = pred_mma ? smem_stage + k_tiles * kStageTileBytes                 // [k_tiles][16 rows][128 B]
+                              : smem_res + (p.res_tma ? 4 * p.res_slot_bytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_pw + (pred_mma ? k_tiles * kPredTileBytes : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = bars + kMaxStages;
@@ -556,7 +608,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
   uint64_t* pred_bar = bars + 4 * kMaxStages + 9;
   uint64_t* pstage_bar = bars + 4 * kMaxStages + 11;   // 2-CTA: both CTAs have staged their activated tile (leader's copy)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * kMaxStages + 10);
-  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 12);  // [n_blocks * block_n], zero padded (x 0.5: hbias)
+  uint64_t* res_bar = bars + 4 * kMaxStages + 12;      // res_tma: residual tiles of a staging sub-group have landed (4 x 2)
+  float* s_bias = reinterpret_cast<float*>(bars + 4 * kMaxStages + 20);  // [n_blocks * block_n], zero padded (x 0.5: hbias)
   float* s_pw = s_bias + p.n_blocks * p.block_n;                         // FMA prediction path: weights [N][16]
   float* s_red = s_pw + p.block_n * 16;                                  // [2][128][16] partial sums of the upper column half
 
@@ -575,6 +628,8 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
     tma_prefetch_desc(&p.tmB);
     if (p.bgroup == 3) { tma_prefetch_desc(&p.tmB3[0]); tma_prefetch_desc(&p.tmB3[1]); }
     if (p.ts) tma_prefetch_desc(&p.tmO);
+    if (p.res_tma && p.res_post_bytes) tma_prefetch_desc(&p.tmRpost);
+    if (p.res_tma && p.res_pre_half_bytes) tma_prefetch_desc(&p.tmRpre);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.sa; ++s) {
@@ -591,6 +646,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       mbar_init(&tempty_bar[s], k2 ? 2 * ew_arr : ew_arr);  // 2-CTA: the peer's epilogue warps arrive too
     }
     mbar_init(bres_full, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(pred_bar, 1);
     mbar_init(pstage_bar, 2);
     fence_mbar_init();
@@ -933,6 +989,15 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       tsg.parts = 2;
     }
     const int half_ts = egrp ? (half & 1) : half;
+    tsg.res = nullptr; tsg.res_bar = nullptr; tsg.res_count = 0u; tsg.res_row = 0; tsg.res_row_pre = 0;
+    const int res_kc = (egrp && p.block_n >= 128) ? (half & 1) : 0;   // the 64-channel tile this sub-group stores
+    if (p.res_tma && egrp) {
+      const int sub_idx = my_slot * 2 + res_kc;
+      tsg.res = smem_res + sub_idx * p.res_slot_bytes;
+      tsg.res_bar = &res_bar[sub_idx];
+      tsg.res_row = ((py >> p.post_shift) << (p.tile_w_log2 - p.post_shift)) + (px >> p.post_shift);
+      tsg.res_row_pre = ((py >> p.pre_shift) << (p.tile_w_log2 - p.pre_shift)) + (px >> p.pre_shift);
+    }
     uint32_t sbuf = 0;     // staging tiles written by this warp group (TMA-store epilogue)
     int it = 0;
     uint32_t tcount = 0;   // tiles processed by this CTA (prediction-MMA barrier phase, FMA scratch slot)
@@ -941,6 +1006,27 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
       const TileCoord t = decode(tile);
       const int as = it % p.nacc;
       const uint32_t aph = static_cast<uint32_t>(it / p.nacc) & 1u;
+      if constexpr (EC == EC_ALL || EC == EC_BF16_TSR) {
+        // Residual operands of the TMA-store epilogue.  Per-thread global loads of this pixel's row cost one L1 tag
+        // lookup per 16 bytes (every lane another pixel, the same problem the TMA store solves on the way out): 1x1
+        // 128 -> 128 + residual at 256^2 ran 152 us against 100 us without one.  Instead the TMA unit drops the residual
+        // tile of this (work item, 64-channel tile) into shared memory, requested here - before the accumulator wait -
+        // and read row-wise (swizzled, conflict-free) in epi_tile_ts.
+        if (p.res_tma && tsg.issuer && tsg.res_bar != nullptr) {
+          // (two slots per sub-group with the request one work item further ahead measured slower: 145 -> 160 us on the
+          // 256^2 layer - the extra tile decode and bookkeeping cost the 96-register epilogue more than the latency hid)
+          mbar_arrive_expect_tx(tsg.res_bar, static_cast<uint32_t>(p.res_post_bytes + 2 * p.res_pre_half_bytes));
+          uint8_t* dst = const_cast<uint8_t*>(tsg.res);
+          const int ch0 = t.n0 + res_kc * kChunkK;
+          if (p.res_post_bytes)
+            tma_load_5d(dst, &p.tmRpost, tsg.res_bar, ch0, t.x0 >> p.post_shift, 0, t.y0 >> p.post_shift, t.b);
+          if (p.res_pre_half_bytes) {   // fp32 viewed as 2-byte elements: 32 floats = one 128-byte row
+            tma_load_5d(dst + p.res_post_bytes, &p.tmRpre, tsg.res_bar, 2 * ch0, t.x0 >> p.pre_shift, 0, t.y0 >> p.pre_shift, t.b);
+            tma_load_5d(dst + p.res_post_bytes + p.res_pre_half_bytes, &p.tmRpre, tsg.res_bar, 2 * ch0 + kChunkK,
+                        t.x0 >> p.pre_shift, 0, t.y0 >> p.pre_shift, t.b);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       if (p.trace != nullptr && warp == 4 && lane == 0 && p.trace[6] == 0ull) trace_stamp(p, 6);
@@ -955,7 +1041,7 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
         case EPI_BF16:
         case EPI_BF16_PRE:
         case EPI_BF16_POST:
-        case EPI_BF16_PREPOST: { if constexpr (EC == EC_ALL || EC == EC_BF16 || EC == EC_BF16_TS) {
+        case EPI_BF16_PREPOST: { if constexpr (EC == EC_ALL || EC == EC_BF16 || EC == EC_BF16_TS || EC == EC_BF16_TSR) {
           const bool has_pre = (p.epi == EPI_BF16_PRE || p.epi == EPI_BF16_PREPOST);
           const bool has_post = (p.epi == EPI_BF16_POST || p.epi == EPI_BF16_PREPOST);
           const float* pre = nullptr;
@@ -973,12 +1059,13 @@ __global__ void __launch_bounds__((4 + EW) * 32, 1) conv_gemm_kernel(const __gri
               post = p.post_res + ((static_cast<int64_t>(t.b) * hs + (oy >> p.post_shift)) * ws + (ox >> p.post_shift)) * p.post_ld + t.n0;
             }
           }
-          if constexpr (EC == EC_ALL || EC == EC_BF16_TS) if (p.ts) {
+          if constexpr (EC == EC_ALL || EC == EC_BF16_TS || EC == EC_BF16_TSR) if (p.ts) {
+            constexpr int RS = (EC == EC_BF16_TSR) ? 2 : (EC == EC_ALL) ? 1 : 0;
             const int y_tile = t.y0 + m * p.tile_h;
-            if (has_pre && has_post) epi_tile_ts<true, true>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else if (has_pre) epi_tile_ts<true, false>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else if (has_post) epi_tile_ts<false, true>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
-            else epi_tile_ts<false, false>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            if (has_pre && has_post) epi_tile_ts<true, true, RS>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_pre) epi_tile_ts<true, false, RS>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if (has_post) epi_tile_ts<false, true, RS>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
+            else if constexpr (EC != EC_BF16_TSR) epi_tile_ts<false, false, 0>(p, tsg, taddr, r, half_ts, k_tiles, valid, p.act_epi, sb, pre, post, t, y_tile, sbuf);
             break;
           }
           if constexpr (EC == EC_ALL || EC == EC_BF16) {
@@ -1247,9 +1334,14 @@ constexpr int EC_PRED_MMA16 = EC_COUNT + 1;   // tensor-core prediction class wi
 constexpr int EC2_ALL = EC_COUNT + 2;         // 2-CTA kernel, every epilogue
 constexpr int EC2_PRED_MMA16 = EC_COUNT + 3;  // 2-CTA kernel, tensor-core prediction class, 16 epilogue warps
 constexpr int EC2_BF16_TS16 = EC_COUNT + 4;   // 2-CTA kernel, TMA-store class, 16 epilogue warps
-constexpr int EC_KERNELS = EC_COUNT + 5;
+constexpr int EC_BF16_TS16R = EC_COUNT + 5;   // TMA-store class with TMA-staged residual operands, 16 epilogue warps
+constexpr int EC2_BF16_TS16R = EC_COUNT + 6;  // the same on the 2-CTA kernel
+constexpr int EC_KERNELS = EC_COUNT + 7;
 ConvKernelFn conv_kernel_for(int ec) {
   switch (ec) {
+    case EC_BF16_TS16R: return conv_gemm_kernel<false, EC_BF16_TSR, 16>;
+    case EC2_BF16_TS16R: return conv_gemm_kernel<true, EC_BF16_TSR, 16>;
+    case EC_BF16_TSR: return conv_gemm_kernel<false, EC_BF16_TS>;   // (8-warp residual class: not used)
     case EC_BF16_TS16: return conv_gemm_kernel<false, EC_BF16_TS, 16>;
     case EC_PRED_MMA16: return conv_gemm_kernel<false, EC_PRED_MMA, 16>;
     case EC2_ALL: return conv_gemm_kernel<true, EC_ALL>;
@@ -1597,12 +1689,38 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
   const int b_tap_bytes = g.block_n * kRowBytes;
   bool bres = false;
   k.bgroup = 1;
+  // residual operands of the 16-warp TMA-store class through TMA + shared memory (see the epilogue): one work item = one
+  // tile, residual resolution = the output's (post) or half of it (pre / post)
+  bool res_tma = false;
+  int res_post_bytes = 0, res_pre_half = 0;
+  if ((d->pre_res || d->post_res) && egrp_want && ts && (g.block_n == 64 || g.block_n == 128) && mt == 1 && !patch &&
+      (k.epi == EPI_BF16_PRE || k.epi == EPI_BF16_POST || k.epi == EPI_BF16_PREPOST) &&
+      getenv("GLSDET_CONV_NO_RES_TMA") == nullptr) {
+    bool ok = true;
+    if (d->post_res) {
+      const int sh = d->post_shift;
+      ok = ok && (sh == 0 || sh == 1) && (best_w >> sh) >= 1 && (k.tile_h >> sh) >= 1 && (g.Ho % (1 << sh)) == 0 &&
+           (g.Wo % (1 << sh)) == 0;
+      res_post_bytes = kRowBytes * (best_w >> sh) * (k.tile_h >> sh);
+      ok = ok && (res_post_bytes % 1024) == 0;
+    }
+    if (d->pre_res) {
+      const int sh = d->pre_shift;
+      ok = ok && sh == 1 && (best_w >> sh) >= 1 && (k.tile_h >> sh) >= 1 && (g.Ho % 2) == 0 && (g.Wo % 2) == 0;
+      res_pre_half = kRowBytes * (best_w >> sh) * (k.tile_h >> sh);
+      ok = ok && (res_pre_half % 1024) == 0;
+    }
+    res_tma = ok;
+    if (!ok) res_post_bytes = res_pre_half = 0;
+  }
+  const int res_slot_bytes = res_post_bytes + 2 * res_pre_half;
+  const int res_nbuf = 1;
   auto size_rings = [&](bool want_bgroup3) -> bool {
     const int pred_smem = !fused_pred ? 0
                           : pred_mma ? (g.block_n / 64) * (kStageTileBytes + kPredTileBytes)
                                      : (g.block_n * 16 + 2 * kBlockM * 16) * 4;
     const int ts_smem = ts ? ((g.block_n >= 128 || egrp_want) ? 4 : 2) * kStageTileBytes : 0;
-    const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem + ts_smem;
+    const int fixed = 1024 + 512 + g.n_pad * 4 + pred_smem + ts_smem + (ts && res_tma ? 4 * res_nbuf * res_slot_bytes : 0);
     const int budget = kSmemLimit - fixed;
     bres = false;
     k.bgroup = 1;
@@ -1699,6 +1817,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (fused_pred) k.epi = pred_mma ? EPI_TOWER_PRED_MMA : EPI_TOWER_PRED;
   }
 
+  k.dbg = getenv("GLSDET_CONV_DBG") ? atoi(getenv("GLSDET_CONV_DBG")) : 0;
   k.trace = nullptr;
   if (getenv("GLSDET_CONV_TRACE") != nullptr) {
     void* tp = nullptr;
@@ -1723,6 +1842,21 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     if (!rc)
       rc = encode_act_map(&k.tmA[1], s + d->src0_ld, d->src0_c, d->src0_ld, d->batch, d->height, d->width, 2, best_w,
                           box_rows);
+  }
+  k.res_tma = (k.ts && res_tma) ? 1 : 0;
+  k.res_post_bytes = k.res_tma ? res_post_bytes : 0;
+  k.res_pre_half_bytes = k.res_tma ? res_pre_half : 0;
+  k.res_slot_bytes = k.res_tma ? res_slot_bytes : 0;
+  k.res_nbuf = res_nbuf;
+  if (!rc && k.res_tma && d->post_res) {
+    const int sh = d->post_shift;
+    rc = encode_act_map(&k.tmRpost, d->post_res, d->out_channels, d->post_ld, d->batch, g.Ho >> sh, g.Wo >> sh, 1, best_w >> sh,
+                        k.tile_h >> sh);
+  }
+  if (!rc && k.res_tma && d->pre_res) {   // fp32 rows as 2-byte elements: a 64-element box row = 32 floats = 128 bytes
+    const int sh = d->pre_shift;
+    rc = encode_act_map(&k.tmRpre, d->pre_res, 2 * d->out_channels, 2 * d->pre_ld, d->batch, g.Ho >> sh, g.Wo >> sh, 1,
+                        best_w >> sh, k.tile_h >> sh);
   }
   if (!rc && k.ts) {
     const __nv_bfloat16* obase = reinterpret_cast<const __nv_bfloat16*>(d->out) + d->out_coff;
@@ -1779,7 +1913,7 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
     default: op->ec = EC_ALL;
   }
   if (op->ec == EC_BF16_TS && (g.block_n == 64 || g.block_n == 128) && getenv("GLSDET_CONV_EPI8") == nullptr)
-    op->ec = EC_BF16_TS16;
+    op->ec = k.res_tma ? EC_BF16_TS16R : EC_BF16_TS16;
   // the second tower conv + prediction MMA: its epilogue (activate, stage, prediction MMA round trip, decode) is as long
   // as the MMAs of two tiles with two warps per scheduler; four warps per scheduler halve the per-thread work
   if (op->ec == EC_PRED_MMA && (g.block_n % 64) == 0 && getenv("GLSDET_CONV_EPI8") == nullptr) op->ec = EC_PRED_MMA16;
@@ -1789,9 +1923,12 @@ extern "C" int glsdet_conv_create(const glsdet_conv_desc* d, glsdet_conv_t** out
               k.epi == EPI_TOWER_PRED_MMA)) ? 1 : 0;
   if (op->two_cta)   // the pair kernel: one all-epilogue binary, plus the prediction class with 16 epilogue warps
     op->ec = getenv("GLSDET_CONV_ONE_KERNEL") != nullptr ? EC2_ALL
-             : op->ec == EC_PRED_MMA16 ? EC2_PRED_MMA16 : op->ec == EC_BF16_TS16 ? EC2_BF16_TS16 : EC2_ALL;
-  k.egrp = (egrp_want && (op->ec == EC_BF16_TS16 || op->ec == EC2_BF16_TS16)) ? 1 : 0;
-  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16 || op->ec == EC2_BF16_TS16)
+             : op->ec == EC_PRED_MMA16 ? EC2_PRED_MMA16 : op->ec == EC_BF16_TS16 ? EC2_BF16_TS16
+             : op->ec == EC_BF16_TS16R ? EC2_BF16_TS16R : EC2_ALL;
+  k.egrp = (egrp_want && (op->ec == EC_BF16_TS16 || op->ec == EC2_BF16_TS16 || op->ec == EC_BF16_TS16R || op->ec == EC2_BF16_TS16R)) ? 1 : 0;
+  if (k.res_tma && !k.egrp) { free(mem); set_error("conv_create: internal: residual staging without the two-group epilogue"); return 2; }
+  op->threads = (op->ec == EC_BF16_TS16 || op->ec == EC_PRED_MMA16 || op->ec == EC2_PRED_MMA16 || op->ec == EC2_BF16_TS16 ||
+                 op->ec == EC_BF16_TS16R || op->ec == EC2_BF16_TS16R)
                     ? (4 + 16) * 32 : kThreads;
   static bool attr_set[64] = {false};
   int dev = 0;

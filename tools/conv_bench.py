@@ -25,6 +25,13 @@ CASES = {
     # second tower conv + fused prediction conv (10 classes, sigmoid rows)
     "tower_pred_s4": (16, 256, 256, [128], 128, 3, 1, 10),
     "tower_pred_s8": (16, 128, 128, [128], 128, 3, 1, 10),
+    # residual variants (8th field: "post1" = bf16 residual at half resolution added after the activation, "post0" = same
+    # resolution, "pre1" = fp32 pre-activation partial sums at half resolution)
+    "csp1x1_c128_n128_post1": (16, 256, 256, [128], 128, 1, 1, "post1"),
+    "ffa1x1_c256_n128_post0": (16, 128, 128, [256], 128, 1, 1, "post0"),
+    "ffa1x1_c256_n128": (16, 128, 128, [256], 128, 1, 1),
+    "c3p3_c128_n128_pre1": (16, 128, 128, [128], 128, 1, 1, "pre1"),
+    "c3p3_c128_n128": (16, 128, 128, [128], 128, 1, 1),
 }
 
 
@@ -38,7 +45,17 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name in args.cases.split(","):
         B, H, W, cins, n, k, s = CASES[name][:7]
-        n_pred = CASES[name][7] if len(CASES[name]) > 7 else 0
+        extra = CASES[name][7] if len(CASES[name]) > 7 else 0
+        n_pred = extra if isinstance(extra, int) else 0
+        res_kw = {}
+        if isinstance(extra, str):
+            sh = int(extra[-1])
+            if extra.startswith("post"):
+                res = torch.randn(B, (H // s) >> sh, (W // s) >> sh, n, device=dev).to(torch.bfloat16)
+                res_kw = dict(post_res=View(res), post_shift=sh)
+            else:
+                res = torch.randn(B, (H // s) >> sh, (W // s) >> sh, n, device=dev)
+                res_kw = dict(pre_res=View(res), pre_shift=sh)
         srcs = [View(torch.randn(B, H, W, c, device=dev).to(torch.bfloat16)) for c in cins]
         w = torch.randn(n, sum(cins), k, k, device=dev) * 0.05
         bias = torch.randn(n, device=dev)
@@ -51,7 +68,7 @@ def main():
                         out_batch_stride=rows.shape[1] * (n_pred + 5), pred_weight=wp,
                         pred_bias=torch.zeros(n_pred, device=dev), pred_act=N.ACT_SIGMOID)
         else:
-            op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=View(out))
+            op = ConvOp(srcs, w, bias, ksize=k, stride=s, act=N.ACT_BY_NAME[args.act], out=View(out), **res_kw)
         for _ in range(3):
             op.launch()
         torch.cuda.synchronize()
