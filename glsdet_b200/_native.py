@@ -16,7 +16,7 @@ NMS_COORD_TRICK, NMS_PER_CLASS, NMS_AUTO_CUDA, NMS_AUTO_CPU, NMS_MMCV = range(5)
 PRED_ROWS, PRED_PLANES, PRED_CLS_LOGITS = 0, 1, 2
 DECODE_SIGMOID_OBJ, DECODE_SIGMOID_CLS, DECODE_NORMALISE, DECODE_XYXY = 1, 2, 4, 8
 SE_SLABS = 32
-DT_BF16, DT_F16 = 0, 1   # GLSDET_DT_*: 16-bit storage type of an activation / weight tensor
+DT_BF16, DT_F16, DT_F32 = 0, 1, 2   # GLSDET_DT_*: storage type of an activation tensor (F32: accuracy mode, glsdet_dwconv)
 
 
 def dt_code(dtype) -> int:
@@ -168,6 +168,9 @@ SIGNATURES = {
     "glsdet_gfl_select_scratch_ints": (C.c_int64, [C.c_int32]),
     "glsdet_upsample2x": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "glsdet_dwconv": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                C.c_void_p]),
     "glsdet_focus_nchw_f32_to_nhwc_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                                      C.c_void_p]),
     "glsdet_spp_maxpool": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import (ConvOp, ConvOpF32, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_pair_weight, fold_kx_weight,
+from .ops import (ConvOp, ConvOpF32, DepthwiseOp, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_pair_weight, fold_kx_weight,
                   nhwc_to_nchw, pair_stride2_weight)
 
 BN_EPS = 1e-3
@@ -31,7 +31,7 @@ FEATURES = ("dark2", "dark3", "dark4", "dark5")
 
 def backbone_supported(base_channels: int) -> bool:
     """The native plan needs channel counts that are multiples of 8 (TMA strides of 16 bytes): every phi of the reference
-    except the depthwise 'nano' (base 16, 24 for 'tiny', 32 for 's', ...)."""
+    (base 16 for the depthwise 'nano', 24 for 'tiny', 32 for 's', ...)."""
     return base_channels % 8 == 0
 
 
@@ -86,7 +86,22 @@ class BackbonePlan:
         self.flops += op.flops
         return op
 
+    def _is_dw(self, p: str) -> bool:
+        """`p` names a DWConv (models/base/baseConv.py:22-30; phi = 'nano', darknet.py:48,120)."""
+        return (p + ".dconv.conv.weight") in self.sd
+
     def _base_conv(self, p, srcs, out, stride=1, **kw):
+        if self._is_dw(p):   # DWConv.forward: pconv(dconv(x)); the depthwise half is csrc/dwconv.cu
+            assert len(srcs) == 1
+            src = srcs[0]
+            w, b = self._folded(p + ".dconv")
+            bb, h, w_ = src.bhw
+            t = torch.empty((bb, h // stride, w_ // stride, src.c), dtype=src.t.dtype, device=self.device)
+            self._bufs[p + ".dconv"] = t
+            op = DepthwiseOp(src, w, b, stride=stride, act=self.act, out=View(t))
+            self.ops.append(op)
+            self.flops += op.flops
+            return self._base_conv(p + ".pconv", [View(t)], out, 1, **kw)
         w, b = self._folded(p)
         return self._conv(w, b, srcs, out, stride, **kw)
 
@@ -154,7 +169,8 @@ class BackbonePlan:
             t = self._buf(name + ".0", stride, cout)
             cin = x.shape[3]
             maxc = int(os.environ.get("GLSDET_PAIR_STRIDE2_MAXC", "32"))
-            if not self.fp32 and cin % 32 == 0 and cin <= maxc and x.shape[2] % 2 == 0 and not os.environ.get("GLSDET_NO_PAIR_STRIDE2"):
+            if (not self.fp32 and cin % 32 == 0 and cin <= maxc and x.shape[2] % 2 == 0 and not self._is_dw(f"{name}.0")
+                    and not os.environ.get("GLSDET_NO_PAIR_STRIDE2")):
                 # 32 input channels: the pixel-pair form (K = 6 x 64 instead of 9 x 64 half-empty chunks, dense TMA boxes)
                 w_, b_ = self._folded(f"{name}.0")
                 xp = x.view(x.shape[0], x.shape[1], x.shape[2] // 2, 2 * cin)

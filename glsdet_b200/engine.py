@@ -36,7 +36,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import (ConvOp, ConvOpF32, GatherBiasOp, NhwcTransposeOp, PatchTransposeOp, RectCopyOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
+from .ops import (ConvOp, ConvOpF32, DepthwiseOp, GatherBiasOp, NhwcTransposeOp, PatchTransposeOp, RectCopyOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
                   nchw_to_nhwc, nhwc_to_nchw)
 
 BN_EPS = 1e-3
@@ -111,7 +111,7 @@ class FFAPathPlan:
             self.cd2 = self.c0 // 2
         for c in (self.c0, self.c1, self.c2, self.cd2, self.hc):
             if c % 16:
-                raise NotImplementedError(f"channel count {c} is not a multiple of 16 (depthwise/nano is not supported)")
+                raise NotImplementedError(f"channel count {c} is not a multiple of 16")
         self.strides = (4, 8, 16, 32) if variant == "ffa" else (8, 16, 32)   # levels of the head outputs
         self.stride_hw = {s: (self.in_h // s, self.in_w // s) for s in (4, 8, 16, 32)}
         self.level_hw = [self.stride_hw[s] for s in self.strides]
@@ -174,7 +174,29 @@ class FFAPathPlan:
         self.flops += op1.flops + op2.flops
         return op2
 
+    def _is_dw(self, p: str) -> bool:
+        """`p` names a DWConv (models/base/baseConv.py:22-30; phi = 'nano'): keys p.dconv.* and p.pconv.*."""
+        return (p + ".dconv.conv.weight") in self.sd
+
+    def _dw(self, ops, p: str, src: View, stride: int = 1, act=None) -> View:
+        """dconv half of DWConv `p` (depthwise k x k + BN + act, csrc/dwconv.cu) into a temporary of the source's storage
+        type; returns the view the pconv half reads."""
+        w, b = self._folded(p + ".dconv")
+        bb, h, w_ = src.bhw
+        k = w.shape[-1]
+        pad = (k - 1) // 2
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w_ + 2 * pad - k) // stride + 1
+        t = torch.empty((bb, ho, wo, src.c), dtype=src.t.dtype, device=self.device)
+        self._bufs[p + ".dconv"] = t
+        op = DepthwiseOp(src, w, b, stride=stride, act=self.act if act is None else act, out=View(t))
+        ops.append(op)
+        self.flops += op.flops
+        return View(t)
+
     def _base_conv(self, ops, p, srcs, out, stride=1, act=None, **kw):
+        if self._is_dw(p):   # DWConv.forward: pconv(dconv(x)), both with BN + act
+            assert len(srcs) == 1
+            return self._base_conv(ops, p + ".pconv", [self._dw(ops, p, srcs[0], stride, act)], out, 1, act, **kw)
         w, b = self._folded(p)
         return self._conv(ops, w, b, srcs, out, w.shape[-1], stride, act, **kw)
 
@@ -587,34 +609,47 @@ class FFAPathPlan:
         a_off = 0
         for k, (h, w) in enumerate(self.level_hw):
             i = k if self.variant in ("stock", "p2") else (3 if k == 0 else k - 1)
-            wc0, bc0 = self._folded(f"head.cls_convs.{i}.0")
-            wr0, br0 = self._folded(f"head.reg_convs.{i}.0")
             F = self._buf(f"tower{k}", self.strides[k], 2 * hc)
-            self._conv(self.tower_ops, torch.cat([wc0, wr0], 0), torch.cat([bc0, br0], 0), [View(self.p[k])], View(F), 3)
-            wc1, bc1 = self._folded(f"head.cls_convs.{i}.1")
-            wr1, br1 = self._folded(f"head.reg_convs.{i}.1")
+            cls_in, reg_in = [View(F, 0, hc)], [View(F, hc, hc)]
+            k2 = 3   # kernel size of the conv that carries the fused prediction conv
+            if self._is_dw(f"head.cls_convs.{i}.0"):
+                # phi = 'nano': every tower conv is a DWConv.  The first pair cannot share one GEMM any more (each tower
+                # has its own depthwise filter on p_k); the depthwise halves of the second pair run in tower_ops and the
+                # prediction convs are fused into their 1x1 pconv halves.
+                self._base_conv(self.tower_ops, f"head.cls_convs.{i}.0", [View(self.p[k])], cls_in[0])
+                self._base_conv(self.tower_ops, f"head.reg_convs.{i}.0", [View(self.p[k])], reg_in[0])
+                cls_in = [self._dw(self.tower_ops, f"head.cls_convs.{i}.1", cls_in[0])]
+                reg_in = [self._dw(self.tower_ops, f"head.reg_convs.{i}.1", reg_in[0])]
+                wc1, bc1 = self._folded(f"head.cls_convs.{i}.1.pconv")
+                wr1, br1 = self._folded(f"head.reg_convs.{i}.1.pconv")
+                k2 = 1
+            else:
+                wc0, bc0 = self._folded(f"head.cls_convs.{i}.0")
+                wr0, br0 = self._folded(f"head.reg_convs.{i}.0")
+                self._conv(self.tower_ops, torch.cat([wc0, wr0], 0), torch.cat([bc0, br0], 0), [View(self.p[k])], View(F), 3)
+                wc1, bc1 = self._folded(f"head.cls_convs.{i}.1")
+                wr1, br1 = self._folded(f"head.reg_convs.{i}.1")
             w_ro = torch.cat([sd[f"head.reg_preds.{i}.weight"], sd[f"head.obj_preds.{i}.weight"]], 0).float()
             b_ro = torch.cat([sd[f"head.reg_preds.{i}.bias"], sd[f"head.obj_preds.{i}.bias"]], 0).float()
             w_cl, b_cl = sd[f"head.cls_preds.{i}.weight"].float(), sd[f"head.cls_preds.{i}.bias"].float()
-            cls_in, reg_in = [View(F, 0, hc)], [View(F, hc, hc)]
             # The second tower conv and the 1x1 prediction conv run as one kernel (the activated tile stays on the
             # SM).  Raw variant: reference layout cat([reg, obj, cls], 1) (yolox_ffa.py:116).
             kw = dict(out_mode=N.OUT_NCHW_F32, out_ld=nch, out_batch_stride=nch * h * w)
-            self._conv(self.pred_raw_ops, wr1, br1, reg_in, self.logits[k], 3, out_coff=0, pred_weight=w_ro,
+            self._conv(self.pred_raw_ops, wr1, br1, reg_in, self.logits[k], k2, out_coff=0, pred_weight=w_ro,
                        pred_bias=b_ro, pred_act=N.ACT_NONE, **kw)
-            self._conv(self.pred_raw_ops, wc1, bc1, cls_in, self.logits[k], 3, out_coff=5, pred_weight=w_cl,
+            self._conv(self.pred_raw_ops, wc1, bc1, cls_in, self.logits[k], k2, out_coff=5, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             # Decoded variant: the decode runs in the same epilogue, rows of [B, A, 5+nc].  Stride as the reference
             # computes it: input_shape[0] / h (utils_bbox.py:285); equal to the integer mmdet stride.
             stride = float(self.in_h / h)
             kw, c_reg, c_cls = self._pred_out(nch, a_off)
-            op = self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
+            op = self._conv(self.pred_dec_ops, wr1, br1, reg_in, self.pred_store, k2, out_coff=c_reg, pred_weight=w_ro,
                             pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
-            self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+            self._conv(self.pred_dec_ops, wc1, bc1, cls_in, self.pred_store, k2, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             if not self.fp32:
                 self.pred_det_ops.append(op)
-                self._conv(self.pred_det_ops, wc1, bc1, cls_in, self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+                self._conv(self.pred_det_ops, wc1, bc1, cls_in, self.pred_store, k2, out_coff=c_cls, pred_weight=w_cl,
                            pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             a_off += h * w
         # the second tower convs exist twice (raw + decoded variants); count them once, plus the prediction convs

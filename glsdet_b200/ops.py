@@ -414,6 +414,36 @@ class Upsample2xOp:
                                             N.stream_ptr(stream)), "glsdet_upsample2x")
 
 
+class DepthwiseOp:
+    """dconv half of the reference's DWConv (models/base/baseConv.py:22-30): depthwise k x k conv (groups = channels) with
+    the folded BatchNorm and the activation, NHWC channel window -> NHWC channel window of the same storage type (16-bit,
+    or fp32 in the accuracy mode).  `weight` [C, 1, k, k] and `bias` [C] are the BN-folded fp32 values."""
+
+    def __init__(self, src: View, weight: torch.Tensor, bias: torch.Tensor, *, stride: int = 1, act: int = N.ACT_SILU,
+                 out: View):
+        c, one, k, k2 = weight.shape
+        assert one == 1 and k == k2 and c == src.c == out.c, (tuple(weight.shape), src.c, out.c)
+        b, h, w = src.bhw
+        pad = (k - 1) // 2
+        ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        assert out.bhw == (b, ho, wo) and out.t.dtype == src.t.dtype, (out.bhw, (b, ho, wo), out.t.dtype, src.t.dtype)
+        dt = src.t.dtype
+        self.dt = N.DT_F32 if dt == torch.float32 else N.dt_code(dt)
+        dev = src.t.device
+        self.w = weight.detach().float().reshape(c, k * k).t().contiguous().to(dev)   # [tap][C]
+        self.b = bias.detach().float().contiguous().to(dev)
+        self.src, self.out, self.k, self.stride, self.act = src, out, k, stride, act
+        self.flops = 2.0 * b * ho * wo * c * k * k
+        self._lib = N.load()
+
+    def launch(self, stream=None):
+        s, o = self.src, self.out
+        b, h, w = s.bhw
+        N.check(self._lib.glsdet_dwconv(s.t.data_ptr(), s.ld, s.coff, o.t.data_ptr(), o.ld, o.coff, b, h, w, s.c, self.k,
+                                        self.stride, self.w.data_ptr(), self.b.data_ptr(), self.act, self.dt,
+                                        N.stream_ptr(stream)), "glsdet_dwconv")
+
+
 class ConvOpF32:
     """fp32 accuracy-mode twin of ConvOp (glsdet_conv_f32: SIMT fp32 implicit GEMM, every tensor fp32).  Same
     arguments as ConvOp minus the tensor-core-only ones (fused prediction conv, batched / patch modes)."""

@@ -14,8 +14,11 @@ StateDict = Dict[str, torch.Tensor]
 
 def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Dict[str, tuple]:
     """Shapes of every state_dict entry of models/ffa/yolox_ffa.py YoloBody(num_classes, phi)."""
-    depth = {"tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
-    width = {"tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
+    depth = {"nano": 0.33, "tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
+    width = {"nano": 0.25, "tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
+    depthwise = phi == "nano"   # yolox_ffa.py:270: every k > 1 conv outside Focus becomes a DWConv (baseConv.py:22-30)
+    if depthwise and variant in ("p1", "p2"):
+        raise NotImplementedError("phi='nano' shapes exist for the P0 and stock topologies")
     shapes: Dict[str, tuple] = {}
 
     def bc(p, cin, cout, k):
@@ -24,6 +27,13 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
             shapes[f"{p}.bn.{n}"] = (cout,)
         shapes[p + ".bn.num_batches_tracked"] = ()
 
+    def cv(p, cin, cout, k):   # `Conv = DWConv if depthwise else BaseConv`
+        if depthwise:
+            bc(p + ".dconv", 1, cin, k)      # [cin, 1, k, k], groups = cin
+            bc(p + ".pconv", cin, cout, 1)
+        else:
+            bc(p, cin, cout, k)
+
     def csp(p, cin, cout, n):
         hid = int(cout * 0.5)
         bc(p + ".conv1", cin, hid, 1)
@@ -31,7 +41,7 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
         bc(p + ".conv3", 2 * hid, cout, 1)
         for j in range(n):
             bc(f"{p}.m.{j}.conv1", hid, hid, 1)
-            bc(f"{p}.m.{j}.conv2", hid, hid, 3)
+            cv(f"{p}.m.{j}.conv2", hid, hid, 3)
 
     base = int(width * 64)
     bdep = max(round(depth * 3), 1)
@@ -39,9 +49,9 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
     bc(f"{bb}.stem.conv", 12, base, 3)
     for name, cin, cout, n in (("dark2", base, base * 2, bdep), ("dark3", base * 2, base * 4, bdep * 3),
                                ("dark4", base * 4, base * 8, bdep * 3)):
-        bc(f"{bb}.{name}.0", cin, cout, 3)
+        cv(f"{bb}.{name}.0", cin, cout, 3)
         csp(f"{bb}.{name}.1", cout, cout, n)
-    bc(f"{bb}.dark5.0", base * 8, base * 16, 3)
+    cv(f"{bb}.dark5.0", base * 8, base * 16, 3)
     bc(f"{bb}.dark5.1.conv1", base * 16, base * 8, 1)
     bc(f"{bb}.dark5.1.conv2", base * 32, base * 16, 1)
     csp(f"{bb}.dark5.2", base * 16, base * 16, bdep)
@@ -55,11 +65,11 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
     csp("backbone.C3_p3", 2 * c0, c0, n)
     if p2:
         shapes["backbone.P3_Identity.conv.weight"], shapes["backbone.P3_Identity.conv.bias"] = (c0, c0, 7, 7), (c0,)
-    bc("backbone.bu_conv2", c0, c0, 3)
+    cv("backbone.bu_conv2", c0, c0, 3)
     csp("backbone.C3_n3", (3 if p2 else 2) * c0, c1, n)
     if p2:
         shapes["backbone.P4_Identity.conv.weight"], shapes["backbone.P4_Identity.conv.bias"] = (c1, c1, 5, 5), (c1,)
-    bc("backbone.bu_conv1", c1, c1, 3)
+    cv("backbone.bu_conv1", c1, c1, 3)
     csp("backbone.C3_n4", 2 * c1, c2, n)
 
     if p2:
@@ -104,8 +114,8 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
         for i, cin in enumerate((c0, c1, c2)):
             bc(f"head.stems.{i}", cin, hc, 1)
             for br in ("cls_convs", "reg_convs"):
-                bc(f"head.{br}.{i}.0", hc, hc, 3)
-                bc(f"head.{br}.{i}.1", hc, hc, 3)
+                cv(f"head.{br}.{i}.0", hc, hc, 3)
+                cv(f"head.{br}.{i}.1", hc, hc, 3)
             for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
                 shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
                 shapes[f"head.{name}.{i}.bias"] = (co,)
@@ -123,8 +133,8 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
         bc(f"head.stems.{i}", cin, hc, 1)
     for i in range(4):
         for br in ("cls_convs", "reg_convs"):
-            bc(f"head.{br}.{i}.0", hc, hc, 3)
-            bc(f"head.{br}.{i}.1", hc, hc, 3)
+            cv(f"head.{br}.{i}.0", hc, hc, 3)
+            cv(f"head.{br}.{i}.1", hc, hc, 3)
         for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
             shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
             shapes[f"head.{name}.{i}.bias"] = (co,)

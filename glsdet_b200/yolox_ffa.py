@@ -41,12 +41,27 @@ class BaseConv(nn.Module):
                            "through its parent module (CSPDarknet / YOLOPAFPN / YOLOXHead / YoloBody); it has no PyTorch forward")
 
 
+class DWConv(nn.Module):
+    """Parameter holder for the depthwise-separable conv of phi = 'nano' (reference: models/base/baseConv.py:22-30):
+    dconv = BaseConv(C, C, k, stride, groups=C), pconv = BaseConv(C, Cout, 1, 1).  Executed as glsdet_dwconv (csrc/dwconv.cu)
+    + the tcgen05 1x1 conv by the parent module's native plan."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride=1, act="silu"):
+        super().__init__()
+        self.dconv = BaseConv(in_channels, in_channels, ksize, stride, groups=in_channels, act=act)
+        self.pconv = BaseConv(in_channels, out_channels, 1, 1, groups=1, act=act)
+
+    def forward(self, x):
+        return self.dconv(x)   # raises: no PyTorch forward
+
+
 class Bottleneck(nn.Module):
-    def __init__(self, cin, cout, shortcut=True, expansion=0.5, act="silu"):
+    def __init__(self, cin, cout, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
         super().__init__()
         hidden = int(cout * expansion)
+        Conv = DWConv if depthwise else BaseConv
         self.conv1 = BaseConv(cin, hidden, 1, 1, act=act)
-        self.conv2 = BaseConv(hidden, cout, 3, 1, act=act)
+        self.conv2 = Conv(hidden, cout, 3, 1, act=act)
         self.use_add = shortcut and cin == cout
 
 
@@ -55,13 +70,11 @@ class CSPLayer(nn.Module):
 
     def __init__(self, in_channels, out_channels, n=1, shortcut=True, expansion=0.5, depthwise=False, act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') blocks are not part of the native path")
         hidden = int(out_channels * expansion)
         self.conv1 = BaseConv(in_channels, hidden, 1, 1, act=act)
         self.conv2 = BaseConv(in_channels, hidden, 1, 1, act=act)
         self.conv3 = BaseConv(2 * hidden, out_channels, 1, 1, act=act)
-        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, act=act) for _ in range(n)])
+        self.m = nn.Sequential(*[Bottleneck(hidden, hidden, shortcut, 1.0, depthwise, act=act) for _ in range(n)])
 
 
 class Focus(nn.Module):
@@ -205,20 +218,19 @@ class CSPDarknet(_PlanOwner):
     def __init__(self, dep_mul, wid_mul, out_features=("dark2", "dark3", "dark4", "dark5"), depthwise=False,
                  act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported")
         self.out_features = out_features
         self.act_name = act
         c = int(wid_mul * 64)
         d = max(round(dep_mul * 3), 1)
         self.base_channels = c
         self.stem = Focus(3, c, ksize=3, act=act)
+        Conv = DWConv if depthwise else BaseConv   # darknet.py:120
 
         def stage(cin, cout, n, shortcut=True, spp=False):
-            layers = [BaseConv(cin, cout, 3, 2, act=act)]
+            layers = [Conv(cin, cout, 3, 2, act=act)]
             if spp:
                 layers.append(SPPBottleneck(cout, cout, activation=act))
-            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, act=act))
+            layers.append(CSPLayer(cout, cout, n=n, shortcut=shortcut, depthwise=depthwise, act=act))
             return nn.Sequential(*layers)
 
         self.dark2 = stage(c, c * 2, d)
@@ -272,21 +284,20 @@ class YOLOXHead(_PlanOwner):
 
     def __init__(self, num_classes, width=1.0, in_channels=[256, 512, 1024, 256], act="silu", depthwise=False):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
         self.num_classes = num_classes
         hc = int(256 * width)
+        Conv = DWConv if depthwise else BaseConv   # yolox_ffa.py:15
         self.cls_convs, self.reg_convs = nn.ModuleList(), nn.ModuleList()
         self.cls_preds, self.reg_preds, self.obj_preds = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         self.stems = nn.ModuleList()
         self.csp = CSPLayer(int(0.5 * in_channels[0] * width), int(in_channels[0] * width), round(3 * 0.75), False,
-                            act=act)
+                            depthwise=depthwise, act=act)
         self.ftt = FTT(int(width * in_channels[0]))
         for i, cin in enumerate(in_channels):
             if i != 3:
                 self.stems.append(BaseConv(int(cin * width), hc, 1, 1, act=act))
-            self.cls_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 1, act=act)))
-            self.reg_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 1, act=act)))
+            self.cls_convs.append(nn.Sequential(Conv(hc, hc, 3, 1, act=act), Conv(hc, hc, 3, 1, act=act)))
+            self.reg_convs.append(nn.Sequential(Conv(hc, hc, 3, 1, act=act), Conv(hc, hc, 3, 1, act=act)))
             self.cls_preds.append(nn.Conv2d(hc, num_classes, 1, 1, 0))
             self.reg_preds.append(nn.Conv2d(hc, 4, 1, 1, 0))
             self.obj_preds.append(nn.Conv2d(hc, 1, 1, 1, 0))
@@ -312,20 +323,19 @@ class YOLOPAFPN(_PlanOwner):
     def __init__(self, depth=1.0, width=1.0, in_features=("dark2", "dark3", "dark4", "dark5"),
                  in_channels=[256, 512, 1024], depthwise=False, act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
         self.backbone = CSPDarknet(depth, width, depthwise=depthwise, act=act)
         self.in_features = in_features
         c0, c1, c2 = (int(c * width) for c in in_channels)
         n = round(3 * depth)
+        Conv = DWConv if depthwise else BaseConv   # yolox_ffa.py:125
         self.lateral_conv0 = BaseConv(c2, c1, 1, 1, act=act)
-        self.C3_p4 = CSPLayer(2 * c1, c1, n, False, act=act)
+        self.C3_p4 = CSPLayer(2 * c1, c1, n, False, depthwise=depthwise, act=act)
         self.reduce_conv1 = BaseConv(c1, c0, 1, 1, act=act)
-        self.C3_p3 = CSPLayer(2 * c0, c0, n, False, act=act)
-        self.bu_conv2 = BaseConv(c0, c0, 3, 2, act=act)
-        self.C3_n3 = CSPLayer(2 * c0, c1, n, False, act=act)
-        self.bu_conv1 = BaseConv(c1, c1, 3, 2, act=act)
-        self.C3_n4 = CSPLayer(2 * c1, c2, n, False, act=act)
+        self.C3_p3 = CSPLayer(2 * c0, c0, n, False, depthwise=depthwise, act=act)
+        self.bu_conv2 = Conv(c0, c0, 3, 2, act=act)
+        self.C3_n3 = CSPLayer(2 * c0, c1, n, False, depthwise=depthwise, act=act)
+        self.bu_conv1 = Conv(c1, c1, 3, 2, act=act)
+        self.C3_n4 = CSPLayer(2 * c1, c2, n, False, depthwise=depthwise, act=act)
         super().train(False)
 
     def _num_classes(self):

@@ -46,7 +46,7 @@ enum {
 };
 
 /* 16-bit storage type of an activation / weight tensor */
-enum { GLSDET_DT_BF16 = 0, GLSDET_DT_F16 = 1 };
+enum { GLSDET_DT_BF16 = 0, GLSDET_DT_F16 = 1, GLSDET_DT_F32 = 2 /* accuracy mode; glsdet_dwconv only */ };
 
 /* output layouts of the conv epilogue */
 enum {
@@ -260,6 +260,20 @@ int glsdet_nhwc_transpose_16(const void* src, void* dst, int32_t batch, int32_t 
  */
 int glsdet_upsample2x(const void* src, void* dst, int32_t batch, int32_t height, int32_t width, int32_t channels,
                       int32_t src_ld, int32_t src_coff, int32_t dst_ld, int32_t dst_coff, void* stream);
+
+/*
+ * Depthwise half of the reference's DWConv (yolox-drone/models/base/baseConv.py:22-30: dconv = BaseConv(C, C, k, stride,
+ * groups = C) followed by pconv = 1x1 BaseConv; phi = 'nano' builds every k > 1 conv outside Focus this way -
+ * models/ffa/yolox_ffa.py:15,125, models/ffa/darknet.py:48,120).  dst[b, oy, ox, dst_coff + c] =
+ * act(bias[c] + sum_{ky,kx} src[b, oy*stride + ky - pad, ox*stride + kx - pad, src_coff + c] * weight[ky*k + kx][c]),
+ * pad = (k - 1) / 2, zero padding, output size (H + 2 pad - k) / stride + 1.  src / dst: NHWC channel windows of the
+ * storage type `dtype` (GLSDET_DT_BF16 / _F16, or GLSDET_DT_F32 in the accuracy mode); weight fp32 [k*k][channels]
+ * with BatchNorm folded in by the caller, bias fp32 [channels]; act GLSDET_ACT_NONE / SILU / RELU / LRELU (exact
+ * expf-based SiLU).  HBM-bound SIMT kernel; the pconv half runs on glsdet_conv_*.
+ */
+int glsdet_dwconv(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff,
+                  int32_t batch, int32_t height, int32_t width, int32_t channels, int32_t ksize, int32_t stride,
+                  const float* weight, const float* bias, int32_t act, int32_t dtype, void* stream);
 
 /*
  * CSPDarknet backbone pieces that are not convolutions (the backbone's convolutions run on

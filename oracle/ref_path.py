@@ -95,16 +95,21 @@ class _emulate:
 
 def base_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int = 1, act: str = "silu") -> torch.Tensor:
     """act(bn(conv(x))): models/base/baseConv.py:6-16 (pad=(k-1)//2, conv bias=False, BN eps 1e-3, eval mode)."""
+    if (p + ".dconv.conv.weight") in sd:   # DWConv.forward (baseConv.py:22-30; phi = 'nano'): pconv(dconv(x))
+        return base_conv(sd, p + ".pconv", base_conv(sd, p + ".dconv", x, stride, act), 1, act)
     w = sd[p + ".conv.weight"]
     k = w.shape[-1]
+    groups = x.shape[1] // w.shape[1]   # 1, or the channel count for the depthwise half of a DWConv (baseConv.py:25)
     if _EMULATE_BF16:
         # same arithmetic as the reference but with the storage precision of the bf16 path: BN folded into the
         # weights, weights and layer outputs rounded to bf16, accumulation and bias in fp32
         scale = sd[p + ".bn.weight"].double() / torch.sqrt(sd[p + ".bn.running_var"].double() + BN_EPS)
         wf = (w.double() * scale.view(-1, 1, 1, 1)).float()
         bf = (sd[p + ".bn.bias"].double() - sd[p + ".bn.running_mean"].double() * scale).float()
+        if groups > 1:   # the depthwise kernel keeps its folded weights in fp32 (csrc/dwconv.cu)
+            return _q(_act(F.conv2d(_q(x), wf, bf, stride=stride, padding=(k - 1) // 2, groups=groups), act))
         return _q(_act(F.conv2d(_q(x), _q(wf, x), bf, stride=stride, padding=(k - 1) // 2), act))
-    y = F.conv2d(x, w, None, stride=stride, padding=(k - 1) // 2)
+    y = F.conv2d(x, w, None, stride=stride, padding=(k - 1) // 2, groups=groups)
     y = F.batch_norm(y, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"],
                      sd[p + ".bn.bias"], training=False, eps=BN_EPS)
     return _act(y, act)

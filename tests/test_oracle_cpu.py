@@ -134,3 +134,50 @@ def test_oracle_decode_variants_pinned_to_reference_golden():
     for name in ("no_sigmoid", "no_sigmoid_all", "cls_sigmoid", "xyxy"):
         got = ref_path.decode_outputs_variant(levels, shape, name).numpy()
         np.testing.assert_allclose(got, z[name], rtol=1e-6, atol=1e-6, err_msg=name)
+
+
+@pytest.mark.parametrize("case", ["p0", "stock"])
+def test_oracle_nano_dwconv_pinned_to_reference_golden(case):
+    """phi = 'nano' (DWConv = depthwise k x k + pointwise 1x1, models/base/baseConv.py:22-30): the oracle's backbone, neck,
+    head, decode and NMS against tests/golden/nano_cases.npz, which tests/golden/make_golden_nano.py recorded from the REAL
+    models/ffa/yolox_ffa.py / models/base/yolox.py YoloBody(nc, 'nano') run from an image; the state_dict keys (and their
+    order) of the drop-in modules against the real modules' keys."""
+    import json
+
+    z = np.load(GOLD / "nano_cases.npz")
+    m = json.loads((GOLD / "nano_meta.json").read_text())[case]
+    sd = ref_path.synthetic_state_dict(m["nc"], "nano", seed=m["seed"], flavour="calibrated", variant=m["variant"])
+    assert sorted(sd.keys()) == sorted(m["keys"])
+    x = torch.from_numpy(z[f"{case}_image"])
+    feats = ref_path.csp_darknet(sd, x)
+    tol = lambda ref: 1e-4 * max(1.0, ref.abs().max().item())
+    for name, f in zip(("dark2", "dark3", "dark4", "dark5"), feats):
+        if f"{case}_{name}" in z.files:
+            ref = torch.from_numpy(z[f"{case}_{name}"])
+            assert f.shape == ref.shape and (f - ref).abs().max().item() <= tol(ref), name
+    with torch.no_grad():
+        if case == "p0":
+            neck = ref_path.pafpn_neck(sd, feats)
+            logits = ref_path.yolox_head(sd, neck)
+        else:
+            neck = ref_path.pafpn_neck(sd, [None] + list(feats[1:]))[1:]
+            logits = ref_path.stock_head(sd, neck)
+    for i, t in enumerate(neck):
+        ref = torch.from_numpy(z[f"{case}_neck{i}"])
+        assert (t - ref).abs().max().item() <= tol(ref), ("neck", i)
+    for i, t in enumerate(logits):
+        ref = torch.from_numpy(z[f"{case}_logits{i}"])
+        assert (t - ref).abs().max().item() <= tol(ref), ("logits", i)
+    hw = [m["in_h"], m["in_w"]]
+    pred = torch.from_numpy(z[f"{case}_pred"])
+    res = ref_path.non_max_suppression(pred.clone(), m["nc"], hw, np.array(hw), False, m["conf"], m["nms_thr"])
+    for b in range(m["batch"]):
+        assert np.array_equal(res[b], z[f"{case}_nms{b}"]), b
+    # the drop-in modules expose the reference's keys in the reference's order (strict load works, DataParallel-safe)
+    if case == "p0":
+        from glsdet_b200.yolox_ffa import YoloBody
+    else:
+        from glsdet_b200.yolox_base import YoloBody
+    net = YoloBody(m["nc"], "nano")
+    assert list(net.state_dict().keys()) == m["keys"]
+    net.load_state_dict(sd, strict=True)

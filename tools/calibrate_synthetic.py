@@ -56,8 +56,10 @@ def main():
     orig = ref_path.base_conv
 
     def calibrating_base_conv(sd_, p, x, stride=1, act="silu"):
+        if (p + ".dconv.conv.weight") in sd_:   # DWConv (phi = 'nano'): the oracle recurses into dconv / pconv
+            return orig(sd_, p, x, stride, act)
         w = sd_[p + ".conv.weight"]
-        y = F.conv2d(x, w, None, stride=stride, padding=(w.shape[-1] - 1) // 2)
+        y = F.conv2d(x, w, None, stride=stride, padding=(w.shape[-1] - 1) // 2, groups=x.shape[1] // w.shape[1])
         sd_[p + ".bn.running_mean"] = y.mean(dim=(0, 2, 3))
         sd_[p + ".bn.running_var"] = y.var(dim=(0, 2, 3), unbiased=False).clamp_min(1e-4)
         changed[p + ".bn.running_mean"] = sd_[p + ".bn.running_mean"]
