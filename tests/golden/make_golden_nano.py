@@ -5,6 +5,10 @@ IMAGE.  Stored: the image, the backbone's feature maps, the neck outputs, the ra
 predictions and the NMS rows.  tests/golden/nano_cases.npz pins oracle/ref_path.py's DWConv branch and, through it, the
 CUDA path (csrc/dwconv.cu + the tcgen05 1x1 convs).
 
+Weights: glsdet_b200.synthetic "calibrated" flavour, recorded by
+    python tools/calibrate_synthetic.py --phi nano --nc 10 --seed 11 --size 256 --bn-beta 1.0
+    python tools/calibrate_synthetic.py --phi nano --nc 3 --seed 12 --variant stock --size 256 --bn-beta 1.0
+
 Run in the build container only (the GPU box has no /root/reference):
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_nano.py
 """
