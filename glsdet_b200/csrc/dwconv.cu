@@ -27,6 +27,7 @@ struct DwParams {
   int sld, scoff, dld, dcoff;
   int k, stride, act;
   int f16;             // 16-bit flavour (VEC == 8 only)
+  int xt, ry;          // 3x3 kernel: CTA tile = ry output rows x xt strips of TX pixels (x all channel vectors)
   int64_t total;       // B * Ho * Wo * (C / VEC)
 };
 
@@ -105,115 +106,175 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const DwParams p) {
   }
 }
 
-// 3x3 specialisation (every DWConv of the reference is 3x3): the generic kernel above measured 0.07 - 0.30 of the HBM peak -
-// nine dependent load -> FMA rounds per thread, 48 bytes through L1 per tap (16 of activations, 32 of weights) and 64-bit
-// index arithmetic per tap.  Here a thread owns TX horizontally adjacent output pixels of one channel vector: per kernel row
-// it issues all (TX - 1) * S + 3 column loads at once (independent, so their latencies overlap), every loaded pixel feeds up
-// to three outputs from registers (S = 1: 4.5 loads per output instead of 9), and the folded weights + bias sit in shared
-// memory (read once per TX outputs, bank-conflict free: lanes with the same channel vector broadcast).
-template <int VEC, int S, int TX>
-__global__ void __launch_bounds__(256) dw3_kernel(const DwParams p) {
-  extern __shared__ float s_w[];   // [9][C] weights, then [C] bias
-  pdl_prologue();
-  for (int i = threadIdx.x; i < 10 * p.C; i += blockDim.x) s_w[i] = (i < 9 * p.C) ? __ldg(p.w + i) : __ldg(p.bias + (i - 9 * p.C));
-  __syncthreads();
-  constexpr int NC = (TX - 1) * S + 3;   // input columns under TX outputs
-  const int nvec = p.C / VEC;
-  const int wt = (p.Wo + TX - 1) / TX;
-  const int64_t total = static_cast<int64_t>(p.B) * p.Ho * wt * nvec;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % nvec);
-    int64_t r = i / nvec;
-    const int xt = static_cast<int>(r % wt);
-    r /= wt;
-    const int oy = static_cast<int>(r % p.Ho);
-    const int b = static_cast<int>(r / p.Ho);
-    const int c0 = v * VEC;
-    const int ox0 = xt * TX;
-    const int ix0 = ox0 * S - 1;
-    float acc[TX][VEC];
+// 3x3 specialisation (every DWConv of the reference is 3x3).  The generic kernel above measured 0.07 - 0.30 of the HBM peak:
+// nine dependent load -> FMA rounds per thread, 48 bytes through L1 per tap (16 of activations, 32 of weights), 64-bit index
+// arithmetic and an exact SiLU (expf + IEEE division, ~20 instructions) per element - it is ISSUE-bound, not memory-bound.
+// Here:
+//   * a thread owns TX horizontally adjacent output pixels of one channel vector: per kernel row it issues all
+//     (TX - 1) * S + 3 column loads at once (independent: their latencies overlap) and every loaded pixel feeds up to three
+//     outputs from registers (S = 1: 4.5 loads and conversions per output instead of 9);
+//   * grid = (strips x channel vectors, output row, image): no 64-bit divisions, 32-bit offsets inside an image;
+//   * tiles whose 3 x NC input window lies inside the image take a path without any bounds predicate (zero padding only
+//     matters for the border strips);
+//   * folded weights + bias sit in shared memory, filled BEFORE griddepcontrol.wait (they are constants of the plan), read
+//     once per TX outputs, conflict-free (lanes with the same channel vector broadcast);
+//   * CTA tile = several output rows x strips (see the kernel): the input rows shared by neighbouring output rows are L1
+//     hits (one output row per CTA: 137 us for 3x3/1 C = 64 at 16 x 256^2, tiled: 115 us);
+//   * 16-bit storage: SiLU in the tanh form h + h tanh(h), h = x / 2 (one MUFU, three instructions; 2^-11 relative, the
+//     form the conv epilogues use); the fp32 accuracy mode keeps expf + IEEE division.
+// Measured (tools/dw_bench.py, L2 flushed, 16 x 1024^2 nano shapes): 0.30 - 0.46 of the HBM copy peak on the large layers
+// (generic kernel: 0.12 - 0.30), DRAM traffic = the algorithmic bytes (ncu: 134 MB read + 94 MB written for 134 + 134).
+// What is left is instruction issue, not memory: 977 instructions per warp (32 outputs x 8 channels: 288 FFMA, 144
+// conversions, 96 for SiLU, the rest addressing / packing) at IPC 2.1 with two CTAs per SM (103 registers).  Strips of two
+// pixels (more warps, more loads per output) and all 18 loads hoisted in front of the arithmetic measured the same
+// (137 - 141 us before the row tiling): the next step would be a vertical register sliding window (each input converted
+// once per strip instead of three times).
+template <int VEC, int F16>
+__device__ __forceinline__ void dw_unpack(const uint4& raw, float (&x)[VEC]) {
+  if constexpr (VEC == 8) {
+    unpack_16x2(raw.x, F16, x[0], x[1]);
+    unpack_16x2(raw.y, F16, x[2], x[3]);
+    unpack_16x2(raw.z, F16, x[4], x[5]);
+    unpack_16x2(raw.w, F16, x[6], x[7]);
+  } else {
+    x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y);
+    x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
+  }
+}
+
+template <int VEC, int S, int TX, int F16, bool INTERIOR, bool PRE>
+__device__ __forceinline__ void dw3_rows(const DwParams& p, const float* s_w, const uint8_t* img, int oy, int ix0, int c0,
+                                         float (&acc)[TX][VEC]) {
+  constexpr int NC = (TX - 1) * S + 3;
+  constexpr int ES = (VEC == 8) ? 2 : 4;   // element size in bytes
+  constexpr int NR = PRE ? 3 : 1;          // PRE: all 3 x NC loads are issued before any arithmetic (one latency per thread)
+  uint4 raw[NR][NC];
+  auto load_row = [&](int ky, uint4 (&dst)[NC]) {
+    const int iy = oy * S + ky - 1;
+    const bool rowok = INTERIOR || ((iy >= 0) && (iy < p.H));
+    const uint32_t rowoff = static_cast<uint32_t>(iy * p.W + ix0) * static_cast<uint32_t>(p.sld);   // elements; only used when valid
 #pragma unroll
-    for (int t = 0; t < TX; ++t)
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) acc[t][j] = s_w[9 * p.C + c0 + j];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * S + ky - 1;
-      const bool rowok = (iy >= 0) && (iy < p.H);
-      const int64_t rowoff = (static_cast<int64_t>(b) * p.H + iy) * p.W * p.sld + p.scoff + c0;
-      uint4 raw[NC];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        const int ix = ix0 + j;
-        raw[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (rowok && ix >= 0 && ix < p.W) {
-          const int64_t off = rowoff + static_cast<int64_t>(ix) * p.sld;
-          if constexpr (VEC == 8) raw[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.src) + off));
-          else raw[j] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.src) + off));
-        }
-      }
-      float wk[3][VEC];
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-        for (int j = 0; j < VEC; j += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * p.C + c0 + j);
-          wk[kx][j] = t4.x; wk[kx][j + 1] = t4.y; wk[kx][j + 2] = t4.z; wk[kx][j + 3] = t4.w;
-        }
-#pragma unroll
-      for (int j = 0; j < NC; ++j) {
-        float x[VEC];
-        if constexpr (VEC == 8) {
-          unpack_16x2(raw[j].x, p.f16, x[0], x[1]);
-          unpack_16x2(raw[j].y, p.f16, x[2], x[3]);
-          unpack_16x2(raw[j].z, p.f16, x[4], x[5]);
-          unpack_16x2(raw[j].w, p.f16, x[6], x[7]);
-        } else {
-          x[0] = __uint_as_float(raw[j].x); x[1] = __uint_as_float(raw[j].y);
-          x[2] = __uint_as_float(raw[j].z); x[3] = __uint_as_float(raw[j].w);
-        }
-#pragma unroll
-        for (int t = 0; t < TX; ++t) {
-          const int kx = j - t * S;   // compile-time after unrolling
-          if (kx >= 0 && kx < 3) {
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) acc[t][q] = fmaf(x[q], wk[kx][q], acc[t][q]);
-          }
-        }
-      }
+    for (int j = 0; j < NC; ++j) {
+      if (INTERIOR || (rowok && (ix0 + j >= 0) && (ix0 + j < p.W)))
+        dst[j] = __ldg(reinterpret_cast<const uint4*>(img + static_cast<size_t>(rowoff + static_cast<uint32_t>(j * p.sld)) * ES));
+      else
+        dst[j] = make_uint4(0u, 0u, 0u, 0u);
     }
-    const int64_t orow = (static_cast<int64_t>(b) * p.Ho + oy) * p.Wo;
+  };
+  if constexpr (PRE) {
 #pragma unroll
-    for (int t = 0; t < TX; ++t) {
-      const int ox = ox0 + t;
-      if (ox >= p.Wo) break;
+    for (int ky = 0; ky < 3; ++ky) load_row(ky, raw[ky]);
+  }
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[t][q] = dw_act(acc[t][q], p.act);
-      const int64_t ooff = (orow + ox) * p.dld + p.dcoff + c0;
-      if constexpr (VEC == 8) {
-        uint4 o;
-        o.x = pack_16x2(acc[t][0], acc[t][1], p.f16);
-        o.y = pack_16x2(acc[t][2], acc[t][3], p.f16);
-        o.z = pack_16x2(acc[t][4], acc[t][5], p.f16);
-        o.w = pack_16x2(acc[t][6], acc[t][7], p.f16);
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.dst) + ooff) = o;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.dst) + ooff) =
-            make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+  for (int ky = 0; ky < 3; ++ky) {
+    if constexpr (!PRE) load_row(ky, raw[0]);
+    const uint4 (&rw)[NC] = raw[PRE ? ky : 0];
+    float wk[3][VEC];
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * p.C + ((j >> 2) * (p.C / VEC) + c0 / VEC) * 4);
+        wk[kx][j] = t4.x; wk[kx][j + 1] = t4.y; wk[kx][j + 2] = t4.z; wk[kx][j + 3] = t4.w;
+      }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      float x[VEC];
+      dw_unpack<VEC, F16>(rw[j], x);
+#pragma unroll
+      for (int t = 0; t < TX; ++t) {
+        const int kx = j - t * S;   // compile-time after unrolling
+        if (kx >= 0 && kx < 3) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[t][q] = fmaf(x[q], wk[kx][q], acc[t][q]);
+        }
       }
     }
   }
 }
 
-template <int VEC, int S, int TX>
-static void launch_dw3(const DwParams& p, cudaStream_t st) {
+template <int VEC, int S, int TX, int F16, bool PRE>
+__global__ void __launch_bounds__(256) dw3_kernel(const DwParams p) {
+  extern __shared__ float s_w[];   // [9][C] weights, then [C] bias
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // shared layout [tap | bias][VEC / 4 quads][channel vector][4 floats]: the channel vectors of a quarter-warp read
+  // consecutive 16-byte words (conflict-free; [tap][C] order put vectors 32 bytes apart: 5.8-way conflicts in the ncu capture)
+  {
+    const int nv = p.C / VEC;
+    for (int i = threadIdx.x; i < 10 * p.C; i += blockDim.x) {
+      const int tap = i / p.C, c = i - tap * p.C;
+      const int v = c / VEC, e = c - v * VEC;
+      s_w[tap * p.C + ((e >> 2) * nv + v) * 4 + (e & 3)] = (tap < 9) ? __ldg(p.w + i) : __ldg(p.bias + c);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+  constexpr int NC = (TX - 1) * S + 3;
+  constexpr int ES = (VEC == 8) ? 2 : 4;
+  // CTA tile = p.ry output rows x p.xt strips x all channel vectors (lanes: channel vector fastest, then strip, then row):
+  // the three input rows an output row needs are shared with its neighbours INSIDE the CTA (L1 hits) - with one output row
+  // per CTA every input row travelled L2 -> SM three times
+  const uint32_t nvec = static_cast<uint32_t>(p.C / VEC);
+  const uint32_t wt = static_cast<uint32_t>((p.Wo + TX - 1) / TX);
+  const uint32_t slab = static_cast<uint32_t>(p.xt) * nvec;          // threads of one row of the tile
+  const uint32_t r = threadIdx.x / slab;
+  const uint32_t in_row = threadIdx.x - r * slab;
+  const uint32_t xl = in_row / nvec;
+  const int xt = static_cast<int>(blockIdx.x * static_cast<uint32_t>(p.xt) + xl);
+  const int c0 = static_cast<int>(in_row - xl * nvec) * VEC;
+  const int oy = static_cast<int>(blockIdx.y * static_cast<uint32_t>(p.ry) + r);
+  const int b = static_cast<int>(blockIdx.z);
+  if (r >= static_cast<uint32_t>(p.ry) || static_cast<uint32_t>(xt) >= wt || oy >= p.Ho) return;
+  const int ox0 = xt * TX;
+  const int ix0 = ox0 * S - 1;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src) +
+                       (static_cast<size_t>(b) * p.H * p.W * p.sld + p.scoff + c0) * ES;   // this image, this channel vector
+  float acc[TX][VEC];
+#pragma unroll
+  for (int t = 0; t < TX; ++t)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[t][j] = s_w[9 * p.C + ((j >> 2) * (p.C / VEC) + c0 / VEC) * 4 + (j & 3)];
+  const bool interior = (oy * S >= 1) && (oy * S + 1 < p.H) && (ix0 >= 0) && (ix0 + NC <= p.W);
+  if (interior) dw3_rows<VEC, S, TX, F16, true, PRE>(p, s_w, img, oy, ix0, c0, acc);
+  else dw3_rows<VEC, S, TX, F16, false, false>(p, s_w, img, oy, ix0, c0, acc);
+  uint8_t* orow = reinterpret_cast<uint8_t*>(p.dst) +
+                  ((static_cast<size_t>(b) * p.Ho + oy) * p.Wo * p.dld + p.dcoff + c0) * ES;
+#pragma unroll
+  for (int t = 0; t < TX; ++t) {
+    const int ox = ox0 + t;
+    if (ox >= p.Wo) break;
+    uint8_t* o = orow + static_cast<size_t>(static_cast<uint32_t>(ox) * static_cast<uint32_t>(p.dld)) * ES;
+    if constexpr (VEC == 8) {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[t][q] = (p.act == GLSDET_ACT_SILU) ? silu_fast(acc[t][q]) : dw_act(acc[t][q], p.act);
+      uint4 v;
+      v.x = pack_16x2(acc[t][0], acc[t][1], F16);
+      v.y = pack_16x2(acc[t][2], acc[t][3], F16);
+      v.z = pack_16x2(acc[t][4], acc[t][5], F16);
+      v.w = pack_16x2(acc[t][6], acc[t][7], F16);
+      *reinterpret_cast<uint4*>(o) = v;
+    } else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[t][q] = dw_act(acc[t][q], p.act);
+      *reinterpret_cast<float4*>(o) = make_float4(acc[t][0], acc[t][1], acc[t][2], acc[t][3]);
+    }
+  }
+}
+
+template <int VEC, int S, int TX, int F16, bool PRE = false>
+static void launch_dw3(DwParams p, cudaStream_t st) {
   const int wt = (p.Wo + TX - 1) / TX;
-  const int64_t total = static_cast<int64_t>(p.B) * p.Ho * wt * (p.C / VEC);
-  const int64_t want = (total + 255) / 256;
-  const int64_t cap = static_cast<int64_t>(device_sm_count()) * 16;
-  const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
-  launch_pdl(dw3_kernel<VEC, S, TX>, dim3(grid), dim3(256), static_cast<size_t>(10 * p.C) * sizeof(float), st, p);
+  const int nvec = p.C / VEC;
+  int xt = 64 / nvec;                   // about 64 threads per tile row
+  if (xt < 1) xt = 1;
+  if (xt > wt) xt = wt;
+  int ry = 256 / (xt * nvec);           // rows of the tile: 256 threads per CTA
+  if (ry < 1) ry = 1;
+  if (ry > p.Ho) ry = p.Ho;
+  p.xt = xt; p.ry = ry;
+  const int threads = ((xt * nvec * ry + 31) / 32) * 32;
+  const dim3 grid(static_cast<unsigned>((wt + xt - 1) / xt), static_cast<unsigned>((p.Ho + ry - 1) / ry), static_cast<unsigned>(p.B));
+  launch_pdl(dw3_kernel<VEC, S, TX, F16, PRE>, grid, dim3(threads), static_cast<size_t>(10 * p.C) * sizeof(float), st, p);
 }
 
 }  // namespace glsdet
@@ -252,11 +313,13 @@ extern "C" int glsdet_dwconv(const void* src, int32_t src_ld, int32_t src_coff, 
   const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool generic_only = getenv("GLSDET_DW_GENERIC") != nullptr;   // tests: force the generic kernel
-  if (ksize == 3 && channels <= 1024 && !generic_only) {   // weights + bias of the 3x3 kernel: 40 bytes per channel of shared memory
-    if (vec == 8 && stride == 1) launch_dw3<8, 1, 4>(p, st);
-    else if (vec == 8) launch_dw3<8, 2, 2>(p, st);
-    else if (stride == 1) launch_dw3<4, 1, 4>(p, st);
-    else launch_dw3<4, 2, 2>(p, st);
+  const bool fits32 = static_cast<int64_t>(height) * width * src_ld < (1ll << 31) && p.Ho <= 65535 && batch <= 65535;
+  p.xt = p.ry = 1;
+  if (ksize == 3 && channels <= 1024 && fits32 && !generic_only) {   // weights + bias of the 3x3 kernel: 40 bytes per channel of shared memory
+    if (vec == 8 && stride == 1) { if (p.f16) launch_dw3<8, 1, 4, 1>(p, st); else launch_dw3<8, 1, 4, 0>(p, st); }
+    else if (vec == 8) { if (p.f16) launch_dw3<8, 2, 2, 1>(p, st); else launch_dw3<8, 2, 2, 0>(p, st); }
+    else if (stride == 1) launch_dw3<4, 1, 4, 0>(p, st);
+    else launch_dw3<4, 2, 2, 0>(p, st);
     return count_launch("dw3_kernel");
   }
   if (vec == 8) launch_pdl(dwconv_kernel<8>, dim3(grid), dim3(256), 0, st, p);
