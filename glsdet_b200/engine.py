@@ -95,12 +95,12 @@ class FFAPathPlan:
         elif "stems" in self.parts:
             self.c0, self.c1, self.c2 = (sd[f"head.stems.{i}.conv.weight"].shape[1] for i in range(3))
         else:   # towers only: the neck-side buffers are never touched, any consistent sizes do
-            self.c0 = sd["head.cls_convs.0.0.conv.weight"].shape[1]
+            self.c0 = sd["head.cls_preds.0.weight"].shape[1]
             self.c1, self.c2 = 2 * self.c0, 4 * self.c0
         if "stems" in self.parts:
             self.hc = sd["head.stems.0.conv.weight"].shape[0]            # head width int(256 * width)
         elif "towers" in self.parts:
-            self.hc = sd["head.cls_convs.0.0.conv.weight"].shape[1]
+            self.hc = sd["head.cls_preds.0.weight"].shape[1]             # (the tower convs may be DWConvs: no .conv.weight)
         else:
             self.hc = self.c0
         if variant == "ffa" and "stems" in self.parts:

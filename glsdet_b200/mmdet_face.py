@@ -96,10 +96,31 @@ def _check_norm(norm_cfg):
         raise NotImplementedError("the native plan folds BatchNorm with eps=1e-3 (YOLOX default)")
 
 
+class _DWSepConv(nn.Module):
+    """Parameter holder of mmcv's DepthwiseSeparableConvModule as the YOLOX modules build it with `use_depthwise=True`
+    (necks/yolox_pafpn.py:55, utils/csp_layer.py:44, dense_heads/yolox_head.py:146-147): depthwise_conv = ConvModule(C, C, k,
+    stride, groups=C) and pointwise_conv = ConvModule(C, Cout, 1), each conv -> BN -> act.  mmcv is absent, so this layout
+    (attribute names depthwise_conv / pointwise_conv, norm and activation on both halves: mmcv 1.x defaults dw_norm_cfg =
+    pw_norm_cfg = norm_cfg, dw_act_cfg = pw_act_cfg = act_cfg) is restated; the math is the yolox-drone DWConv
+    (models/base/baseConv.py:22-30), which IS pinned, and runs on glsdet_dwconv + the tcgen05 1x1 conv."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride, act):
+        super().__init__()
+        self.depthwise_conv = BaseConv(in_channels, in_channels, ksize, stride, groups=in_channels, act=act)
+        self.pointwise_conv = BaseConv(in_channels, out_channels, 1, 1, act=act)
+
+
+def _conv3(depthwise, cin, cout, stride, act):
+    return _DWSepConv(cin, cout, 3, stride, act) if depthwise else BaseConv(cin, cout, 3, stride, act=act)
+
+
+_DW_MAP = ((".depthwise_conv.", ".dconv."), (".pointwise_conv.", ".pconv."))
+
+
 class _CSPLayer(nn.Module):
     """mmdet/models/utils/csp_layer.py:75-150 parameter layout (main_conv, short_conv, final_conv, blocks.j.conv1/2)."""
 
-    def __init__(self, in_channels, out_channels, num_blocks, act):
+    def __init__(self, in_channels, out_channels, num_blocks, act, depthwise=False):
         super().__init__()
         mid = int(out_channels * 0.5)
         self.main_conv = BaseConv(in_channels, mid, 1, 1, act=act)
@@ -110,7 +131,7 @@ class _CSPLayer(nn.Module):
             def __init__(self):
                 super().__init__()
                 self.conv1 = BaseConv(mid, mid, 1, 1, act=act)
-                self.conv2 = BaseConv(mid, mid, 3, 1, act=act)
+                self.conv2 = _conv3(depthwise, mid, mid, 1, act)
 
         self.blocks = nn.Sequential(*[_Block() for _ in range(num_blocks)])
 
@@ -135,8 +156,8 @@ class YOLOXPAFPN(_PlanOwner):
                  upsample_cfg=dict(scale_factor=2, mode="nearest"), conv_cfg=None,
                  norm_cfg=dict(type="BN", momentum=0.03, eps=0.001), act_cfg=dict(type="Swish"), init_cfg=None):
         super().__init__()
-        if use_depthwise or conv_cfg is not None:
-            raise NotImplementedError("depthwise / custom conv layers are not supported by the native path")
+        if conv_cfg is not None:
+            raise NotImplementedError("custom conv layers are not supported by the native path")
         if len(in_channels) != 3 or upsample_cfg.get("scale_factor", 2) != 2 or upsample_cfg.get("mode") != "nearest":
             raise NotImplementedError("the native plan implements the 3-level nearest-x2 YOLOX PAFPN")
         if not (in_channels[1] == 2 * in_channels[0] and in_channels[2] == 4 * in_channels[0]):
@@ -148,11 +169,11 @@ class YOLOXPAFPN(_PlanOwner):
         self.reduce_layers, self.top_down_blocks = nn.ModuleList(), nn.ModuleList()
         for idx in range(2, 0, -1):
             self.reduce_layers.append(BaseConv(in_channels[idx], in_channels[idx - 1], 1, 1, act=act))
-            self.top_down_blocks.append(_CSPLayer(in_channels[idx - 1] * 2, in_channels[idx - 1], num_csp_blocks, act))
+            self.top_down_blocks.append(_CSPLayer(in_channels[idx - 1] * 2, in_channels[idx - 1], num_csp_blocks, act, use_depthwise))
         self.downsamples, self.bottom_up_blocks = nn.ModuleList(), nn.ModuleList()
         for idx in range(2):
-            self.downsamples.append(BaseConv(in_channels[idx], in_channels[idx], 3, 2, act=act))
-            self.bottom_up_blocks.append(_CSPLayer(in_channels[idx] * 2, in_channels[idx + 1], num_csp_blocks, act))
+            self.downsamples.append(_conv3(use_depthwise, in_channels[idx], in_channels[idx], 2, act))
+            self.bottom_up_blocks.append(_CSPLayer(in_channels[idx] * 2, in_channels[idx + 1], num_csp_blocks, act, use_depthwise))
         self.out_convs = nn.ModuleList([BaseConv(c, out_channels, 1, 1, act=act) for c in in_channels])
         nn.Module.train(self, False)
 
@@ -172,7 +193,7 @@ class YOLOXPAFPN(_PlanOwner):
                 if k.startswith(a):
                     k = b + k[len(a):]
                     break
-            for a, b in _CSP_MAP:
+            for a, b in _CSP_MAP + _DW_MAP:
                 k = k.replace(a, b)
             out["backbone." + k] = v
         return out
@@ -206,8 +227,8 @@ class YOLOXHead(_PlanOwner):
                  norm_cfg=dict(type="BN", momentum=0.03, eps=0.001), act_cfg=dict(type="Swish"), loss_cls=None,
                  loss_bbox=None, loss_obj=None, loss_l1=None, train_cfg=None, test_cfg=None, init_cfg=None):
         super().__init__()
-        if use_depthwise or dcn_on_last_conv or conv_cfg is not None:
-            raise NotImplementedError("depthwise / DCN / custom conv layers are not supported by the native path")
+        if dcn_on_last_conv or conv_cfg is not None:
+            raise NotImplementedError("DCN / custom conv layers are not supported by the native path")
         if stacked_convs != 2 or list(strides) != [8, 16, 32] or in_channels != feat_channels:
             raise NotImplementedError("the native plan implements stacked_convs=2, strides [8,16,32], "
                                       "in_channels == feat_channels")
@@ -221,7 +242,7 @@ class YOLOXHead(_PlanOwner):
         fc = feat_channels
 
         def tower():
-            return nn.Sequential(BaseConv(in_channels, fc, 3, 1, act=act), BaseConv(fc, fc, 3, 1, act=act))
+            return nn.Sequential(_conv3(use_depthwise, in_channels, fc, 1, act), _conv3(use_depthwise, fc, fc, 1, act))
 
         self.multi_level_cls_convs = nn.ModuleList([tower() for _ in strides])
         self.multi_level_reg_convs = nn.ModuleList([tower() for _ in strides])
@@ -247,6 +268,8 @@ class YOLOXHead(_PlanOwner):
                 if k.startswith(a):
                     k = b + k[len(a):]
                     break
+            for a, b in _DW_MAP:
+                k = k.replace(a, b)
             out["head." + k] = v
         return out
 

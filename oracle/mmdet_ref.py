@@ -46,6 +46,8 @@ def drone_to_mmdet_keys(sd: StateDict) -> (StateDict, StateDict):
     for k, v in sd.items():
         if k.startswith("backbone.backbone."):
             continue
+        # phi = 'nano' (DWConv, baseConv.py:22-30) <-> mmcv DepthwiseSeparableConvModule (use_depthwise=True)
+        k = k.replace(".dconv.", ".depthwise_conv.").replace(".pconv.", ".pointwise_conv.")
         for a, b in head_map:
             if k.startswith(a):
                 head[b + k[len(a):]] = v

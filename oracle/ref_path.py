@@ -95,8 +95,11 @@ class _emulate:
 
 def base_conv(sd: StateDict, p: str, x: torch.Tensor, stride: int = 1, act: str = "silu") -> torch.Tensor:
     """act(bn(conv(x))): models/base/baseConv.py:6-16 (pad=(k-1)//2, conv bias=False, BN eps 1e-3, eval mode)."""
-    if (p + ".dconv.conv.weight") in sd:   # DWConv.forward (baseConv.py:22-30; phi = 'nano'): pconv(dconv(x))
-        return base_conv(sd, p + ".pconv", base_conv(sd, p + ".dconv", x, stride, act), 1, act)
+    # DWConv.forward (baseConv.py:22-30; phi = 'nano'): pconv(dconv(x)); the same block under mmcv's names
+    # (DepthwiseSeparableConvModule: depthwise_conv / pointwise_conv) for the mmdet face with use_depthwise=True
+    for dn, pn in ((".dconv", ".pconv"), (".depthwise_conv", ".pointwise_conv")):
+        if (p + dn + ".conv.weight") in sd:
+            return base_conv(sd, p + pn, base_conv(sd, p + dn, x, stride, act), 1, act)
     w = sd[p + ".conv.weight"]
     k = w.shape[-1]
     groups = x.shape[1] // w.shape[1]   # 1, or the channel count for the depthwise half of a DWConv (baseConv.py:25)

@@ -114,3 +114,35 @@ def test_mmdet_oracle_pinned_to_reference_source_golden():
         for i, (d, l) in enumerate(res):
             assert np.array_equal(np.asarray(l), z[f"{tag}_labels{i}"]), (tag, i)
             assert np.allclose(np.asarray(d), z[f"{tag}_dets{i}"], rtol=1e-6, atol=1e-5), (tag, i)
+
+
+def test_mmdet_use_depthwise_matches_the_pinned_nano_model():
+    """use_depthwise=True (mmcv DepthwiseSeparableConvModule in necks/yolox_pafpn.py:55, utils/csp_layer.py:44,
+    dense_heads/yolox_head.py:146-147) is the yolox-drone DWConv under other key names: the nano weights of the stock
+    YOLOX renamed onto the mmdet modules (oracle restatement AND the drop-in modules' own key translation) reproduce the
+    golden logits recorded from the REAL models/base/yolox.py YoloBody(nc, 'nano') (tests/golden/make_golden_nano.py)."""
+    from glsdet_b200.mmdet_face import YOLOXHead, YOLOXPAFPN
+
+    z = np.load(GOLD / "nano_cases.npz")
+    m = json.loads((GOLD / "nano_meta.json").read_text())["stock"]
+    sd = ref_path.synthetic_state_dict(m["nc"], "nano", seed=m["seed"], flavour="calibrated", variant="stock")
+    neck_sd, head_sd = mmdet_ref.drone_to_mmdet_keys(sd)
+    assert any(".depthwise_conv." in k for k in neck_sd) and any(".pointwise_conv." in k for k in head_sd)
+    feats = [torch.from_numpy(z[f"stock_dark{i}"]) for i in (3, 4, 5)]
+    with torch.no_grad():
+        p = mmdet_ref.yolox_pafpn(neck_sd, feats)
+        cls, box, obj = mmdet_ref.yolox_head_forward(head_sd, p)
+    for i in range(3):
+        got = torch.cat([box[i], obj[i], cls[i]], 1).numpy()
+        np.testing.assert_allclose(got, z[f"stock_logits{i}"], rtol=1e-4, atol=5e-5)
+    # the drop-in modules: mmdet YOLOX-nano config (configs/yolox/yolox_nano_8x8_300e_coco.py shapes), strict load, and the
+    # key translation back to the plan's naming is the inverse of the renaming above
+    neck = YOLOXPAFPN(in_channels=[64, 128, 256], out_channels=64, num_csp_blocks=1, use_depthwise=True)
+    head = YOLOXHead(num_classes=m["nc"], in_channels=64, feat_channels=64, use_depthwise=True)
+    neck.load_state_dict(neck_sd, strict=True)
+    head.load_state_dict(head_sd, strict=True)
+    back = dict(neck._plan_state_dict())
+    back.update(head._plan_state_dict())
+    want = {k for k in sd if not k.startswith("backbone.backbone.")}
+    assert set(back) == want
+    assert all(torch.equal(back[k], sd[k]) for k in want)

@@ -190,3 +190,30 @@ def test_nano_fp32_accuracy_mode(native_lib, cuda_device):
     for i, t in enumerate(net(x)):
         ref = torch.from_numpy(z[f"p0_logits{i}"])
         assert rel_l2(t, ref) <= 1e-3, (i, rel_l2(t, ref))
+
+
+def test_mmdet_face_use_depthwise(native_lib, cuda_device):
+    """mmdet YOLOXPAFPN / YOLOXHead with use_depthwise=True (mmcv DepthwiseSeparableConvModule; YOLOX-nano config shapes)
+    on the native path: the stock nano weights renamed to mmdet's keys give the logits of the REAL models/base/yolox.py
+    nano model (golden), and get_bboxes runs on them."""
+    from glsdet_b200.mmdet_face import YOLOXHead, YOLOXPAFPN
+    from oracle import mmdet_ref
+
+    z = np.load(GOLD / "nano_cases.npz")
+    m = json.loads((GOLD / "nano_meta.json").read_text())["stock"]
+    sd = ref_path.synthetic_state_dict(m["nc"], "nano", seed=m["seed"], flavour="calibrated", variant="stock")
+    neck_sd, head_sd = mmdet_ref.drone_to_mmdet_keys(sd)
+    neck = YOLOXPAFPN(in_channels=[64, 128, 256], out_channels=64, num_csp_blocks=1, use_depthwise=True)
+    head = YOLOXHead(num_classes=m["nc"], in_channels=64, feat_channels=64, use_depthwise=True,
+                     test_cfg=dict(score_thr=0.01, nms=dict(type="nms", iou_threshold=0.65)))
+    neck.load_state_dict(neck_sd, strict=True)
+    head.load_state_dict(head_sd, strict=True)
+    neck, head = neck.to(cuda_device).eval(), head.to(cuda_device).eval()
+    feats = tuple(torch.from_numpy(z[f"stock_dark{i}"]).to(cuda_device) for i in (3, 4, 5))
+    cls, box, obj = head(neck(feats))
+    for i in range(3):
+        got = torch.cat([box[i], obj[i], cls[i]], 1)
+        ref = torch.from_numpy(z[f"stock_logits{i}"])
+        assert rel_l2(got, ref) <= 2e-2, (i, rel_l2(got, ref))
+    res = head.get_bboxes(cls, box, obj, img_metas=[dict(scale_factor=[1.0, 1.0, 1.0, 1.0])] * m["batch"])
+    assert len(res) == m["batch"] and res[0][0].shape[1] == 5 and torch.isfinite(res[0][0]).all()

@@ -189,3 +189,38 @@ def test_plan_graph_matches_oracle(variant, phi, precision, op_models):
     for i, (t, r) in enumerate(zip(plan.logits, ref)):
         assert t.shape == r.shape
         assert _rel(t, r) <= tol, (i, _rel(t, r))
+
+
+def test_mmdet_depthwise_plans_match_golden(op_models):
+    """mmdet face with use_depthwise=True: the neck (+ out_convs) plan and the towers-only plan built from the drop-in
+    modules' translated state dicts, against the golden logits of the real stock nano model."""
+    import json
+    from pathlib import Path
+
+    engine, _ = op_models
+    from glsdet_b200.mmdet_face import YOLOXHead, YOLOXPAFPN
+    from oracle import mmdet_ref
+
+    gold = Path(__file__).resolve().parent / "golden"
+    z = np.load(gold / "nano_cases.npz")
+    m = json.loads((gold / "nano_meta.json").read_text())["stock"]
+    sd = ref_path.synthetic_state_dict(m["nc"], "nano", seed=m["seed"], flavour="calibrated", variant="stock")
+    neck_sd, head_sd = mmdet_ref.drone_to_mmdet_keys(sd)
+    neck = YOLOXPAFPN(in_channels=[64, 128, 256], out_channels=64, num_csp_blocks=1, use_depthwise=True)
+    head = YOLOXHead(num_classes=m["nc"], in_channels=64, feat_channels=64, use_depthwise=True)
+    neck.load_state_dict(neck_sd, strict=True)
+    head.load_state_dict(head_sd, strict=True)
+    b, hw = m["batch"], (m["in_h"], m["in_w"])
+    feats = [torch.from_numpy(z[f"stock_dark{i}"]) for i in (3, 4, 5)]
+    pn = engine.FFAPathPlan(neck._plan_state_dict(), b, hw, 1, device="cpu", parts=neck._parts, variant="stock",
+                            precision="fp32")
+    pn.load_features(feats)
+    pn.run_neck()
+    pn.run_stems()
+    p_k = pn.stem_outputs_nchw()
+    ph = engine.FFAPathPlan(head._plan_state_dict(), b, hw, m["nc"], device="cpu", parts=head._parts, variant="stock",
+                            decode="mmdet", precision="fp32")
+    ph.load_tower_inputs(p_k)
+    ph.run_towers(False)
+    for i, t in enumerate(ph.logits):
+        assert _rel(t, torch.from_numpy(z[f"stock_logits{i}"])) <= 1e-4, i
