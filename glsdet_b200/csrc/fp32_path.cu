@@ -271,3 +271,98 @@ extern "C" int glsdet_scale_pixel_shuffle_f32(const float* x, const float* gate,
       x, gate, dst, height, width, out_channels, dst_ld, dst_coff, total);
   return count_launch("scale_shuffle_f32_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------- batched fp32 GEMM
+// The dot-product non-local block (yolox-drone/models/new/Non_local_family.py:32-48; models/block/non_local/
+// Identity_Conv.py:205-246) in the fp32 accuracy mode.  The reference forms P = theta^T phi / T ([T, T]) and y = P g; with
+// no softmax in between the same y is  theta (phi^T g / T): one [C, C] matrix per patch image instead of the [T, T] one.
+// Both products are batched GEMMs over NHWC fp32 channel windows:
+//     C[b][m][n] = alpha * sum_k A[b](m, k) * B[b][k][n]
+// with A stored [M][K] (a_trans = 0: y = theta M) or [K][M] (a_trans = 1: M = phi^T g, k = pixel).  Plain SIMT FMA, fixed
+// summation order (k ascending) - deterministic; CTA = 64 x 64 outputs, thread = 4 x 4, K in slices of 16.
+namespace glsdet {
+
+struct BGemmParams {
+  const float* A; const float* B; float* C;
+  long long a_bs, b_bs, c_bs;
+  int lda, ldb, ldc;
+  int M, N, K, a_trans;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256) bgemm_f32_kernel(const BGemmParams p) {
+  __shared__ float sA[kFK][kFM + 4];   // [k][m]
+  __shared__ float sB[kFK][kFN + 4];   // [k][n]
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * kFM, n0 = blockIdx.x * kFN;
+  const float* A = p.A + static_cast<long long>(b) * p.a_bs;
+  const float* Bm = p.B + static_cast<long long>(b) * p.b_bs;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  for (int k0 = 0; k0 < p.K; k0 += kFK) {
+    for (int e = threadIdx.x; e < kFK * kFM; e += 256) {
+      int kk, mm;
+      if (p.a_trans) { kk = e / kFM; mm = e - kk * kFM; }   // A is [K][M]: consecutive threads along m (contiguous)
+      else { mm = e / kFK; kk = e - mm * kFK; }              // A is [M][K]: consecutive threads along k (contiguous)
+      const int m = m0 + mm, k = k0 + kk;
+      float v = 0.0f;
+      if (m < p.M && k < p.K)
+        v = p.a_trans ? __ldg(A + static_cast<long long>(k) * p.lda + m) : __ldg(A + static_cast<long long>(m) * p.lda + k);
+      sA[kk][mm] = v;
+    }
+    for (int e = threadIdx.x; e < kFK * kFN; e += 256) {
+      const int kk = e / kFN, nn = e - kk * kFN;
+      const int k = k0 + kk, n = n0 + nn;
+      sB[kk][nn] = (k < p.K && n < p.N) ? __ldg(Bm + static_cast<long long>(k) * p.ldb + n) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kFK; ++kk) {
+      float a[4], bb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bb[j] = sB[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* Cm = p.C + static_cast<long long>(b) * p.c_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < p.N) Cm[static_cast<long long>(m) * p.ldc + n] = p.alpha * acc[i][j];
+    }
+  }
+}
+
+}  // namespace glsdet
+
+extern "C" int glsdet_bgemm_f32(const float* a, int32_t a_trans, int32_t lda, int64_t a_batch_stride, const float* b,
+                                int32_t ldb, int64_t b_batch_stride, float* c, int32_t ldc, int64_t c_batch_stride,
+                                int32_t m, int32_t n, int32_t k, float alpha, int32_t batch, void* stream) {
+  using namespace glsdet;
+  GLSDET_REQUIRE(a && b && c && m > 0 && n > 0 && k > 0 && batch > 0 && batch <= 65535, "bgemm_f32: bad arguments");
+  GLSDET_REQUIRE(lda >= (a_trans ? m : k) && ldb >= n && ldc >= n, "bgemm_f32: leading dimensions too small");
+  BGemmParams p;
+  p.A = a; p.B = b; p.C = c;
+  p.a_bs = a_batch_stride; p.b_bs = b_batch_stride; p.c_bs = c_batch_stride;
+  p.lda = lda; p.ldb = ldb; p.ldc = ldc;
+  p.M = m; p.N = n; p.K = k; p.a_trans = a_trans ? 1 : 0;
+  p.alpha = alpha;
+  const dim3 grid(static_cast<unsigned>((n + kFN - 1) / kFN), static_cast<unsigned>((m + kFM - 1) / kFM), static_cast<unsigned>(batch));
+  GLSDET_REQUIRE(grid.y <= 65535, "bgemm_f32: M too large");
+  bgemm_f32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return count_launch("bgemm_f32_kernel");
+}

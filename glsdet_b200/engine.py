@@ -36,7 +36,7 @@ from typing import Dict, List, Optional, Sequence
 import torch
 
 from . import _native as N
-from .ops import (ConvOp, ConvOpF32, DepthwiseOp, GatherBiasOp, NhwcTransposeOp, PatchTransposeOp, RectCopyOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
+from .ops import (BGemmF32Op, ConvOp, ConvOpF32, DepthwiseOp, GatherBiasOp, NhwcTransposeOp, PatchTransposeOp, RectCopyOp, ScaleShuffleOp, SeGateOp, Upsample2xOp, View, fold_bn,
                   nchw_to_nhwc, nhwc_to_nchw)
 
 BN_EPS = 1e-3
@@ -60,8 +60,6 @@ class FFAPathPlan:
         # 16-bit storage policy of the tensor-core path: "mixed" (default) = bf16 at stride 4, fp16 at the coarser
         # levels (glsdet_b200/_native.py::storage_dtype); "bf16" / "f16" force one type
         self.storage = storage
-        if self.fp32 and variant in ("p1", "p2"):
-            raise NotImplementedError("the fp32 accuracy mode covers the P0 and stock topologies")
         dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         parts = set(parts)
@@ -351,7 +349,18 @@ class FFAPathPlan:
         sd, dev = self.sd, self.device
         B, H, W_, C = x.shape
         nl = self._buf(p + ".nl", stride, C)
-        if H % 2 or W_ % 2:
+        if self.fp32:
+            # accuracy mode: every patch position is cut out as a dense fp32 batch and runs the block un-folded
+            # (theta / phi / g convs, phi^T g / T, theta M, conv_out + residual: _nonlocal_f32)
+            h2, w2 = H // 2, W_ // 2
+            for pos, (y0, x0, ph, pw) in (("lt", (0, 0, h2, w2)), ("rt", (0, w2, h2, W_ - w2)),
+                                          ("lb", (h2, 0, H - h2, w2)), ("rb", (h2, w2, H - h2, W_ - w2))):
+                xp = torch.empty((B, ph, pw, C), dtype=x.dtype, device=dev)
+                ops.append(RectCopyOp(View(x), View(xp), B, [(0, y0, x0, 0, 0, 0, ph, pw)]))
+                nlp = self._nonlocal_f32(ops, f"{p}.feat_patchconv_{pos}_nonlocal", View(xp))
+                ops.append(RectCopyOp(View(nlp), View(nl), B, [(0, 0, 0, 0, y0, x0, ph, pw)]))
+                self._keepalive = getattr(self, "_keepalive", []) + [xp, nlp]
+        elif H % 2 or W_ % 2:
             # unequal 2x2 split (int(H/2), int(W/2): Non_local_family.py:230-233, e.g. 17 x 32 at 544 x 1024): every
             # patch position is cut out as its own dense batch and runs its own chain of GEMMs
             h2, w2 = H // 2, W_ // 2
@@ -376,6 +385,29 @@ class FFAPathPlan:
             self._conv(ops, None, None, [View(x)], View(nl), 1, act=N.ACT_NONE, weight_raw=Wm.view(Bp, C, Ca), n_out=C,
                        patch_mode=True, pre_res=View(bias), pre_shift=30, post_res=View(x), post_shift=0)
         self._base_conv(ops, p + ".channel_conv", [View(nl)], View(out), post_res=View(x), post_shift=0)
+
+    def _nonlocal_f32(self, ops, q: str, x: View) -> torch.Tensor:
+        """Non_local_Block.forward (models/new/Non_local_family.py:32-48; Identity_Conv.py:205-246, dot-product mode) on a
+        dense fp32 batch of patches, fp32 accuracy mode:  theta | phi | g = 1x1 convs with bias (one stacked launch),
+        M = phi^T g / T per image (the reference's  P = theta^T phi / T, y = P g  is  theta (phi^T g / T): no softmax sits
+        between the two products), y = theta M, out = x + conv_out(y)."""
+        sd, dev = self.sd, self.device
+        wt, wp, wg, wo = (sd[f"{q}.{n}.weight"].float() for n in ("theta", "phi", "g", "conv_out"))
+        bt, bp, bg, bo = (sd[f"{q}.{n}.bias"].float() for n in ("theta", "phi", "g", "conv_out"))
+        ci = wt.shape[0]
+        B, h, w = x.bhw
+        tpg = torch.empty((B, h, w, 3 * ci), dtype=torch.float32, device=dev)
+        self._conv(ops, torch.cat([wt, wp, wg], 0), torch.cat([bt, bp, bg], 0), [x], View(tpg), 1, act=N.ACT_NONE)
+        m = torch.empty((B, ci, ci), dtype=torch.float32, device=dev)
+        y = torch.empty((B, h, w, ci), dtype=torch.float32, device=dev)
+        for op in (BGemmF32Op("gram", View(tpg, ci, ci), View(tpg, 2 * ci, ci), m, alpha=1.0 / (h * w)),
+                   BGemmF32Op("apply", View(tpg, 0, ci), m, View(y))):
+            ops.append(op)
+            self.attn_flops = getattr(self, "attn_flops", 0.0) + op.flops
+        out = torch.empty((B, h, w, wo.shape[0]), dtype=torch.float32, device=dev)
+        self._conv(ops, wo, bo, [View(y)], View(out), 1, act=N.ACT_NONE, post_res=x, post_shift=0)
+        self._keepalive = getattr(self, "_keepalive", []) + [tpg, m, y]
+        return out
 
     def _nonlocal_operand(self, p: str, Bp: int, C: int, T: int, dtype):
         """Per-patch transposed operand Xt[b'][c][t] / sqrt(T) with the ones row (channel sums / conv biases) preset.
@@ -457,7 +489,13 @@ class FFAPathPlan:
         for i, nm in enumerate(names):
             self._base_conv(ops, f"{p}.feat_patchconv_{nm}", [View(xp[i * B:(i + 1) * B])], View(y[i * B:(i + 1) * B]),
                             stride=stride)
-        if nonlocal_:
+        if nonlocal_ and self.fp32:
+            nl = torch.empty_like(y)
+            for i, nm in enumerate(names):
+                nlp = self._nonlocal_f32(ops, f"{p}.feat_patchconv_{nm}_nonlocal", View(y[i * B:(i + 1) * B]))
+                ops.append(RectCopyOp(View(nlp), View(nl[i * B:(i + 1) * B]), B, [(0, 0, 0, 0, 0, 0, hq, wq)]))
+                self._keepalive = getattr(self, "_keepalive", []) + [nlp]
+        elif nonlocal_:
             T = hq * wq
             xt, Ca = self._nonlocal_operand(p, 4 * B, mid, T, dt)
             ops.append(NhwcTransposeOp(View(y), xt, scale=T ** -0.5))

@@ -68,6 +68,14 @@ class View:
         return tuple(self.t.shape[:3])
 
 
+def as16(v: "View") -> "View":
+    """An fp32 channel window seen as a 16-bit one with twice the channels (bit copies only: rectangle copies, nearest
+    upsampling - the kernels move 16-byte vectors and never interpret the elements); 16-bit windows pass through."""
+    if v.t.dtype != torch.float32:
+        return v
+    return View(v.t.view(torch.float16), 2 * v.coff, 2 * v.c)
+
+
 class FoldedView:
     """Source view of a few-channel 3x3 conv with the kx taps folded into the channel dimension (glsdet_conv_desc.ksize_w
     = 1): `t` is a zero-bordered NHWC bf16 buffer [B, H, W + 2, c_pix] (+ slack behind the last row); the conv sees, at
@@ -401,6 +409,7 @@ class Upsample2xOp:
     """dst window = nearest 2x upsampling of the src window (NHWC bf16)."""
 
     def __init__(self, src: View, dst: View):
+        src, dst = as16(src), as16(dst)   # fp32 accuracy mode: copied as 16-bit pairs
         b, h, w = src.bhw
         assert dst.bhw == (b, 2 * h, 2 * w) and dst.c == src.c
         assert src.t.dtype == dst.t.dtype and src.t.dtype in (torch.bfloat16, torch.float16)   # a plain 16-bit copy
@@ -502,11 +511,43 @@ class ConvOpF32:
         N.check(self._lib.glsdet_conv_f32(C.byref(self.desc), N.stream_ptr(stream)), "glsdet_conv_f32")
 
 
+class BGemmF32Op:
+    """Batched fp32 GEMM on NHWC fp32 channel windows (glsdet_bgemm_f32), the two products of the dot-product non-local
+    block in the fp32 accuracy mode.  mode "gram":  out[b][i][j] = alpha * sum_t a[b, t, i] * b_[b, t, j]  (a, b_: windows of
+    [B, h, w, .] tensors, t = pixel; out: [B, Ci, Cj] fp32);  mode "apply":  out[b, t, j] = sum_i a[b, t, i] * m[b][i][j]
+    (a: window, m: [B, Ci, Cj] fp32, out: window)."""
+
+    def __init__(self, mode: str, a: View, b, out, alpha: float = 1.0):
+        assert mode in ("gram", "apply") and a.t.dtype == torch.float32
+        bb, h, w = a.bhw
+        t = h * w
+        self._keep = (a, b, out)
+        self._lib = N.load()
+        es = 4
+        if mode == "gram":
+            assert isinstance(b, View) and b.bhw == a.bhw and b.t.dtype == torch.float32
+            assert out.dtype == torch.float32 and tuple(out.shape) == (bb, a.c, b.c) and out.is_contiguous()
+            self.args = (a.ptr, 1, a.ld, t * a.ld, b.ptr, b.ld, t * b.ld, out.data_ptr(), b.c, a.c * b.c, a.c, b.c, t,
+                         float(alpha), bb)
+            self.flops = 2.0 * bb * t * a.c * b.c
+        else:
+            assert b.dtype == torch.float32 and b.dim() == 3 and b.shape[0] == bb and b.shape[1] == a.c and b.is_contiguous()
+            assert isinstance(out, View) and out.bhw == a.bhw and out.c == b.shape[2] and out.t.dtype == torch.float32
+            self.args = (a.ptr, 0, a.ld, t * a.ld, b.data_ptr(), b.shape[2], b.shape[1] * b.shape[2], out.ptr, out.ld,
+                         t * out.ld, t, b.shape[2], a.c, float(alpha), bb)
+            self.flops = 2.0 * bb * t * a.c * b.shape[2]
+        del es
+
+    def launch(self, stream=None):
+        N.check(self._lib.glsdet_bgemm_f32(*self.args, N.stream_ptr(stream)), "glsdet_bgemm_f32")
+
+
 class RectCopyOp:
     """Up to 8 rectangle copies between two NHWC bf16 tensors in one launch (glsdet_rect_copy):
     rects = [(src_image0, sy, sx, dst_image0, dy, dx, h, w), ...], each applied to `batch` consecutive images."""
 
     def __init__(self, src: View, dst: View, batch: int, rects):
+        src, dst = as16(src), as16(dst)   # fp32 accuracy mode: copied as 16-bit pairs
         assert src.t.dtype == dst.t.dtype and src.t.dtype in (torch.bfloat16, torch.float16) and src.c == dst.c
         assert 1 <= len(rects) <= 8
         self.src, self.dst, self.batch = src, dst, batch

@@ -186,6 +186,16 @@ typedef struct glsdet_conv_f32_desc {
   float dec_stride, dec_in_w, dec_in_h;
 } glsdet_conv_f32_desc;
 int glsdet_conv_f32(const glsdet_conv_f32_desc* desc, void* stream);
+/*
+ * Batched fp32 GEMM of the accuracy mode: C[b][m][n] = alpha * sum_k A[b](m, k) * B[b][k][n], A stored [M][K] (a_trans = 0)
+ * or [K][M] (a_trans = 1), B [K][N], C [M][N]; leading dimensions and batch strides in elements, so NHWC fp32 channel
+ * windows are operands as they are.  The two products of the dot-product non-local block (yolox-drone/models/new/
+ * Non_local_family.py:27-31,40-45: P = theta^T phi / T, y = P g, evaluated as theta (phi^T g / T)) in fp32 plans of the P1 /
+ * P2 models.  SIMT FMA, fixed summation order.
+ */
+int glsdet_bgemm_f32(const float* a, int32_t a_trans, int32_t lda, int64_t a_batch_stride, const float* b, int32_t ldb,
+                     int64_t b_batch_stride, float* c, int32_t ldc, int64_t c_batch_stride, int32_t m, int32_t n, int32_t k,
+                     float alpha, int32_t batch, void* stream);
 /* NCHW fp32 <-> channel window of an NHWC fp32 buffer (to_nhwc = 1: src is NCHW; 0: src is the NHWC buffer) */
 int glsdet_nchw_nhwc_f32(const float* src, float* dst, int32_t batch, int32_t channels, int32_t height, int32_t width,
                          int32_t nhwc_ld, int32_t nhwc_coff, int32_t to_nhwc, void* stream);

@@ -134,3 +134,50 @@ def test_config1_yolox_s_640_fp32(native_lib, cuda_device):
     ref_res = ref_path.non_max_suppression(ref_path.decode_outputs(ref2, [640, 640]), nc, [640, 640], np.array([640, 640]),
                                            False, 0.01, 0.65, strategy="auto_cpu")
     np.testing.assert_array_equal(res[0], ref_res[0])
+
+
+def test_batched_gemm_f32_kernel(native_lib, cuda_device):
+    """glsdet_bgemm_f32 (the two products of the un-folded non-local block) on channel windows of NHWC fp32 tensors, against
+    float64 torch: the Gram form (A stored [K][M], k = pixel) and the apply form; ragged sizes."""
+    from glsdet_b200.ops import BGemmF32Op, View
+
+    dev = cuda_device
+    g = torch.Generator().manual_seed(11)
+    for b, h, w, ci in ((2, 8, 12, 64), (3, 5, 7, 48), (1, 32, 32, 128), (2, 1, 3, 16)):
+        t = torch.randn(b, h, w, 3 * ci + 8, generator=g).to(dev)
+        a, bb = View(t, 8, ci), View(t, 8 + ci, ci)
+        m = torch.full((b, ci, ci), float("nan"), device=dev)
+        BGemmF32Op("gram", a, bb, m, alpha=1.0 / (h * w)).launch()
+        A = t[..., 8:8 + ci].flatten(1, 2).double()
+        Bm = t[..., 8 + ci:8 + 2 * ci].flatten(1, 2).double()
+        ref = torch.einsum("bti,btj->bij", A, Bm) / (h * w)
+        assert (m.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), (b, h, w, ci)
+        y = torch.full((b, h, w, ci + 8), 5.0, device=dev)
+        BGemmF32Op("apply", a, m, View(y, 8, ci)).launch()
+        torch.cuda.synchronize()
+        ref_y = torch.einsum("bti,bij->btj", A, m.double()).view(b, h, w, ci)
+        assert (y[..., 8:].double() - ref_y).abs().max().item() <= 1e-5 * max(1.0, ref_y.abs().max().item())
+        assert (y[..., :8] == 5.0).all()
+
+
+@pytest.mark.parametrize("variant", ["p1", "p2"])
+def test_fp32_mode_of_p1_p2_matches_reference_golden(variant, native_lib, cuda_device):
+    """fp32 accuracy mode of the GLSDet P1 (models/new/yolox10.py: patch non-local attention + cross-level head) and P2
+    (models/block/non_local/yolo_patch_nonlocal_plus.py) models: neck outputs and logits within 1e-3 relative (BASELINE.json)
+    of the REAL reference's outputs (tests/golden/p{1,2}_s_calibrated.npz); measured at summation-order noise."""
+    import importlib
+
+    meta = META[variant]
+    z = np.load(GOLD / f"{meta['name']}.npz")
+    sd = ref_path.synthetic_state_dict(meta["nc"], meta["phi"], seed=meta["seed"], flavour="calibrated", variant=variant)
+    mod = importlib.import_module("glsdet_b200.yolox10" if variant == "p1" else "glsdet_b200.yolo_patch_nonlocal_plus")
+    net = mod.YoloBody(meta["nc"], meta["phi"])
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval().set_precision("fp32")
+    nf = 4 if variant == "p1" else 3
+    feats = [torch.from_numpy(z[f"feat{i}"]).to(cuda_device) for i in range(nf)]
+    logits = net.forward_features(feats)
+    worst = 0.0
+    for i, t in enumerate(logits):
+        worst = max(worst, _close(t, torch.from_numpy(z[f"logits{i}"]), f"fp32 {variant} logits{i}"))
+    assert worst <= 1e-4, f"fp32 {variant} should sit at summation-order noise, got {worst:.3g}"

@@ -128,6 +128,45 @@ class ModelScaleShuffleOp:
         self.dst.t[..., self.dst.coff:self.dst.coff + co] = t.to(self.dst.t.dtype)
 
 
+class ModelRectCopyOp:
+    """glsdet_rect_copy: rects = (src image0, sy, sx, dst image0, dy, dx, h, w), each applied to `batch` consecutive images."""
+
+    def __init__(self, src, dst, batch, rects):
+        self.src, self.dst, self.batch, self.rects = src, dst, batch, list(rects)
+
+    def launch(self, stream=None):
+        s, d = self.src, self.dst
+        for sb, sy, sx, db, dy, dx, h, w in self.rects:
+            for i in range(self.batch):
+                d.t[db + i, dy:dy + h, dx:dx + w, d.coff:d.coff + d.c] = s.t[sb + i, sy:sy + h, sx:sx + w, s.coff:s.coff + s.c]
+
+
+class ModelUpsample2xOp:
+    def __init__(self, src, dst):
+        self.src, self.dst = src, dst
+
+    def launch(self, stream=None):
+        _store(self.dst, F.interpolate(_win(self.src), scale_factor=2, mode="nearest"))
+
+
+class ModelBGemmF32Op:
+    """glsdet_bgemm_f32 in its two uses: "gram" out[b] = alpha * a[b]^T b[b] over the pixels, "apply" out[b] = a[b] m[b]."""
+
+    def __init__(self, mode, a, b, out, alpha=1.0):
+        self.mode, self.a, self.b, self.out, self.alpha = mode, a, b, out, alpha
+        self.flops = 0.0
+
+    def launch(self, stream=None):
+        a = self.a.t[..., self.a.coff:self.a.coff + self.a.c].flatten(1, 2)          # [B, T, Ci]
+        if self.mode == "gram":
+            bm = self.b.t[..., self.b.coff:self.b.coff + self.b.c].flatten(1, 2)
+            self.out.copy_(self.alpha * torch.einsum("bti,btj->bij", a, bm))
+        else:
+            y = torch.einsum("bti,bij->btj", a, self.b)
+            o = self.out
+            o.t[..., o.coff:o.coff + o.c] = y.view(o.t.shape[0], o.t.shape[1], o.t.shape[2], -1)
+
+
 def _nchw_to_nhwc(src, dst, stream=None):
     _store(dst, src)
 
@@ -145,7 +184,8 @@ def op_models(monkeypatch):
     for mod in (engine, backbone):
         for name, model in (("ConvOp", ModelConvOp), ("ConvOpF32", ModelConvOp), ("DepthwiseOp", ModelDepthwiseOp),
                             ("FocusOp", ModelFocusOp), ("SppPoolOp", ModelSppPoolOp), ("SeGateOp", ModelSeGateOp),
-                            ("ScaleShuffleOp", ModelScaleShuffleOp), ("nchw_to_nhwc", _nchw_to_nhwc),
+                            ("ScaleShuffleOp", ModelScaleShuffleOp), ("RectCopyOp", ModelRectCopyOp),
+                            ("Upsample2xOp", ModelUpsample2xOp), ("BGemmF32Op", ModelBGemmF32Op), ("nchw_to_nhwc", _nchw_to_nhwc),
                             ("nhwc_to_nchw", _nhwc_to_nchw)):
             if hasattr(mod, name):
                 monkeypatch.setattr(mod, name, model)
@@ -224,3 +264,27 @@ def test_mmdet_depthwise_plans_match_golden(op_models):
     ph.run_towers(False)
     for i, t in enumerate(ph.logits):
         assert _rel(t, torch.from_numpy(z[f"stock_logits{i}"])) <= 1e-4, i
+
+
+@pytest.mark.parametrize("variant,hw", [("p1", (128, 192)), ("p1", (96, 160)), ("p2", (128, 192))])
+def test_fp32_plans_of_p1_p2_match_oracle(variant, hw, op_models):
+    """fp32 accuracy mode of the GLSDet P1 / P2 topologies (patch non-local attention un-folded into theta / phi / g convs and
+    two batched fp32 GEMMs, engine.py::_nonlocal_f32): features -> logits against oracle.ref_path at 1e-4.  The second P1
+    size has odd level sizes (unequal 2x2 patch splits, Non_local_family.py:230-233)."""
+    engine, _ = op_models
+    from glsdet_b200.synthetic import synthetic_state_dict
+
+    nc, b = 3, 2
+    h, w = hw
+    sd = synthetic_state_dict(nc, "s", seed=7, flavour="kaiming", variant=variant)
+    g = torch.Generator().manual_seed(8)
+    chans = (64, 128, 256, 512) if variant == "p1" else (128, 256, 512)
+    strides = (4, 8, 16, 32) if variant == "p1" else (8, 16, 32)
+    feats = [torch.randn(b, c, h // s_, w // s_, generator=g) for c, s_ in zip(chans, strides)]
+    ref = ref_path.p1_neck_head(sd, feats) if variant == "p1" else ref_path.p2_neck_head(sd, feats)
+    plan = engine.FFAPathPlan(sd, b, hw, nc, device="cpu", variant=variant, precision="fp32")
+    assert not plan.pre_loads
+    out = plan.forward_logits(feats)
+    for i, (t, r) in enumerate(zip(out, ref)):
+        assert t.shape == r.shape
+        assert _rel(t, r) <= 1e-4, (variant, i, _rel(t, r))
