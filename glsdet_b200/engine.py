@@ -414,7 +414,7 @@ class FFAPathPlan:
         The 1 / sqrt(T) on both Gram operands makes S = Xt Xt^T the MEAN outer product (the 1 / T of
         Non_local_family.py:29), whose entries are O(1) - the plain sum over T = 4096 pixels would leave the fp16 range."""
         Tp = (T + 63) // 64 * 64
-        Ca = C + 64
+        Ca = (C // 64 + 1) * 64      # C channels + the ones row, padded to whole 64-wide K chunks (C = 32 at nano width)
         xt = torch.zeros((Bp, Ca, Tp), dtype=dtype, device=self.device)
         xt[:, C, :T] = T ** -0.5
         self._bufs[p + ".xt"] = xt
@@ -588,25 +588,33 @@ class FFAPathPlan:
             tr = self._buf(f"p1_tr{k}", s_, hc)
             self._base_conv(tw, f"head.cls_convs.{k}.0", [View(cat[k])], View(tc))
             self._base_conv(tw, f"head.reg_convs.{k}.0", [xs[k]], View(tr))
-            wc1, bc1 = self._folded(f"head.cls_convs.{k}.1")
-            wr1, br1 = self._folded(f"head.reg_convs.{k}.1")
+            cls_in, reg_in, k2 = View(tc), View(tr), 3
+            if self._is_dw(f"head.cls_convs.{k}.1"):   # phi = 'nano': depthwise halves here, predictions fused into the 1x1 halves
+                cls_in = self._dw(tw, f"head.cls_convs.{k}.1", cls_in)
+                reg_in = self._dw(tw, f"head.reg_convs.{k}.1", reg_in)
+                wc1, bc1 = self._folded(f"head.cls_convs.{k}.1.pconv")
+                wr1, br1 = self._folded(f"head.reg_convs.{k}.1.pconv")
+                k2 = 1
+            else:
+                wc1, bc1 = self._folded(f"head.cls_convs.{k}.1")
+                wr1, br1 = self._folded(f"head.reg_convs.{k}.1")
             w_ro = torch.cat([sd[f"head.reg_preds.{k}.weight"], sd[f"head.obj_preds.{k}.weight"]], 0).float()
             b_ro = torch.cat([sd[f"head.reg_preds.{k}.bias"], sd[f"head.obj_preds.{k}.bias"]], 0).float()
             w_cl, b_cl = sd[f"head.cls_preds.{k}.weight"].float(), sd[f"head.cls_preds.{k}.bias"].float()
             kw = dict(out_mode=N.OUT_NCHW_F32, out_ld=nch, out_batch_stride=nch * h * w)
-            self._conv(self.pred_raw_ops, wr1, br1, [View(tr)], self.logits[k], 3, out_coff=0, pred_weight=w_ro,
+            self._conv(self.pred_raw_ops, wr1, br1, [reg_in], self.logits[k], k2, out_coff=0, pred_weight=w_ro,
                        pred_bias=b_ro, pred_act=N.ACT_NONE, **kw)
-            self._conv(self.pred_raw_ops, wc1, bc1, [View(tc)], self.logits[k], 3, out_coff=5, pred_weight=w_cl,
+            self._conv(self.pred_raw_ops, wc1, bc1, [cls_in], self.logits[k], k2, out_coff=5, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             stride = float(self.in_h / h)
             kw, c_reg, c_cls = self._pred_out(nch, a_off)
-            op = self._conv(self.pred_dec_ops, wr1, br1, [View(tr)], self.pred_store, 3, out_coff=c_reg, pred_weight=w_ro,
+            op = self._conv(self.pred_dec_ops, wr1, br1, [reg_in], self.pred_store, k2, out_coff=c_reg, pred_weight=w_ro,
                             pred_bias=b_ro, pred_act=box_act, dec=(stride, float(self.in_w), float(self.in_h)), **kw)
-            self._conv(self.pred_dec_ops, wc1, bc1, [View(tc)], self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+            self._conv(self.pred_dec_ops, wc1, bc1, [cls_in], self.pred_store, k2, out_coff=c_cls, pred_weight=w_cl,
                        pred_bias=b_cl, pred_act=N.ACT_SIGMOID, **kw)
             if not self.fp32:
                 self.pred_det_ops.append(op)
-                self._conv(self.pred_det_ops, wc1, bc1, [View(tc)], self.pred_store, 3, out_coff=c_cls, pred_weight=w_cl,
+                self._conv(self.pred_det_ops, wc1, bc1, [cls_in], self.pred_store, k2, out_coff=c_cls, pred_weight=w_cl,
                            pred_bias=b_cl, pred_act=N.ACT_NONE, **kw)
             a_off += h * w
         self.flops -= sum(op.flops for op in self.pred_dec_ops) + sum(op.flops for op in self.pred_det_ops[1::2])

@@ -17,8 +17,6 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
     depth = {"nano": 0.33, "tiny": 0.33, "s": 0.33, "m": 0.67, "l": 1.0, "x": 1.33}[phi]
     width = {"nano": 0.25, "tiny": 0.375, "s": 0.50, "m": 0.75, "l": 1.0, "x": 1.25}[phi]
     depthwise = phi == "nano"   # yolox_ffa.py:270: every k > 1 conv outside Focus becomes a DWConv (baseConv.py:22-30)
-    if depthwise and variant in ("p1", "p2"):
-        raise NotImplementedError("phi='nano' shapes exist for the P0 and stock topologies")
     shapes: Dict[str, tuple] = {}
 
     def bc(p, cin, cout, k):
@@ -99,13 +97,13 @@ def p0_state_dict_shapes(num_classes: int, phi: str, variant: str = "ffa") -> Di
         csp("head.csp_feat0", int(0.5 * 256 * width), hc, round(3 * 0.75))
         for i, cin in enumerate((c0, c1, c2)):
             bc(f"head.stems.{i}", cin, hc, 1)
-            bc(f"head.up_convs.{i}.0", hc, hc, 3)
-            bc(f"head.up_convs.{i}.1", hc, hc, 3)
+            cv(f"head.up_convs.{i}.0", hc, hc, 3)
+            cv(f"head.up_convs.{i}.1", hc, hc, 3)
             m = 2 if i == 2 else 3
-            bc(f"head.cls_convs.{i}.0", m * hc, m * hc, 3)
-            bc(f"head.cls_convs.{i}.1", m * hc, hc, 3)
-            bc(f"head.reg_convs.{i}.0", hc, hc, 3)
-            bc(f"head.reg_convs.{i}.1", hc, hc, 3)
+            cv(f"head.cls_convs.{i}.0", m * hc, m * hc, 3)
+            cv(f"head.cls_convs.{i}.1", m * hc, hc, 3)
+            cv(f"head.reg_convs.{i}.0", hc, hc, 3)
+            cv(f"head.reg_convs.{i}.1", hc, hc, 3)
             for name, co in (("cls_preds", num_classes), ("reg_preds", 4), ("obj_preds", 1)):
                 shapes[f"head.{name}.{i}.weight"] = (co, hc, 1, 1)
                 shapes[f"head.{name}.{i}.bias"] = (co,)

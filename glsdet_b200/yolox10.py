@@ -14,7 +14,7 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .yolox_ffa import _DEPTH, _WIDTH, BaseConv, CSPDarknet, CSPLayer, _PlanOwner
+from .yolox_ffa import _DEPTH, _WIDTH, BaseConv, CSPDarknet, CSPLayer, DWConv, _PlanOwner
 from .yolox_ffa import YoloBody as _FFAYoloBody
 
 
@@ -62,23 +62,22 @@ class YOLOXHead(_PlanOwner):
 
     def __init__(self, num_classes, width=1.0, in_channels=[256, 512, 1024], act="silu", depthwise=False):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
         self.num_classes = num_classes
         hc = int(256 * width)
+        Conv = DWConv if depthwise else BaseConv   # yolox10.py:11
         self.cls_convs, self.reg_convs = nn.ModuleList(), nn.ModuleList()
         self.cls_preds, self.reg_preds, self.obj_preds = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
         self.stems = nn.ModuleList()
         self.csp_feat0 = CSPLayer(int(0.5 * in_channels[0] * width), int(in_channels[0] * width), round(3 * 0.75),
-                                  False, act=act)
+                                  False, depthwise=depthwise, act=act)
         self.up_convs = nn.ModuleList()
         for i, cin in enumerate(in_channels):
             self.stems.append(BaseConv(int(cin * width), hc, 1, 1, act=act))
-            self.up_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 2, act=act)))
+            self.up_convs.append(nn.Sequential(Conv(hc, hc, 3, 1, act=act), Conv(hc, hc, 3, 2, act=act)))
             m = 2 if i == 2 else 3
-            self.cls_convs.append(nn.Sequential(BaseConv(m * hc, m * hc, 3, 1, act=act), BaseConv(m * hc, hc, 3, 1, act=act)))
+            self.cls_convs.append(nn.Sequential(Conv(m * hc, m * hc, 3, 1, act=act), Conv(m * hc, hc, 3, 1, act=act)))
             self.cls_preds.append(nn.Conv2d(hc, num_classes, 1, 1, 0))
-            self.reg_convs.append(nn.Sequential(BaseConv(hc, hc, 3, 1, act=act), BaseConv(hc, hc, 3, 1, act=act)))
+            self.reg_convs.append(nn.Sequential(Conv(hc, hc, 3, 1, act=act), Conv(hc, hc, 3, 1, act=act)))
             self.reg_preds.append(nn.Conv2d(hc, 4, 1, 1, 0))
             self.obj_preds.append(nn.Conv2d(hc, 1, 1, 1, 0))
         nn.Module.train(self, False)
@@ -105,20 +104,19 @@ class YOLOPAFPN(_PlanOwner):
     def __init__(self, depth=1.0, width=1.0, in_features=("dark2", "dark3", "dark4", "dark5"),
                  in_channels=[256, 512, 1024], depthwise=False, act="silu"):
         super().__init__()
-        if depthwise:
-            raise NotImplementedError("depthwise (phi='nano') is not supported by the native path")
         self.backbone = CSPDarknet(depth, width, depthwise=depthwise, act=act)
         self.in_features = in_features
         c0, c1, c2 = (int(c * width) for c in in_channels)
         n = round(3 * depth)
+        Conv = DWConv if depthwise else BaseConv   # yolox10.py:165
         self.lateral_conv0 = BaseConv(c2, c1, 1, 1, act=act)
-        self.C3_p4 = CSPLayer(2 * c1, c1, n, False, act=act)
+        self.C3_p4 = CSPLayer(2 * c1, c1, n, False, depthwise=depthwise, act=act)
         self.reduce_conv1 = BaseConv(c1, c0, 1, 1, act=act)
-        self.C3_p3 = CSPLayer(2 * c0, c0, n, False, act=act)
-        self.bu_conv2 = BaseConv(c0, c0, 3, 2, act=act)
-        self.C3_n3 = CSPLayer(2 * c0, c1, n, False, act=act)
-        self.bu_conv1 = BaseConv(c1, c1, 3, 2, act=act)
-        self.C3_n4 = CSPLayer(2 * c1, c2, n, False, act=act)
+        self.C3_p3 = CSPLayer(2 * c0, c0, n, False, depthwise=depthwise, act=act)
+        self.bu_conv2 = Conv(c0, c0, 3, 2, act=act)
+        self.C3_n3 = CSPLayer(2 * c0, c1, n, False, depthwise=depthwise, act=act)
+        self.bu_conv1 = Conv(c1, c1, 3, 2, act=act)
+        self.C3_n4 = CSPLayer(2 * c1, c2, n, False, depthwise=depthwise, act=act)
         self.Patch_conv_feat1 = Patch_Conv_NonLocal_new(c0, c0, channel_scale=1, patch_scale=2)
         self.Patch_conv_feat2 = Patch_Conv_NonLocal_new(c1, c1, channel_scale=1, patch_scale=2)
         self.Patch_conv_feat3 = Patch_Conv_NonLocal_new(c2, c2, channel_scale=1, patch_scale=2)

@@ -217,3 +217,34 @@ def test_mmdet_face_use_depthwise(native_lib, cuda_device):
         assert rel_l2(got, ref) <= 2e-2, (i, rel_l2(got, ref))
     res = head.get_bboxes(cls, box, obj, img_metas=[dict(scale_factor=[1.0, 1.0, 1.0, 1.0])] * m["batch"])
     assert len(res) == m["batch"] and res[0][0].shape[1] == 5 and torch.isfinite(res[0][0]).all()
+
+
+@pytest.mark.parametrize("case", ["p1", "p2"])
+def test_nano_p1_p2_models_match_reference_golden(case, native_lib, cuda_device):
+    """phi = 'nano' of the GLSDet P1 (models/new/yolox10.py) and P2 (yolo_patch_nonlocal_plus.py) models - DWConv in the
+    neck's bu_convs / Bottlenecks, the cross-level head's up / tower convs, plus the patch non-local attention at nano width
+    - against the REAL reference's logits: 16-bit path within 2e-2 (from the reference's features and from the image), fp32
+    accuracy mode within 1e-3."""
+    import importlib
+
+    z = np.load(GOLD / "nano_cases.npz")
+    m = json.loads((GOLD / "nano_meta.json").read_text())[case]
+    sd = ref_path.synthetic_state_dict(m["nc"], "nano", seed=m["seed"], flavour="calibrated", variant=m["variant"])
+    mod = importlib.import_module("glsdet_b200.yolox10" if case == "p1" else "glsdet_b200.yolo_patch_nonlocal_plus")
+    net = mod.YoloBody(m["nc"], "nano")
+    net.load_state_dict(sd, strict=True)
+    net = net.to(cuda_device).eval()
+    x = torch.from_numpy(z[f"{case}_image"]).to(cuda_device)
+    names = ("dark2", "dark3", "dark4", "dark5") if case == "p1" else ("dark3", "dark4", "dark5")
+    ref_feats = [torch.from_numpy(z[f"{case}_{n}"]).to(cuda_device) for n in names]
+    refs = [torch.from_numpy(z[f"{case}_logits{i}"]) for i in range(3)]
+    for tag, logits in (("features", net.forward_features(ref_feats)), ("image", net(x))):
+        for i, t in enumerate(logits):
+            assert t.shape == refs[i].shape
+            assert rel_l2(t, refs[i]) <= 2e-2, (case, tag, i, rel_l2(t, refs[i]))
+    det, cnt = net.detect_features(ref_feats, conf_thres=m["conf"], nms_thres=m["nms_thr"])
+    torch.cuda.synchronize()
+    assert int(cnt.min()) > 0 and torch.isfinite(det[0, :int(cnt[0])]).all()
+    net.set_precision("fp32")
+    for i, t in enumerate(net.forward_features(ref_feats)):
+        assert rel_l2(t, refs[i]) <= 1e-3, (case, "fp32", i, rel_l2(t, refs[i]))

@@ -136,7 +136,7 @@ def test_oracle_decode_variants_pinned_to_reference_golden():
         np.testing.assert_allclose(got, z[name], rtol=1e-6, atol=1e-6, err_msg=name)
 
 
-@pytest.mark.parametrize("case", ["p0", "stock"])
+@pytest.mark.parametrize("case", ["p0", "stock", "p1", "p2"])
 def test_oracle_nano_dwconv_pinned_to_reference_golden(case):
     """phi = 'nano' (DWConv = depthwise k x k + pointwise 1x1, models/base/baseConv.py:22-30): the oracle's backbone, neck,
     head, decode and NMS against tests/golden/nano_cases.npz, which tests/golden/make_golden_nano.py recorded from the REAL
@@ -159,6 +159,12 @@ def test_oracle_nano_dwconv_pinned_to_reference_golden(case):
         if case == "p0":
             neck = ref_path.pafpn_neck(sd, feats)
             logits = ref_path.yolox_head(sd, neck)
+        elif case == "p1":
+            neck = ref_path.p1_neck(sd, feats)
+            logits = ref_path.p1_head(sd, neck)
+        elif case == "p2":
+            neck = ref_path.p2_neck(sd, feats[1:])
+            logits = ref_path.stock_head(sd, neck)
         else:
             neck = ref_path.pafpn_neck(sd, [None] + list(feats[1:]))[1:]
             logits = ref_path.stock_head(sd, neck)
@@ -174,10 +180,10 @@ def test_oracle_nano_dwconv_pinned_to_reference_golden(case):
     for b in range(m["batch"]):
         assert np.array_equal(res[b], z[f"{case}_nms{b}"]), b
     # the drop-in modules expose the reference's keys in the reference's order (strict load works, DataParallel-safe)
-    if case == "p0":
-        from glsdet_b200.yolox_ffa import YoloBody
-    else:
-        from glsdet_b200.yolox_base import YoloBody
+    import importlib
+
+    YoloBody = importlib.import_module({"p0": "glsdet_b200.yolox_ffa", "stock": "glsdet_b200.yolox_base", "p1": "glsdet_b200.yolox10",
+                                        "p2": "glsdet_b200.yolo_patch_nonlocal_plus"}[case]).YoloBody
     net = YoloBody(m["nc"], "nano")
     assert list(net.state_dict().keys()) == m["keys"]
     net.load_state_dict(sd, strict=True)

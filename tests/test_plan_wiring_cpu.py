@@ -266,8 +266,9 @@ def test_mmdet_depthwise_plans_match_golden(op_models):
         assert _rel(t, torch.from_numpy(z[f"stock_logits{i}"])) <= 1e-4, i
 
 
-@pytest.mark.parametrize("variant,hw", [("p1", (128, 192)), ("p1", (96, 160)), ("p2", (128, 192))])
-def test_fp32_plans_of_p1_p2_match_oracle(variant, hw, op_models):
+@pytest.mark.parametrize("variant,hw,phi", [("p1", (128, 192), "s"), ("p1", (96, 160), "s"), ("p2", (128, 192), "s"),
+                                            ("p1", (128, 192), "nano"), ("p2", (128, 192), "nano")])
+def test_fp32_plans_of_p1_p2_match_oracle(variant, hw, phi, op_models):
     """fp32 accuracy mode of the GLSDet P1 / P2 topologies (patch non-local attention un-folded into theta / phi / g convs and
     two batched fp32 GEMMs, engine.py::_nonlocal_f32): features -> logits against oracle.ref_path at 1e-4.  The second P1
     size has odd level sizes (unequal 2x2 patch splits, Non_local_family.py:230-233)."""
@@ -276,9 +277,10 @@ def test_fp32_plans_of_p1_p2_match_oracle(variant, hw, op_models):
 
     nc, b = 3, 2
     h, w = hw
-    sd = synthetic_state_dict(nc, "s", seed=7, flavour="kaiming", variant=variant)
+    sd = synthetic_state_dict(nc, phi, seed=7, flavour="kaiming", variant=variant)
     g = torch.Generator().manual_seed(8)
-    chans = (64, 128, 256, 512) if variant == "p1" else (128, 256, 512)
+    wm = 2 if phi == "s" else 1     # width 0.5 / 0.25 (nano: every k > 1 conv of neck and head is a DWConv)
+    chans = tuple(c * wm for c in ((32, 64, 128, 256) if variant == "p1" else (64, 128, 256)))
     strides = (4, 8, 16, 32) if variant == "p1" else (8, 16, 32)
     feats = [torch.randn(b, c, h // s_, w // s_, generator=g) for c, s_ in zip(chans, strides)]
     ref = ref_path.p1_neck_head(sd, feats) if variant == "p1" else ref_path.p2_neck_head(sd, feats)
