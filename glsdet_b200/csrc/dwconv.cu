@@ -261,6 +261,162 @@ __global__ void __launch_bounds__(256) dw3_kernel(const DwParams p) {
   }
 }
 
+// Vertical streaming variant of the 3x3 kernel (16-bit storage): a thread owns a strip of TX output pixels of one channel
+// vector over a BAND of output rows and walks down the input rows; every input row is loaded and converted ONCE and scattered
+// into the (up to three) output rows it contributes to, whose accumulators sit in a rotating set of register slots
+// (S = 1: three slots, S = 2: two).  Per 16 outputs x 8 channels: 4 loads, 32 conversions, 18 shared-memory weight reads,
+// 144 FFMA - the tiled kernel above converts every input three times (S = 1).  The row loop is unrolled by the slot period so
+// that slot indices are compile-time register arrays; a slot is stored (if its row is real) and reset to the bias right
+// after its last contribution, which also discards what the rows above the band's first output row scattered into it.
+template <int VEC, int S, int TX, int F16>
+__global__ void __launch_bounds__(256) dw3s_kernel(const DwParams p) {
+  extern __shared__ float s_w[];   // conflict-free layout of dw3_kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  {
+    const int nv = p.C / VEC;
+    for (int i = threadIdx.x; i < 10 * p.C; i += blockDim.x) {
+      const int tap = i / p.C, c = i - tap * p.C;
+      const int v = c / VEC, e = c - v * VEC;
+      s_w[tap * p.C + ((e >> 2) * nv + v) * 4 + (e & 3)] = (tap < 9) ? __ldg(p.w + i) : __ldg(p.bias + c);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __syncthreads();
+  constexpr int NC = (TX - 1) * S + 3;
+  constexpr int ES = (VEC == 8) ? 2 : 4;
+  constexpr int NSLOT = (S == 1) ? 3 : 2;   // output rows in flight
+  constexpr int PERIOD = (S == 1) ? 3 : 4;  // input rows per slot rotation
+  const uint32_t nvec = static_cast<uint32_t>(p.C / VEC);
+  const uint32_t wt = static_cast<uint32_t>((p.Wo + TX - 1) / TX);
+  const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wt * nvec) return;
+  const int xt = static_cast<int>(idx / nvec);
+  const int vch = static_cast<int>(idx - static_cast<uint32_t>(xt) * nvec);
+  const int c0 = vch * VEC;
+  const int b = static_cast<int>(blockIdx.z);
+  const int oy0 = static_cast<int>(blockIdx.y) * p.ry;
+  const int nrows = min(p.ry, p.Ho - oy0);
+  const int nsteps = (S == 1) ? nrows + 2 : 2 * nrows + 1;   // input rows iy = oy0 * S - 1 + j, j = 0 .. nsteps - 1
+  const int ox0 = xt * TX;
+  const int ix0 = ox0 * S - 1;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(p.src) +
+                       (static_cast<size_t>(b) * p.H * p.W * p.sld + p.scoff + c0) * ES;
+  uint8_t* oimg = reinterpret_cast<uint8_t*>(p.dst) + (static_cast<size_t>(b) * p.Ho * p.Wo * p.dld + p.dcoff + c0) * ES;
+  const bool cols_in = (ix0 >= 0) && (ix0 + NC <= p.W);
+  float bias[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) bias[q] = s_w[9 * p.C + ((q >> 2) * nvec + vch) * 4 + (q & 3)];
+  float acc[NSLOT][TX][VEC];
+#pragma unroll
+  for (int sl = 0; sl < NSLOT; ++sl)
+#pragma unroll
+    for (int t = 0; t < TX; ++t)
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[sl][t][q] = bias[q];
+
+  for (int j0 = 0; j0 < nsteps; j0 += PERIOD) {
+#pragma unroll
+    for (int r = 0; r < PERIOD; ++r) {
+      const int j = j0 + r;
+      if (j < nsteps) {
+        const int iy = oy0 * S - 1 + j;
+        float x[NC][VEC];
+        const bool rowok = (iy >= 0) && (iy < p.H);
+        if (rowok) {
+          const uint32_t rowoff = static_cast<uint32_t>(iy * p.W + ix0) * static_cast<uint32_t>(p.sld);
+          uint4 raw[NC];
+#pragma unroll
+          for (int jc = 0; jc < NC; ++jc) {
+            if (cols_in || ((ix0 + jc >= 0) && (ix0 + jc < p.W)))
+              raw[jc] = __ldg(reinterpret_cast<const uint4*>(img + static_cast<size_t>(rowoff + static_cast<uint32_t>(jc * p.sld)) * ES));
+            else
+              raw[jc] = make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int jc = 0; jc < NC; ++jc) dw_unpack<VEC, F16>(raw[jc], x[jc]);
+          // contributions of this input row: (kernel row ky, slot of the output row it goes to), compile-time per r
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            // S = 1: output row q = j - ky;  S = 2: j = 2q + ky  ->  q = (j - ky) / 2 when j - ky is even
+            const bool has = (S == 1) ? true : (((r - ky) & 1) == 0);
+            if (has) {
+              const int sl = (S == 1) ? ((r - ky + 3) % 3) : ((((r - ky + 4) >> 1)) & 1);   // slot of q (q mod NSLOT; j0 is a multiple of the period)
+              float wk[3][VEC];
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                for (int q4 = 0; q4 < VEC; q4 += 4) {
+                  const float4 t4 = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * p.C + ((q4 >> 2) * nvec + vch) * 4);
+                  wk[kx][q4] = t4.x; wk[kx][q4 + 1] = t4.y; wk[kx][q4 + 2] = t4.z; wk[kx][q4 + 3] = t4.w;
+                }
+#pragma unroll
+              for (int jc = 0; jc < NC; ++jc)
+#pragma unroll
+                for (int t = 0; t < TX; ++t) {
+                  const int kx = jc - t * S;
+                  if (kx >= 0 && kx < 3) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[sl][t][q] = fmaf(x[jc][q], wk[kx][q], acc[sl][t][q]);
+                  }
+                }
+            }
+          }
+        }
+        // the output row that received its LAST contribution (ky = 2) from this input row: S = 1: q = j - 2; S = 2: even j,
+        // q = (j - 2) / 2.  Store it if it is a real row of the band, then reset the slot.
+        const bool done = (S == 1) ? true : ((r & 1) == 0);
+        if (done) {
+          const int sl = (S == 1) ? ((r + 1) % 3) : (((r + 2) >> 1) & 1);
+          const int q_out = (S == 1) ? (j - 2) : ((j - 2) >> 1);
+          if (j >= 2 && q_out < nrows) {
+            uint8_t* orow = oimg + static_cast<size_t>(static_cast<uint32_t>((oy0 + q_out) * p.Wo) * static_cast<uint32_t>(p.dld)) * ES;
+#pragma unroll
+            for (int t = 0; t < TX; ++t) {
+              const int ox = ox0 + t;
+              if (ox < p.Wo) {
+                float o[VEC];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q)
+                  o[q] = (VEC == 8 && p.act == GLSDET_ACT_SILU) ? silu_fast(acc[sl][t][q]) : dw_act(acc[sl][t][q], p.act);
+                uint8_t* op = orow + static_cast<size_t>(static_cast<uint32_t>(ox) * static_cast<uint32_t>(p.dld)) * ES;
+                if constexpr (VEC == 8) {
+                  uint4 v;
+                  v.x = pack_16x2(o[0], o[1], F16);
+                  v.y = pack_16x2(o[2], o[3], F16);
+                  v.z = pack_16x2(o[4], o[5], F16);
+                  v.w = pack_16x2(o[6], o[7], F16);
+                  *reinterpret_cast<uint4*>(op) = v;
+                } else {
+                  *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TX; ++t)
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[sl][t][q] = bias[q];
+        }
+      }
+    }
+  }
+}
+
+template <int VEC, int S, int TX, int F16>
+static void launch_dw3s(DwParams p, cudaStream_t st) {
+  const int wt = (p.Wo + TX - 1) / TX;
+  const int per_row = wt * (p.C / VEC);
+  const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
+  const int gx = (per_row + threads - 1) / threads;
+  // band height: long bands re-read fewer halo rows ((ry + 2) / ry), short ones give the device enough CTAs
+  int ry = 16;
+  const int64_t want = 4ll * device_sm_count();
+  while (ry > 2 && static_cast<int64_t>(gx) * ((p.Ho + ry - 1) / ry) * p.B < want) ry >>= 1;
+  p.ry = ry;
+  const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((p.Ho + ry - 1) / ry), static_cast<unsigned>(p.B));
+  launch_pdl(dw3s_kernel<VEC, S, TX, F16>, grid, dim3(threads), static_cast<size_t>(10 * p.C) * sizeof(float), st, p);
+}
+
 template <int VEC, int S, int TX, int F16, bool PRE = false>
 static void launch_dw3(DwParams p, cudaStream_t st) {
   const int wt = (p.Wo + TX - 1) / TX;
@@ -316,6 +472,13 @@ extern "C" int glsdet_dwconv(const void* src, int32_t src_ld, int32_t src_coff, 
   const bool fits32 = static_cast<int64_t>(height) * width * src_ld < (1ll << 31) && p.Ho <= 65535 && batch <= 65535;
   p.xt = p.ry = 1;
   if (ksize == 3 && channels <= 1024 && fits32 && !generic_only) {   // weights + bias of the 3x3 kernel: 40 bytes per channel of shared memory
+    const char* se = getenv("GLSDET_DW_STREAM");   // A/B knob: 0 = the row-tiled kernel for every shape
+    const bool stream_rows = !(se && se[0] == '0');
+    if (vec == 8 && stream_rows) {
+      if (stride == 1) { if (p.f16) launch_dw3s<8, 1, 2, 1>(p, st); else launch_dw3s<8, 1, 2, 0>(p, st); }
+      else { if (p.f16) launch_dw3s<8, 2, 2, 1>(p, st); else launch_dw3s<8, 2, 2, 0>(p, st); }
+      return count_launch("dw3s_kernel");
+    }
     if (vec == 8 && stride == 1) { if (p.f16) launch_dw3<8, 1, 4, 1>(p, st); else launch_dw3<8, 1, 4, 0>(p, st); }
     else if (vec == 8) { if (p.f16) launch_dw3<8, 2, 2, 1>(p, st); else launch_dw3<8, 2, 2, 0>(p, st); }
     else if (stride == 1) launch_dw3<4, 1, 4, 0>(p, st);

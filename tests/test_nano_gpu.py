@@ -28,22 +28,26 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm()).item()
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["k3", "generic"])
+@pytest.mark.parametrize("generic", [False, True, "tiled"], ids=["k3", "generic", "k3_tiled"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32], ids=["bf16", "f16", "f32"])
 def test_depthwise_kernel_matches_torch(dtype, generic, native_lib, cuda_device, monkeypatch):
     """glsdet_dwconv vs F.conv2d(groups = C) on the same rounded inputs: stride 1 / 2, k = 3 / 5, odd sizes (zero padding
     at every border, ragged x strips), one-pixel images, channel windows on both sides, every activation; the 3x3
-    specialisation (four / two outputs per thread) and the generic kernel (GLSDET_DW_GENERIC=1)."""
+    specialisations (row-streaming, and row-tiled with GLSDET_DW_STREAM=0) and the generic kernel (GLSDET_DW_GENERIC=1)."""
     from glsdet_b200 import _native as N
     from glsdet_b200.ops import DepthwiseOp, View
 
-    if generic:
+    if generic == "tiled":
+        monkeypatch.setenv("GLSDET_DW_STREAM", "0")   # the row-tiled 3x3 kernel instead of the row-streaming one
+    elif generic:
         monkeypatch.setenv("GLSDET_DW_GENERIC", "1")
     dev = cuda_device
     g = torch.Generator().manual_seed(5)
     cases = [(2, 16, 24, 40, 3, 1, "silu"), (1, 32, 33, 17, 3, 2, "silu"), (3, 64, 7, 9, 5, 1, "relu"),
              (1, 8, 1, 1, 3, 1, "lrelu"), (2, 128, 16, 16, 3, 2, "none"), (1, 256, 5, 64, 3, 1, "silu"),
-             (2, 24, 9, 7, 3, 1, "silu"), (1, 16, 6, 11, 3, 2, "relu"), (1, 8, 3, 2, 3, 2, "silu"), (1, 40, 2, 1, 3, 1, "none")]
+             (2, 24, 9, 7, 3, 1, "silu"), (1, 16, 6, 11, 3, 2, "relu"), (1, 8, 3, 2, 3, 2, "silu"), (1, 40, 2, 1, 3, 1, "none"),
+             # tall maps: row bands of 16 / 8 output rows with a ragged last band (the row-streaming kernel's slot rotation)
+             (4, 64, 600, 256, 3, 1, "silu"), (4, 64, 1201, 255, 3, 2, "silu")]
     for b, c, h, w, k, s, act in cases:
         x = torch.randn(b, c, h, w, generator=g).to(dev).to(dtype)
         wt = (torch.randn(c, 1, k, k, generator=g) / k).to(dev)
