@@ -9,6 +9,8 @@ import os
 from pathlib import Path
 
 _LIB_PATH = Path(__file__).resolve().parent / "lib" / "libglsdet_b200.so"
+if os.environ.get("GLSDET_LIB"):   # A/B measurements of two builds on one box (tools/): another in-tree build of the same ABI
+    _LIB_PATH = Path(os.environ["GLSDET_LIB"]).resolve()
 
 ACT_NONE, ACT_SILU, ACT_RELU, ACT_LRELU, ACT_SIGMOID, ACT_YOLOX_BOX, ACT_MMDET_BOX = range(7)
 OUT_NHWC_BF16, OUT_NHWC_F32, OUT_NCHW_F32 = range(3)
