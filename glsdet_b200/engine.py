@@ -31,6 +31,7 @@ conv) -> pred_raw_ops | pred_dec_ops (second tower conv + fused prediction conv)
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -199,7 +200,7 @@ class FFAPathPlan:
         return self._conv(ops, w, b, srcs, out, w.shape[-1], stride, act, **kw)
 
     def _csp(self, ops, p: str, stride: int, src: Optional[View], out, *, up_src: Optional[View] = None,
-             x_name: str, **out_kw):
+             x_name: str, scratch=None, **out_kw):
         """CSPLayer (models/ffa/darknet.py:91-112), shortcut=False.  With `up_src` the block input is
         cat([upsample(up_src), src], 1) (yolox_ffa.py:207-211,224-228)."""
         sd = self.sd
@@ -208,7 +209,7 @@ class FFAPathPlan:
         w12, b12 = torch.cat([w1, w2], 0), torch.cat([b1, b2], 0)
         hid = w1.shape[0]
         srcs = list(src) if isinstance(src, (list, tuple)) else [src]
-        X = self._buf(x_name, stride, 2 * hid)
+        X = scratch[0] if scratch is not None else self._buf(x_name, stride, 2 * hid)
         if up_src is not None:
             ca = up_src.c
             T = self._buf(x_name + "_T", stride * 2, 2 * hid, torch.float32)
@@ -216,7 +217,7 @@ class FFAPathPlan:
             self._conv(ops, w12[:, ca:].contiguous(), b12, srcs, View(X), 1, pre_res=View(T), pre_shift=1)
         else:
             self._conv(ops, w12, b12, srcs, View(X), 1)
-        bb = self._buf(x_name + "_b", stride, hid)
+        bb = scratch[1] if scratch is not None else self._buf(x_name + "_b", stride, hid)
         j = 0
         while f"{p}.m.{j}.conv1.conv.weight" in sd:
             self._base_conv(ops, f"{p}.m.{j}.conv1", [View(X, 0, hid)], View(bb))
@@ -330,7 +331,22 @@ class FFAPathPlan:
         self._base_conv(hd, f + ".create_text_extractor.0", [View(catf)], View(tx), act=relu)
         self._base_conv(hd, f + ".conv3", [View(tx)], View(zz), act=relu, post_res=View(catf, c0, hc), post_shift=0)
         # ---- head inputs: yolox_ffa.py:66-73
-        self._csp(hd, "head.csp", 4, View(d2), View(p[0]), x_name="hcsp", post_res=View(zz), post_shift=1)
+        split = int(os.environ.get("GLSDET_HCSP_SPLIT", "1"))
+        self.hcsp_split = split if (split > 1 and self.B % split == 0 and not self.fp32) else 1
+        if self.hcsp_split > 1:
+            # the six launches of the block at stride 4 run per group of B / split images on ONE set of scratch buffers
+            # sized for a group, so that the intermediates (64 + 32 MB for four 1024^2 images) stay in the 126 MB L2
+            # instead of round-tripping HBM between the launches
+            nb = self.B // split
+            hid = self.sd["head.csp.conv1.conv.weight"].shape[0]
+            X = self._buf("hcsp", 4, 2 * hid)[:nb]
+            bb = self._buf("hcsp_b", 4, hid)[:nb]
+            for g in range(split):
+                sl = slice(g * nb, (g + 1) * nb)
+                self._csp(hd, "head.csp", 4, View(d2[sl]), View(p[0][sl]), x_name="hcsp", scratch=(X, bb),
+                          post_res=View(zz[sl]), post_shift=1)
+        else:
+            self._csp(hd, "head.csp", 4, View(d2), View(p[0]), x_name="hcsp", post_res=View(zz), post_shift=1)
         self._base_conv(hd, "head.stems.0", [P3o], View(p[1]))
         self._base_conv(hd, "head.stems.1", [View(p4out)], View(p[2]))
         self._base_conv(hd, "head.stems.2", [View(p5out)], View(p[3]))

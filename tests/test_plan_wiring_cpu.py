@@ -199,6 +199,18 @@ def _rel(a, b):
 @pytest.mark.parametrize("variant,phi,precision", [("ffa", "nano", "fp32"), ("ffa", "nano", "bf16"), ("stock", "nano", "fp32"),
                                                    ("ffa", "s", "fp32"), ("stock", "tiny", "bf16")])
 def test_plan_graph_matches_oracle(variant, phi, precision, op_models):
+    _plan_graph_case(variant, phi, precision, op_models)
+
+
+@pytest.mark.parametrize("phi", ["s", "nano"])
+def test_head_csp_group_split_wiring(phi, op_models, monkeypatch):
+    """GLSDET_HCSP_SPLIT: the stride-4 CSP block of the FFA head built once per group of images on shared scratch buffers
+    (batch slices of the input, the output and the residual) gives the same logits."""
+    monkeypatch.setenv("GLSDET_HCSP_SPLIT", "2")
+    _plan_graph_case("ffa", phi, "bf16", op_models, expect_split=2)
+
+
+def _plan_graph_case(variant, phi, precision, op_models, expect_split=1):
     """image -> BackbonePlan -> FFAPathPlan (neck, head, raw logits) with the operators modelled in torch, against
     oracle.ref_path on the same seeded weights: 1e-4 in the fp32 mode, 2e-2 (BASELINE.json's 16-bit bound) with the
     16-bit storage policy applied to the buffers."""
@@ -220,6 +232,8 @@ def test_plan_graph_matches_oracle(variant, phi, precision, op_models):
                                outs=dict(zip(names, plan.inputs)))
     n_dw = sum(isinstance(op, ModelDepthwiseOp) for op in bb.ops + plan.neck_ops + plan.stem_ops + plan.tower_ops)
     assert (n_dw > 0) == (phi == "nano")
+    if expect_split > 1:   # the block's scratch buffers hold one group of images
+        assert plan.hcsp_split == expect_split
     bb.run(x)
     tol = 1e-4 if precision == "fp32" else 2e-2
     for name, t, r in zip(names, plan.inputs, feats[-len(names):]):
