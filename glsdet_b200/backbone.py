@@ -21,6 +21,7 @@ import torch
 
 from . import _native as N
 from .ops import (ConvOp, ConvOpF32, DepthwiseOp, FocusOp, FoldedView, SppPoolOp, View, fold_bn, fold_kx_pair_weight, fold_kx_weight,
+                  pair_bias, pair_conv3_weight, pair_pointwise_weight,
                   nhwc_to_nchw, pair_stride2_weight)
 
 BN_EPS = 1e-3
@@ -60,6 +61,7 @@ class BackbonePlan:
         if not backbone_supported(self.base):
             raise NotImplementedError(f"CSPDarknet base width {self.base} is not a multiple of 8")
         self.ops: List = []
+        self.pair_csp_blocks: List[str] = []   # CSPLayers built in pixel-pair form (_csp_pairs)
         self.flops = 0.0
         self._bufs: Dict[str, torch.Tensor] = {}
         self.outs: Dict[str, torch.Tensor] = dict(outs or {})
@@ -110,6 +112,8 @@ class BackbonePlan:
         w1, b1 = self._folded(p + ".conv1")
         w2, b2 = self._folded(p + ".conv2")
         hid = w1.shape[0]
+        if self._pair_csp_ok(p, hid, src, out, shortcut):
+            return self._csp_pairs(p, stride, src, out, (w1, b1, w2, b2))
         X = self._buf(p + ".X", stride, 2 * hid)
         self._conv(torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), [src], View(X))
         bb = self._buf(p + ".b", stride, hid)
@@ -123,6 +127,49 @@ class BackbonePlan:
                 self._base_conv(f"{p}.m.{j}.conv2", [View(bb)], x1)
             j += 1
         self._base_conv(p + ".conv3", [View(X)], out)
+
+    def _pair_csp_ok(self, p: str, hid: int, src: View, out: View, shortcut: bool) -> bool:
+        """The pixel-pair form of a whole CSPLayer: 32-channel halves only (dark2 of phi = 's'), whole buffers on both sides."""
+        if self.fp32 or not shortcut or hid != 32 or os.environ.get("GLSDET_NO_PAIR_CSP"):
+            return False
+        if self._is_dw(p + ".m.0.conv2") or src.t.shape[2] % 2 or src.coff or out.coff:
+            return False
+        return src.c == src.t.shape[3] == 2 * hid and out.c == out.t.shape[3] == 2 * hid
+
+    def _csp_pairs(self, p: str, stride: int, src: View, out: View, w12):
+        """CSPLayer with 32-channel halves in PIXEL-PAIR form: every tensor is viewed as [B, H, W/2, 2C] (pair X = pixels 2X,
+        2X+1) and every conv becomes a conv over pairs with block-structured weights (ops.pair_*): the 32-channel layers (one
+        half-empty 64-channel K chunk per tap, N = 32 direct-store epilogue: 58 + 129 us at 16 x 256^2) turn into 64 -> 64
+        layers on half as many GEMM rows with full K chunks and the TMA-store epilogue.  The concat buffer holds
+        (x1(p0) | x1(p1) | x2(p0) | x2(p1)) per pair so that the bottleneck's x1 stays one contiguous window; conv3's weight
+        columns are permuted to match and its pair output is the natural [B, H, W, 2 * hid] layout again."""
+        w1, b1, w2, b2 = w12
+        hid = w1.shape[0]
+        bsz, h, w_, _ = src.t.shape
+        self.pair_csp_blocks.append(p)
+        flops0 = self.flops
+
+        def pairs(t):
+            return t.view(t.shape[0], t.shape[1], t.shape[2] // 2, 2 * t.shape[3])
+
+        Xp = pairs(self._buf(p + ".X", stride, 2 * hid))
+        bbp = pairs(self._buf(p + ".b", stride, hid))
+        w12n = torch.cat([w1, w2], 0)
+        self._conv(pair_pointwise_weight(w12n, 1, 2), pair_bias(torch.cat([b1, b2], 0), 2), [View(pairs(src.t))], View(Xp))
+        ref = 2.0 * bsz * h * w_ * (2 * hid) * (2 * hid)
+        x1 = View(Xp, 0, 2 * hid)
+        j = 0
+        while f"{p}.m.{j}.conv1.conv.weight" in self.sd:
+            wa, ba = self._folded(f"{p}.m.{j}.conv1")
+            wb, bb_ = self._folded(f"{p}.m.{j}.conv2")
+            self._conv(pair_pointwise_weight(wa), pair_bias(ba), [x1], View(bbp))
+            self._conv(pair_conv3_weight(wb), pair_bias(bb_), [View(bbp)], x1, post_res=x1, post_shift=0)
+            ref += 2.0 * bsz * h * w_ * hid * hid * 10
+            j += 1
+        w3, b3 = self._folded(p + ".conv3")
+        self._conv(pair_pointwise_weight(w3, 2, 1), pair_bias(b3), [View(Xp)], View(pairs(out.t)))
+        ref += 2.0 * bsz * h * w_ * (2 * hid) * w3.shape[0]
+        self.flops = flops0 + ref   # the reference's FLOPs: the structural zeros of the pair weights are not work
 
     def _out(self, name: str, stride: int, channels: int) -> torch.Tensor:
         t = self.outs.get(name)

@@ -156,6 +156,47 @@ def pair_stride2_weight(weight: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pair_pointwise_weight(weight: torch.Tensor, in_groups: int = 1, out_groups: int = 1) -> torch.Tensor:
+    """[N, C, 1, 1] of a 1x1 conv -> [2N, 2C, 1, 1] for the pixel-pair form of a stride-1 layer: the tensors are viewed as
+    [B, H, W/2, 2C] (pair X = pixels 2X, 2X+1) and both pixels of a pair go through the same weights.  The channels of a
+    pair are ordered (group, pixel, channel within the group): with one group that is (pixel 0 | pixel 1), with two groups
+    of C/2 channels (x1(p0) | x1(p1) | x2(p0) | x2(p1)) - the layout that keeps each half of a CSPLayer's concat buffer
+    one contiguous window of the pair view."""
+    n, c = weight.shape[:2]
+    assert weight.shape[2:] == (1, 1) and c % in_groups == 0 and n % out_groups == 0
+    w = weight[:, :, 0, 0]
+    gi, go = c // in_groups, n // out_groups
+    out = torch.zeros((2 * n, 2 * c), dtype=weight.dtype, device=weight.device)
+    for a in range(out_groups):
+        for b in range(in_groups):
+            blk = w[a * go:(a + 1) * go, b * gi:(b + 1) * gi]
+            for px in range(2):
+                out[(2 * a + px) * go:(2 * a + px + 1) * go, (2 * b + px) * gi:(2 * b + px + 1) * gi] = blk
+    return out[:, :, None, None].contiguous()
+
+
+def pair_bias(bias: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """Bias of a pair-form layer in the (group, pixel, channel) order of pair_pointwise_weight."""
+    g = bias.shape[0] // groups
+    return torch.cat([bias[a * g:(a + 1) * g] for a in range(groups) for _ in range(2)])
+
+
+def pair_conv3_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[N, C, 3, 3] of a stride-1 3x3 conv -> [2N, 2C, 3, 3] for the pixel-pair form: output pixel 2X + po reads input pixels
+    2X + po - 1 .. 2X + po + 1; input pixel 2(X + kx' - 1) + pi is tap kx = 2(kx' - 1) + pi - po + 1 of it (when 0 <= kx <= 2).
+    The zero padding of the pair view (pairs -1 and W/2) is the zero padding of the pixels -1 and W."""
+    n, c, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    out = torch.zeros((2 * n, 2 * c, 3, 3), dtype=weight.dtype, device=weight.device)
+    for po in range(2):
+        for pi in range(2):
+            for kxp in range(3):
+                kx = 2 * (kxp - 1) + pi - po + 1
+                if 0 <= kx <= 2:
+                    out[po * n:(po + 1) * n, pi * c:(pi + 1) * c, :, kxp] = weight[:, :, :, kx]
+    return out
+
+
 class ConvOp:
     """conv(+cat)(+bias)(+residual) -> act (+residual) -> store; see glsdet_conv_desc in include/glsdet_b200.h."""
 

@@ -210,6 +210,50 @@ def test_head_csp_group_split_wiring(phi, op_models, monkeypatch):
     _plan_graph_case("ffa", phi, "bf16", op_models, expect_split=2)
 
 
+def test_backbone_pair_form_csp_block(op_models, monkeypatch):
+    """The dark2 CSPLayer of phi = 's' (32-channel halves) is built in pixel-pair form (backbone.py::_csp_pairs: pair views,
+    block-structured weights of ops.pair_*); with the operators modelled in torch it gives the feature maps of the plain
+    form (GLSDET_NO_PAIR_CSP=1) up to the 16-bit rounding of the stored tensors, and both match the oracle."""
+    _, backbone = op_models
+    from glsdet_b200.synthetic import synthetic_images, synthetic_state_dict
+
+    b, h, w = 2, 64, 96
+    sd = synthetic_state_dict(3, "s", seed=5, flavour="kaiming", variant="ffa")
+    x = synthetic_images(b, h, w, seed=6)
+    with torch.no_grad():
+        feats = ref_path.csp_darknet(sd, x)
+    outs = []
+    for plain in (False, True):
+        if plain:
+            monkeypatch.setenv("GLSDET_NO_PAIR_CSP", "1")
+        bb = backbone.BackbonePlan(sd, b, (h, w), device="cpu", prefix="backbone.backbone.", precision="bf16")
+        assert bb.pair_csp_blocks == ([] if plain else ["dark2.1"])
+        bb.run(x)
+        outs.append([bb.outs[n].float().permute(0, 3, 1, 2) for n in backbone.FEATURES])
+        for t, r in zip(outs[-1], feats):
+            assert _rel(t, r) <= 2e-2
+    assert outs[0][0].shape == outs[1][0].shape
+    for a, c in zip(outs[0], outs[1]):
+        assert _rel(a, c) <= 1e-2
+    # the weight transforms alone, in fp64: pair-form convs == the plain convs on the pixel view
+    g = torch.Generator().manual_seed(3)
+    from glsdet_b200.ops import pair_bias, pair_conv3_weight, pair_pointwise_weight
+    xx = torch.randn(2, 8, 6, 10, generator=g, dtype=torch.float64)            # NCHW, W even
+    w3 = torch.randn(12, 8, 3, 3, generator=g, dtype=torch.float64)
+    b3 = torch.randn(12, generator=g, dtype=torch.float64)
+    ref = F.conv2d(xx, w3, b3, padding=1)
+
+    def to_pairs(t):   # NCHW -> pair view NCHW': channels (pixel, c)
+        n, c, hh, ww = t.shape
+        return t.permute(0, 2, 3, 1).reshape(n, hh, ww // 2, 2 * c).permute(0, 3, 1, 2)
+
+    got = F.conv2d(to_pairs(xx), pair_conv3_weight(w3), pair_bias(b3), padding=1)
+    assert torch.allclose(got, to_pairs(ref), atol=1e-12)
+    w1 = torch.randn(12, 8, 1, 1, generator=g, dtype=torch.float64)
+    got = F.conv2d(to_pairs(xx), pair_pointwise_weight(w1), pair_bias(b3))
+    assert torch.allclose(got, to_pairs(F.conv2d(xx, w1, b3)), atol=1e-12)
+
+
 def _plan_graph_case(variant, phi, precision, op_models, expect_split=1):
     """image -> BackbonePlan -> FFAPathPlan (neck, head, raw logits) with the operators modelled in torch, against
     oracle.ref_path on the same seeded weights: 1e-4 in the fp32 mode, 2e-2 (BASELINE.json's 16-bit bound) with the
